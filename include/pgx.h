@@ -1,0 +1,180 @@
+/*
+ * pgx.h — C ABI of the B200-native loopy belief propagation engine.
+ *
+ * This is the drop-in boundary for PGMax's inference path.  Every entry point
+ * replaces one piece of the reference's Python/JAX surface (citations are
+ * relative to the reference tree, pgmax 0.6.1):
+ *
+ *   pgx_plan_create      InfererContext.__post_init__           pgmax/infer/inferer.py:65-118
+ *                        (+ the Wiring arrays it concatenates:  pgmax/factor/factor.py:132-192,
+ *                         enum.py:54-72, logical.py:76-104, pool.py:62-83)
+ *   pgx_bp_run           BP.run / run_with_diffs / run_bp       pgmax/infer/bp.py:63-176
+ *                        (pass_var_to_fac_messages :191-219, FAC_TO_VAR_UPDATES loop :107-123,
+ *                         damping + normalize_and_clip_msgs :127-133,222-260, msgs_delta :136;
+ *                         per-type updates enum.py:398-475, logical.py:492-779, pool.py:276-474)
+ *   pgx_beliefs          InfererContext.get_beliefs             pgmax/infer/inferer.py:211-225
+ *   pgx_decode           decode_map_states + get_marginals      pgmax/infer/inferer.py:251-264,
+ *                                                               pgmax/infer/bp.py:263-288
+ *   pgx_infer_host       the benchmark's timed region           benchmark/rbm_lib.py:173-187
+ *                        (init -> run -> get_beliefs -> decode_map_states) with HOST buffers
+ *
+ * Shape of the ABI: XLA-FFI-like — plain device pointers, sizes and scalar
+ * attributes plus a stream; stateless apart from the immutable plan handle.
+ * No torch / jax types appear in any signature.  Functions return 0 on
+ * success and a negative pgx_status otherwise, never throw, never exit; the
+ * message of the last error on the calling thread is pgx_last_error().
+ *
+ * Data contract (identical to BPArrays, pgmax/infer/bp_state.py:30-55):
+ *   log_potentials [C] or [B, C], ftov_msgs [E_s] or [B, E_s],
+ *   evidence [V_s] or [B, V_s]; contiguous fp32, batch-major.  The leading
+ *   batch axis replaces jax.vmap.  Inputs are never written.
+ */
+#ifndef PGX_H_
+#define PGX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGX_VERSION 1
+
+/* Numerics policy, reference pgmax/utils/__init__.py:26-37 and logical.py:33. */
+#define PGX_MSG_NEG_INF (-1e32f)
+#define PGX_LOG_POTENTIAL_MAX_ABS (1e6f)
+#define PGX_TEMPERATURE_STABILITY_THRE (0.5f)
+
+typedef enum pgx_status {
+  PGX_OK = 0,
+  PGX_ERR_INVALID = -1,     /* bad argument / inconsistent graph description */
+  PGX_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+  PGX_ERR_UNSUPPORTED = -3, /* valid graph the kernels do not cover yet */
+  PGX_ERR_NO_DEVICE = -4    /* no CUDA device visible: there is no CPU fallback */
+} pgx_status;
+
+/* One group of EnumFactors sharing a configuration table
+ * (pgmax/fgroup/enum.py:30-95; replaces the reference's expanded
+ * factor_configs_edge_states rows, pgmax/factor/enum.py:364-394).
+ * Factor f (0 <= f < num_factors) of the block owns edges
+ * [first_edge + f*arity, +arity), whose message slots are contiguous from
+ * first_msg on, and potentials [first_potential + f*num_configs, +num_configs). */
+typedef struct pgx_enum_block {
+  int64_t num_factors;
+  int32_t arity;
+  int32_t num_configs;
+  const int32_t* configs; /* host, [num_configs * arity]: state of variable a in configuration k */
+  int64_t first_edge;
+  int64_t first_msg;
+  int64_t first_potential;
+} pgx_enum_block;
+
+/* All OR factors, all AND factors, or all Pool factors of the graph
+ * (LogicalWiring pgmax/factor/logical.py:39-104, PoolWiring pool.py:34-83).
+ * Message indices are GLOBAL (slice start already added).  parents_factor is
+ * ascending and every factor has >= 1 parent, as in every wiring the
+ * reference compiles (logical.py:472-483). */
+typedef struct pgx_logical_desc {
+  int64_t num_factors;
+  int64_t num_parents;
+  const int32_t* parents_factor; /* host, [num_parents] */
+  const int32_t* parents_msg;    /* host, [num_parents]: state 0 (OR, Pool) / state 1 (AND) */
+  const int32_t* children_msg;   /* host, [num_factors] */
+  int32_t edge_states_offset;    /* +1 OR and Pool, -1 AND */
+} pgx_logical_desc;
+
+/* Flat layout of a compiled factor graph.  An "edge" is a
+ * (factor, variable) pair; its states are contiguous in the message vector and
+ * in the evidence vector, so the incidence is given per edge. */
+typedef struct pgx_graph_desc {
+  int64_t num_vars;
+  const int32_t* var_num_states;  /* host, [num_vars]; sum = V_s */
+  int64_t num_edges;
+  const int32_t* edge_var_start;  /* host, [num_edges]: var-state index of the edge's state 0 */
+  const int32_t* edge_num_states; /* host, [num_edges]; sum = E_s */
+  int64_t num_potentials;         /* C */
+  int32_t num_enum_blocks;
+  const pgx_enum_block* enum_blocks;
+  pgx_logical_desc or_factors;
+  pgx_logical_desc and_factors;
+  pgx_logical_desc pool_factors;
+} pgx_graph_desc;
+
+typedef struct pgx_plan pgx_plan;
+
+/* Sizes a caller needs to allocate buffers. */
+typedef struct pgx_plan_info {
+  int64_t num_vars, num_var_states, num_edges, num_edge_states, num_potentials;
+  int64_t max_var_states;       /* largest num_states of any variable */
+  int64_t device_bytes;         /* index structures resident on the device */
+  int32_t device;               /* CUDA device the plan lives on */
+  int32_t num_sms;
+} pgx_plan_info;
+
+/* Builds the device-resident plan (index structures incl. the variable->edges
+ * CSR the reference never builds) on the current CUDA device.  The
+ * description is copied; the caller may free it on return. */
+int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan);
+void pgx_plan_destroy(pgx_plan* plan);
+int pgx_plan_get_info(const pgx_plan* plan, pgx_plan_info* out_info);
+
+/* num_iters iterations of damped loopy BP, enqueued on `stream` (a
+ * cudaStream_t; NULL = legacy default stream).  All pointers are DEVICE
+ * pointers.  batch >= 1.  lp_batched / ev_batched / msgs_batched say whether
+ * the corresponding input carries the leading batch axis; ftov_out is
+ * [batch, E_s].  ftov_in may be NULL (zero messages, as bp.init gives).
+ * deltas may be NULL, else [batch, num_iters] receives max|m' - m| per
+ * iteration (run_with_diffs).  temperature == 0 selects max-product.
+ * ftov_out may alias ftov_in.  No host synchronisation is performed unless the
+ * plan's workspace has to grow (first call for a given batch size). */
+int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch,
+               const float* log_potentials, int lp_batched,
+               const float* evidence, int ev_batched,
+               const float* ftov_in, int msgs_batched,
+               float* ftov_out, float* deltas,
+               int32_t num_iters, float damping, float temperature);
+
+/* beliefs_out[batch, V_s] = evidence + sum of incoming messages. */
+int pgx_beliefs(pgx_plan* plan, void* stream, int64_t batch,
+                const float* evidence, int ev_batched,
+                const float* ftov_msgs, int msgs_batched,
+                float* beliefs_out);
+
+/* Fused beliefs + MAP decode (+ marginals).  map_out[batch, num_vars] int32 =
+ * first arg-max state of every variable; marginals_out (may be NULL)
+ * [batch, V_s] = softmax of the beliefs per variable; tie_count_out (may be
+ * NULL) [batch] int32 = number of variables whose two largest beliefs are
+ * exactly equal (the north-star's tie rule). */
+int pgx_decode(pgx_plan* plan, void* stream, int64_t batch,
+               const float* evidence, int ev_batched,
+               const float* ftov_msgs, int msgs_batched,
+               int32_t* map_out, float* marginals_out, int32_t* tie_count_out);
+
+/* End-to-end call with HOST buffers: H2D copies, pgx_bp_run, pgx_decode, D2H
+ * copies, then a stream synchronise.  ftov_in_host may be NULL (zeros);
+ * ftov_out_host, marginals_out_host, tie_count_out_host, deltas_out_host may be
+ * NULL (not copied back).  Host buffers should be page-locked for the copies
+ * to overlap; pageable memory works but is slower. */
+int pgx_infer_host(pgx_plan* plan, void* stream, int64_t batch,
+                   const float* log_potentials_host, int lp_batched,
+                   const float* evidence_host, int ev_batched,
+                   const float* ftov_in_host, int msgs_batched,
+                   int32_t num_iters, float damping, float temperature,
+                   int32_t* map_out_host, float* marginals_out_host,
+                   int32_t* tie_count_out_host, float* ftov_out_host,
+                   float* deltas_out_host);
+
+/* Number of kernels this library launched on behalf of `plan` since creation
+ * (bench.py reports it as gpu_launches). */
+int64_t pgx_plan_launch_count(const pgx_plan* plan);
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char* pgx_last_error(void);
+
+/* Library / build information: "pgx <version> sm_100a ..." */
+const char* pgx_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGX_H_ */

@@ -1,0 +1,301 @@
+"""ctypes binding of the C ABI in include/pgx.h (csrc/libpgx.so).
+
+This module is the only place the Python host mirror touches native code.
+It never computes messages itself and has no fallback: if the shared library
+is missing, or no CUDA device is visible, calls raise ``PgxError``.
+"""
+
+import ctypes
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpgx.so")
+BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
+
+PGX_OK = 0
+PGX_ERR_INVALID = -1
+PGX_ERR_CUDA = -2
+PGX_ERR_UNSUPPORTED = -3
+PGX_ERR_NO_DEVICE = -4
+
+# Every symbol include/pgx.h declares; tests/test_abi.py checks the .so exports all of them.
+EXPORTED_SYMBOLS = (
+    "pgx_plan_create",
+    "pgx_plan_destroy",
+    "pgx_plan_get_info",
+    "pgx_bp_run",
+    "pgx_beliefs",
+    "pgx_decode",
+    "pgx_infer_host",
+    "pgx_plan_launch_count",
+    "pgx_last_error",
+    "pgx_build_info",
+)
+
+
+class PgxError(RuntimeError):
+  """A pgx_* call failed; ``code`` is the pgx_status."""
+
+  def __init__(self, code: int, message: str):
+    super().__init__(f"pgx error {code}: {message}")
+    self.code = code
+
+
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+class EnumBlockC(ctypes.Structure):
+  _fields_ = [
+      ("num_factors", ctypes.c_int64),
+      ("arity", ctypes.c_int32),
+      ("num_configs", ctypes.c_int32),
+      ("configs", _i32p),
+      ("first_edge", ctypes.c_int64),
+      ("first_msg", ctypes.c_int64),
+      ("first_potential", ctypes.c_int64),
+  ]
+
+
+class LogicalDescC(ctypes.Structure):
+  _fields_ = [
+      ("num_factors", ctypes.c_int64),
+      ("num_parents", ctypes.c_int64),
+      ("parents_factor", _i32p),
+      ("parents_msg", _i32p),
+      ("children_msg", _i32p),
+      ("edge_states_offset", ctypes.c_int32),
+  ]
+
+
+class GraphDescC(ctypes.Structure):
+  _fields_ = [
+      ("num_vars", ctypes.c_int64),
+      ("var_num_states", _i32p),
+      ("num_edges", ctypes.c_int64),
+      ("edge_var_start", _i32p),
+      ("edge_num_states", _i32p),
+      ("num_potentials", ctypes.c_int64),
+      ("num_enum_blocks", ctypes.c_int32),
+      ("enum_blocks", ctypes.POINTER(EnumBlockC)),
+      ("or_factors", LogicalDescC),
+      ("and_factors", LogicalDescC),
+      ("pool_factors", LogicalDescC),
+  ]
+
+
+class PlanInfoC(ctypes.Structure):
+  _fields_ = [
+      ("num_vars", ctypes.c_int64),
+      ("num_var_states", ctypes.c_int64),
+      ("num_edges", ctypes.c_int64),
+      ("num_edge_states", ctypes.c_int64),
+      ("num_potentials", ctypes.c_int64),
+      ("max_var_states", ctypes.c_int64),
+      ("device_bytes", ctypes.c_int64),
+      ("device", ctypes.c_int32),
+      ("num_sms", ctypes.c_int32),
+  ]
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+  """Compiles csrc/libpgx.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+  out = subprocess.run(
+      ["bash", BUILD_SCRIPT], check=True, capture_output=not verbose, text=True
+  )
+  if verbose and out.stdout:
+    print(out.stdout)
+  return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+  """Loads libpgx.so and declares the signatures of include/pgx.h."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise PgxError(
+        PGX_ERR_NO_DEVICE,
+        f"{LIB_PATH} is missing: build it with pgmax_b200/csrc/build.sh "
+        "(there is no CPU fallback for the BP kernels)",
+    )
+  lib = ctypes.CDLL(LIB_PATH)
+  vp, i64, i32, f32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float
+  lib.pgx_plan_create.argtypes = [ctypes.POINTER(GraphDescC), ctypes.POINTER(vp)]
+  lib.pgx_plan_create.restype = ctypes.c_int
+  lib.pgx_plan_destroy.argtypes = [vp]
+  lib.pgx_plan_destroy.restype = None
+  lib.pgx_plan_get_info.argtypes = [vp, ctypes.POINTER(PlanInfoC)]
+  lib.pgx_plan_get_info.restype = ctypes.c_int
+  lib.pgx_bp_run.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp,
+                             ctypes.c_int, vp, vp, i32, f32, f32]
+  lib.pgx_bp_run.restype = ctypes.c_int
+  lib.pgx_beliefs.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp]
+  lib.pgx_beliefs.restype = ctypes.c_int
+  lib.pgx_decode.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp]
+  lib.pgx_decode.restype = ctypes.c_int
+  lib.pgx_infer_host.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp,
+                                 ctypes.c_int, i32, f32, f32, vp, vp, vp, vp, vp]
+  lib.pgx_infer_host.restype = ctypes.c_int
+  lib.pgx_plan_launch_count.argtypes = [vp]
+  lib.pgx_plan_launch_count.restype = ctypes.c_int64
+  lib.pgx_last_error.argtypes = []
+  lib.pgx_last_error.restype = ctypes.c_char_p
+  lib.pgx_build_info.argtypes = []
+  lib.pgx_build_info.restype = ctypes.c_char_p
+  _lib = lib
+  return lib
+
+
+def check(code: int) -> None:
+  if code != PGX_OK:
+    raise PgxError(code, load().pgx_last_error().decode())
+
+
+def _i32(arr) -> np.ndarray:
+  arr = np.asarray(arr)
+  if arr.size and (arr.max() >= 2**31 or arr.min() < -(2**31)):
+    raise ValueError("index does not fit int32")
+  return np.ascontiguousarray(arr, dtype=np.int32)
+
+
+def _ptr(arr: np.ndarray):
+  return arr.ctypes.data_as(_i32p)
+
+
+def _logical_desc(keep: list, wiring, parents, children, offset: int, msg_start: int) -> LogicalDescC:
+  """LogicalWiring / PoolWiring arrays (local indices) -> pgx_logical_desc (global)."""
+  d = LogicalDescC()
+  d.num_factors = int(children.shape[0])
+  d.num_parents = int(parents.shape[0])
+  d.edge_states_offset = int(offset)
+  if d.num_factors:
+    pf, pm, cm = _i32(parents[:, 0]), _i32(parents[:, 1] + msg_start), _i32(children + msg_start)
+    keep.extend([pf, pm, cm])
+    d.parents_factor, d.parents_msg, d.children_msg = _ptr(pf), _ptr(pm), _ptr(cm)
+  return d
+
+
+class Plan:
+  """Owns a pgx_plan built from a FactorGraphState (device index structures)."""
+
+  def __init__(self, fg_state):
+    # pylint: disable=g-import-not-at-top
+    from pgmax_b200 import factor
+
+    lib = load()
+    keep = []  # numpy arrays that must outlive pgx_plan_create
+    desc = GraphDescC()
+    var_states = _i32(
+        np.concatenate(
+            [vg.num_states.reshape(-1) for vg in fg_state.variable_groups]
+            + [np.empty((0,), dtype=np.int64)]
+        )
+    )
+    keep.append(var_states)
+    desc.num_vars = int(var_states.shape[0])
+    desc.var_num_states = _ptr(var_states)
+
+    wirings = [fg_state.wiring[ft] for ft in factor.FACTOR_TYPES]
+    edge_var_start = _i32(np.concatenate([w.edge_var_start for w in wirings]))
+    edge_num_states = _i32(np.concatenate([w.edge_num_states for w in wirings]))
+    keep.extend([edge_var_start, edge_num_states])
+    desc.num_edges = int(edge_var_start.shape[0])
+    desc.edge_var_start = _ptr(edge_var_start)
+    desc.edge_num_states = _ptr(edge_num_states)
+    desc.num_potentials = int(fg_state.log_potentials.shape[0])
+    edge_msg_start = np.cumsum(edge_num_states, dtype=np.int64) - edge_num_states
+
+    # Enum blocks: local (edge, config) offsets -> global.  The Enum slice comes
+    # first in every vector, so its local edge / message offsets are global.
+    enum_w = fg_state.wiring[factor.EnumFactor]
+    pot_start = fg_state.factor_type_to_potentials_range[factor.EnumFactor][0]
+    blocks = (EnumBlockC * max(len(enum_w.blocks), 1))()
+    for i, b in enumerate(enum_w.blocks):
+      cfg = _i32(b.factor_configs)
+      keep.append(cfg)
+      blocks[i].num_factors = b.num_factors
+      blocks[i].arity = b.arity
+      blocks[i].num_configs = b.num_configs
+      blocks[i].configs = _ptr(cfg)
+      blocks[i].first_edge = b.first_edge
+      blocks[i].first_msg = int(edge_msg_start[b.first_edge])
+      blocks[i].first_potential = pot_start + b.first_config
+    keep.append(blocks)
+    desc.num_enum_blocks = len(enum_w.blocks)
+    desc.enum_blocks = blocks
+
+    ranges = fg_state.factor_type_to_msgs_range
+    w = fg_state.wiring[factor.ORFactor]
+    desc.or_factors = _logical_desc(
+        keep, w, w.parents_edge_states, w.children_edge_states, 1, ranges[factor.ORFactor][0]
+    )
+    w = fg_state.wiring[factor.ANDFactor]
+    desc.and_factors = _logical_desc(
+        keep, w, w.parents_edge_states, w.children_edge_states, -1, ranges[factor.ANDFactor][0]
+    )
+    w = fg_state.wiring[factor.PoolFactor]
+    desc.pool_factors = _logical_desc(
+        keep, w, w.pool_choices_edge_states, w.pool_indicators_edge_states, 1,
+        ranges[factor.PoolFactor][0],
+    )
+
+    handle = ctypes.c_void_p()
+    check(lib.pgx_plan_create(ctypes.byref(desc), ctypes.byref(handle)))
+    self._lib = lib
+    self.handle = handle
+    info = PlanInfoC()
+    check(lib.pgx_plan_get_info(handle, ctypes.byref(info)))
+    self.info = info
+    self.num_vars = int(info.num_vars)
+    self.num_var_states = int(info.num_var_states)
+    self.num_edge_states = int(info.num_edge_states)
+    self.num_potentials = int(info.num_potentials)
+    self.device = int(info.device)
+
+  def __del__(self):
+    handle = getattr(self, "handle", None)
+    if handle:
+      self._lib.pgx_plan_destroy(handle)
+      self.handle = None
+
+  @property
+  def launch_count(self) -> int:
+    return int(self._lib.pgx_plan_launch_count(self.handle))
+
+  # The methods below take raw device pointers (ints) so that any owner of device
+  # memory (torch tensors here) can call them.
+  def bp_run(self, stream: int, batch: int, lp: int, lp_batched: bool, ev: int, ev_batched: bool,
+             msgs_in: Optional[int], msgs_batched: bool, msgs_out: int, deltas: Optional[int],
+             num_iters: int, damping: float, temperature: float) -> None:
+    check(self._lib.pgx_bp_run(self.handle, stream, batch, lp, int(lp_batched), ev, int(ev_batched),
+                               msgs_in, int(msgs_batched), msgs_out, deltas, num_iters,
+                               damping, temperature))
+
+  def beliefs(self, stream: int, batch: int, ev: int, ev_batched: bool, msgs: int,
+              msgs_batched: bool, out: int) -> None:
+    check(self._lib.pgx_beliefs(self.handle, stream, batch, ev, int(ev_batched), msgs,
+                                int(msgs_batched), out))
+
+  def decode(self, stream: int, batch: int, ev: int, ev_batched: bool, msgs: int,
+             msgs_batched: bool, map_out: Optional[int], marginals: Optional[int],
+             ties: Optional[int]) -> None:
+    check(self._lib.pgx_decode(self.handle, stream, batch, ev, int(ev_batched), msgs,
+                               int(msgs_batched), map_out, marginals, ties))
+
+  def infer_host(self, stream: int, batch: int, lp: int, lp_batched: bool, ev: int,
+                 ev_batched: bool, msgs_in: Optional[int], msgs_batched: bool, num_iters: int,
+                 damping: float, temperature: float, map_out: Optional[int],
+                 marginals: Optional[int], ties: Optional[int], msgs_out: Optional[int],
+                 deltas: Optional[int]) -> None:
+    check(self._lib.pgx_infer_host(self.handle, stream, batch, lp, int(lp_batched), ev,
+                                   int(ev_batched), msgs_in, int(msgs_batched), num_iters,
+                                   damping, temperature, map_out, marginals, ties, msgs_out,
+                                   deltas))

@@ -1,0 +1,688 @@
+// pgx.cu — plan builder, workspace and launch sequencing behind include/pgx.h.
+//
+// Nothing in this file computes messages on the host: the plan builder only
+// derives index structures (the variable -> incident-edges CSR, transposed
+// configuration lists, parent offsets), uploads them once, and pgx_bp_run
+// enqueues kernels.  There is no CPU fallback: without a CUDA device every
+// entry point fails with PGX_ERR_NO_DEVICE.
+
+#include "../../include/pgx.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "pgx_kernels.cuh"
+
+#define PGX_STR2(x) #x
+#define PGX_STR(x) PGX_STR2(x)
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define PGX_CUDA(expr)                                                                    \
+  do {                                                                                    \
+    cudaError_t err__ = (expr);                                                           \
+    if (err__ != cudaSuccess)                                                             \
+      return fail(PGX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+#define PGX_CHECK(cond, ...) \
+  do {                       \
+    if (!(cond)) return fail(PGX_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// Index arrays are computed in int64 on the host and stored as int32 on the device
+// (all counts are checked to be < 2^31 at plan creation).
+std::vector<int32_t> narrow(const std::vector<int64_t>& v) { return std::vector<int32_t>(v.begin(), v.end()); }
+
+template <typename T>
+int upload(const std::vector<T>& host, T** dev, int64_t* bytes) {
+  *dev = nullptr;
+  if (host.empty()) return PGX_OK;
+  PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), host.size() * sizeof(T)));
+  PGX_CUDA(cudaMemcpy(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *bytes += int64_t(host.size() * sizeof(T));
+  return PGX_OK;
+}
+
+enum EnumVariant { kPw2 = 0, kSmall = 1, kBig = 2 };
+
+struct EnumBlockPlan {
+  pgx::EnumBlockDev dev{};
+  EnumVariant variant = kSmall;
+  int32_t *d_cfg_es = nullptr, *d_t_ptr = nullptr, *d_t_k = nullptr, *d_edge_off = nullptr;
+};
+
+struct LogicalPlan {
+  pgx::LogicalDev dev{};
+  int32_t *d_parent_ptr = nullptr, *d_parents_msg = nullptr, *d_parents_vs = nullptr, *d_children_msg = nullptr,
+          *d_children_vs = nullptr;
+};
+
+struct Workspace {
+  int64_t batch = 0;
+  int ld = 0;
+  float *mA = nullptr, *mB = nullptr, *S = nullptr, *evT = nullptr, *lpT = nullptr;
+  // staging for pgx_infer_host
+  float *h_lp = nullptr, *h_ev = nullptr, *h_msgs_in = nullptr, *h_msgs_out = nullptr,
+        *h_marg = nullptr, *h_deltas = nullptr;
+  int32_t *h_map = nullptr, *h_ties = nullptr;
+  int64_t n_lp = 0, n_ev = 0, n_msgs_in = 0, n_msgs_out = 0, n_marg = 0, n_deltas = 0, n_map = 0,
+          n_ties = 0;
+};
+
+}  // namespace
+
+struct pgx_plan {
+  int device = 0;
+  int num_sms = 0;
+  int64_t num_vars = 0, num_var_states = 0, num_edges = 0, num_edge_states = 0, num_potentials = 0;
+  int64_t max_var_states = 0;
+  int64_t device_bytes = 0;
+  int64_t launches = 0;
+  // device index structures
+  int32_t* d_edge_vs = nullptr;          // [num_edges] var-state of each edge's state 0
+  int32_t* d_edge_msg_start = nullptr;   // [num_edges + 1]
+  int32_t* d_vs_var = nullptr;           // [V_s] variable of each var-state
+  int32_t* d_var_first_state = nullptr;  // [num_vars + 1]
+  int32_t* d_var_ptr = nullptr;          // [num_vars + 1] CSR offsets
+  int32_t* d_var_edge_msg = nullptr;     // [num_edges] message start of incident edges, ascending
+  std::vector<EnumBlockPlan> enum_blocks;
+  LogicalPlan or_f, and_f, pool_f;
+  Workspace ws;
+};
+
+namespace {
+
+void free_dev(void* p) {
+  if (p) cudaFree(p);
+}
+
+void free_workspace(Workspace& ws) {
+  free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT);
+  free_dev(ws.h_lp); free_dev(ws.h_ev); free_dev(ws.h_msgs_in); free_dev(ws.h_msgs_out);
+  free_dev(ws.h_marg); free_dev(ws.h_deltas); free_dev(ws.h_map); free_dev(ws.h_ties);
+  ws = Workspace{};
+}
+
+pgx::BatchMap make_map(int64_t batch) {
+  pgx::BatchMap mp;
+  mp.batch = int(batch);
+  mp.ld = batch == 1 ? 1 : int((batch + 7) / 8 * 8);
+  int lg = 0;
+  while ((1 << lg) < batch && lg < 5) ++lg;
+  mp.bx_log = lg;
+  mp.nbt = int((batch + (1 << lg) - 1) >> lg);
+  return mp;
+}
+
+// Grid for a "one thread per (element, sample)" kernel: enough warps to cover the
+// work, capped at a few CTAs per SM (workers then loop over contiguous chunks),
+// and a whole number of nbt-warp workers.
+int grid_for(const pgx_plan* plan, const pgx::BatchMap& mp, int64_t units) {
+  const int upw = 32 >> mp.bx_log;
+  const int wpb = pgx::kThreads / 32;
+  int64_t warps = std::max<int64_t>(1, (units + upw - 1) / upw) * mp.nbt;
+  int64_t blocks = (warps + wpb - 1) / wpb;
+  blocks = std::min<int64_t>(blocks, int64_t(plan->num_sms) * 8);
+  const int64_t quantum = mp.nbt / std::gcd<int64_t>(mp.nbt, wpb);
+  blocks = (blocks + quantum - 1) / quantum * quantum;
+  return int(std::max<int64_t>(blocks, quantum));
+}
+
+int build_logical(pgx_plan* plan, const pgx_logical_desc& d, const std::vector<int64_t>& edge_msg_start,
+                  const std::vector<int32_t>& edge_vs, const std::vector<int32_t>& edge_ns,
+                  std::vector<uint8_t>& edge_covered, const char* what, LogicalPlan* out) {
+  out->dev.num_factors = d.num_factors;
+  out->dev.off = d.edge_states_offset;
+  if (d.num_factors == 0) return PGX_OK;
+  PGX_CHECK(d.edge_states_offset == 1 || d.edge_states_offset == -1,
+            "%s: edge_states_offset must be +1 or -1, got %d", what, d.edge_states_offset);
+  PGX_CHECK(d.parents_factor && d.parents_msg && d.children_msg, "%s: null wiring array", what);
+  const int rel = d.edge_states_offset > 0 ? 0 : 1;  // state the wiring points at
+  std::vector<int64_t> ptr(d.num_factors + 1, 0);
+  for (int64_t i = 0; i < d.num_parents; ++i) {
+    const int32_t f = d.parents_factor[i];
+    PGX_CHECK(f >= 0 && f < d.num_factors, "%s: parent %lld has factor index %d out of range", what,
+              (long long)i, f);
+    PGX_CHECK(i == 0 || d.parents_factor[i - 1] <= f, "%s: parents must be grouped by ascending factor",
+              what);
+    ++ptr[f + 1];
+  }
+  for (int64_t f = 0; f < d.num_factors; ++f) {
+    PGX_CHECK(ptr[f + 1] >= 1, "%s: factor %lld has no parent", what, (long long)f);
+    ptr[f + 1] += ptr[f];
+  }
+  auto resolve = [&](int32_t msg, int32_t* vs) -> int {
+    // edge containing message index `msg`
+    const int64_t lo_msg = int64_t(msg) - rel;
+    auto it = std::upper_bound(edge_msg_start.begin(), edge_msg_start.end(), lo_msg);
+    const int64_t e = (it - edge_msg_start.begin()) - 1;
+    PGX_CHECK(e >= 0 && e < plan->num_edges && edge_msg_start[e] == lo_msg && edge_ns[e] == 2,
+              "%s: message index %d is not state %d of a binary edge", what, msg, rel);
+    PGX_CHECK(!edge_covered[e], "%s: edge %lld is updated by more than one factor", what, (long long)e);
+    edge_covered[e] = 1;
+    *vs = edge_vs[e] + rel;
+    return PGX_OK;
+  };
+  std::vector<int32_t> pvs(d.num_parents), cvs(d.num_factors);
+  for (int64_t i = 0; i < d.num_parents; ++i)
+    if (int rc = resolve(d.parents_msg[i], &pvs[i])) return rc;
+  for (int64_t f = 0; f < d.num_factors; ++f)
+    if (int rc = resolve(d.children_msg[f], &cvs[f])) return rc;
+  std::vector<int32_t> pmsg(d.parents_msg, d.parents_msg + d.num_parents);
+  std::vector<int32_t> cmsg(d.children_msg, d.children_msg + d.num_factors);
+  int rc;
+  if ((rc = upload(narrow(ptr), &out->d_parent_ptr, &plan->device_bytes))) return rc;
+  if ((rc = upload(pmsg, &out->d_parents_msg, &plan->device_bytes))) return rc;
+  if ((rc = upload(pvs, &out->d_parents_vs, &plan->device_bytes))) return rc;
+  if ((rc = upload(cmsg, &out->d_children_msg, &plan->device_bytes))) return rc;
+  if ((rc = upload(cvs, &out->d_children_vs, &plan->device_bytes))) return rc;
+  out->dev.parent_ptr = out->d_parent_ptr;
+  out->dev.parents_msg = out->d_parents_msg;
+  out->dev.parents_vs = out->d_parents_vs;
+  out->dev.children_msg = out->d_children_msg;
+  out->dev.children_vs = out->d_children_vs;
+  return PGX_OK;
+}
+
+int build_enum_block(pgx_plan* plan, const pgx_enum_block& b, int idx,
+                     const std::vector<int64_t>& edge_msg_start, const std::vector<int32_t>& edge_ns,
+                     std::vector<uint8_t>& edge_covered, EnumBlockPlan* out) {
+  PGX_CHECK(b.num_factors >= 1 && b.arity >= 1 && b.num_configs >= 0 && b.configs != nullptr,
+            "enum block %d: bad sizes", idx);
+  const int A = b.arity, K = b.num_configs;
+  PGX_CHECK(b.first_edge >= 0 && b.first_edge + b.num_factors * A <= plan->num_edges,
+            "enum block %d: edge range out of bounds", idx);
+  PGX_CHECK(edge_msg_start[b.first_edge] == b.first_msg,
+            "enum block %d: first_msg %lld does not match the edge table (%lld)", idx,
+            (long long)b.first_msg, (long long)edge_msg_start[b.first_edge]);
+  PGX_CHECK(b.first_potential >= 0 && b.first_potential + b.num_factors * K <= plan->num_potentials,
+            "enum block %d: potential range out of bounds", idx);
+  std::vector<int32_t> edge_off(A + 1, 0);
+  for (int a = 0; a < A; ++a) edge_off[a + 1] = edge_off[a] + edge_ns[b.first_edge + a];
+  const int ns = edge_off[A];
+  for (int64_t f = 0; f < b.num_factors; ++f)
+    for (int a = 0; a < A; ++a) {
+      const int64_t e = b.first_edge + f * A + a;
+      if (edge_ns[e] != edge_off[a + 1] - edge_off[a])
+        return fail(PGX_ERR_UNSUPPORTED,
+                    "enum block %d: factors with different numbers of states share one block; "
+                    "split the group per state signature", idx);
+      PGX_CHECK(!edge_covered[e], "enum block %d: edge %lld is updated by more than one factor", idx,
+                (long long)e);
+      edge_covered[e] = 1;
+    }
+  std::vector<int32_t> cfg_es(size_t(K) * A), t_ptr(ns + 1, 0), t_k(size_t(K) * A);
+  for (int k = 0; k < K; ++k)
+    for (int a = 0; a < A; ++a) {
+      const int32_t st = b.configs[size_t(k) * A + a];
+      PGX_CHECK(st >= 0 && st < edge_off[a + 1] - edge_off[a],
+                "enum block %d: configuration %d assigns state %d to variable %d", idx, k, st, a);
+      cfg_es[size_t(k) * A + a] = edge_off[a] + st;
+      ++t_ptr[edge_off[a] + st + 1];
+    }
+  for (int s = 0; s < ns; ++s) t_ptr[s + 1] += t_ptr[s];
+  {
+    std::vector<int32_t> cursor(t_ptr.begin(), t_ptr.end() - 1);
+    for (int k = 0; k < K; ++k)  // ascending k within every list
+      for (int a = 0; a < A; ++a) t_k[cursor[cfg_es[size_t(k) * A + a]]++] = k;
+  }
+  const bool full_binary_pair =
+      A == 2 && K == 4 && ns == 4 && b.configs[0] == 0 && b.configs[1] == 0 && b.configs[2] == 0 &&
+      b.configs[3] == 1 && b.configs[4] == 1 && b.configs[5] == 0 && b.configs[6] == 1 &&
+      b.configs[7] == 1;
+  out->variant = full_binary_pair ? kPw2 : (ns <= pgx::kSmallMaxNS ? kSmall : kBig);
+  if (out->variant == kBig && size_t(2 * ns + 32) * sizeof(float) > 227 * 1024)
+    return fail(PGX_ERR_UNSUPPORTED, "enum block %d: %d edge-states per factor exceed shared memory",
+                idx, ns);
+  int rc;
+  if ((rc = upload(cfg_es, &out->d_cfg_es, &plan->device_bytes))) return rc;
+  if ((rc = upload(t_ptr, &out->d_t_ptr, &plan->device_bytes))) return rc;
+  if ((rc = upload(t_k, &out->d_t_k, &plan->device_bytes))) return rc;
+  if ((rc = upload(edge_off, &out->d_edge_off, &plan->device_bytes))) return rc;
+  out->dev.num_factors = b.num_factors;
+  out->dev.first_edge = b.first_edge;
+  out->dev.first_msg = b.first_msg;
+  out->dev.first_pot = b.first_potential;
+  out->dev.arity = A;
+  out->dev.num_configs = K;
+  out->dev.ns = ns;
+  out->dev.cfg_es = out->d_cfg_es;
+  out->dev.t_ptr = out->d_t_ptr;
+  out->dev.t_k = out->d_t_k;
+  out->dev.edge_off = out->d_edge_off;
+  return PGX_OK;
+}
+
+int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT) {
+  Workspace& ws = plan->ws;
+  const pgx::BatchMap mp = make_map(batch);
+  if (ws.batch != batch) {
+    free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT);
+    ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = nullptr;
+    ws.batch = batch;
+    ws.ld = mp.ld;
+    const size_t nm = size_t(std::max<int64_t>(plan->num_edge_states, 1)) * mp.ld * sizeof(float);
+    const size_t nv = size_t(std::max<int64_t>(plan->num_var_states, 1)) * mp.ld * sizeof(float);
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.mA), nm));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.mB), nm));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.S), nv));
+  }
+  if (need_evT && ws.evT == nullptr)
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.evT),
+                        size_t(std::max<int64_t>(plan->num_var_states, 1)) * mp.ld * sizeof(float)));
+  if (need_lpT && ws.lpT == nullptr)
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.lpT),
+                        size_t(std::max<int64_t>(plan->num_potentials, 1)) * mp.ld * sizeof(float)));
+  return PGX_OK;
+}
+
+int check_launch(pgx_plan* plan, const char* what) {
+  ++plan->launches;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(PGX_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(err));
+  return PGX_OK;
+}
+
+int to_batch_inner(pgx_plan* plan, cudaStream_t st, const float* src, float* dst, int64_t n, int64_t batch,
+                   int ld) {
+  if (n == 0) return PGX_OK;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((ld + 31) / 32)), block(32, 8);
+  pgx::k_to_batch_inner<<<grid, block, 0, st>>>(src, dst, n, int(batch), ld);
+  return check_launch(plan, "k_to_batch_inner");
+}
+
+int from_batch_inner(pgx_plan* plan, cudaStream_t st, const float* src, float* dst, int64_t n, int64_t batch,
+                     int ld) {
+  if (n == 0) return PGX_OK;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((batch + 31) / 32)), block(32, 8);
+  pgx::k_from_batch_inner<<<grid, block, 0, st>>>(src, dst, n, int(batch), ld);
+  return check_launch(plan, "k_from_batch_inner");
+}
+
+template <bool kSum>
+int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::View lp, const float* S,
+               const float* m_old, float* m_new, float d, float omd, float T, float* deltas,
+               int64_t dstride, int64_t doff) {
+  int rc;
+  for (EnumBlockPlan& eb : plan->enum_blocks) {
+    const int64_t F = eb.dev.num_factors;
+    if (eb.variant == kPw2) {
+      pgx::k_enum_pw2<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
+          mp, F, eb.dev.first_edge, eb.dev.first_msg, eb.dev.first_pot, plan->d_edge_vs, lp, S, m_old,
+          m_new, d, omd, T, deltas, dstride, doff);
+      if ((rc = check_launch(plan, "k_enum_pw2"))) return rc;
+    } else if (eb.variant == kSmall) {
+      pgx::k_enum_small<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
+          mp, eb.dev, plan->d_edge_vs, lp, S, m_old, m_new, d, omd, T, deltas, dstride, doff);
+      if ((rc = check_launch(plan, "k_enum_small"))) return rc;
+    } else {
+      const size_t smem = size_t(2 * eb.dev.ns + 32) * sizeof(float);
+      const int64_t units = F * mp.batch;
+      const int grid = int(std::min<int64_t>(units, int64_t(plan->num_sms) * 8));
+      pgx::k_enum_big<kSum><<<grid, pgx::kThreads, smem, st>>>(mp.batch, mp.ld, eb.dev, plan->d_edge_vs,
+                                                               lp, S, m_old, m_new, d, omd, T, deltas,
+                                                               dstride, doff);
+      if ((rc = check_launch(plan, "k_enum_big"))) return rc;
+    }
+  }
+  for (LogicalPlan* lg : {&plan->or_f, &plan->and_f}) {
+    if (lg->dev.num_factors == 0) continue;
+    pgx::k_logical<kSum><<<grid_for(plan, mp, lg->dev.num_factors), pgx::kThreads, 0, st>>>(
+        mp, lg->dev, S, m_old, m_new, d, omd, T, deltas, dstride, doff);
+    if ((rc = check_launch(plan, "k_logical"))) return rc;
+  }
+  if (plan->pool_f.dev.num_factors > 0) {
+    pgx::k_pool<kSum><<<grid_for(plan, mp, plan->pool_f.dev.num_factors), pgx::kThreads, 0, st>>>(
+        mp, plan->pool_f.dev, S, m_old, m_new, d, omd, T, deltas, dstride, doff);
+    if ((rc = check_launch(plan, "k_pool"))) return rc;
+  }
+  return PGX_OK;
+}
+
+int check_device(pgx_plan* plan) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(PGX_ERR_NO_DEVICE, "no CUDA device");
+  if (dev != plan->device) PGX_CUDA(cudaSetDevice(plan->device));
+  return PGX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pgx_last_error(void) { return g_last_error.c_str(); }
+
+const char* pgx_build_info(void) {
+  return "pgx 1 sm_100a cuda-" PGX_STR(CUDART_VERSION) " fmad=off";
+}
+
+int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
+  if (out_plan == nullptr || desc == nullptr) return fail(PGX_ERR_INVALID, "null argument");
+  *out_plan = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(PGX_ERR_NO_DEVICE,
+                "no CUDA device visible; pgx has no CPU fallback (the oracle under oracle/ is test-only)");
+  pgx_plan* plan = new pgx_plan();
+  auto bail = [&](int rc) {
+    pgx_plan_destroy(plan);
+    return rc;
+  };
+#define PGX_TRY(expr)                 \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__ != PGX_OK) return bail(rc__); \
+  } while (0)
+#define PGX_REQUIRE(cond, ...)                                   \
+  do {                                                           \
+    if (!(cond)) return bail(fail(PGX_ERR_INVALID, __VA_ARGS__)); \
+  } while (0)
+
+  if (cudaGetDevice(&plan->device) != cudaSuccess) return bail(fail(PGX_ERR_CUDA, "cudaGetDevice failed"));
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, plan->device) != cudaSuccess)
+    return bail(fail(PGX_ERR_CUDA, "cudaGetDeviceProperties failed"));
+  plan->num_sms = prop.multiProcessorCount;
+
+  PGX_REQUIRE(desc->num_vars >= 0 && desc->num_edges >= 0 && desc->num_potentials >= 0, "negative size");
+  PGX_REQUIRE(desc->num_vars < INT32_MAX && desc->num_edges < INT32_MAX, "graph too large for int32 indices");
+  PGX_REQUIRE(desc->num_vars == 0 || desc->var_num_states, "var_num_states is null");
+  PGX_REQUIRE(desc->num_edges == 0 || (desc->edge_var_start && desc->edge_num_states), "edge table is null");
+  plan->num_vars = desc->num_vars;
+  plan->num_edges = desc->num_edges;
+  plan->num_potentials = desc->num_potentials;
+
+  // variables
+  std::vector<int32_t> var_first_state(plan->num_vars + 1, 0);
+  for (int64_t v = 0; v < plan->num_vars; ++v) {
+    const int32_t ns = desc->var_num_states[v];
+    PGX_REQUIRE(ns >= 0, "variable %lld has %d states", (long long)v, ns);
+    const int64_t next = int64_t(var_first_state[v]) + ns;
+    PGX_REQUIRE(next < INT32_MAX, "more than 2^31 variable states");
+    var_first_state[v + 1] = int32_t(next);
+    plan->max_var_states = std::max<int64_t>(plan->max_var_states, ns);
+  }
+  plan->num_var_states = var_first_state[plan->num_vars];
+  std::vector<int32_t> vs_var(plan->num_var_states);
+  for (int64_t v = 0; v < plan->num_vars; ++v)
+    for (int32_t s = var_first_state[v]; s < var_first_state[v + 1]; ++s) vs_var[s] = int32_t(v);
+
+  // edges, message offsets, variable -> incident edges CSR (ascending message index)
+  std::vector<int64_t> edge_msg_start(plan->num_edges + 1, 0);
+  std::vector<int32_t> edge_vs(desc->edge_var_start, desc->edge_var_start + plan->num_edges);
+  std::vector<int32_t> edge_ns(desc->edge_num_states, desc->edge_num_states + plan->num_edges);
+  std::vector<int64_t> var_ptr(plan->num_vars + 1, 0);
+  for (int64_t e = 0; e < plan->num_edges; ++e) {
+    const int32_t vs = edge_vs[e];
+    PGX_REQUIRE(vs >= 0 && vs < plan->num_var_states, "edge %lld: var-state %d out of range", (long long)e, vs);
+    const int32_t var = vs_var[vs];
+    PGX_REQUIRE(var_first_state[var] == vs && desc->var_num_states[var] == edge_ns[e],
+                "edge %lld does not span exactly the states of variable %d", (long long)e, var);
+    edge_msg_start[e + 1] = edge_msg_start[e] + edge_ns[e];
+    ++var_ptr[var + 1];
+  }
+  plan->num_edge_states = edge_msg_start[plan->num_edges];
+  PGX_REQUIRE(plan->num_edge_states < INT32_MAX, "more than 2^31 edge states");
+  for (int64_t v = 0; v < plan->num_vars; ++v) var_ptr[v + 1] += var_ptr[v];
+  std::vector<int64_t> var_edge_msg(plan->num_edges);
+  {
+    std::vector<int64_t> cursor(var_ptr.begin(), var_ptr.end() - 1);
+    for (int64_t e = 0; e < plan->num_edges; ++e) var_edge_msg[cursor[vs_var[edge_vs[e]]]++] = edge_msg_start[e];
+  }
+  PGX_TRY(upload(edge_vs, &plan->d_edge_vs, &plan->device_bytes));
+  PGX_TRY(upload(narrow(edge_msg_start), &plan->d_edge_msg_start, &plan->device_bytes));
+  PGX_TRY(upload(vs_var, &plan->d_vs_var, &plan->device_bytes));
+  PGX_TRY(upload(var_first_state, &plan->d_var_first_state, &plan->device_bytes));
+  PGX_TRY(upload(narrow(var_ptr), &plan->d_var_ptr, &plan->device_bytes));
+  PGX_TRY(upload(narrow(var_edge_msg), &plan->d_var_edge_msg, &plan->device_bytes));
+
+  // factor types
+  std::vector<uint8_t> edge_covered(plan->num_edges, 0);
+  PGX_REQUIRE(desc->num_enum_blocks == 0 || desc->enum_blocks, "enum_blocks is null");
+  plan->enum_blocks.resize(desc->num_enum_blocks);
+  for (int i = 0; i < desc->num_enum_blocks; ++i)
+    PGX_TRY(build_enum_block(plan, desc->enum_blocks[i], i, edge_msg_start, edge_ns, edge_covered,
+                             &plan->enum_blocks[i]));
+  PGX_TRY(build_logical(plan, desc->or_factors, edge_msg_start, edge_vs, edge_ns, edge_covered, "OR factors",
+                        &plan->or_f));
+  PGX_TRY(build_logical(plan, desc->and_factors, edge_msg_start, edge_vs, edge_ns, edge_covered,
+                        "AND factors", &plan->and_f));
+  PGX_REQUIRE(desc->pool_factors.num_factors == 0 || desc->pool_factors.edge_states_offset == 1,
+              "Pool factors: edge_states_offset must be +1");
+  PGX_TRY(build_logical(plan, desc->pool_factors, edge_msg_start, edge_vs, edge_ns, edge_covered,
+                        "Pool factors", &plan->pool_f));
+  for (int64_t e = 0; e < plan->num_edges; ++e)
+    PGX_REQUIRE(edge_covered[e], "edge %lld belongs to no factor description", (long long)e);
+#undef PGX_TRY
+#undef PGX_REQUIRE
+  *out_plan = plan;
+  return PGX_OK;
+}
+
+void pgx_plan_destroy(pgx_plan* plan) {
+  if (plan == nullptr) return;
+  free_dev(plan->d_edge_vs); free_dev(plan->d_edge_msg_start); free_dev(plan->d_vs_var);
+  free_dev(plan->d_var_first_state); free_dev(plan->d_var_ptr); free_dev(plan->d_var_edge_msg);
+  for (EnumBlockPlan& eb : plan->enum_blocks) {
+    free_dev(eb.d_cfg_es); free_dev(eb.d_t_ptr); free_dev(eb.d_t_k); free_dev(eb.d_edge_off);
+  }
+  for (LogicalPlan* lg : {&plan->or_f, &plan->and_f, &plan->pool_f}) {
+    free_dev(lg->d_parent_ptr); free_dev(lg->d_parents_msg); free_dev(lg->d_parents_vs);
+    free_dev(lg->d_children_msg); free_dev(lg->d_children_vs);
+  }
+  free_workspace(plan->ws);
+  delete plan;
+}
+
+int pgx_plan_get_info(const pgx_plan* plan, pgx_plan_info* info) {
+  if (!plan || !info) return fail(PGX_ERR_INVALID, "null argument");
+  info->num_vars = plan->num_vars;
+  info->num_var_states = plan->num_var_states;
+  info->num_edges = plan->num_edges;
+  info->num_edge_states = plan->num_edge_states;
+  info->num_potentials = plan->num_potentials;
+  info->max_var_states = plan->max_var_states;
+  info->device_bytes = plan->device_bytes;
+  info->device = plan->device;
+  info->num_sms = plan->num_sms;
+  return PGX_OK;
+}
+
+int64_t pgx_plan_launch_count(const pgx_plan* plan) { return plan ? plan->launches : 0; }
+
+int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch, const float* log_potentials, int lp_batched,
+               const float* evidence, int ev_batched, const float* ftov_in, int msgs_batched,
+               float* ftov_out, float* deltas, int32_t num_iters, float damping, float temperature) {
+  if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+  PGX_CHECK(batch >= 1 && batch < (1 << 24), "batch must be in [1, 2^24), got %lld", (long long)batch);
+  PGX_CHECK(num_iters >= 1, "num_iters must be >= 1, got %d", num_iters);
+  PGX_CHECK(temperature >= 0.f, "temperature must be >= 0");
+  PGX_CHECK(ftov_out != nullptr, "ftov_out is null");
+  PGX_CHECK(plan->num_var_states == 0 || evidence != nullptr, "evidence is null");
+  PGX_CHECK(plan->num_potentials == 0 || log_potentials != nullptr, "log_potentials is null");
+  int rc;
+  if ((rc = check_device(plan))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const pgx::BatchMap mp = make_map(batch);
+  PGX_CHECK(int64_t(plan->num_edge_states) * mp.ld < (int64_t(1) << 40), "workspace too large");
+  const bool single = batch == 1;
+  const bool evT = !single && ev_batched, lpT = !single && lp_batched;
+  if ((rc = ensure_workspace(plan, batch, evT, lpT))) return rc;
+  Workspace& ws = plan->ws;
+  const int64_t Es = plan->num_edge_states, Vs = plan->num_var_states, C = plan->num_potentials;
+  if (Es == 0) return PGX_OK;
+
+  // ---- inputs -> batch-inner workspace ---------------------------------------------------
+  pgx::View ev{evidence, 1, 0}, lp{log_potentials, 1, 0};
+  if (evT) {
+    if ((rc = to_batch_inner(plan, st, evidence, ws.evT, Vs, batch, mp.ld))) return rc;
+    ev = pgx::View{ws.evT, mp.ld, 1};
+  }
+  if (lpT) {
+    if ((rc = to_batch_inner(plan, st, log_potentials, ws.lpT, C, batch, mp.ld))) return rc;
+    lp = pgx::View{ws.lpT, mp.ld, 1};
+  }
+  float* cur = ws.mA;
+  float* nxt = ws.mB;
+  if (ftov_in == nullptr) {
+    PGX_CUDA(cudaMemsetAsync(cur, 0, size_t(Es) * mp.ld * sizeof(float), st));  // NC(0) = 0
+  } else {
+    if (single) {
+      PGX_CUDA(cudaMemcpyAsync(cur, ftov_in, size_t(Es) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else if (msgs_batched) {
+      if ((rc = to_batch_inner(plan, st, ftov_in, cur, Es, batch, mp.ld))) return rc;
+    } else {
+      pgx::k_broadcast_rows<<<plan->num_sms * 8, pgx::kThreads, 0, st>>>(ftov_in, cur, Es, mp.ld);
+      if ((rc = check_launch(plan, "k_broadcast_rows"))) return rc;
+    }
+    pgx::k_normalize_edges<<<grid_for(plan, mp, plan->num_edges), pgx::kThreads, 0, st>>>(
+        mp, plan->num_edges, plan->d_edge_msg_start, cur);
+    if ((rc = check_launch(plan, "k_normalize_edges"))) return rc;
+  }
+  if (deltas) PGX_CUDA(cudaMemsetAsync(deltas, 0, size_t(batch) * num_iters * sizeof(float), st));
+
+  // ---- iterations ------------------------------------------------------------------------
+  const float omd = 1.0f - damping;
+  for (int it = 0; it < num_iters; ++it) {
+    pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(
+        mp, Vs, plan->d_vs_var, plan->d_var_first_state, plan->d_var_ptr, plan->d_var_edge_msg, ev, cur,
+        ws.S);
+    if ((rc = check_launch(plan, "k_var_sums"))) return rc;
+    // With one sample the last iteration writes straight into the caller's buffer.
+    float* dst = (single && it == num_iters - 1) ? ftov_out : nxt;
+    if (temperature == 0.f)
+      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, damping, omd, temperature, deltas, num_iters, it);
+    else
+      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, damping, omd, temperature, deltas, num_iters, it);
+    if (rc) return rc;
+    nxt = cur;
+    cur = dst;
+  }
+  if (!single) {
+    if ((rc = from_batch_inner(plan, st, cur, ftov_out, Es, batch, mp.ld))) return rc;
+  }
+  return PGX_OK;
+}
+
+static int decode_impl(pgx_plan* plan, cudaStream_t st, int64_t batch, const float* evidence, int ev_batched,
+                       const float* ftov_msgs, int msgs_batched, float* beliefs, int32_t* map_out,
+                       float* marginals, int32_t* ties) {
+  PGX_CHECK(batch >= 1, "batch must be >= 1");
+  PGX_CHECK(plan->num_var_states == 0 || evidence != nullptr, "evidence is null");
+  PGX_CHECK(plan->num_edge_states == 0 || ftov_msgs != nullptr, "ftov_msgs is null");
+  int rc;
+  if ((rc = check_device(plan))) return rc;
+  if (ties) PGX_CUDA(cudaMemsetAsync(ties, 0, size_t(batch) * sizeof(int32_t), st));
+  if (plan->num_vars == 0) return PGX_OK;
+  const pgx::BatchMap mp = make_map(batch);
+  // The ABI arrays are read in place through strided views (batch-major).
+  pgx::View ev{evidence, 1, ev_batched ? plan->num_var_states : 0};
+  pgx::View m{ftov_msgs, 1, msgs_batched ? plan->num_edge_states : 0};
+  pgx::k_decode<<<grid_for(plan, mp, plan->num_vars), pgx::kThreads, 0, st>>>(
+      mp, plan->num_vars, plan->num_var_states, plan->d_var_first_state, plan->d_var_ptr,
+      plan->d_var_edge_msg, ev, m, beliefs, map_out, marginals, ties);
+  return check_launch(plan, "k_decode");
+}
+
+int pgx_beliefs(pgx_plan* plan, void* stream, int64_t batch, const float* evidence, int ev_batched,
+                const float* ftov_msgs, int msgs_batched, float* beliefs_out) {
+  if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+  PGX_CHECK(beliefs_out != nullptr || plan->num_var_states == 0, "beliefs_out is null");
+  return decode_impl(plan, static_cast<cudaStream_t>(stream), batch, evidence, ev_batched, ftov_msgs,
+                     msgs_batched, beliefs_out, nullptr, nullptr, nullptr);
+}
+
+int pgx_decode(pgx_plan* plan, void* stream, int64_t batch, const float* evidence, int ev_batched,
+               const float* ftov_msgs, int msgs_batched, int32_t* map_out, float* marginals_out,
+               int32_t* tie_count_out) {
+  if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+  return decode_impl(plan, static_cast<cudaStream_t>(stream), batch, evidence, ev_batched, ftov_msgs,
+                     msgs_batched, nullptr, map_out, marginals_out, tie_count_out);
+}
+
+}  // extern "C"
+
+namespace {
+template <typename T>
+int grow(T** p, int64_t* have, int64_t need) {
+  if (need <= *have) return PGX_OK;
+  free_dev(*p);
+  *p = nullptr;
+  *have = 0;
+  PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(p), size_t(need) * sizeof(T)));
+  *have = need;
+  return PGX_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int pgx_infer_host(pgx_plan* plan, void* stream, int64_t batch, const float* lp_h, int lp_batched,
+                   const float* ev_h, int ev_batched, const float* msgs_h, int msgs_batched,
+                   int32_t num_iters, float damping, float temperature, int32_t* map_h, float* marg_h,
+                   int32_t* ties_h, float* msgs_out_h, float* deltas_h) {
+  if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+  PGX_CHECK(batch >= 1, "batch must be >= 1");
+  int rc;
+  if ((rc = check_device(plan))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Workspace& ws = plan->ws;
+  const int64_t n_lp = plan->num_potentials * (lp_batched ? batch : 1);
+  const int64_t n_ev = plan->num_var_states * (ev_batched ? batch : 1);
+  const int64_t n_in = msgs_h ? plan->num_edge_states * (msgs_batched ? batch : 1) : 0;
+  const int64_t n_out = plan->num_edge_states * batch;
+  if ((rc = grow(&ws.h_lp, &ws.n_lp, std::max<int64_t>(n_lp, 1)))) return rc;
+  if ((rc = grow(&ws.h_ev, &ws.n_ev, std::max<int64_t>(n_ev, 1)))) return rc;
+  if ((rc = grow(&ws.h_msgs_in, &ws.n_msgs_in, std::max<int64_t>(n_in, 1)))) return rc;
+  if ((rc = grow(&ws.h_msgs_out, &ws.n_msgs_out, std::max<int64_t>(n_out, 1)))) return rc;
+  if ((rc = grow(&ws.h_map, &ws.n_map, std::max<int64_t>(plan->num_vars * batch, 1)))) return rc;
+  if ((rc = grow(&ws.h_ties, &ws.n_ties, batch))) return rc;
+  if (marg_h && (rc = grow(&ws.h_marg, &ws.n_marg, std::max<int64_t>(plan->num_var_states * batch, 1))))
+    return rc;
+  if (deltas_h && (rc = grow(&ws.h_deltas, &ws.n_deltas, batch * num_iters))) return rc;
+  if (n_lp) PGX_CUDA(cudaMemcpyAsync(ws.h_lp, lp_h, size_t(n_lp) * 4, cudaMemcpyHostToDevice, st));
+  if (n_ev) PGX_CUDA(cudaMemcpyAsync(ws.h_ev, ev_h, size_t(n_ev) * 4, cudaMemcpyHostToDevice, st));
+  if (n_in) PGX_CUDA(cudaMemcpyAsync(ws.h_msgs_in, msgs_h, size_t(n_in) * 4, cudaMemcpyHostToDevice, st));
+  if ((rc = pgx_bp_run(plan, stream, batch, ws.h_lp, lp_batched, ws.h_ev, ev_batched,
+                       msgs_h ? ws.h_msgs_in : nullptr, msgs_batched, ws.h_msgs_out,
+                       deltas_h ? ws.h_deltas : nullptr, num_iters, damping, temperature)))
+    return rc;
+  if (map_h || marg_h || ties_h) {
+    if ((rc = pgx_decode(plan, stream, batch, ws.h_ev, ev_batched, ws.h_msgs_out, 1, map_h ? ws.h_map : nullptr,
+                         marg_h ? ws.h_marg : nullptr, ties_h ? ws.h_ties : nullptr)))
+      return rc;
+  }
+  if (map_h)
+    PGX_CUDA(cudaMemcpyAsync(map_h, ws.h_map, size_t(plan->num_vars) * batch * 4, cudaMemcpyDeviceToHost, st));
+  if (marg_h)
+    PGX_CUDA(cudaMemcpyAsync(marg_h, ws.h_marg, size_t(plan->num_var_states) * batch * 4,
+                             cudaMemcpyDeviceToHost, st));
+  if (ties_h) PGX_CUDA(cudaMemcpyAsync(ties_h, ws.h_ties, size_t(batch) * 4, cudaMemcpyDeviceToHost, st));
+  if (msgs_out_h)
+    PGX_CUDA(cudaMemcpyAsync(msgs_out_h, ws.h_msgs_out, size_t(n_out) * 4, cudaMemcpyDeviceToHost, st));
+  if (deltas_h)
+    PGX_CUDA(cudaMemcpyAsync(deltas_h, ws.h_deltas, size_t(batch) * num_iters * 4, cudaMemcpyDeviceToHost, st));
+  PGX_CUDA(cudaStreamSynchronize(st));
+  return PGX_OK;
+}
+
+}  // extern "C"

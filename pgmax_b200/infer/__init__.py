@@ -1,0 +1,29 @@
+"""Inference (host mirror of the pgmax.infer sub-package).
+
+``build_inferer(bp_state, backend)`` dispatches on a backend string exactly like
+the reference (pgmax/infer/__init__.py:34-40); only "bp" is on the B200 hot
+path.  "sdlp" (smooth dual LP-MAP) is listed as next in SURVEY.md §8(f).
+"""
+
+from pgmax_b200.infer.bp import BeliefPropagation
+from pgmax_b200.infer.bp import BP
+from pgmax_b200.infer.bp import get_marginals
+from pgmax_b200.infer.bp_state import BPArrays
+from pgmax_b200.infer.bp_state import BPState
+from pgmax_b200.infer.bp_state import Evidence
+from pgmax_b200.infer.bp_state import FToVMessages
+from pgmax_b200.infer.bp_state import LogPotentials
+from pgmax_b200.infer.inferer import decode_map_states
+from pgmax_b200.infer.inferer import Inferer
+from pgmax_b200.infer.inferer import InfererContext
+
+
+def build_inferer(bp_state: BPState, backend: str) -> Inferer:
+  """Inferer for ``bp_state``: backend "bp" -> BP(bp_state)."""
+  if backend == "bp":
+    return BP(bp_state)
+  if backend == "sdlp":
+    raise NotImplementedError(
+        "The smooth dual LP-MAP solver is outside the B200 hot path (SURVEY.md §8f)."
+    )
+  raise NotImplementedError(f"Inferer {backend} is not supported.")

@@ -1,0 +1,157 @@
+"""Model builders shared by the tests (graphs follow the reference's tests / notebooks)."""
+
+import itertools
+
+import numpy as np
+from scipy.ndimage import gaussian_filter
+
+from pgmax_b200 import factor, fgraph, fgroup, infer, vgroup
+
+
+# 29 valid configurations of the 4-variable "cut" factors and the suppression
+# configurations of the reference's e2e test (tests/test_pgmax.py:176-213, 37-61).
+CUT_CONFIGS = np.array([
+    [0, 0, 0, 0], [1, 0, 1, 0], [2, 0, 2, 0], [0, 0, 1, 1], [0, 0, 2, 2], [2, 0, 0, 1],
+    [1, 0, 0, 2], [1, 0, 1, 1], [2, 0, 2, 1], [1, 0, 1, 2], [2, 0, 2, 2], [0, 1, 0, 1],
+    [1, 1, 0, 0], [0, 1, 2, 0], [1, 1, 0, 1], [2, 1, 0, 1], [0, 1, 1, 1], [0, 1, 2, 1],
+    [1, 1, 1, 0], [2, 1, 2, 0], [0, 2, 0, 2], [2, 2, 0, 0], [0, 2, 1, 0], [2, 2, 0, 2],
+    [1, 2, 0, 2], [0, 2, 2, 2], [0, 2, 1, 2], [2, 2, 2, 0], [1, 2, 1, 0],
+])
+
+
+def suppression_configs(diameter: int) -> np.ndarray:
+  rows = [[0] * diameter]
+  for idx in range(diameter):
+    for val in (1, 2):
+      row = [0] * diameter
+      row[idx] = val
+      rows.append(row)
+  return np.array(rows)
+
+
+def cut_model(im_size: int = 3, seed: int = 23):
+  """The 3x3 depth-scene cut model of tests/test_pgmax.py:35-421 (evidence from
+  default_rng(23) logistic noise, drawn in the same order).  Returns
+  (fg, bp_state, grid_vars, additional_vars)."""
+  rng = np.random.default_rng(seed)
+  depth = 5.0 * np.ones((im_size, im_size))
+  depth[np.tril_indices(im_size, 0)] = 1.0
+  depth = gaussian_filter(depth, sigma=0.5)
+  M = N = im_size
+  dh = depth[:-1] - depth[1:]
+  dv = depth[:, :-1] - depth[:, 1:]
+  cuts = np.zeros((2, M, N), dtype=np.int32)
+  cuts[0, :-1] = np.where(dh < 0, 1, np.where(dh > 0, 2, 0))
+  cuts[1, :, :-1] = np.where(dv < 0, 1, np.where(dv > 0, 2, 0))
+
+  grid_vars = vgroup.NDVarArray(shape=(2, M - 1, N - 1), num_states=3)
+  extra_names = tuple(
+      [(0, row, N - 1) for row in range(M - 1)] + [(1, M - 1, col) for col in range(N - 1)]
+  )
+  additional_vars = vgroup.VarDict(variable_names=extra_names, num_states=3)
+
+  grid_ev = np.zeros((2, M - 1, N - 1, 3))
+  extra_ev = {}
+  for i, row, col in itertools.product(range(2), range(M), range(N)):
+    ev = np.zeros(3)
+    ev[cuts[i, row, col]] = 2.0
+    ev = ev - ev[0]
+    ev[1:] += 0.1 * rng.logistic(size=2)  # noise is drawn for EVERY (i, row, col)
+    if row < M - 1 and col < N - 1:
+      grid_ev[i, row, col] = ev
+    elif (i, row, col) in extra_names:
+      extra_ev[i, row, col] = ev
+
+  def var(i, row, col):
+    if row < M - 1 and col < N - 1:
+      return grid_vars[i, row, col]
+    return additional_vars[i, row, col]
+
+  fg = fgraph.FactorGraph(variable_groups=[grid_vars, additional_vars])
+  for row, col in itertools.product(range(M - 1), range(N - 1)):
+    fg.add_factors(
+        factor.EnumFactor(
+            variables=[var(0, row, col), var(1, row, col), var(0, row, col + 1), var(1, row + 1, col)],
+            factor_configs=CUT_CONFIGS,
+            log_potentials=np.zeros(CUT_CONFIGS.shape[0]),
+        )
+    )
+  diameter = 2
+  supp = suppression_configs(diameter)
+  vert = [
+      [var(0, r, col) for r in range(start, start + diameter)]
+      for col in range(N)
+      for start in range(M - diameter)
+  ]
+  horz = [
+      [var(1, row, c) for c in range(start, start + diameter)]
+      for row in range(M)
+      for start in range(N - diameter)
+  ]
+  fg.add_factors(fgroup.EnumFactorGroup(variables_for_factors=vert, factor_configs=supp))
+  fg.add_factors(
+      fgroup.EnumFactorGroup(
+          variables_for_factors=horz, factor_configs=supp, log_potentials=np.zeros(supp.shape[0])
+      )
+  )
+  bp_state = fg.bp_state
+  bp_state.evidence[grid_vars] = grid_ev
+  bp_state.evidence[additional_vars] = extra_ev
+  return fg, bp_state, grid_vars, additional_vars
+
+
+def ising_model(n: int = 50, coupling: float = 0.8, seed: int = 0, batch=None):
+  """n x n binary torus, pairwise factors [(i,j),(i+1,j)] and [(i,j),(i,j+1)]
+  (examples/ising_model.ipynb cells 8-12; tests/test_examples.py:26-41).
+  Returns (fg, variables, evidence_array)."""
+  variables = vgroup.NDVarArray(num_states=2, shape=(n, n))
+  fg = fgraph.FactorGraph(variable_groups=variables)
+  pairs = []
+  for ii in range(n):
+    for jj in range(n):
+      kk, ll = (ii + 1) % n, (jj + 1) % n
+      pairs.append([variables[ii, jj], variables[kk, jj]])
+      pairs.append([variables[ii, jj], variables[ii, ll]])
+  fg.add_factors(
+      fgroup.PairwiseFactorGroup(
+          variables_for_factors=pairs,
+          log_potential_matrix=coupling * np.array([[1.0, -1.0], [-1.0, 1.0]]),
+      )
+  )
+  rng = np.random.default_rng(seed)
+  shape = (n, n, 2) if batch is None else (batch, n, n, 2)
+  return fg, variables, rng.gumbel(size=shape)
+
+
+def rbm_model(W, bh, bv):
+  """RBM as in benchmark/rbm_lib.py:138-169: hidden and visible unary EnumFactors,
+  then one pairwise factor per (hidden, visible) pair with log-potential W at (1, 1).
+  Returns (fg, hidden_vars, visible_vars)."""
+  nh, nv = bh.shape[0], bv.shape[0]
+  hidden = vgroup.NDVarArray(num_states=2, shape=(nh,))
+  visible = vgroup.NDVarArray(num_states=2, shape=(nv,))
+  fg = fgraph.FactorGraph(variable_groups=[hidden, visible])
+  unary_cfg = np.arange(2)[:, None]
+  hidden_unaries = fgroup.EnumFactorGroup(
+      variables_for_factors=[[hidden[i]] for i in range(nh)],
+      factor_configs=unary_cfg,
+      log_potentials=np.stack([np.zeros_like(bh), bh], axis=1),
+  )
+  visible_unaries = fgroup.EnumFactorGroup(
+      variables_for_factors=[[visible[j]] for j in range(nv)],
+      factor_configs=unary_cfg,
+      log_potentials=np.stack([np.zeros_like(bv), bv], axis=1),
+  )
+  lpm = np.zeros((nh * nv, 2, 2))
+  lpm[:, 1, 1] = W.ravel()
+  pairwise = fgroup.PairwiseFactorGroup(
+      variables_for_factors=[[hidden[i], visible[j]] for i in range(nh) for j in range(nv)],
+      log_potential_matrix=lpm,
+  )
+  fg.add_factors([hidden_unaries, visible_unaries, pairwise])
+  return fg, hidden, visible
+
+
+def rbm_energy(hidden, visible, W, bh, bv):
+  """Energy of an RBM configuration (benchmark/rbm_lib.py calc_energies)."""
+  return -(hidden @ bh) - (visible @ bv) - hidden @ W @ visible

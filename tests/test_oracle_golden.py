@@ -1,0 +1,67 @@
+"""Pins the CPU oracle to the reference's own known answers (no GPU needed).
+
+(1) tests/test_pgmax.py:63-152,252-265 — 84 golden messages (atol 1e-6, the
+    reference's own tolerance at :418) and 12 golden MAP states after 100
+    max-product iterations on the 3x3 cut model.
+(2) benchmark/precomputed_results n_units_24 — the reference's decoded RBM states
+    after 20 and 200 max-product iterations (identical on its CPU and GPU
+    back-ends), harness benchmark/rbm_lib.py:135-214.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+import models
+from oracle import bp_oracle
+from pgmax_b200 import infer
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_cut_model_golden_messages_and_map():
+  gold = np.load(os.path.join(GOLDEN, "e2e_sanity.npz"))
+  fg, bp_state, grid_vars, additional_vars = models.cut_model()
+  bp = infer.BP(bp_state, temperature=0.0)
+  graph = bp_oracle.graph_from_context(bp.context)
+  arrays = bp.init()
+  msgs, deltas = bp_oracle.run_bp(
+      graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence,
+      num_iters=100, damping=0.5, temperature=0.0)
+  assert msgs.shape == (84,) and deltas.shape == (100,)
+  # The reference's criterion is jnp.allclose(..., atol=1e-06), i.e. rtol = 1e-5 (default).
+  np.testing.assert_allclose(msgs, gold["true_final_msgs_output"], atol=1e-6, rtol=1e-5)
+  assert np.max(np.abs(msgs - gold["true_final_msgs_output"])) < 2e-6
+
+  beliefs = infer.inferer.unflatten_beliefs(
+      bp_oracle.flat_beliefs(graph, msgs, arrays.evidence), fg.variable_groups)
+  decoded = infer.decode_map_states(beliefs)
+  groups = {"grid_vars": grid_vars, "additional_vars": additional_vars}
+  for name, index, state in zip(gold["map_groups"], gold["map_indices"], gold["map_states"]):
+    assert decoded[groups[str(name)]][tuple(index)] == state
+
+
+@pytest.mark.parametrize("num_iters", [20, 200])
+def test_rbm24_decoded_states_match_reference(num_iters):
+  gold = np.load(os.path.join(GOLDEN, "rbm24.npz"))
+  # The reference's CPU and GPU back-ends agree on every 24-unit RBM.
+  np.testing.assert_array_equal(gold[f"hidden_cpu_{num_iters}"], gold[f"hidden_gpu_{num_iters}"])
+  mismatches = 0
+  for idx in range(0, 50, 5):
+    W, bh, bv = gold["W"][idx], gold["bh"][idx], gold["bv"][idx]
+    fg, hidden, visible = models.rbm_model(W, bh, bv)
+    bp = infer.BP(fg.bp_state, temperature=0.0)
+    graph = bp_oracle.graph_from_context(bp.context)
+    arrays = bp.init()
+    msgs, _ = bp_oracle.run_bp(
+        graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence,
+        num_iters=num_iters, damping=0.5, temperature=0.0)
+    states, _, _ = bp_oracle.decode_flat(graph, bp_oracle.flat_beliefs(graph, msgs, arrays.evidence))
+    pred_h, pred_v = states[: bh.shape[0]], states[bh.shape[0] :]
+    same = np.array_equal(pred_h, gold[f"hidden_cpu_{num_iters}"][idx]) and np.array_equal(
+        pred_v, gold[f"visible_cpu_{num_iters}"][idx])
+    energy = models.rbm_energy(pred_h, pred_v, W, bh, bv)
+    np.testing.assert_allclose(energy, gold[f"energy_cpu_{num_iters}"][idx], rtol=1e-5, atol=1e-5) if same else None
+    mismatches += int(not same)
+  assert mismatches == 0
