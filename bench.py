@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — BP messages updated per second on the configurations BASELINE.json names.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rbm|ising50|ising_big]
+  python bench.py --impl reference ...      # the CPU arm (NumPy oracle on the host cores)
+
+A "step" is one call of the hot path over one batch of synthetic input: bp.run for
+the workload's iteration count (pgx_bp_run: all iterations enqueued back to back on
+one stream).  Default workload (N=1): BASELINE.json configs[1], the RBM 784 x 500,
+sum-product with Gumbel evidence, batch 1024, 200 iterations, damping 0.5.
+
+One JSON line on stdout (rank 0):
+  value        messages (edge-states) updated / s, whole job, inputs resident in HBM
+  e2e          the same through pgx_infer_host with pinned HOST buffers: H2D copies,
+               all iterations, fused decode, D2H of the MAP states inside the timing
+  roofline     dominant kernel: algorithmic bytes per launch / its CUDA-event time,
+               against MEASURED_PEAKS.json's hbm_gbs (fallback 6650 GB/s)
+  cpu_baseline the NumPy oracle on the host cores (bounded sample), rank 0, N=1 only
+
+Multi-GPU (torchrun, one rank per GPU): independent samples are split by batch
+index, every rank runs the identical kernels on its own shard, no data-path
+collective ("scaling": "weak": per-GPU batch is fixed).  Timing: barrier +
+synchronize on both sides, CUDA events, max over ranks.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+  if _p not in sys.path:
+    sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "bp_messages_updated_per_sec"
+UNIT = "edge_states/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+# ----------------------------------------------------------------------------------------
+# Workloads (synthetic data of the named shapes)
+# ----------------------------------------------------------------------------------------
+def build_workload(name: str, batch_override=None, iters_override=None):
+  """Returns dict(fg groups, evidence (host fp32), temperature, iters, damping, batch, ...)."""
+  import models
+  from pgmax_b200 import infer
+
+  if name == "rbm":
+    # benchmark/rbm_lib.py:138-169 shape; examples/rbm.ipynb sizes; np.random.seed(0) weights
+    nh, nv, batch, iters, temperature = 500, 784, 1024, 200, 1.0
+    rs = np.random.RandomState(0)
+    W, bh, bv = rs.normal(size=(nh, nv)), rs.logistic(size=nh), rs.logistic(size=nv)
+    fg, hidden, visible = models.rbm_model(W, bh, bv)
+    batch = batch_override or batch
+    rng = np.random.default_rng(0)
+    bp = infer.BP(fg.bp_state, temperature=temperature)
+    evidence = {hidden: rng.gumbel(size=(batch, nh, 2)).astype(np.float32),
+                visible: rng.gumbel(size=(batch, nv, 2)).astype(np.float32)}
+    label = f"RBM {nv}x{nh} pairwise EnumFactors, sum-product T=1, Gumbel evidence"
+  elif name == "rbm_small":  # CPU-sized stand-in used by the tests of bench.py itself
+    nh, nv, batch, iters, temperature = 20, 30, 8, 10, 1.0
+    rs = np.random.RandomState(0)
+    W, bh, bv = rs.normal(size=(nh, nv)), rs.logistic(size=nh), rs.logistic(size=nv)
+    fg, hidden, visible = models.rbm_model(W, bh, bv)
+    batch = batch_override or batch
+    rng = np.random.default_rng(0)
+    bp = infer.BP(fg.bp_state, temperature=temperature)
+    evidence = {hidden: rng.gumbel(size=(batch, nh, 2)).astype(np.float32),
+                visible: rng.gumbel(size=(batch, nv, 2)).astype(np.float32)}
+    label = f"RBM {nv}x{nh} (test size)"
+  elif name == "ising50":
+    # examples/ising_model.ipynb: 50x50 torus, coupling 0.8, 1000 iters, T=0.05
+    batch, iters, temperature = batch_override, 1000, 0.05
+    fg, variables, ev = models.ising_model(n=50, batch=batch)
+    bp = infer.BP(fg.bp_state, temperature=temperature)
+    evidence = {variables: ev.astype(np.float32)}
+    label = "Ising 50x50 torus, pairwise EnumFactors, T=0.05"
+  else:
+    raise ValueError(f"unknown workload {name}")
+  iters = iters_override or iters
+  arrays = bp.init(evidence_updates=evidence)
+  return dict(name=name, label=label, bp=bp, arrays=arrays, iters=iters, damping=0.5,
+              temperature=temperature, batch=batch or 1)
+
+
+def algorithmic_bytes_per_iter(plan, batch, lp_batched):
+  """4 * (2*E_s*B + V_s*B + C*B_lp + E_s)."""
+  es, vs, c = plan.num_edge_states, plan.num_var_states, plan.num_potentials
+  return 4 * (2 * es * batch + vs * batch + c * (batch if lp_batched else 1) + es)
+
+
+# ----------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+  """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+
+  QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+           "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+           "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index: int):
+    self.index, self.proc, self.lines = index, None, []
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(
+          ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+           "--format=csv,noheader,nounits", "-lms", "100"],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except OSError:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.lines.append(line.strip())
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    self.proc.terminate()
+    self.thread.join(timeout=2)
+    sm, mx, reasons = [], [], set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for line in self.lines:
+      parts = [p.strip() for p in line.split(",")]
+      if len(parts) < 6:
+        continue
+      try:
+        sm.append(float(parts[0])); mx.append(float(parts[1]))
+      except ValueError:
+        continue
+      for n, v in zip(names, parts[2:6]):
+        if v.lower().startswith("active"):
+          reasons.add(n)
+    return {"sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+            "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the NumPy oracle on the host cores
+# ----------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init(name):
+  wl = build_workload(name, batch_override=1)
+  from oracle import bp_oracle
+  _W["graph"] = bp_oracle.graph_from_context(wl["bp"].context)
+  _W["wl"] = wl
+
+
+def _cpu_worker_run(args):
+  seed, iters = args
+  from oracle import bp_oracle
+  wl, graph = _W["wl"], _W["graph"]
+  a = wl["arrays"]
+  rng = np.random.default_rng(1000 + seed)
+  ev = rng.gumbel(size=graph.num_var_states).astype(np.float32)
+  msgs, _ = bp_oracle.run_bp(graph, np.asarray(a.log_potentials).reshape(-1)[: a.log_potentials.shape[-1]],
+                             np.zeros(a.ftov_msgs.shape[-1], np.float32), ev, iters,
+                             wl["damping"], wl["temperature"])
+  return float(msgs.sum())
+
+
+def cpu_arm(name, steps, warmup, iters_per_sample):
+  """Oracle throughput with one process per host core; each step = `cores` independent
+  samples x `iters_per_sample` iterations of the workload's graph."""
+  import multiprocessing as mp
+  cores = len(os.sched_getaffinity(0))
+  ctx = mp.get_context("spawn")
+  with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(name,)) as pool:
+    pool.map(_cpu_worker_run, [(i, 1) for i in range(cores)])  # touch everything once
+    for _ in range(warmup):
+      pool.map(_cpu_worker_run, [(i, 1) for i in range(cores)])
+    t0 = time.perf_counter()
+    for s in range(steps):
+      pool.map(_cpu_worker_run, [(s * cores + i, iters_per_sample) for i in range(cores)])
+    dt = time.perf_counter() - t0
+  wl = build_workload(name)
+  es = int(sum(int(w.edge_num_states.sum()) for w in wl["bp"].context.wiring.values()))
+  total = es * cores * iters_per_sample * steps
+  return dict(value=total / dt, seconds=dt, cores=cores, es=es,
+              sample=f"{cores} samples x {iters_per_sample} iterations per step, {steps} steps "
+                     f"(one oracle process per core; the workload is {wl['batch']} samples x {wl['iters']} iterations)",
+              label=wl["label"], temperature=wl["temperature"], iters=wl["iters"])
+
+
+def run_reference(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  iters = 3 if args.workload == "rbm" else 50
+  res = cpu_arm(args.workload, max(args.steps, 1), min(args.warmup, 1), iters)
+  line = {
+      "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
+      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+      "ms_per_step": 1e3 * res["seconds"] / max(args.steps, 1), "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+      "config": {"workload": res["label"], "iters": res["iters"], "damping": 0.5,
+                 "temperature": res["temperature"]},
+      "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                       "sample": res["sample"]},
+      "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+      "note": "NumPy fp32 restatement of the reference's run_bp (oracle/bp_oracle.py); JAX is not installable here",
+  }
+  print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=3)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="pgx", choices=["pgx", "reference"])
+  ap.add_argument("--workload", default="rbm")
+  ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
+  ap.add_argument("--iters", type=int, default=None, help="BP iterations per step override")
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  if args.impl == "reference":
+    run_reference(args)
+    return
+
+  import torch
+  import torch.distributed as dist
+  from pgmax_b200 import _native
+  from pgmax_b200.infer.bp_state import BPArrays
+
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise _native.PgxError(_native.PGX_ERR_NO_DEVICE, "bench.py needs a CUDA device (no CPU fallback)")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+  wl = build_workload(args.workload, batch_override=args.batch, iters_override=args.iters)
+  bp, iters, damping, T = wl["bp"], wl["iters"], wl["damping"], wl["temperature"]
+  # every rank draws its own shard of samples (weak scaling: per-GPU batch fixed)
+  host = wl["arrays"]
+  if world > 1 and host.evidence.ndim == 2:
+    rng = np.random.default_rng(100 + rank)
+    host = BPArrays(log_potentials=host.log_potentials, ftov_msgs=host.ftov_msgs,
+                    evidence=rng.gumbel(size=host.evidence.shape).astype(np.float32))
+  plan = bp.context.plan
+  batch = host.batch_size or 1
+  put = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+  dev_arrays = BPArrays(log_potentials=put(host.log_potentials), ftov_msgs=put(host.ftov_msgs),
+                        evidence=put(host.evidence))
+  es = plan.num_edge_states
+  msgs_per_step = es * batch * iters
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---- device-resident timing ------------------------------------------------------------
+  for _ in range(args.warmup):
+    out = bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
+  barrier()
+  launches0 = plan.launch_count
+  plan.profile_enable(True)
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  for _ in range(args.steps):
+    out = bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
+  e1.record()
+  barrier()
+  ms = e0.elapsed_time(e1)
+  clocks = sampler.stop()
+  n_prof, prof_ms, prof_name = plan.profile_read()
+  plan.profile_enable(False)
+  launches = plan.launch_count - launches0
+  checksum = float(out.ftov_msgs.float().abs().max().item())
+
+  # ---- end to end through the C ABI with host buffers ---------------------------------------
+  pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory()
+  h_lp, h_ev = pin(host.log_potentials), pin(host.evidence)
+  h_map = torch.empty((batch, plan.num_vars), dtype=torch.int32).pin_memory()
+  h_ties = torch.empty((batch,), dtype=torch.int32).pin_memory()
+  stream = torch.cuda.current_stream(dev).cuda_stream
+
+  def e2e_step():
+    plan.infer_host(stream, batch, h_lp.data_ptr(), h_lp.ndim == 2, h_ev.data_ptr(), h_ev.ndim == 2,
+                    None, False, iters, damping, T, h_map.data_ptr(), None, h_ties.data_ptr(), None, None)
+
+  for _ in range(min(args.warmup, 2)):
+    e2e_step()
+  barrier()
+  e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t0 = time.perf_counter()
+  e2.record()
+  for _ in range(args.steps):
+    e2e_step()
+  e3.record()
+  barrier()
+  e2e_ms = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+  h2d = 4 * (h_lp.numel() + h_ev.numel())
+  d2h = 4 * (h_map.numel() + h_ties.numel())
+
+  if world > 1:
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+
+  if rank == 0:
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = FALLBACK_HBM_GBS, "fallback"
+    if os.path.exists(peaks_path):
+      try:
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+      except (KeyError, ValueError):
+        pass
+    lp_batched = host.log_potentials.ndim == 2
+    bytes_iter = algorithmic_bytes_per_iter(plan, batch, lp_batched)
+    kernel_ms = prof_ms / max(n_prof, 1)
+    achieved = bytes_iter / (kernel_ms * 1e-3) / 1e9 if n_prof else None
+    line = {
+        "metric": METRIC, "value": msgs_per_step * args.steps * world / (ms * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["label"], "batch_per_gpu": batch, "global_batch": batch * world,
+                   "iters": iters, "damping": damping, "temperature": T, "edge_states": es,
+                   "l2": "working set (2 x %.2f GB of messages) larger than L2" % (4e-9 * es * batch)
+                   if 8 * es * batch > 126e6 else "L2-resident working set (reported, not an HBM figure)",
+                   "parallelism": f"batch-sharded x{world}, no collective"},
+        "e2e": {"value": msgs_per_step * args.steps * world / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None,
+                     "kernel": prof_name, "kernel_ms": kernel_ms, "launches_timed": n_prof,
+                     "algorithmic_bytes_per_launch": bytes_iter, "peak_source": peak_src,
+                     "iter_ms": ms / args.steps / iters},
+        "checksum_max_abs_msg": checksum,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+      sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",
+                            "--workload", args.workload, "--steps", "2", "--warmup", "1"],
+                           capture_output=True, text=True)
+      try:
+        ref = json.loads(sub.stdout.strip().splitlines()[-1])
+        line["cpu_baseline"] = ref["cpu_baseline"]
+      except (IndexError, ValueError, KeyError):
+        line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
+                                "sample": "failed: " + sub.stderr[-300:]}
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -168,6 +168,17 @@ int pgx_infer_host(pgx_plan* plan, void* stream, int64_t batch,
  * (bench.py reports it as gpu_launches). */
 int64_t pgx_plan_launch_count(const pgx_plan* plan);
 
+/* Device-time instrumentation for the roofline figure (bench.py).  While
+ * enabled, pgx_bp_run brackets, in every iteration, the launch of the plan's
+ * dominant kernel (the factor->variable kernel that covers the most
+ * edge-states) with CUDA events recorded on the run's stream.
+ * pgx_plan_profile_read synchronises those events, returns the number of
+ * bracketed launches and their summed device time since the last read, the
+ * kernel's name, and resets the counters.  Off by default (no events). */
+int pgx_plan_profile_enable(pgx_plan* plan, int enabled);
+int pgx_plan_profile_read(pgx_plan* plan, int64_t* num_launches, double* total_ms,
+                          const char** kernel_name);
+
 /* Message of the last failure on the calling thread ("" if none). */
 const char* pgx_last_error(void);
 

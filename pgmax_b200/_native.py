@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = (
     "pgx_decode",
     "pgx_infer_host",
     "pgx_plan_launch_count",
+    "pgx_plan_profile_enable",
+    "pgx_plan_profile_read",
     "pgx_last_error",
     "pgx_build_info",
 )
@@ -146,6 +148,11 @@ def load() -> ctypes.CDLL:
   lib.pgx_infer_host.restype = ctypes.c_int
   lib.pgx_plan_launch_count.argtypes = [vp]
   lib.pgx_plan_launch_count.restype = ctypes.c_int64
+  lib.pgx_plan_profile_enable.argtypes = [vp, ctypes.c_int]
+  lib.pgx_plan_profile_enable.restype = ctypes.c_int
+  lib.pgx_plan_profile_read.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double),
+                                        ctypes.POINTER(ctypes.c_char_p)]
+  lib.pgx_plan_profile_read.restype = ctypes.c_int
   lib.pgx_last_error.argtypes = []
   lib.pgx_last_error.restype = ctypes.c_char_p
   lib.pgx_build_info.argtypes = []
@@ -269,6 +276,16 @@ class Plan:
   @property
   def launch_count(self) -> int:
     return int(self._lib.pgx_plan_launch_count(self.handle))
+
+  def profile_enable(self, enabled: bool) -> None:
+    check(self._lib.pgx_plan_profile_enable(self.handle, int(enabled)))
+
+  def profile_read(self):
+    """(launches, total_ms, kernel_name) of the dominant kernel since the last read."""
+    n, ms, name = ctypes.c_int64(), ctypes.c_double(), ctypes.c_char_p()
+    check(self._lib.pgx_plan_profile_read(self.handle, ctypes.byref(n), ctypes.byref(ms),
+                                          ctypes.byref(name)))
+    return int(n.value), float(ms.value), (name.value or b"").decode()
 
   # The methods below take raw device pointers (ints) so that any owner of device
   # memory (torch tensors here) can call them.

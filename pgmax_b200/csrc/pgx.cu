@@ -107,6 +107,14 @@ struct pgx_plan {
   std::vector<EnumBlockPlan> enum_blocks;
   LogicalPlan or_f, and_f, pool_f;
   Workspace ws;
+  // roofline instrumentation (pgx_plan_profile_*): the dominant kernel is the f2v
+  // launch covering the most edge-states; id = enum block index, or -1/-2/-3 for
+  // the OR / AND / Pool launch.
+  bool profiling = false;
+  int dominant = 0;
+  const char* dominant_name = "";
+  std::vector<cudaEvent_t> prof_events;  // pairs (begin, end)
+  size_t prof_used = 0;
 };
 
 namespace {
@@ -318,13 +326,27 @@ int from_batch_inner(pgx_plan* plan, cudaStream_t st, const float* src, float* d
   return check_launch(plan, "k_from_batch_inner");
 }
 
+// Records a profiling event if `id` is the plan's dominant launch.
+int prof_mark(pgx_plan* plan, cudaStream_t st, int id) {
+  if (!plan->profiling || id != plan->dominant) return PGX_OK;
+  if (plan->prof_used == plan->prof_events.size()) {
+    cudaEvent_t e;
+    PGX_CUDA(cudaEventCreate(&e));
+    plan->prof_events.push_back(e);
+  }
+  PGX_CUDA(cudaEventRecord(plan->prof_events[plan->prof_used++], st));
+  return PGX_OK;
+}
+
 template <bool kSum>
 int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::View lp, const float* S,
                const float* m_old, float* m_new, float d, float omd, float T, float* deltas,
                int64_t dstride, int64_t doff) {
   int rc;
-  for (EnumBlockPlan& eb : plan->enum_blocks) {
+  for (size_t bi = 0; bi < plan->enum_blocks.size(); ++bi) {
+    EnumBlockPlan& eb = plan->enum_blocks[bi];
     const int64_t F = eb.dev.num_factors;
+    if ((rc = prof_mark(plan, st, int(bi)))) return rc;
     if (eb.variant == kPw2) {
       pgx::k_enum_pw2<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
           mp, F, eb.dev.first_edge, eb.dev.first_msg, eb.dev.first_pot, plan->d_edge_vs, lp, S, m_old,
@@ -343,17 +365,24 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
                                                                dstride, doff);
       if ((rc = check_launch(plan, "k_enum_big"))) return rc;
     }
+    if ((rc = prof_mark(plan, st, int(bi)))) return rc;
   }
+  int lid = -1;
   for (LogicalPlan* lg : {&plan->or_f, &plan->and_f}) {
+    const int id = lid--;
     if (lg->dev.num_factors == 0) continue;
+    if ((rc = prof_mark(plan, st, id))) return rc;
     pgx::k_logical<kSum><<<grid_for(plan, mp, lg->dev.num_factors), pgx::kThreads, 0, st>>>(
         mp, lg->dev, S, m_old, m_new, d, omd, T, deltas, dstride, doff);
     if ((rc = check_launch(plan, "k_logical"))) return rc;
+    if ((rc = prof_mark(plan, st, id))) return rc;
   }
   if (plan->pool_f.dev.num_factors > 0) {
+    if ((rc = prof_mark(plan, st, -3))) return rc;
     pgx::k_pool<kSum><<<grid_for(plan, mp, plan->pool_f.dev.num_factors), pgx::kThreads, 0, st>>>(
         mp, plan->pool_f.dev, S, m_old, m_new, d, omd, T, deltas, dstride, doff);
     if ((rc = check_launch(plan, "k_pool"))) return rc;
+    if ((rc = prof_mark(plan, st, -3))) return rc;
   }
   return PGX_OK;
 }
@@ -456,6 +485,8 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
   PGX_TRY(upload(narrow(var_edge_msg), &plan->d_var_edge_msg, &plan->device_bytes));
 
   // factor types
+  const int64_t desc_num_parents[3] = {desc->or_factors.num_parents, desc->and_factors.num_parents,
+                                       desc->pool_factors.num_parents};
   std::vector<uint8_t> edge_covered(plan->num_edges, 0);
   PGX_REQUIRE(desc->num_enum_blocks == 0 || desc->enum_blocks, "enum_blocks is null");
   plan->enum_blocks.resize(desc->num_enum_blocks);
@@ -472,6 +503,20 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
                         "Pool factors", &plan->pool_f));
   for (int64_t e = 0; e < plan->num_edges; ++e)
     PGX_REQUIRE(edge_covered[e], "edge %lld belongs to no factor description", (long long)e);
+  {  // dominant launch = most edge-states
+    int64_t best = -1;
+    static const char* const kEnumNames[] = {"k_enum_pw2", "k_enum_small", "k_enum_big"};
+    for (size_t i = 0; i < plan->enum_blocks.size(); ++i) {
+      const int64_t es = plan->enum_blocks[i].dev.num_factors * plan->enum_blocks[i].dev.ns;
+      if (es > best) { best = es; plan->dominant = int(i); plan->dominant_name = kEnumNames[plan->enum_blocks[i].variant]; }
+    }
+    int lid = -1;
+    for (const LogicalPlan* lg : {&plan->or_f, &plan->and_f, &plan->pool_f}) {
+      const int id = lid--;
+      const int64_t es = 2 * (lg->dev.num_factors + (lg->dev.num_factors ? desc_num_parents[-id - 1] : 0));
+      if (lg->dev.num_factors && es > best) { best = es; plan->dominant = id; plan->dominant_name = id == -3 ? "k_pool" : "k_logical"; }
+    }
+  }
 #undef PGX_TRY
 #undef PGX_REQUIRE
   *out_plan = plan;
@@ -490,6 +535,7 @@ void pgx_plan_destroy(pgx_plan* plan) {
     free_dev(lg->d_children_msg); free_dev(lg->d_children_vs);
   }
   free_workspace(plan->ws);
+  for (cudaEvent_t e : plan->prof_events) cudaEventDestroy(e);
   delete plan;
 }
 
@@ -508,6 +554,30 @@ int pgx_plan_get_info(const pgx_plan* plan, pgx_plan_info* info) {
 }
 
 int64_t pgx_plan_launch_count(const pgx_plan* plan) { return plan ? plan->launches : 0; }
+
+int pgx_plan_profile_enable(pgx_plan* plan, int enabled) {
+  if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+  plan->profiling = enabled != 0;
+  plan->prof_used = 0;
+  return PGX_OK;
+}
+
+int pgx_plan_profile_read(pgx_plan* plan, int64_t* num_launches, double* total_ms, const char** kernel_name) {
+  if (!plan || !num_launches || !total_ms) return fail(PGX_ERR_INVALID, "null argument");
+  double total = 0.0;
+  const size_t pairs = plan->prof_used / 2;
+  for (size_t i = 0; i < pairs; ++i) {
+    PGX_CUDA(cudaEventSynchronize(plan->prof_events[2 * i + 1]));
+    float ms = 0.f;
+    PGX_CUDA(cudaEventElapsedTime(&ms, plan->prof_events[2 * i], plan->prof_events[2 * i + 1]));
+    total += ms;
+  }
+  *num_launches = int64_t(pairs);
+  *total_ms = total;
+  if (kernel_name) *kernel_name = plan->dominant_name;
+  plan->prof_used = 0;
+  return PGX_OK;
+}
 
 int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch, const float* log_potentials, int lp_batched,
                const float* evidence, int ev_batched, const float* ftov_in, int msgs_batched,

@@ -155,3 +155,71 @@ def rbm_model(W, bh, bv):
 def rbm_energy(hidden, visible, W, bh, bv):
   """Energy of an RBM configuration (benchmark/rbm_lib.py calc_energies)."""
   return -(hidden @ bh) - (visible @ bv) - hidden @ W @ visible
+
+
+def _logical_enum_configs(kind: str, num_parents: int) -> np.ndarray:
+  """All valid configurations of an OR / AND / Pool factor with `num_parents`
+  parents (choices) and the child (indicator) last — the equivalent EnumFactor of
+  tests/factor/test_or.py:120-140, test_and.py, test_pool.py."""
+  configs = np.array(list(itertools.product([0, 1], repeat=num_parents + 1)))
+  parents, child = configs[:, :-1], configs[:, -1]
+  if kind == "or":
+    ok = (parents.sum(axis=1) >= 1) == (child == 1)
+  elif kind == "and":
+    ok = (parents.sum(axis=1) == num_parents) == (child == 1)
+  elif kind == "pool":
+    ok = parents.sum(axis=1) == child
+  else:
+    raise ValueError(kind)
+  return configs[ok]
+
+
+def logical_pair(kind: str, seed: int):
+  """Two equivalent graphs in the spirit of the reference's differential tests
+  (tests/factor/test_or.py:30-290): graph A holds the first half of the factors
+  as `kind` factors and the second half as their equivalent EnumFactors; graph B
+  the other way round (seed 0: all-logical vs all-enum).  Returns a dict with the
+  two graphs, their variable groups, and shared random evidence / initial messages."""
+  rng = np.random.RandomState(seed)
+  num_factors = rng.randint(10, 20)
+  num_parents = rng.randint(1, 10, num_factors)
+  cum = np.insert(np.cumsum(num_parents), 0, 0)
+  group_cls = {"or": fgroup.ORFactorGroup, "and": fgroup.ANDFactorGroup,
+               "pool": fgroup.PoolFactorGroup}[kind]
+  split = num_factors if seed == 0 else num_factors // 2
+
+  graphs = []
+  for which in range(2):
+    parents = vgroup.NDVarArray(num_states=2, shape=(int(num_parents.sum()),))
+    children = vgroup.NDVarArray(num_states=2, shape=(num_factors,))
+    fg = fgraph.FactorGraph(variable_groups=[parents, children])
+    vff = [[parents[i] for i in range(cum[f], cum[f + 1])] + [children[f]]
+           for f in range(num_factors)]
+    as_logical = list(range(split)) if which == 0 else list(range(split, num_factors))
+    as_enum = [f for f in range(num_factors) if f not in as_logical]
+    for f in as_enum:
+      cfg = _logical_enum_configs(kind, int(num_parents[f]))
+      fg.add_factors(factor.EnumFactor(variables=vff[f], factor_configs=cfg,
+                                       log_potentials=np.zeros(cfg.shape[0])))
+    if as_logical:
+      fg.add_factors(group_cls(variables_for_factors=[vff[f] for f in as_logical]))
+    graphs.append((fg, parents, children))
+  ev_parents = rng.gumbel(size=(int(num_parents.sum()), 2))
+  ev_children = rng.gumbel(size=(num_factors, 2))
+  msg_parents = rng.normal(size=(int(num_parents.sum()), 2))
+  msg_children = rng.normal(size=(num_factors, 2))
+  return dict(graphs=graphs, ev_parents=ev_parents, ev_children=ev_children,
+              msg_parents=msg_parents, msg_children=msg_children,
+              num_factors=num_factors, num_parents=num_parents)
+
+
+def init_logical(bp, entry, data):
+  """BPArrays for one graph of logical_pair: evidence + per-variable initial messages
+  (update_ftov_msgs by variable spreads data / num_edges, bp_state.py:208-228)."""
+  _, parents, children = entry
+  msgs = {parents[i]: data["msg_parents"][i] for i in range(data["msg_parents"].shape[0])}
+  msgs.update({children[i]: data["msg_children"][i] for i in range(data["msg_children"].shape[0])})
+  return bp.init(
+      evidence_updates={parents: data["ev_parents"], children: data["ev_children"]},
+      ftov_msgs_updates=msgs,
+  )

@@ -1,0 +1,220 @@
+"""GPU parity: the sm_100a kernels behind include/pgx.h against the CPU oracle and
+the reference's golden vectors.  Every call goes through the C ABI
+(pgmax_b200._native -> libpgx.so).
+
+Tolerances: max-product (T=0) messages are compared at 1e-6 absolute and MAP
+decodings must be identical (exactly-tied variables are counted and excluded);
+sum-product messages / marginals within 1e-5 absolute (BASELINE.json north_star).
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+import models
+from oracle import bp_oracle
+from pgmax_b200 import infer
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _finite_close(a, b, atol):
+  """allclose that treats the -1e32 clip floor as a category, not a number."""
+  a, b = np.asarray(a), np.asarray(b)
+  floor_a, floor_b = a <= -1e31, b <= -1e31
+  np.testing.assert_array_equal(floor_a, floor_b)
+  np.testing.assert_allclose(a[~floor_a], b[~floor_b], atol=atol, rtol=1e-5)
+
+
+def _run_both(bp, arrays, num_iters, damping, temperature):
+  graph = bp_oracle.graph_from_context(bp.context)
+  want, want_d = bp_oracle.run_bp_batched(
+      graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, num_iters, damping,
+      temperature)
+  got, got_d = bp.run_with_diffs(arrays, num_iters=num_iters, damping=damping,
+                                 temperature=temperature)
+  return graph, want, want_d, got, got_d
+
+
+def test_cut_model_golden():
+  gold = np.load(os.path.join(GOLDEN, "e2e_sanity.npz"))
+  fg, bp_state, grid_vars, additional_vars = models.cut_model()
+  bp = infer.BP(bp_state, temperature=0.0)
+  arrays = bp.init()
+  out = bp.run(arrays, num_iters=100, damping=0.5)
+  np.testing.assert_allclose(out.ftov_msgs, gold["true_final_msgs_output"], atol=1e-6, rtol=1e-5)
+  decoded = infer.decode_map_states(bp.get_beliefs(out))
+  fused = bp.get_map_states(out)
+  groups = {"grid_vars": grid_vars, "additional_vars": additional_vars}
+  for name, index, state in zip(gold["map_groups"], gold["map_indices"], gold["map_states"]):
+    assert decoded[groups[str(name)]][tuple(index)] == state
+    assert fused[groups[str(name)]][tuple(index)] == state
+  # deprecated alias gives the same answer (tests/fgraph/test_fgraph.py:249-282)
+  with pytest.warns(UserWarning):
+    out2 = bp.run_bp(arrays, num_iters=100, damping=0.5)
+  np.testing.assert_array_equal(out.ftov_msgs, out2.ftov_msgs)
+
+
+@pytest.mark.parametrize("temperature", [0.0, 0.5, 1.0])
+def test_cut_model_vs_oracle(temperature):
+  _, bp_state, _, _ = models.cut_model()
+  bp = infer.BP(bp_state, temperature=temperature)
+  arrays = bp.init()
+  _, want, want_d, got, got_d = _run_both(bp, arrays, 30, 0.5, temperature)
+  _finite_close(got.ftov_msgs, want, 1e-6 if temperature == 0.0 else 1e-5)
+  np.testing.assert_allclose(got_d, want_d, atol=1e-5)
+
+
+@pytest.mark.parametrize("temperature", [0.0, 0.05, 1.0])
+@pytest.mark.parametrize("batch", [None, 3, 40])
+def test_ising_vs_oracle(temperature, batch):
+  fg, variables, evidence = models.ising_model(n=12, batch=batch)
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  arrays = bp.init(evidence_updates={variables: evidence})
+  graph, want, want_d, got, got_d = _run_both(bp, arrays, 20, 0.5, temperature)
+  atol = 1e-6 if temperature == 0.0 else 1e-5
+  np.testing.assert_allclose(got.ftov_msgs, want, atol=atol)
+  np.testing.assert_allclose(got_d, want_d, atol=atol)
+  if temperature == 0.0:
+    # max-product on pairwise binary factors involves no transcendental: bit-exact
+    np.testing.assert_array_equal(got.ftov_msgs, want)
+  # beliefs / decode / marginals
+  want_b = bp_oracle.flat_beliefs(graph, want, arrays.evidence)
+  got_b = bp.context.flat_beliefs(got)
+  np.testing.assert_allclose(got_b, want_b, atol=atol * 4)
+  states, marg, ties = bp.context.decode(got, marginals=True)
+  w_states, w_marg, w_ties = bp_oracle.decode_flat(graph, got_b)
+  np.testing.assert_array_equal(states, w_states)
+  np.testing.assert_array_equal(ties, w_ties)
+  np.testing.assert_allclose(marg, w_marg, atol=1e-6)
+
+
+@pytest.mark.parametrize("num_iters", [20, 200])
+def test_rbm24_reference_decodings(num_iters):
+  gold = np.load(os.path.join(GOLDEN, "rbm24.npz"))
+  for idx in range(0, 50, 7):
+    W, bh, bv = gold["W"][idx], gold["bh"][idx], gold["bv"][idx]
+    fg, hidden, visible = models.rbm_model(W, bh, bv)
+    bp = infer.BP(fg.bp_state, temperature=0.0)
+    out = bp.run(bp.init(), num_iters=num_iters, damping=0.5)
+    states = bp.get_map_states(out)
+    np.testing.assert_array_equal(states[hidden], gold[f"hidden_cpu_{num_iters}"][idx])
+    np.testing.assert_array_equal(states[visible], gold[f"visible_cpu_{num_iters}"][idx])
+
+
+@pytest.mark.parametrize("temperature", [0.0, 1.0])
+def test_rbm_batched_gumbel_vs_oracle(temperature):
+  rng = np.random.default_rng(0)
+  nh, nv, batch = 12, 20, 37
+  W, bh, bv = rng.normal(size=(nh, nv)), rng.logistic(size=nh), rng.logistic(size=nv)
+  fg, hidden, visible = models.rbm_model(W, bh, bv)
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  arrays = bp.init(evidence_updates={
+      hidden: rng.gumbel(size=(batch, nh, 2)), visible: rng.gumbel(size=(batch, nv, 2))})
+  assert arrays.evidence.shape == (batch, 2 * (nh + nv))
+  _, want, want_d, got, got_d = _run_both(bp, arrays, 25, 0.5, temperature)
+  np.testing.assert_allclose(got.ftov_msgs, want, atol=1e-6 if temperature == 0 else 1e-5)
+  np.testing.assert_allclose(got_d, want_d, atol=1e-5)
+
+
+TEMPS = [(0.0, 1e-5), (0.001, 5e-3), (0.3, 5e-3), (0.8, 1e-5)]
+
+
+@pytest.mark.parametrize("kind", ["or", "and", "pool"])
+@pytest.mark.parametrize("seed", range(8))
+def test_logical_vs_oracle_and_vs_enum(kind, seed):
+  """The reference's differential test (tests/factor/test_or.py:30-290 etc.) on the GPU:
+  logical factors == equivalent EnumFactors, and both == the oracle."""
+  temperature, atol = TEMPS[seed % 4]
+  data = models.logical_pair(kind, seed)
+  beliefs = []
+  for entry in data["graphs"]:
+    bp = infer.BP(entry[0].bp_state, temperature=temperature)
+    arrays = models.init_logical(bp, entry, data)
+    graph, want, _, got, _ = _run_both(bp, arrays, 5, 0.5, temperature)
+    # vs the oracle: same branch structure, so tight even at low temperature
+    _finite_close(got.ftov_msgs, want, 2e-5 if temperature >= 0.5 or temperature == 0 else 1e-3)
+    beliefs.append(bp.context.flat_beliefs(got))
+  np.testing.assert_allclose(beliefs[0], beliefs[1], atol=atol, rtol=0)
+
+
+def test_clipping_equality_factors():
+  """tests/test_clipping.py:24-58: messages hit the -1e32 floor; all decode to 1."""
+  from pgmax_b200 import fgraph, fgroup, vgroup
+  num = 10
+  variables = vgroup.NDVarArray(num_states=2, shape=(num,))
+  fg = fgraph.FactorGraph(variables)
+  pairs = [[variables[i], variables[j]] for i in range(num) for j in range(i + 1, num)]
+  fg.add_factors(fgroup.EnumFactorGroup(
+      variables_for_factors=pairs, factor_configs=np.array([[0, 0], [1, 1]])))
+  bp = infer.BP(fg.bp_state, temperature=0.0)
+  arrays = bp.init(evidence_updates={variables: np.tile(np.array([0.0, 1.0]), (num, 1))})
+  graph, want, _, got, _ = _run_both(bp, arrays, 100, 0.0, 0.0)
+  _finite_close(got.ftov_msgs, want, 1e-6)
+  np.testing.assert_array_equal(bp.get_map_states(got)[variables], np.ones(num))
+
+
+def test_infinite_potentials_are_clipped_inside_run():
+  """tests/test_energy.py:75-100: -inf potentials are clipped to -1e6 in run only."""
+  from pgmax_b200 import factor, fgraph, vgroup
+  variables = vgroup.NDVarArray(num_states=2, shape=(2,))
+  fg = fgraph.FactorGraph(variables)
+  fg.add_factors(factor.EnumFactor(
+      variables=[variables[0], variables[1]],
+      factor_configs=np.array([[0, 0], [0, 1], [1, 0], [1, 1]]),
+      log_potentials=np.array([-np.inf, -np.inf, -np.inf, 0.0])))
+  bp = infer.BP(fg.bp_state, temperature=0.0)
+  arrays = bp.init()
+  out = bp.run(arrays, num_iters=1, damping=0.0)
+  assert out.log_potentials is arrays.log_potentials  # returned unclipped
+  np.testing.assert_array_equal(bp.get_map_states(out)[variables], [1, 1])
+  graph = bp_oracle.graph_from_context(bp.context)
+  want, _ = bp_oracle.run_bp(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 1, 0.0, 0.0)
+  np.testing.assert_array_equal(out.ftov_msgs, want)
+
+
+def test_ragged_num_states():
+  """tests/fgraph/test_fgraph.py:285-333: variables with different numbers of states."""
+  from pgmax_b200 import factor, fgraph, vgroup
+  rng = np.random.default_rng(1)
+  ns = np.array([2, 3, 4, 3])
+  variables = vgroup.NDVarArray(num_states=ns, shape=(4,))
+  fg = fgraph.FactorGraph(variables)
+  for a, b in [(0, 1), (1, 2), (2, 3), (3, 0)]:
+    cfg = np.array([[i, j] for i in range(ns[a]) for j in range(ns[b]) if (i + j) % 3 != 2])
+    fg.add_factors(factor.EnumFactor(variables=[variables[a], variables[b]], factor_configs=cfg,
+                                     log_potentials=rng.normal(size=cfg.shape[0])))
+  for temperature in (0.0, 1.0):
+    bp = infer.BP(fg.bp_state, temperature=temperature)
+    arrays = bp.init(evidence_updates={variables[i]: rng.gumbel(size=ns[i]) for i in range(4)})
+    graph, want, _, got, _ = _run_both(bp, arrays, 10, 0.5, temperature)
+    _finite_close(got.ftov_msgs, want, 1e-5)
+    beliefs = bp.get_beliefs(got)[variables]
+    assert beliefs.shape == (4, 4) and np.isneginf(beliefs[0, 2:]).all()
+    marg = infer.get_marginals(bp.get_beliefs(got))[variables]
+    np.testing.assert_allclose(marg.sum(-1), 1.0, atol=1e-6)
+
+
+def test_infer_host_end_to_end():
+  fg, variables, evidence = models.ising_model(n=10, batch=5)
+  bp = infer.BP(fg.bp_state, temperature=0.0)
+  arrays = bp.init(evidence_updates={variables: evidence})
+  res = bp.infer_host(arrays, num_iters=30, damping=0.5, marginals=True, return_msgs=True)
+  got = bp.run(arrays, num_iters=30, damping=0.5)
+  np.testing.assert_array_equal(res["ftov_msgs"], got.ftov_msgs)
+  states, marg, ties = bp.context.decode(got, marginals=True)
+  np.testing.assert_array_equal(res["flat_map_states"], states)
+  np.testing.assert_array_equal(res["tie_counts"], ties)
+  np.testing.assert_allclose(res["marginals"], marg, atol=0)
+
+
+def test_split_run_equals_single_run():
+  """Resume contract: run(a)+run(b) == run(a+b) because NC is idempotent."""
+  fg, variables, evidence = models.ising_model(n=8)
+  bp = infer.BP(fg.bp_state, temperature=1.0)
+  arrays = bp.init(evidence_updates={variables: evidence})
+  one = bp.run(arrays, num_iters=12, damping=0.5)
+  two = bp.run(bp.run(arrays, num_iters=5, damping=0.5), num_iters=7, damping=0.5)
+  np.testing.assert_array_equal(one.ftov_msgs, two.ftov_msgs)
