@@ -231,6 +231,8 @@ def main():
   ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
   ap.add_argument("--iters", type=int, default=None, help="BP iterations per step override")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--exact-order", action="store_true",
+                  help="force the two-pass serial-summation-order path (pgx_plan_set_exact_order)")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)
@@ -260,6 +262,7 @@ def main():
     host = BPArrays(log_potentials=host.log_potentials, ftov_msgs=host.ftov_msgs,
                     evidence=rng.gumbel(size=host.evidence.shape).astype(np.float32))
   plan = bp.context.plan
+  plan.set_exact_order(args.exact_order)
   batch = host.batch_size or 1
   put = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
   dev_arrays = BPArrays(log_potentials=put(host.log_potentials), ftov_msgs=put(host.ftov_msgs),
@@ -345,6 +348,8 @@ def main():
                    "iters": iters, "damping": damping, "temperature": T, "edge_states": es,
                    "l2": "working set (2 x %.2f GB of messages) larger than L2" % (4e-9 * es * batch)
                    if 8 * es * batch > 126e6 else "L2-resident working set (reported, not an HBM figure)",
+                   "summation_order": "serial (two-pass)" if args.exact_order or not plan.has_fused_blocks
+                   or batch <= 16 else "tiled partial sums (single pass)",
                    "parallelism": f"batch-sharded x{world}, no collective"},
         "e2e": {"value": msgs_per_step * args.steps * world / (e2e_ms * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

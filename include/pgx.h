@@ -168,6 +168,19 @@ int pgx_infer_host(pgx_plan* plan, void* stream, int64_t batch,
  * (bench.py reports it as gpu_launches). */
 int64_t pgx_plan_launch_count(const pgx_plan* plan);
 
+/* Summation order of the variable sums S_v = ev_v + sum of incoming messages.
+ * Default (0): blocks of pairwise binary factors that form a dense rows x columns
+ * grid (RBM-like) are updated in ONE pass per iteration when batch > 16; their
+ * contribution to S_v is then added as per-tile partial sums in a fixed tree
+ * order - deterministic, but not the serial ascending order of a CPU
+ * scatter-add (the reference's own GPU scatter-add is unordered atomics).
+ * 1: always use the two-pass path that accumulates S_v serially in ascending
+ * message index, bit-compatible with the CPU oracle for max-product.  The
+ * environment variable PGX_EXACT_ORDER=1 sets the default for new plans. */
+int pgx_plan_set_exact_order(pgx_plan* plan, int enabled);
+/* Number of enum blocks for which the single-pass path is available. */
+int pgx_plan_num_fused_blocks(const pgx_plan* plan);
+
 /* Device-time instrumentation for the roofline figure (bench.py).  While
  * enabled, pgx_bp_run brackets, in every iteration, the launch of the plan's
  * dominant kernel (the factor->variable kernel that covers the most

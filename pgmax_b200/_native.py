@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = (
     "pgx_decode",
     "pgx_infer_host",
     "pgx_plan_launch_count",
+    "pgx_plan_set_exact_order",
+    "pgx_plan_num_fused_blocks",
     "pgx_plan_profile_enable",
     "pgx_plan_profile_read",
     "pgx_last_error",
@@ -148,6 +150,10 @@ def load() -> ctypes.CDLL:
   lib.pgx_infer_host.restype = ctypes.c_int
   lib.pgx_plan_launch_count.argtypes = [vp]
   lib.pgx_plan_launch_count.restype = ctypes.c_int64
+  lib.pgx_plan_num_fused_blocks.argtypes = [vp]
+  lib.pgx_plan_num_fused_blocks.restype = ctypes.c_int
+  lib.pgx_plan_set_exact_order.argtypes = [vp, ctypes.c_int]
+  lib.pgx_plan_set_exact_order.restype = ctypes.c_int
   lib.pgx_plan_profile_enable.argtypes = [vp, ctypes.c_int]
   lib.pgx_plan_profile_enable.restype = ctypes.c_int
   lib.pgx_plan_profile_read.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double),
@@ -276,6 +282,15 @@ class Plan:
   @property
   def launch_count(self) -> int:
     return int(self._lib.pgx_plan_launch_count(self.handle))
+
+  @property
+  def has_fused_blocks(self) -> bool:
+    """True when the plan found dense-grid pairwise blocks (single-pass path available)."""
+    return bool(self._lib.pgx_plan_num_fused_blocks(self.handle))
+
+  def set_exact_order(self, enabled: bool) -> None:
+    """Force the two-pass, serial-summation-order path (see pgx_plan_set_exact_order)."""
+    check(self._lib.pgx_plan_set_exact_order(self.handle, int(enabled)))
 
   def profile_enable(self, enabled: bool) -> None:
     check(self._lib.pgx_plan_profile_enable(self.handle, int(enabled)))

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -67,7 +68,14 @@ enum EnumVariant { kPw2 = 0, kSmall = 1, kBig = 2 };
 struct EnumBlockPlan {
   pgx::EnumBlockDev dev{};
   EnumVariant variant = kSmall;
+  int bip = -1;  // index into pgx_plan::bips when the block has the dense-grid structure
   int32_t *d_cfg_es = nullptr, *d_t_ptr = nullptr, *d_t_k = nullptr, *d_edge_off = nullptr;
+};
+
+// A pairwise-binary enum block whose factors form a dense I x J grid (see BipDev).
+struct BipPlan {
+  pgx::BipDev dev{};
+  int32_t *d_row_vs = nullptr, *d_col_vs = nullptr, *d_row_part = nullptr, *d_col_part = nullptr;
 };
 
 struct LogicalPlan {
@@ -79,7 +87,7 @@ struct LogicalPlan {
 struct Workspace {
   int64_t batch = 0;
   int ld = 0;
-  float *mA = nullptr, *mB = nullptr, *S = nullptr, *evT = nullptr, *lpT = nullptr;
+  float *mA = nullptr, *mB = nullptr, *S = nullptr, *evT = nullptr, *lpT = nullptr, *part = nullptr;
   // staging for pgx_infer_host
   float *h_lp = nullptr, *h_ev = nullptr, *h_msgs_in = nullptr, *h_msgs_out = nullptr,
         *h_marg = nullptr, *h_deltas = nullptr;
@@ -107,6 +115,14 @@ struct pgx_plan {
   std::vector<EnumBlockPlan> enum_blocks;
   LogicalPlan or_f, and_f, pool_f;
   Workspace ws;
+  // fused single-pass structures (dense-grid pairwise blocks)
+  std::vector<BipPlan> bips;
+  bool exact_order = false;            // force the two-pass, serial-order path
+  int64_t part_rows = 0;               // rows of the partial-sum buffer
+  int32_t* d_rest_ptr = nullptr;       // [num_vars + 1] CSR over edges NOT covered by a fused block
+  int32_t* d_rest_edge_msg = nullptr;
+  int32_t* d_part_first = nullptr;     // [num_vars] first partial row of the variable
+  int32_t* d_part_count = nullptr;     // [num_vars] partial slots (each 2 rows: state 0, state 1)
   // roofline instrumentation (pgx_plan_profile_*): the dominant kernel is the f2v
   // launch covering the most edge-states; id = enum block index, or -1/-2/-3 for
   // the OR / AND / Pool launch.
@@ -124,7 +140,7 @@ void free_dev(void* p) {
 }
 
 void free_workspace(Workspace& ws) {
-  free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT);
+  free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT); free_dev(ws.part);
   free_dev(ws.h_lp); free_dev(ws.h_ev); free_dev(ws.h_msgs_in); free_dev(ws.h_msgs_out);
   free_dev(ws.h_marg); free_dev(ws.h_deltas); free_dev(ws.h_map); free_dev(ws.h_ties);
   ws = Workspace{};
@@ -280,12 +296,12 @@ int build_enum_block(pgx_plan* plan, const pgx_enum_block& b, int idx,
   return PGX_OK;
 }
 
-int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT) {
+int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT, bool need_part) {
   Workspace& ws = plan->ws;
   const pgx::BatchMap mp = make_map(batch);
   if (ws.batch != batch) {
-    free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT);
-    ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = nullptr;
+    free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT); free_dev(ws.part);
+    ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = ws.part = nullptr;
     ws.batch = batch;
     ws.ld = mp.ld;
     const size_t nm = size_t(std::max<int64_t>(plan->num_edge_states, 1)) * mp.ld * sizeof(float);
@@ -294,6 +310,9 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.mB), nm));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.S), nv));
   }
+  if (need_part && ws.part == nullptr)
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.part),
+                        size_t(std::max<int64_t>(plan->part_rows, 1)) * mp.ld * sizeof(float)));
   if (need_evT && ws.evT == nullptr)
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.evT),
                         size_t(std::max<int64_t>(plan->num_var_states, 1)) * mp.ld * sizeof(float)));
@@ -341,17 +360,28 @@ int prof_mark(pgx_plan* plan, cudaStream_t st, int id) {
 template <bool kSum>
 int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::View lp, const float* S,
                const float* m_old, float* m_new, float d, float omd, float T, float* deltas,
-               int64_t dstride, int64_t doff) {
+               int64_t dstride, int64_t doff, bool fused) {
   int rc;
   for (size_t bi = 0; bi < plan->enum_blocks.size(); ++bi) {
     EnumBlockPlan& eb = plan->enum_blocks[bi];
     const int64_t F = eb.dev.num_factors;
     if ((rc = prof_mark(plan, st, int(bi)))) return rc;
-    if (eb.variant == kPw2) {
+    if (fused && eb.bip >= 0) {
+      const pgx::BipDev& g = plan->bips[eb.bip].dev;
+      constexpr int TJ = pgx::kBipTJ;
+      const int groups = (mp.nbt + pgx::kBipWarps - 1) / pgx::kBipWarps;
+      const int64_t grid = int64_t(g.NS) * g.NR * groups;
+      const size_t smem = size_t(g.RI) * TJ * 4 * sizeof(float);
+      pgx::k_enum_pw2_bip<kSum, TJ><<<unsigned(grid), pgx::kBipWarps * 32, smem, st>>>(
+          mp.batch, mp.ld, groups, g, lp.p, S, m_old, m_new, plan->ws.part, d, omd, T, deltas, dstride, doff);
+      if ((rc = check_launch(plan, "k_enum_pw2_bip"))) return rc;
+      if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2_bip";
+    } else if (eb.variant == kPw2) {
       pgx::k_enum_pw2<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
           mp, F, eb.dev.first_edge, eb.dev.first_msg, eb.dev.first_pot, plan->d_edge_vs, lp, S, m_old,
           m_new, d, omd, T, deltas, dstride, doff);
       if ((rc = check_launch(plan, "k_enum_pw2"))) return rc;
+      if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2";
     } else if (eb.variant == kSmall) {
       pgx::k_enum_small<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
           mp, eb.dev, plan->d_edge_vs, lp, S, m_old, m_new, d, omd, T, deltas, dstride, doff);
@@ -503,9 +533,113 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
                         "Pool factors", &plan->pool_f));
   for (int64_t e = 0; e < plan->num_edges; ++e)
     PGX_REQUIRE(edge_covered[e], "edge %lld belongs to no factor description", (long long)e);
+  {  // dense-grid pairwise blocks -> fused single-pass structures
+    std::vector<uint8_t> edge_fused(plan->num_edges, 0);
+    std::vector<int32_t> part_count(plan->num_vars, 0);
+    struct Grid { int blk; int32_t I, J; };
+    std::vector<Grid> grids;
+    for (size_t bi = 0; bi < plan->enum_blocks.size(); ++bi) {
+      EnumBlockPlan& eb = plan->enum_blocks[bi];
+      if (eb.variant != kPw2) continue;
+      const int64_t F = eb.dev.num_factors, e0 = eb.dev.first_edge;
+      int64_t J = 1;
+      while (J < F && edge_vs[e0 + 2 * J] == edge_vs[e0]) ++J;
+      if (F % J != 0 || F / J < 2 || J < 2 || F >= INT32_MAX) continue;
+      bool ok = true;
+      for (int64_t f = 0; f < F && ok; ++f)
+        ok = edge_vs[e0 + 2 * f] == edge_vs[e0 + 2 * (f / J * J)] && edge_vs[e0 + 2 * f + 1] == edge_vs[e0 + 2 * (f % J) + 1];
+      // rows (and columns) must be distinct variables: partial slots are per (variable, block)
+      if (!ok) continue;
+      grids.push_back({int(bi), int32_t(F / J), int32_t(J)});
+    }
+    const char* env = getenv("PGX_EXACT_ORDER");
+    plan->exact_order = env != nullptr && env[0] == '1';
+    if (!grids.empty()) {
+      constexpr int TJ = pgx::kBipTJ;
+      // slots per variable, in block order
+      std::vector<std::vector<int32_t>> row_slot(grids.size()), col_slot(grids.size());
+      for (size_t gi = 0; gi < grids.size(); ++gi) {
+        const Grid& gr = grids[gi];
+        const EnumBlockPlan& eb = plan->enum_blocks[gr.blk];
+        const int64_t e0 = eb.dev.first_edge;
+        const int32_t NS = (gr.J + TJ - 1) / TJ;
+        const int32_t NR = std::max<int32_t>(1, (gr.I + 31) / 32);
+        row_slot[gi].resize(gr.I);
+        col_slot[gi].resize(gr.J);
+        for (int32_t i = 0; i < gr.I; ++i) {
+          const int32_t var = vs_var[edge_vs[e0 + 2 * int64_t(i) * gr.J]];
+          row_slot[gi][i] = part_count[var];
+          part_count[var] += NS;
+        }
+        for (int32_t j = 0; j < gr.J; ++j) {
+          const int32_t var = vs_var[edge_vs[e0 + 2 * int64_t(j) + 1]];
+          col_slot[gi][j] = part_count[var];
+          part_count[var] += NR;
+        }
+        for (int64_t e = e0; e < e0 + 2 * eb.dev.num_factors; ++e) edge_fused[e] = 1;
+      }
+      std::vector<int32_t> part_first(plan->num_vars, 0);
+      int64_t rows = 0;
+      for (int64_t v = 0; v < plan->num_vars; ++v) {
+        part_first[v] = int32_t(rows);
+        rows += 2 * int64_t(part_count[v]);
+        PGX_REQUIRE(rows < INT32_MAX, "partial-sum buffer too large");
+      }
+      plan->part_rows = rows;
+      plan->bips.resize(grids.size());
+      for (size_t gi = 0; gi < grids.size(); ++gi) {
+        const Grid& gr = grids[gi];
+        EnumBlockPlan& eb = plan->enum_blocks[gr.blk];
+        BipPlan& bp = plan->bips[gi];
+        const int64_t e0 = eb.dev.first_edge;
+        std::vector<int32_t> row_vs(gr.I), col_vs(gr.J), row_part(gr.I), col_part(gr.J);
+        for (int32_t i = 0; i < gr.I; ++i) {
+          row_vs[i] = edge_vs[e0 + 2 * int64_t(i) * gr.J];
+          row_part[i] = part_first[vs_var[row_vs[i]]] + 2 * row_slot[gi][i];
+        }
+        for (int32_t j = 0; j < gr.J; ++j) {
+          col_vs[j] = edge_vs[e0 + 2 * int64_t(j) + 1];
+          col_part[j] = part_first[vs_var[col_vs[j]]] + 2 * col_slot[gi][j];
+        }
+        PGX_TRY(upload(row_vs, &bp.d_row_vs, &plan->device_bytes));
+        PGX_TRY(upload(col_vs, &bp.d_col_vs, &plan->device_bytes));
+        PGX_TRY(upload(row_part, &bp.d_row_part, &plan->device_bytes));
+        PGX_TRY(upload(col_part, &bp.d_col_part, &plan->device_bytes));
+        bp.dev.first_msg = eb.dev.first_msg;
+        bp.dev.first_pot = eb.dev.first_pot;
+        bp.dev.I = gr.I;
+        bp.dev.J = gr.J;
+        bp.dev.NS = (gr.J + TJ - 1) / TJ;
+        bp.dev.NR = std::max<int32_t>(1, (gr.I + 31) / 32);
+        bp.dev.RI = (gr.I + bp.dev.NR - 1) / bp.dev.NR;
+        bp.dev.NR = (gr.I + bp.dev.RI - 1) / bp.dev.RI;  // no empty chunk
+        bp.dev.row_vs = bp.d_row_vs;
+        bp.dev.col_vs = bp.d_col_vs;
+        bp.dev.row_part = bp.d_row_part;
+        bp.dev.col_part = bp.d_col_part;
+        eb.bip = int(gi);
+      }
+      // CSR over the remaining edges (ascending message index within a variable)
+      std::vector<int64_t> rest_ptr(plan->num_vars + 1, 0);
+      for (int64_t e = 0; e < plan->num_edges; ++e)
+        if (!edge_fused[e]) ++rest_ptr[vs_var[edge_vs[e]] + 1];
+      for (int64_t v = 0; v < plan->num_vars; ++v) rest_ptr[v + 1] += rest_ptr[v];
+      std::vector<int64_t> rest_edge_msg(std::max<int64_t>(rest_ptr[plan->num_vars], 1), 0);
+      {
+        std::vector<int64_t> cursor(rest_ptr.begin(), rest_ptr.end() - 1);
+        for (int64_t e = 0; e < plan->num_edges; ++e)
+          if (!edge_fused[e]) rest_edge_msg[cursor[vs_var[edge_vs[e]]]++] = edge_msg_start[e];
+      }
+      PGX_TRY(upload(narrow(rest_ptr), &plan->d_rest_ptr, &plan->device_bytes));
+      PGX_TRY(upload(narrow(rest_edge_msg), &plan->d_rest_edge_msg, &plan->device_bytes));
+      PGX_TRY(upload(part_first, &plan->d_part_first, &plan->device_bytes));
+      PGX_TRY(upload(part_count, &plan->d_part_count, &plan->device_bytes));
+    }
+  }
   {  // dominant launch = most edge-states
     int64_t best = -1;
     static const char* const kEnumNames[] = {"k_enum_pw2", "k_enum_small", "k_enum_big"};
+    // (with the single-pass path active the pw2 launch of a dense-grid block is k_enum_pw2_bip)
     for (size_t i = 0; i < plan->enum_blocks.size(); ++i) {
       const int64_t es = plan->enum_blocks[i].dev.num_factors * plan->enum_blocks[i].dev.ns;
       if (es > best) { best = es; plan->dominant = int(i); plan->dominant_name = kEnumNames[plan->enum_blocks[i].variant]; }
@@ -534,6 +668,11 @@ void pgx_plan_destroy(pgx_plan* plan) {
     free_dev(lg->d_parent_ptr); free_dev(lg->d_parents_msg); free_dev(lg->d_parents_vs);
     free_dev(lg->d_children_msg); free_dev(lg->d_children_vs);
   }
+  for (BipPlan& bp : plan->bips) {
+    free_dev(bp.d_row_vs); free_dev(bp.d_col_vs); free_dev(bp.d_row_part); free_dev(bp.d_col_part);
+  }
+  free_dev(plan->d_rest_ptr); free_dev(plan->d_rest_edge_msg); free_dev(plan->d_part_first);
+  free_dev(plan->d_part_count);
   free_workspace(plan->ws);
   for (cudaEvent_t e : plan->prof_events) cudaEventDestroy(e);
   delete plan;
@@ -554,6 +693,14 @@ int pgx_plan_get_info(const pgx_plan* plan, pgx_plan_info* info) {
 }
 
 int64_t pgx_plan_launch_count(const pgx_plan* plan) { return plan ? plan->launches : 0; }
+
+int pgx_plan_set_exact_order(pgx_plan* plan, int enabled) {
+  if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+  plan->exact_order = enabled != 0;
+  return PGX_OK;
+}
+
+int pgx_plan_num_fused_blocks(const pgx_plan* plan) { return plan ? int(plan->bips.size()) : 0; }
 
 int pgx_plan_profile_enable(pgx_plan* plan, int enabled) {
   if (!plan) return fail(PGX_ERR_INVALID, "null plan");
@@ -596,7 +743,10 @@ int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch, const float* log_pot
   PGX_CHECK(int64_t(plan->num_edge_states) * mp.ld < (int64_t(1) << 40), "workspace too large");
   const bool single = batch == 1;
   const bool evT = !single && ev_batched, lpT = !single && lp_batched;
-  if ((rc = ensure_workspace(plan, batch, evT, lpT))) return rc;
+  // Single-pass mode: dense-grid pairwise blocks emit per-tile partial sums of the new
+  // messages; needs full warps of samples and potentials shared by the batch.
+  const bool fused = !plan->bips.empty() && !plan->exact_order && mp.bx_log == 5 && !lpT;
+  if ((rc = ensure_workspace(plan, batch, evT, lpT, fused))) return rc;
   Workspace& ws = plan->ws;
   const int64_t Es = plan->num_edge_states, Vs = plan->num_var_states, C = plan->num_potentials;
   if (Es == 0) return PGX_OK;
@@ -633,17 +783,26 @@ int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch, const float* log_pot
   // ---- iterations ------------------------------------------------------------------------
   const float omd = 1.0f - damping;
   for (int it = 0; it < num_iters; ++it) {
-    pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(
-        mp, Vs, plan->d_vs_var, plan->d_var_first_state, plan->d_var_ptr, plan->d_var_edge_msg, ev, cur,
-        ws.S);
-    if ((rc = check_launch(plan, "k_var_sums"))) return rc;
+    if (!fused || it == 0) {
+      pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(
+          mp, Vs, plan->d_vs_var, plan->d_var_first_state, plan->d_var_ptr, plan->d_var_edge_msg, ev, cur,
+          ws.S);
+      if ((rc = check_launch(plan, "k_var_sums"))) return rc;
+    }
     // With one sample the last iteration writes straight into the caller's buffer.
     float* dst = (single && it == num_iters - 1) ? ftov_out : nxt;
     if (temperature == 0.f)
-      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, damping, omd, temperature, deltas, num_iters, it);
+      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, damping, omd, temperature, deltas, num_iters, it, fused);
     else
-      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, damping, omd, temperature, deltas, num_iters, it);
+      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, damping, omd, temperature, deltas, num_iters, it, fused);
     if (rc) return rc;
+    if (fused && it + 1 < num_iters) {
+      // next iteration's variable sums from the partial sums the fused blocks just wrote
+      pgx::k_var_reduce<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(
+          mp, Vs, plan->d_vs_var, plan->d_var_first_state, plan->d_rest_ptr, plan->d_rest_edge_msg,
+          plan->d_part_first, plan->d_part_count, ev, dst, ws.part, ws.S);
+      if ((rc = check_launch(plan, "k_var_reduce"))) return rc;
+    }
     nxt = cur;
     cur = dst;
   }

@@ -211,13 +211,48 @@ __device__ __forceinline__ float damp(float m_old, float f, float d, float one_m
 }
 
 // ---------------------------------------------------------------------------
-// K2a: EnumFactor update, pairwise binary factors with all 4 configurations
-// valid (PairwiseFactorGroup over binary variables: Ising, RBM).  One thread
-// per (factor, sample), everything in registers.
+// Pairwise binary EnumFactor with all 4 configurations valid (PairwiseFactorGroup
+// over binary variables: Ising, RBM).  Everything in registers.
 //   s_k = (q_a + q_b) + lp_k;  M_e = max over the 2 configs containing e;
 //   T = 0: f_e = M_e - q_e;  T > 0: f_e = (T log sum exp((s_k - M_e)/T) + M_e) - q_e
-// (pgmax/factor/enum.py:451-475, update_utils.py:68-98.)
+// (pgmax/factor/enum.py:451-475, update_utils.py:68-98.)  With two terms the sum is
+// exp(0) + exp((min - max)/T) = 1 + e exactly as the reference forms it, so one
+// expf per edge-state suffices; (min - max)/T is evaluated as (min - max) * (1/T)
+// (exact for T = 1; one extra rounding of the exponent otherwise, far inside the
+// 1e-5 sum-product tolerance).
 // ---------------------------------------------------------------------------
+template <bool kSumProduct>
+__device__ __forceinline__ float lse2(float a, float b, float T, float inv_T) {
+  const float mx = fmaxf(a, b);
+  if (!kSumProduct) return mx;
+  const float mn = fminf(a, b);
+  return T * logf(1.0f + expf((mn - mx) * inv_T)) + mx;
+}
+
+// In: old messages m[4] = (v0s0, v0s1, v1s0, v1s1), var sums S[4] of the same
+// var-states, clipped potentials lp[4] in config order (0,0),(0,1),(1,0),(1,1).
+// Out: n[4] damped + normalised + clipped; returns max|n - m|.
+template <bool kSumProduct>
+__device__ __forceinline__ float pw2_update(const float (&m)[4], const float (&Sv)[4],
+                                            const float (&lp)[4], float d, float one_minus_d,
+                                            float T, float inv_T, float (&n)[4]) {
+  const float q0 = Sv[0] - m[0], q1 = Sv[1] - m[1], q2 = Sv[2] - m[2], q3 = Sv[3] - m[3];
+  const float s00 = (q0 + q2) + lp[0], s01 = (q0 + q3) + lp[1];
+  const float s10 = (q1 + q2) + lp[2], s11 = (q1 + q3) + lp[3];
+  const float f0 = lse2<kSumProduct>(s00, s01, T, inv_T) - q0;
+  const float f1 = lse2<kSumProduct>(s10, s11, T, inv_T) - q1;
+  const float f2 = lse2<kSumProduct>(s00, s10, T, inv_T) - q2;
+  const float f3 = lse2<kSumProduct>(s01, s11, T, inv_T) - q3;
+  float n0 = damp(m[0], f0, d, one_minus_d), n1 = damp(m[1], f1, d, one_minus_d);
+  float n2 = damp(m[2], f2, d, one_minus_d), n3 = damp(m[3], f3, d, one_minus_d);
+  const float mxa = fmaxf(n0, n1), mxb = fmaxf(n2, n3);
+  n[0] = fmaxf(n0 - mxa, kMsgNegInf); n[1] = fmaxf(n1 - mxa, kMsgNegInf);
+  n[2] = fmaxf(n2 - mxb, kMsgNegInf); n[3] = fmaxf(n3 - mxb, kMsgNegInf);
+  return fmaxf(fmaxf(fabsf(n[0] - m[0]), fabsf(n[1] - m[1])),
+               fmaxf(fabsf(n[2] - m[2]), fabsf(n[3] - m[3])));
+}
+
+// K2a: one thread per (factor, sample).
 template <bool kSumProduct>
 __global__ void __launch_bounds__(kThreads)
 k_enum_pw2(BatchMap mp, int64_t num_factors, int64_t first_edge, int64_t first_msg,
@@ -229,39 +264,163 @@ k_enum_pw2(BatchMap mp, int64_t num_factors, int64_t first_edge, int64_t first_m
   if (!L.b_ok) return;
   float dmax = 0.f;
   const int b = L.b;
+  const int64_t ld = mp.ld;
+  const float inv_T = kSumProduct ? 1.0f / T : 0.f;
   for (int64_t f = L.u; f < L.u_end; f += L.step) {
     const int64_t e = first_edge + 2 * f;
     const int64_t vs0 = edge_vs[e], vs1 = edge_vs[e + 1];
-    const int64_t mb = (first_msg + 4 * f) * mp.ld + b;
-    const float m0 = m_old[mb], m1 = m_old[mb + mp.ld], m2 = m_old[mb + 2 * mp.ld],
-                m3 = m_old[mb + 3 * mp.ld];
-    const float q0 = S[vs0 * mp.ld + b] - m0;
-    const float q1 = S[(vs0 + 1) * mp.ld + b] - m1;
-    const float q2 = S[vs1 * mp.ld + b] - m2;
-    const float q3 = S[(vs1 + 1) * mp.ld + b] - m3;
+    const int64_t mb = (first_msg + 4 * f) * ld + b;
+    const float m[4] = {m_old[mb], m_old[mb + ld], m_old[mb + 2 * ld], m_old[mb + 3 * ld]};
+    const float Sv[4] = {S[vs0 * ld + b], S[(vs0 + 1) * ld + b], S[vs1 * ld + b],
+                         S[(vs1 + 1) * ld + b]};
     const int64_t pb = first_pot + 4 * f;
-    const float s00 = (q0 + q2) + clip_lp(lp.at(pb, b));
-    const float s01 = (q0 + q3) + clip_lp(lp.at(pb + 1, b));
-    const float s10 = (q1 + q2) + clip_lp(lp.at(pb + 2, b));
-    const float s11 = (q1 + q3) + clip_lp(lp.at(pb + 3, b));
-    float f0 = fmaxf(s00, s01), f1 = fmaxf(s10, s11), f2 = fmaxf(s00, s10), f3 = fmaxf(s01, s11);
-    if (kSumProduct) {
-      f0 = T * logf(expf((s00 - f0) / T) + expf((s01 - f0) / T)) + f0;
-      f1 = T * logf(expf((s10 - f1) / T) + expf((s11 - f1) / T)) + f1;
-      f2 = T * logf(expf((s00 - f2) / T) + expf((s10 - f2) / T)) + f2;
-      f3 = T * logf(expf((s01 - f3) / T) + expf((s11 - f3) / T)) + f3;
-    }
-    f0 -= q0; f1 -= q1; f2 -= q2; f3 -= q3;
-    float n0 = damp(m0, f0, d, one_minus_d), n1 = damp(m1, f1, d, one_minus_d);
-    float n2 = damp(m2, f2, d, one_minus_d), n3 = damp(m3, f3, d, one_minus_d);
-    const float mxa = fmaxf(n0, n1), mxb = fmaxf(n2, n3);
-    n0 = fmaxf(n0 - mxa, kMsgNegInf); n1 = fmaxf(n1 - mxa, kMsgNegInf);
-    n2 = fmaxf(n2 - mxb, kMsgNegInf); n3 = fmaxf(n3 - mxb, kMsgNegInf);
-    m_new[mb] = n0; m_new[mb + mp.ld] = n1; m_new[mb + 2 * mp.ld] = n2; m_new[mb + 3 * mp.ld] = n3;
-    dmax = fmaxf(dmax, fmaxf(fmaxf(fabsf(n0 - m0), fabsf(n1 - m1)),
-                             fmaxf(fabsf(n2 - m2), fabsf(n3 - m3))));
+    const float lpv[4] = {clip_lp(lp.at(pb, b)), clip_lp(lp.at(pb + 1, b)),
+                          clip_lp(lp.at(pb + 2, b)), clip_lp(lp.at(pb + 3, b))};
+    float n[4];
+    dmax = fmaxf(dmax, pw2_update<kSumProduct>(m, Sv, lpv, d, one_minus_d, T, inv_T, n));
+    m_new[mb] = n[0]; m_new[mb + ld] = n[1]; m_new[mb + 2 * ld] = n[2]; m_new[mb + 3 * ld] = n[3];
   }
   publish_delta(deltas, int64_t(b) * delta_stride + delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
+// K2a-fused: a pairwise-binary block whose factors form a dense I x J grid,
+// factor (i, j) = row variable i x column variable j, stored row-major (the RBM
+// of benchmark/rbm_lib.py:138-169: i = hidden unit, j = visible unit).  One pass
+// per iteration: besides the new messages the kernel produces, per warp tile, the
+// partial sums of the NEW messages per variable, so that the next iteration's
+// variable sums need no second read of the message array (k_var_reduce adds the
+// partials in a fixed order: deterministic, but a tree order rather than the
+// serial ascending order of k_var_sums).
+//
+// A warp owns (sample tile of 32 lanes) x (strip of TJ columns) x (chunk of RI
+// rows): column sums S_v and the column accumulators live in registers for the
+// whole chunk, the row accumulator for one row.  The four warps of a CTA share
+// strip and chunk (their potentials are staged once in shared memory) and cover
+// four adjacent sample tiles, i.e. 512 contiguous bytes of every message row.
+// ---------------------------------------------------------------------------
+struct BipDev {
+  int64_t first_msg, first_pot;
+  int32_t I, J;          // rows, columns
+  int32_t NS, NR, RI;    // column strips, row chunks, rows per chunk
+  const int32_t* row_vs;   // [I] var-state of state 0 of row variable i
+  const int32_t* col_vs;   // [J]
+  const int32_t* row_part; // [I] partial-buffer row of (row var i, state 0, strip 0); state s, strip k at +2k+s
+  const int32_t* col_part; // [J] same for column variables / row chunks
+};
+
+constexpr int kBipWarps = 4;
+constexpr int kBipTJ = 16;
+
+template <bool kSumProduct, int TJ>
+__global__ void __launch_bounds__(kBipWarps * 32)
+k_enum_pw2_bip(int batch, int ld, int nbt_groups, BipDev g, const float* __restrict__ lp,
+               const float* __restrict__ S, const float* __restrict__ m_old,
+               float* __restrict__ m_new, float* __restrict__ part, float d, float one_minus_d,
+               float T, float* __restrict__ deltas, int64_t delta_stride, int64_t delta_off) {
+  extern __shared__ float lp_s[];  // [RI][TJ][4] clipped potentials of this (strip, chunk)
+  // blockIdx.x = (chunk * NS + strip) * nbt_groups + sample-tile group
+  const int grp = blockIdx.x % nbt_groups;
+  const int sc = blockIdx.x / nbt_groups;
+  const int js = sc % g.NS, rc = sc / g.NS;
+  const int j0 = js * TJ, i0 = rc * g.RI;
+  const int i1 = min(i0 + g.RI, g.I);
+  const int nj = min(TJ, g.J - j0);
+  for (int t = threadIdx.x; t < (i1 - i0) * TJ * 4; t += blockDim.x) {
+    const int r = t / (TJ * 4), c = t - r * (TJ * 4);
+    lp_s[t] = (c < nj * 4) ? clip_lp(lp[g.first_pot + 4 * (int64_t(i0 + r) * g.J + j0) + c]) : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = (grp * kBipWarps + w) * 32 + lane;
+  if (b >= batch) return;
+  const float inv_T = kSumProduct ? 1.0f / T : 0.f;
+  float Sc0[TJ], Sc1[TJ], ac0[TJ], ac1[TJ];
+#pragma unroll
+  for (int jj = 0; jj < TJ; ++jj) {
+    const int64_t vs = g.col_vs[min(j0 + jj, g.J - 1)];
+    Sc0[jj] = S[vs * ld + b];
+    Sc1[jj] = S[(vs + 1) * ld + b];
+    ac0[jj] = 0.f;
+    ac1[jj] = 0.f;
+  }
+  float dmax = 0.f;
+  for (int i = i0; i < i1; ++i) {
+    const int64_t rvs = g.row_vs[i];
+    const float Sr0 = S[rvs * ld + b], Sr1 = S[(rvs + 1) * ld + b];
+    const int64_t mb = (g.first_msg + 4 * (int64_t(i) * g.J + j0)) * ld + b;
+    const float* lrow = lp_s + (i - i0) * TJ * 4;
+    float mo[TJ][4];
+#pragma unroll
+    for (int jj = 0; jj < TJ; ++jj) {
+      if (jj < nj) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mo[jj][k] = m_old[mb + int64_t(4 * jj + k) * ld];
+      }
+    }
+    float ar0 = 0.f, ar1 = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < TJ; ++jj) {
+      if (jj < nj) {
+        const float Sv[4] = {Sr0, Sr1, Sc0[jj], Sc1[jj]};
+        const float lpv[4] = {lrow[4 * jj], lrow[4 * jj + 1], lrow[4 * jj + 2], lrow[4 * jj + 3]};
+        float n[4];
+        dmax = fmaxf(dmax, pw2_update<kSumProduct>(mo[jj], Sv, lpv, d, one_minus_d, T, inv_T, n));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) m_new[mb + int64_t(4 * jj + k) * ld] = n[k];
+        ar0 += n[0]; ar1 += n[1];
+        ac0[jj] += n[2]; ac1[jj] += n[3];
+      }
+    }
+    const int64_t pr = (int64_t(g.row_part[i]) + 2 * js) * ld + b;
+    part[pr] = ar0;
+    part[pr + ld] = ar1;
+  }
+#pragma unroll
+  for (int jj = 0; jj < TJ; ++jj) {
+    if (jj < nj) {
+      const int64_t pc = (int64_t(g.col_part[j0 + jj]) + 2 * rc) * ld + b;
+      part[pc] = ac0[jj];
+      part[pc + ld] = ac1[jj];
+    }
+  }
+  publish_delta(deltas, int64_t(b) * delta_stride + delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
+// K1-fused: S_v = ev_v + (messages of the edges that no fused block covers, in
+// ascending message index) + (partial sums written by the fused blocks, in
+// ascending partial row).  One thread per (var-state, sample).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_var_reduce(BatchMap mp, int64_t num_var_states, const int32_t* __restrict__ vs_var,
+             const int32_t* __restrict__ var_first_state, const int32_t* __restrict__ rest_ptr,
+             const int32_t* __restrict__ rest_edge_msg, const int32_t* __restrict__ part_first,
+             const int32_t* __restrict__ part_count, View ev, const float* __restrict__ m,
+             const float* __restrict__ part, float* __restrict__ S) {
+  UnitLoop L = unit_loop(mp, num_var_states);
+  if (!L.b_ok) return;
+  const int64_t ld = mp.ld;
+  for (int64_t v = L.u; v < L.u_end; v += L.step) {
+    const int var = vs_var[v];
+    const int64_t st = v - var_first_state[var];
+    float acc = ev.at(v, L.b);
+    for (int64_t k = rest_ptr[var]; k < rest_ptr[var + 1]; ++k)
+      acc += m[(rest_edge_msg[k] + st) * ld + L.b];
+    // partial rows of (var, state st): first + 2*k + st for binary variables
+    const int64_t p0 = part_first[var];
+    const int cnt = part_count[var];
+    int k = 0;
+    for (; k + 4 <= cnt; k += 4) {
+      const float a0 = part[(p0 + 2 * k + st) * ld + L.b];
+      const float a1 = part[(p0 + 2 * (k + 1) + st) * ld + L.b];
+      const float a2 = part[(p0 + 2 * (k + 2) + st) * ld + L.b];
+      const float a3 = part[(p0 + 2 * (k + 3) + st) * ld + L.b];
+      acc += a0; acc += a1; acc += a2; acc += a3;
+    }
+    for (; k < cnt; ++k) acc += part[(p0 + 2 * k + st) * ld + L.b];
+    S[v * ld + L.b] = acc;
+  }
 }
 
 // Device-side description of one enum block (see pgx_enum_block in pgx.h).

@@ -104,19 +104,78 @@ def test_rbm24_reference_decodings(num_iters):
     np.testing.assert_array_equal(states[visible], gold[f"visible_cpu_{num_iters}"][idx])
 
 
-@pytest.mark.parametrize("temperature", [0.0, 1.0])
-def test_rbm_batched_gumbel_vs_oracle(temperature):
+def _small_rbm(nh=12, nv=20, batch=37, temperature=0.0, scale=1.0):
   rng = np.random.default_rng(0)
-  nh, nv, batch = 12, 20, 37
-  W, bh, bv = rng.normal(size=(nh, nv)), rng.logistic(size=nh), rng.logistic(size=nv)
+  W, bh, bv = scale * rng.normal(size=(nh, nv)), rng.logistic(size=nh), rng.logistic(size=nv)
   fg, hidden, visible = models.rbm_model(W, bh, bv)
   bp = infer.BP(fg.bp_state, temperature=temperature)
   arrays = bp.init(evidence_updates={
       hidden: rng.gumbel(size=(batch, nh, 2)), visible: rng.gumbel(size=(batch, nv, 2))})
-  assert arrays.evidence.shape == (batch, 2 * (nh + nv))
+  return bp, arrays
+
+
+@pytest.mark.parametrize("temperature", [0.0, 1.0])
+def test_rbm_batched_exact_order_vs_oracle(temperature):
+  """Two-pass path (serial summation order): max-product is bit-exact with the oracle."""
+  bp, arrays = _small_rbm(temperature=temperature)
+  bp.context.plan.set_exact_order(True)
+  assert arrays.evidence.shape == (37, 2 * (12 + 20))
   _, want, want_d, got, got_d = _run_both(bp, arrays, 25, 0.5, temperature)
-  np.testing.assert_allclose(got.ftov_msgs, want, atol=1e-6 if temperature == 0 else 1e-5)
+  if temperature == 0.0:
+    np.testing.assert_array_equal(got.ftov_msgs, want)
+  np.testing.assert_allclose(got.ftov_msgs, want, atol=1e-5)
   np.testing.assert_allclose(got_d, want_d, atol=1e-5)
+
+
+@pytest.mark.parametrize("temperature", [0.0, 0.5, 1.0])
+@pytest.mark.parametrize("shape", [(12, 20, 37), (5, 33, 64), (40, 17, 100), (2, 2, 32)])
+def test_rbm_fused_single_pass_vs_oracle(temperature, shape):
+  """Dense-grid pairwise blocks, batch > 16: one pass per iteration with tiled partial
+  sums (tree summation order).  Weak couplings keep BP contractive so that rounding-order
+  differences do not amplify; tolerance = north-star 1e-5."""
+  nh, nv, batch = shape
+  bp, arrays = _small_rbm(nh, nv, batch, temperature, scale=0.3)
+  assert bp.context.plan.has_fused_blocks
+  _, want, want_d, got, got_d = _run_both(bp, arrays, 25, 0.5, temperature)
+  np.testing.assert_allclose(got.ftov_msgs, want, atol=1e-5)
+  np.testing.assert_allclose(got_d, want_d, atol=1e-5)
+  states, _, _ = bp.context.decode(got)
+  graph = bp_oracle.graph_from_context(bp.context)
+  w_states, _, _ = bp_oracle.decode_flat(graph, bp_oracle.flat_beliefs(graph, want, arrays.evidence))
+  beliefs = bp_oracle.flat_beliefs(graph, want, arrays.evidence).reshape(batch, -1, 2)
+  near_tie = np.abs(beliefs[..., 0] - beliefs[..., 1]) < 1e-4
+  assert np.array_equal(states[~near_tie], w_states[~near_tie])
+
+
+def test_rbm_full_size_fused_properties():
+  """BASELINE configs[1] shape (RBM 784 x 500) at batch 64 / 96, sum-product:
+  (1) the single-pass path agrees with the serial-order two-pass path over a short horizon
+      (var sums here are sums of ~800 terms of magnitude ~1e2: one fp32 ulp is 3e-5, and BP on
+      this model is chaotic, so only a short horizon is comparable at all);
+  (2) sharding invariance: a sample's result does not depend on its batch-mates (bit-exact);
+  (3) messages stay normalised: every edge has max 0; deltas are finite."""
+  rs = np.random.RandomState(0)
+  nh, nv = 500, 784
+  W, bh, bv = rs.normal(size=(nh, nv)), rs.logistic(size=nh), rs.logistic(size=nv)
+  fg, hidden, visible = models.rbm_model(W, bh, bv)
+  bp = infer.BP(fg.bp_state, temperature=1.0)
+  rng = np.random.default_rng(0)
+  ev_h, ev_v = rng.gumbel(size=(96, nh, 2)), rng.gumbel(size=(96, nv, 2))
+  big = bp.init(evidence_updates={hidden: ev_h, visible: ev_v})
+  small = bp.init(evidence_updates={hidden: ev_h[:64], visible: ev_v[:64]})
+  plan = bp.context.plan
+  assert plan.has_fused_blocks
+  fused2 = bp.run(small, num_iters=2, damping=0.5).ftov_msgs
+  plan.set_exact_order(True)
+  exact2 = bp.run(small, num_iters=2, damping=0.5).ftov_msgs
+  plan.set_exact_order(False)
+  assert np.max(np.abs(fused2 - exact2)) < 2e-4
+  out_small, d_small = bp.run_with_diffs(small, num_iters=6, damping=0.5)
+  out_big, d_big = bp.run_with_diffs(big, num_iters=6, damping=0.5)
+  np.testing.assert_array_equal(out_big.ftov_msgs[:64], out_small.ftov_msgs)
+  np.testing.assert_array_equal(d_big[:64], d_small)
+  edge_max = out_big.ftov_msgs.reshape(96, -1, 2).max(axis=-1)
+  assert np.all(edge_max == 0.0) and np.all(np.isfinite(d_big))
 
 
 TEMPS = [(0.0, 1e-5), (0.001, 5e-3), (0.3, 5e-3), (0.8, 1e-5)]
