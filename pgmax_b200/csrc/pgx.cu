@@ -86,7 +86,6 @@ struct LogicalPlan {
 
 struct Workspace {
   int64_t batch = 0;
-  int ld = 0;
   float *mA = nullptr, *mB = nullptr, *S = nullptr, *evT = nullptr, *lpT = nullptr, *part = nullptr;
   // staging for pgx_infer_host
   float *h_lp = nullptr, *h_ev = nullptr, *h_msgs_in = nullptr, *h_msgs_out = nullptr,
@@ -149,12 +148,16 @@ void free_workspace(Workspace& ws) {
 pgx::BatchMap make_map(int64_t batch) {
   pgx::BatchMap mp;
   mp.batch = int(batch);
-  mp.ld = batch == 1 ? 1 : int((batch + 7) / 8 * 8);
   int lg = 0;
   while ((1 << lg) < batch && lg < 5) ++lg;
   mp.bx_log = lg;
   mp.nbt = int((batch + (1 << lg) - 1) >> lg);
   return mp;
+}
+
+// Floats of a tile-blocked array with n_rows elements per sample.
+size_t tiled_floats(const pgx::BatchMap& mp, int64_t n_rows) {
+  return (size_t(std::max<int64_t>(n_rows, 1)) * mp.nbt) << mp.bx_log;
 }
 
 // Grid for a "one thread per (element, sample)" kernel: enough warps to cover the
@@ -303,22 +306,19 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
     free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT); free_dev(ws.part);
     ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = ws.part = nullptr;
     ws.batch = batch;
-    ws.ld = mp.ld;
-    const size_t nm = size_t(std::max<int64_t>(plan->num_edge_states, 1)) * mp.ld * sizeof(float);
-    const size_t nv = size_t(std::max<int64_t>(plan->num_var_states, 1)) * mp.ld * sizeof(float);
+    const size_t nm = tiled_floats(mp, plan->num_edge_states) * sizeof(float);
+    const size_t nv = tiled_floats(mp, plan->num_var_states) * sizeof(float);
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.mA), nm));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.mB), nm));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.S), nv));
+    PGX_CUDA(cudaMemset(ws.S, 0, nv));  // padded sample slots stay finite
   }
   if (need_part && ws.part == nullptr)
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.part),
-                        size_t(std::max<int64_t>(plan->part_rows, 1)) * mp.ld * sizeof(float)));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.part), tiled_floats(mp, plan->part_rows) * sizeof(float)));
   if (need_evT && ws.evT == nullptr)
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.evT),
-                        size_t(std::max<int64_t>(plan->num_var_states, 1)) * mp.ld * sizeof(float)));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.evT), tiled_floats(mp, plan->num_var_states) * sizeof(float)));
   if (need_lpT && ws.lpT == nullptr)
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.lpT),
-                        size_t(std::max<int64_t>(plan->num_potentials, 1)) * mp.ld * sizeof(float)));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.lpT), tiled_floats(mp, plan->num_potentials) * sizeof(float)));
   return PGX_OK;
 }
 
@@ -329,20 +329,19 @@ int check_launch(pgx_plan* plan, const char* what) {
   return PGX_OK;
 }
 
-int to_batch_inner(pgx_plan* plan, cudaStream_t st, const float* src, float* dst, int64_t n, int64_t batch,
-                   int ld) {
+int to_tiles(pgx_plan* plan, cudaStream_t st, const float* src, float* dst, int64_t n, const pgx::BatchMap& mp) {
   if (n == 0) return PGX_OK;
-  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((ld + 31) / 32)), block(32, 8);
-  pgx::k_to_batch_inner<<<grid, block, 0, st>>>(src, dst, n, int(batch), ld);
-  return check_launch(plan, "k_to_batch_inner");
+  const int padded = mp.nbt << mp.bx_log;
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((padded + 31) / 32)), block(32, 8);
+  pgx::k_to_tiles<<<grid, block, 0, st>>>(src, dst, n, mp);
+  return check_launch(plan, "k_to_tiles");
 }
 
-int from_batch_inner(pgx_plan* plan, cudaStream_t st, const float* src, float* dst, int64_t n, int64_t batch,
-                     int ld) {
+int from_tiles(pgx_plan* plan, cudaStream_t st, const float* src, float* dst, int64_t n, const pgx::BatchMap& mp) {
   if (n == 0) return PGX_OK;
-  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((batch + 31) / 32)), block(32, 8);
-  pgx::k_from_batch_inner<<<grid, block, 0, st>>>(src, dst, n, int(batch), ld);
-  return check_launch(plan, "k_from_batch_inner");
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((mp.batch + 31) / 32)), block(32, 8);
+  pgx::k_from_tiles<<<grid, block, 0, st>>>(src, dst, n, mp);
+  return check_launch(plan, "k_from_tiles");
 }
 
 // Records a profiling event if `id` is the plan's dominant launch.
@@ -359,8 +358,7 @@ int prof_mark(pgx_plan* plan, cudaStream_t st, int id) {
 
 template <bool kSum>
 int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::View lp, const float* S,
-               const float* m_old, float* m_new, float d, float omd, float T, float* deltas,
-               int64_t dstride, int64_t doff, bool fused) {
+               const float* m_old, float* m_new, const pgx::RunArgs& a, bool fused) {
   int rc;
   for (size_t bi = 0; bi < plan->enum_blocks.size(); ++bi) {
     EnumBlockPlan& eb = plan->enum_blocks[bi];
@@ -371,28 +369,33 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       constexpr int TJ = pgx::kBipTJ;
       const int groups = (mp.nbt + pgx::kBipWarps - 1) / pgx::kBipWarps;
       const int64_t grid = int64_t(g.NS) * g.NR * groups;
-      const size_t smem = size_t(g.RI) * TJ * 4 * sizeof(float);
+      const size_t smem = pgx::bip_smem_bytes(g.RI, TJ);
+      static bool attr_set[2] = {false, false};
+      if (!attr_set[kSum]) {
+        PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pw2_bip<kSum, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(pgx::bip_smem_bytes(32, TJ))));
+        attr_set[kSum] = true;
+      }
       pgx::k_enum_pw2_bip<kSum, TJ><<<unsigned(grid), pgx::kBipWarps * 32, smem, st>>>(
-          mp.batch, mp.ld, groups, g, lp.p, S, m_old, m_new, plan->ws.part, d, omd, T, deltas, dstride, doff);
+          mp.batch, groups, g, lp.p, S, m_old, m_new, plan->ws.part, plan->part_rows, a);
       if ((rc = check_launch(plan, "k_enum_pw2_bip"))) return rc;
       if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2_bip";
     } else if (eb.variant == kPw2) {
       pgx::k_enum_pw2<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
           mp, F, eb.dev.first_edge, eb.dev.first_msg, eb.dev.first_pot, plan->d_edge_vs, lp, S, m_old,
-          m_new, d, omd, T, deltas, dstride, doff);
+          m_new, a);
       if ((rc = check_launch(plan, "k_enum_pw2"))) return rc;
       if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2";
     } else if (eb.variant == kSmall) {
       pgx::k_enum_small<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
-          mp, eb.dev, plan->d_edge_vs, lp, S, m_old, m_new, d, omd, T, deltas, dstride, doff);
+          mp, eb.dev, plan->d_edge_vs, lp, S, m_old, m_new, a);
       if ((rc = check_launch(plan, "k_enum_small"))) return rc;
     } else {
       const size_t smem = size_t(2 * eb.dev.ns + 32) * sizeof(float);
       const int64_t units = F * mp.batch;
       const int grid = int(std::min<int64_t>(units, int64_t(plan->num_sms) * 8));
-      pgx::k_enum_big<kSum><<<grid, pgx::kThreads, smem, st>>>(mp.batch, mp.ld, eb.dev, plan->d_edge_vs,
-                                                               lp, S, m_old, m_new, d, omd, T, deltas,
-                                                               dstride, doff);
+      pgx::k_enum_big<kSum><<<grid, pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old,
+                                                               m_new, a);
       if ((rc = check_launch(plan, "k_enum_big"))) return rc;
     }
     if ((rc = prof_mark(plan, st, int(bi)))) return rc;
@@ -403,14 +406,14 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
     if (lg->dev.num_factors == 0) continue;
     if ((rc = prof_mark(plan, st, id))) return rc;
     pgx::k_logical<kSum><<<grid_for(plan, mp, lg->dev.num_factors), pgx::kThreads, 0, st>>>(
-        mp, lg->dev, S, m_old, m_new, d, omd, T, deltas, dstride, doff);
+        mp, lg->dev, S, m_old, m_new, a);
     if ((rc = check_launch(plan, "k_logical"))) return rc;
     if ((rc = prof_mark(plan, st, id))) return rc;
   }
   if (plan->pool_f.dev.num_factors > 0) {
     if ((rc = prof_mark(plan, st, -3))) return rc;
     pgx::k_pool<kSum><<<grid_for(plan, mp, plan->pool_f.dev.num_factors), pgx::kThreads, 0, st>>>(
-        mp, plan->pool_f.dev, S, m_old, m_new, d, omd, T, deltas, dstride, doff);
+        mp, plan->pool_f.dev, S, m_old, m_new, a);
     if ((rc = check_launch(plan, "k_pool"))) return rc;
     if ((rc = prof_mark(plan, st, -3))) return rc;
   }
@@ -740,7 +743,7 @@ int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch, const float* log_pot
   if ((rc = check_device(plan))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const pgx::BatchMap mp = make_map(batch);
-  PGX_CHECK(int64_t(plan->num_edge_states) * mp.ld < (int64_t(1) << 40), "workspace too large");
+  PGX_CHECK(tiled_floats(mp, plan->num_edge_states) < (size_t(1) << 40), "workspace too large");
   const bool single = batch == 1;
   const bool evT = !single && ev_batched, lpT = !single && lp_batched;
   // Single-pass mode: dense-grid pairwise blocks emit per-tile partial sums of the new
@@ -751,63 +754,75 @@ int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch, const float* log_pot
   const int64_t Es = plan->num_edge_states, Vs = plan->num_var_states, C = plan->num_potentials;
   if (Es == 0) return PGX_OK;
 
-  // ---- inputs -> batch-inner workspace ---------------------------------------------------
-  pgx::View ev{evidence, 1, 0}, lp{log_potentials, 1, 0};
+  // ---- inputs -> tile-blocked workspace ----------------------------------------------------
+  pgx::View ev{evidence, Vs, 0}, lp{log_potentials, C, 0};
   if (evT) {
-    if ((rc = to_batch_inner(plan, st, evidence, ws.evT, Vs, batch, mp.ld))) return rc;
-    ev = pgx::View{ws.evT, mp.ld, 1};
+    if ((rc = to_tiles(plan, st, evidence, ws.evT, Vs, mp))) return rc;
+    ev = pgx::View{ws.evT, Vs, 1};
   }
   if (lpT) {
-    if ((rc = to_batch_inner(plan, st, log_potentials, ws.lpT, C, batch, mp.ld))) return rc;
-    lp = pgx::View{ws.lpT, mp.ld, 1};
+    if ((rc = to_tiles(plan, st, log_potentials, ws.lpT, C, mp))) return rc;
+    lp = pgx::View{ws.lpT, C, 1};
   }
   float* cur = ws.mA;
   float* nxt = ws.mB;
   if (ftov_in == nullptr) {
-    PGX_CUDA(cudaMemsetAsync(cur, 0, size_t(Es) * mp.ld * sizeof(float), st));  // NC(0) = 0
+    PGX_CUDA(cudaMemsetAsync(cur, 0, tiled_floats(mp, Es) * sizeof(float), st));  // NC(0) = 0
   } else {
     if (single) {
       PGX_CUDA(cudaMemcpyAsync(cur, ftov_in, size_t(Es) * sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else if (msgs_batched) {
-      if ((rc = to_batch_inner(plan, st, ftov_in, cur, Es, batch, mp.ld))) return rc;
+      if ((rc = to_tiles(plan, st, ftov_in, cur, Es, mp))) return rc;
     } else {
-      pgx::k_broadcast_rows<<<plan->num_sms * 8, pgx::kThreads, 0, st>>>(ftov_in, cur, Es, mp.ld);
+      pgx::k_broadcast_rows<<<plan->num_sms * 8, pgx::kThreads, 0, st>>>(ftov_in, cur, Es, mp);
       if ((rc = check_launch(plan, "k_broadcast_rows"))) return rc;
     }
     pgx::k_normalize_edges<<<grid_for(plan, mp, plan->num_edges), pgx::kThreads, 0, st>>>(
-        mp, plan->num_edges, plan->d_edge_msg_start, cur);
+        mp, plan->num_edges, Es, plan->d_edge_msg_start, cur);
     if ((rc = check_launch(plan, "k_normalize_edges"))) return rc;
   }
   if (deltas) PGX_CUDA(cudaMemsetAsync(deltas, 0, size_t(batch) * num_iters * sizeof(float), st));
 
   // ---- iterations ------------------------------------------------------------------------
-  const float omd = 1.0f - damping;
+  pgx::RunArgs a{};
+  a.d = damping;
+  a.one_minus_d = 1.0f - damping;
+  a.T = temperature;
+  if (temperature > 0.f) {
+    a.c_exp = float(1.4426950408889634 / double(temperature));
+    a.c_log = float(0.6931471805599453 * double(temperature));
+  }
+  a.deltas = deltas;
+  a.delta_stride = num_iters;
+  a.Es = Es;
+  a.Vs = Vs;
   for (int it = 0; it < num_iters; ++it) {
+    a.delta_off = it;
     if (!fused || it == 0) {
       pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(
-          mp, Vs, plan->d_vs_var, plan->d_var_first_state, plan->d_var_ptr, plan->d_var_edge_msg, ev, cur,
+          mp, Vs, Es, plan->d_vs_var, plan->d_var_first_state, plan->d_var_ptr, plan->d_var_edge_msg, ev, cur,
           ws.S);
       if ((rc = check_launch(plan, "k_var_sums"))) return rc;
     }
     // With one sample the last iteration writes straight into the caller's buffer.
     float* dst = (single && it == num_iters - 1) ? ftov_out : nxt;
     if (temperature == 0.f)
-      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, damping, omd, temperature, deltas, num_iters, it, fused);
+      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, a, fused);
     else
-      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, damping, omd, temperature, deltas, num_iters, it, fused);
+      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, a, fused);
     if (rc) return rc;
     if (fused && it + 1 < num_iters) {
       // next iteration's variable sums from the partial sums the fused blocks just wrote
       pgx::k_var_reduce<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(
-          mp, Vs, plan->d_vs_var, plan->d_var_first_state, plan->d_rest_ptr, plan->d_rest_edge_msg,
-          plan->d_part_first, plan->d_part_count, ev, dst, ws.part, ws.S);
+          mp, Vs, Es, plan->part_rows, plan->d_vs_var, plan->d_var_first_state, plan->d_rest_ptr,
+          plan->d_rest_edge_msg, plan->d_part_first, plan->d_part_count, ev, dst, ws.part, ws.S);
       if ((rc = check_launch(plan, "k_var_reduce"))) return rc;
     }
     nxt = cur;
     cur = dst;
   }
   if (!single) {
-    if ((rc = from_batch_inner(plan, st, cur, ftov_out, Es, batch, mp.ld))) return rc;
+    if ((rc = from_tiles(plan, st, cur, ftov_out, Es, mp))) return rc;
   }
   return PGX_OK;
 }
@@ -824,8 +839,8 @@ static int decode_impl(pgx_plan* plan, cudaStream_t st, int64_t batch, const flo
   if (plan->num_vars == 0) return PGX_OK;
   const pgx::BatchMap mp = make_map(batch);
   // The ABI arrays are read in place through strided views (batch-major).
-  pgx::View ev{evidence, 1, ev_batched ? plan->num_var_states : 0};
-  pgx::View m{ftov_msgs, 1, msgs_batched ? plan->num_edge_states : 0};
+  pgx::View ev{evidence, plan->num_var_states, ev_batched ? 2 : 0};
+  pgx::View m{ftov_msgs, plan->num_edge_states, msgs_batched ? 2 : 0};
   pgx::k_decode<<<grid_for(plan, mp, plan->num_vars), pgx::kThreads, 0, st>>>(
       mp, plan->num_vars, plan->num_var_states, plan->d_var_first_state, plan->d_var_ptr,
       plan->d_var_edge_msg, ev, m, beliefs, map_out, marginals, ties);

@@ -1,18 +1,26 @@
 // pgx_kernels.cuh — sm_100a kernels of the loopy-BP hot path.
 //
-// Internal data layout ("batch-inner"): every per-sample vector x[b][n] of the
-// ABI (batch-major, as jax.vmap produces) is held as X[n][ld] with the batch
-// index fastest (ld = batch rounded up to 8 floats, or 1 when batch == 1).
-// A warp then covers 32 samples of ONE graph element, so
-//   * every index load (incidence, wiring, config tables) is warp-uniform, and
-//   * every message / evidence / var-sum access is a coalesced row segment,
-// whatever the graph's structure.  For batch == 1 the same code degenerates to
-// one graph element per lane over the reference's flat vectors.
+// Internal data layout ("tile-blocked batch-inner"): every per-sample vector
+// x[b][n] of the ABI (batch-major, as jax.vmap produces) is held as
+// X[tile][n][TW]: samples are grouped in tiles of TW = min(32, pow2ceil(B))
+// consecutive samples; inside a tile the sample index is fastest and element n
+// of the tile starts at float offset (tile * N + n) * TW.  A warp covers the TW
+// samples of 32 / TW graph elements, so
+//   * every index load (incidence, wiring, config tables) is warp-uniform per
+//     element, every message / evidence / var-sum access is a full coalesced
+//     row, whatever the graph's structure;
+//   * consecutive elements of one tile are CONTIGUOUS in memory (128 B apart
+//     for TW = 32): a factor's edge-states, and a run of factors, form one
+//     contiguous span that a single TMA bulk copy can move, and all address
+//     arithmetic is "lane pointer + (n << log2 TW)".
+// For batch == 1 this degenerates to the reference's flat vectors, one graph
+// element per lane.
 //
 // Arithmetic follows SURVEY.md App. A operation by operation (same order of
-// additions, true division by the temperature, expf/logf/log1pf/expm1f, no
-// FMA contraction: the library is compiled with -fmad=false) so that
-// max-product results are bit-comparable with the CPU oracle.
+// additions, expf/logf/log1pf/expm1f, no FMA contraction: the library is compiled
+// with -fmad=false) so that max-product results are bit-comparable with the CPU
+// oracle.  The one deliberate exception is the sum-product path of the
+// pairwise-binary kernels (see lse2 below).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -31,20 +39,38 @@ constexpr int kSmallMaxNS = 64;        // enum "small" kernel: edge-states per f
 // How threads map onto (graph element, sample) pairs.
 struct BatchMap {
   int batch;   // B
-  int ld;      // row pitch of batch-inner arrays
-  int bx_log;  // log2 of samples covered by one warp (BX = min(32, pow2ceil(B)))
-  int nbt;     // number of BX-wide sample tiles
+  int bx_log;  // log2 TW, TW = samples per tile = samples covered side by side in a warp
+  int nbt;     // number of tiles
 };
 
-// A strided view of a per-sample vector: element n of sample b is p[n*rs + b*bs].
-// (rs, bs) = (ld, 1) for batch-inner workspace arrays, (1, 0) for an array shared
-// by the whole batch that is read in place.
+// Offset (in floats) of (element 0, sample b) in a tile-blocked array of n_rows elements;
+// element n of that sample is at  off + (n << bx_log).
+__device__ __forceinline__ int64_t lane_off(const BatchMap& mp, int64_t n_rows, int b) {
+  const int bt = b >> mp.bx_log, bl = b & ((1 << mp.bx_log) - 1);
+  return ((int64_t(bt) * n_rows) << mp.bx_log) + bl;
+}
+
+// A per-sample vector as the kernels see it.  kind 0: shared by the whole batch,
+// read in place (x[n]); kind 1: tile-blocked workspace array; kind 2: the ABI's
+// batch-major array read in place (x[b * n_rows + n]).
 struct View {
   const float* p;
-  int64_t rs;
-  int64_t bs;
-  __device__ __forceinline__ float at(int64_t n, int b) const { return p[n * rs + b * bs]; }
+  int64_t n_rows;
+  int kind;
 };
+
+// The view of ONE sample: element n is q[n << sh].
+struct LaneView {
+  const float* q;
+  int sh;
+  __device__ __forceinline__ float at(int64_t n) const { return q[n << sh]; }
+};
+
+__device__ __forceinline__ LaneView lane_view(const View& v, const BatchMap& mp, int b) {
+  if (v.kind == 1) return LaneView{v.p + lane_off(mp, v.n_rows, b), mp.bx_log};
+  if (v.kind == 2) return LaneView{v.p + int64_t(b) * v.n_rows, 0};
+  return LaneView{v.p, 0};
+}
 
 struct UnitLoop {
   int b;
@@ -103,71 +129,72 @@ __device__ __forceinline__ float logminusexp_t(float x, float y, float T, float 
 }
 
 // ---------------------------------------------------------------------------
-// Layout conversion: ABI batch-major [B][N]  <->  batch-inner [N][ld]
+// Layout conversion: ABI batch-major [B][N]  <->  tile-blocked [tile][N][TW]
 // ---------------------------------------------------------------------------
-__global__ void k_to_batch_inner(const float* __restrict__ src, float* __restrict__ dst,
-                                 int64_t N, int B, int ld) {
+__global__ void k_to_tiles(const float* __restrict__ src, float* __restrict__ dst, int64_t N,
+                           BatchMap mp) {
   __shared__ float tile[32][33];
   const int64_t n0 = int64_t(blockIdx.x) * 32;
   const int b0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int b = b0 + r;
     const int64_t n = n0 + threadIdx.x;
-    tile[r][threadIdx.x] = (b < B && n < N) ? src[int64_t(b) * N + n] : 0.f;
+    tile[r][threadIdx.x] = (b < mp.batch && n < N) ? src[int64_t(b) * N + n] : 0.f;
   }
   __syncthreads();
+  const int tw = 1 << mp.bx_log;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int64_t n = n0 + r;
     const int b = b0 + threadIdx.x;
-    if (n < N && b < ld) dst[n * ld + b] = tile[threadIdx.x][r];
+    if (n < N && b < mp.nbt * tw) dst[lane_off(mp, N, b) + (n << mp.bx_log)] = tile[threadIdx.x][r];
   }
 }
 
-__global__ void k_from_batch_inner(const float* __restrict__ src, float* __restrict__ dst,
-                                   int64_t N, int B, int ld) {
+__global__ void k_from_tiles(const float* __restrict__ src, float* __restrict__ dst, int64_t N,
+                             BatchMap mp) {
   __shared__ float tile[32][33];
   const int64_t n0 = int64_t(blockIdx.x) * 32;
   const int b0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int64_t n = n0 + r;
     const int b = b0 + threadIdx.x;
-    tile[r][threadIdx.x] = (n < N && b < B) ? src[n * ld + b] : 0.f;
+    tile[r][threadIdx.x] = (n < N && b < mp.batch) ? src[lane_off(mp, N, b) + (n << mp.bx_log)] : 0.f;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int b = b0 + r;
     const int64_t n = n0 + threadIdx.x;
-    if (b < B && n < N) dst[int64_t(b) * N + n] = tile[threadIdx.x][r];
+    if (b < mp.batch && n < N) dst[int64_t(b) * N + n] = tile[threadIdx.x][r];
   }
 }
 
-// Broadcast a shared [N] vector into batch-inner [N][ld] (messages given once for the batch).
+// Broadcast a shared [N] vector into every sample of a tile-blocked array.
 __global__ void k_broadcast_rows(const float* __restrict__ src, float* __restrict__ dst,
-                                 int64_t N, int ld) {
-  const int64_t total = N * ld;
+                                 int64_t N, BatchMap mp) {
+  const int64_t per_tile = N << mp.bx_log;
+  const int64_t total = per_tile * mp.nbt;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x)
-    dst[i] = src[i / ld];
+    dst[i] = src[(i % per_tile) >> mp.bx_log];
 }
 
 // ---------------------------------------------------------------------------
 // normalize_and_clip_msgs applied to the INPUT messages (pgmax/infer/bp.py:92-96,
 // 249-259): per edge subtract the max over its states, clip below at -1e32.
-// In place on the batch-inner buffer.
+// In place on the tile-blocked buffer.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_normalize_edges(BatchMap mp, int64_t num_edges, const int32_t* __restrict__ edge_msg_start,
-                  float* __restrict__ m) {
+k_normalize_edges(BatchMap mp, int64_t num_edges, int64_t Es,
+                  const int32_t* __restrict__ edge_msg_start, float* __restrict__ m) {
   UnitLoop L = unit_loop(mp, num_edges);
   if (!L.b_ok) return;
+  float* mL = m + lane_off(mp, Es, L.b);
+  const int sh = mp.bx_log;
   for (int64_t e = L.u; e < L.u_end; e += L.step) {
     const int64_t s0 = edge_msg_start[e], s1 = edge_msg_start[e + 1];
     float mx = -INFINITY;
-    for (int64_t s = s0; s < s1; ++s) mx = fmaxf(mx, m[s * mp.ld + L.b]);
-    for (int64_t s = s0; s < s1; ++s) {
-      float* p = m + s * mp.ld + L.b;
-      *p = fmaxf(*p - mx, kMsgNegInf);
-    }
+    for (int64_t s = s0; s < s1; ++s) mx = fmaxf(mx, mL[s << sh]);
+    for (int64_t s = s0; s < s1; ++s) mL[s << sh] = fmaxf(mL[s << sh] - mx, kMsgNegInf);
   }
 }
 
@@ -178,27 +205,31 @@ k_normalize_edges(BatchMap mp, int64_t num_edges, const int32_t* __restrict__ ed
 // walking the variable's incident-edge list (CSR built by the plan).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_var_sums(BatchMap mp, int64_t num_var_states, const int32_t* __restrict__ vs_var,
+k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int32_t* __restrict__ vs_var,
            const int32_t* __restrict__ var_first_state, const int32_t* __restrict__ var_ptr,
            const int32_t* __restrict__ var_edge_msg, View ev, const float* __restrict__ m,
            float* __restrict__ S) {
   UnitLoop L = unit_loop(mp, num_var_states);
   if (!L.b_ok) return;
+  const LaneView evL = lane_view(ev, mp, L.b);
+  const float* mL = m + lane_off(mp, Es, L.b);
+  float* SL = S + lane_off(mp, num_var_states, L.b);
+  const int sh = mp.bx_log;
   for (int64_t v = L.u; v < L.u_end; v += L.step) {
     const int var = vs_var[v];
     const int64_t st = v - var_first_state[var];
     const int64_t k0 = var_ptr[var], k1 = var_ptr[var + 1];
-    float acc = ev.at(v, L.b);
+    float acc = evL.at(v);
     int64_t k = k0;
     for (; k + 4 <= k1; k += 4) {  // loads are independent of the running sum
-      const float a0 = m[(var_edge_msg[k] + st) * mp.ld + L.b];
-      const float a1 = m[(var_edge_msg[k + 1] + st) * mp.ld + L.b];
-      const float a2 = m[(var_edge_msg[k + 2] + st) * mp.ld + L.b];
-      const float a3 = m[(var_edge_msg[k + 3] + st) * mp.ld + L.b];
+      const float a0 = mL[(var_edge_msg[k] + st) << sh];
+      const float a1 = mL[(var_edge_msg[k + 1] + st) << sh];
+      const float a2 = mL[(var_edge_msg[k + 2] + st) << sh];
+      const float a3 = mL[(var_edge_msg[k + 3] + st) << sh];
       acc += a0; acc += a1; acc += a2; acc += a3;
     }
-    for (; k < k1; ++k) acc += m[(var_edge_msg[k] + st) * mp.ld + L.b];
-    S[v * mp.ld + L.b] = acc;
+    for (; k < k1; ++k) acc += mL[(var_edge_msg[k] + st) << sh];
+    SL[v << sh] = acc;
   }
 }
 
@@ -210,23 +241,49 @@ __device__ __forceinline__ float damp(float m_old, float f, float d, float one_m
   return d * m_old + one_minus_d * f;
 }
 
+// Scalars of one run shared by every factor->variable kernel.
+struct RunArgs {
+  float d, one_minus_d;  // damping
+  float T;               // temperature
+  float c_exp, c_log;    // log2(e) / T and T * ln(2) (fast pairwise sum-product path)
+  float* deltas;         // [batch][delta_stride] or null
+  int64_t delta_stride, delta_off;
+  int64_t Es, Vs;        // rows of the message / var-sum arrays
+};
+
 // ---------------------------------------------------------------------------
 // Pairwise binary EnumFactor with all 4 configurations valid (PairwiseFactorGroup
 // over binary variables: Ising, RBM).  Everything in registers.
 //   s_k = (q_a + q_b) + lp_k;  M_e = max over the 2 configs containing e;
 //   T = 0: f_e = M_e - q_e;  T > 0: f_e = (T log sum exp((s_k - M_e)/T) + M_e) - q_e
 // (pgmax/factor/enum.py:451-475, update_utils.py:68-98.)  With two terms the sum is
-// exp(0) + exp((min - max)/T) = 1 + e exactly as the reference forms it, so one
-// expf per edge-state suffices; (min - max)/T is evaluated as (min - max) * (1/T)
-// (exact for T = 1; one extra rounding of the exponent otherwise, far inside the
-// 1e-5 sum-product tolerance).
+// exp(0) + exp((min - max)/T) = 1 + e, exactly as the reference forms it.
+// This is the one place the library trades the last bits for speed: the pair
+// kernels are bandwidth-bound only if the four softplus terms per factor are
+// cheap, so e and log(1 + e) use the hardware ex2 / lg2 units
+// (e = ex2((min - max) * log2(e)/T), relative error 2^-22; lg2 on (1, 2] has
+// absolute error <= 2^-22, i.e. <= 1.7e-7 * T on the message) instead of the
+// ~33-instruction expf / logf pair.  Messages are O(1..10), where one fp32 ulp is
+// 1e-7..1e-6, and the north-star tolerance for sum-product is 1e-5.
+// Max-product (T = 0) involves no transcendental and stays bit-exact.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <bool kSumProduct>
-__device__ __forceinline__ float lse2(float a, float b, float T, float inv_T) {
+__device__ __forceinline__ float lse2(float a, float b, float c_exp, float c_log) {
   const float mx = fmaxf(a, b);
   if (!kSumProduct) return mx;
   const float mn = fminf(a, b);
-  return T * logf(1.0f + expf((mn - mx) * inv_T)) + mx;
+  return __fmaf_rn(c_log, lg2_approx(1.0f + ex2_approx((mn - mx) * c_exp)), mx);
 }
 
 // In: old messages m[4] = (v0s0, v0s1, v1s0, v1s1), var sums S[4] of the same
@@ -234,17 +291,17 @@ __device__ __forceinline__ float lse2(float a, float b, float T, float inv_T) {
 // Out: n[4] damped + normalised + clipped; returns max|n - m|.
 template <bool kSumProduct>
 __device__ __forceinline__ float pw2_update(const float (&m)[4], const float (&Sv)[4],
-                                            const float (&lp)[4], float d, float one_minus_d,
-                                            float T, float inv_T, float (&n)[4]) {
+                                            const float (&lp)[4], const RunArgs& a,
+                                            float (&n)[4]) {
   const float q0 = Sv[0] - m[0], q1 = Sv[1] - m[1], q2 = Sv[2] - m[2], q3 = Sv[3] - m[3];
   const float s00 = (q0 + q2) + lp[0], s01 = (q0 + q3) + lp[1];
   const float s10 = (q1 + q2) + lp[2], s11 = (q1 + q3) + lp[3];
-  const float f0 = lse2<kSumProduct>(s00, s01, T, inv_T) - q0;
-  const float f1 = lse2<kSumProduct>(s10, s11, T, inv_T) - q1;
-  const float f2 = lse2<kSumProduct>(s00, s10, T, inv_T) - q2;
-  const float f3 = lse2<kSumProduct>(s01, s11, T, inv_T) - q3;
-  float n0 = damp(m[0], f0, d, one_minus_d), n1 = damp(m[1], f1, d, one_minus_d);
-  float n2 = damp(m[2], f2, d, one_minus_d), n3 = damp(m[3], f3, d, one_minus_d);
+  const float f0 = lse2<kSumProduct>(s00, s01, a.c_exp, a.c_log) - q0;
+  const float f1 = lse2<kSumProduct>(s10, s11, a.c_exp, a.c_log) - q1;
+  const float f2 = lse2<kSumProduct>(s00, s10, a.c_exp, a.c_log) - q2;
+  const float f3 = lse2<kSumProduct>(s01, s11, a.c_exp, a.c_log) - q3;
+  const float n0 = damp(m[0], f0, a.d, a.one_minus_d), n1 = damp(m[1], f1, a.d, a.one_minus_d);
+  const float n2 = damp(m[2], f2, a.d, a.one_minus_d), n3 = damp(m[3], f3, a.d, a.one_minus_d);
   const float mxa = fmaxf(n0, n1), mxb = fmaxf(n2, n3);
   n[0] = fmaxf(n0 - mxa, kMsgNegInf); n[1] = fmaxf(n1 - mxa, kMsgNegInf);
   n[2] = fmaxf(n2 - mxb, kMsgNegInf); n[3] = fmaxf(n3 - mxb, kMsgNegInf);
@@ -258,29 +315,78 @@ __global__ void __launch_bounds__(kThreads)
 k_enum_pw2(BatchMap mp, int64_t num_factors, int64_t first_edge, int64_t first_msg,
            int64_t first_pot, const int32_t* __restrict__ edge_vs, View lp,
            const float* __restrict__ S, const float* __restrict__ m_old,
-           float* __restrict__ m_new, float d, float one_minus_d, float T,
-           float* __restrict__ deltas, int64_t delta_stride, int64_t delta_off) {
+           float* __restrict__ m_new, RunArgs a) {
   UnitLoop L = unit_loop(mp, num_factors);
   if (!L.b_ok) return;
   float dmax = 0.f;
-  const int b = L.b;
-  const int64_t ld = mp.ld;
-  const float inv_T = kSumProduct ? 1.0f / T : 0.f;
+  const int sh = mp.bx_log;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const LaneView lpL = lane_view(lp, mp, L.b);
   for (int64_t f = L.u; f < L.u_end; f += L.step) {
     const int64_t e = first_edge + 2 * f;
     const int64_t vs0 = edge_vs[e], vs1 = edge_vs[e + 1];
-    const int64_t mb = (first_msg + 4 * f) * ld + b;
-    const float m[4] = {m_old[mb], m_old[mb + ld], m_old[mb + 2 * ld], m_old[mb + 3 * ld]};
-    const float Sv[4] = {S[vs0 * ld + b], S[(vs0 + 1) * ld + b], S[vs1 * ld + b],
-                         S[(vs1 + 1) * ld + b]};
+    const int64_t mb = first_msg + 4 * f;
+    const float m[4] = {mo[mb << sh], mo[(mb + 1) << sh], mo[(mb + 2) << sh], mo[(mb + 3) << sh]};
+    const float Sv[4] = {SL[vs0 << sh], SL[(vs0 + 1) << sh], SL[vs1 << sh], SL[(vs1 + 1) << sh]};
     const int64_t pb = first_pot + 4 * f;
-    const float lpv[4] = {clip_lp(lp.at(pb, b)), clip_lp(lp.at(pb + 1, b)),
-                          clip_lp(lp.at(pb + 2, b)), clip_lp(lp.at(pb + 3, b))};
+    const float lpv[4] = {clip_lp(lpL.at(pb)), clip_lp(lpL.at(pb + 1)), clip_lp(lpL.at(pb + 2)),
+                          clip_lp(lpL.at(pb + 3))};
     float n[4];
-    dmax = fmaxf(dmax, pw2_update<kSumProduct>(m, Sv, lpv, d, one_minus_d, T, inv_T, n));
-    m_new[mb] = n[0]; m_new[mb + ld] = n[1]; m_new[mb + 2 * ld] = n[2]; m_new[mb + 3 * ld] = n[3];
+    dmax = fmaxf(dmax, pw2_update<kSumProduct>(m, Sv, lpv, a, n));
+    mn[mb << sh] = n[0]; mn[(mb + 1) << sh] = n[1]; mn[(mb + 2) << sh] = n[2]; mn[(mb + 3) << sh] = n[3];
   }
-  publish_delta(deltas, int64_t(b) * delta_stride + delta_off, dmax);
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier helpers, sm_90+ PTX.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+// global -> shared, completion signalled on `bar` (complete_tx::bytes)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global, tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+               "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------
@@ -293,11 +399,16 @@ k_enum_pw2(BatchMap mp, int64_t num_factors, int64_t first_edge, int64_t first_m
 // partials in a fixed order: deterministic, but a tree order rather than the
 // serial ascending order of k_var_sums).
 //
-// A warp owns (sample tile of 32 lanes) x (strip of TJ columns) x (chunk of RI
-// rows): column sums S_v and the column accumulators live in registers for the
-// whole chunk, the row accumulator for one row.  The four warps of a CTA share
-// strip and chunk (their potentials are staged once in shared memory) and cover
-// four adjacent sample tiles, i.e. 512 contiguous bytes of every message row.
+// A warp owns (one tile of 32 samples) x (strip of TJ columns) x (chunk of RI
+// rows).  In the tile-blocked layout the messages of TJ consecutive factors of
+// one row are ONE contiguous span of TJ*4*128 B (8 KiB for TJ = 16): the warp
+// streams its chunk row by row through a private ring of kBipStages shared-memory
+// buffers with TMA bulk copies (global -> shared on an mbarrier; shared -> global
+// as a bulk group), updates each row in place in shared memory, and never holds a
+// message in a long-latency register load.  Column sums S_v and the column
+// accumulators live in registers for the whole chunk, the row accumulator for
+// one row.  The four warps of a CTA share strip and chunk (their potentials are
+// staged once in shared memory) and cover four sample tiles.
 // ---------------------------------------------------------------------------
 struct BipDev {
   int64_t first_msg, first_pot;
@@ -311,14 +422,26 @@ struct BipDev {
 
 constexpr int kBipWarps = 4;
 constexpr int kBipTJ = 16;
+constexpr int kBipStages = 3;
+
+// dynamic shared memory of k_enum_pw2_bip
+__host__ __device__ constexpr size_t bip_smem_bytes(int RI, int TJ) {
+  return size_t(kBipWarps) * kBipStages * TJ * 4 * 32 * sizeof(float)  // rings
+         + size_t(RI) * TJ * 4 * sizeof(float)                         // potentials
+         + size_t(kBipWarps) * kBipStages * sizeof(uint64_t);          // mbarriers
+}
 
 template <bool kSumProduct, int TJ>
 __global__ void __launch_bounds__(kBipWarps * 32)
-k_enum_pw2_bip(int batch, int ld, int nbt_groups, BipDev g, const float* __restrict__ lp,
+k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp,
                const float* __restrict__ S, const float* __restrict__ m_old,
-               float* __restrict__ m_new, float* __restrict__ part, float d, float one_minus_d,
-               float T, float* __restrict__ deltas, int64_t delta_stride, int64_t delta_off) {
-  extern __shared__ float lp_s[];  // [RI][TJ][4] clipped potentials of this (strip, chunk)
+               float* __restrict__ m_new, float* __restrict__ part, int64_t part_rows, RunArgs a) {
+  constexpr int kRowFloats = TJ * 4 * 32;  // one row of a strip for one sample tile
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* ring = reinterpret_cast<float*>(smem_raw);
+  float* lp_s = ring + kBipWarps * kBipStages * kRowFloats;  // [RI][TJ][4]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(lp_s + g.RI * TJ * 4);
+
   // blockIdx.x = (chunk * NS + strip) * nbt_groups + sample-tile group
   const int grp = blockIdx.x % nbt_groups;
   const int sc = blockIdx.x / nbt_groups;
@@ -326,65 +449,111 @@ k_enum_pw2_bip(int batch, int ld, int nbt_groups, BipDev g, const float* __restr
   const int j0 = js * TJ, i0 = rc * g.RI;
   const int i1 = min(i0 + g.RI, g.I);
   const int nj = min(TJ, g.J - j0);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int bt = grp * kBipWarps + w;        // sample tile of this warp
+  const bool active = bt * 32 < batch;       // whole warp in or out
+  const int b = bt * 32 + lane;
+
+  if (threadIdx.x < kBipWarps * kBipStages) mbar_init(&bars[threadIdx.x], 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (int t = threadIdx.x; t < (i1 - i0) * TJ * 4; t += blockDim.x) {
     const int r = t / (TJ * 4), c = t - r * (TJ * 4);
     lp_s[t] = (c < nj * 4) ? clip_lp(lp[g.first_pot + 4 * (int64_t(i0 + r) * g.J + j0) + c]) : 0.f;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int b = (grp * kBipWarps + w) * 32 + lane;
-  if (b >= batch) return;
-  const float inv_T = kSumProduct ? 1.0f / T : 0.f;
+  if (!active) return;
+
+  float* my_ring = ring + w * kBipStages * kRowFloats;
+  uint64_t* my_bar = bars + w * kBipStages;
+  const uint32_t row_bytes = uint32_t(nj) * 4 * 32 * sizeof(float);
+  // global float offset of (row i, first factor of the strip) for this sample tile
+  const int64_t tile_base = (int64_t(bt) * a.Es + g.first_msg) * 32;
+  auto row_off = [&](int i) { return tile_base + (int64_t(i) * g.J + j0) * (4 * 32); };
+  const int nrows = i1 - i0;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kBipStages - 1; ++s)
+      if (s < nrows) {
+        mbar_expect_tx(&my_bar[s], row_bytes);
+        bulk_g2s(my_ring + s * kRowFloats, m_old + row_off(i0 + s), row_bytes, &my_bar[s]);
+      }
+  }
+
+  const float* SL = S + (int64_t(bt) * a.Vs) * 32 + lane;
+  float* PL = part + (int64_t(bt) * part_rows) * 32 + lane;
   float Sc0[TJ], Sc1[TJ], ac0[TJ], ac1[TJ];
 #pragma unroll
   for (int jj = 0; jj < TJ; ++jj) {
     const int64_t vs = g.col_vs[min(j0 + jj, g.J - 1)];
-    Sc0[jj] = S[vs * ld + b];
-    Sc1[jj] = S[(vs + 1) * ld + b];
+    Sc0[jj] = SL[vs * 32];
+    Sc1[jj] = SL[(vs + 1) * 32];
     ac0[jj] = 0.f;
     ac1[jj] = 0.f;
   }
   float dmax = 0.f;
-  for (int i = i0; i < i1; ++i) {
-    const int64_t rvs = g.row_vs[i];
-    const float Sr0 = S[rvs * ld + b], Sr1 = S[(rvs + 1) * ld + b];
-    const int64_t mb = (g.first_msg + 4 * (int64_t(i) * g.J + j0)) * ld + b;
-    const float* lrow = lp_s + (i - i0) * TJ * 4;
-    float mo[TJ][4];
-#pragma unroll
-    for (int jj = 0; jj < TJ; ++jj) {
-      if (jj < nj) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) mo[jj][k] = m_old[mb + int64_t(4 * jj + k) * ld];
-      }
+  int64_t rvs = g.row_vs[i0];
+  float Sr0 = SL[rvs * 32], Sr1 = SL[(rvs + 1) * 32];
+  for (int r = 0; r < nrows; ++r) {
+    const int i = i0 + r;
+    const int stage = r % kBipStages;
+    float* buf = my_ring + stage * kRowFloats + lane;
+    // row sums of the NEXT row: issue the loads before waiting on this row's data
+    float nSr0 = 0.f, nSr1 = 0.f;
+    if (r + 1 < nrows) {
+      rvs = g.row_vs[i + 1];
+      nSr0 = SL[rvs * 32];
+      nSr1 = SL[(rvs + 1) * 32];
     }
+    mbar_wait(&my_bar[stage], (r / kBipStages) & 1);
+    const float* lrow = lp_s + r * TJ * 4;
     float ar0 = 0.f, ar1 = 0.f;
 #pragma unroll
     for (int jj = 0; jj < TJ; ++jj) {
       if (jj < nj) {
+        const float4 lq = *reinterpret_cast<const float4*>(lrow + 4 * jj);
+        const float mo[4] = {buf[(4 * jj) * 32], buf[(4 * jj + 1) * 32], buf[(4 * jj + 2) * 32],
+                             buf[(4 * jj + 3) * 32]};
         const float Sv[4] = {Sr0, Sr1, Sc0[jj], Sc1[jj]};
-        const float lpv[4] = {lrow[4 * jj], lrow[4 * jj + 1], lrow[4 * jj + 2], lrow[4 * jj + 3]};
+        const float lpv[4] = {lq.x, lq.y, lq.z, lq.w};
         float n[4];
-        dmax = fmaxf(dmax, pw2_update<kSumProduct>(mo[jj], Sv, lpv, d, one_minus_d, T, inv_T, n));
+        dmax = fmaxf(dmax, pw2_update<kSumProduct>(mo, Sv, lpv, a, n));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) m_new[mb + int64_t(4 * jj + k) * ld] = n[k];
+        for (int k = 0; k < 4; ++k) buf[(4 * jj + k) * 32] = n[k];
         ar0 += n[0]; ar1 += n[1];
         ac0[jj] += n[2]; ac1[jj] += n[3];
       }
     }
-    const int64_t pr = (int64_t(g.row_part[i]) + 2 * js) * ld + b;
-    part[pr] = ar0;
-    part[pr + ld] = ar1;
+    const int64_t pr = (int64_t(g.row_part[i]) + 2 * js) * 32;
+    PL[pr] = ar0;
+    PL[pr + 32] = ar1;
+    // the row is final in shared memory: hand it to the async proxy and store it
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(m_new + row_off(i), my_ring + stage * kRowFloats, row_bytes);
+      bulk_commit();
+      // refill the stage the PREVIOUS row used once its store has drained
+      const int nr = r + kBipStages - 1;
+      if (nr < nrows) {
+        bulk_wait_read<1>();
+        const int ns = nr % kBipStages;
+        mbar_expect_tx(&my_bar[ns], row_bytes);
+        bulk_g2s(my_ring + ns * kRowFloats, m_old + row_off(i0 + nr), row_bytes, &my_bar[ns]);
+      }
+    }
+    Sr0 = nSr0;
+    Sr1 = nSr1;
   }
 #pragma unroll
   for (int jj = 0; jj < TJ; ++jj) {
     if (jj < nj) {
-      const int64_t pc = (int64_t(g.col_part[j0 + jj]) + 2 * rc) * ld + b;
-      part[pc] = ac0[jj];
-      part[pc + ld] = ac1[jj];
+      const int64_t pc = (int64_t(g.col_part[j0 + jj]) + 2 * rc) * 32;
+      PL[pc] = ac0[jj];
+      PL[pc + 32] = ac1[jj];
     }
   }
-  publish_delta(deltas, int64_t(b) * delta_stride + delta_off, dmax);
+  if (b < batch) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+  if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the pending stores
 }
 
 // ---------------------------------------------------------------------------
@@ -393,33 +562,37 @@ k_enum_pw2_bip(int batch, int ld, int nbt_groups, BipDev g, const float* __restr
 // ascending partial row).  One thread per (var-state, sample).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_var_reduce(BatchMap mp, int64_t num_var_states, const int32_t* __restrict__ vs_var,
-             const int32_t* __restrict__ var_first_state, const int32_t* __restrict__ rest_ptr,
-             const int32_t* __restrict__ rest_edge_msg, const int32_t* __restrict__ part_first,
-             const int32_t* __restrict__ part_count, View ev, const float* __restrict__ m,
-             const float* __restrict__ part, float* __restrict__ S) {
+k_var_reduce(BatchMap mp, int64_t num_var_states, int64_t Es, int64_t part_rows,
+             const int32_t* __restrict__ vs_var, const int32_t* __restrict__ var_first_state,
+             const int32_t* __restrict__ rest_ptr, const int32_t* __restrict__ rest_edge_msg,
+             const int32_t* __restrict__ part_first, const int32_t* __restrict__ part_count, View ev,
+             const float* __restrict__ m, const float* __restrict__ part, float* __restrict__ S) {
   UnitLoop L = unit_loop(mp, num_var_states);
   if (!L.b_ok) return;
-  const int64_t ld = mp.ld;
+  const LaneView evL = lane_view(ev, mp, L.b);
+  const float* mL = m + lane_off(mp, Es, L.b);
+  const float* PL = part + lane_off(mp, part_rows, L.b);
+  float* SL = S + lane_off(mp, num_var_states, L.b);
+  const int sh = mp.bx_log;
   for (int64_t v = L.u; v < L.u_end; v += L.step) {
     const int var = vs_var[v];
     const int64_t st = v - var_first_state[var];
-    float acc = ev.at(v, L.b);
+    float acc = evL.at(v);
     for (int64_t k = rest_ptr[var]; k < rest_ptr[var + 1]; ++k)
-      acc += m[(rest_edge_msg[k] + st) * ld + L.b];
-    // partial rows of (var, state st): first + 2*k + st for binary variables
-    const int64_t p0 = part_first[var];
+      acc += mL[(rest_edge_msg[k] + st) << sh];
+    // partial rows of (var, state st): first + 2*k + st (fused blocks hold binary variables)
+    const int64_t p0 = part_first[var] + st;
     const int cnt = part_count[var];
     int k = 0;
     for (; k + 4 <= cnt; k += 4) {
-      const float a0 = part[(p0 + 2 * k + st) * ld + L.b];
-      const float a1 = part[(p0 + 2 * (k + 1) + st) * ld + L.b];
-      const float a2 = part[(p0 + 2 * (k + 2) + st) * ld + L.b];
-      const float a3 = part[(p0 + 2 * (k + 3) + st) * ld + L.b];
+      const float a0 = PL[(p0 + 2 * k) << sh];
+      const float a1 = PL[(p0 + 2 * (k + 1)) << sh];
+      const float a2 = PL[(p0 + 2 * (k + 2)) << sh];
+      const float a3 = PL[(p0 + 2 * (k + 3)) << sh];
       acc += a0; acc += a1; acc += a2; acc += a3;
     }
-    for (; k < cnt; ++k) acc += part[(p0 + 2 * k + st) * ld + L.b];
-    S[v * ld + L.b] = acc;
+    for (; k < cnt; ++k) acc += PL[(p0 + 2 * k) << sh];
+    SL[v << sh] = acc;
   }
 }
 
@@ -448,22 +621,27 @@ template <bool kSumProduct>
 __global__ void __launch_bounds__(kThreads)
 k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
              const float* __restrict__ S, const float* __restrict__ m_old,
-             float* __restrict__ m_new, float d, float one_minus_d, float T,
-             float* __restrict__ deltas, int64_t delta_stride, int64_t delta_off) {
+             float* __restrict__ m_new, RunArgs a) {
   UnitLoop L = unit_loop(mp, blk.num_factors);
   if (!L.b_ok) return;
   float dmax = 0.f;
-  const int b = L.b;
+  const int sh = mp.bx_log;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const LaneView lpL = lane_view(lp, mp, L.b);
+  const float T = a.T;
   float q[kSmallMaxNS];
   float nv[kSmallMaxNS];
   for (int64_t f = L.u; f < L.u_end; f += L.step) {
     const int64_t mbase = blk.first_msg + f * blk.ns;
     const int64_t ebase = blk.first_edge + f * blk.arity;
     const int64_t pbase = blk.first_pot + f * blk.num_configs;
-    for (int a = 0; a < blk.arity; ++a) {
-      const int64_t vs = edge_vs[ebase + a];
-      for (int s = blk.edge_off[a]; s < blk.edge_off[a + 1]; ++s)
-        q[s] = S[(vs + s - blk.edge_off[a]) * mp.ld + b] - m_old[(mbase + s) * mp.ld + b];
+    for (int e = 0; e < blk.arity; ++e) {
+      const int64_t vs = edge_vs[ebase + e];
+      for (int s = blk.edge_off[e]; s < blk.edge_off[e + 1]; ++s)
+        q[s] = SL[(vs + s - blk.edge_off[e]) << sh] - mo[(mbase + s) << sh];
     }
     for (int s = 0; s < blk.ns; ++s) {
       const int j0 = blk.t_ptr[s], j1 = blk.t_ptr[s + 1];
@@ -471,8 +649,8 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
       for (int j = j0; j < j1; ++j) {
         const int k = blk.t_k[j];
         float sk = 0.f;
-        for (int a = 0; a < blk.arity; ++a) sk += q[blk.cfg_es[k * blk.arity + a]];
-        sk += clip_lp(lp.at(pbase + k, b));
+        for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
+        sk += clip_lp(lpL.at(pbase + k));
         M = fmaxf(M, sk);
       }
       float val = M;
@@ -481,27 +659,27 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
         for (int j = j0; j < j1; ++j) {
           const int k = blk.t_k[j];
           float sk = 0.f;
-          for (int a = 0; a < blk.arity; ++a) sk += q[blk.cfg_es[k * blk.arity + a]];
-          sk += clip_lp(lp.at(pbase + k, b));
+          for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
+          sk += clip_lp(lpL.at(pbase + k));
           sum += expf((sk - M) / T);
         }
         val = T * logf(sum) + M;
       }
-      nv[s] = damp(m_old[(mbase + s) * mp.ld + b], val - q[s], d, one_minus_d);
+      nv[s] = damp(mo[(mbase + s) << sh], val - q[s], a.d, a.one_minus_d);
     }
-    for (int a = 0; a < blk.arity; ++a) {
-      const int s0 = blk.edge_off[a], s1 = blk.edge_off[a + 1];
+    for (int e = 0; e < blk.arity; ++e) {
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
       float mx = -INFINITY;
       for (int s = s0; s < s1; ++s) mx = fmaxf(mx, nv[s]);
       for (int s = s0; s < s1; ++s) {
         const float out = fmaxf(nv[s] - mx, kMsgNegInf);
-        const int64_t idx = (mbase + s) * mp.ld + b;
-        dmax = fmaxf(dmax, fabsf(out - m_old[idx]));
-        m_new[idx] = out;
+        const int64_t idx = (mbase + s) << sh;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
       }
     }
   }
-  publish_delta(deltas, int64_t(b) * delta_stride + delta_off, dmax);
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
 }
 
 // ---------------------------------------------------------------------------
@@ -524,27 +702,33 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 
 template <bool kSumProduct>
 __global__ void __launch_bounds__(kThreads)
-k_enum_big(int batch, int ld, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
+k_enum_big(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
            const float* __restrict__ S, const float* __restrict__ m_old,
-           float* __restrict__ m_new, float d, float one_minus_d, float T,
-           float* __restrict__ deltas, int64_t delta_stride, int64_t delta_off) {
+           float* __restrict__ m_new, RunArgs a) {
   extern __shared__ float smem[];
   float* q = smem;
   float* nv = smem + blk.ns;
   float* red = smem + 2 * blk.ns;
-  const int64_t total = blk.num_factors * batch;
+  const int sh = mp.bx_log;
+  const float T = a.T;
+  const int64_t total = blk.num_factors * mp.batch;
   for (int64_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
-    const int64_t f = unit / batch;
-    const int b = int(unit - f * batch);
+    const int64_t f = unit / mp.batch;
+    const int b = int(unit - f * mp.batch);
+    const int64_t moff = lane_off(mp, a.Es, b);
+    const float* mo = m_old + moff;
+    float* mn = m_new + moff;
+    const float* SL = S + lane_off(mp, a.Vs, b);
+    const LaneView lpL = lane_view(lp, mp, b);
     const int64_t mbase = blk.first_msg + f * blk.ns;
     const int64_t ebase = blk.first_edge + f * blk.arity;
     const int64_t pbase = blk.first_pot + f * blk.num_configs;
     __syncthreads();  // previous unit done with q / nv
-    for (int a = 0; a < blk.arity; ++a) {
-      const int64_t vs = edge_vs[ebase + a];
-      const int s0 = blk.edge_off[a], s1 = blk.edge_off[a + 1];
+    for (int e = 0; e < blk.arity; ++e) {
+      const int64_t vs = edge_vs[ebase + e];
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
       for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x)
-        q[s] = S[(vs + s - s0) * ld + b] - m_old[(mbase + s) * ld + b];
+        q[s] = SL[(vs + s - s0) << sh] - mo[(mbase + s) << sh];
     }
     __syncthreads();
     for (int s = threadIdx.x; s < blk.ns; s += blockDim.x) {
@@ -553,8 +737,8 @@ k_enum_big(int batch, int ld, EnumBlockDev blk, const int32_t* __restrict__ edge
       for (int j = j0; j < j1; ++j) {
         const int k = blk.t_k[j];
         float sk = 0.f;
-        for (int a = 0; a < blk.arity; ++a) sk += q[blk.cfg_es[k * blk.arity + a]];
-        sk += clip_lp(lp.at(pbase + k, b));
+        for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
+        sk += clip_lp(lpL.at(pbase + k));
         M = fmaxf(M, sk);
       }
       float val = M;
@@ -563,31 +747,31 @@ k_enum_big(int batch, int ld, EnumBlockDev blk, const int32_t* __restrict__ edge
         for (int j = j0; j < j1; ++j) {
           const int k = blk.t_k[j];
           float sk = 0.f;
-          for (int a = 0; a < blk.arity; ++a) sk += q[blk.cfg_es[k * blk.arity + a]];
-          sk += clip_lp(lp.at(pbase + k, b));
+          for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
+          sk += clip_lp(lpL.at(pbase + k));
           sum += expf((sk - M) / T);
         }
         val = T * logf(sum) + M;
       }
-      nv[s] = damp(m_old[(mbase + s) * ld + b], val - q[s], d, one_minus_d);
+      nv[s] = damp(mo[(mbase + s) << sh], val - q[s], a.d, a.one_minus_d);
     }
     float dmax = 0.f;
-    for (int a = 0; a < blk.arity; ++a) {
-      const int s0 = blk.edge_off[a], s1 = blk.edge_off[a + 1];
+    for (int e = 0; e < blk.arity; ++e) {
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
       __syncthreads();
       float mx = -INFINITY;
       for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) mx = fmaxf(mx, nv[s]);
       mx = block_max(mx, red);
       for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
         const float out = fmaxf(nv[s] - mx, kMsgNegInf);
-        const int64_t idx = (mbase + s) * ld + b;
-        dmax = fmaxf(dmax, fabsf(out - m_old[idx]));
-        m_new[idx] = out;
+        const int64_t idx = (mbase + s) << sh;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
       }
     }
-    if (deltas != nullptr) {
+    if (a.deltas != nullptr) {
       dmax = block_max(dmax, red);
-      if (threadIdx.x == 0) publish_delta(deltas, int64_t(b) * delta_stride + delta_off, dmax);
+      if (threadIdx.x == 0) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
     }
   }
 }
@@ -595,20 +779,19 @@ k_enum_big(int batch, int ld, EnumBlockDev blk, const int32_t* __restrict__ edge
 // ---------------------------------------------------------------------------
 // Writes the two states of a binary edge whose factor->variable message is
 // (0, x) or (x, 0): damping + normalisation + clip + delta.
-//   lo = message index of the edge's state 0.
+//   lo = message index of the edge's state 0; mo / mn are lane pointers.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float write_binary_edge(const float* __restrict__ m_old,
-                                                   float* __restrict__ m_new, int64_t lo, int ld,
-                                                   int b, float f0, float f1, float d,
-                                                   float one_minus_d) {
-  const int64_t i0 = lo * ld + b, i1 = i0 + ld;
-  const float a0 = m_old[i0], a1 = m_old[i1];
+__device__ __forceinline__ float write_binary_edge(const float* __restrict__ mo,
+                                                   float* __restrict__ mn, int64_t lo, int sh,
+                                                   float f0, float f1, float d, float one_minus_d) {
+  const int64_t i0 = lo << sh, i1 = (lo + 1) << sh;
+  const float a0 = mo[i0], a1 = mo[i1];
   float n0 = damp(a0, f0, d, one_minus_d), n1 = damp(a1, f1, d, one_minus_d);
   const float mx = fmaxf(n0, n1);
   n0 = fmaxf(n0 - mx, kMsgNegInf);
   n1 = fmaxf(n1 - mx, kMsgNegInf);
-  m_new[i0] = n0;
-  m_new[i1] = n1;
+  mn[i0] = n0;
+  mn[i1] = n1;
   return fmaxf(fabsf(n0 - a0), fabsf(n1 - a1));
 }
 
@@ -633,28 +816,30 @@ struct LogicalDev {
 template <bool kSumProduct>
 __global__ void __launch_bounds__(kThreads)
 k_logical(BatchMap mp, LogicalDev w, const float* __restrict__ S,
-          const float* __restrict__ m_old, float* __restrict__ m_new, float d,
-          float one_minus_d, float T, float* __restrict__ deltas, int64_t delta_stride,
-          int64_t delta_off) {
+          const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
   UnitLoop L = unit_loop(mp, w.num_factors);
   if (!L.b_ok) return;
   float dmax = 0.f;
-  const int b = L.b;
-  const int ld = mp.ld;
+  const int sh = mp.bx_log;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
   const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
   for (int64_t f = L.u; f < L.u_end; f += L.step) {
     const int64_t p0 = w.parent_ptr[f], p1 = w.parent_ptr[f + 1];
     const int64_t c = w.children_msg[f], cvs = w.children_vs[f];
-    const float ca = S[(cvs + off) * ld + b] - m_old[(c + off) * ld + b];  // "relevant" state
-    const float cb = S[cvs * ld + b] - m_old[c * ld + b];                  // "other" state
+    const float ca = SL[(cvs + off) << sh] - mo[(c + off) << sh];  // "relevant" state
+    const float cb = SL[cvs << sh] - mo[c << sh];                  // "other" state
     // Pass 1: sums in ascending parent order, first / second max of the differences
     // (first arg-max = LARGEST tied index, update_utils.py:51-63).
     float Sb = 0.f, acc = 0.f, d1 = -INFINITY, d2 = -INFINITY;
     int64_t istar = p0;
     for (int64_t i = p0; i < p1; ++i) {
       const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
-      const float a_i = S[(pv + off) * ld + b] - m_old[(pm + off) * ld + b];
-      const float b_i = S[pv * ld + b] - m_old[pm * ld + b];
+      const float a_i = SL[(pv + off) << sh] - mo[(pm + off) << sh];
+      const float b_i = SL[pv << sh] - mo[pm << sh];
       const float dl = a_i - b_i;
       Sb += b_i;
       acc += kSumProduct ? logaddexp_t(a_i, b_i, T) : fmaxf(b_i, a_i);
@@ -672,8 +857,8 @@ k_logical(BatchMap mp, LogicalDev w, const float* __restrict__ S,
     // Pass 2: outgoing messages to the parents.
     for (int64_t i = p0; i < p1; ++i) {
       const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
-      const float a_i = S[(pv + off) * ld + b] - m_old[(pm + off) * ld + b];
-      const float b_i = S[pv * ld + b] - m_old[pm * ld + b];
+      const float a_i = SL[(pv + off) << sh] - mo[(pm + off) << sh];
+      const float b_i = SL[pv << sh] - mo[pm << sh];
       float PR, PO;
       if (kSumProduct) {
         const float l_i = logaddexp_t(a_i, b_i, T);
@@ -695,15 +880,15 @@ k_logical(BatchMap mp, LogicalDev w, const float* __restrict__ S,
       if (single) { PR = ca; PO = cb; }  // logical.py:739-757
       const float x = PR - PO;          // message of the "p_i + off" state; the other state gets 0
       const int64_t lo = (off > 0) ? pm : pm - 1;
-      dmax = fmaxf(dmax, write_binary_edge(m_old, m_new, lo, ld, b, off > 0 ? 0.f : x,
-                                           off > 0 ? x : 0.f, d, one_minus_d));
+      dmax = fmaxf(dmax, write_binary_edge(mo, mn, lo, sh, off > 0 ? 0.f : x, off > 0 ? x : 0.f, d,
+                                           one_minus_d));
     }
     const float xc = CR - Sb;
     const int64_t lo = (off > 0) ? c : c - 1;
-    dmax = fmaxf(dmax, write_binary_edge(m_old, m_new, lo, ld, b, off > 0 ? 0.f : xc,
-                                         off > 0 ? xc : 0.f, d, one_minus_d));
+    dmax = fmaxf(dmax, write_binary_edge(mo, mn, lo, sh, off > 0 ? 0.f : xc, off > 0 ? xc : 0.f, d,
+                                         one_minus_d));
   }
-  publish_delta(deltas, int64_t(b) * delta_stride + delta_off, dmax);
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
 }
 
 // ---------------------------------------------------------------------------
@@ -712,24 +897,28 @@ k_logical(BatchMap mp, LogicalDev w, const float* __restrict__ S,
 template <bool kSumProduct>
 __global__ void __launch_bounds__(kThreads)
 k_pool(BatchMap mp, LogicalDev w, const float* __restrict__ S, const float* __restrict__ m_old,
-       float* __restrict__ m_new, float d, float one_minus_d, float T,
-       float* __restrict__ deltas, int64_t delta_stride, int64_t delta_off) {
+       float* __restrict__ m_new, RunArgs a) {
   UnitLoop L = unit_loop(mp, w.num_factors);
   if (!L.b_ok) return;
   float dmax = 0.f;
-  const int b = L.b;
-  const int ld = mp.ld;
+  const int sh = mp.bx_log;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  // difference (state 1 - state 0) of the variable->factor message of a binary edge
+  auto diff = [&](int64_t pm, int64_t pv) {
+    return (SL[(pv + 1) << sh] - mo[(pm + 1) << sh]) - (SL[pv << sh] - mo[pm << sh]);
+  };
   for (int64_t f = L.u; f < L.u_end; f += L.step) {
     const int64_t p0 = w.parent_ptr[f], p1 = w.parent_ptr[f + 1];
     const int64_t c = w.children_msg[f], cvs = w.children_vs[f];
-    const float D = (S[(cvs + 1) * ld + b] - m_old[(c + 1) * ld + b]) -
-                    (S[cvs * ld + b] - m_old[c * ld + b]);
+    const float D = diff(c, cvs);
     float d1 = -INFINITY, d2 = -INFINITY;
     int64_t istar = p0;
     for (int64_t i = p0; i < p1; ++i) {
-      const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
-      const float dl = (S[(pv + 1) * ld + b] - m_old[(pm + 1) * ld + b]) -
-                       (S[pv * ld + b] - m_old[pm * ld + b]);
+      const float dl = diff(w.parents_msg[i], w.parents_vs[i]);
       if (dl >= d1) { d2 = d1; d1 = dl; istar = i; }
       else if (dl > d2) d2 = dl;
     }
@@ -740,9 +929,7 @@ k_pool(BatchMap mp, LogicalDev w, const float* __restrict__ S, const float* __re
       // the arg-max choice is replaced by -D (own max), both in ascending order.
       float sum = 0.f, mx2 = -INFINITY;
       for (int64_t i = p0; i < p1; ++i) {
-        const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
-        const float dl = (S[(pv + 1) * ld + b] - m_old[(pm + 1) * ld + b]) -
-                         (S[pv * ld + b] - m_old[pm * ld + b]);
+        const float dl = diff(w.parents_msg[i], w.parents_vs[i]);
         sum += expf((dl - d1) / T);
         mx2 = fmaxf(mx2, (i == istar) ? -D : dl);
       }
@@ -750,29 +937,26 @@ k_pool(BatchMap mp, LogicalDev w, const float* __restrict__ S, const float* __re
       G = logaddexp_t(out_ind, -D, T);
       float sum2 = 0.f;
       for (int64_t i = p0; i < p1; ++i) {
-        const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
-        const float dl = (S[(pv + 1) * ld + b] - m_old[(pm + 1) * ld + b]) -
-                         (S[pv * ld + b] - m_old[pm * ld + b]);
+        const float dl = diff(w.parents_msg[i], w.parents_vs[i]);
         sum2 += expf((((i == istar) ? -D : dl) - mx2) / T);
       }
       out_star = -(T * logf(sum2) + mx2);
     }
     for (int64_t i = p0; i < p1; ++i) {
-      const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
+      const int64_t pm = w.parents_msg[i];
       float x;
       if (kSumProduct) {
-        const float dl = (S[(pv + 1) * ld + b] - m_old[(pm + 1) * ld + b]) -
-                         (S[pv * ld + b] - m_old[pm * ld + b]);
+        const float dl = diff(pm, w.parents_vs[i]);
         x = (i == istar) ? out_star : -logminusexp_t(G, dl, T, 1e-30f);
       } else {
         x = fminf(D, -((i == istar) ? d2 : d1));
       }
       if (single) x = D;  // pool.py:430-450
-      dmax = fmaxf(dmax, write_binary_edge(m_old, m_new, pm, ld, b, 0.f, x, d, one_minus_d));
+      dmax = fmaxf(dmax, write_binary_edge(mo, mn, pm, sh, 0.f, x, d, one_minus_d));
     }
-    dmax = fmaxf(dmax, write_binary_edge(m_old, m_new, c, ld, b, 0.f, out_ind, d, one_minus_d));
+    dmax = fmaxf(dmax, write_binary_edge(mo, mn, c, sh, 0.f, out_ind, d, one_minus_d));
   }
-  publish_delta(deltas, int64_t(b) * delta_stride + delta_off, dmax);
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
 }
 
 // ---------------------------------------------------------------------------
@@ -790,6 +974,7 @@ k_decode(BatchMap mp, int64_t num_vars, int64_t num_var_states,
   UnitLoop L = unit_loop(mp, num_vars);
   if (!L.b_ok) return;
   const int b = L.b;
+  const LaneView evL = lane_view(ev, mp, b), mL = lane_view(m, mp, b);
   int ntie = 0;
   for (int64_t var = L.u; var < L.u_end; var += L.step) {
     const int64_t v0 = var_first_state[var], v1 = var_first_state[var + 1];
@@ -797,8 +982,8 @@ k_decode(BatchMap mp, int64_t num_vars, int64_t num_var_states,
     float best = -INFINITY, second = -INFINITY;
     int arg = 0;
     for (int64_t v = v0; v < v1; ++v) {
-      float acc = ev.at(v, b);
-      for (int64_t k = k0; k < k1; ++k) acc += m.at(var_edge_msg[k] + (v - v0), b);
+      float acc = evL.at(v);
+      for (int64_t k = k0; k < k1; ++k) acc += mL.at(var_edge_msg[k] + (v - v0));
       if (beliefs) beliefs[int64_t(b) * num_var_states + v] = acc;
       if (acc > best) { second = best; best = acc; arg = int(v - v0); }
       else if (acc > second) second = acc;
@@ -809,14 +994,14 @@ k_decode(BatchMap mp, int64_t num_vars, int64_t num_var_states,
       // exp(x - logsumexp(x)), logsumexp = max + log sum exp(x - max)
       float sum = 0.f;
       for (int64_t v = v0; v < v1; ++v) {
-        float acc = ev.at(v, b);
-        for (int64_t k = k0; k < k1; ++k) acc += m.at(var_edge_msg[k] + (v - v0), b);
+        float acc = evL.at(v);
+        for (int64_t k = k0; k < k1; ++k) acc += mL.at(var_edge_msg[k] + (v - v0));
         sum += expf(acc - best);
       }
       const float lse = best + logf(sum);
       for (int64_t v = v0; v < v1; ++v) {
-        float acc = ev.at(v, b);
-        for (int64_t k = k0; k < k1; ++k) acc += m.at(var_edge_msg[k] + (v - v0), b);
+        float acc = evL.at(v);
+        for (int64_t k = k0; k < k1; ++k) acc += mL.at(var_edge_msg[k] + (v - v0));
         marginals[int64_t(b) * num_var_states + v] = expf(acc - lse);
       }
     }
