@@ -90,6 +90,79 @@ def build_workload(name: str, batch_override=None, iters_override=None):
               temperature=temperature, batch=batch or 1)
 
 
+def run_ising_big(args):
+  """BASELINE.json configs[4]: one n x n Ising torus (default 8192), sum-product T=1,
+  200 iterations, row strips across the ranks with a per-iteration halo exchange
+  (pgmax_b200/dist.py).  Strong scaling: the graph is fixed, ranks split it."""
+  import torch
+  import torch.distributed as dist
+  from pgmax_b200 import dist as pdist
+
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+  n = args.size or 8192
+  iters = args.iters or 200
+  T = 1.0
+  strip = pdist.ising_strip(n, rank, world)
+  runner = pdist.StripRunner(strip, pdist.PgxStepEngine(strip.flat, dev), dev)
+  gen = torch.Generator(device=dev).manual_seed(rank)
+  u = torch.rand(strip.rows * n * 2, generator=gen, device=dev).clamp_(1e-7, 1 - 1e-7)
+  ev_own = -torch.log(-torch.log(u))  # Gumbel(0, 1), generated on the device
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+  msgs = None
+  for _ in range(args.warmup):
+    msgs, _ = runner.run(ev_own, min(iters, 5), 0.5, T)
+  launches0 = runner.engine.plan.launch_count
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  for _ in range(args.steps):
+    msgs, _ = runner.run(ev_own, iters, 0.5, T)
+  e1.record()
+  barrier()
+  ms = e0.elapsed_time(e1)
+  clocks = sampler.stop()
+  launches = runner.engine.plan.launch_count - launches0
+  if world > 1:
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+  if rank == 0:
+    es = 8 * n * n
+    bytes_iter = 17 * es  # 4 * (2 + 0.25 + 1 + 1) * E_s, SURVEY.md 8(d)
+    iter_s = ms * 1e-3 / args.steps / iters
+    peak = FALLBACK_HBM_GBS
+    line = {
+        "metric": METRIC, "value": es * iters * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"Ising {n}x{n} torus, single graph, sum-product T=1", "iters": iters,
+                   "damping": 0.5, "temperature": T, "edge_states": es,
+                   "parallelism": f"row strips x{world}, halo exchange per iteration (NCCL send/recv)"},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": bytes_iter / iter_s / 1e9 / world, "peak": peak, "unit": "GB/s",
+                     "frac": bytes_iter / iter_s / 1e9 / world / peak, "traffic": None,
+                     "kernel": "whole iteration (k_var_sums + k_enum_pw2), per GPU",
+                     "algorithmic_bytes_per_launch": bytes_iter // world, "peak_source": "fallback",
+                     "iter_ms": iter_s * 1e3},
+        "checksum_max_abs_msg": float(msgs.abs().max().item()),
+    }
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
 def algorithmic_bytes_per_iter(plan, batch, lp_batched):
   """4 * (2*E_s*B + V_s*B + C*B_lp + E_s)."""
   es, vs, c = plan.num_edge_states, plan.num_var_states, plan.num_potentials
@@ -230,12 +303,17 @@ def main():
   ap.add_argument("--workload", default="rbm")
   ap.add_argument("--batch", type=int, default=None, help="per-GPU batch override")
   ap.add_argument("--iters", type=int, default=None, help="BP iterations per step override")
+  ap.add_argument("--size", type=int, default=None, help="grid side of the ising_big workload")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--exact-order", action="store_true",
                   help="force the two-pass serial-summation-order path (pgx_plan_set_exact_order)")
   args = ap.parse_args()
   if args.impl == "reference":
     run_reference(args)
+    return
+
+  if args.workload == "ising_big":
+    run_ising_big(args)
     return
 
   import torch

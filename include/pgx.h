@@ -134,6 +134,20 @@ int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch,
                float* ftov_out, float* deltas,
                int32_t num_iters, float damping, float temperature);
 
+/* pgx_bp_run with flags.  PGX_RUN_INPUT_NORMALIZED: the caller guarantees that
+ * ftov_in is the output of a previous run (every edge already has max 0 and is
+ * clipped), so the initial normalisation pass (bp.py:92-96, idempotent) is
+ * skipped; for batch == 1 and ftov_in != ftov_out the input is then read in
+ * place with no staging copy.  This is the step function of callers that must
+ * touch the evidence between iterations (multi-GPU halo exchange, dist.py). */
+#define PGX_RUN_INPUT_NORMALIZED 1u
+int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch,
+                     const float* log_potentials, int lp_batched,
+                     const float* evidence, int ev_batched,
+                     const float* ftov_in, int msgs_batched,
+                     float* ftov_out, float* deltas,
+                     int32_t num_iters, float damping, float temperature, uint32_t flags);
+
 /* beliefs_out[batch, V_s] = evidence + sum of incoming messages. */
 int pgx_beliefs(pgx_plan* plan, void* stream, int64_t batch,
                 const float* evidence, int ev_batched,

@@ -83,6 +83,44 @@ def graph_from_context(context) -> OracleGraph:
   )
 
 
+def graph_from_flat(flat) -> OracleGraph:
+  """OracleGraph from a pgmax_b200._native.FlatGraph (EnumFactor blocks only): expands the
+  block descriptors into the reference's per-row arrays (pgmax/factor/enum.py:364-394)."""
+  edge_ns = np.asarray(flat.edge_num_states, dtype=np.int64)
+  edge_vs = np.asarray(flat.edge_var_start, dtype=np.int64)
+  edge_msg_start = np.cumsum(edge_ns) - edge_ns
+  num_es = int(edge_ns.sum())
+  edge_of_es = np.repeat(np.arange(edge_ns.shape[0]), edge_ns)
+  vs_of_es = edge_vs[edge_of_es] + (np.arange(num_es) - edge_msg_start[edge_of_es])
+  cfg_idx, cfg_es = [], []
+  for blk in flat.enum_blocks:
+    cfg = np.asarray(blk.factor_configs, dtype=np.int64)
+    K, A = cfg.shape
+    off = np.concatenate([[0], np.cumsum(edge_ns[blk.first_edge : blk.first_edge + A])])
+    ns, first_msg = int(off[-1]), int(edge_msg_start[blk.first_edge])
+    f = np.arange(blk.num_factors)[:, None, None]
+    k = np.arange(K)[None, :, None]
+    cfg_idx.append(np.broadcast_to(blk.first_potential + f * K + k, (blk.num_factors, K, A)).reshape(-1))
+    cfg_es.append((first_msg + f * ns + (off[:-1][None, None, :] + cfg[None])).reshape(-1))
+  empty = np.zeros((0,), dtype=np.int64)
+  enum_args = dict(
+      factor_configs_indices=np.concatenate(cfg_idx) if cfg_idx else empty,
+      factor_configs_edge_states=np.concatenate(cfg_es) if cfg_es else empty,
+      num_val_configs=int(flat.num_potentials),
+      num_factors=int(sum(b.num_factors for b in flat.enum_blocks)),
+  )
+  return OracleGraph(
+      var_states_for_edge_states=vs_of_es,
+      edge_indices_for_edge_states=edge_of_es,
+      num_edges=int(edge_ns.shape[0]),
+      num_var_states=int(np.asarray(flat.var_num_states, dtype=np.int64).sum()),
+      msgs_range={ENUM: (0, num_es), OR: (0, 0), AND: (0, 0), POOL: (0, 0)},
+      potentials_range={ENUM: (0, int(flat.num_potentials)), OR: (0, 0), AND: (0, 0), POOL: (0, 0)},
+      inference_arguments={ENUM: enum_args, OR: {}, AND: {}, POOL: {}},
+      var_num_states=np.asarray(flat.var_num_states, dtype=np.int64),
+  )
+
+
 # ----------------------------------------------------------------------------
 # update_utils.py
 # ----------------------------------------------------------------------------

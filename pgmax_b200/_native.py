@@ -6,9 +6,10 @@ is missing, or no CUDA device is visible, calls raise ``PgxError``.
 """
 
 import ctypes
+import dataclasses
 import os
 import subprocess
-from typing import Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 
@@ -28,6 +29,7 @@ EXPORTED_SYMBOLS = (
     "pgx_plan_destroy",
     "pgx_plan_get_info",
     "pgx_bp_run",
+    "pgx_bp_run_flags",
     "pgx_beliefs",
     "pgx_decode",
     "pgx_infer_host",
@@ -141,6 +143,8 @@ def load() -> ctypes.CDLL:
   lib.pgx_bp_run.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp,
                              ctypes.c_int, vp, vp, i32, f32, f32]
   lib.pgx_bp_run.restype = ctypes.c_int
+  lib.pgx_bp_run_flags.argtypes = lib.pgx_bp_run.argtypes + [ctypes.c_uint32]
+  lib.pgx_bp_run_flags.restype = ctypes.c_int
   lib.pgx_beliefs.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp]
   lib.pgx_beliefs.restype = ctypes.c_int
   lib.pgx_decode.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp]
@@ -196,16 +200,78 @@ def _logical_desc(keep: list, wiring, parents, children, offset: int, msg_start:
   return d
 
 
+@dataclasses.dataclass
+class FlatEnumBlock:
+  """One pgx_enum_block in host arrays (see include/pgx.h)."""
+
+  num_factors: int
+  factor_configs: np.ndarray  # [num_configs, arity]
+  first_edge: int
+  first_potential: int
+
+
+@dataclasses.dataclass
+class FlatGraph:
+  """A compiled factor graph as the flat arrays of pgx_graph_desc,
+  for graphs generated directly in array form (no per-factor Python objects).
+  Only EnumFactor blocks; logical / pool factors go through FactorGraphState."""
+
+  var_num_states: np.ndarray   # [num_vars]
+  edge_var_start: np.ndarray   # [num_edges] var-state index of the edge's state 0
+  edge_num_states: np.ndarray  # [num_edges]
+  num_potentials: int
+  enum_blocks: List[FlatEnumBlock]
+
+
 class Plan:
-  """Owns a pgx_plan built from a FactorGraphState (device index structures)."""
+  """Owns a pgx_plan (device index structures) built from a FactorGraphState or a FlatGraph."""
 
   def __init__(self, fg_state):
-    # pylint: disable=g-import-not-at-top
-    from pgmax_b200 import factor
-
     lib = load()
     keep = []  # numpy arrays that must outlive pgx_plan_create
     desc = GraphDescC()
+    if isinstance(fg_state, FlatGraph):
+      self._fill_from_flat(desc, keep, fg_state)
+    else:
+      self._fill_from_state(desc, keep, fg_state)
+    self._create(lib, desc)
+
+  @staticmethod
+  def _fill_from_flat(desc, keep, flat: FlatGraph):
+    var_states = _i32(flat.var_num_states)
+    edge_var_start, edge_num_states = _i32(flat.edge_var_start), _i32(flat.edge_num_states)
+    keep.extend([var_states, edge_var_start, edge_num_states])
+    desc.num_vars = int(var_states.shape[0])
+    desc.var_num_states = _ptr(var_states)
+    desc.num_edges = int(edge_var_start.shape[0])
+    desc.edge_var_start = _ptr(edge_var_start)
+    desc.edge_num_states = _ptr(edge_num_states)
+    desc.num_potentials = int(flat.num_potentials)
+    blocks = (EnumBlockC * max(len(flat.enum_blocks), 1))()
+    for i, b in enumerate(flat.enum_blocks):
+      cfg = _i32(b.factor_configs)
+      keep.append(cfg)
+      blocks[i].num_factors = int(b.num_factors)
+      blocks[i].arity = int(cfg.shape[1])
+      blocks[i].num_configs = int(cfg.shape[0])
+      blocks[i].configs = _ptr(cfg)
+      blocks[i].first_edge = int(b.first_edge)
+      # message offset of the block's first edge
+      blocks[i].first_msg = int(edge_num_states[: b.first_edge].sum(dtype=np.int64))
+      blocks[i].first_potential = int(b.first_potential)
+    keep.append(blocks)
+    desc.num_enum_blocks = len(flat.enum_blocks)
+    desc.enum_blocks = blocks
+    for name in ("or_factors", "and_factors", "pool_factors"):
+      empty = LogicalDescC()
+      empty.edge_states_offset = -1 if name == "and_factors" else 1
+      setattr(desc, name, empty)
+
+  @staticmethod
+  def _fill_from_state(desc, keep, fg_state):
+    # pylint: disable=g-import-not-at-top
+    from pgmax_b200 import factor
+
     var_states = _i32(
         np.concatenate(
             [vg.num_states.reshape(-1) for vg in fg_state.variable_groups]
@@ -260,6 +326,7 @@ class Plan:
         ranges[factor.PoolFactor][0],
     )
 
+  def _create(self, lib, desc):
     handle = ctypes.c_void_p()
     check(lib.pgx_plan_create(ctypes.byref(desc), ctypes.byref(handle)))
     self._lib = lib
@@ -310,6 +377,13 @@ class Plan:
     check(self._lib.pgx_bp_run(self.handle, stream, batch, lp, int(lp_batched), ev, int(ev_batched),
                                msgs_in, int(msgs_batched), msgs_out, deltas, num_iters,
                                damping, temperature))
+
+  def bp_step(self, stream: int, lp: int, ev: int, msgs_in: int, msgs_out: int, damping: float,
+              temperature: float, num_iters: int = 1) -> None:
+    """One-sample iterations on messages that are already normalised (the output of an
+    earlier run): read in place, no staging copy (PGX_RUN_INPUT_NORMALIZED)."""
+    check(self._lib.pgx_bp_run_flags(self.handle, stream, 1, lp, 0, ev, 0, msgs_in, 0, msgs_out,
+                                     None, num_iters, damping, temperature, 1))
 
   def beliefs(self, stream: int, batch: int, ev: int, ev_batched: bool, msgs: int,
               msgs_batched: bool, out: int) -> None:

@@ -160,18 +160,17 @@ size_t tiled_floats(const pgx::BatchMap& mp, int64_t n_rows) {
   return (size_t(std::max<int64_t>(n_rows, 1)) * mp.nbt) << mp.bx_log;
 }
 
-// Grid for a "one thread per (element, sample)" kernel: enough warps to cover the
-// work, capped at a few CTAs per SM (workers then loop over contiguous chunks),
-// and a whole number of nbt-warp workers.
-int grid_for(const pgx_plan* plan, const pgx::BatchMap& mp, int64_t units) {
+// Grid for a "one thread per (element, sample)" kernel: y = sample tiles; x = enough
+// CTAs to cover the elements of one tile, capped so that the whole grid is a few CTAs
+// per SM (warps then loop over contiguous chunks).
+dim3 grid_for(const pgx_plan* plan, const pgx::BatchMap& mp, int64_t units) {
   const int upw = 32 >> mp.bx_log;
   const int wpb = pgx::kThreads / 32;
-  int64_t warps = std::max<int64_t>(1, (units + upw - 1) / upw) * mp.nbt;
+  const int64_t warps = std::max<int64_t>(1, (units + upw - 1) / upw);
   int64_t blocks = (warps + wpb - 1) / wpb;
-  blocks = std::min<int64_t>(blocks, int64_t(plan->num_sms) * 8);
-  const int64_t quantum = mp.nbt / std::gcd<int64_t>(mp.nbt, wpb);
-  blocks = (blocks + quantum - 1) / quantum * quantum;
-  return int(std::max<int64_t>(blocks, quantum));
+  const int64_t cap = std::max<int64_t>(1, (int64_t(plan->num_sms) * 8 + mp.nbt - 1) / mp.nbt);
+  blocks = std::min<int64_t>(blocks, cap);
+  return dim3(unsigned(blocks), unsigned(mp.nbt), 1);
 }
 
 int build_logical(pgx_plan* plan, const pgx_logical_desc& d, const std::vector<int64_t>& edge_msg_start,
@@ -394,6 +393,11 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       const size_t smem = size_t(2 * eb.dev.ns + 32) * sizeof(float);
       const int64_t units = F * mp.batch;
       const int grid = int(std::min<int64_t>(units, int64_t(plan->num_sms) * 8));
+      static bool big_attr[2] = {false, false};
+      if (!big_attr[kSum]) {
+        PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big<kSum>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        big_attr[kSum] = true;
+      }
       pgx::k_enum_big<kSum><<<grid, pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old,
                                                                m_new, a);
       if ((rc = check_launch(plan, "k_enum_big"))) return rc;
@@ -732,6 +736,14 @@ int pgx_plan_profile_read(pgx_plan* plan, int64_t* num_launches, double* total_m
 int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch, const float* log_potentials, int lp_batched,
                const float* evidence, int ev_batched, const float* ftov_in, int msgs_batched,
                float* ftov_out, float* deltas, int32_t num_iters, float damping, float temperature) {
+  return pgx_bp_run_flags(plan, stream, batch, log_potentials, lp_batched, evidence, ev_batched, ftov_in,
+                          msgs_batched, ftov_out, deltas, num_iters, damping, temperature, 0);
+}
+
+int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* log_potentials, int lp_batched,
+                     const float* evidence, int ev_batched, const float* ftov_in, int msgs_batched,
+                     float* ftov_out, float* deltas, int32_t num_iters, float damping, float temperature,
+                     uint32_t flags) {
   if (!plan) return fail(PGX_ERR_INVALID, "null plan");
   PGX_CHECK(batch >= 1 && batch < (1 << 24), "batch must be in [1, 2^24), got %lld", (long long)batch);
   PGX_CHECK(num_iters >= 1, "num_iters must be >= 1, got %d", num_iters);
@@ -764,22 +776,31 @@ int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch, const float* log_pot
     if ((rc = to_tiles(plan, st, log_potentials, ws.lpT, C, mp))) return rc;
     lp = pgx::View{ws.lpT, C, 1};
   }
-  float* cur = ws.mA;
+  // Messages the caller guarantees to be normalised already (output of a previous run) are,
+  // for one sample, read in place: no staging copy, no normalisation pass.
+  const bool in_place = single && ftov_in != nullptr && (flags & PGX_RUN_INPUT_NORMALIZED) != 0 &&
+                        ftov_in != ftov_out;
+  const float* cur = ws.mA;
   float* nxt = ws.mB;
-  if (ftov_in == nullptr) {
-    PGX_CUDA(cudaMemsetAsync(cur, 0, tiled_floats(mp, Es) * sizeof(float), st));  // NC(0) = 0
+  if (in_place) {
+    cur = ftov_in;
+    nxt = ws.mA;
+  } else if (ftov_in == nullptr) {
+    PGX_CUDA(cudaMemsetAsync(ws.mA, 0, tiled_floats(mp, Es) * sizeof(float), st));  // NC(0) = 0
   } else {
     if (single) {
-      PGX_CUDA(cudaMemcpyAsync(cur, ftov_in, size_t(Es) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      PGX_CUDA(cudaMemcpyAsync(ws.mA, ftov_in, size_t(Es) * sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else if (msgs_batched) {
-      if ((rc = to_tiles(plan, st, ftov_in, cur, Es, mp))) return rc;
+      if ((rc = to_tiles(plan, st, ftov_in, ws.mA, Es, mp))) return rc;
     } else {
-      pgx::k_broadcast_rows<<<plan->num_sms * 8, pgx::kThreads, 0, st>>>(ftov_in, cur, Es, mp);
+      pgx::k_broadcast_rows<<<plan->num_sms * 8, pgx::kThreads, 0, st>>>(ftov_in, ws.mA, Es, mp);
       if ((rc = check_launch(plan, "k_broadcast_rows"))) return rc;
     }
-    pgx::k_normalize_edges<<<grid_for(plan, mp, plan->num_edges), pgx::kThreads, 0, st>>>(
-        mp, plan->num_edges, Es, plan->d_edge_msg_start, cur);
-    if ((rc = check_launch(plan, "k_normalize_edges"))) return rc;
+    if ((flags & PGX_RUN_INPUT_NORMALIZED) == 0) {
+      pgx::k_normalize_edges<<<grid_for(plan, mp, plan->num_edges), pgx::kThreads, 0, st>>>(
+          mp, plan->num_edges, Es, plan->d_edge_msg_start, ws.mA);
+      if ((rc = check_launch(plan, "k_normalize_edges"))) return rc;
+    }
   }
   if (deltas) PGX_CUDA(cudaMemsetAsync(deltas, 0, size_t(batch) * num_iters * sizeof(float), st));
 
@@ -818,7 +839,8 @@ int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch, const float* log_pot
           plan->d_rest_edge_msg, plan->d_part_first, plan->d_part_count, ev, dst, ws.part, ws.S);
       if ((rc = check_launch(plan, "k_var_reduce"))) return rc;
     }
-    nxt = cur;
+    // ping-pong between the two workspace buffers; the caller's input is never written
+    nxt = (dst == ws.mA) ? ws.mB : ws.mA;
     cur = dst;
   }
   if (!single) {

@@ -79,9 +79,10 @@ struct UnitLoop {
   int step;
 };
 
-// Splits `num_units` graph elements over the grid.  Warps are grouped into
-// workers of `nbt` warps (one per sample tile); each worker walks a contiguous
-// chunk of elements, so consecutive iterations touch consecutive index entries.
+// Splits `num_units` graph elements over the grid.  blockIdx.y is the sample tile;
+// within a tile every warp walks a contiguous chunk of elements, so a warp streams a
+// contiguous span of its tile's arrays and re-reads of the (small) index arrays by
+// the other tiles hit L2.
 __device__ __forceinline__ UnitLoop unit_loop(const BatchMap& mp, int64_t num_units) {
   UnitLoop L;
   const int lane = threadIdx.x & 31;
@@ -89,18 +90,14 @@ __device__ __forceinline__ UnitLoop unit_loop(const BatchMap& mp, int64_t num_un
   const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   const int bx = 1 << mp.bx_log;
   const int upw = 32 >> mp.bx_log;  // elements handled side by side in one warp
-  const int64_t worker = gwarp / mp.nbt;
-  const int64_t nworkers = nwarps / mp.nbt;
-  const int bt = int(gwarp - worker * mp.nbt);
-  L.b = bt * bx + (lane & (bx - 1));
+  L.b = blockIdx.y * bx + (lane & (bx - 1));
   L.b_ok = L.b < mp.batch;
-  int64_t chunk = (num_units + nworkers - 1) / nworkers;
+  int64_t chunk = (num_units + nwarps - 1) / nwarps;
   chunk = (chunk + upw - 1) / upw * upw;
-  const int64_t u0 = worker * chunk;
+  const int64_t u0 = gwarp * chunk;
   L.u_end = min(u0 + chunk, num_units);
-  L.u = u0 + (lane >> mp.bx_log);
+  L.u = min(u0, num_units) + (lane >> mp.bx_log);
   L.step = upw;
-  if (worker >= nworkers) L.u = L.u_end;  // warps beyond the last full worker idle
   return L;
 }
 

@@ -1,0 +1,251 @@
+"""Partitioning of the BP path across the GPUs of one box.
+
+One process per GPU (torch.distributed; NCCL over NVLink on the box, gloo in the
+CPU tests).  Two modes, as the north-star names them:
+
+* independent problems of a batch (RBM samples, deconvolution images) are split by
+  batch index: ``shard_bounds`` / ``shard_batch``.  Every rank runs the identical
+  kernels on its shard; there is NO data-path collective (``all_gather_batch`` only
+  collects results afterwards);
+* one giant Ising grid is split into row strips: ``ising_strip`` builds the local
+  graph of a rank directly in array form (no per-factor Python objects: the 8192^2
+  torus has 134 M factors) and ``StripRunner`` runs BP with ONE halo exchange per
+  iteration.
+
+Halo exchange (torus of n x n variables, variable (i, j) owns the vertical factor
+[(i, j), (i+1, j)] and the horizontal factor [(i, j), (i, j+1)], as
+examples/ising_model.ipynb cell 12).  Rank g owns rows [r0, r1) and their factors and
+keeps a ghost copy of row r1 (owned by rank g+1), the second variable of its last
+row's vertical factors.  Both halo quantities depend only on the messages of the
+previous iteration, so one simultaneous exchange at the top of every iteration
+suffices:
+
+  g -> g+1: the boundary factors' factor->variable messages into row r1 (2n floats);
+            g+1 adds them to the evidence of its first row;
+  g+1 -> g: for its first row, ev_v + (messages from its OWN factors) (2n floats):
+            the evidence of g's ghost copies, so that the local variable sum of a
+            ghost is the full S_v and q = S_v - m is the boundary variable->factor
+            message.
+
+A rank's local BP iteration is then exactly the single-GPU kernel sequence on the
+local graph (pgx_bp_run_flags with PGX_RUN_INPUT_NORMALIZED, messages read in
+place).  The summation order of the boundary rows differs from the single-graph
+order (partial sums), so multi-rank results agree with the single graph to fp32
+rounding (<= 1e-6 in the tests), not bit for bit.
+"""
+
+import dataclasses
+from typing import Optional, Tuple
+
+import numpy as np
+
+from pgmax_b200 import _native
+
+
+# ----------------------------------------------------------------------------------------
+# batch sharding
+# ----------------------------------------------------------------------------------------
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+  """Contiguous, balanced split of range(n): the first n % world ranks get one extra."""
+  if not 0 <= rank < world:
+    raise ValueError(f"rank {rank} outside world of size {world}")
+  base, extra = divmod(n, world)
+  start = rank * base + min(rank, extra)
+  return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_batch(bp_arrays, world: int, rank: int):
+  """This rank's slice of the batch axis of every batched field of a BPArrays;
+  fields without a batch axis (shared potentials) pass through."""
+  from pgmax_b200.infer.bp_state import BPArrays  # pylint: disable=g-import-not-at-top
+
+  batch = bp_arrays.batch_size
+  if batch is None:
+    raise ValueError("BPArrays has no batch axis to shard")
+  lo, hi = shard_bounds(batch, world, rank)
+  pick = lambda a: a[lo:hi] if a.ndim == 2 else a
+  return BPArrays(log_potentials=pick(bp_arrays.log_potentials),
+                  ftov_msgs=pick(bp_arrays.ftov_msgs), evidence=pick(bp_arrays.evidence))
+
+
+def all_gather_batch(local, total: int, group=None):
+  """Concatenates per-rank results along the batch axis on every rank (result
+  collection only; shards may differ in size by one)."""
+  import torch  # pylint: disable=g-import-not-at-top
+  import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+
+  world = dist.get_world_size(group)
+  t = local if torch.is_tensor(local) else torch.from_numpy(np.ascontiguousarray(local))
+  sizes = [shard_bounds(total, world, r) for r in range(world)]
+  width = max(hi - lo for lo, hi in sizes)
+  padded = torch.zeros((width,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+  padded[: t.shape[0]] = t
+  out = [torch.empty_like(padded) for _ in range(world)]
+  dist.all_gather(out, padded, group=group)
+  return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
+
+
+# ----------------------------------------------------------------------------------------
+# row strips of an Ising torus
+# ----------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class IsingStrip:
+  """Local graph of one rank + the index arrays of its halo exchange."""
+
+  n: int
+  rank: int
+  world: int
+  row0: int
+  rows: int                       # owned rows
+  flat: _native.FlatGraph         # (rows [+1 ghost]) x n binary variables, 2 * rows * n factors
+  log_potentials: np.ndarray      # [4 * num_factors] fp32
+  send_down_msg: np.ndarray       # [n, 2] messages of the last row's vertical factors into the ghost row
+  first_row_vs: np.ndarray        # [n, 2] var-states of the first owned row
+  first_row_own_msgs: np.ndarray  # [n, 3, 2] messages into the first row from this rank's factors, ascending
+  ghost_vs: np.ndarray            # [n, 2] var-states of the ghost row
+
+  @property
+  def num_msgs(self) -> int:
+    return 8 * self.rows * self.n
+
+  @property
+  def num_var_states(self) -> int:
+    return int(self.flat.var_num_states.shape[0]) * 2
+
+  @property
+  def global_msg_range(self) -> Tuple[int, int]:
+    """The local message vector is this slice of the single-graph message vector."""
+    return 8 * self.row0 * self.n, 8 * (self.row0 + self.rows) * self.n
+
+
+def ising_strip(n: int, rank: int = 0, world: int = 1, coupling: float = 0.8) -> IsingStrip:
+  """Row strip `rank` of `world` of the n x n Ising torus (world == 1: the whole torus,
+  identical to the graph examples/ising_model.ipynb builds).  Vectorised."""
+  row0, row1 = shard_bounds(n, world, rank)
+  rows = row1 - row0
+  if world > 1 and rows < 2:
+    raise ValueError("every strip needs at least 2 rows")
+  local_rows = rows + (1 if world > 1 else 0)
+  num_vars = local_rows * n
+  ll, jj = np.meshgrid(np.arange(rows), np.arange(n), indexing="ij")
+  v0 = ll * n + jj
+  below = (ll + 1) if world > 1 else (ll + 1) % n
+  v_vert = below * n + jj
+  v_horz = ll * n + (jj + 1) % n
+  # factor 2*(l*n+j)+t, t = 0 vertical, 1 horizontal; edges (factor, var0), (factor, var1)
+  edge_var = np.stack([v0, v_vert, v0, v_horz], axis=-1).reshape(-1)
+  num_factors = 2 * rows * n
+  flat = _native.FlatGraph(
+      var_num_states=np.full((num_vars,), 2, dtype=np.int32),
+      edge_var_start=(2 * edge_var).astype(np.int32),
+      edge_num_states=np.full((2 * num_factors,), 2, dtype=np.int32),
+      num_potentials=4 * num_factors,
+      enum_blocks=[_native.FlatEnumBlock(
+          num_factors=num_factors,
+          factor_configs=np.array([[0, 0], [0, 1], [1, 0], [1, 1]], dtype=np.int32),
+          first_edge=0, first_potential=0)],
+  )
+  lp = np.tile(np.float32(coupling) * np.array([1.0, -1.0, -1.0, 1.0], dtype=np.float32), num_factors)
+  cols = np.arange(n)
+  s = np.arange(2)
+  fvert = lambda l, j: 2 * (l * n + j)
+  fhorz = lambda l, j: 2 * (l * n + j) + 1
+  send_down = (4 * fvert(rows - 1, cols) + 2)[:, None] + s[None]
+  first_vs = (2 * cols)[:, None] + s[None]
+  own = np.stack([4 * fvert(0, cols), 4 * fhorz(0, cols), 4 * fhorz(0, (cols - 1) % n) + 2], axis=1)
+  own = np.sort(own, axis=1)[:, :, None] + s[None, None]
+  ghost = (2 * (rows * n + cols))[:, None] + s[None]
+  return IsingStrip(n=n, rank=rank, world=world, row0=row0, rows=rows, flat=flat, log_potentials=lp,
+                    send_down_msg=send_down.astype(np.int64), first_row_vs=first_vs.astype(np.int64),
+                    first_row_own_msgs=own.astype(np.int64), ghost_vs=ghost.astype(np.int64))
+
+
+class PgxStepEngine:
+  """One BP iteration of a FlatGraph on this rank's GPU through the C ABI."""
+
+  def __init__(self, flat: _native.FlatGraph, device):
+    import torch  # pylint: disable=g-import-not-at-top
+
+    self.torch = torch
+    self.device = torch.device(device)
+    with torch.cuda.device(self.device):
+      self.plan = _native.Plan(flat)
+
+  def step(self, lp, ev, msgs_in, msgs_out, damping: float, temperature: float) -> None:
+    stream = self.torch.cuda.current_stream(self.device).cuda_stream
+    self.plan.bp_step(stream, lp.data_ptr(), ev.data_ptr(), msgs_in.data_ptr(), msgs_out.data_ptr(),
+                      damping, temperature)
+
+  def beliefs(self, ev, msgs):
+    out = self.torch.empty_like(ev)
+    stream = self.torch.cuda.current_stream(self.device).cuda_stream
+    self.plan.beliefs(stream, 1, ev.data_ptr(), False, msgs.data_ptr(), False, out.data_ptr())
+    return out
+
+
+class StripRunner:
+  """Loopy BP on one row strip with a per-iteration halo exchange.
+
+  `engine` does the local iteration (PgxStepEngine on a GPU; the tests inject an
+  oracle-backed engine on CPU tensors, which is how the N > 1 host logic is covered
+  without GPUs).  All tensors live on `device`.
+  """
+
+  def __init__(self, strip: IsingStrip, engine, device, group=None):
+    import torch  # pylint: disable=g-import-not-at-top
+
+    self.torch = torch
+    self.strip, self.engine, self.device, self.group = strip, engine, torch.device(device), group
+    to = lambda a: torch.from_numpy(a).to(self.device)
+    self.lp = to(strip.log_potentials)
+    self.send_down_msg = to(strip.send_down_msg.reshape(-1))
+    self.first_row_vs = to(strip.first_row_vs.reshape(-1))
+    self.own_msgs = [to(np.ascontiguousarray(strip.first_row_own_msgs[:, k, :]).reshape(-1)) for k in range(3)]
+    self.ghost_vs = to(strip.ghost_vs.reshape(-1))
+    width = 2 * strip.n
+    self.recv_up = torch.zeros(width, dtype=torch.float32, device=self.device)
+    self.recv_down = torch.zeros(width, dtype=torch.float32, device=self.device)
+
+  def _exchange(self, ev_own, msgs, ev_local):
+    """Fills ev_local (evidence of the local graph for the coming iteration)."""
+    torch, strip = self.torch, self.strip
+    ev_local[: ev_own.shape[0]] = ev_own
+    if strip.world == 1:
+      return
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+
+    down = (strip.rank + 1) % strip.world
+    up = (strip.rank - 1) % strip.world
+    send_down = msgs[self.send_down_msg]
+    send_up = ev_own[self.first_row_vs]
+    for idx in self.own_msgs:  # ascending message index
+      send_up = send_up + msgs[idx]
+    ops = [dist.P2POp(dist.isend, send_down, down, self.group),
+           dist.P2POp(dist.isend, send_up, up, self.group),
+           dist.P2POp(dist.irecv, self.recv_up, up, self.group),
+           dist.P2POp(dist.irecv, self.recv_down, down, self.group)]
+    for req in dist.batch_isend_irecv(ops):
+      req.wait()
+    ev_local[self.first_row_vs] = ev_own[self.first_row_vs] + self.recv_up
+    ev_local[self.ghost_vs] = self.recv_down
+
+  def run(self, evidence_own, num_iters: int, damping: float = 0.5, temperature: float = 0.0,
+          msgs=None):
+    """evidence_own: [rows * n * 2] evidence of the owned variables.  Returns
+    (messages [8 * rows * n], local evidence incl. halo terms of the LAST exchange)."""
+    torch, strip = self.torch, self.strip
+    ev_own = torch.as_tensor(evidence_own, dtype=torch.float32, device=self.device).reshape(-1)
+    ev_local = torch.zeros(strip.num_var_states, dtype=torch.float32, device=self.device)
+    cur = torch.zeros(strip.num_msgs, dtype=torch.float32, device=self.device) if msgs is None else msgs
+    nxt = torch.empty_like(cur)
+    for _ in range(max(int(num_iters), 1)):
+      self._exchange(ev_own, cur, ev_local)
+      self.engine.step(self.lp, ev_local, cur, nxt, float(damping), float(temperature))
+      cur, nxt = nxt, cur
+    return cur, ev_own
+
+  def beliefs(self, ev_own, msgs):
+    """Beliefs of the owned variables [rows * n * 2] (one more boundary exchange)."""
+    ev_local = self.torch.zeros(self.strip.num_var_states, dtype=self.torch.float32, device=self.device)
+    self._exchange(ev_own, msgs, ev_local)
+    return self.engine.beliefs(ev_local, msgs)[: ev_own.shape[0]]
