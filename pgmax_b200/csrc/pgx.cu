@@ -114,6 +114,11 @@ struct pgx_plan {
   std::vector<EnumBlockPlan> enum_blocks;
   LogicalPlan or_f, and_f, pool_f;
   Workspace ws;
+  // pull mode (every factor is a pairwise-binary enum factor on low-degree variables)
+  bool pull_ok = false;
+  int2* d_edge_csr = nullptr;          // [num_edges] CSR row (begin, end) of the edge's variable
+  unsigned int* d_grid_bar = nullptr;  // barrier counter of the persistent kernel
+  int coop_blocks_per_sm[2] = {0, 0};  // occupancy of k_enum_pw2_pull_persistent<false / true>
   // fused single-pass structures (dense-grid pairwise blocks)
   std::vector<BipPlan> bips;
   bool exact_order = false;            // force the two-pass, serial-order path
@@ -540,6 +545,32 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
                         "Pool factors", &plan->pool_f));
   for (int64_t e = 0; e < plan->num_edges; ++e)
     PGX_REQUIRE(edge_covered[e], "edge %lld belongs to no factor description", (long long)e);
+  {  // pull mode: all factors pairwise-binary, every variable of degree <= kPullMaxDegree
+    constexpr int64_t kPullMaxDegree = 8;
+    bool ok = !plan->enum_blocks.empty() && plan->or_f.dev.num_factors == 0 &&
+              plan->and_f.dev.num_factors == 0 && plan->pool_f.dev.num_factors == 0;
+    for (const EnumBlockPlan& eb : plan->enum_blocks) ok = ok && eb.variant == kPw2;
+    for (int64_t v = 0; v < plan->num_vars && ok; ++v) ok = var_ptr[v + 1] - var_ptr[v] <= kPullMaxDegree;
+    if (ok) {
+      std::vector<int2> edge_csr(plan->num_edges);
+      for (int64_t e = 0; e < plan->num_edges; ++e) {
+        const int32_t var = vs_var[edge_vs[e]];
+        edge_csr[e] = make_int2(int(var_ptr[var]), int(var_ptr[var + 1]));
+      }
+      PGX_TRY(upload(edge_csr, &plan->d_edge_csr, &plan->device_bytes));
+      if (cudaMalloc(reinterpret_cast<void**>(&plan->d_grid_bar), sizeof(unsigned int)) != cudaSuccess)
+        return bail(fail(PGX_ERR_CUDA, "cudaMalloc failed"));
+      int coop = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, plan->device);
+      if (coop) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plan->coop_blocks_per_sm[0],
+                                                      pgx::k_enum_pw2_pull_persistent<false>, pgx::kThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plan->coop_blocks_per_sm[1],
+                                                      pgx::k_enum_pw2_pull_persistent<true>, pgx::kThreads, 0);
+      }
+      plan->pull_ok = true;
+    }
+  }
   {  // dense-grid pairwise blocks -> fused single-pass structures
     std::vector<uint8_t> edge_fused(plan->num_edges, 0);
     std::vector<int32_t> part_count(plan->num_vars, 0);
@@ -678,6 +709,7 @@ void pgx_plan_destroy(pgx_plan* plan) {
   for (BipPlan& bp : plan->bips) {
     free_dev(bp.d_row_vs); free_dev(bp.d_col_vs); free_dev(bp.d_row_part); free_dev(bp.d_col_part);
   }
+  free_dev(plan->d_edge_csr); free_dev(plan->d_grid_bar);
   free_dev(plan->d_rest_ptr); free_dev(plan->d_rest_edge_msg); free_dev(plan->d_part_first);
   free_dev(plan->d_part_count);
   free_workspace(plan->ws);
@@ -817,7 +849,70 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   a.delta_stride = num_iters;
   a.Es = Es;
   a.Vs = Vs;
-  for (int it = 0; it < num_iters; ++it) {
+  // Pull mode: graphs made only of pairwise-binary factors on low-degree variables (grids)
+  // need no var-sum array: one kernel per block and iteration, bit-identical to the
+  // two-pass path.  Small such graphs with a single block run ALL iterations in one
+  // cooperative launch.
+  const bool pull = plan->pull_ok && !fused;
+  if (pull) {
+    auto pull_args = [&](const EnumBlockPlan& eb) {
+      pgx::PullArgs g;
+      g.num_factors = eb.dev.num_factors;
+      g.first_edge = eb.dev.first_edge;
+      g.first_msg = eb.dev.first_msg;
+      g.first_pot = eb.dev.first_pot;
+      g.edge_vs = plan->d_edge_vs;
+      g.edge_csr = plan->d_edge_csr;
+      g.var_edge_msg = plan->d_var_edge_msg;
+      return g;
+    };
+    const int ks = temperature == 0.f ? 0 : 1;
+    const EnumBlockPlan& eb0 = plan->enum_blocks[0];
+    const dim3 grid0 = grid_for(plan, mp, eb0.dev.num_factors);
+    const int64_t coop_cap = int64_t(plan->coop_blocks_per_sm[ks]) * plan->num_sms;
+    const bool persistent = plan->enum_blocks.size() == 1 && num_iters >= 2 && !plan->profiling &&
+                            eb0.dev.num_factors * batch <= (int64_t(1) << 20) &&
+                            int64_t(grid0.x) * grid0.y <= coop_cap;
+    if (persistent) {
+      PGX_CUDA(cudaMemsetAsync(plan->d_grid_bar, 0, sizeof(unsigned int), st));
+      pgx::PullArgs g = pull_args(eb0);
+      pgx::BatchMap mpv = mp;
+      float* out = single ? ftov_out : nullptr;
+      int iters = num_iters;
+      void* args[] = {&mpv, &g, &ev, &lp, &cur, &ws.mA, &ws.mB, &out, &iters, &a, &plan->d_grid_bar};
+      const void* fn = ks ? reinterpret_cast<const void*>(pgx::k_enum_pw2_pull_persistent<true>)
+                          : reinterpret_cast<const void*>(pgx::k_enum_pw2_pull_persistent<false>);
+      PGX_CUDA(cudaLaunchCooperativeKernel(fn, grid0, dim3(pgx::kThreads), args, 0, st));
+      if ((rc = check_launch(plan, "k_enum_pw2_pull_persistent"))) return rc;
+      // where the kernel left the final messages (same rule as in the kernel)
+      float* nx = (cur == ws.mA) ? ws.mB : ws.mA;
+      for (int it = 0; it < num_iters; ++it) {
+        float* dst = (it == num_iters - 1 && out != nullptr) ? out : nx;
+        nx = (dst == ws.mA) ? ws.mB : ws.mA;
+        cur = dst;
+      }
+    } else {
+      for (int it = 0; it < num_iters; ++it) {
+        a.delta_off = it;
+        float* dst = (single && it == num_iters - 1) ? ftov_out : nxt;
+        for (size_t bi = 0; bi < plan->enum_blocks.size(); ++bi) {
+          const EnumBlockPlan& eb = plan->enum_blocks[bi];
+          const dim3 grid = grid_for(plan, mp, eb.dev.num_factors);
+          if ((rc = prof_mark(plan, st, int(bi)))) return rc;
+          if (ks)
+            pgx::k_enum_pw2_pull<true><<<grid, pgx::kThreads, 0, st>>>(mp, pull_args(eb), ev, lp, cur, dst, a);
+          else
+            pgx::k_enum_pw2_pull<false><<<grid, pgx::kThreads, 0, st>>>(mp, pull_args(eb), ev, lp, cur, dst, a);
+          if ((rc = check_launch(plan, "k_enum_pw2_pull"))) return rc;
+          if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2_pull";
+          if ((rc = prof_mark(plan, st, int(bi)))) return rc;
+        }
+        nxt = (dst == ws.mA) ? ws.mB : ws.mA;
+        cur = dst;
+      }
+    }
+  }
+  for (int it = 0; it < (pull ? 0 : num_iters); ++it) {
     a.delta_off = it;
     if (!fused || it == 0) {
       pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(

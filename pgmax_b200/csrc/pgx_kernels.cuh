@@ -339,6 +339,113 @@ k_enum_pw2(BatchMap mp, int64_t num_factors, int64_t first_edge, int64_t first_m
 }
 
 // ---------------------------------------------------------------------------
+// K2a-pull: pairwise-binary block on LOW-DEGREE variables (grids: Ising).  One
+// pass per iteration without a var-sum array: every (factor, sample) thread
+// re-derives the sums of its two variables by walking their incident-edge lists
+// (evidence first, then messages in ascending index: the same serial order as
+// k_var_sums, hence bit-identical results).  The degree-fold re-reads hit L1/L2
+// (neighbouring factors share variables); HBM sees the messages once.
+// edge_csr[e] = (begin, end) of the CSR row of edge e's variable.
+// ---------------------------------------------------------------------------
+struct PullArgs {
+  int64_t num_factors, first_edge, first_msg, first_pot;
+  const int32_t* edge_vs;
+  const int2* edge_csr;
+  const int32_t* var_edge_msg;
+};
+
+// kViaL2: message loads bypass L1 (ld.global.cg) - required inside the persistent kernel,
+// where other SMs rewrite the buffers between iterations.
+template <bool kSumProduct, bool kViaL2>
+__device__ __forceinline__ float pull_factors(const BatchMap& mp, const UnitLoop& L, const PullArgs& g,
+                                              const LaneView& evL, const LaneView& lpL,
+                                              const float* mo_, float* mn, const RunArgs& a) {
+  const int sh = mp.bx_log;
+  float dmax = 0.f;
+  struct Loader {
+    const float* p;
+    __device__ __forceinline__ float operator[](int64_t i) const { return kViaL2 ? __ldcg(p + i) : p[i]; }
+  } mo{mo_};
+  for (int64_t f = L.u; f < L.u_end; f += L.step) {
+    const int64_t e = g.first_edge + 2 * f;
+    const int64_t vs0 = g.edge_vs[e], vs1 = g.edge_vs[e + 1];
+    const int2 c0 = g.edge_csr[e], c1 = g.edge_csr[e + 1];
+    float Sv[4] = {evL.at(vs0), evL.at(vs0 + 1), evL.at(vs1), evL.at(vs1 + 1)};
+    for (int k = c0.x; k < c0.y; ++k) {
+      const int64_t ms = g.var_edge_msg[k];
+      Sv[0] += mo[ms << sh];
+      Sv[1] += mo[(ms + 1) << sh];
+    }
+    for (int k = c1.x; k < c1.y; ++k) {
+      const int64_t ms = g.var_edge_msg[k];
+      Sv[2] += mo[ms << sh];
+      Sv[3] += mo[(ms + 1) << sh];
+    }
+    const int64_t mb = g.first_msg + 4 * f;
+    const float m[4] = {mo[mb << sh], mo[(mb + 1) << sh], mo[(mb + 2) << sh], mo[(mb + 3) << sh]};
+    const int64_t pb = g.first_pot + 4 * f;
+    const float lpv[4] = {clip_lp(lpL.at(pb)), clip_lp(lpL.at(pb + 1)), clip_lp(lpL.at(pb + 2)),
+                          clip_lp(lpL.at(pb + 3))};
+    float n[4];
+    dmax = fmaxf(dmax, pw2_update<kSumProduct>(m, Sv, lpv, a, n));
+    mn[mb << sh] = n[0]; mn[(mb + 1) << sh] = n[1]; mn[(mb + 2) << sh] = n[2]; mn[(mb + 3) << sh] = n[3];
+  }
+  return dmax;
+}
+
+template <bool kSumProduct>
+__global__ void __launch_bounds__(kThreads)
+k_enum_pw2_pull(BatchMap mp, PullArgs g, View ev, View lp, const float* __restrict__ m_old,
+                float* __restrict__ m_new, RunArgs a) {
+  UnitLoop L = unit_loop(mp, g.num_factors);
+  if (!L.b_ok) return;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float dmax = pull_factors<kSumProduct, false>(mp, L, g, lane_view(ev, mp, L.b),
+                                                      lane_view(lp, mp, L.b), m_old + moff, m_new + moff, a);
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// Persistent variant for graphs that are ONE pull block and small enough to be
+// latency-bound (Ising 50x50: 20 000 messages, 1000 iterations): all iterations in one
+// cooperative launch, one grid-wide barrier per iteration instead of two kernel launches.
+// Buffers: iteration 0 reads `src0`; iteration `it` writes `out` if it is the last one
+// and out != null, else it ping-pongs between bufA and bufB (never writing src0).
+template <bool kSumProduct>
+__global__ void __launch_bounds__(kThreads)
+k_enum_pw2_pull_persistent(BatchMap mp, PullArgs g, View ev, View lp, const float* src0, float* bufA,
+                           float* bufB, float* out, int num_iters, RunArgs a, unsigned int* bar) {
+  UnitLoop L = unit_loop(mp, g.num_factors);
+  const int64_t moff = L.b_ok ? lane_off(mp, a.Es, L.b) : 0;
+  const LaneView evL = lane_view(ev, mp, L.b_ok ? L.b : 0), lpL = lane_view(lp, mp, L.b_ok ? L.b : 0);
+  const unsigned int nblocks = gridDim.x * gridDim.y;
+  const float* cur = src0;
+  float* nxt = (src0 == bufA) ? bufB : bufA;
+  for (int it = 0; it < num_iters; ++it) {
+    float* dst = (it == num_iters - 1 && out != nullptr) ? out : nxt;
+    if (L.b_ok) {
+      a.delta_off = it;
+      const float dmax = pull_factors<kSumProduct, true>(mp, L, g, evL, lpL, cur + moff, dst + moff, a);
+      publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+    }
+    nxt = (dst == bufA) ? bufB : bufA;
+    cur = dst;
+    if (it + 1 < num_iters) {
+      // grid-wide barrier (all CTAs are co-resident: cooperative launch): monotonic counter
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const unsigned int target = (unsigned int)(it + 1) * nblocks;
+        while (*reinterpret_cast<volatile unsigned int*>(bar) < target) {
+        }
+        __threadfence();
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // TMA (bulk async copy) + mbarrier helpers, sm_90+ PTX.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -281,3 +281,24 @@ def test_split_run_equals_single_run():
   one = bp.run(arrays, num_iters=12, damping=0.5)
   two = bp.run(bp.run(arrays, num_iters=5, damping=0.5), num_iters=7, damping=0.5)
   np.testing.assert_array_equal(one.ftov_msgs, two.ftov_msgs)
+
+
+@pytest.mark.parametrize("temperature", [0.0, 0.05])
+@pytest.mark.parametrize("batch", [None, 40])
+def test_pull_mode_streaming_equals_persistent(temperature, batch):
+  """Pairwise-only graphs on low-degree variables run without a var-sum array (pull mode):
+  small ones as ONE cooperative launch for all iterations, otherwise one launch per
+  iteration.  Enabling the profiling hooks forces the per-iteration launches; both must be
+  bit-identical (and both are compared with the oracle in test_ising_vs_oracle)."""
+  fg, variables, evidence = models.ising_model(n=10, batch=batch)
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  arrays = bp.init(evidence_updates={variables: evidence})
+  persistent, d_p = bp.run_with_diffs(arrays, num_iters=40, damping=0.5)
+  plan = bp.context.plan
+  plan.profile_enable(True)
+  streaming, d_s = bp.run_with_diffs(arrays, num_iters=40, damping=0.5)
+  launches, _, name = plan.profile_read()
+  plan.profile_enable(False)
+  assert launches == 40 and name == "k_enum_pw2_pull"
+  np.testing.assert_array_equal(persistent.ftov_msgs, streaming.ftov_msgs)
+  np.testing.assert_array_equal(d_p, d_s)
