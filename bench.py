@@ -82,6 +82,22 @@ def build_workload(name: str, batch_override=None, iters_override=None):
     bp = infer.BP(fg.bp_state, temperature=temperature)
     evidence = {variables: ev.astype(np.float32)}
     label = "Ising 50x50 torus, pairwise EnumFactors, T=0.05"
+  elif name == "deconv":
+    # examples/pmp_binary_deconvolution.ipynb shape: one 28x28 image per graph, 5 features 6x6,
+    # 100 synthetic images batched, max-product, 100 iterations
+    batch, iters, temperature = batch_override or 100, 100, 0.0
+    fg, groups = models.deconv_model()
+    bp = infer.BP(fg.bp_state, temperature=temperature)
+    evidence = {k: v.astype(np.float32) for k, v in models.deconv_evidence(groups, batch).items()}
+    label = "binary deconvolution 28x28, 95 220 AND + 784 OR factors, max-product"
+  elif name == "rcn":
+    # examples/rcn.ipynb shape: 20 models x 80 variables of 625 states, large-config pairwise
+    # EnumFactors (perturb radius 2..8), max-product, 30 iterations
+    batch, iters, temperature = batch_override, 30, 0.0
+    fg, groups, evidence = models.rcn_model()
+    bp = infer.BP(fg.bp_state, temperature=temperature)
+    evidence = {k: v.astype(np.float32) for k, v in evidence.items()}
+    label = "RCN-shaped: 20 x 80 variables of 625 states, 3 180 large-config EnumFactors, max-product"
   else:
     raise ValueError(f"unknown workload {name}")
   iters = iters_override or iters

@@ -15,6 +15,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "pgx_kernels.cuh"
@@ -70,6 +71,7 @@ struct EnumBlockPlan {
   EnumVariant variant = kSmall;
   int bip = -1;  // index into pgx_plan::bips when the block has the dense-grid structure
   int32_t *d_cfg_es = nullptr, *d_t_ptr = nullptr, *d_t_k = nullptr, *d_edge_off = nullptr;
+  int32_t *d_fac_edge = nullptr, *d_fac_msg = nullptr, *d_fac_pot = nullptr;
 };
 
 // A pairwise-binary enum block whose factors form a dense I x J grid (see BipDev).
@@ -118,7 +120,7 @@ struct pgx_plan {
   bool pull_ok = false;
   int2* d_edge_csr = nullptr;          // [num_edges] CSR row (begin, end) of the edge's variable
   unsigned int* d_grid_bar = nullptr;  // barrier counter of the persistent kernel
-  int coop_blocks_per_sm[2] = {0, 0};  // occupancy of k_enum_pw2_pull_persistent<false / true>
+  int coop_blocks_per_sm[2] = {0, 0};  // occupancy of k_enum_pw2_pull_resident<false / true, coop>
   // fused single-pass structures (dense-grid pairwise blocks)
   std::vector<BipPlan> bips;
   bool exact_order = false;            // force the two-pass, serial-order path
@@ -234,9 +236,9 @@ int build_logical(pgx_plan* plan, const pgx_logical_desc& d, const std::vector<i
   return PGX_OK;
 }
 
-int build_enum_block(pgx_plan* plan, const pgx_enum_block& b, int idx,
-                     const std::vector<int64_t>& edge_msg_start, const std::vector<int32_t>& edge_ns,
-                     std::vector<uint8_t>& edge_covered, EnumBlockPlan* out) {
+// Checks one pgx_enum_block against the edge table and marks its edges as covered.
+int check_enum_block(pgx_plan* plan, const pgx_enum_block& b, int idx, const std::vector<int64_t>& edge_msg_start,
+                     const std::vector<int32_t>& edge_ns, std::vector<uint8_t>& edge_covered) {
   PGX_CHECK(b.num_factors >= 1 && b.arity >= 1 && b.num_configs >= 0 && b.configs != nullptr,
             "enum block %d: bad sizes", idx);
   const int A = b.arity, K = b.num_configs;
@@ -247,13 +249,10 @@ int build_enum_block(pgx_plan* plan, const pgx_enum_block& b, int idx,
             (long long)b.first_msg, (long long)edge_msg_start[b.first_edge]);
   PGX_CHECK(b.first_potential >= 0 && b.first_potential + b.num_factors * K <= plan->num_potentials,
             "enum block %d: potential range out of bounds", idx);
-  std::vector<int32_t> edge_off(A + 1, 0);
-  for (int a = 0; a < A; ++a) edge_off[a + 1] = edge_off[a] + edge_ns[b.first_edge + a];
-  const int ns = edge_off[A];
   for (int64_t f = 0; f < b.num_factors; ++f)
     for (int a = 0; a < A; ++a) {
       const int64_t e = b.first_edge + f * A + a;
-      if (edge_ns[e] != edge_off[a + 1] - edge_off[a])
+      if (edge_ns[e] != edge_ns[b.first_edge + a])
         return fail(PGX_ERR_UNSUPPORTED,
                     "enum block %d: factors with different numbers of states share one block; "
                     "split the group per state signature", idx);
@@ -261,6 +260,22 @@ int build_enum_block(pgx_plan* plan, const pgx_enum_block& b, int idx,
                 (long long)e);
       edge_covered[e] = 1;
     }
+  return PGX_OK;
+}
+
+// Builds the device structures of one group of enum blocks that share the configuration
+// table and the per-variable state counts (`members` index desc_blocks; one member = the
+// usual case of an EnumFactorGroup; many members = e.g. the RCN graphs, where every factor
+// is its own group but only a handful of distinct tables exist, examples/rcn.ipynb cell 26).
+int build_enum_block(pgx_plan* plan, const pgx_enum_block* desc_blocks, const std::vector<int>& members,
+                     const std::vector<int64_t>& edge_msg_start, const std::vector<int32_t>& edge_ns,
+                     EnumBlockPlan* out) {
+  const pgx_enum_block& b = desc_blocks[members[0]];
+  const int idx = members[0];
+  const int A = b.arity, K = b.num_configs;
+  std::vector<int32_t> edge_off(A + 1, 0);
+  for (int a = 0; a < A; ++a) edge_off[a + 1] = edge_off[a] + edge_ns[b.first_edge + a];
+  const int ns = edge_off[A];
   std::vector<int32_t> cfg_es(size_t(K) * A), t_ptr(ns + 1, 0), t_k(size_t(K) * A);
   for (int k = 0; k < K; ++k)
     for (int a = 0; a < A; ++a) {
@@ -289,7 +304,27 @@ int build_enum_block(pgx_plan* plan, const pgx_enum_block& b, int idx,
   if ((rc = upload(t_ptr, &out->d_t_ptr, &plan->device_bytes))) return rc;
   if ((rc = upload(t_k, &out->d_t_k, &plan->device_bytes))) return rc;
   if ((rc = upload(edge_off, &out->d_edge_off, &plan->device_bytes))) return rc;
-  out->dev.num_factors = b.num_factors;
+  int64_t total = 0;
+  for (int m : members) total += desc_blocks[m].num_factors;
+  if (members.size() > 1) {  // factors are not an arithmetic progression: per-factor offsets
+    std::vector<int32_t> fe, fm, fp;
+    fe.reserve(total); fm.reserve(total); fp.reserve(total);
+    for (int m : members) {
+      const pgx_enum_block& mb = desc_blocks[m];
+      for (int64_t f = 0; f < mb.num_factors; ++f) {
+        fe.push_back(int32_t(mb.first_edge + f * A));
+        fm.push_back(int32_t(mb.first_msg + f * ns));
+        fp.push_back(int32_t(mb.first_potential + f * K));
+      }
+    }
+    if ((rc = upload(fe, &out->d_fac_edge, &plan->device_bytes))) return rc;
+    if ((rc = upload(fm, &out->d_fac_msg, &plan->device_bytes))) return rc;
+    if ((rc = upload(fp, &out->d_fac_pot, &plan->device_bytes))) return rc;
+  }
+  out->dev.fac_edge = out->d_fac_edge;
+  out->dev.fac_msg = out->d_fac_msg;
+  out->dev.fac_pot = out->d_fac_pot;
+  out->dev.num_factors = total;
   out->dev.first_edge = b.first_edge;
   out->dev.first_msg = b.first_msg;
   out->dev.first_pot = b.first_potential;
@@ -531,10 +566,48 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
                                        desc->pool_factors.num_parents};
   std::vector<uint8_t> edge_covered(plan->num_edges, 0);
   PGX_REQUIRE(desc->num_enum_blocks == 0 || desc->enum_blocks, "enum_blocks is null");
-  plan->enum_blocks.resize(desc->num_enum_blocks);
-  for (int i = 0; i < desc->num_enum_blocks; ++i)
-    PGX_TRY(build_enum_block(plan, desc->enum_blocks[i], i, edge_msg_start, edge_ns, edge_covered,
-                             &plan->enum_blocks[i]));
+  {
+    // Blocks with identical (arity, configuration table, state counts) share one set of device
+    // tables and one launch, except full pairwise-binary blocks (those keep their arithmetic
+    // indexing for the dense-grid / pull kernels).
+    std::vector<std::vector<int>> groups;
+    std::unordered_map<uint64_t, std::vector<int>> by_hash;  // hash -> group indices
+    for (int i = 0; i < desc->num_enum_blocks; ++i) {
+      const pgx_enum_block& b = desc->enum_blocks[i];
+      PGX_TRY(check_enum_block(plan, b, i, edge_msg_start, edge_ns, edge_covered));
+      const size_t nbytes = size_t(b.num_configs) * b.arity * sizeof(int32_t);
+      uint64_t h = 1469598103934665603ull;
+      auto mix = [&h](const void* p, size_t n) {
+        const unsigned char* c = static_cast<const unsigned char*>(p);
+        for (size_t k = 0; k < n; ++k) h = (h ^ c[k]) * 1099511628211ull;
+      };
+      mix(&b.arity, sizeof(b.arity));
+      mix(&b.num_configs, sizeof(b.num_configs));
+      for (int a = 0; a < b.arity; ++a) mix(&edge_ns[b.first_edge + a], sizeof(int32_t));
+      mix(b.configs, nbytes);
+      const bool pw2 = b.arity == 2 && b.num_configs == 4 && edge_ns[b.first_edge] == 2 &&
+                       edge_ns[b.first_edge + 1] == 2;
+      int found = -1;
+      if (!pw2)
+        for (int gi : by_hash[h]) {
+          const pgx_enum_block& r = desc->enum_blocks[groups[gi][0]];
+          bool same = r.arity == b.arity && r.num_configs == b.num_configs &&
+                      std::memcmp(r.configs, b.configs, nbytes) == 0;
+          for (int a = 0; a < b.arity && same; ++a) same = edge_ns[r.first_edge + a] == edge_ns[b.first_edge + a];
+          if (same) { found = gi; break; }
+        }
+      if (found < 0) {
+        if (!pw2) by_hash[h].push_back(int(groups.size()));
+        groups.push_back({i});
+      } else {
+        groups[found].push_back(i);
+      }
+    }
+    plan->enum_blocks.resize(groups.size());
+    for (size_t gi = 0; gi < groups.size(); ++gi)
+      PGX_TRY(build_enum_block(plan, desc->enum_blocks, groups[gi], edge_msg_start, edge_ns,
+                               &plan->enum_blocks[gi]));
+  }
   PGX_TRY(build_logical(plan, desc->or_factors, edge_msg_start, edge_vs, edge_ns, edge_covered, "OR factors",
                         &plan->or_f));
   PGX_TRY(build_logical(plan, desc->and_factors, edge_msg_start, edge_vs, edge_ns, edge_covered,
@@ -546,7 +619,7 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
   for (int64_t e = 0; e < plan->num_edges; ++e)
     PGX_REQUIRE(edge_covered[e], "edge %lld belongs to no factor description", (long long)e);
   {  // pull mode: all factors pairwise-binary, every variable of degree <= kPullMaxDegree
-    constexpr int64_t kPullMaxDegree = 8;
+    constexpr int64_t kPullMaxDegree = pgx::kPullMaxDegree;
     bool ok = !plan->enum_blocks.empty() && plan->or_f.dev.num_factors == 0 &&
               plan->and_f.dev.num_factors == 0 && plan->pool_f.dev.num_factors == 0;
     for (const EnumBlockPlan& eb : plan->enum_blocks) ok = ok && eb.variant == kPw2;
@@ -564,9 +637,9 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, plan->device);
       if (coop) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plan->coop_blocks_per_sm[0],
-                                                      pgx::k_enum_pw2_pull_persistent<false>, pgx::kThreads, 0);
+                                                      pgx::k_enum_pw2_pull_resident<false, false>, pgx::kThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&plan->coop_blocks_per_sm[1],
-                                                      pgx::k_enum_pw2_pull_persistent<true>, pgx::kThreads, 0);
+                                                      pgx::k_enum_pw2_pull_resident<true, false>, pgx::kThreads, 0);
       }
       plan->pull_ok = true;
     }
@@ -701,6 +774,7 @@ void pgx_plan_destroy(pgx_plan* plan) {
   free_dev(plan->d_var_first_state); free_dev(plan->d_var_ptr); free_dev(plan->d_var_edge_msg);
   for (EnumBlockPlan& eb : plan->enum_blocks) {
     free_dev(eb.d_cfg_es); free_dev(eb.d_t_ptr); free_dev(eb.d_t_k); free_dev(eb.d_edge_off);
+    free_dev(eb.d_fac_edge); free_dev(eb.d_fac_msg); free_dev(eb.d_fac_pot);
   }
   for (LogicalPlan* lg : {&plan->or_f, &plan->and_f, &plan->pool_f}) {
     free_dev(lg->d_parent_ptr); free_dev(lg->d_parents_msg); free_dev(lg->d_parents_vs);
@@ -868,22 +942,60 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     };
     const int ks = temperature == 0.f ? 0 : 1;
     const EnumBlockPlan& eb0 = plan->enum_blocks[0];
-    const dim3 grid0 = grid_for(plan, mp, eb0.dev.num_factors);
+    // resident kernels: one thread per (factor, sample)
+    const int upw = 32 >> mp.bx_log;
+    const int64_t res_warps = ((eb0.dev.num_factors + upw - 1) / upw) * mp.nbt;
+    const bool res_ok = plan->enum_blocks.size() == 1 && num_iters >= 2 && !plan->profiling;
+    const bool cluster = res_ok && res_warps * 32 <= int64_t(pgx::kResidentClusterCtas) * pgx::kResidentClusterThreads;
     const int64_t coop_cap = int64_t(plan->coop_blocks_per_sm[ks]) * plan->num_sms;
-    const bool persistent = plan->enum_blocks.size() == 1 && num_iters >= 2 && !plan->profiling &&
-                            eb0.dev.num_factors * batch <= (int64_t(1) << 20) &&
-                            int64_t(grid0.x) * grid0.y <= coop_cap;
-    if (persistent) {
+    const int64_t coop_blocks = (res_warps * 32 + pgx::kThreads - 1) / pgx::kThreads;
+    bool cluster_done = false;
+    pgx::PullArgs g0 = pull_args(eb0);
+    pgx::BatchMap mpv = mp;
+    float* out = single ? ftov_out : nullptr;
+    int iters = num_iters;
+    if (cluster) {
+      const int ctas = int(std::min<int64_t>(pgx::kResidentClusterCtas, (res_warps + 3) / 4));
+      const int threads = int((res_warps + ctas - 1) / ctas) * 32;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(ctas);
+      cfg.blockDim = dim3(threads);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = ctas;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      unsigned int* no_bar = nullptr;
+      cudaError_t err;
+      if (ks) {
+        cudaFuncSetAttribute(pgx::k_enum_pw2_pull_resident<true, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        err = cudaLaunchKernelEx(&cfg, pgx::k_enum_pw2_pull_resident<true, true>, mpv, g0, ev, lp, cur, ws.mA, ws.mB,
+                                 out, iters, a, no_bar);
+      } else {
+        cudaFuncSetAttribute(pgx::k_enum_pw2_pull_resident<false, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        err = cudaLaunchKernelEx(&cfg, pgx::k_enum_pw2_pull_resident<false, true>, mpv, g0, ev, lp, cur, ws.mA, ws.mB,
+                                 out, iters, a, no_bar);
+      }
+      if (err == cudaSuccess) {
+        if ((rc = check_launch(plan, "k_enum_pw2_pull_resident<cluster>"))) return rc;
+        cluster_done = true;
+      } else {
+        cudaGetLastError();  // cluster shape not schedulable here: use the cooperative variant
+      }
+    }
+    const bool coop = res_ok && !cluster_done && coop_blocks <= coop_cap;
+    if (coop) {
       PGX_CUDA(cudaMemsetAsync(plan->d_grid_bar, 0, sizeof(unsigned int), st));
-      pgx::PullArgs g = pull_args(eb0);
-      pgx::BatchMap mpv = mp;
-      float* out = single ? ftov_out : nullptr;
-      int iters = num_iters;
-      void* args[] = {&mpv, &g, &ev, &lp, &cur, &ws.mA, &ws.mB, &out, &iters, &a, &plan->d_grid_bar};
-      const void* fn = ks ? reinterpret_cast<const void*>(pgx::k_enum_pw2_pull_persistent<true>)
-                          : reinterpret_cast<const void*>(pgx::k_enum_pw2_pull_persistent<false>);
-      PGX_CUDA(cudaLaunchCooperativeKernel(fn, grid0, dim3(pgx::kThreads), args, 0, st));
-      if ((rc = check_launch(plan, "k_enum_pw2_pull_persistent"))) return rc;
+      void* args[] = {&mpv, &g0, &ev, &lp, &cur, &ws.mA, &ws.mB, &out, &iters, &a, &plan->d_grid_bar};
+      const void* fn = ks ? reinterpret_cast<const void*>(pgx::k_enum_pw2_pull_resident<true, false>)
+                          : reinterpret_cast<const void*>(pgx::k_enum_pw2_pull_resident<false, false>);
+      PGX_CUDA(cudaLaunchCooperativeKernel(fn, dim3(unsigned(coop_blocks)), dim3(pgx::kThreads), args, 0, st));
+      if ((rc = check_launch(plan, "k_enum_pw2_pull_resident<coop>"))) return rc;
+    }
+    if (cluster_done || coop) {
       // where the kernel left the final messages (same rule as in the kernel)
       float* nx = (cur == ws.mA) ? ws.mB : ws.mA;
       for (int it = 0; it < num_iters; ++it) {

@@ -76,13 +76,15 @@ struct UnitLoop {
   int b;
   bool b_ok;
   int64_t u, u_end;
-  int step;
+  int64_t step;
 };
 
 // Splits `num_units` graph elements over the grid.  blockIdx.y is the sample tile;
-// within a tile every warp walks a contiguous chunk of elements, so a warp streams a
-// contiguous span of its tile's arrays and re-reads of the (small) index arrays by
-// the other tiles hit L2.
+// within a tile the warps sweep the elements together (grid-stride): at any moment the
+// whole grid works on one contiguous window of the tile's arrays, so neighbouring
+// elements' data (gathers into adjacent grid rows, shared index entries) is still in
+// L2 when it is needed again, and re-reads of the (small) index arrays by the other
+// tiles hit L2.
 __device__ __forceinline__ UnitLoop unit_loop(const BatchMap& mp, int64_t num_units) {
   UnitLoop L;
   const int lane = threadIdx.x & 31;
@@ -92,12 +94,9 @@ __device__ __forceinline__ UnitLoop unit_loop(const BatchMap& mp, int64_t num_un
   const int upw = 32 >> mp.bx_log;  // elements handled side by side in one warp
   L.b = blockIdx.y * bx + (lane & (bx - 1));
   L.b_ok = L.b < mp.batch;
-  int64_t chunk = (num_units + nwarps - 1) / nwarps;
-  chunk = (chunk + upw - 1) / upw * upw;
-  const int64_t u0 = gwarp * chunk;
-  L.u_end = min(u0 + chunk, num_units);
-  L.u = min(u0, num_units) + (lane >> mp.bx_log);
-  L.step = upw;
+  L.u = gwarp * upw + (lane >> mp.bx_log);
+  L.u_end = num_units;
+  L.step = nwarps * upw;
   return L;
 }
 
@@ -347,6 +346,8 @@ k_enum_pw2(BatchMap mp, int64_t num_factors, int64_t first_edge, int64_t first_m
 // (neighbouring factors share variables); HBM sees the messages once.
 // edge_csr[e] = (begin, end) of the CSR row of edge e's variable.
 // ---------------------------------------------------------------------------
+constexpr int kPullMaxDegree = 6;
+
 struct PullArgs {
   int64_t num_factors, first_edge, first_msg, first_pot;
   const int32_t* edge_vs;
@@ -371,15 +372,26 @@ __device__ __forceinline__ float pull_factors(const BatchMap& mp, const UnitLoop
     const int64_t vs0 = g.edge_vs[e], vs1 = g.edge_vs[e + 1];
     const int2 c0 = g.edge_csr[e], c1 = g.edge_csr[e + 1];
     float Sv[4] = {evL.at(vs0), evL.at(vs0 + 1), evL.at(vs1), evL.at(vs1 + 1)};
-    for (int k = c0.x; k < c0.y; ++k) {
-      const int64_t ms = g.var_edge_msg[k];
-      Sv[0] += mo[ms << sh];
-      Sv[1] += mo[(ms + 1) << sh];
+    // incident-edge lists (degree <= kPullMaxDegree): all index loads first, then all
+    // message loads, then the additions in ascending message order
+    int32_t i0[kPullMaxDegree], i1[kPullMaxDegree];
+#pragma unroll
+    for (int k = 0; k < kPullMaxDegree; ++k) {
+      i0[k] = (c0.x + k < c0.y) ? g.var_edge_msg[c0.x + k] : -1;
+      i1[k] = (c1.x + k < c1.y) ? g.var_edge_msg[c1.x + k] : -1;
     }
-    for (int k = c1.x; k < c1.y; ++k) {
-      const int64_t ms = g.var_edge_msg[k];
-      Sv[2] += mo[ms << sh];
-      Sv[3] += mo[(ms + 1) << sh];
+    float g0[kPullMaxDegree][2], g1[kPullMaxDegree][2];
+#pragma unroll
+    for (int k = 0; k < kPullMaxDegree; ++k) {
+      g0[k][0] = i0[k] >= 0 ? mo[int64_t(i0[k]) << sh] : 0.f;
+      g0[k][1] = i0[k] >= 0 ? mo[int64_t(i0[k] + 1) << sh] : 0.f;
+      g1[k][0] = i1[k] >= 0 ? mo[int64_t(i1[k]) << sh] : 0.f;
+      g1[k][1] = i1[k] >= 0 ? mo[int64_t(i1[k] + 1) << sh] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kPullMaxDegree; ++k) {
+      if (i0[k] >= 0) { Sv[0] += g0[k][0]; Sv[1] += g0[k][1]; }
+      if (i1[k] >= 0) { Sv[2] += g1[k][0]; Sv[3] += g1[k][1]; }
     }
     const int64_t mb = g.first_msg + 4 * f;
     const float m[4] = {mo[mb << sh], mo[(mb + 1) << sh], mo[(mb + 2) << sh], mo[(mb + 3) << sh]};
@@ -405,42 +417,104 @@ k_enum_pw2_pull(BatchMap mp, PullArgs g, View ev, View lp, const float* __restri
   publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
 }
 
-// Persistent variant for graphs that are ONE pull block and small enough to be
-// latency-bound (Ising 50x50: 20 000 messages, 1000 iterations): all iterations in one
-// cooperative launch, one grid-wide barrier per iteration instead of two kernel launches.
+// Resident variant for graphs that are ONE pull block and small enough that every
+// (factor, sample) pair gets its own thread (Ising 50x50: 5 000 factors, 1000
+// iterations: latency-bound, the working set lives in L2): ALL iterations in one
+// launch.  Each thread keeps its factor's indices, evidence and potentials in
+// registers across iterations; per iteration it issues its (<= 2 * degree + 4)
+// message loads at once (ld.global.cg: other SMs rewrite the buffers), updates,
+// stores, and joins one barrier:
+//   kCluster = true : the grid is ONE thread-block cluster (<= 16 CTAs); the barrier is
+//                     the hardware cluster barrier (arrive.release / wait.acquire);
+//   kCluster = false: cooperative launch; barrier = monotonic counter in global memory.
 // Buffers: iteration 0 reads `src0`; iteration `it` writes `out` if it is the last one
 // and out != null, else it ping-pongs between bufA and bufB (never writing src0).
-template <bool kSumProduct>
-__global__ void __launch_bounds__(kThreads)
-k_enum_pw2_pull_persistent(BatchMap mp, PullArgs g, View ev, View lp, const float* src0, float* bufA,
-                           float* bufB, float* out, int num_iters, RunArgs a, unsigned int* bar) {
-  UnitLoop L = unit_loop(mp, g.num_factors);
-  const int64_t moff = L.b_ok ? lane_off(mp, a.Es, L.b) : 0;
-  const LaneView evL = lane_view(ev, mp, L.b_ok ? L.b : 0), lpL = lane_view(lp, mp, L.b_ok ? L.b : 0);
-  const unsigned int nblocks = gridDim.x * gridDim.y;
+constexpr int kResidentClusterThreads = 384;
+constexpr int kResidentClusterCtas = 16;  // non-portable cluster size (B200 allows 16)
+
+template <bool kSumProduct, bool kCluster>
+__global__ void __launch_bounds__(kCluster ? kResidentClusterThreads : kThreads)
+k_enum_pw2_pull_resident(BatchMap mp, PullArgs g, View ev, View lp, const float* src0, float* bufA,
+                         float* bufB, float* out, int num_iters, RunArgs a, unsigned int* bar) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int bx = 1 << mp.bx_log, upw = 32 >> mp.bx_log, sh = mp.bx_log;
+  const int64_t wpt = (g.num_factors + upw - 1) / upw;  // warps per sample tile
+  const int tile = int(gwarp / wpt);
+  const int64_t f = (gwarp - int64_t(tile) * wpt) * upw + (lane >> mp.bx_log);
+  const int b = tile * bx + (lane & (bx - 1));
+  const bool ok = tile < mp.nbt && f < g.num_factors && b < mp.batch;
+
+  // loop-invariant state of this thread's factor
+  int32_t i0[kPullMaxDegree], i1[kPullMaxDegree];
+  float ev4[4] = {0.f, 0.f, 0.f, 0.f}, lpv[4] = {0.f, 0.f, 0.f, 0.f};
+  int64_t moff = 0, mb = 0;
+#pragma unroll
+  for (int k = 0; k < kPullMaxDegree; ++k) i0[k] = i1[k] = -1;
+  if (ok) {
+    const int64_t e = g.first_edge + 2 * f;
+    const int64_t vs0 = g.edge_vs[e], vs1 = g.edge_vs[e + 1];
+    const int2 c0 = g.edge_csr[e], c1 = g.edge_csr[e + 1];
+#pragma unroll
+    for (int k = 0; k < kPullMaxDegree; ++k) {
+      if (c0.x + k < c0.y) i0[k] = g.var_edge_msg[c0.x + k];
+      if (c1.x + k < c1.y) i1[k] = g.var_edge_msg[c1.x + k];
+    }
+    const LaneView evL = lane_view(ev, mp, b), lpL = lane_view(lp, mp, b);
+    ev4[0] = evL.at(vs0); ev4[1] = evL.at(vs0 + 1); ev4[2] = evL.at(vs1); ev4[3] = evL.at(vs1 + 1);
+    const int64_t pb = g.first_pot + 4 * f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) lpv[k] = clip_lp(lpL.at(pb + k));
+    moff = lane_off(mp, a.Es, b);
+    mb = g.first_msg + 4 * f;
+  }
+  const unsigned int nblocks = gridDim.x;
   const float* cur = src0;
   float* nxt = (src0 == bufA) ? bufB : bufA;
   for (int it = 0; it < num_iters; ++it) {
     float* dst = (it == num_iters - 1 && out != nullptr) ? out : nxt;
-    if (L.b_ok) {
-      a.delta_off = it;
-      const float dmax = pull_factors<kSumProduct, true>(mp, L, g, evL, lpL, cur + moff, dst + moff, a);
-      publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+    if (ok) {
+      const float* mo = cur + moff;
+      float g0[kPullMaxDegree][2], g1[kPullMaxDegree][2], m[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) m[k] = __ldcg(mo + ((mb + k) << sh));
+#pragma unroll
+      for (int k = 0; k < kPullMaxDegree; ++k) {
+        g0[k][0] = i0[k] >= 0 ? __ldcg(mo + (int64_t(i0[k]) << sh)) : 0.f;
+        g0[k][1] = i0[k] >= 0 ? __ldcg(mo + (int64_t(i0[k] + 1) << sh)) : 0.f;
+        g1[k][0] = i1[k] >= 0 ? __ldcg(mo + (int64_t(i1[k]) << sh)) : 0.f;
+        g1[k][1] = i1[k] >= 0 ? __ldcg(mo + (int64_t(i1[k] + 1) << sh)) : 0.f;
+      }
+      float Sv[4] = {ev4[0], ev4[1], ev4[2], ev4[3]};
+#pragma unroll
+      for (int k = 0; k < kPullMaxDegree; ++k) {
+        if (i0[k] >= 0) { Sv[0] += g0[k][0]; Sv[1] += g0[k][1]; }
+        if (i1[k] >= 0) { Sv[2] += g1[k][0]; Sv[3] += g1[k][1]; }
+      }
+      float n[4];
+      const float dmax = pw2_update<kSumProduct>(m, Sv, lpv, a, n);
+      float* mn = dst + moff;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mn[(mb + k) << sh] = n[k];
+      publish_delta(a.deltas, int64_t(b) * a.delta_stride + it, dmax);
     }
     nxt = (dst == bufA) ? bufB : bufA;
     cur = dst;
     if (it + 1 < num_iters) {
-      // grid-wide barrier (all CTAs are co-resident: cooperative launch): monotonic counter
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
-        const unsigned int target = (unsigned int)(it + 1) * nblocks;
-        while (*reinterpret_cast<volatile unsigned int*>(bar) < target) {
+      if (kCluster) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+      } else {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          __threadfence();
+          atomicAdd(bar, 1u);
+          const unsigned int target = (unsigned int)(it + 1) * nblocks;
+          while (*reinterpret_cast<volatile unsigned int*>(bar) < target) {
+          }
+          __threadfence();
         }
-        __threadfence();
+        __syncthreads();
       }
-      __syncthreads();
     }
   }
 }
@@ -713,6 +787,14 @@ struct EnumBlockDev {
   const int32_t* t_ptr;
   const int32_t* t_k;
   const int32_t* edge_off;  // [arity + 1]
+  // per-factor offsets when the block merges several descriptor blocks (else null and the
+  // factors are the arithmetic progression first_* + f * stride)
+  const int32_t* fac_edge;
+  const int32_t* fac_msg;
+  const int32_t* fac_pot;
+  __device__ __forceinline__ int64_t msg_base(int64_t f) const { return fac_msg ? fac_msg[f] : first_msg + f * ns; }
+  __device__ __forceinline__ int64_t edge_base(int64_t f) const { return fac_edge ? fac_edge[f] : first_edge + f * arity; }
+  __device__ __forceinline__ int64_t pot_base(int64_t f) const { return fac_pot ? fac_pot[f] : first_pot + f * num_configs; }
 };
 
 // ---------------------------------------------------------------------------
@@ -739,9 +821,9 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
   float q[kSmallMaxNS];
   float nv[kSmallMaxNS];
   for (int64_t f = L.u; f < L.u_end; f += L.step) {
-    const int64_t mbase = blk.first_msg + f * blk.ns;
-    const int64_t ebase = blk.first_edge + f * blk.arity;
-    const int64_t pbase = blk.first_pot + f * blk.num_configs;
+    const int64_t mbase = blk.msg_base(f);
+    const int64_t ebase = blk.edge_base(f);
+    const int64_t pbase = blk.pot_base(f);
     for (int e = 0; e < blk.arity; ++e) {
       const int64_t vs = edge_vs[ebase + e];
       for (int s = blk.edge_off[e]; s < blk.edge_off[e + 1]; ++s)
@@ -824,9 +906,9 @@ k_enum_big(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, V
     float* mn = m_new + moff;
     const float* SL = S + lane_off(mp, a.Vs, b);
     const LaneView lpL = lane_view(lp, mp, b);
-    const int64_t mbase = blk.first_msg + f * blk.ns;
-    const int64_t ebase = blk.first_edge + f * blk.arity;
-    const int64_t pbase = blk.first_pot + f * blk.num_configs;
+    const int64_t mbase = blk.msg_base(f);
+    const int64_t ebase = blk.edge_base(f);
+    const int64_t pbase = blk.pot_base(f);
     __syncthreads();  // previous unit done with q / nv
     for (int e = 0; e < blk.arity; ++e) {
       const int64_t vs = edge_vs[ebase + e];

@@ -223,3 +223,93 @@ def init_logical(bp, entry, data):
       evidence_updates={parents: data["ev_parents"], children: data["ev_children"]},
       ftov_msgs_updates=msgs,
   )
+
+
+def rcn_valid_configs(r: int, hps: int, vps: int) -> np.ndarray:
+  """Valid (state0, state1) pairs of an RCN lateral factor with perturb radius r
+  (examples/rcn.ipynb cell 24): pool positions within a Chebyshev box of radius r."""
+  rows, cols = 2 * hps + 1, 2 * vps + 1
+  r1, c1 = np.divmod(np.arange(rows * cols), cols)
+  configs = []
+  for i in range(rows * cols):
+    rr = np.arange(max(r1[i] - r, 0), min(r1[i] + r, 2 * hps) + 1)
+    cc = np.arange(max(c1[i] - r, 0), min(c1[i] + r, 2 * vps) + 1)
+    j = (rr[:, None] * cols + cc[None, :]).ravel()
+    configs.append(np.stack([np.full(j.shape, i), j], axis=1))
+  return np.concatenate(configs)
+
+
+def rcn_model(num_models=20, num_vars=80, hps=12, vps=12, radii=(2, 3, 5, 8), extra_edges=80, seed=0):
+  """Synthetic RCN-shaped graph (examples/rcn.ipynb cells 21-26; rcn.npz is not shipped):
+  per model `num_vars` variables with (2 hps + 1)(2 vps + 1) states, lateral pairwise
+  EnumFactors along a random spanning tree plus `extra_edges` random edges, each factor its
+  OWN EnumFactorGroup with the valid configs of a random perturb radius and zero potentials.
+  Returns (fg, variable groups, {VarGroup: evidence array})."""
+  rng = np.random.default_rng(seed)
+  M = (2 * hps + 1) * (2 * vps + 1)
+  tables = {r: rcn_valid_configs(r, hps, vps) for r in radii}
+  groups = [vgroup.NDVarArray(num_states=M, shape=(num_vars,)) for _ in range(num_models)]
+  fg = fgraph.FactorGraph(groups)
+  for vg in groups:
+    pairs = set()
+    order = rng.permutation(num_vars)
+    for k in range(1, num_vars):  # random spanning tree
+      pairs.add((int(order[rng.integers(k)]), int(order[k])))
+    while len(pairs) < num_vars - 1 + extra_edges:
+      i, j = rng.integers(num_vars, size=2)
+      if i != j and (int(i), int(j)) not in pairs and (int(j), int(i)) not in pairs:
+        pairs.add((int(i), int(j)))
+    for i, j in sorted(pairs):
+      r = int(rng.choice(radii))
+      fg.add_factors(fgroup.EnumFactorGroup(
+          variables_for_factors=[[vg[i], vg[j]]], factor_configs=tables[r]))
+  # bottom-up evidence in {+1, -1}: sparse edge map gathered per pool window (cell 34)
+  evidence = {vg: np.where(rng.random((num_vars, M)) < 0.05, 1.0, -1.0) for vg in groups}
+  return fg, groups, evidence
+
+
+def deconv_model(im_height=28, im_width=28, n_feat=5, feat_height=6, feat_width=6, n_chan=1):
+  """Binary deconvolution graph for ONE image (examples/pmp_binary_deconvolution.ipynb
+  cells 12-14): AND factors (S, W -> SW) and OR factors (SW... -> X).
+  Returns (fg, dict of the variable groups S, W, SW, X)."""
+  s_height, s_width = im_height - feat_height + 1, im_width - feat_width + 1
+  W = vgroup.NDVarArray(num_states=2, shape=(n_chan, n_feat, feat_height, feat_width))
+  S = vgroup.NDVarArray(num_states=2, shape=(1, n_feat, s_height, s_width))
+  SW = vgroup.NDVarArray(num_states=2, shape=(1, n_chan, im_height, im_width, n_feat, feat_height, feat_width))
+  X = vgroup.NDVarArray(num_states=2, shape=(1, n_chan, im_height, im_width))
+  fg = fgraph.FactorGraph(variable_groups=[S, W, SW, X])
+  and_vars, or_vars = [], {}
+  for c in range(n_chan):
+    for sh in range(s_height):
+      for sw in range(s_width):
+        for f in range(n_feat):
+          for fh in range(feat_height):
+            for fw in range(feat_width):
+              ih, iw = fh + sh, fw + sw
+              sw_var = SW[0, c, ih, iw, f, fh, fw]
+              and_vars.append([S[0, f, sh, sw], W[c, f, fh, fw], sw_var])
+              or_vars.setdefault((c, ih, iw), []).append(sw_var)
+  fg.add_factors(fgroup.ANDFactorGroup(and_vars))
+  fg.add_factors(fgroup.ORFactorGroup(
+      [parents + [X[0, c, ih, iw]] for (c, ih, iw), parents in or_vars.items()]))
+  return fg, dict(S=S, W=W, SW=SW, X=X)
+
+
+def deconv_evidence(groups, batch, seed=0, pW=0.25, pS=1e-75, pX=1e-100):
+  """Evidence of the deconvolution notebook (cells 19-21) for `batch` synthetic images:
+  random 5x5 features OR-convolved at Bernoulli locations; Gumbel noise on S and W."""
+  from scipy.special import logit
+  rng = np.random.default_rng(seed)
+  S, W, SW, X = groups["S"], groups["W"], groups["SW"], groups["X"]
+  _, n_chan, ih, iw = X.shape
+  imgs = np.zeros((batch, 1, n_chan, ih, iw))
+  feats = rng.random((4, 5, 5)) < 0.4
+  for b in range(batch):
+    for _ in range(6):
+      f, r, c = rng.integers(4), rng.integers(ih - 5), rng.integers(iw - 5)
+      imgs[b, 0, :, r : r + 5, c : c + 5] = np.maximum(imgs[b, 0, :, r : r + 5, c : c + 5], feats[f])
+  uW = np.zeros((batch,) + W.shape + (2,)); uW[..., 1] = logit(pW)
+  uS = np.zeros((batch,) + S.shape + (2,)); uS[..., 1] = logit(pS)
+  uX = np.zeros((batch,) + X.shape + (2,)); uX[..., 0] = (2 * imgs - 1) * logit(pX)
+  return {S: uS + rng.gumbel(size=uS.shape), W: uW + rng.gumbel(size=uW.shape),
+          SW: np.zeros((batch,) + SW.shape + (2,)), X: uX}

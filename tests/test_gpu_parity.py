@@ -302,3 +302,34 @@ def test_pull_mode_streaming_equals_persistent(temperature, batch):
   assert launches == 40 and name == "k_enum_pw2_pull"
   np.testing.assert_array_equal(persistent.ftov_msgs, streaming.ftov_msgs)
   np.testing.assert_array_equal(d_p, d_s)
+
+
+@pytest.mark.parametrize("temperature", [0.0, 1.0])
+def test_rcn_shaped_merged_single_factor_groups(temperature):
+  """RCN-shaped graph (examples/rcn.ipynb cell 26): every factor is its own EnumFactorGroup
+  but only a few distinct config tables exist; the plan merges them into one launch per table.
+  25-state variables -> 50 edge-states per factor (k_enum_small) and 81-state variables ->
+  162 edge-states (k_enum_big, shared-memory CTA kernel)."""
+  for hps, vps in ((2, 2), (4, 4)):
+    fg, groups, evidence = models.rcn_model(num_models=3, num_vars=7, hps=hps, vps=vps, radii=(1, 2),
+                                            extra_edges=4, seed=1)
+    bp = infer.BP(fg.bp_state, temperature=temperature)
+    arrays = bp.init(evidence_updates=evidence)
+    graph, want, want_d, got, got_d = _run_both(bp, arrays, 10, 0.5, temperature)
+    _finite_close(got.ftov_msgs, want, 1e-6 if temperature == 0.0 else 1e-5)
+    np.testing.assert_allclose(got_d, want_d, atol=1e-5)
+    states, _, _ = bp.context.decode(got)
+    w_states, _, _ = bp_oracle.decode_flat(graph, bp_oracle.flat_beliefs(graph, got.ftov_msgs, arrays.evidence))
+    np.testing.assert_array_equal(states, w_states)
+
+
+def test_deconvolution_logical_batched():
+  """Binary deconvolution (AND + OR factor groups, examples/pmp_binary_deconvolution.ipynb),
+  small image, batch of 5, max-product: GPU vs oracle."""
+  fg, groups = models.deconv_model(im_height=8, im_width=8, n_feat=2, feat_height=3, feat_width=3)
+  evidence = models.deconv_evidence(groups, batch=5)
+  bp = infer.BP(fg.bp_state, temperature=0.0)
+  arrays = bp.init(evidence_updates=evidence)
+  _, want, want_d, got, got_d = _run_both(bp, arrays, 15, 0.5, 0.0)
+  _finite_close(got.ftov_msgs, want, 1e-4)  # messages reach |logit(1e-100)| = 230: ulp 1.5e-5
+  np.testing.assert_allclose(got_d, want_d, rtol=1e-5, atol=1e-4)
