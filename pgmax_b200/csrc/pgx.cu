@@ -927,7 +927,15 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   // need no var-sum array: one kernel per block and iteration, bit-identical to the
   // two-pass path.  Small such graphs with a single block run ALL iterations in one
   // cooperative launch.
-  const bool pull = plan->pull_ok && !fused;
+  // (Large grids keep the two-pass path: re-deriving S per edge costs 4x the gathers and
+  // measured slower than k_var_sums + k_enum_pw2 once the graph no longer fits in cache.)
+  bool pull = false;
+  if (plan->pull_ok && !fused && plan->enum_blocks.size() == 1) {
+    const int upw0 = 32 >> mp.bx_log;
+    const int64_t warps0 = ((plan->enum_blocks[0].dev.num_factors + upw0 - 1) / upw0) * mp.nbt;
+    const int ks0 = temperature == 0.f ? 0 : 1;
+    pull = warps0 * 32 <= int64_t(plan->coop_blocks_per_sm[ks0]) * plan->num_sms * pgx::kThreads;
+  }
   if (pull) {
     auto pull_args = [&](const EnumBlockPlan& eb) {
       pgx::PullArgs g;
