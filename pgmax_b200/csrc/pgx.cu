@@ -321,6 +321,12 @@ int build_enum_block(pgx_plan* plan, const pgx_enum_block* desc_blocks, const st
     if ((rc = upload(fm, &out->d_fac_msg, &plan->device_bytes))) return rc;
     if ((rc = upload(fp, &out->d_fac_pot, &plan->device_bytes))) return rc;
   }
+  {  // configs sorted by the first variable's state (arity 2)?
+    bool sorted0 = A == 2;
+    for (int s0 = 0; s0 < edge_off[1] && sorted0; ++s0)
+      for (int j = t_ptr[s0]; j < t_ptr[s0 + 1] && sorted0; ++j) sorted0 = t_k[j] == j;
+    out->dev.sorted0 = sorted0 ? 1 : 0;
+  }
   out->dev.fac_edge = out->d_fac_edge;
   out->dev.fac_msg = out->d_fac_msg;
   out->dev.fac_pot = out->d_fac_pot;
@@ -438,9 +444,20 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
         PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big<kSum>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         big_attr[kSum] = true;
       }
-      pgx::k_enum_big<kSum><<<grid, pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old,
-                                                               m_new, a);
-      if ((rc = check_launch(plan, "k_enum_big"))) return rc;
+      if (!kSum && eb.dev.sorted0) {
+        static bool mp_attr = false;
+        if (!mp_attr) {
+          PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          mp_attr = true;
+        }
+        pgx::k_enum_big_maxprod<<<grid, pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old,
+                                                                   m_new, a);
+        if ((rc = check_launch(plan, "k_enum_big_maxprod"))) return rc;
+      } else {
+        pgx::k_enum_big<kSum><<<grid, pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old,
+                                                                 m_new, a);
+        if ((rc = check_launch(plan, "k_enum_big"))) return rc;
+      }
     }
     if ((rc = prof_mark(plan, st, int(bi)))) return rc;
   }

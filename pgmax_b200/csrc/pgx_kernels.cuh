@@ -217,7 +217,17 @@ k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int32_t* __res
     const int64_t k0 = var_ptr[var], k1 = var_ptr[var + 1];
     float acc = evL.at(v);
     int64_t k = k0;
-    for (; k + 4 <= k1; k += 4) {  // loads are independent of the running sum
+    // loads are independent of the running sum: issue 16 / 4 at a time (high-degree
+    // variables - RBM units, shared deconvolution features - would otherwise serialise
+    // one DRAM latency per edge), add in ascending order
+    for (; k + 16 <= k1; k += 16) {
+      float x[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) x[j] = mL[(var_edge_msg[k + j] + st) << sh];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc += x[j];
+    }
+    for (; k + 4 <= k1; k += 4) {
       const float a0 = mL[(var_edge_msg[k] + st) << sh];
       const float a1 = mL[(var_edge_msg[k + 1] + st) << sh];
       const float a2 = mL[(var_edge_msg[k + 2] + st) << sh];
@@ -792,6 +802,9 @@ struct EnumBlockDev {
   const int32_t* fac_edge;
   const int32_t* fac_msg;
   const int32_t* fac_pot;
+  // arity 2 and the configurations are sorted by the first variable's state: the configs of
+  // state a of variable 0 are the contiguous range [t_ptr[a], t_ptr[a + 1]) of k
+  int32_t sorted0;
   __device__ __forceinline__ int64_t msg_base(int64_t f) const { return fac_msg ? fac_msg[f] : first_msg + f * ns; }
   __device__ __forceinline__ int64_t edge_base(int64_t f) const { return fac_edge ? fac_edge[f] : first_edge + f * arity; }
   __device__ __forceinline__ int64_t pot_base(int64_t f) const { return fac_pot ? fac_pot[f] : first_pot + f * num_configs; }
@@ -963,6 +976,93 @@ k_enum_big(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, V
 }
 
 // ---------------------------------------------------------------------------
+// K2c-max: max-product update of large PAIRWISE factors whose configuration table is
+// sorted by the first variable's state (RCN lateral factors, examples/rcn.ipynb cell
+// 24-26).  Configuration-major: every valid configuration is visited ONCE per
+// iteration (the reference visits each twice, through 5 expanded R-sized arrays):
+// a warp owns a state a of variable 0, its lanes stride the contiguous config range of
+// a (coalesced reads of the table and of the potentials), s_k = (q_a + q_b) + lp_k,
+// the max over k for a by warp shuffle, for the partner states b by an ordered-int
+// atomicMax in shared memory.  max is order-independent, so the result is bit-identical
+// to the edge-state-major kernel and to the oracle.
+// Dynamic smem: 2 * ns floats + 32 floats.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_float_shared(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_enum_big_maxprod(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
+                   const float* __restrict__ S, const float* __restrict__ m_old,
+                   float* __restrict__ m_new, RunArgs a) {
+  extern __shared__ float smem[];
+  float* q = smem;
+  float* M = smem + blk.ns;
+  float* red = smem + 2 * blk.ns;
+  const int sh = mp.bx_log;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int n0 = blk.edge_off[1];  // states of variable 0
+  const int64_t total = blk.num_factors * mp.batch;
+  for (int64_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    const int64_t f = unit / mp.batch;
+    const int b = int(unit - f * mp.batch);
+    const int64_t moff = lane_off(mp, a.Es, b);
+    const float* mo = m_old + moff;
+    float* mn = m_new + moff;
+    const float* SL = S + lane_off(mp, a.Vs, b);
+    const LaneView lpL = lane_view(lp, mp, b);
+    const int64_t mbase = blk.msg_base(f), ebase = blk.edge_base(f), pbase = blk.pot_base(f);
+    __syncthreads();  // previous unit done with q / M
+    for (int e = 0; e < 2; ++e) {
+      const int64_t vs = edge_vs[ebase + e];
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        q[s] = SL[(vs + s - s0) << sh] - mo[(mbase + s) << sh];
+        M[s] = -INFINITY;
+      }
+    }
+    __syncthreads();
+    for (int s = warp; s < n0; s += nwarp) {
+      const int k0 = blk.t_ptr[s], k1 = blk.t_ptr[s + 1];
+      const float qa = q[s];
+      float best = -INFINITY;
+      for (int k = k0 + lane; k < k1; k += 32) {
+        const int es_b = blk.cfg_es[2 * k + 1];
+        const float sk = (qa + q[es_b]) + clip_lp(lpL.at(pbase + k));
+        best = fmaxf(best, sk);
+        atomic_max_float_shared(&M[es_b], sk);
+      }
+      for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (lane == 0) M[s] = best;
+    }
+    __syncthreads();
+    float dmax = 0.f;
+    for (int e = 0; e < 2; ++e) {
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      float mx = -INFINITY;
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        // f = M - q, damped; M is reused to hold the damped value
+        const float nvs = damp(mo[(mbase + s) << sh], M[s] - q[s], a.d, a.one_minus_d);
+        M[s] = nvs;
+        mx = fmaxf(mx, nvs);
+      }
+      mx = block_max(mx, red);
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const float out = fmaxf(M[s] - mx, kMsgNegInf);
+        const int64_t idx = (mbase + s) << sh;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
+      }
+    }
+    if (a.deltas != nullptr) {
+      dmax = block_max(dmax, red);
+      if (threadIdx.x == 0) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Writes the two states of a binary edge whose factor->variable message is
 // (0, x) or (x, 0): damping + normalisation + clip + delta.
 //   lo = message index of the edge's state 0; mo / mn are lane pointers.
@@ -997,8 +1097,63 @@ struct LogicalDev {
 // ---------------------------------------------------------------------------
 // K4: OR / AND update, closed form from per-factor sums and the two largest
 // parent differences (pgmax/factor/logical.py:561-779).
-// One thread per (factor, sample); two passes over the parents.
+// One thread per (factor, sample).  Factors with <= kRegParents parents (the AND
+// factors of the deconvolution graphs have 2) keep the parents' variable->factor
+// messages in registers: every message is read once.  Wider factors (ORs with up
+// to 180 parents) make two passes over the parents, loading kChunk parents' worth
+// of independent gathers at a time.
 // ---------------------------------------------------------------------------
+constexpr int kRegParents = 4;
+constexpr int kParentChunk = 4;
+
+// Arithmetic shared by both paths, exactly App. A.3.
+struct LogicalAcc {
+  float Sb = 0.f, acc = 0.f, d1 = -INFINITY, d2 = -INFINITY;
+  int64_t istar = 0;
+  template <bool kSumProduct>
+  __device__ __forceinline__ void add(int64_t i, float a_i, float b_i, float T) {
+    const float dl = a_i - b_i;
+    Sb += b_i;
+    acc += kSumProduct ? logaddexp_t(a_i, b_i, T) : fmaxf(b_i, a_i);
+    if (dl >= d1) { d2 = d1; d1 = dl; istar = i; }  // first arg-max = LARGEST tied index
+    else if (dl > d2) d2 = dl;
+  }
+  template <bool kSumProduct>
+  __device__ __forceinline__ float child_relevant(float T) const {
+    if (kSumProduct) {
+      float CR = logminusexp_t(acc, Sb, T, 1e-4f);
+      if (T < kTempStabThre) CR = fmaxf(CR, logaddexp_t(Sb + d1, Sb + d2, T));
+      return CR;
+    }
+    return acc + fminf(0.f, d1);
+  }
+  // message difference (relevant - other) to parent i
+  template <bool kSumProduct>
+  __device__ __forceinline__ float parent_out(int64_t i, float a_i, float b_i, float ca, float cb,
+                                              float T, bool single) const {
+    float PR, PO;
+    if (kSumProduct) {
+      const float l_i = logaddexp_t(a_i, b_i, T);
+      const float Lw = acc - l_i, Sw = Sb - b_i;
+      PR = ca + Lw;
+      const float o1 = cb + Sw, o2 = ca + Lw, o3 = ca + Sw;
+      PO = logminusexp_t(logaddexp_t(o1, o2, T), o3, T, 1e-4f);
+      if (T < kTempStabThre) {
+        const float bound = (i == istar) ? (Sw + d2) : (Sw + d1);
+        PO = fmaxf(PO, logaddexp_t(o1, ca + bound, T));
+      }
+    } else {
+      const float mu = fmaxf(b_i, a_i);
+      PR = (acc + ca) - mu;
+      const float o1 = (cb + Sb) - b_i;
+      const float o2 = PR + ((i == istar) ? fminf(0.f, d2) : fminf(0.f, d1));
+      PO = fmaxf(o1, o2);
+    }
+    if (single) { PR = ca; PO = cb; }  // logical.py:739-757
+    return PR - PO;
+  }
+};
+
 template <bool kSumProduct>
 __global__ void __launch_bounds__(kThreads)
 k_logical(BatchMap mp, LogicalDev w, const float* __restrict__ S,
@@ -1013,66 +1168,79 @@ k_logical(BatchMap mp, LogicalDev w, const float* __restrict__ S,
   const float* SL = S + lane_off(mp, a.Vs, L.b);
   const int off = w.off;
   const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  // variable->factor message of the wiring's state (at msg index pm / var-state pv) and of
+  // the "relevant" state (+off)
+  auto q_rel = [&](int64_t pm, int64_t pv) { return SL[(pv + off) << sh] - mo[(pm + off) << sh]; };
+  auto q_oth = [&](int64_t pm, int64_t pv) { return SL[pv << sh] - mo[pm << sh]; };
+  auto write_edge = [&](int64_t pm, float x) {  // x = message of the "+off" state; the other state gets 0
+    const int64_t lo = (off > 0) ? pm : pm - 1;
+    dmax = fmaxf(dmax, write_binary_edge(mo, mn, lo, sh, off > 0 ? 0.f : x, off > 0 ? x : 0.f, d, one_minus_d));
+  };
   for (int64_t f = L.u; f < L.u_end; f += L.step) {
     const int64_t p0 = w.parent_ptr[f], p1 = w.parent_ptr[f + 1];
     const int64_t c = w.children_msg[f], cvs = w.children_vs[f];
-    const float ca = SL[(cvs + off) << sh] - mo[(c + off) << sh];  // "relevant" state
-    const float cb = SL[cvs << sh] - mo[c << sh];                  // "other" state
-    // Pass 1: sums in ascending parent order, first / second max of the differences
-    // (first arg-max = LARGEST tied index, update_utils.py:51-63).
-    float Sb = 0.f, acc = 0.f, d1 = -INFINITY, d2 = -INFINITY;
-    int64_t istar = p0;
-    for (int64_t i = p0; i < p1; ++i) {
-      const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
-      const float a_i = SL[(pv + off) << sh] - mo[(pm + off) << sh];
-      const float b_i = SL[pv << sh] - mo[pm << sh];
-      const float dl = a_i - b_i;
-      Sb += b_i;
-      acc += kSumProduct ? logaddexp_t(a_i, b_i, T) : fmaxf(b_i, a_i);
-      if (dl >= d1) { d2 = d1; d1 = dl; istar = i; }
-      else if (dl > d2) d2 = dl;
-    }
+    const float ca = q_rel(c, cvs), cb = q_oth(c, cvs);
     const bool single = (p1 - p0) == 1;
-    float CR;
-    if (kSumProduct) {
-      CR = logminusexp_t(acc, Sb, T, 1e-4f);
-      if (T < kTempStabThre) CR = fmaxf(CR, logaddexp_t(Sb + d1, Sb + d2, T));
-    } else {
-      CR = acc + fminf(0.f, d1);
-    }
-    // Pass 2: outgoing messages to the parents.
-    for (int64_t i = p0; i < p1; ++i) {
-      const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
-      const float a_i = SL[(pv + off) << sh] - mo[(pm + off) << sh];
-      const float b_i = SL[pv << sh] - mo[pm << sh];
-      float PR, PO;
-      if (kSumProduct) {
-        const float l_i = logaddexp_t(a_i, b_i, T);
-        const float Lw = acc - l_i, Sw = Sb - b_i;
-        PR = ca + Lw;
-        const float o1 = cb + Sw, o2 = ca + Lw, o3 = ca + Sw;
-        PO = logminusexp_t(logaddexp_t(o1, o2, T), o3, T, 1e-4f);
-        if (T < kTempStabThre) {
-          const float bound = (i == istar) ? (Sw + d2) : (Sw + d1);
-          PO = fmaxf(PO, logaddexp_t(o1, ca + bound, T));
+    LogicalAcc A;
+    A.istar = p0;
+    if (p1 - p0 <= kRegParents) {
+      int64_t pm[kRegParents];
+      float av[kRegParents], bv[kRegParents];
+#pragma unroll
+      for (int j = 0; j < kRegParents; ++j) {
+        if (p0 + j < p1) {
+          pm[j] = w.parents_msg[p0 + j];
+          const int64_t pv = w.parents_vs[p0 + j];
+          av[j] = q_rel(pm[j], pv);
+          bv[j] = q_oth(pm[j], pv);
         }
-      } else {
-        const float mu = fmaxf(b_i, a_i);
-        PR = (acc + ca) - mu;
-        const float o1 = (cb + Sb) - b_i;
-        const float o2 = PR + ((i == istar) ? fminf(0.f, d2) : fminf(0.f, d1));
-        PO = fmaxf(o1, o2);
       }
-      if (single) { PR = ca; PO = cb; }  // logical.py:739-757
-      const float x = PR - PO;          // message of the "p_i + off" state; the other state gets 0
-      const int64_t lo = (off > 0) ? pm : pm - 1;
-      dmax = fmaxf(dmax, write_binary_edge(mo, mn, lo, sh, off > 0 ? 0.f : x, off > 0 ? x : 0.f, d,
-                                           one_minus_d));
+#pragma unroll
+      for (int j = 0; j < kRegParents; ++j)
+        if (p0 + j < p1) A.add<kSumProduct>(p0 + j, av[j], bv[j], T);
+#pragma unroll
+      for (int j = 0; j < kRegParents; ++j)
+        if (p0 + j < p1) write_edge(pm[j], A.parent_out<kSumProduct>(p0 + j, av[j], bv[j], ca, cb, T, single));
+    } else {
+      // Pass 1: sums in ascending parent order, first / second max of the differences.
+      int64_t i = p0;
+      for (; i + kParentChunk <= p1; i += kParentChunk) {
+        float av[kParentChunk], bv[kParentChunk];
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j) {
+          const int64_t pm = w.parents_msg[i + j], pv = w.parents_vs[i + j];
+          av[j] = q_rel(pm, pv);
+          bv[j] = q_oth(pm, pv);
+        }
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j) A.add<kSumProduct>(i + j, av[j], bv[j], T);
+      }
+      for (; i < p1; ++i) {
+        const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
+        A.add<kSumProduct>(i, q_rel(pm, pv), q_oth(pm, pv), T);
+      }
+      // Pass 2: outgoing messages to the parents.
+      i = p0;
+      for (; i + kParentChunk <= p1; i += kParentChunk) {
+        int64_t pm[kParentChunk];
+        float av[kParentChunk], bv[kParentChunk];
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j) {
+          pm[j] = w.parents_msg[i + j];
+          const int64_t pv = w.parents_vs[i + j];
+          av[j] = q_rel(pm[j], pv);
+          bv[j] = q_oth(pm[j], pv);
+        }
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j)
+          write_edge(pm[j], A.parent_out<kSumProduct>(i + j, av[j], bv[j], ca, cb, T, single));
+      }
+      for (; i < p1; ++i) {
+        const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
+        write_edge(pm, A.parent_out<kSumProduct>(i, q_rel(pm, pv), q_oth(pm, pv), ca, cb, T, single));
+      }
     }
-    const float xc = CR - Sb;
-    const int64_t lo = (off > 0) ? c : c - 1;
-    dmax = fmaxf(dmax, write_binary_edge(mo, mn, lo, sh, off > 0 ? 0.f : xc, off > 0 ? xc : 0.f, d,
-                                         one_minus_d));
+    write_edge(c, A.child_relevant<kSumProduct>(T) - A.Sb);
   }
   publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
 }
