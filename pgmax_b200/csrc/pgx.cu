@@ -82,6 +82,7 @@ struct BipPlan {
 
 struct LogicalPlan {
   pgx::LogicalDev dev{};
+  int64_t max_parents = 0;
   int32_t *d_parent_ptr = nullptr, *d_parents_msg = nullptr, *d_parents_vs = nullptr, *d_children_msg = nullptr,
           *d_children_vs = nullptr;
 };
@@ -109,6 +110,7 @@ struct pgx_plan {
   // device index structures
   int32_t* d_edge_vs = nullptr;          // [num_edges] var-state of each edge's state 0
   int32_t* d_edge_msg_start = nullptr;   // [num_edges + 1]
+  int4* d_vs_csr = nullptr;              // [V_s] (CSR begin, end, state offset, 0) of each var-state
   int32_t* d_vs_var = nullptr;           // [V_s] variable of each var-state
   int32_t* d_var_first_state = nullptr;  // [num_vars + 1]
   int32_t* d_var_ptr = nullptr;          // [num_vars + 1] CSR offsets
@@ -228,6 +230,13 @@ int build_logical(pgx_plan* plan, const pgx_logical_desc& d, const std::vector<i
   if ((rc = upload(pvs, &out->d_parents_vs, &plan->device_bytes))) return rc;
   if ((rc = upload(cmsg, &out->d_children_msg, &plan->device_bytes))) return rc;
   if ((rc = upload(cvs, &out->d_children_vs, &plan->device_bytes))) return rc;
+  {
+    const int64_t n0 = ptr[1] - ptr[0];
+    bool uniform = true;
+    for (int64_t f = 0; f < d.num_factors && uniform; ++f) uniform = ptr[f + 1] - ptr[f] == n0;
+    out->dev.uniform = uniform ? int32_t(n0) : 0;
+    for (int64_t f = 0; f < d.num_factors; ++f) out->max_parents = std::max<int64_t>(out->max_parents, ptr[f + 1] - ptr[f]);
+  }
   out->dev.parent_ptr = out->d_parent_ptr;
   out->dev.parents_msg = out->d_parents_msg;
   out->dev.parents_vs = out->d_parents_vs;
@@ -466,8 +475,12 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
     const int id = lid--;
     if (lg->dev.num_factors == 0) continue;
     if ((rc = prof_mark(plan, st, id))) return rc;
-    pgx::k_logical<kSum><<<grid_for(plan, mp, lg->dev.num_factors), pgx::kThreads, 0, st>>>(
-        mp, lg->dev, S, m_old, m_new, a);
+    if (lg->max_parents <= pgx::kRegParents)
+      pgx::k_logical<kSum, true><<<grid_for(plan, mp, lg->dev.num_factors), pgx::kThreads, 0, st>>>(
+          mp, lg->dev, S, m_old, m_new, a);
+    else
+      pgx::k_logical<kSum, false><<<grid_for(plan, mp, lg->dev.num_factors), pgx::kThreads, 0, st>>>(
+          mp, lg->dev, S, m_old, m_new, a);
     if ((rc = check_launch(plan, "k_logical"))) return rc;
     if ((rc = prof_mark(plan, st, id))) return rc;
   }
@@ -573,6 +586,14 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
   }
   PGX_TRY(upload(edge_vs, &plan->d_edge_vs, &plan->device_bytes));
   PGX_TRY(upload(narrow(edge_msg_start), &plan->d_edge_msg_start, &plan->device_bytes));
+  {
+    std::vector<int4> vs_csr(plan->num_var_states);
+    for (int64_t s = 0; s < plan->num_var_states; ++s) {
+      const int32_t var = vs_var[s];
+      vs_csr[s] = make_int4(int(var_ptr[var]), int(var_ptr[var + 1]), int(s - var_first_state[var]), 0);
+    }
+    PGX_TRY(upload(vs_csr, &plan->d_vs_csr, &plan->device_bytes));
+  }
   PGX_TRY(upload(vs_var, &plan->d_vs_var, &plan->device_bytes));
   PGX_TRY(upload(var_first_state, &plan->d_var_first_state, &plan->device_bytes));
   PGX_TRY(upload(narrow(var_ptr), &plan->d_var_ptr, &plan->device_bytes));
@@ -787,6 +808,7 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
 
 void pgx_plan_destroy(pgx_plan* plan) {
   if (plan == nullptr) return;
+  free_dev(plan->d_vs_csr);
   free_dev(plan->d_edge_vs); free_dev(plan->d_edge_msg_start); free_dev(plan->d_vs_var);
   free_dev(plan->d_var_first_state); free_dev(plan->d_var_ptr); free_dev(plan->d_var_edge_msg);
   for (EnumBlockPlan& eb : plan->enum_blocks) {
@@ -1053,8 +1075,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     a.delta_off = it;
     if (!fused || it == 0) {
       pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(
-          mp, Vs, Es, plan->d_vs_var, plan->d_var_first_state, plan->d_var_ptr, plan->d_var_edge_msg, ev, cur,
-          ws.S);
+          mp, Vs, Es, plan->d_vs_csr, plan->d_var_edge_msg, ev, cur, ws.S);
       if ((rc = check_launch(plan, "k_var_sums"))) return rc;
     }
     // With one sample the last iteration writes straight into the caller's buffer.

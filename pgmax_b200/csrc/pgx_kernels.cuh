@@ -201,22 +201,27 @@ k_normalize_edges(BatchMap mp, int64_t num_edges, int64_t Es,
 // walking the variable's incident-edge list (CSR built by the plan).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int32_t* __restrict__ vs_var,
-           const int32_t* __restrict__ var_first_state, const int32_t* __restrict__ var_ptr,
+k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int4* __restrict__ vs_csr,
            const int32_t* __restrict__ var_edge_msg, View ev, const float* __restrict__ m,
            float* __restrict__ S) {
+  // vs_csr[v] = (begin, end, state offset within the variable, unused): one index load per
+  // var-state instead of the chain var-state -> variable -> CSR row; the entry of the
+  // thread's NEXT var-state is fetched while the current one is summed.
   UnitLoop L = unit_loop(mp, num_var_states);
   if (!L.b_ok) return;
   const LaneView evL = lane_view(ev, mp, L.b);
   const float* mL = m + lane_off(mp, Es, L.b);
   float* SL = S + lane_off(mp, num_var_states, L.b);
   const int sh = mp.bx_log;
-  for (int64_t v = L.u; v < L.u_end; v += L.step) {
-    const int var = vs_var[v];
-    const int64_t st = v - var_first_state[var];
-    const int64_t k0 = var_ptr[var], k1 = var_ptr[var + 1];
+  int64_t v = L.u;
+  int4 row = v < L.u_end ? vs_csr[v] : make_int4(0, 0, 0, 0);
+  while (v < L.u_end) {
+    const int64_t vn = v + L.step;
+    const int4 next = vn < L.u_end ? vs_csr[vn] : make_int4(0, 0, 0, 0);
+    const int64_t st = row.z;
+    const int64_t k1 = row.y;
     float acc = evL.at(v);
-    int64_t k = k0;
+    int64_t k = row.x;
     // loads are independent of the running sum: issue 16 / 4 at a time (high-degree
     // variables - RBM units, shared deconvolution features - would otherwise serialise
     // one DRAM latency per edge), add in ascending order
@@ -236,6 +241,8 @@ k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int32_t* __res
     }
     for (; k < k1; ++k) acc += mL[(var_edge_msg[k] + st) << sh];
     SL[v << sh] = acc;
+    v = vn;
+    row = next;
   }
 }
 
@@ -1092,6 +1099,7 @@ struct LogicalDev {
   const int32_t* children_msg;
   const int32_t* children_vs;
   int32_t off;  // +1 OR / Pool, -1 AND
+  int32_t uniform;  // > 0: every factor has exactly this many parents (parent_ptr[f] = f * uniform)
 };
 
 // ---------------------------------------------------------------------------
@@ -1104,7 +1112,7 @@ struct LogicalDev {
 // of independent gathers at a time.
 // ---------------------------------------------------------------------------
 constexpr int kRegParents = 4;
-constexpr int kParentChunk = 4;
+constexpr int kParentChunk = 8;
 
 // Arithmetic shared by both paths, exactly App. A.3.
 struct LogicalAcc {
@@ -1154,7 +1162,9 @@ struct LogicalAcc {
   }
 };
 
-template <bool kSumProduct>
+// kNarrow: every factor of the group has <= kRegParents parents (the wide path is compiled out,
+// which halves the register count and doubles the resident warps).
+template <bool kSumProduct, bool kNarrow>
 __global__ void __launch_bounds__(kThreads)
 k_logical(BatchMap mp, LogicalDev w, const float* __restrict__ S,
           const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
@@ -1176,23 +1186,41 @@ k_logical(BatchMap mp, LogicalDev w, const float* __restrict__ S,
     const int64_t lo = (off > 0) ? pm : pm - 1;
     dmax = fmaxf(dmax, write_binary_edge(mo, mn, lo, sh, off > 0 ? 0.f : x, off > 0 ? x : 0.f, d, one_minus_d));
   };
-  for (int64_t f = L.u; f < L.u_end; f += L.step) {
-    const int64_t p0 = w.parent_ptr[f], p1 = w.parent_ptr[f + 1];
-    const int64_t c = w.children_msg[f], cvs = w.children_vs[f];
+  // wiring of one factor; fetched one factor ahead so that its (dependent) index loads
+  // overlap the current factor's gathers
+  struct Wiring {
+    int64_t p0, p1;
+    int32_t c, cvs;
+    int32_t pm[kRegParents], pv[kRegParents];
+  };
+  auto load_wiring = [&](int64_t f, Wiring& x) {
+    if (w.uniform > 0) { x.p0 = f * w.uniform; x.p1 = x.p0 + w.uniform; }
+    else { x.p0 = w.parent_ptr[f]; x.p1 = w.parent_ptr[f + 1]; }
+    x.c = w.children_msg[f];
+    x.cvs = w.children_vs[f];
+    if (x.p1 - x.p0 <= kRegParents) {
+#pragma unroll
+      for (int j = 0; j < kRegParents; ++j)
+        if (x.p0 + j < x.p1) { x.pm[j] = w.parents_msg[x.p0 + j]; x.pv[j] = w.parents_vs[x.p0 + j]; }
+    }
+  };
+  Wiring cur_w, next_w;
+  if (L.u < L.u_end) load_wiring(L.u, cur_w);
+  for (int64_t f = L.u; f < L.u_end; f += L.step, cur_w = next_w) {
+    if (f + L.step < L.u_end) load_wiring(f + L.step, next_w);
+    const int64_t p0 = cur_w.p0, p1 = cur_w.p1;
+    const int64_t c = cur_w.c, cvs = cur_w.cvs;
     const float ca = q_rel(c, cvs), cb = q_oth(c, cvs);
     const bool single = (p1 - p0) == 1;
     LogicalAcc A;
     A.istar = p0;
-    if (p1 - p0 <= kRegParents) {
-      int64_t pm[kRegParents];
+    if (kNarrow || p1 - p0 <= kRegParents) {
       float av[kRegParents], bv[kRegParents];
 #pragma unroll
       for (int j = 0; j < kRegParents; ++j) {
         if (p0 + j < p1) {
-          pm[j] = w.parents_msg[p0 + j];
-          const int64_t pv = w.parents_vs[p0 + j];
-          av[j] = q_rel(pm[j], pv);
-          bv[j] = q_oth(pm[j], pv);
+          av[j] = q_rel(cur_w.pm[j], cur_w.pv[j]);
+          bv[j] = q_oth(cur_w.pm[j], cur_w.pv[j]);
         }
       }
 #pragma unroll
@@ -1200,8 +1228,9 @@ k_logical(BatchMap mp, LogicalDev w, const float* __restrict__ S,
         if (p0 + j < p1) A.add<kSumProduct>(p0 + j, av[j], bv[j], T);
 #pragma unroll
       for (int j = 0; j < kRegParents; ++j)
-        if (p0 + j < p1) write_edge(pm[j], A.parent_out<kSumProduct>(p0 + j, av[j], bv[j], ca, cb, T, single));
-    } else {
+        if (p0 + j < p1)
+          write_edge(cur_w.pm[j], A.parent_out<kSumProduct>(p0 + j, av[j], bv[j], ca, cb, T, single));
+    } else if (!kNarrow) {
       // Pass 1: sums in ascending parent order, first / second max of the differences.
       int64_t i = p0;
       for (; i + kParentChunk <= p1; i += kParentChunk) {
