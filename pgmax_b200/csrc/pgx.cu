@@ -475,7 +475,10 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
     const int id = lid--;
     if (lg->dev.num_factors == 0) continue;
     if ((rc = prof_mark(plan, st, id))) return rc;
-    if (lg->max_parents <= pgx::kRegParents)
+    if (lg->dev.uniform > 0 && lg->dev.uniform <= pgx::kRegParents)
+      pgx::k_logical_uniform<kSum><<<grid_for(plan, mp, lg->dev.num_factors), pgx::kThreads, 0, st>>>(
+          mp, lg->dev, S, m_old, m_new, a);
+    else if (lg->max_parents <= pgx::kRegParents)
       pgx::k_logical<kSum, true><<<grid_for(plan, mp, lg->dev.num_factors), pgx::kThreads, 0, st>>>(
           mp, lg->dev, S, m_old, m_new, a);
     else

@@ -200,49 +200,80 @@ k_normalize_edges(BatchMap mp, int64_t num_edges, int64_t Es,
 // scatter-add, pgmax/infer/bp.py:217).  One thread per (var-state, sample)
 // walking the variable's incident-edge list (CSR built by the plan).
 // ---------------------------------------------------------------------------
+constexpr int kVsUnits = 4;    // var-states processed together by one thread
+constexpr int kVsLowDeg = 4;   // ... when each has at most this many incident edges
+
 __global__ void __launch_bounds__(kThreads)
 k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int4* __restrict__ vs_csr,
            const int32_t* __restrict__ var_edge_msg, View ev, const float* __restrict__ m,
            float* __restrict__ S) {
   // vs_csr[v] = (begin, end, state offset within the variable, unused): one index load per
-  // var-state instead of the chain var-state -> variable -> CSR row; the entry of the
-  // thread's NEXT var-state is fetched while the current one is summed.
+  // var-state instead of the chain var-state -> variable -> CSR row.  A thread takes
+  // kVsUnits var-states per iteration: their rows are loaded together, and when all of them
+  // are low-degree (the common case in sparse graphs) so are all their gathers, which keeps
+  // 4 x more bytes in flight per thread than one short dependent chain at a time.
   UnitLoop L = unit_loop(mp, num_var_states);
   if (!L.b_ok) return;
   const LaneView evL = lane_view(ev, mp, L.b);
   const float* mL = m + lane_off(mp, Es, L.b);
   float* SL = S + lane_off(mp, num_var_states, L.b);
   const int sh = mp.bx_log;
-  int64_t v = L.u;
-  int4 row = v < L.u_end ? vs_csr[v] : make_int4(0, 0, 0, 0);
-  while (v < L.u_end) {
-    const int64_t vn = v + L.step;
-    const int4 next = vn < L.u_end ? vs_csr[vn] : make_int4(0, 0, 0, 0);
-    const int64_t st = row.z;
-    const int64_t k1 = row.y;
-    float acc = evL.at(v);
-    int64_t k = row.x;
-    // loads are independent of the running sum: issue 16 / 4 at a time (high-degree
-    // variables - RBM units, shared deconvolution features - would otherwise serialise
-    // one DRAM latency per edge), add in ascending order
-    for (; k + 16 <= k1; k += 16) {
-      float x[16];
+  for (int64_t v0 = L.u; v0 < L.u_end; v0 += kVsUnits * L.step) {
+    int4 row[kVsUnits];
+    bool low = true;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) x[j] = mL[(var_edge_msg[k + j] + st) << sh];
+    for (int u = 0; u < kVsUnits; ++u) {
+      const int64_t v = v0 + u * L.step;
+      row[u] = v < L.u_end ? vs_csr[v] : make_int4(0, 0, 0, 0);
+      low = low && (row[u].y - row[u].x <= kVsLowDeg);
+    }
+    if (low) {
+      float acc[kVsUnits], x[kVsUnits][kVsLowDeg];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc += x[j];
+      for (int u = 0; u < kVsUnits; ++u) {
+        const int64_t v = v0 + u * L.step;
+        acc[u] = v < L.u_end ? evL.at(v) : 0.f;
+#pragma unroll
+        for (int j = 0; j < kVsLowDeg; ++j)
+          x[u][j] = (row[u].x + j < row[u].y) ? mL[(int64_t(var_edge_msg[row[u].x + j]) + row[u].z) << sh] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kVsUnits; ++u) {
+#pragma unroll
+        for (int j = 0; j < kVsLowDeg; ++j)
+          if (row[u].x + j < row[u].y) acc[u] += x[u][j];
+        const int64_t v = v0 + u * L.step;
+        if (v < L.u_end) SL[v << sh] = acc[u];
+      }
+      continue;
     }
-    for (; k + 4 <= k1; k += 4) {
-      const float a0 = mL[(var_edge_msg[k] + st) << sh];
-      const float a1 = mL[(var_edge_msg[k + 1] + st) << sh];
-      const float a2 = mL[(var_edge_msg[k + 2] + st) << sh];
-      const float a3 = mL[(var_edge_msg[k + 3] + st) << sh];
-      acc += a0; acc += a1; acc += a2; acc += a3;
+#pragma unroll 1
+    for (int u = 0; u < kVsUnits; ++u) {
+      const int64_t v = v0 + u * L.step;
+      if (v >= L.u_end) break;
+      const int64_t st = row[u].z, k1 = row[u].y;
+      float acc = evL.at(v);
+      int64_t k = row[u].x;
+      // loads are independent of the running sum: issue 16 / 4 at a time (high-degree
+      // variables - RBM units, shared deconvolution features - would otherwise serialise
+      // one DRAM latency per edge), add in ascending order
+      for (; k + 16 <= k1; k += 16) {
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = mL[(var_edge_msg[k + j] + st) << sh];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc += x[j];
+      }
+      for (; k + 4 <= k1; k += 4) {
+        const float a0 = mL[(var_edge_msg[k] + st) << sh];
+        const float a1 = mL[(var_edge_msg[k + 1] + st) << sh];
+        const float a2 = mL[(var_edge_msg[k + 2] + st) << sh];
+        const float a3 = mL[(var_edge_msg[k + 3] + st) << sh];
+        acc += a0; acc += a1; acc += a2; acc += a3;
+      }
+      for (; k < k1; ++k) acc += mL[(var_edge_msg[k] + st) << sh];
+      SL[v << sh] = acc;
     }
-    for (; k < k1; ++k) acc += mL[(var_edge_msg[k] + st) << sh];
-    SL[v << sh] = acc;
-    v = vn;
-    row = next;
   }
 }
 
@@ -1161,6 +1192,78 @@ struct LogicalAcc {
     return PR - PO;
   }
 };
+
+// Groups whose factors all have the same number n <= kRegParents of parents (the AND
+// factors of the deconvolution graphs: n = 2).  One thread per (factor, sample), TWO factors
+// per iteration: the wiring of both is loaded first, then all their gathers (2 * 2(n + 1)
+// message / var-sum pairs in flight), then the closed form of App. A.3 for each.
+constexpr int kLogicalUnits = 2;
+
+template <bool kSumProduct>
+__global__ void __launch_bounds__(kThreads)
+k_logical_uniform(BatchMap mp, LogicalDev w, const float* __restrict__ S,
+                  const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  UnitLoop L = unit_loop(mp, w.num_factors);
+  if (!L.b_ok) return;
+  float dmax = 0.f;
+  const int sh = mp.bx_log;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const int off = w.off, n = w.uniform;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  auto write_edge = [&](int64_t pm, float x) {
+    const int64_t lo = (off > 0) ? pm : pm - 1;
+    dmax = fmaxf(dmax, write_binary_edge(mo, mn, lo, sh, off > 0 ? 0.f : x, off > 0 ? x : 0.f, d, one_minus_d));
+  };
+  for (int64_t f0 = L.u; f0 < L.u_end; f0 += kLogicalUnits * L.step) {
+    int32_t c[kLogicalUnits], cvs[kLogicalUnits], pm[kLogicalUnits][kRegParents], pv[kLogicalUnits][kRegParents];
+#pragma unroll
+    for (int u = 0; u < kLogicalUnits; ++u) {
+      const int64_t f = f0 + u * L.step;
+      if (f < L.u_end) {
+        c[u] = w.children_msg[f];
+        cvs[u] = w.children_vs[f];
+#pragma unroll
+        for (int j = 0; j < kRegParents; ++j)
+          if (j < n) { pm[u][j] = w.parents_msg[f * n + j]; pv[u][j] = w.parents_vs[f * n + j]; }
+      }
+    }
+    float ca[kLogicalUnits], cb[kLogicalUnits], av[kLogicalUnits][kRegParents], bv[kLogicalUnits][kRegParents];
+#pragma unroll
+    for (int u = 0; u < kLogicalUnits; ++u) {
+      if (f0 + u * L.step < L.u_end) {
+        ca[u] = SL[int64_t(cvs[u] + off) << sh] - mo[int64_t(c[u] + off) << sh];
+        cb[u] = SL[int64_t(cvs[u]) << sh] - mo[int64_t(c[u]) << sh];
+#pragma unroll
+        for (int j = 0; j < kRegParents; ++j)
+          if (j < n) {
+            av[u][j] = SL[int64_t(pv[u][j] + off) << sh] - mo[int64_t(pm[u][j] + off) << sh];
+            bv[u][j] = SL[int64_t(pv[u][j]) << sh] - mo[int64_t(pm[u][j]) << sh];
+          }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kLogicalUnits; ++u) {
+      const int64_t f = f0 + u * L.step;
+      if (f < L.u_end) {
+        const int64_t p0 = f * n;
+        LogicalAcc A;
+        A.istar = p0;
+#pragma unroll
+        for (int j = 0; j < kRegParents; ++j)
+          if (j < n) A.add<kSumProduct>(p0 + j, av[u][j], bv[u][j], T);
+#pragma unroll
+        for (int j = 0; j < kRegParents; ++j)
+          if (j < n)
+            write_edge(pm[u][j], A.parent_out<kSumProduct>(p0 + j, av[u][j], bv[u][j], ca[u], cb[u], T, n == 1));
+        write_edge(c[u], A.child_relevant<kSumProduct>(T) - A.Sb);
+      }
+    }
+  }
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
 
 // kNarrow: every factor of the group has <= kRegParents parents (the wide path is compiled out,
 // which halves the register count and doubles the resident warps).

@@ -174,7 +174,7 @@ def _logical_enum_configs(kind: str, num_parents: int) -> np.ndarray:
   return configs[ok]
 
 
-def logical_pair(kind: str, seed: int):
+def logical_pair(kind: str, seed: int, parents_range=(1, 10)):
   """Two equivalent graphs in the spirit of the reference's differential tests
   (tests/factor/test_or.py:30-290): graph A holds the first half of the factors
   as `kind` factors and the second half as their equivalent EnumFactors; graph B
@@ -182,7 +182,7 @@ def logical_pair(kind: str, seed: int):
   two graphs, their variable groups, and shared random evidence / initial messages."""
   rng = np.random.RandomState(seed)
   num_factors = rng.randint(10, 20)
-  num_parents = rng.randint(1, 10, num_factors)
+  num_parents = rng.randint(parents_range[0], parents_range[1], num_factors)
   cum = np.insert(np.cumsum(num_parents), 0, 0)
   group_cls = {"or": fgroup.ORFactorGroup, "and": fgroup.ANDFactorGroup,
                "pool": fgroup.PoolFactorGroup}[kind]

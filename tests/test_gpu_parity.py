@@ -333,3 +333,21 @@ def test_deconvolution_logical_batched():
   _, want, want_d, got, got_d = _run_both(bp, arrays, 15, 0.5, 0.0)
   _finite_close(got.ftov_msgs, want, 1e-4)  # messages reach |logit(1e-100)| = 230: ulp 1.5e-5
   np.testing.assert_allclose(got_d, want_d, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("kind", ["or", "and"])
+@pytest.mark.parametrize("parents_range", [(1, 2), (3, 4), (1, 5)])
+@pytest.mark.parametrize("temperature", [0.0, 0.8])
+def test_logical_narrow_and_uniform_groups(kind, parents_range, temperature):
+  """Groups whose factors all have the same small number of parents (k_logical_uniform: 1 and
+  3 parents here, 2 in the deconvolution test) and ragged groups of <= 4 parents
+  (k_logical<narrow>), against the oracle and against the equivalent EnumFactors."""
+  data = models.logical_pair(kind, 2, parents_range=parents_range)
+  beliefs = []
+  for entry in data["graphs"]:
+    bp = infer.BP(entry[0].bp_state, temperature=temperature)
+    arrays = models.init_logical(bp, entry, data)
+    _, want, _, got, _ = _run_both(bp, arrays, 5, 0.5, temperature)
+    _finite_close(got.ftov_msgs, want, 2e-5)
+    beliefs.append(bp.context.flat_beliefs(got))
+  np.testing.assert_allclose(beliefs[0], beliefs[1], atol=1e-5, rtol=0)
