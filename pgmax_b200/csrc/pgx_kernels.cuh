@@ -369,18 +369,46 @@ k_enum_pw2(BatchMap mp, int64_t num_factors, int64_t first_edge, int64_t first_m
   float* mn = m_new + moff;
   const float* SL = S + lane_off(mp, a.Vs, L.b);
   const LaneView lpL = lane_view(lp, mp, L.b);
-  for (int64_t f = L.u; f < L.u_end; f += L.step) {
-    const int64_t e = first_edge + 2 * f;
-    const int64_t vs0 = edge_vs[e], vs1 = edge_vs[e + 1];
-    const int64_t mb = first_msg + 4 * f;
-    const float m[4] = {mo[mb << sh], mo[(mb + 1) << sh], mo[(mb + 2) << sh], mo[(mb + 3) << sh]};
-    const float Sv[4] = {SL[vs0 << sh], SL[(vs0 + 1) << sh], SL[vs1 << sh], SL[(vs1 + 1) << sh]};
-    const int64_t pb = first_pot + 4 * f;
-    const float lpv[4] = {clip_lp(lpL.at(pb)), clip_lp(lpL.at(pb + 1)), clip_lp(lpL.at(pb + 2)),
-                          clip_lp(lpL.at(pb + 3))};
-    float n[4];
-    dmax = fmaxf(dmax, pw2_update<kSumProduct>(m, Sv, lpv, a, n));
-    mn[mb << sh] = n[0]; mn[(mb + 1) << sh] = n[1]; mn[(mb + 2) << sh] = n[2]; mn[(mb + 3) << sh] = n[3];
+  // One sample (flat vectors, one factor per lane): the factor's 4 messages, its 4 potentials
+  // and each variable's 2 sums are contiguous -> 128-bit / 64-bit accesses when aligned.
+  const bool vec = sh == 0 && lpL.sh == 0 && ((first_msg | first_pot) & 3) == 0 && (first_edge & 1) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(mo) | reinterpret_cast<uintptr_t>(mn) |
+                     reinterpret_cast<uintptr_t>(lpL.q)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(SL) & 7) == 0;
+  if (vec) {
+    for (int64_t f = L.u; f < L.u_end; f += L.step) {
+      const int2 vs = *reinterpret_cast<const int2*>(edge_vs + first_edge + 2 * f);
+      const int64_t mb = first_msg + 4 * f;
+      const float4 m4 = *reinterpret_cast<const float4*>(mo + mb);
+      const float4 l4 = *reinterpret_cast<const float4*>(lpL.q + first_pot + 4 * f);
+      float Sv[4];
+      if (((vs.x | vs.y) & 1) == 0) {
+        const float2 s0 = *reinterpret_cast<const float2*>(SL + vs.x);
+        const float2 s1 = *reinterpret_cast<const float2*>(SL + vs.y);
+        Sv[0] = s0.x; Sv[1] = s0.y; Sv[2] = s1.x; Sv[3] = s1.y;
+      } else {
+        Sv[0] = SL[vs.x]; Sv[1] = SL[vs.x + 1]; Sv[2] = SL[vs.y]; Sv[3] = SL[vs.y + 1];
+      }
+      const float m[4] = {m4.x, m4.y, m4.z, m4.w};
+      const float lpv[4] = {clip_lp(l4.x), clip_lp(l4.y), clip_lp(l4.z), clip_lp(l4.w)};
+      float n[4];
+      dmax = fmaxf(dmax, pw2_update<kSumProduct>(m, Sv, lpv, a, n));
+      *reinterpret_cast<float4*>(mn + mb) = make_float4(n[0], n[1], n[2], n[3]);
+    }
+  } else {
+    for (int64_t f = L.u; f < L.u_end; f += L.step) {
+      const int64_t e = first_edge + 2 * f;
+      const int64_t vs0 = edge_vs[e], vs1 = edge_vs[e + 1];
+      const int64_t mb = first_msg + 4 * f;
+      const float m[4] = {mo[mb << sh], mo[(mb + 1) << sh], mo[(mb + 2) << sh], mo[(mb + 3) << sh]};
+      const float Sv[4] = {SL[vs0 << sh], SL[(vs0 + 1) << sh], SL[vs1 << sh], SL[(vs1 + 1) << sh]};
+      const int64_t pb = first_pot + 4 * f;
+      const float lpv[4] = {clip_lp(lpL.at(pb)), clip_lp(lpL.at(pb + 1)), clip_lp(lpL.at(pb + 2)),
+                            clip_lp(lpL.at(pb + 3))};
+      float n[4];
+      dmax = fmaxf(dmax, pw2_update<kSumProduct>(m, Sv, lpv, a, n));
+      mn[mb << sh] = n[0]; mn[(mb + 1) << sh] = n[1]; mn[(mb + 2) << sh] = n[2]; mn[(mb + 3) << sh] = n[3];
+    }
   }
   publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
 }
