@@ -110,7 +110,7 @@ struct pgx_plan {
   // device index structures
   int32_t* d_edge_vs = nullptr;          // [num_edges] var-state of each edge's state 0
   int32_t* d_edge_msg_start = nullptr;   // [num_edges + 1]
-  int4* d_vs_csr = nullptr;              // [V_s] (CSR begin, end, state offset, 0) of each var-state
+  int2* d_vs_csr = nullptr;              // [V_s] (CSR begin, degree << 12 | state offset) of each var-state
   int32_t* d_vs_var = nullptr;           // [V_s] variable of each var-state
   int32_t* d_var_first_state = nullptr;  // [num_vars + 1]
   int32_t* d_var_ptr = nullptr;          // [num_vars + 1] CSR offsets
@@ -590,10 +590,14 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
   PGX_TRY(upload(edge_vs, &plan->d_edge_vs, &plan->device_bytes));
   PGX_TRY(upload(narrow(edge_msg_start), &plan->d_edge_msg_start, &plan->device_bytes));
   {
-    std::vector<int4> vs_csr(plan->num_var_states);
+    std::vector<int2> vs_csr(plan->num_var_states);
     for (int64_t s = 0; s < plan->num_var_states; ++s) {
       const int32_t var = vs_var[s];
-      vs_csr[s] = make_int4(int(var_ptr[var]), int(var_ptr[var + 1]), int(s - var_first_state[var]), 0);
+      const int64_t deg = var_ptr[var + 1] - var_ptr[var], st = s - var_first_state[var];
+      if (st >= (1 << pgx::kVsStateBits) || deg >= (int64_t(1) << (31 - pgx::kVsStateBits)))
+        return bail(fail(PGX_ERR_UNSUPPORTED, "variable %d: %lld states / %lld incident edges exceed the packed CSR row format",
+                         var, (long long)desc->var_num_states[var], (long long)deg));
+      vs_csr[s] = make_int2(int(var_ptr[var]), int((deg << pgx::kVsStateBits) | st));
     }
     PGX_TRY(upload(vs_csr, &plan->d_vs_csr, &plan->device_bytes));
   }

@@ -200,15 +200,16 @@ k_normalize_edges(BatchMap mp, int64_t num_edges, int64_t Es,
 // scatter-add, pgmax/infer/bp.py:217).  One thread per (var-state, sample)
 // walking the variable's incident-edge list (CSR built by the plan).
 // ---------------------------------------------------------------------------
+constexpr int kVsStateBits = 12;  // vs_csr packing: states per variable < 4096, degree < 2^19
 constexpr int kVsUnits = 4;    // var-states processed together by one thread
 constexpr int kVsLowDeg = 4;   // ... when each has at most this many incident edges
 
 __global__ void __launch_bounds__(kThreads)
-k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int4* __restrict__ vs_csr,
+k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int2* __restrict__ vs_csr,
            const int32_t* __restrict__ var_edge_msg, View ev, const float* __restrict__ m,
            float* __restrict__ S) {
-  // vs_csr[v] = (begin, end, state offset within the variable, unused): one index load per
-  // var-state instead of the chain var-state -> variable -> CSR row.  A thread takes
+  // vs_csr[v] = (CSR begin, degree << kVsStateBits | state offset within the variable): one
+  // 8-byte index load per var-state instead of the chain var-state -> variable -> CSR row.  A thread takes
   // kVsUnits var-states per iteration: their rows are loaded together, and when all of them
   // are low-degree (the common case in sparse graphs) so are all their gathers, which keeps
   // 4 x more bytes in flight per thread than one short dependent chain at a time.
@@ -219,12 +220,13 @@ k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int4* __restri
   float* SL = S + lane_off(mp, num_var_states, L.b);
   const int sh = mp.bx_log;
   for (int64_t v0 = L.u; v0 < L.u_end; v0 += kVsUnits * L.step) {
-    int4 row[kVsUnits];
+    int4 row[kVsUnits];  // (begin, end, state offset)
     bool low = true;
 #pragma unroll
     for (int u = 0; u < kVsUnits; ++u) {
       const int64_t v = v0 + u * L.step;
-      row[u] = v < L.u_end ? vs_csr[v] : make_int4(0, 0, 0, 0);
+      const int2 r = v < L.u_end ? vs_csr[v] : make_int2(0, 0);
+      row[u] = make_int4(r.x, r.x + (r.y >> kVsStateBits), r.y & ((1 << kVsStateBits) - 1), 0);
       low = low && (row[u].y - row[u].x <= kVsLowDeg);
     }
     if (low) {
