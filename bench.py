@@ -157,7 +157,7 @@ def run_ising_big(args):
     es = 8 * n * n
     bytes_iter = 17 * es  # 4 * (2 + 0.25 + 1 + 1) * E_s, SURVEY.md 8(d)
     iter_s = ms * 1e-3 / args.steps / iters
-    peak = FALLBACK_HBM_GBS
+    peak, peak_src = hbm_peak()
     line = {
         "metric": METRIC, "value": es * iters * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -170,13 +170,21 @@ def run_ising_big(args):
         "roofline": {"bound": "hbm", "achieved": bytes_iter / iter_s / 1e9 / world, "peak": peak, "unit": "GB/s",
                      "frac": bytes_iter / iter_s / 1e9 / world / peak, "traffic": None,
                      "kernel": "whole iteration (k_var_sums + k_enum_pw2), per GPU",
-                     "algorithmic_bytes_per_launch": bytes_iter // world, "peak_source": "fallback",
+                     "algorithmic_bytes_per_launch": bytes_iter // world, "peak_source": peak_src,
                      "iter_ms": iter_s * 1e3},
         "checksum_max_abs_msg": float(msgs.abs().max().item()),
     }
     print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
+
+
+def hbm_peak():
+  """(GB/s, source): MEASURED_PEAKS.json's copy bandwidth, else the profiling guide's fallback."""
+  try:
+    return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+  except (OSError, KeyError, ValueError):
+    return FALLBACK_HBM_GBS, "fallback"
 
 
 def algorithmic_bytes_per_iter(plan, batch, lp_batched):
@@ -262,7 +270,7 @@ def _cpu_worker_run(args):
   return float(msgs.sum())
 
 
-def cpu_arm(name, steps, warmup, iters_per_sample):
+def cpu_arm(name, steps, warmup, iters_per_sample, budget_s=8.0):
   """Oracle throughput with one process per host core; each step = `cores` independent
   samples x `iters_per_sample` iterations of the workload's graph."""
   import multiprocessing as mp
@@ -270,8 +278,12 @@ def cpu_arm(name, steps, warmup, iters_per_sample):
   ctx = mp.get_context("spawn")
   with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(name,)) as pool:
     pool.map(_cpu_worker_run, [(i, 1) for i in range(cores)])  # touch everything once
-    for _ in range(warmup):
+    t1 = time.perf_counter()
+    for _ in range(max(warmup, 1)):
       pool.map(_cpu_worker_run, [(i, 1) for i in range(cores)])
+    t1 = (time.perf_counter() - t1) / max(warmup, 1)
+    # bounded sample: about `budget_s` seconds of oracle work per step
+    iters_per_sample = max(1, min(iters_per_sample, int(budget_s / max(t1, 1e-6))))
     t0 = time.perf_counter()
     for s in range(steps):
       pool.map(_cpu_worker_run, [(s * cores + i, iters_per_sample) for i in range(cores)])
@@ -426,13 +438,7 @@ def main():
     ms, e2e_ms = t.tolist()
 
   if rank == 0:
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak, peak_src = FALLBACK_HBM_GBS, "fallback"
-    if os.path.exists(peaks_path):
-      try:
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
-      except (KeyError, ValueError):
-        pass
+    peak, peak_src = hbm_peak()
     lp_batched = host.log_potentials.ndim == 2
     bytes_iter = algorithmic_bytes_per_iter(plan, batch, lp_batched)
     traffic = None
@@ -469,15 +475,15 @@ def main():
         "checksum_max_abs_msg": checksum,
     }
     if world == 1 and not args.no_cpu_baseline:
-      sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",
-                            "--workload", args.workload, "--steps", "2", "--warmup", "1"],
-                           capture_output=True, text=True)
       try:
+        sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",
+                              "--workload", args.workload, "--steps", "2", "--warmup", "1"],
+                             capture_output=True, text=True, timeout=240)
         ref = json.loads(sub.stdout.strip().splitlines()[-1])
         line["cpu_baseline"] = ref["cpu_baseline"]
-      except (IndexError, ValueError, KeyError):
+      except (IndexError, ValueError, KeyError, subprocess.TimeoutExpired) as err:
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
-                                "sample": "failed: " + sub.stderr[-300:]}
+                                "sample": "failed: " + repr(err)[-300:]}
     print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()

@@ -195,6 +195,22 @@ int pgx_plan_set_exact_order(pgx_plan* plan, int enabled);
 /* Number of enum blocks for which the single-pass path is available. */
 int pgx_plan_num_fused_blocks(const pgx_plan* plan);
 
+/* Specialised launch paths pgx_bp_run may choose from the graph's structure.  Every path
+ * computes the same arithmetic in the same order (bit-identical messages); the mask only
+ * exists so that tests and profiles can pin a path.  Default: nothing disabled.
+ *   PGX_PATH_LATTICE   index-free stencil kernel for a graph that is one 2-D lattice of
+ *                      pairwise binary factors (Ising grids, batch == 1)
+ *   PGX_PATH_RESIDENT  all iterations of a small pairwise graph in one cluster /
+ *                      cooperative launch
+ *   PGX_PATH_PULL      pairwise kernels that re-derive the variable sums per factor
+ *                      instead of materialising them */
+#define PGX_PATH_LATTICE 1u
+#define PGX_PATH_RESIDENT 2u
+#define PGX_PATH_PULL 4u
+int pgx_plan_disable_paths(pgx_plan* plan, uint32_t mask);
+/* 1 if the lattice path is available for this plan. */
+int pgx_plan_is_lattice(const pgx_plan* plan);
+
 /* Device-time instrumentation for the roofline figure (bench.py).  While
  * enabled, pgx_bp_run brackets, in every iteration, the launch of the plan's
  * dominant kernel (the factor->variable kernel that covers the most

@@ -36,6 +36,8 @@ EXPORTED_SYMBOLS = (
     "pgx_plan_launch_count",
     "pgx_plan_set_exact_order",
     "pgx_plan_num_fused_blocks",
+    "pgx_plan_disable_paths",
+    "pgx_plan_is_lattice",
     "pgx_plan_profile_enable",
     "pgx_plan_profile_read",
     "pgx_last_error",
@@ -158,6 +160,10 @@ def load() -> ctypes.CDLL:
   lib.pgx_plan_num_fused_blocks.restype = ctypes.c_int
   lib.pgx_plan_set_exact_order.argtypes = [vp, ctypes.c_int]
   lib.pgx_plan_set_exact_order.restype = ctypes.c_int
+  lib.pgx_plan_disable_paths.argtypes = [vp, ctypes.c_uint32]
+  lib.pgx_plan_disable_paths.restype = ctypes.c_int
+  lib.pgx_plan_is_lattice.argtypes = [vp]
+  lib.pgx_plan_is_lattice.restype = ctypes.c_int
   lib.pgx_plan_profile_enable.argtypes = [vp, ctypes.c_int]
   lib.pgx_plan_profile_enable.restype = ctypes.c_int
   lib.pgx_plan_profile_read.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double),
@@ -354,6 +360,16 @@ class Plan:
   def has_fused_blocks(self) -> bool:
     """True when the plan found dense-grid pairwise blocks (single-pass path available)."""
     return bool(self._lib.pgx_plan_num_fused_blocks(self.handle))
+
+  PATH_LATTICE, PATH_RESIDENT, PATH_PULL = 1, 2, 4
+
+  def disable_paths(self, mask: int) -> None:
+    """Pin the launch path (PGX_PATH_* bits of include/pgx.h); all paths are bit-identical."""
+    check(self._lib.pgx_plan_disable_paths(self.handle, int(mask)))
+
+  @property
+  def is_lattice(self) -> bool:
+    return bool(self._lib.pgx_plan_is_lattice(self.handle))
 
   def set_exact_order(self, enabled: bool) -> None:
     """Force the two-pass, serial-summation-order path (see pgx_plan_set_exact_order)."""

@@ -123,6 +123,10 @@ struct pgx_plan {
   int2* d_edge_csr = nullptr;          // [num_edges] CSR row (begin, end) of the edge's variable
   unsigned int* d_grid_bar = nullptr;  // barrier counter of the persistent kernel
   int coop_blocks_per_sm[2] = {0, 0};  // occupancy of k_enum_pw2_pull_resident<false / true, coop>
+  // lattice mode (the whole graph is one 2-D nearest-neighbour lattice block; LatticeDev)
+  bool lattice_ok = false;
+  pgx::LatticeDev lattice{};
+  uint32_t disabled_paths = 0;         // PGX_PATH_* bits (pgx_plan_disable_paths)
   // fused single-pass structures (dense-grid pairwise blocks)
   std::vector<BipPlan> bips;
   bool exact_order = false;            // force the two-pass, serial-order path
@@ -689,6 +693,36 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       plan->pull_ok = true;
     }
   }
+  // lattice mode: ONE pairwise-binary block whose factor 2u + t joins variable u with the
+  // variable one row below (t = 0) / one column to the right, wrapping (t = 1), and nothing else
+  if (plan->enum_blocks.size() == 1 && plan->enum_blocks[0].variant == kPw2 && plan->or_f.dev.num_factors == 0 &&
+      plan->and_f.dev.num_factors == 0 && plan->pool_f.dev.num_factors == 0) {
+    const EnumBlockPlan& eb = plan->enum_blocks[0];
+    const int64_t F = eb.dev.num_factors, e0 = eb.dev.first_edge;
+    const int64_t U = F / 2;
+    const int64_t N = (F >= 2 && F % 2 == 0) ? edge_vs[e0 + 1] / 2 : 0;
+    if (N >= 2 && U % N == 0 && edge_vs[e0] == 0 && (eb.dev.first_msg & 3) == 0 && (eb.dev.first_pot & 3) == 0) {
+      const int64_t R = U / N;
+      const bool torus = edge_vs[e0 + 4 * (R - 1) * N + 1] == 0;
+      const int64_t Rv = torus ? R : R + 1;
+      bool ok = plan->num_vars == Rv * N && R >= (torus ? 2 : 1) && R < INT32_MAX && N < INT32_MAX;
+      for (int64_t u = 0; u < U && ok; ++u) {
+        const int64_t l = u / N, j = u - l * N;
+        const int64_t below = torus ? ((l + 1) % R) * N + j : u + N;
+        const int64_t right = l * N + (j + 1) % N;
+        ok = edge_vs[e0 + 4 * u] == 2 * u && edge_vs[e0 + 4 * u + 2] == 2 * u &&
+             edge_vs[e0 + 4 * u + 1] == 2 * below && edge_vs[e0 + 4 * u + 3] == 2 * right;
+      }
+      if (ok) {
+        plan->lattice_ok = true;
+        plan->lattice.first_msg = eb.dev.first_msg;
+        plan->lattice.first_pot = eb.dev.first_pot;
+        plan->lattice.R = int32_t(R);
+        plan->lattice.N = int32_t(N);
+        plan->lattice.torus = torus ? 1 : 0;
+      }
+    }
+  }
   {  // dense-grid pairwise blocks -> fused single-pass structures
     std::vector<uint8_t> edge_fused(plan->num_edges, 0);
     std::vector<int32_t> part_count(plan->num_vars, 0);
@@ -861,6 +895,14 @@ int pgx_plan_set_exact_order(pgx_plan* plan, int enabled) {
 
 int pgx_plan_num_fused_blocks(const pgx_plan* plan) { return plan ? int(plan->bips.size()) : 0; }
 
+int pgx_plan_disable_paths(pgx_plan* plan, uint32_t mask) {
+  if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+  plan->disabled_paths = mask;
+  return PGX_OK;
+}
+
+int pgx_plan_is_lattice(const pgx_plan* plan) { return plan && plan->lattice_ok ? 1 : 0; }
+
 int pgx_plan_profile_enable(pgx_plan* plan, int enabled) {
   if (!plan) return fail(PGX_ERR_INVALID, "null plan");
   plan->profiling = enabled != 0;
@@ -982,6 +1024,43 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     const int ks0 = temperature == 0.f ? 0 : 1;
     pull = warps0 * 32 <= int64_t(plan->coop_blocks_per_sm[ks0]) * plan->num_sms * pgx::kThreads;
   }
+  // Lattice mode (one sample): one index-free kernel per iteration, bit-identical to the
+  // two-pass path.  Graphs small enough for the resident kernels keep those (no launches).
+  bool lattice = false;
+  if (plan->disabled_paths & PGX_PATH_PULL) pull = false;
+  const bool use_resident = pull && num_iters >= 2 && !plan->profiling && !(plan->disabled_paths & PGX_PATH_RESIDENT);
+  if (plan->lattice_ok && single && !(plan->disabled_paths & PGX_PATH_LATTICE) && !use_resident) {
+    const auto misaligned = [](const void* p, uintptr_t mask) { return (reinterpret_cast<uintptr_t>(p) & mask) != 0; };
+    lattice = !misaligned(cur, 15) && !misaligned(ws.mA, 15) && !misaligned(ws.mB, 15) && !misaligned(ftov_out, 15) &&
+              !misaligned(log_potentials, 15) && !misaligned(evidence, 7);
+  }
+  if (lattice) {
+    static bool lat_attr = false;
+    if (!lat_attr) {
+      PGX_CUDA(cudaFuncSetAttribute(pgx::k_lattice<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(pgx::lattice_smem_bytes())));
+      PGX_CUDA(cudaFuncSetAttribute(pgx::k_lattice<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    int(pgx::lattice_smem_bytes())));
+      lat_attr = true;
+    }
+    const pgx::LatticeDev& g = plan->lattice;
+    const dim3 grid(unsigned((g.N + pgx::kLatTC - 1) / pgx::kLatTC), unsigned((g.R + pgx::kLatTR - 1) / pgx::kLatTR));
+    plan->dominant_name = "k_lattice";
+    for (int it = 0; it < num_iters; ++it) {
+      a.delta_off = it;
+      float* dst = (it == num_iters - 1) ? ftov_out : nxt;
+      if ((rc = prof_mark(plan, st, 0))) return rc;
+      if (temperature == 0.f)
+        pgx::k_lattice<false><<<grid, pgx::kLatThreads, pgx::lattice_smem_bytes(), st>>>(g, evidence, log_potentials, cur, dst, a);
+      else
+        pgx::k_lattice<true><<<grid, pgx::kLatThreads, pgx::lattice_smem_bytes(), st>>>(g, evidence, log_potentials, cur, dst, a);
+      if ((rc = check_launch(plan, "k_lattice"))) return rc;
+      if ((rc = prof_mark(plan, st, 0))) return rc;
+      nxt = (dst == ws.mA) ? ws.mB : ws.mA;
+      cur = dst;
+    }
+    pull = false;
+  }
   if (pull) {
     auto pull_args = [&](const EnumBlockPlan& eb) {
       pgx::PullArgs g;
@@ -999,7 +1078,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     // resident kernels: one thread per (factor, sample)
     const int upw = 32 >> mp.bx_log;
     const int64_t res_warps = ((eb0.dev.num_factors + upw - 1) / upw) * mp.nbt;
-    const bool res_ok = plan->enum_blocks.size() == 1 && num_iters >= 2 && !plan->profiling;
+    const bool res_ok = use_resident;
     const bool cluster = res_ok && res_warps * 32 <= int64_t(pgx::kResidentClusterCtas) * pgx::kResidentClusterThreads;
     const int64_t coop_cap = int64_t(plan->coop_blocks_per_sm[ks]) * plan->num_sms;
     const int64_t coop_blocks = (res_warps * 32 + pgx::kThreads - 1) / pgx::kThreads;
@@ -1078,7 +1157,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
       }
     }
   }
-  for (int it = 0; it < (pull ? 0 : num_iters); ++it) {
+  for (int it = 0; it < ((pull || lattice) ? 0 : num_iters); ++it) {
     a.delta_off = it;
     if (!fused || it == 0) {
       pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(

@@ -598,6 +598,153 @@ k_enum_pw2_pull_resident(BatchMap mp, PullArgs g, View ev, View lp, const float*
 }
 
 // ---------------------------------------------------------------------------
+// K2a-lattice: ONE pass per iteration, no index array at all, for a graph that is a 2-D
+// nearest-neighbour lattice of binary variables built as examples/ising_model.ipynb cell 12
+// builds it: variable (l, j) = l * N + j owns the vertical factor 2 * var (to (l + 1, j))
+// and the horizontal factor 2 * var + 1 (to (l, j + 1) mod N), so that its 8 messages are
+// the 32 contiguous bytes m[8 var .. 8 var + 7] = (V.v0s0, V.v0s1, V.v1s0, V.v1s1,
+// H.v0s0, H.v0s1, H.v1s0, H.v1s1).  torus = 1: rows wrap (the notebook's graph);
+// torus = 0: R owner rows plus a ghost row R that only receives (the row strips of
+// dist.py).  The structure is detected from the generic edge table at plan time.
+//
+// A CTA owns a TR x TC tile of owner variables: it stages the messages of the tile plus a
+// one-variable halo in shared memory (128-bit loads), forms the variable sums of the
+// (TR + 1) x (TC + 1) variables its factors touch - evidence first, then the incident
+// messages in ASCENDING MESSAGE INDEX, i.e. the order of the serial scatter-add of
+// pgmax/infer/bp.py:217 and of k_var_sums, wrap-around neighbours included - and updates
+// its 2 TR TC factors with 128-bit loads of the potentials and 128-bit stores.  Per
+// iteration HBM sees the messages once in and once out, the potentials and the evidence:
+// 13 bytes per edge-state, against 17 "algorithmic" ones (which include the incidence
+// index this kernel does not need); halo re-reads hit L2 (neighbouring tiles run
+// concurrently).  One sample only (flat vectors).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p);
+
+struct LatticeDev {
+  int64_t first_msg, first_pot;
+  int32_t R, N;   // owner rows, columns
+  int32_t torus;  // 1: rows wrap; 0: ghost row R below the last owner row
+};
+
+constexpr int kLatTR = 16, kLatTC = 64, kLatThreads = 256;
+constexpr int kLatMR = kLatTR + 2, kLatMC = kLatTC + 2;
+__host__ __device__ constexpr size_t lattice_smem_bytes() {
+  return size_t(kLatMR) * kLatMC * 2 * sizeof(float4) + size_t(kLatTR + 1) * (kLatTC + 1) * sizeof(float2);
+}
+
+template <bool kSumProduct>
+__global__ void __launch_bounds__(kLatThreads)
+k_lattice(LatticeDev g, const float* __restrict__ ev, const float* __restrict__ lp,
+          const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  constexpr int TR = kLatTR, TC = kLatTC, MR = kLatMR, MC = kLatMC;
+  extern __shared__ float4 lat_smem[];
+  float4* sm = lat_smem;                                      // [MR][MC][2]: (V, H) messages
+  float2* Ss = reinterpret_cast<float2*>(sm + MR * MC * 2);   // [TR + 1][TC + 1] variable sums
+  const int l0 = blockIdx.y * TR, j0 = blockIdx.x * TC;
+  const int R = g.R, N = g.N;
+  const bool torus = g.torus != 0;
+  const float4* mo4 = reinterpret_cast<const float4*>(m_old + g.first_msg);
+  float4* mn4 = reinterpret_cast<float4*>(m_new + g.first_msg);
+  const float4* lp4 = reinterpret_cast<const float4*>(lp + g.first_pot);
+  const float2* ev2 = reinterpret_cast<const float2*>(ev);
+
+  // ---- phase 1: messages of rows l0 - 1 .. l0 + TR, columns j0 - 1 .. j0 + TC ----------
+  // cp.async (LDGSTS, 16 B, L2 only): every load of the thread is in flight at once and no
+  // register is held for it; the potentials of the thread's factors (needed in phase 3) are
+  // requested now as well, so that their latency hides behind phases 1 and 2.
+  constexpr int kLoads = (MR * MC * 2 + kLatThreads - 1) / kLatThreads;
+#pragma unroll
+  for (int k = 0; k < kLoads; ++k) {
+    const int t = threadIdx.x + k * kLatThreads;
+    const int cell = t >> 1;
+    const int rr = cell / MC, cc = cell - rr * MC;
+    int l = l0 - 1 + rr, j = j0 - 1 + cc;
+    bool ok = j >= -1 && j <= N;
+    j = (j < 0) ? N - 1 : (j == N ? 0 : j);
+    if (torus) {
+      ok = ok && l <= R;
+      l = (l < 0) ? R - 1 : (l == R ? 0 : l);
+    } else {
+      ok = ok && l >= 0 && l < R;  // the ghost row owns no factor
+    }
+    if (t < MR * MC * 2) {
+      if (ok)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sm + t)),
+                     "l"(mo4 + (int64_t(l) * N + j) * 2 + (t & 1)) : "memory");
+      else
+        sm[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  constexpr int kFac = TR * TC * 2 / kLatThreads;
+  float4 lq[kFac];
+#pragma unroll
+  for (int k = 0; k < kFac; ++k) {
+    const int t = threadIdx.x + k * kLatThreads;
+    const int cell = t >> 1;
+    const int rr = cell / TC, cc = cell - rr * TC;
+    const int l = min(l0 + rr, R - 1), j = min(j0 + cc, N - 1);
+    const float4* src = lp4 + (int64_t(l) * N + j) * 2 + (t & 1);
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(lq[k].x), "=f"(lq[k].y), "=f"(lq[k].z), "=f"(lq[k].w) : "l"(src));
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- phase 2: variable sums of rows l0 .. l0 + TR, columns j0 .. j0 + TC -------------
+  for (int t = threadIdx.x; t < (TR + 1) * (TC + 1); t += kLatThreads) {
+    const int rr = t / (TC + 1), cc = t - rr * (TC + 1);
+    int l = l0 + rr, j = j0 + cc;
+    if (l > R || j > N) continue;
+    if (j == N) j = 0;
+    if (torus && l == R) l = 0;
+    const bool has_own = l < R;              // owner row (always true on the torus)
+    const bool has_up = torus || l > 0;
+    const bool up_wrap = torus && l == 0;    // the upper neighbour is row R - 1: largest index
+    const bool left_wrap = j == 0;           // the left neighbour is column N - 1: after the own ones
+    const float2 e = __ldg(ev2 + (int64_t(l) * N + j));
+    const float4 own_v = sm[((rr + 1) * MC + cc + 1) * 2], own_h = sm[((rr + 1) * MC + cc + 1) * 2 + 1];
+    const float4 up = sm[(rr * MC + cc + 1) * 2];            // V factor of the row above: v1 slot
+    const float4 left = sm[((rr + 1) * MC + cc) * 2 + 1];    // H factor of the left neighbour: v1 slot
+    float s0 = e.x, s1 = e.y;
+    if (has_up && !up_wrap) { s0 += up.z; s1 += up.w; }
+    if (has_own && !left_wrap) { s0 += left.z; s1 += left.w; }
+    if (has_own) { s0 += own_v.x; s1 += own_v.y; s0 += own_h.x; s1 += own_h.y; }
+    if (has_own && left_wrap) { s0 += left.z; s1 += left.w; }
+    if (up_wrap) { s0 += up.z; s1 += up.w; }
+    Ss[t] = make_float2(s0, s1);
+  }
+  __syncthreads();
+
+  // ---- phase 3: the 2 TR TC factors of the tile ---------------------------------------------
+  float dmax = 0.f;
+#pragma unroll
+  for (int k = 0; k < kFac; ++k) {
+    const int t = threadIdx.x + k * kLatThreads;
+    const int tt = t & 1, cell = t >> 1;
+    const int rr = cell / TC, cc = cell - rr * TC;
+    const int l = l0 + rr, j = j0 + cc;
+    if (l < R && j < N) {
+      const int64_t f = (int64_t(l) * N + j) * 2 + tt;
+      const float4 l4 = lq[k];
+      const float4 m4 = sm[((rr + 1) * MC + cc + 1) * 2 + tt];
+      const float2 sa = Ss[rr * (TC + 1) + cc];
+      const float2 sb = tt == 0 ? Ss[(rr + 1) * (TC + 1) + cc] : Ss[rr * (TC + 1) + cc + 1];
+      const float m[4] = {m4.x, m4.y, m4.z, m4.w};
+      const float Sv[4] = {sa.x, sa.y, sb.x, sb.y};
+      const float lpv[4] = {clip_lp(l4.x), clip_lp(l4.y), clip_lp(l4.z), clip_lp(l4.w)};
+      float n[4];
+      dmax = fmaxf(dmax, pw2_update<kSumProduct>(m, Sv, lpv, a, n));
+      mn4[f] = make_float4(n[0], n[1], n[2], n[3]);
+    }
+  }
+  if (a.deltas != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if ((threadIdx.x & 31) == 0) publish_delta(a.deltas, a.delta_off, dmax);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // TMA (bulk async copy) + mbarrier helpers, sm_90+ PTX.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -295,6 +295,7 @@ def test_pull_mode_streaming_equals_persistent(temperature, batch):
   arrays = bp.init(evidence_updates={variables: evidence})
   persistent, d_p = bp.run_with_diffs(arrays, num_iters=40, damping=0.5)
   plan = bp.context.plan
+  plan.disable_paths(plan.PATH_LATTICE)  # a one-sample grid would otherwise stream through k_lattice
   plan.profile_enable(True)
   streaming, d_s = bp.run_with_diffs(arrays, num_iters=40, damping=0.5)
   launches, _, name = plan.profile_read()
@@ -302,6 +303,13 @@ def test_pull_mode_streaming_equals_persistent(temperature, batch):
   assert launches == 40 and name == "k_enum_pw2_pull"
   np.testing.assert_array_equal(persistent.ftov_msgs, streaming.ftov_msgs)
   np.testing.assert_array_equal(d_p, d_s)
+  if batch is None:  # and the index-free lattice kernel, bit for bit
+    plan.disable_paths(plan.PATH_RESIDENT | plan.PATH_PULL)
+    assert plan.is_lattice
+    lattice, d_l = bp.run_with_diffs(arrays, num_iters=40, damping=0.5)
+    np.testing.assert_array_equal(persistent.ftov_msgs, lattice.ftov_msgs)
+    np.testing.assert_array_equal(d_p, d_l)
+    plan.disable_paths(0)
 
 
 @pytest.mark.parametrize("temperature", [0.0, 1.0])
