@@ -449,7 +449,14 @@ def main():
     except (OSError, ValueError):
       pass
     kernel_ms = prof_ms / max(n_prof, 1)
-    achieved = bytes_iter / (kernel_ms * 1e-3) / 1e9 if n_prof else None
+    # the dominant launch updates dom_es of the es edge-states: its share of the iteration's
+    # algorithmic bytes (single-kernel iterations: all of them)
+    single_kernel = prof_name in ("k_enum_pw2_bip", "k_lattice", "k_enum_pw2_pull")
+    dom_es = es if single_kernel else min(plan.dominant_edge_states, es)
+    kernel_bytes = bytes_iter * dom_es // es
+    achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if n_prof else None
+    iter_ms = ms / args.steps / iters
+    iter_gbs = bytes_iter / (iter_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": msgs_per_step * args.steps * world / (ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -470,8 +477,11 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "kernel": prof_name, "kernel_ms": kernel_ms, "launches_timed": n_prof,
-                     "algorithmic_bytes_per_launch": bytes_iter, "peak_source": peak_src,
-                     "iter_ms": ms / args.steps / iters},
+                     "algorithmic_bytes_per_launch": kernel_bytes, "peak_source": peak_src,
+                     "edge_states_per_launch": dom_es * batch,
+                     # the whole iteration (every kernel of it) against the same peak
+                     "iter_ms": iter_ms, "iter_algorithmic_bytes": bytes_iter,
+                     "iter_achieved": iter_gbs, "iter_frac": iter_gbs / peak},
         "checksum_max_abs_msg": checksum,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -203,10 +203,16 @@ int pgx_plan_num_fused_blocks(const pgx_plan* plan);
  *   PGX_PATH_RESIDENT  all iterations of a small pairwise graph in one cluster /
  *                      cooperative launch
  *   PGX_PATH_PULL      pairwise kernels that re-derive the variable sums per factor
- *                      instead of materialising them */
+ *                      instead of materialising them
+ *   PGX_PATH_MERGED_MAX  all large pairwise max-product groups (RCN) in one balanced launch */
 #define PGX_PATH_LATTICE 1u
 #define PGX_PATH_RESIDENT 2u
 #define PGX_PATH_PULL 4u
+#define PGX_PATH_MERGED_MAX 8u /* one launch for all large sorted pairwise max-product groups */
+#define PGX_PATH_LATTICE_STREAM 32u /* persistent TMA variant of the lattice kernel (large lattices) */
+#define PGX_PATH_AUX_STREAM 64u /* the smaller of the OR / AND groups on an auxiliary stream */
+#define PGX_PATH_WIDE_SPLIT 128u /* wide OR / AND update as a serial reduce launch + a parent-parallel emit launch */
+#define PGX_PATH_LOGICAL_PULL 16u /* OR / AND kernels that re-derive the sums of variables with <= 2 edges */
 int pgx_plan_disable_paths(pgx_plan* plan, uint32_t mask);
 /* 1 if the lattice path is available for this plan. */
 int pgx_plan_is_lattice(const pgx_plan* plan);
@@ -219,6 +225,8 @@ int pgx_plan_is_lattice(const pgx_plan* plan);
  * bracketed launches and their summed device time since the last read, the
  * kernel's name, and resets the counters.  Off by default (no events). */
 int pgx_plan_profile_enable(pgx_plan* plan, int enabled);
+/* Edge-states (per sample) the dominant launch updates: the units of its roofline figure. */
+int64_t pgx_plan_dominant_edge_states(const pgx_plan* plan);
 int pgx_plan_profile_read(pgx_plan* plan, int64_t* num_launches, double* total_ms,
                           const char** kernel_name);
 

@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = (
     "pgx_plan_num_fused_blocks",
     "pgx_plan_disable_paths",
     "pgx_plan_is_lattice",
+    "pgx_plan_dominant_edge_states",
     "pgx_plan_profile_enable",
     "pgx_plan_profile_read",
     "pgx_last_error",
@@ -164,6 +165,8 @@ def load() -> ctypes.CDLL:
   lib.pgx_plan_disable_paths.restype = ctypes.c_int
   lib.pgx_plan_is_lattice.argtypes = [vp]
   lib.pgx_plan_is_lattice.restype = ctypes.c_int
+  lib.pgx_plan_dominant_edge_states.argtypes = [vp]
+  lib.pgx_plan_dominant_edge_states.restype = ctypes.c_int64
   lib.pgx_plan_profile_enable.argtypes = [vp, ctypes.c_int]
   lib.pgx_plan_profile_enable.restype = ctypes.c_int
   lib.pgx_plan_profile_read.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double),
@@ -361,11 +364,16 @@ class Plan:
     """True when the plan found dense-grid pairwise blocks (single-pass path available)."""
     return bool(self._lib.pgx_plan_num_fused_blocks(self.handle))
 
-  PATH_LATTICE, PATH_RESIDENT, PATH_PULL = 1, 2, 4
+  PATH_LATTICE, PATH_RESIDENT, PATH_PULL, PATH_MERGED_MAX, PATH_LOGICAL_PULL = 1, 2, 4, 8, 16
+  PATH_LATTICE_STREAM, PATH_AUX_STREAM, PATH_WIDE_SPLIT = 32, 64, 128
 
   def disable_paths(self, mask: int) -> None:
     """Pin the launch path (PGX_PATH_* bits of include/pgx.h); all paths are bit-identical."""
     check(self._lib.pgx_plan_disable_paths(self.handle, int(mask)))
+
+  @property
+  def dominant_edge_states(self) -> int:
+    return int(self._lib.pgx_plan_dominant_edge_states(self.handle))
 
   @property
   def is_lattice(self) -> bool:

@@ -72,6 +72,11 @@ struct EnumBlockPlan {
   int bip = -1;  // index into pgx_plan::bips when the block has the dense-grid structure
   int32_t *d_cfg_es = nullptr, *d_t_ptr = nullptr, *d_t_k = nullptr, *d_edge_off = nullptr;
   int32_t *d_fac_edge = nullptr, *d_fac_msg = nullptr, *d_fac_pot = nullptr;
+  uint16_t* d_cfg_b = nullptr;  // partner-state table of the merged max-product launch
+  int2* d_steps = nullptr;      // its step schedule
+  int32_t warp_first[pgx::kBigWarps + 1] = {0};
+  int bigmax = -1;              // index into the plan's BigMaxGroup array, or -1
+  int n0 = 0;                   // states of the first variable
 };
 
 // A pairwise-binary enum block whose factors form a dense I x J grid (see BipDev).
@@ -83,6 +88,13 @@ struct BipPlan {
 struct LogicalPlan {
   pgx::LogicalDev dev{};
   int64_t max_parents = 0;
+  // pull path (k_logical_pull_*): packed wiring with the "other edge" of low-degree variables
+  pgx::LogicalPullDev pull{};
+  pgx::EdgeW *d_parents_w = nullptr, *d_children_w = nullptr;
+  int32_t* d_parent_factor = nullptr;  // [P] factor of every parent (two-launch wide update)
+  int64_t num_parents = 0;
+  std::vector<int32_t> h_ptr, h_pmsg, h_pvs, h_cmsg, h_cvs;  // host copies, dropped after plan creation
+  bool needs_s = false;  // some edge reads its variable's sum from S
   int32_t *d_parent_ptr = nullptr, *d_parents_msg = nullptr, *d_parents_vs = nullptr, *d_children_msg = nullptr,
           *d_children_vs = nullptr;
 };
@@ -90,6 +102,7 @@ struct LogicalPlan {
 struct Workspace {
   int64_t batch = 0;
   float *mA = nullptr, *mB = nullptr, *S = nullptr, *evT = nullptr, *lpT = nullptr, *part = nullptr;
+  float* agg = nullptr;  // per-factor aggregates of the two-launch wide logical update
   // staging for pgx_infer_host
   float *h_lp = nullptr, *h_ev = nullptr, *h_msgs_in = nullptr, *h_msgs_out = nullptr,
         *h_marg = nullptr, *h_deltas = nullptr;
@@ -123,6 +136,23 @@ struct pgx_plan {
   int2* d_edge_csr = nullptr;          // [num_edges] CSR row (begin, end) of the edge's variable
   unsigned int* d_grid_bar = nullptr;  // barrier counter of the persistent kernel
   int coop_blocks_per_sm[2] = {0, 0};  // occupancy of k_enum_pw2_pull_resident<false / true, coop>
+  // logical pull path: OR / AND kernels re-derive the sums of variables with <= 2 edges;
+  // k_var_sums_list covers the rest
+  bool logical_pull_ok = false;
+  int32_t* d_hi_list = nullptr;
+  int64_t hi_len = 0;
+  // the smaller of the OR / AND groups runs on an auxiliary stream beside the larger one
+  // (long serial parent chains of wide OR factors hide behind the bandwidth-bound AND kernel)
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int aux_group = 0;          // -1: OR group on aux, -2: AND group, 0: none
+  bool aux_needs_s = false;   // that group reads the variable-sum array
+  // merged max-product launch over all large sorted pairwise groups (k_enum_big_maxprod_all)
+  pgx::BigMaxGroup* d_bigmax_groups = nullptr;
+  int2* d_bigmax_units = nullptr;
+  int64_t bigmax_units = 0, bigmax_es = 0;
+  size_t bigmax_smem = 0;
+  unsigned int* d_bigmax_counter = nullptr;
   // lattice mode (the whole graph is one 2-D nearest-neighbour lattice block; LatticeDev)
   bool lattice_ok = false;
   pgx::LatticeDev lattice{};
@@ -140,6 +170,7 @@ struct pgx_plan {
   // the OR / AND / Pool launch.
   bool profiling = false;
   int dominant = 0;
+  int64_t dominant_es = 0;  // edge-states the dominant launch updates
   const char* dominant_name = "";
   std::vector<cudaEvent_t> prof_events;  // pairs (begin, end)
   size_t prof_used = 0;
@@ -153,6 +184,7 @@ void free_dev(void* p) {
 
 void free_workspace(Workspace& ws) {
   free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT); free_dev(ws.part);
+  free_dev(ws.agg);
   free_dev(ws.h_lp); free_dev(ws.h_ev); free_dev(ws.h_msgs_in); free_dev(ws.h_msgs_out);
   free_dev(ws.h_marg); free_dev(ws.h_deltas); free_dev(ws.h_map); free_dev(ws.h_ties);
   ws = Workspace{};
@@ -229,6 +261,11 @@ int build_logical(pgx_plan* plan, const pgx_logical_desc& d, const std::vector<i
   std::vector<int32_t> pmsg(d.parents_msg, d.parents_msg + d.num_parents);
   std::vector<int32_t> cmsg(d.children_msg, d.children_msg + d.num_factors);
   int rc;
+  out->h_ptr = narrow(ptr);
+  out->h_pmsg = pmsg;
+  out->h_pvs = pvs;
+  out->h_cmsg = cmsg;
+  out->h_cvs = cvs;
   if ((rc = upload(narrow(ptr), &out->d_parent_ptr, &plan->device_bytes))) return rc;
   if ((rc = upload(pmsg, &out->d_parents_msg, &plan->device_bytes))) return rc;
   if ((rc = upload(pvs, &out->d_parents_vs, &plan->device_bytes))) return rc;
@@ -339,6 +376,40 @@ int build_enum_block(pgx_plan* plan, const pgx_enum_block* desc_blocks, const st
     for (int s0 = 0; s0 < edge_off[1] && sorted0; ++s0)
       for (int j = t_ptr[s0]; j < t_ptr[s0 + 1] && sorted0; ++j) sorted0 = t_k[j] == j;
     out->dev.sorted0 = sorted0 ? 1 : 0;
+    // merged max-product launch: additionally the partner states of every state's list must be
+    // strictly ascending (no duplicate configuration: lanes of one step update distinct slots)
+    bool strict = sorted0 && out->variant == kBig && ns - edge_off[1] <= 65535 && edge_off[1] <= 65535;
+    for (int s0 = 0; s0 < edge_off[1] && strict; ++s0)
+      for (int k = t_ptr[s0] + 1; k < t_ptr[s0 + 1] && strict; ++k)
+        strict = cfg_es[size_t(k) * 2 + 1] > cfg_es[size_t(k - 1) * 2 + 1];
+    if (strict) {
+      std::vector<uint16_t> cfg_b(std::max<size_t>(K, 1));
+      for (int k = 0; k < K; ++k) cfg_b[k] = uint16_t(cfg_es[size_t(k) * 2 + 1] - edge_off[1]);
+      if ((rc = upload(cfg_b, &out->d_cfg_b, &plan->device_bytes))) return rc;
+      // step schedule: every state's list cut into runs of <= 32 configurations
+      std::vector<int2> steps;
+      std::vector<int32_t> list_first;  // index of the first step of every non-empty list
+      for (int s0 = 0; s0 < edge_off[1]; ++s0) {
+        const int k0 = t_ptr[s0], k1 = t_ptr[s0 + 1];
+        if (k1 > k0) list_first.push_back(int32_t(steps.size()));
+        for (int k = k0; k < k1; k += 32) {
+          const int cnt = std::min(32, k1 - k);
+          steps.push_back(make_int2(s0 | ((cnt - 1) << 16) | ((k + 32 >= k1 ? 1 : 0) << 21), k));
+        }
+      }
+      const int32_t num_steps = int32_t(steps.size());
+      out->warp_first[0] = 0;
+      for (int w = 1; w < pgx::kBigWarps; ++w) {  // cut at the list boundary nearest to an even share
+        const int32_t target = int32_t(int64_t(num_steps) * w / pgx::kBigWarps);
+        auto it = std::lower_bound(list_first.begin(), list_first.end(), target);
+        out->warp_first[w] = it == list_first.end() ? num_steps : *it;
+      }
+      out->warp_first[pgx::kBigWarps] = num_steps;
+      if (steps.empty()) steps.push_back(make_int2(0, 0));
+      if ((rc = upload(steps, &out->d_steps, &plan->device_bytes))) return rc;
+      out->bigmax = 0;  // index assigned by the caller
+      out->n0 = edge_off[1];
+    }
   }
   out->dev.fac_edge = out->d_fac_edge;
   out->dev.fac_msg = out->d_fac_msg;
@@ -362,7 +433,8 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
   const pgx::BatchMap mp = make_map(batch);
   if (ws.batch != batch) {
     free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT); free_dev(ws.part);
-    ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = ws.part = nullptr;
+    free_dev(ws.agg);
+    ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = ws.part = ws.agg = nullptr;
     ws.batch = batch;
     const size_t nm = tiled_floats(mp, plan->num_edge_states) * sizeof(float);
     const size_t nv = tiled_floats(mp, plan->num_var_states) * sizeof(float);
@@ -370,6 +442,13 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.mB), nm));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.S), nv));
     PGX_CUDA(cudaMemset(ws.S, 0, nv));  // padded sample slots stay finite
+  }
+  if (plan->logical_pull_ok && mp.bx_log == 5 && ws.agg == nullptr) {
+    int64_t wide = 0;  // factors of the groups that take the two-launch wide update
+    for (const LogicalPlan* lg : {&plan->or_f, &plan->and_f})
+      if (lg->max_parents > pgx::kRegParents) wide = std::max<int64_t>(wide, lg->dev.num_factors);
+    if (wide > 0)
+      PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.agg), size_t(wide) * pgx::kAggRows * 32 * mp.nbt * sizeof(float)));
   }
   if (need_part && ws.part == nullptr)
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.part), tiled_floats(mp, plan->part_rows) * sizeof(float)));
@@ -416,11 +495,41 @@ int prof_mark(pgx_plan* plan, cudaStream_t st, int id) {
 
 template <bool kSum>
 int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::View lp, const float* S,
-               const float* m_old, float* m_new, const pgx::RunArgs& a, bool fused) {
+               const float* m_old, float* m_new, const pgx::RunArgs& a, bool fused, bool lpull, pgx::View ev,
+               cudaStream_t aux) {
   int rc;
+  const bool merged_max = !kSum && plan->bigmax_units > 0 && !(plan->disabled_paths & PGX_PATH_MERGED_MAX);
+  if (merged_max) {
+    const bool dom = plan->dominant >= 0 && size_t(plan->dominant) < plan->enum_blocks.size() &&
+                     plan->enum_blocks[plan->dominant].bigmax >= 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+      PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod_all<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod_all<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    PGX_CUDA(cudaMemsetAsync(plan->d_bigmax_counter, 0, sizeof(unsigned int), st));
+    if (dom && (rc = prof_mark(plan, st, plan->dominant))) return rc;
+    const int per_sm = int(std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / plan->bigmax_smem)));
+    const int64_t grid = std::min<int64_t>(plan->bigmax_units * mp.batch, int64_t(plan->num_sms) * per_sm);
+    if (lp.kind != 1)
+      pgx::k_enum_big_maxprod_all<true><<<unsigned(grid), pgx::kThreads, plan->bigmax_smem, st>>>(
+          mp, plan->d_bigmax_groups, plan->d_bigmax_units, plan->bigmax_units, plan->d_bigmax_counter, plan->d_edge_vs,
+          lp, S, m_old, m_new, a);
+    else
+      pgx::k_enum_big_maxprod_all<false><<<unsigned(grid), pgx::kThreads, plan->bigmax_smem, st>>>(
+          mp, plan->d_bigmax_groups, plan->d_bigmax_units, plan->bigmax_units, plan->d_bigmax_counter, plan->d_edge_vs,
+          lp, S, m_old, m_new, a);
+    if ((rc = check_launch(plan, "k_enum_big_maxprod_all"))) return rc;
+    if (dom) {
+      plan->dominant_name = "k_enum_big_maxprod_all";
+      if ((rc = prof_mark(plan, st, plan->dominant))) return rc;
+    }
+  }
   for (size_t bi = 0; bi < plan->enum_blocks.size(); ++bi) {
     EnumBlockPlan& eb = plan->enum_blocks[bi];
     const int64_t F = eb.dev.num_factors;
+    if (merged_max && eb.bigmax >= 0) continue;
     if ((rc = prof_mark(plan, st, int(bi)))) return rc;
     if (fused && eb.bip >= 0) {
       const pgx::BipDev& g = plan->bips[eb.bip].dev;
@@ -430,12 +539,18 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       const size_t smem = pgx::bip_smem_bytes(g.RI, TJ);
       static bool attr_set[2] = {false, false};
       if (!attr_set[kSum]) {
-        PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pw2_bip<kSum, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pw2_bip<kSum, TJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(pgx::bip_smem_bytes(32, TJ))));
+        PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pw2_bip<kSum, TJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(pgx::bip_smem_bytes(32, TJ))));
         attr_set[kSum] = true;
       }
-      pgx::k_enum_pw2_bip<kSum, TJ><<<unsigned(grid), pgx::kBipWarps * 32, smem, st>>>(
-          mp.batch, groups, g, lp.p, S, m_old, m_new, plan->ws.part, plan->part_rows, a);
+      if (a.deltas != nullptr)
+        pgx::k_enum_pw2_bip<kSum, TJ, true><<<unsigned(grid), pgx::kBipWarps * 32, smem, st>>>(
+            mp.batch, groups, g, lp.p, S, m_old, m_new, plan->ws.part, plan->part_rows, a);
+      else
+        pgx::k_enum_pw2_bip<kSum, TJ, false><<<unsigned(grid), pgx::kBipWarps * 32, smem, st>>>(
+            mp.batch, groups, g, lp.p, S, m_old, m_new, plan->ws.part, plan->part_rows, a);
       if ((rc = check_launch(plan, "k_enum_pw2_bip"))) return rc;
       if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2_bip";
     } else if (eb.variant == kPw2) {
@@ -466,6 +581,7 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
         pgx::k_enum_big_maxprod<<<grid, pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old,
                                                                    m_new, a);
         if ((rc = check_launch(plan, "k_enum_big_maxprod"))) return rc;
+        if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_big_maxprod";
       } else {
         pgx::k_enum_big<kSum><<<grid, pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old,
                                                                  m_new, a);
@@ -475,10 +591,68 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
     if ((rc = prof_mark(plan, st, int(bi)))) return rc;
   }
   int lid = -1;
+  const cudaStream_t main_st = st;
   for (LogicalPlan* lg : {&plan->or_f, &plan->and_f}) {
     const int id = lid--;
     if (lg->dev.num_factors == 0) continue;
+    const cudaStream_t st = (lpull && aux != nullptr && id == plan->aux_group) ? aux : main_st;  // NOLINT
     if ((rc = prof_mark(plan, st, id))) return rc;
+    if (lpull) {
+      const bool delta = a.deltas != nullptr;
+      const int64_t F = lg->dev.num_factors;
+      if (lg->max_parents <= pgx::kRegParents) {
+        const int un = lg->dev.uniform;  // 0: ragged
+        const int units = (un == 1 || un == 2) ? 2 : 1;
+        const int64_t warps = (F + units - 1) / units;
+        const dim3 grid(unsigned(std::min<int64_t>((warps + 7) / 8, std::max<int64_t>(1, int64_t(plan->num_sms) * 16 / mp.nbt))),
+                        unsigned(mp.nbt));
+#define PGX_LAUNCH_SMALL(NP, U, UNI)                                                                            \
+  do {                                                                                                          \
+    if (delta)                                                                                                  \
+      pgx::k_logical_pull_small<kSum, true, NP, U, UNI><<<grid, pgx::kThreads, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, \
+                                                                                        m_new, a);             \
+    else                                                                                                        \
+      pgx::k_logical_pull_small<kSum, false, NP, U, UNI><<<grid, pgx::kThreads, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, \
+                                                                                         m_new, a);            \
+  } while (0)
+        if (un == 1) PGX_LAUNCH_SMALL(1, 2, true);
+        else if (un == 2) PGX_LAUNCH_SMALL(2, 2, true);
+        else if (un == 3) PGX_LAUNCH_SMALL(3, 1, true);
+        else if (un == 4) PGX_LAUNCH_SMALL(4, 1, true);
+        else PGX_LAUNCH_SMALL(4, 1, false);
+#undef PGX_LAUNCH_SMALL
+        if ((rc = check_launch(plan, "k_logical_pull_small"))) return rc;
+        if (id == plan->dominant) plan->dominant_name = "k_logical_pull_small";
+      } else {
+        if (plan->disabled_paths & PGX_PATH_WIDE_SPLIT) {
+          const dim3 grid(unsigned((F + 3) / 4), unsigned(mp.nbt));
+          if (delta)
+            pgx::k_logical_pull_wide<kSum, true><<<grid, 128, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, m_new, a);
+          else
+            pgx::k_logical_pull_wide<kSum, false><<<grid, 128, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, m_new, a);
+        } else {
+          // two launches: serial accumulation per factor, then a parent-parallel emit
+          const dim3 grid1(unsigned(std::min<int64_t>(F, 1 << 20)), unsigned(mp.nbt));
+          const int64_t warps2 = (lg->num_parents + pgx::kEmitUnits - 1) / pgx::kEmitUnits;
+          const dim3 grid2(unsigned(std::min<int64_t>((warps2 + 7) / 8, std::max<int64_t>(1, int64_t(plan->num_sms) * 16 / mp.nbt))),
+                           unsigned(mp.nbt));
+          if (delta) {
+            pgx::k_logical_wide_reduce<kSum, true><<<grid1, 32, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, m_new, plan->ws.agg, a);
+            pgx::k_logical_wide_emit<kSum, true><<<grid2, pgx::kThreads, 0, st>>>(
+                mp.batch, lg->pull, lg->d_parent_factor, lg->num_parents, ev, S, m_old, m_new, plan->ws.agg, a);
+          } else {
+            pgx::k_logical_wide_reduce<kSum, false><<<grid1, 32, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, m_new, plan->ws.agg, a);
+            pgx::k_logical_wide_emit<kSum, false><<<grid2, pgx::kThreads, 0, st>>>(
+                mp.batch, lg->pull, lg->d_parent_factor, lg->num_parents, ev, S, m_old, m_new, plan->ws.agg, a);
+          }
+          ++plan->launches;
+        }
+        if ((rc = check_launch(plan, "k_logical_pull_wide"))) return rc;
+        if (id == plan->dominant) plan->dominant_name = "k_logical_pull_wide";
+      }
+      if ((rc = prof_mark(plan, st, id))) return rc;
+      continue;
+    }
     if (lg->dev.uniform > 0 && lg->dev.uniform <= pgx::kRegParents)
       pgx::k_logical_uniform<kSum><<<grid_for(plan, mp, lg->dev.num_factors), pgx::kThreads, 0, st>>>(
           mp, lg->dev, S, m_old, m_new, a);
@@ -657,6 +831,37 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       PGX_TRY(build_enum_block(plan, desc->enum_blocks, groups[gi], edge_msg_start, edge_ns,
                                &plan->enum_blocks[gi]));
   }
+  {  // merged max-product launch: group table + work units sorted by configuration count
+    std::vector<pgx::BigMaxGroup> groups;
+    struct Unit { int g; int32_t f; int32_t cost; };
+    std::vector<Unit> units;
+    const int nwarp = pgx::kThreads / 32;
+    for (EnumBlockPlan& eb : plan->enum_blocks) {
+      if (eb.bigmax < 0) continue;
+      const size_t smem = (size_t(2) * eb.dev.ns + size_t(nwarp) * (eb.dev.ns - eb.n0 + 32) + 32) * sizeof(float);
+      if (smem > 200 * 1024 || eb.dev.num_factors >= INT32_MAX) { eb.bigmax = -1; continue; }
+      eb.bigmax = int(groups.size());
+      plan->bigmax_smem = std::max(plan->bigmax_smem, smem);
+      plan->bigmax_es += eb.dev.num_factors * eb.dev.ns;
+      pgx::BigMaxGroup g;
+      g.blk = eb.dev;
+      g.cfg_b = eb.d_cfg_b;
+      g.steps = eb.d_steps;
+      for (int w = 0; w <= pgx::kBigWarps; ++w) g.warp_first[w] = eb.warp_first[w];
+      groups.push_back(g);
+      for (int64_t f = 0; f < eb.dev.num_factors; ++f) units.push_back({eb.bigmax, int32_t(f), eb.dev.num_configs});
+    }
+    if (!groups.empty()) {
+      std::stable_sort(units.begin(), units.end(), [](const Unit& x, const Unit& y) { return x.cost > y.cost; });
+      std::vector<int2> u2(units.size());
+      for (size_t i = 0; i < units.size(); ++i) u2[i] = make_int2(units[i].g, units[i].f);
+      PGX_TRY(upload(groups, &plan->d_bigmax_groups, &plan->device_bytes));
+      PGX_TRY(upload(u2, &plan->d_bigmax_units, &plan->device_bytes));
+      plan->bigmax_units = int64_t(units.size());
+      if (cudaMalloc(reinterpret_cast<void**>(&plan->d_bigmax_counter), sizeof(unsigned int)) != cudaSuccess)
+        return bail(fail(PGX_ERR_CUDA, "cudaMalloc failed"));
+    }
+  }
   PGX_TRY(build_logical(plan, desc->or_factors, edge_msg_start, edge_vs, edge_ns, edge_covered, "OR factors",
                         &plan->or_f));
   PGX_TRY(build_logical(plan, desc->and_factors, edge_msg_start, edge_vs, edge_ns, edge_covered,
@@ -667,6 +872,72 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
                         "Pool factors", &plan->pool_f));
   for (int64_t e = 0; e < plan->num_edges; ++e)
     PGX_REQUIRE(edge_covered[e], "edge %lld belongs to no factor description", (long long)e);
+  if (plan->enum_blocks.empty() && plan->pool_f.dev.num_factors == 0 &&
+      plan->or_f.dev.num_factors + plan->and_f.dev.num_factors > 0) {
+    // pull wiring: per edge the message index of the variable's only other edge (-1: none,
+    // -2: more than two edges, sum read from S)
+    for (LogicalPlan* lg : {&plan->or_f, &plan->and_f}) {
+      if (lg->dev.num_factors == 0) continue;
+      const int rel = lg->dev.off > 0 ? 0 : 1;
+      auto pack = [&](int32_t msg, int32_t vs) {
+        const int32_t var = vs_var[vs];
+        const int64_t k0 = var_ptr[var], deg = var_ptr[var + 1] - k0;
+        pgx::EdgeW w{msg, vs, -2, 0};
+        if (deg == 1) w.other = -1;
+        else if (deg == 2) {
+          const int64_t own_lo = int64_t(msg) - rel;
+          const int64_t other_lo = var_edge_msg[k0] == own_lo ? var_edge_msg[k0 + 1] : var_edge_msg[k0];
+          w.other = int32_t(other_lo + rel);
+        }
+        return w;
+      };
+      std::vector<pgx::EdgeW> pw(lg->h_pmsg.size()), cw(lg->h_cmsg.size());
+      for (size_t i = 0; i < pw.size(); ++i) pw[i] = pack(lg->h_pmsg[i], lg->h_pvs[i]);
+      for (size_t f = 0; f < cw.size(); ++f) cw[f] = pack(lg->h_cmsg[f], lg->h_cvs[f]);
+      for (const pgx::EdgeW& e : pw) lg->needs_s = lg->needs_s || e.other == -2;
+      for (const pgx::EdgeW& e : cw) lg->needs_s = lg->needs_s || e.other == -2;
+      PGX_TRY(upload(pw, &lg->d_parents_w, &plan->device_bytes));
+      PGX_TRY(upload(cw, &lg->d_children_w, &plan->device_bytes));
+      {
+        std::vector<int32_t> pf(pw.size());
+        for (int64_t f = 0; f < lg->dev.num_factors; ++f)
+          for (int32_t i = lg->h_ptr[f]; i < lg->h_ptr[f + 1]; ++i) pf[i] = int32_t(f);
+        PGX_TRY(upload(pf, &lg->d_parent_factor, &plan->device_bytes));
+        lg->num_parents = int64_t(pw.size());
+      }
+      lg->pull.num_factors = lg->dev.num_factors;
+      lg->pull.parent_ptr = lg->d_parent_ptr;
+      lg->pull.parents = lg->d_parents_w;
+      lg->pull.children = lg->d_children_w;
+      lg->pull.off = lg->dev.off;
+      lg->pull.uniform = lg->dev.uniform;
+    }
+    std::vector<int32_t> hi;
+    for (int64_t v = 0; v < plan->num_vars; ++v)
+      if (var_ptr[v + 1] - var_ptr[v] > 2)
+        for (int32_t sidx = var_first_state[v]; sidx < var_first_state[v + 1]; ++sidx) hi.push_back(sidx);
+    // longest rows first: their serial chains start at once, the short ones fill in behind
+    std::stable_sort(hi.begin(), hi.end(), [&](int32_t x, int32_t y) {
+      const int32_t vx = vs_var[x], vy = vs_var[y];
+      return var_ptr[vx + 1] - var_ptr[vx] > var_ptr[vy + 1] - var_ptr[vy];
+    });
+    PGX_TRY(upload(hi, &plan->d_hi_list, &plan->device_bytes));
+    plan->hi_len = int64_t(hi.size());
+    plan->logical_pull_ok = true;
+    if (plan->or_f.dev.num_factors > 0 && plan->and_f.dev.num_factors > 0) {
+      const int64_t es_or = plan->or_f.dev.num_factors + desc->or_factors.num_parents;
+      const int64_t es_and = plan->and_f.dev.num_factors + desc->and_factors.num_parents;
+      plan->aux_group = es_or <= es_and ? -1 : -2;
+      plan->aux_needs_s = es_or <= es_and ? plan->or_f.needs_s : plan->and_f.needs_s;
+      if (cudaStreamCreateWithFlags(&plan->aux, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(PGX_ERR_CUDA, "creating the auxiliary stream failed"));
+    }
+  }
+  for (LogicalPlan* lg : {&plan->or_f, &plan->and_f, &plan->pool_f}) {
+    lg->h_ptr = {}; lg->h_pmsg = {}; lg->h_pvs = {}; lg->h_cmsg = {}; lg->h_cvs = {};
+  }
   {  // pull mode: all factors pairwise-binary, every variable of degree <= kPullMaxDegree
     constexpr int64_t kPullMaxDegree = pgx::kPullMaxDegree;
     bool ok = !plan->enum_blocks.empty() && plan->or_f.dev.num_factors == 0 &&
@@ -840,6 +1111,11 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       const int64_t es = 2 * (lg->dev.num_factors + (lg->dev.num_factors ? desc_num_parents[-id - 1] : 0));
       if (lg->dev.num_factors && es > best) { best = es; plan->dominant = id; plan->dominant_name = id == -3 ? "k_pool" : "k_logical"; }
     }
+    plan->dominant_es = std::max<int64_t>(best, 0);
+    // (max-product) the dominant block may be part of the merged launch: its units are all merged groups'
+    if (plan->dominant >= 0 && size_t(plan->dominant) < plan->enum_blocks.size() &&
+        plan->enum_blocks[plan->dominant].bigmax >= 0)
+      plan->dominant_es = plan->bigmax_es;
   }
 #undef PGX_TRY
 #undef PGX_REQUIRE
@@ -854,12 +1130,18 @@ void pgx_plan_destroy(pgx_plan* plan) {
   free_dev(plan->d_var_first_state); free_dev(plan->d_var_ptr); free_dev(plan->d_var_edge_msg);
   for (EnumBlockPlan& eb : plan->enum_blocks) {
     free_dev(eb.d_cfg_es); free_dev(eb.d_t_ptr); free_dev(eb.d_t_k); free_dev(eb.d_edge_off);
-    free_dev(eb.d_fac_edge); free_dev(eb.d_fac_msg); free_dev(eb.d_fac_pot);
+    free_dev(eb.d_fac_edge); free_dev(eb.d_fac_msg); free_dev(eb.d_fac_pot); free_dev(eb.d_cfg_b); free_dev(eb.d_steps);
   }
+  free_dev(plan->d_bigmax_groups); free_dev(plan->d_bigmax_units); free_dev(plan->d_bigmax_counter);
   for (LogicalPlan* lg : {&plan->or_f, &plan->and_f, &plan->pool_f}) {
     free_dev(lg->d_parent_ptr); free_dev(lg->d_parents_msg); free_dev(lg->d_parents_vs);
     free_dev(lg->d_children_msg); free_dev(lg->d_children_vs);
+    free_dev(lg->d_parents_w); free_dev(lg->d_children_w); free_dev(lg->d_parent_factor);
   }
+  free_dev(plan->d_hi_list);
+  if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
+  if (plan->ev_join) cudaEventDestroy(plan->ev_join);
+  if (plan->aux) cudaStreamDestroy(plan->aux);
   for (BipPlan& bp : plan->bips) {
     free_dev(bp.d_row_vs); free_dev(bp.d_col_vs); free_dev(bp.d_row_part); free_dev(bp.d_col_part);
   }
@@ -902,6 +1184,8 @@ int pgx_plan_disable_paths(pgx_plan* plan, uint32_t mask) {
 }
 
 int pgx_plan_is_lattice(const pgx_plan* plan) { return plan && plan->lattice_ok ? 1 : 0; }
+
+int64_t pgx_plan_dominant_edge_states(const pgx_plan* plan) { return plan ? plan->dominant_es : 0; }
 
 int pgx_plan_profile_enable(pgx_plan* plan, int enabled) {
   if (!plan) return fail(PGX_ERR_INVALID, "null plan");
@@ -1017,6 +1301,10 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   // cooperative launch.
   // (Large grids keep the two-pass path: re-deriving S per edge costs 4x the gathers and
   // measured slower than k_var_sums + k_enum_pw2 once the graph no longer fits in cache.)
+  // Logical pull path: full sample tiles, 32-bit offsets inside a tile
+  const bool lpull = plan->logical_pull_ok && mp.bx_log == 5 && !(plan->disabled_paths & PGX_PATH_LOGICAL_PULL) &&
+                     Es < (int64_t(1) << 26) && Vs < (int64_t(1) << 26);
+  const cudaStream_t aux = (lpull && plan->aux != nullptr && !(plan->disabled_paths & PGX_PATH_AUX_STREAM)) ? plan->aux : nullptr;
   bool pull = false;
   if (plan->pull_ok && !fused && plan->enum_blocks.size() == 1) {
     const int upw0 = 32 >> mp.bx_log;
@@ -1035,25 +1323,40 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
               !misaligned(log_potentials, 15) && !misaligned(evidence, 7);
   }
   if (lattice) {
-    static bool lat_attr = false;
-    if (!lat_attr) {
-      PGX_CUDA(cudaFuncSetAttribute(pgx::k_lattice<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    int(pgx::lattice_smem_bytes())));
-      PGX_CUDA(cudaFuncSetAttribute(pgx::k_lattice<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    int(pgx::lattice_smem_bytes())));
-      lat_attr = true;
-    }
     const pgx::LatticeDev& g = plan->lattice;
     const dim3 grid(unsigned((g.N + pgx::kLatTC - 1) / pgx::kLatTC), unsigned((g.R + pgx::kLatTR - 1) / pgx::kLatTR));
-    plan->dominant_name = "k_lattice";
+    // large lattices stream through the persistent TMA kernel, small ones (a few tiles per SM)
+    // keep the one-tile-per-CTA kernel
+    const int64_t num_tiles = int64_t(grid.x) * grid.y;
+    const bool stream = num_tiles >= 4 * int64_t(plan->num_sms) && !(plan->disabled_paths & PGX_PATH_LATTICE_STREAM);
+    const bool want_delta = deltas != nullptr;
+    const int variant = (temperature == 0.f ? 0 : 2) + (want_delta ? 1 : 0);
+    using LatFn = void (*)(pgx::LatticeDev, const float*, const float*, const float*, float*, pgx::RunArgs);
+    static const LatFn tile_fn[4] = {pgx::k_lattice<false, false>, pgx::k_lattice<false, true>, pgx::k_lattice<true, false>,
+                                     pgx::k_lattice<true, true>};
+    static const LatFn stream_fn[4] = {pgx::k_lattice_stream<false, false>, pgx::k_lattice_stream<false, true>,
+                                       pgx::k_lattice_stream<true, false>, pgx::k_lattice_stream<true, true>};
+    static bool lat_attr = false;
+    if (!lat_attr) {
+      for (int v = 0; v < 4; ++v) {
+        PGX_CUDA(cudaFuncSetAttribute(tile_fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, int(pgx::lattice_smem_bytes())));
+        PGX_CUDA(cudaFuncSetAttribute(stream_fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(pgx::lattice_stream_smem_bytes())));
+      }
+      lat_attr = true;
+    }
+    plan->dominant_name = stream ? "k_lattice_stream" : "k_lattice";
     for (int it = 0; it < num_iters; ++it) {
       a.delta_off = it;
       float* dst = (it == num_iters - 1) ? ftov_out : nxt;
       if ((rc = prof_mark(plan, st, 0))) return rc;
-      if (temperature == 0.f)
-        pgx::k_lattice<false><<<grid, pgx::kLatThreads, pgx::lattice_smem_bytes(), st>>>(g, evidence, log_potentials, cur, dst, a);
-      else
-        pgx::k_lattice<true><<<grid, pgx::kLatThreads, pgx::lattice_smem_bytes(), st>>>(g, evidence, log_potentials, cur, dst, a);
+      if (stream) {
+        const unsigned sgrid = unsigned(std::min<int64_t>(num_tiles, plan->num_sms));
+        stream_fn[variant]<<<sgrid, pgx::kLsThreads, pgx::lattice_stream_smem_bytes(), st>>>(g, evidence, log_potentials, cur,
+                                                                                          dst, a);
+      } else {
+        tile_fn[variant]<<<grid, pgx::kLatThreads, pgx::lattice_smem_bytes(), st>>>(g, evidence, log_potentials, cur, dst, a);
+      }
       if ((rc = check_launch(plan, "k_lattice"))) return rc;
       if ((rc = prof_mark(plan, st, 0))) return rc;
       nxt = (dst == ws.mA) ? ws.mB : ws.mA;
@@ -1159,18 +1462,38 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   }
   for (int it = 0; it < ((pull || lattice) ? 0 : num_iters); ++it) {
     a.delta_off = it;
-    if (!fused || it == 0) {
+    if (aux != nullptr && !plan->aux_needs_s) {
+      PGX_CUDA(cudaEventRecord(plan->ev_fork, st));
+      PGX_CUDA(cudaStreamWaitEvent(aux, plan->ev_fork, 0));
+    }
+    if (lpull) {
+      if (plan->hi_len > 0) {
+        const int64_t per_tile = std::min<int64_t>(plan->hi_len, (int64_t(1) << 30) / mp.nbt);
+        pgx::k_var_sums_list<<<unsigned(per_tile * mp.nbt), 32, 0, st>>>(mp.batch, mp.nbt, Es, Vs, plan->d_vs_csr,
+                                                                      plan->d_var_edge_msg, plan->d_hi_list, plan->hi_len,
+                                                                      ev, cur, ws.S);
+        if ((rc = check_launch(plan, "k_var_sums_list"))) return rc;
+      }
+    } else if (!fused || it == 0) {
       pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(
           mp, Vs, Es, plan->d_vs_csr, plan->d_var_edge_msg, ev, cur, ws.S);
       if ((rc = check_launch(plan, "k_var_sums"))) return rc;
     }
+    if (aux != nullptr && plan->aux_needs_s) {
+      PGX_CUDA(cudaEventRecord(plan->ev_fork, st));
+      PGX_CUDA(cudaStreamWaitEvent(aux, plan->ev_fork, 0));
+    }
     // With one sample the last iteration writes straight into the caller's buffer.
     float* dst = (single && it == num_iters - 1) ? ftov_out : nxt;
     if (temperature == 0.f)
-      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, a, fused);
+      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux);
     else
-      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, a, fused);
+      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux);
     if (rc) return rc;
+    if (aux != nullptr) {
+      PGX_CUDA(cudaEventRecord(plan->ev_join, aux));
+      PGX_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
+    }
     if (fused && it + 1 < num_iters) {
       // next iteration's variable sums from the partial sums the fused blocks just wrote
       pgx::k_var_reduce<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(

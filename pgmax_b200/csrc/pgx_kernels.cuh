@@ -279,6 +279,57 @@ k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int2* __restri
   }
 }
 
+// K1-list: the same sums for a LIST of var-states only (full sample tiles, TW = 32): the
+// high-degree var-states when the factor kernels re-derive the sums of low-degree variables
+// themselves (k_logical_pull_*).  A warp = the 32 samples of one var-state; 32 gathers in
+// flight per lane, added in ascending message index.
+constexpr int kVsListChunk = 32;
+
+__global__ void __launch_bounds__(32)
+k_var_sums_list(int batch, int nbt, int64_t Es, int64_t Vs, const int2* __restrict__ vs_csr,
+                const int32_t* __restrict__ var_edge_msg, const int32_t* __restrict__ list, int64_t list_len,
+                View ev, const float* __restrict__ m, float* __restrict__ S) {
+  // launched with ONE warp per CTA: a long serial chain (a variable with hundreds of edges) then
+  // holds only its own warp's resources, not a whole CTA of finished warps.  The list is sorted
+  // by degree, longest first, and the sample tile is the FASTEST block coordinate, so the long
+  // chains of all tiles start at once and the short rows fill in behind.
+  const int lane = threadIdx.x & 31;
+  const int tile_i = int(blockIdx.x % unsigned(nbt));
+  const bool live = tile_i * 32 + lane < batch;
+  const int ll = live ? lane : 0;  // dead lanes shadow sample 0 of the tile (they stay for the shuffles)
+  const size_t tile = tile_i;
+  const float* mL = m + tile * size_t(Es) * 32 + ll;
+  float* SL = S + tile * size_t(Vs) * 32 + ll;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + ll : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const int64_t gwarp = blockIdx.x / unsigned(nbt);
+  const int64_t nwarps = gridDim.x / unsigned(nbt);
+  for (int64_t i = gwarp; i < list_len; i += nwarps) {
+    const int v = list[i];
+    const int2 r = vs_csr[v];
+    const int st = r.y & ((1 << kVsStateBits) - 1);
+    const int k1 = r.x + (r.y >> kVsStateBits);
+    float acc = evq[uint32_t(v) << esh];
+    // 32 incident edges per round: ONE coalesced index load (lane j: edge k + j), indices handed
+    // out by shuffles, 32 gathers in flight per lane, added in ascending message index
+    int mine = r.x + lane < k1 ? var_edge_msg[r.x + lane] : 0;
+    for (int k = r.x; k < k1; k += kVsListChunk) {
+      const int held = mine;
+      if (k + kVsListChunk + lane < k1) mine = var_edge_msg[k + kVsListChunk + lane];
+      float x[kVsListChunk];
+#pragma unroll
+      for (int j = 0; j < kVsListChunk; ++j) {
+        const int idx = __shfl_sync(0xffffffffu, held, j);
+        x[j] = (k + j < k1) ? mL[uint32_t(idx + st) << 5] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kVsListChunk; ++j)
+        if (k + j < k1) acc += x[j];
+    }
+    if (live) SL[uint32_t(v) << 5] = acc;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Shared epilogue: damping, per-edge max-normalisation, clip, delta
 // (pgmax/infer/bp.py:127-136).  `one_minus_d` is computed on the host in fp32.
@@ -328,14 +379,18 @@ template <bool kSumProduct>
 __device__ __forceinline__ float lse2(float a, float b, float c_exp, float c_log) {
   const float mx = fmaxf(a, b);
   if (!kSumProduct) return mx;
-  const float mn = fminf(a, b);
-  return __fmaf_rn(c_log, lg2_approx(1.0f + ex2_approx((mn - mx) * c_exp)), mx);
+  // min - max == -|a - b| exactly (one subtraction either way): one FADD, the sign and the
+  // absolute value ride on the FMUL as operand modifiers
+  return __fmaf_rn(c_log, lg2_approx(1.0f + ex2_approx(-fabsf(a - b) * c_exp)), mx);
 }
 
 // In: old messages m[4] = (v0s0, v0s1, v1s0, v1s1), var sums S[4] of the same
 // var-states, clipped potentials lp[4] in config order (0,0),(0,1),(1,0),(1,1).
-// Out: n[4] damped + normalised + clipped; returns max|n - m|.
-template <bool kSumProduct>
+// Out: n[4] damped + normalised + clipped; returns max|n - m| (kDelta; else 0).
+// Damping: max-product rounds d*m and (1-d)*f separately, as the reference does (bit-exact
+// with the oracle); sum-product, which already carries the 1e-7-level ex2/lg2 error, fuses
+// the second product into an FMA.
+template <bool kSumProduct, bool kDelta = true>
 __device__ __forceinline__ float pw2_update(const float (&m)[4], const float (&Sv)[4],
                                             const float (&lp)[4], const RunArgs& a,
                                             float (&n)[4]) {
@@ -346,11 +401,18 @@ __device__ __forceinline__ float pw2_update(const float (&m)[4], const float (&S
   const float f1 = lse2<kSumProduct>(s10, s11, a.c_exp, a.c_log) - q1;
   const float f2 = lse2<kSumProduct>(s00, s10, a.c_exp, a.c_log) - q2;
   const float f3 = lse2<kSumProduct>(s01, s11, a.c_exp, a.c_log) - q3;
-  const float n0 = damp(m[0], f0, a.d, a.one_minus_d), n1 = damp(m[1], f1, a.d, a.one_minus_d);
-  const float n2 = damp(m[2], f2, a.d, a.one_minus_d), n3 = damp(m[3], f3, a.d, a.one_minus_d);
+  float n0, n1, n2, n3;
+  if (kSumProduct) {
+    n0 = __fmaf_rn(a.d, m[0], a.one_minus_d * f0); n1 = __fmaf_rn(a.d, m[1], a.one_minus_d * f1);
+    n2 = __fmaf_rn(a.d, m[2], a.one_minus_d * f2); n3 = __fmaf_rn(a.d, m[3], a.one_minus_d * f3);
+  } else {
+    n0 = damp(m[0], f0, a.d, a.one_minus_d); n1 = damp(m[1], f1, a.d, a.one_minus_d);
+    n2 = damp(m[2], f2, a.d, a.one_minus_d); n3 = damp(m[3], f3, a.d, a.one_minus_d);
+  }
   const float mxa = fmaxf(n0, n1), mxb = fmaxf(n2, n3);
   n[0] = fmaxf(n0 - mxa, kMsgNegInf); n[1] = fmaxf(n1 - mxa, kMsgNegInf);
   n[2] = fmaxf(n2 - mxb, kMsgNegInf); n[3] = fmaxf(n3 - mxb, kMsgNegInf);
+  if (!kDelta) return 0.f;
   return fmaxf(fmaxf(fabsf(n[0] - m[0]), fabsf(n[1] - m[1])),
                fmaxf(fabsf(n[2] - m[2]), fabsf(n[3] - m[3])));
 }
@@ -632,7 +694,7 @@ __host__ __device__ constexpr size_t lattice_smem_bytes() {
   return size_t(kLatMR) * kLatMC * 2 * sizeof(float4) + size_t(kLatTR + 1) * (kLatTC + 1) * sizeof(float2);
 }
 
-template <bool kSumProduct>
+template <bool kSumProduct, bool kDelta>
 __global__ void __launch_bounds__(kLatThreads)
 k_lattice(LatticeDev g, const float* __restrict__ ev, const float* __restrict__ lp,
           const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
@@ -734,11 +796,11 @@ k_lattice(LatticeDev g, const float* __restrict__ ev, const float* __restrict__ 
       const float Sv[4] = {sa.x, sa.y, sb.x, sb.y};
       const float lpv[4] = {clip_lp(l4.x), clip_lp(l4.y), clip_lp(l4.z), clip_lp(l4.w)};
       float n[4];
-      dmax = fmaxf(dmax, pw2_update<kSumProduct>(m, Sv, lpv, a, n));
+      dmax = fmaxf(dmax, pw2_update<kSumProduct, kDelta>(m, Sv, lpv, a, n));
       mn4[f] = make_float4(n[0], n[1], n[2], n[3]);
     }
   }
-  if (a.deltas != nullptr) {
+  if (kDelta) {
     for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
     if ((threadIdx.x & 31) == 0) publish_delta(a.deltas, a.delta_off, dmax);
   }
@@ -793,6 +855,204 @@ __device__ __forceinline__ void fence_proxy_async() {
 }
 
 // ---------------------------------------------------------------------------
+// K2a-lattice, streaming variant: the same update as k_lattice (identical arithmetic, same
+// summation order: bit-identical) as a PERSISTENT, warp-specialised kernel - one CTA per SM,
+// tiles handed out round-robin in row-major order (the CTAs sweep the grid together, so a
+// tile's halo rows are still in L2 when the next tile-row needs them):
+//   * a producer warp moves every tile with TMA bulk copies: the message rows of the tile +
+//     halo and the potential rows global -> shared on an mbarrier (<= 4 copies per row, one
+//     lane per row), and the updated rows shared -> global as bulk groups; no LSU
+//     instruction touches global memory for messages or potentials;
+//   * 16 consumer warps wait for the tile, form the variable sums, update the factors IN
+//     PLACE in shared memory and hand the tile back; two stages, so the loads of tile i + 1
+//     and the stores of tile i - 1 overlap the arithmetic of tile i.
+// Shared memory: 2 x (message tile 18 x 66 cells + potential tile 16 x 64 cells) x 32 B
+// + 2 sum buffers = 156 KB.
+// ---------------------------------------------------------------------------
+constexpr int kLsConsumers = 512;               // 16 warps
+constexpr int kLsThreads = kLsConsumers + 32;   // + producer warp
+constexpr int kLsStages = 2;
+constexpr int kLsMsgF4 = kLatMR * kLatMC * 2;   // float4 per message stage
+constexpr int kLsLpF4 = kLatTR * kLatTC * 2;    // float4 per potential stage
+constexpr int kLsSumF2 = (kLatTR + 1) * (kLatTC + 1);
+__host__ __device__ constexpr size_t lattice_stream_smem_bytes() {
+  return size_t(kLsStages) * (kLsMsgF4 + kLsLpF4) * sizeof(float4) + size_t(2) * kLsSumF2 * sizeof(float2) +
+         2 * kLsStages * sizeof(uint64_t);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <bool kSumProduct, bool kDelta>
+__global__ void __launch_bounds__(kLsThreads, 1)
+k_lattice_stream(LatticeDev g, const float* __restrict__ ev, const float* __restrict__ lp,
+                 const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  constexpr int TR = kLatTR, TC = kLatTC, MC = kLatMC;
+  extern __shared__ __align__(128) unsigned char ls_raw[];
+  float4* msg_s = reinterpret_cast<float4*>(ls_raw);                       // [stage][MR][MC][2]
+  float4* lp_s = msg_s + kLsStages * kLsMsgF4;                             // [stage][TR][TC][2]
+  float2* sum_s = reinterpret_cast<float2*>(lp_s + kLsStages * kLsLpF4);   // [2][TR + 1][TC + 1]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sum_s + 2 * kLsSumF2);      // [stage] tile landed
+  uint64_t* done = full + kLsStages;                                       // [stage] tile updated
+  const int R = g.R, N = g.N;
+  const bool torus = g.torus != 0;
+  const int tiles_x = (N + TC - 1) / TC, tiles_y = (R + TR - 1) / TR;
+  const int64_t num_tiles = int64_t(tiles_x) * tiles_y;
+  const int64_t my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kLsStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&done[s], kLsConsumers);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const float4* mo4 = reinterpret_cast<const float4*>(m_old + g.first_msg);
+  float4* mn4 = reinterpret_cast<float4*>(m_new + g.first_msg);
+  const float4* lp4 = reinterpret_cast<const float4*>(lp + g.first_pot);
+
+  if (threadIdx.x >= kLsConsumers) {
+    // ------------------------------- producer warp ---------------------------------------
+    const int lane = threadIdx.x & 31;
+    auto load_tile = [&](int64_t i) {
+      const int64_t tile = blockIdx.x + i * gridDim.x;
+      const int ty = int(tile / tiles_x), tx = int(tile - int64_t(ty) * tiles_x);
+      const int l0 = ty * TR, j0 = tx * TC;
+      const int stage = int(i & 1);
+      float4* ms = msg_s + stage * kLsMsgF4;
+      float4* ls = lp_s + stage * kLsLpF4;
+      const int ncols = min(TC + 1, N - j0);        // cells from column j0 on (incl. the right halo if inside)
+      const bool wrap_right = j0 + TC >= N;         // right halo of the last valid column is column 0
+      const int lcols = min(TC, N - j0);
+      // rows: sm row rr <-> lattice row l0 - 1 + rr
+      int l = l0 - 1 + lane;
+      bool row_ok = lane < kLatMR;
+      if (torus) { row_ok = row_ok && l <= R; l = l < 0 ? R - 1 : (l == R ? 0 : l); }
+      else row_ok = row_ok && l >= 0 && l < R;
+      const bool lp_ok = lane < TR && l0 + lane < R;
+      const uint32_t row_bytes = uint32_t(32 + ncols * 32 + (wrap_right ? 32 : 0));
+      const uint32_t my_bytes = (row_ok ? row_bytes : 0u) + (lp_ok ? uint32_t(lcols) * 32u : 0u);
+      uint32_t total = my_bytes;
+      for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+      if (lane == 0) mbar_expect_tx(&full[stage], total);
+      __syncwarp();
+      if (row_ok) {
+        const float4* src = mo4 + int64_t(l) * N * 2;
+        float4* dst = ms + lane * MC * 2;
+        bulk_g2s(dst, src + int64_t(j0 == 0 ? N - 1 : j0 - 1) * 2, 32, &full[stage]);
+        bulk_g2s(dst + 2, src + int64_t(j0) * 2, uint32_t(ncols) * 32u, &full[stage]);
+        if (wrap_right) bulk_g2s(dst + 2 + ncols * 2, src, 32, &full[stage]);
+      }
+      if (lp_ok)
+        bulk_g2s(ls + lane * TC * 2, lp4 + (int64_t(l0 + lane) * N + j0) * 2, uint32_t(lcols) * 32u, &full[stage]);
+    };
+    if (my_tiles > 0) load_tile(0);
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      // the other stage's previous stores have been drained below: refill it with tile i + 1
+      if (i + 1 < my_tiles) load_tile(i + 1);
+      const int stage = int(i & 1);
+      mbar_wait(&done[stage], uint32_t(i >> 1) & 1u);
+      const int64_t tile = blockIdx.x + i * gridDim.x;
+      const int ty = int(tile / tiles_x), tx = int(tile - int64_t(ty) * tiles_x);
+      const int l0 = ty * TR, j0 = tx * TC;
+      const int lcols = min(TC, N - j0);
+      if (lane < TR && l0 + lane < R) {
+        bulk_s2g(mn4 + (int64_t(l0 + lane) * N + j0) * 2, msg_s + stage * kLsMsgF4 + ((lane + 1) * MC + 1) * 2,
+                 uint32_t(lcols) * 32u);
+        bulk_commit();
+      }
+      bulk_wait_read<0>();  // this stage's shared memory may be overwritten from here on
+      __syncwarp();
+    }
+    return;
+  }
+
+  // --------------------------------- consumer warps -----------------------------------------
+  const float2* ev2 = reinterpret_cast<const float2*>(ev);
+  float dmax = 0.f;
+  for (int64_t i = 0; i < my_tiles; ++i) {
+    const int64_t tile = blockIdx.x + i * gridDim.x;
+    const int ty = int(tile / tiles_x), tx = int(tile - int64_t(ty) * tiles_x);
+    const int l0 = ty * TR, j0 = tx * TC;
+    const int stage = int(i & 1);
+    float4* sm = msg_s + stage * kLsMsgF4;
+    const float4* lq = lp_s + stage * kLsLpF4;
+    float2* Ss = sum_s + (i & 1) * kLsSumF2;
+    // evidence of this thread's variables: requested before the wait
+    constexpr int kVars = (kLsSumF2 + kLsConsumers - 1) / kLsConsumers;
+    float2 e[kVars];
+#pragma unroll
+    for (int k = 0; k < kVars; ++k) {
+      const int t = threadIdx.x + k * kLsConsumers;
+      const int rr = t / (TC + 1), cc = t - rr * (TC + 1);
+      int l = l0 + rr, j = j0 + cc;
+      e[k] = make_float2(0.f, 0.f);
+      if (t < kLsSumF2 && l <= R && j <= N) {
+        if (j == N) j = 0;
+        if (torus && l == R) l = 0;
+        e[k] = __ldg(ev2 + (int64_t(l) * N + j));
+      }
+    }
+    mbar_wait(&full[stage], uint32_t(i >> 1) & 1u);
+    // ---- variable sums (same order as k_lattice) -------------------------------------------
+#pragma unroll
+    for (int k = 0; k < kVars; ++k) {
+      const int t = threadIdx.x + k * kLsConsumers;
+      const int rr = t / (TC + 1), cc = t - rr * (TC + 1);
+      int l = l0 + rr, j = j0 + cc;
+      if (t >= kLsSumF2 || l > R || j > N) continue;
+      if (j == N) j = 0;
+      if (torus && l == R) l = 0;
+      const bool has_own = l < R;
+      const bool has_up = torus || l > 0;
+      const bool up_wrap = torus && l == 0;
+      const bool left_wrap = j == 0;
+      // cell of column j0 + cc sits at sm column cc + 1, except the wrapped right halo
+      const int col = (j0 + cc == N) ? (N - j0) + 1 : cc + 1;
+      const float4 own_v = sm[((rr + 1) * MC + col) * 2], own_h = sm[((rr + 1) * MC + col) * 2 + 1];
+      const float4 up = sm[(rr * MC + col) * 2];
+      const float4 left = sm[((rr + 1) * MC + col - 1) * 2 + 1];
+      float s0 = e[k].x, s1 = e[k].y;
+      if (has_up && !up_wrap) { s0 += up.z; s1 += up.w; }
+      if (has_own && !left_wrap) { s0 += left.z; s1 += left.w; }
+      if (has_own) { s0 += own_v.x; s1 += own_v.y; s0 += own_h.x; s1 += own_h.y; }
+      if (has_own && left_wrap) { s0 += left.z; s1 += left.w; }
+      if (up_wrap) { s0 += up.z; s1 += up.w; }
+      Ss[t] = make_float2(s0, s1);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kLsConsumers) : "memory");
+    // ---- factors, in place --------------------------------------------------------------------
+    constexpr int kFac = TR * TC * 2 / kLsConsumers;
+#pragma unroll
+    for (int k = 0; k < kFac; ++k) {
+      const int t = threadIdx.x + k * kLsConsumers;
+      const int tt = t & 1, cell = t >> 1;
+      const int rr = cell / TC, cc = cell - rr * TC;
+      if (l0 + rr < R && j0 + cc < N) {
+        const float4 l4 = lq[t];
+        float4* slot = sm + ((rr + 1) * MC + cc + 1) * 2 + tt;
+        const float4 m4 = *slot;
+        const float2 sa = Ss[rr * (TC + 1) + cc];
+        const float2 sb = tt == 0 ? Ss[(rr + 1) * (TC + 1) + cc] : Ss[rr * (TC + 1) + cc + 1];
+        const float m[4] = {m4.x, m4.y, m4.z, m4.w};
+        const float Sv[4] = {sa.x, sa.y, sb.x, sb.y};
+        const float lpv[4] = {clip_lp(l4.x), clip_lp(l4.y), clip_lp(l4.z), clip_lp(l4.w)};
+        float n[4];
+        dmax = fmaxf(dmax, pw2_update<kSumProduct, kDelta>(m, Sv, lpv, a, n));
+        *slot = make_float4(n[0], n[1], n[2], n[3]);
+      }
+    }
+    fence_proxy_async();
+    mbar_arrive(&done[stage]);
+  }
+  if (kDelta) {
+    for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    if ((threadIdx.x & 31) == 0) publish_delta(a.deltas, a.delta_off, dmax);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // K2a-fused: a pairwise-binary block whose factors form a dense I x J grid,
 // factor (i, j) = row variable i x column variable j, stored row-major (the RBM
 // of benchmark/rbm_lib.py:138-169: i = hidden unit, j = visible unit).  One pass
@@ -834,7 +1094,7 @@ __host__ __device__ constexpr size_t bip_smem_bytes(int RI, int TJ) {
          + size_t(kBipWarps) * kBipStages * sizeof(uint64_t);          // mbarriers
 }
 
-template <bool kSumProduct, int TJ>
+template <bool kSumProduct, int TJ, bool kDelta>
 __global__ void __launch_bounds__(kBipWarps * 32)
 k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp,
                const float* __restrict__ S, const float* __restrict__ m_old,
@@ -919,7 +1179,7 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
         const float Sv[4] = {Sr0, Sr1, Sc0[jj], Sc1[jj]};
         const float lpv[4] = {lq.x, lq.y, lq.z, lq.w};
         float n[4];
-        dmax = fmaxf(dmax, pw2_update<kSumProduct>(mo, Sv, lpv, a, n));
+        dmax = fmaxf(dmax, pw2_update<kSumProduct, kDelta>(mo, Sv, lpv, a, n));
 #pragma unroll
         for (int k = 0; k < 4; ++k) buf[(4 * jj + k) * 32] = n[k];
         ar0 += n[0]; ar1 += n[1];
@@ -955,7 +1215,7 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
       PL[pc + 32] = ac1[jj];
     }
   }
-  if (b < batch) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+  if (kDelta && b < batch) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
   if (lane == 0) bulk_wait_read<0>();  // shared memory must outlive the pending stores
 }
 
@@ -1278,6 +1538,170 @@ k_enum_big_maxprod(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ ed
 }
 
 // ---------------------------------------------------------------------------
+// K2c-max2: the same update without shared-memory atomics (ATOMS on spread addresses costs
+// ~2 cycles per LANE on this part, which made the kernel above atomics-bound), for ALL such
+// groups of the graph in ONE launch.
+//   * the plan cuts every state's configuration list into STEPS of <= 32 configurations
+//     (a, first k, count, last-of-list): a schedule per configuration table, shared by all
+//     factors of the group, so the kernel carries no list logic;
+//   * a warp executes a contiguous run of steps (runs are cut at list boundaries).  Within a
+//     step all partner states b are distinct, so every warp keeps a PRIVATE copy Mw[warp][b]
+//     of the partner-side maxima and updates it with a plain read-max-write (__syncwarp
+//     between steps); the copies are max-reduced once per factor.  The a-side maximum is a
+//     warp reduction at the end of each list.  max is order-independent: bit-identical to
+//     the other kernels and to the oracle;
+//   * the partner state of a configuration comes from a compact uint16 table (2 B from L2),
+//     the potential from HBM (4 B, streamed once): 6 B per configuration instead of 12;
+//   * loads run one trip (kBigTrip steps) ahead of their use in registers;
+//   * work units (factor, sample) of all groups are sorted by configuration count
+//     (descending) and handed out through an atomic counter: the launch ends balanced.
+// Dynamic smem: (2 ns + nwarps * (n1 + 32) + 32) floats of the largest group.
+// ---------------------------------------------------------------------------
+constexpr int kBigWarps = kThreads / 32;
+struct BigMaxGroup {
+  EnumBlockDev blk;
+  const uint16_t* cfg_b;  // [num_configs] state of variable 1 in configuration k
+  const int2* steps;      // [num_steps] x = a | (count - 1) << 16 | last << 21, y = first k
+  int32_t warp_first[kBigWarps + 1];  // steps [warp_first[w], warp_first[w + 1]) belong to warp w
+};
+
+constexpr int kBigTrip = 8;
+
+template <bool kFlatLp>  // potentials addressed without a sample-tile shift (shared or batch-major)
+__global__ void __launch_bounds__(kThreads)
+k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, const int2* __restrict__ units,
+                       int64_t num_units, unsigned int* __restrict__ counter,
+                       const int32_t* __restrict__ edge_vs, View lp, const float* __restrict__ S,
+                       const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  extern __shared__ float smem[];
+  __shared__ unsigned int s_unit;
+  const int sh = mp.bx_log;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t total = num_units * mp.batch;
+  for (;;) {
+    __syncthreads();  // previous unit done with shared memory (and with s_unit)
+    if (threadIdx.x == 0) s_unit = atomicAdd(counter, 1u);
+    __syncthreads();
+    const int64_t unit = s_unit;
+    if (unit >= total) break;
+    const int64_t u = unit / mp.batch;
+    const int b = int(unit - u * mp.batch);
+    const int2 uf = units[u];
+    const BigMaxGroup& G = groups[uf.x];
+    const EnumBlockDev& blk = G.blk;
+    const int64_t f = uf.y;
+    const int ns = blk.ns, n0 = blk.edge_off[1], n1 = ns - n0;
+    float* q = smem;                       // [ns]
+    float* M = q + ns;                     // [ns] maxima, then damped values
+    float* Mw = M + ns;                    // [kBigWarps][n1 + 32] per-warp partner-side maxima
+    float* red = Mw + kBigWarps * (n1 + 32);
+    const int64_t moff = lane_off(mp, a.Es, b);
+    const float* mo = m_old + moff;
+    float* mn = m_new + moff;
+    const float* SL = S + lane_off(mp, a.Vs, b);
+    const LaneView lpL = lane_view(lp, mp, b);
+    const int64_t mbase = blk.msg_base(f), ebase = blk.edge_base(f), pbase = blk.pot_base(f);
+    for (int e = 0; e < 2; ++e) {
+      const int64_t vs = edge_vs[ebase + e];
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        q[s] = SL[(vs + s - s0) << sh] - mo[(mbase + s) << sh];
+        M[s] = -INFINITY;
+      }
+    }
+    for (int i = threadIdx.x; i < kBigWarps * (n1 + 32); i += blockDim.x) Mw[i] = -INFINITY;
+    __syncthreads();
+
+    {  // ---- configurations: this warp's run of steps ----------------------------------------
+      const uint16_t* __restrict__ cb = G.cfg_b;
+      const int2* __restrict__ steps = G.steps;
+      const float* __restrict__ lpu = lpL.q + (pbase << lpL.sh);
+      const int lsh = lpL.sh;
+      const uint32_t q_s = smem_u32(q), qb_s = q_s + 4u * n0, M_s = smem_u32(M);
+      const uint32_t mw_s = smem_u32(Mw + warp * (n1 + 32));
+      const uint32_t dummy_s = mw_s + 4u * (n1 + lane);  // idle lanes read-max-write their own slot
+      auto lds_f = [](uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; };
+      auto sts_f = [](uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); };
+      const int s_end = G.warp_first[warp + 1];
+      // one trip = kBigTrip steps: lane p < kBigTrip fetches the descriptor of step s + p; every
+      // lane then requests (partner state, potential) of its configuration in each step
+      int2 meta_n = make_int2(0, 0);
+      int rb_n[kBigTrip];
+      float rl_n[kBigTrip];
+      auto request = [&](int s0) {
+        meta_n = (lane < kBigTrip && s0 + lane < s_end) ? __ldg(steps + s0 + lane) : make_int2(0, 0);
+#pragma unroll
+        for (int p = 0; p < kBigTrip; ++p) {
+          const int x = __shfl_sync(0xffffffffu, meta_n.x, p), k0 = __shfl_sync(0xffffffffu, meta_n.y, p);
+          // unconditional loads (idle lanes re-read the step's first configuration, a valid
+          // address; absent steps read configuration 0): no branch between the requests
+          const uint32_t k = uint32_t(k0) + (lane <= ((x >> 16) & 31) ? uint32_t(lane) : 0u);
+          rb_n[p] = int(__ldg(cb + k));
+          rl_n[p] = kFlatLp ? __ldcs(lpu + k) : __ldcs(lpu + (size_t(k) << lsh));
+        }
+      };
+      float best = -INFINITY;
+      int s0 = G.warp_first[warp];
+      if (s0 < s_end) request(s0);
+      for (; s0 < s_end; s0 += kBigTrip) {
+        const int2 meta = meta_n;
+        int rb[kBigTrip];
+        float rl[kBigTrip];
+#pragma unroll
+        for (int p = 0; p < kBigTrip; ++p) { rb[p] = rb_n[p]; rl[p] = rl_n[p]; }
+        if (s0 + kBigTrip < s_end) request(s0 + kBigTrip);  // next trip in flight during this one
+#pragma unroll
+        for (int p = 0; p < kBigTrip; ++p) {
+          if (s0 + p >= s_end) break;
+          const int x = __shfl_sync(0xffffffffu, meta.x, p);
+          const int a_cur = x & 0xffff;
+          const bool on = lane <= ((x >> 16) & 31);
+          const uint32_t b_s = 4u * uint32_t(rb[p]);
+          const float sk = on ? (lds_f(q_s + 4u * a_cur) + lds_f(qb_s + b_s)) + clip_lp(rl[p]) : -INFINITY;
+          best = fmaxf(best, sk);
+          const uint32_t slot = on ? mw_s + b_s : dummy_s;
+          sts_f(slot, fmaxf(lds_f(slot), sk));
+          __syncwarp();
+          if (x & (1 << 21)) {  // last step of a_cur's list
+            for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane == 0) sts_f(M_s + 4u * a_cur, best);
+            best = -INFINITY;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < n1; s += blockDim.x) {
+      float v = Mw[s];
+      for (int w = 1; w < kBigWarps; ++w) v = fmaxf(v, Mw[w * (n1 + 32) + s]);
+      M[n0 + s] = v;
+    }
+    __syncthreads();
+    float dmax = 0.f;
+    for (int e = 0; e < 2; ++e) {
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      float mx = -INFINITY;
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const float nvs = damp(mo[(mbase + s) << sh], M[s] - q[s], a.d, a.one_minus_d);
+        M[s] = nvs;
+        mx = fmaxf(mx, nvs);
+      }
+      mx = block_max(mx, red);
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const float out = fmaxf(M[s] - mx, kMsgNegInf);
+        const int64_t idx = (mbase + s) << sh;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
+      }
+    }
+    if (a.deltas != nullptr) {
+      dmax = block_max(dmax, red);
+      if (threadIdx.x == 0) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Writes the two states of a binary edge whose factor->variable message is
 // (0, x) or (x, 0): damping + normalisation + clip + delta.
 //   lo = message index of the edge's state 0; mo / mn are lane pointers.
@@ -1552,6 +1976,365 @@ k_logical(BatchMap mp, LogicalDev w, const float* __restrict__ S,
     write_edge(c, A.child_relevant<kSumProduct>(T) - A.Sb);
   }
   publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
+// K4-pull: OR / AND update for full sample tiles (TW = 32: a warp = the 32 samples of ONE
+// factor, every index warp-uniform) that needs the variable-sum array only for HIGH-degree
+// variables.  For a variable with one or two incident edges the kernel re-derives
+// S_v = ev_v + (incident messages in ascending message index) itself - the same additions
+// in the same order as k_var_sums, so results are bit-identical - which removes the S
+// write + gather and the message re-read of k_var_sums for those variables (in the
+// deconvolution graphs: every SW and X variable, 2/3 of all var-states); k_var_sums then
+// only runs over the listed high-degree var-states (S and W).
+// Wiring per edge (EdgeW, one 16-byte load): msg = message index of the state the
+// reference's wiring points at (state 0 for OR, state 1 for AND), vs = var-state of that
+// state, other = message index (same state) of the variable's only other edge, -1 if the
+// variable has no other edge, -2 if its sum is to be read from S.
+// All loads of a factor are issued before the first use (no data-dependent branch between
+// them); addresses are 32-bit offsets from per-lane bases.
+// ---------------------------------------------------------------------------
+struct EdgeW {
+  int32_t msg, vs, other, pad;
+};
+
+struct LogicalPullDev {
+  int64_t num_factors;
+  const int32_t* parent_ptr;  // [F + 1] (null when uniform)
+  const EdgeW* parents;       // [P]
+  const EdgeW* children;      // [F]
+  int32_t off;                // +1 OR, -1 AND
+  int32_t uniform;            // > 0: every factor has this many parents
+};
+
+// What stays live per edge between the loads and their use: 8 registers.
+struct EdgeIn {
+  float m_p, m_r;  // old messages: pointed state, relevant (+off) state
+  float a_p, a_r;  // S (kind 0) or evidence
+  float o_p, o_r;  // the other edge's messages (kinds 2, 3)
+  int32_t msg;
+  int32_t kind;    // 0: sums from S; 1: no other edge; 2: other edge first; 3: own edge first
+};
+
+// Issues the (up to) 6 loads of an edge; no data-dependent branch.
+__device__ __forceinline__ EdgeIn load_edge(const EdgeW& e, int off, const float* __restrict__ mo,
+                                            const float* __restrict__ evq, int esh,
+                                            const float* __restrict__ SL) {
+  EdgeIn r;
+  r.msg = e.msg;
+  r.kind = e.other == -2 ? 0 : (e.other == -1 ? 1 : (e.other < e.msg ? 2 : 3));
+  r.m_p = mo[uint32_t(e.msg) << 5];
+  r.m_r = mo[uint32_t(e.msg + off) << 5];
+  const bool from_s = e.other == -2;
+  r.a_p = *(from_s ? SL + (uint32_t(e.vs) << 5) : evq + (uint32_t(e.vs) << esh));
+  r.a_r = *(from_s ? SL + (uint32_t(e.vs + off) << 5) : evq + (uint32_t(e.vs + off) << esh));
+  r.o_p = 0.f;
+  r.o_r = 0.f;
+  if (e.other >= 0) {
+    r.o_p = mo[uint32_t(e.other) << 5];
+    r.o_r = mo[uint32_t(e.other + off) << 5];
+  }
+  return r;
+}
+// variable -> factor messages (pointed state, relevant state): S - m with S accumulated from
+// the evidence in ascending message index
+__device__ __forceinline__ void edge_q(const EdgeIn& r, float& q_p, float& q_r) {
+  float s_p = r.a_p, s_r = r.a_r;
+  if (r.kind != 0) {
+    const bool other_first = r.kind == 2;
+    s_p += other_first ? r.o_p : r.m_p;
+    s_r += other_first ? r.o_r : r.m_r;
+    if (r.kind >= 2) {
+      s_p += other_first ? r.m_p : r.o_p;
+      s_r += other_first ? r.m_r : r.o_r;
+    }
+  }
+  q_p = s_p - r.m_p;
+  q_r = s_r - r.m_r;
+}
+
+// new message (x at the relevant state, 0 at the pointed state): damping, normalisation,
+// clip, store; returns max|new - old| when kDelta
+template <bool kDelta>
+__device__ __forceinline__ float store_edge(float* __restrict__ mn, int off, const EdgeIn& r, float x, float d,
+                                            float one_minus_d) {
+  float n_p = damp(r.m_p, 0.f, d, one_minus_d), n_r = damp(r.m_r, x, d, one_minus_d);
+  const float mx = fmaxf(n_p, n_r);
+  n_p = fmaxf(n_p - mx, kMsgNegInf);
+  n_r = fmaxf(n_r - mx, kMsgNegInf);
+  mn[uint32_t(r.msg) << 5] = n_p;
+  mn[uint32_t(r.msg + off) << 5] = n_r;
+  return kDelta ? fmaxf(fabsf(n_p - r.m_p), fabsf(n_r - r.m_r)) : 0.f;
+}
+
+// Factors with <= NP parents (AND factors: NP = 2), everything in registers, U factors per
+// warp iteration (their loads are all in flight together).  kUniform: every factor has
+// exactly NP parents.
+template <bool kSumProduct, bool kDelta, int NP, int U, bool kUniform>
+__global__ void __launch_bounds__(kThreads)
+k_logical_pull_small(int batch, LogicalPullDev w, View ev, const float* __restrict__ S,
+                     const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y * 32 + lane;
+  if (b >= batch) return;
+  const size_t tile = blockIdx.y;
+  const float* mo = m_old + tile * size_t(a.Es) * 32 + lane;
+  float* mn = m_new + tile * size_t(a.Es) * 32 + lane;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + lane;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + lane : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float dmax = 0.f;
+  for (int64_t f0 = gwarp; f0 < w.num_factors; f0 += U * nwarps) {
+    EdgeIn ce[U], pe[U][NP];
+    int np[U];
+    int64_t p0[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t f = f0 + u * nwarps;
+      np[u] = 0;
+      p0[u] = 0;
+      if (f < w.num_factors) {
+        if (kUniform) { p0[u] = f * NP; np[u] = NP; }
+        else { p0[u] = w.parent_ptr[f]; np[u] = int(w.parent_ptr[f + 1] - p0[u]); }
+        ce[u] = load_edge(w.children[f], off, mo, evq, esh, SL);
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+          if (kUniform || j < np[u]) pe[u][j] = load_edge(w.parents[p0[u] + j], off, mo, evq, esh, SL);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (f0 + u * nwarps < w.num_factors) {
+        float c_p, c_r, q_p[NP], q_r[NP];
+        edge_q(ce[u], c_p, c_r);
+        LogicalAcc A;
+        A.istar = p0[u];
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+          if (kUniform || j < np[u]) {
+            edge_q(pe[u][j], q_p[j], q_r[j]);
+            A.add<kSumProduct>(p0[u] + j, q_r[j], q_p[j], T);
+          }
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+          if (kUniform || j < np[u]) {
+            const float x = A.parent_out<kSumProduct>(p0[u] + j, q_r[j], q_p[j], c_r, c_p, T, np[u] == 1);
+            dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, pe[u][j], x, d, one_minus_d));
+          }
+        dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, ce[u], A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
+      }
+    }
+  }
+  if (kDelta) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// Any number of parents (OR factors with up to hundreds): two passes over the parents.  The
+// wiring of 32 parents is fetched with ONE coalesced load (lane j holds parent i + j) and
+// handed out by shuffles; the parents' loads are issued kParentChunk at a time.  All lanes
+// stay alive for the shuffles; lanes beyond the batch read a valid sample and store nothing.
+template <bool kSumProduct, bool kDelta>
+__global__ void __launch_bounds__(128)
+k_logical_pull_wide(int batch, LogicalPullDev w, View ev, const float* __restrict__ S,
+                    const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int b_raw = blockIdx.y * 32 + lane;
+  const bool live = b_raw < batch;
+  const int ll = live ? lane : 0;  // dead lanes shadow sample 0 of the tile (always valid)
+  const size_t tile = blockIdx.y;
+  const float* mo = m_old + tile * size_t(a.Es) * 32 + ll;
+  float* mn = m_new + tile * size_t(a.Es) * 32 + ll;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + ll;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + ll : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float dmax = 0.f;
+  for (int64_t f = gwarp; f < w.num_factors; f += nwarps) {
+    int64_t p0, p1;
+    if (w.uniform > 0) { p0 = f * w.uniform; p1 = p0 + w.uniform; }
+    else { p0 = w.parent_ptr[f]; p1 = w.parent_ptr[f + 1]; }
+    const EdgeIn ce = load_edge(w.children[f], off, mo, evq, esh, SL);
+    LogicalAcc A;
+    A.istar = p0;
+    const bool single = (p1 - p0) == 1;
+    float c_p = 0.f, c_r = 0.f;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1) edge_q(ce, c_p, c_r);
+      EdgeW mine = (p0 + lane < p1) ? w.parents[p0 + lane] : EdgeW{0, 0, -1, 0};
+      for (int64_t i32 = p0; i32 < p1; i32 += 32) {
+        const EdgeW held = mine;
+        if (i32 + 32 + lane < p1) mine = w.parents[i32 + 32 + lane];  // next 32, in flight during this block
+        const int n32 = int(min(int64_t(32), p1 - i32));
+#pragma unroll 1
+        for (int c0 = 0; c0 < n32; c0 += kParentChunk) {
+          EdgeIn r[kParentChunk];
+#pragma unroll
+          for (int j = 0; j < kParentChunk; ++j) {
+            EdgeW e;
+            e.msg = __shfl_sync(0xffffffffu, held.msg, (c0 + j) & 31);
+            e.vs = __shfl_sync(0xffffffffu, held.vs, (c0 + j) & 31);
+            e.other = __shfl_sync(0xffffffffu, held.other, (c0 + j) & 31);
+            if (c0 + j < n32) r[j] = load_edge(e, off, mo, evq, esh, SL);
+          }
+#pragma unroll
+          for (int j = 0; j < kParentChunk; ++j)
+            if (c0 + j < n32) {
+              float q_p, q_r;
+              edge_q(r[j], q_p, q_r);
+              const int64_t i = i32 + c0 + j;
+              if (pass == 0) {
+                A.add<kSumProduct>(i, q_r, q_p, T);
+              } else {
+                const float x = A.parent_out<kSumProduct>(i, q_r, q_p, c_r, c_p, T, single);
+                if (live) dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, r[j], x, d, one_minus_d));
+              }
+            }
+        }
+      }
+    }
+    if (live)
+      dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
+  }
+  if (kDelta && live) publish_delta(a.deltas, int64_t(b_raw) * a.delta_stride + a.delta_off, dmax);
+}
+
+// The wide update split in two launches, so that only the part that must be serial is:
+//   pass 1 (k_logical_wide_reduce): one warp per (factor, sample tile) walks the parents once,
+//     accumulating the sums in ascending parent order and the two largest differences, writes
+//     the child's message and the factor's aggregates [F][8][32 samples] (tile-blocked);
+//   pass 2 (k_logical_wide_emit): one warp per (PARENT, sample tile) - fully parallel,
+//     bandwidth-bound - re-derives its own variable -> factor message and emits the message to
+//     the parent from the aggregates.
+// Same arithmetic as k_logical_pull_wide (LogicalAcc), hence bit-identical.
+constexpr int kAggRows = 8;  // acc, Sb, d1, d2, istar - p0 (int bits), c_p, c_r, unused
+
+template <bool kSumProduct, bool kDelta>
+__global__ void __launch_bounds__(32, 16)  // one warp per CTA: a serial chain holds only its own warp
+k_logical_wide_reduce(int batch, LogicalPullDev w, View ev, const float* __restrict__ S,
+                      const float* __restrict__ m_old, float* __restrict__ m_new, float* __restrict__ agg,
+                      RunArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int b_raw = blockIdx.y * 32 + lane;
+  const bool live = b_raw < batch;
+  const int ll = live ? lane : 0;
+  const size_t tile = blockIdx.y;
+  const float* mo = m_old + tile * size_t(a.Es) * 32 + ll;
+  float* mn = m_new + tile * size_t(a.Es) * 32 + ll;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + ll;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + ll : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  float* aggL = agg + tile * size_t(w.num_factors) * kAggRows * 32 + ll;
+  const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float dmax = 0.f;
+  for (int64_t f = gwarp; f < w.num_factors; f += nwarps) {
+    int64_t p0, p1;
+    if (w.uniform > 0) { p0 = f * w.uniform; p1 = p0 + w.uniform; }
+    else { p0 = w.parent_ptr[f]; p1 = w.parent_ptr[f + 1]; }
+    const EdgeIn ce = load_edge(w.children[f], off, mo, evq, esh, SL);
+    LogicalAcc A;
+    A.istar = p0;
+    EdgeW mine = (p0 + lane < p1) ? w.parents[p0 + lane] : EdgeW{0, 0, -1, 0};
+    for (int64_t i32 = p0; i32 < p1; i32 += 32) {
+      const EdgeW held = mine;
+      if (i32 + 32 + lane < p1) mine = w.parents[i32 + 32 + lane];
+      const int n32 = int(min(int64_t(32), p1 - i32));
+#pragma unroll 1
+      for (int c0 = 0; c0 < n32; c0 += kParentChunk) {
+        EdgeIn r[kParentChunk];
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j) {
+          EdgeW e;
+          e.msg = __shfl_sync(0xffffffffu, held.msg, (c0 + j) & 31);
+          e.vs = __shfl_sync(0xffffffffu, held.vs, (c0 + j) & 31);
+          e.other = __shfl_sync(0xffffffffu, held.other, (c0 + j) & 31);
+          if (c0 + j < n32) r[j] = load_edge(e, off, mo, evq, esh, SL);
+        }
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j)
+          if (c0 + j < n32) {
+            float q_p, q_r;
+            edge_q(r[j], q_p, q_r);
+            A.add<kSumProduct>(i32 + c0 + j, q_r, q_p, T);
+          }
+      }
+    }
+    float c_p, c_r;
+    edge_q(ce, c_p, c_r);
+    if (live) {
+      float* g = aggL + size_t(f) * kAggRows * 32;
+      g[0] = A.acc; g[32] = A.Sb; g[64] = A.d1; g[96] = A.d2;
+      g[128] = __int_as_float(int(A.istar - p0)); g[160] = c_p; g[192] = c_r;
+      dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
+    }
+  }
+  if (kDelta && live) publish_delta(a.deltas, int64_t(b_raw) * a.delta_stride + a.delta_off, dmax);
+}
+
+// parent_factor[i] = factor of parent i (ascending).  kEmitUnits parents per warp iteration.
+constexpr int kEmitUnits = 2;
+
+template <bool kSumProduct, bool kDelta>
+__global__ void __launch_bounds__(kThreads)
+k_logical_wide_emit(int batch, LogicalPullDev w, const int32_t* __restrict__ parent_factor, int64_t num_parents,
+                    View ev, const float* __restrict__ S, const float* __restrict__ m_old,
+                    float* __restrict__ m_new, const float* __restrict__ agg, RunArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y * 32 + lane;
+  if (b >= batch) return;
+  const size_t tile = blockIdx.y;
+  const float* mo = m_old + tile * size_t(a.Es) * 32 + lane;
+  float* mn = m_new + tile * size_t(a.Es) * 32 + lane;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + lane;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + lane : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const float* aggL = agg + tile * size_t(w.num_factors) * kAggRows * 32 + lane;
+  const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float dmax = 0.f;
+  for (int64_t i0 = gwarp; i0 < num_parents; i0 += kEmitUnits * nwarps) {
+    EdgeIn r[kEmitUnits];
+    float g[kEmitUnits][7];
+    int64_t p0[kEmitUnits], p1[kEmitUnits];
+#pragma unroll
+    for (int u = 0; u < kEmitUnits; ++u) {
+      const int64_t i = i0 + u * nwarps;
+      if (i < num_parents) {
+        const int f = parent_factor[i];
+        if (w.uniform > 0) { p0[u] = int64_t(f) * w.uniform; p1[u] = p0[u] + w.uniform; }
+        else { p0[u] = w.parent_ptr[f]; p1[u] = w.parent_ptr[f + 1]; }
+        r[u] = load_edge(w.parents[i], off, mo, evq, esh, SL);
+        const float* gp = aggL + size_t(f) * kAggRows * 32;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) g[u][k] = gp[k * 32];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kEmitUnits; ++u) {
+      const int64_t i = i0 + u * nwarps;
+      if (i < num_parents) {
+        LogicalAcc A;
+        A.acc = g[u][0]; A.Sb = g[u][1]; A.d1 = g[u][2]; A.d2 = g[u][3];
+        A.istar = p0[u] + __float_as_int(g[u][4]);
+        float q_p, q_r;
+        edge_q(r[u], q_p, q_r);
+        const float x = A.parent_out<kSumProduct>(i, q_r, q_p, g[u][6], g[u][5], T, p1[u] - p0[u] == 1);
+        dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, r[u], x, d, one_minus_d));
+      }
+    }
+  }
+  if (kDelta) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
 }
 
 // ---------------------------------------------------------------------------

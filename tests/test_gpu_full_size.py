@@ -73,6 +73,28 @@ def test_config3_rcn_625_state_factors():
   w_states, _, w_ties = bp_oracle.decode_flat(graph, bp_oracle.flat_beliefs(graph, want, arrays.evidence))
   np.testing.assert_array_equal(states, w_states)
   assert int(ties) == int(w_ties)
+  # the per-group kernel (shared-memory atomics) instead of the merged balanced launch
+  plan = bp.context.plan
+  plan.disable_paths(plan.PATH_MERGED_MAX)
+  np.testing.assert_array_equal(bp.run(arrays, num_iters=30, damping=0.5).ftov_msgs, want)
+  plan.disable_paths(0)
+
+
+def test_config3_rcn_batched_merged_launch():
+  """Three samples (different evidence) of a two-model RCN-shaped graph through the merged
+  max-product launch: every sample bit-identical to its own single-sample oracle run."""
+  fg, groups, evidence = models.rcn_model(num_models=2, num_vars=6, radii=(2, 3, 8), extra_edges=2, seed=5)
+  rng = np.random.default_rng(0)
+  batched = {vg: np.stack([np.where(rng.random(ev.shape) < 0.05, 1.0, -1.0) for _ in range(3)])
+             for vg, ev in evidence.items()}
+  bp = infer.BP(fg.bp_state, temperature=0.0)
+  arrays = bp.init(evidence_updates=batched)
+  got, got_d = bp.run_with_diffs(arrays, num_iters=5, damping=0.5)
+  graph = bp_oracle.graph_from_context(bp.context)
+  want, want_d = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence,
+                                          5, 0.5, 0.0)
+  np.testing.assert_array_equal(got.ftov_msgs, want)
+  np.testing.assert_array_equal(got_d, want_d)
 
 
 def test_config4_ising_1024_sum_product_short_horizon():

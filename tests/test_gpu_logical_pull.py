@@ -1,0 +1,138 @@
+"""GPU tests of the logical pull path (k_logical_pull_small / _wide + k_var_sums_list): graphs of
+OR / AND factors only, batch >= 17 (full sample tiles).  The pull kernels re-derive the sums of
+variables with one or two edges in the serial order of k_var_sums, so they must be BIT-identical
+to the two-pass kernels (PATH_LOGICAL_PULL disabled) and agree with the oracle."""
+
+import numpy as np
+import pytest
+
+import models
+from oracle import bp_oracle
+from pgmax_b200 import fgraph, fgroup, infer, vgroup
+
+pytestmark = pytest.mark.gpu
+
+
+def random_logical_network(seed, and_parents=(1, 4), or_parents=(1, 40)):
+  """Leaves (shared by many AND factors: high degree) -> AND -> mid variables (degree 2, some 3)
+  -> OR -> outputs (degree 1); plus AND factors on top of OR outputs of an earlier layer."""
+  rng = np.random.default_rng(seed)
+  n_leaf, n_mid = 12, int(rng.integers(30, 60))
+  n_out = int(rng.integers(3, 8))
+  leaf = vgroup.NDVarArray(num_states=2, shape=(n_leaf,))
+  mid = vgroup.NDVarArray(num_states=2, shape=(n_mid,))
+  out = vgroup.NDVarArray(num_states=2, shape=(n_out,))
+  top = vgroup.NDVarArray(num_states=2, shape=(2,))
+  fg = fgraph.FactorGraph(variable_groups=[leaf, mid, out, top])
+  ands = []
+  for i in range(n_mid):
+    k = int(rng.integers(and_parents[0], and_parents[1] + 1))
+    ands.append([leaf[int(j)] for j in rng.choice(n_leaf, size=k, replace=False)] + [mid[i]])
+  ors = []
+  pool = list(rng.permutation(n_mid))
+  for o in range(n_out):
+    k = int(min(len(pool), rng.integers(or_parents[0], or_parents[1] + 1))) if o < n_out - 1 else len(pool)
+    k = max(k, 1) if pool else 0
+    take, pool = pool[:k], pool[k:]
+    extra = [int(j) for j in rng.choice(n_mid, size=2, replace=False) if int(j) not in take][:1]  # degree-3 mids
+    if take or extra:
+      ors.append([mid[int(j)] for j in list(take) + extra] + [out[o]])
+  fg.add_factors(fgroup.ORFactorGroup(ors))
+  # uniform AND groups per parent count, plus the outputs feeding two more ANDs
+  by_k = {}
+  for v in ands:
+    by_k.setdefault(len(v), []).append(v)
+  for k in sorted(by_k):
+    fg.add_factors(fgroup.ANDFactorGroup(by_k[k]))
+  fg.add_factors(fgroup.ANDFactorGroup([[out[0], out[1 % n_out], top[0]], [out[0], leaf[0], top[1]]]))
+  groups = dict(leaf=leaf, mid=mid, out=out, top=top)
+  return fg, groups
+
+
+def _evidence(groups, batch, seed):
+  rng = np.random.default_rng(seed)
+  return {g: rng.gumbel(size=(batch,) + g.shape + (2,)).astype(np.float32) * 2.0 for g in groups.values()}
+
+
+def _close_to_oracle(got, want, temperature, atol=2e-5):
+  """Max-product: tight.  Sum-product with many parents: the reference's closed form takes
+  logminusexp(L, Sb) of two sums of magnitude ~1e2 that differ by ~1e-3, behind an eps cut-off
+  (logical.py:673-737): a 1-ulp difference between two correct expf / log1pf implementations moves
+  that difference by 1 % or flips the cut-off, so a few per cent of the messages differ at the
+  1e-3 level between ANY two fp32 evaluations (the GPU paths agree with each other bit for bit,
+  asserted by the callers).  Bound the fraction of such entries and their typical size."""
+  got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+  assert not np.isnan(got).any()
+  if temperature == 0.0:
+    np.testing.assert_allclose(got, want, rtol=2e-6, atol=atol)
+    return
+  floor_g, floor_w = got <= -1e31, ~np.isfinite(want) | (want <= -1e31)
+  both = ~floor_g & ~floor_w
+  err = np.abs(got[both] - want[both])
+  bad = (err > atol + 2e-6 * np.abs(want[both])).sum() + (floor_g != floor_w).sum()
+  assert bad / got.size < 0.10, bad / got.size
+  assert np.median(err) < atol, np.median(err)
+
+
+def _run(bp, arrays, iters, temperature, mask):
+  plan = bp.context.plan
+  plan.disable_paths(mask)
+  out = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
+  plan.disable_paths(0)
+  return out
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+@pytest.mark.parametrize("temperature", [0.0, 0.3, 0.8])
+@pytest.mark.parametrize("batch", [17, 40])
+def test_pull_equals_two_pass_and_oracle(seed, temperature, batch):
+  fg, groups = random_logical_network(seed)
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  arrays = bp.init(evidence_updates=_evidence(groups, batch, seed))
+  plan = bp.context.plan
+  launches = plan.launch_count
+  got, got_d = _run(bp, arrays, 6, temperature, 0)
+  kinds = plan.launch_count - launches
+  ref, ref_d = _run(bp, arrays, 6, temperature, plan.PATH_LOGICAL_PULL)
+  np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
+  np.testing.assert_array_equal(got_d, ref_d)
+  assert kinds > 0
+  # single-launch wide kernel, everything on one stream
+  one, one_d = _run(bp, arrays, 6, temperature, plan.PATH_WIDE_SPLIT | plan.PATH_AUX_STREAM)
+  np.testing.assert_array_equal(got.ftov_msgs, one.ftov_msgs)
+  np.testing.assert_array_equal(got_d, one_d)
+  graph = bp_oracle.graph_from_context(bp.context)
+  if temperature == 0.0:
+    want, want_d = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence,
+                                            6, 0.5, temperature)
+    _close_to_oracle(got.ftov_msgs, want, temperature)
+    np.testing.assert_allclose(got_d, want_d, rtol=1e-5, atol=2e-5)
+  else:
+    # ONE iteration from the state the GPU reached (no propagation of flipped cut-offs)
+    one, _ = _run(bp, got, 1, temperature, 0)
+    want, _ = bp_oracle.run_bp_batched(graph, got.log_potentials, got.ftov_msgs, got.evidence, 1, 0.5, temperature)
+    _close_to_oracle(one.ftov_msgs, want, temperature)
+
+
+@pytest.mark.parametrize("temperature", [0.0, 0.5])
+def test_pull_deconvolution_batch_40(temperature):
+  """Small deconvolution graph (uniform 2-parent ANDs, ORs with up to 18 parents; S and W are
+  the high-degree variables, SW and X are pulled), 40 images, with shared and per-sample evidence."""
+  fg, groups = models.deconv_model(im_height=9, im_width=8, n_feat=2, feat_height=3, feat_width=3)
+  evidence = models.deconv_evidence(groups, batch=40)
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  arrays = bp.init(evidence_updates=evidence)
+  plan = bp.context.plan
+  got, got_d = _run(bp, arrays, 12, temperature, 0)
+  ref, ref_d = _run(bp, arrays, 12, temperature, plan.PATH_LOGICAL_PULL)
+  np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
+  np.testing.assert_array_equal(got_d, ref_d)
+  graph = bp_oracle.graph_from_context(bp.context)
+  if temperature == 0.0:
+    want, _ = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence,
+                                       12, 0.5, temperature)
+    np.testing.assert_allclose(got.ftov_msgs, want, rtol=2e-6, atol=2e-4)  # messages reach 230
+  else:
+    one, _ = _run(bp, got, 1, temperature, 0)
+    want, _ = bp_oracle.run_bp_batched(graph, got.log_potentials, got.ftov_msgs, got.evidence, 1, 0.5, temperature)
+    _close_to_oracle(one.ftov_msgs, want, temperature, atol=2e-4)
