@@ -102,6 +102,7 @@ struct LogicalPlan {
 struct Workspace {
   int64_t batch = 0;
   float *mA = nullptr, *mB = nullptr, *S = nullptr, *evT = nullptr, *lpT = nullptr, *part = nullptr;
+  float *cA = nullptr, *cB = nullptr;  // compressed (one float per edge) messages of the fused blocks
   float* agg = nullptr;  // per-factor aggregates of the two-launch wide logical update
   // staging for pgx_infer_host
   float *h_lp = nullptr, *h_ev = nullptr, *h_msgs_in = nullptr, *h_msgs_out = nullptr,
@@ -161,6 +162,7 @@ struct pgx_plan {
   std::vector<BipPlan> bips;
   bool exact_order = false;            // force the two-pass, serial-order path
   int64_t part_rows = 0;               // rows of the partial-sum buffer
+  int64_t c_rows = 0;                  // rows of the compressed message arrays (edges of the fused blocks)
   int32_t* d_rest_ptr = nullptr;       // [num_vars + 1] CSR over edges NOT covered by a fused block
   int32_t* d_rest_edge_msg = nullptr;
   int32_t* d_part_first = nullptr;     // [num_vars] first partial row of the variable
@@ -184,7 +186,7 @@ void free_dev(void* p) {
 
 void free_workspace(Workspace& ws) {
   free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT); free_dev(ws.part);
-  free_dev(ws.agg);
+  free_dev(ws.agg); free_dev(ws.cA); free_dev(ws.cB);
   free_dev(ws.h_lp); free_dev(ws.h_ev); free_dev(ws.h_msgs_in); free_dev(ws.h_msgs_out);
   free_dev(ws.h_marg); free_dev(ws.h_deltas); free_dev(ws.h_map); free_dev(ws.h_ties);
   ws = Workspace{};
@@ -433,8 +435,8 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
   const pgx::BatchMap mp = make_map(batch);
   if (ws.batch != batch) {
     free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT); free_dev(ws.part);
-    free_dev(ws.agg);
-    ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = ws.part = ws.agg = nullptr;
+    free_dev(ws.agg); free_dev(ws.cA); free_dev(ws.cB);
+    ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = ws.part = ws.agg = ws.cA = ws.cB = nullptr;
     ws.batch = batch;
     const size_t nm = tiled_floats(mp, plan->num_edge_states) * sizeof(float);
     const size_t nv = tiled_floats(mp, plan->num_var_states) * sizeof(float);
@@ -450,8 +452,11 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
     if (wide > 0)
       PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.agg), size_t(wide) * pgx::kAggRows * 32 * mp.nbt * sizeof(float)));
   }
-  if (need_part && ws.part == nullptr)
+  if (need_part && ws.part == nullptr) {
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.part), tiled_floats(mp, plan->part_rows) * sizeof(float)));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cA), tiled_floats(mp, plan->c_rows) * sizeof(float)));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cB), tiled_floats(mp, plan->c_rows) * sizeof(float)));
+  }
   if (need_evT && ws.evT == nullptr)
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.evT), tiled_floats(mp, plan->num_var_states) * sizeof(float)));
   if (need_lpT && ws.lpT == nullptr)
@@ -474,10 +479,13 @@ int to_tiles(pgx_plan* plan, cudaStream_t st, const float* src, float* dst, int6
   return check_launch(plan, "k_to_tiles");
 }
 
-int from_tiles(pgx_plan* plan, cudaStream_t st, const float* src, float* dst, int64_t n, const pgx::BatchMap& mp) {
-  if (n == 0) return PGX_OK;
-  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((mp.batch + 31) / 32)), block(32, 8);
-  pgx::k_from_tiles<<<grid, block, 0, st>>>(src, dst, n, mp);
+// rows [n_begin, n_end) of the n-row arrays
+int from_tiles(pgx_plan* plan, cudaStream_t st, const float* src, float* dst, int64_t n, const pgx::BatchMap& mp,
+               int64_t n_begin = 0, int64_t n_end = -1) {
+  if (n_end < 0) n_end = n;
+  if (n_end <= n_begin) return PGX_OK;
+  dim3 grid((unsigned)((n_end - n_begin + 31) / 32), (unsigned)((mp.batch + 31) / 32)), block(32, 8);
+  pgx::k_from_tiles<<<grid, block, 0, st>>>(src, dst, n, n_begin, n_end, mp);
   return check_launch(plan, "k_from_tiles");
 }
 
@@ -496,7 +504,7 @@ int prof_mark(pgx_plan* plan, cudaStream_t st, int id) {
 template <bool kSum>
 int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::View lp, const float* S,
                const float* m_old, float* m_new, const pgx::RunArgs& a, bool fused, bool lpull, pgx::View ev,
-               cudaStream_t aux) {
+               cudaStream_t aux, const float* c_old = nullptr, float* c_new = nullptr) {
   int rc;
   const bool merged_max = !kSum && plan->bigmax_units > 0 && !(plan->disabled_paths & PGX_PATH_MERGED_MAX);
   if (merged_max) {
@@ -536,21 +544,29 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       constexpr int TJ = pgx::kBipTJ;
       const int groups = (mp.nbt + pgx::kBipWarps - 1) / pgx::kBipWarps;
       const int64_t grid = int64_t(g.NS) * g.NR * groups;
-      const size_t smem = pgx::bip_smem_bytes(g.RI, TJ);
+      // c_old == nullptr: first iteration of a run, the input rows are in the full layout
+      const bool in_full = c_old == nullptr;
+      const size_t smem = pgx::bip_smem_bytes(g.RI, TJ, in_full);
       static bool attr_set[2] = {false, false};
       if (!attr_set[kSum]) {
-        PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pw2_bip<kSum, TJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(pgx::bip_smem_bytes(32, TJ))));
-        PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pw2_bip<kSum, TJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      int(pgx::bip_smem_bytes(32, TJ))));
+#define PGX_BIP_ATTR(DELTA, FULL)                                                                          \
+  PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pw2_bip<kSum, TJ, DELTA, FULL>,                                 \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, int(pgx::bip_smem_bytes(32, TJ, FULL))))
+        PGX_BIP_ATTR(true, true); PGX_BIP_ATTR(true, false); PGX_BIP_ATTR(false, true); PGX_BIP_ATTR(false, false);
+#undef PGX_BIP_ATTR
         attr_set[kSum] = true;
       }
-      if (a.deltas != nullptr)
-        pgx::k_enum_pw2_bip<kSum, TJ, true><<<unsigned(grid), pgx::kBipWarps * 32, smem, st>>>(
-            mp.batch, groups, g, lp.p, S, m_old, m_new, plan->ws.part, plan->part_rows, a);
-      else
-        pgx::k_enum_pw2_bip<kSum, TJ, false><<<unsigned(grid), pgx::kBipWarps * 32, smem, st>>>(
-            mp.batch, groups, g, lp.p, S, m_old, m_new, plan->ws.part, plan->part_rows, a);
+      const float* src = in_full ? m_old : c_old;
+      const int64_t src_rows = in_full ? a.Es : plan->c_rows;
+#define PGX_BIP_LAUNCH(DELTA, FULL)                                                                       \
+  pgx::k_enum_pw2_bip<kSum, TJ, DELTA, FULL><<<unsigned(grid), pgx::kBipWarps * 32, smem, st>>>(           \
+      mp.batch, groups, g, lp.p, S, src, src_rows, c_new, plan->c_rows, plan->ws.part, plan->part_rows, a)
+      if (a.deltas != nullptr) {
+        if (in_full) PGX_BIP_LAUNCH(true, true); else PGX_BIP_LAUNCH(true, false);
+      } else {
+        if (in_full) PGX_BIP_LAUNCH(false, true); else PGX_BIP_LAUNCH(false, false);
+      }
+#undef PGX_BIP_LAUNCH
       if ((rc = check_launch(plan, "k_enum_pw2_bip"))) return rc;
       if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2_bip";
     } else if (eb.variant == kPw2) {
@@ -1068,6 +1084,8 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
         PGX_TRY(upload(col_part, &bp.d_col_part, &plan->device_bytes));
         bp.dev.first_msg = eb.dev.first_msg;
         bp.dev.first_pot = eb.dev.first_pot;
+        bp.dev.first_cmsg = plan->c_rows;
+        plan->c_rows += 2 * int64_t(gr.I) * gr.J;
         bp.dev.I = gr.I;
         bp.dev.J = gr.J;
         bp.dev.NS = (gr.J + TJ - 1) / TJ;
@@ -1485,10 +1503,13 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     }
     // With one sample the last iteration writes straight into the caller's buffer.
     float* dst = (single && it == num_iters - 1) ? ftov_out : nxt;
+    // fused blocks keep their messages compressed (ws.cA / ws.cB) after the first iteration
+    const float* c_old = (fused && it > 0) ? ((it & 1) ? ws.cA : ws.cB) : nullptr;
+    float* c_new = fused ? ((it & 1) ? ws.cB : ws.cA) : nullptr;
     if (temperature == 0.f)
-      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux);
+      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new);
     else
-      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux);
+      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new);
     if (rc) return rc;
     if (aux != nullptr) {
       PGX_CUDA(cudaEventRecord(plan->ev_join, aux));
@@ -1505,8 +1526,27 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     nxt = (dst == ws.mA) ? ws.mB : ws.mA;
     cur = dst;
   }
-  if (!single) {
+  if (!single && !fused) {
     if ((rc = from_tiles(plan, st, cur, ftov_out, Es, mp))) return rc;
+  } else if (!single) {
+    // the fused blocks' messages are expanded from the compressed array, the rest comes from
+    // the full-layout buffer (message ranges of the blocks are disjoint and ascending)
+    const float* c_fin = ((num_iters - 1) & 1) ? ws.cB : ws.cA;
+    int64_t done = 0;
+    std::vector<const BipPlan*> order;
+    for (const BipPlan& bp : plan->bips) order.push_back(&bp);
+    std::sort(order.begin(), order.end(), [](const BipPlan* x, const BipPlan* y) { return x->dev.first_msg < y->dev.first_msg; });
+    for (const BipPlan* bpp : order) {
+      const BipPlan& bp = *bpp;
+      const int64_t count = 2 * int64_t(bp.dev.I) * bp.dev.J;
+      if ((rc = from_tiles(plan, st, cur, ftov_out, Es, mp, done, bp.dev.first_msg))) return rc;
+      dim3 grid((unsigned)((count + 31) / 32), (unsigned)((mp.batch + 31) / 32)), block(32, 8);
+      pgx::k_expand_bin<<<grid, block, 0, st>>>(c_fin, plan->c_rows, bp.dev.first_cmsg, count, ftov_out, Es,
+                                                bp.dev.first_msg, mp);
+      if ((rc = check_launch(plan, "k_expand_bin"))) return rc;
+      done = bp.dev.first_msg + 2 * count;
+    }
+    if ((rc = from_tiles(plan, st, cur, ftov_out, Es, mp, done, Es))) return rc;
   }
   return PGX_OK;
 }

@@ -147,20 +147,50 @@ __global__ void k_to_tiles(const float* __restrict__ src, float* __restrict__ ds
 }
 
 __global__ void k_from_tiles(const float* __restrict__ src, float* __restrict__ dst, int64_t N,
-                             BatchMap mp) {
+                             int64_t n_begin, int64_t n_end, BatchMap mp) {
+  // rows [n_begin, n_end) of the N-row arrays
   __shared__ float tile[32][33];
-  const int64_t n0 = int64_t(blockIdx.x) * 32;
+  const int64_t n0 = n_begin + int64_t(blockIdx.x) * 32;
   const int b0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int64_t n = n0 + r;
     const int b = b0 + threadIdx.x;
-    tile[r][threadIdx.x] = (n < N && b < mp.batch) ? src[lane_off(mp, N, b) + (n << mp.bx_log)] : 0.f;
+    tile[r][threadIdx.x] = (n < n_end && b < mp.batch) ? src[lane_off(mp, N, b) + (n << mp.bx_log)] : 0.f;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int b = b0 + r;
     const int64_t n = n0 + threadIdx.x;
-    if (b < mp.batch && n < N) dst[int64_t(b) * N + n] = tile[threadIdx.x][r];
+    if (b < mp.batch && n < n_end) dst[int64_t(b) * N + n] = tile[threadIdx.x][r];
+  }
+}
+
+// Compressed binary messages (one float per edge, rows [c_begin, c_begin + count) of the
+// c_rows-row tile-blocked array) -> the ABI's batch-major array: edge c -> message rows
+// first_msg + 2c (pointed state), + 2c + 1.  Full sample tiles only (bx_log == 5).
+__global__ void k_expand_bin(const float* __restrict__ src, int64_t c_rows, int64_t c_begin, int64_t count,
+                             float* __restrict__ dst, int64_t N, int64_t first_msg, BatchMap mp) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = int64_t(blockIdx.x) * 32;
+  const int b0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t c = c0 + r;
+    const int b = b0 + threadIdx.x;
+    tile[r][threadIdx.x] = (c < count && b < mp.batch) ? src[lane_off(mp, c_rows, b) + ((c_begin + c) << 5)] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int b = b0 + r;
+    if (b >= mp.batch) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int e = h * 32 + threadIdx.x;  // element of the 64 output floats of this tile
+      const int64_t c = c0 + (e >> 1);
+      if (c < count) {
+        const float x = tile[e >> 1][r];
+        dst[int64_t(b) * N + first_msg + 2 * c0 + e] = (e & 1) ? fminf(x, 0.f) : fminf(-x, 0.f);
+      }
+    }
   }
 }
 
@@ -1075,6 +1105,7 @@ k_lattice_stream(LatticeDev g, const float* __restrict__ ev, const float* __rest
 // ---------------------------------------------------------------------------
 struct BipDev {
   int64_t first_msg, first_pot;
+  int64_t first_cmsg;    // first row of the block in the compressed (one float per edge) message array
   int32_t I, J;          // rows, columns
   int32_t NS, NR, RI;    // column strips, row chunks, rows per chunk
   const int32_t* row_vs;   // [I] var-state of state 0 of row variable i
@@ -1085,24 +1116,40 @@ struct BipDev {
 
 constexpr int kBipWarps = 4;
 constexpr int kBipTJ = 16;
-constexpr int kBipStages = 3;
+constexpr int kBipStages = 3;   // ring depth when the input rows are full (4 floats per factor)
+constexpr int kBipStagesC = 4;  // ... when they are compressed (2 floats per factor)
 
 // dynamic shared memory of k_enum_pw2_bip
-__host__ __device__ constexpr size_t bip_smem_bytes(int RI, int TJ) {
-  return size_t(kBipWarps) * kBipStages * TJ * 4 * 32 * sizeof(float)  // rings
-         + size_t(RI) * TJ * 4 * sizeof(float)                         // potentials
-         + size_t(kBipWarps) * kBipStages * sizeof(uint64_t);          // mbarriers
+__host__ __device__ constexpr size_t bip_smem_bytes(int RI, int TJ, bool in_full) {
+  return size_t(kBipWarps) * (in_full ? kBipStages * 4 : kBipStagesC * 2) * TJ * 32 * sizeof(float)  // rings
+         + size_t(RI) * TJ * 4 * sizeof(float)                                                       // potentials
+         + size_t(kBipWarps) * (in_full ? kBipStages : kBipStagesC) * sizeof(uint64_t);              // mbarriers
 }
 
-template <bool kSumProduct, int TJ, bool kDelta>
+// Binary-difference storage.  A normalised message of a two-state edge is (n_p, n_r) with
+// max(n_p, n_r) == 0 exactly, so the single float x = n_r - n_p carries both states without
+// loss: n_p = min(-x, 0), n_r = min(x, 0) (one of the two is the exact zero, the other is
+// +-x; the clip at -1e32 commutes).  Between iterations the fused kernel keeps only x: half
+// the message traffic of the reference layout, bit-identical values.
+__device__ __forceinline__ void bin_expand(float x, float& n_p, float& n_r) {
+  n_p = fminf(-x, 0.f);
+  n_r = fminf(x, 0.f);
+}
+
+// kInFull: the input rows are in the full tile-blocked layout (first iteration of a run);
+// the output is always compressed.
+template <bool kSumProduct, int TJ, bool kDelta, bool kInFull>
 __global__ void __launch_bounds__(kBipWarps * 32)
 k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp,
-               const float* __restrict__ S, const float* __restrict__ m_old,
-               float* __restrict__ m_new, float* __restrict__ part, int64_t part_rows, RunArgs a) {
-  constexpr int kRowFloats = TJ * 4 * 32;  // one row of a strip for one sample tile
+               const float* __restrict__ S, const float* __restrict__ m_old, int64_t old_rows,
+               float* __restrict__ c_new, int64_t c_rows, float* __restrict__ part, int64_t part_rows,
+               RunArgs a) {
+  constexpr int kIn = kInFull ? 4 : 2;           // floats per factor and sample in the input rows
+  constexpr int kStages = kInFull ? kBipStages : kBipStagesC;
+  constexpr int kRowFloats = TJ * kIn * 32;      // one input row of a strip for one sample tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw);
-  float* lp_s = ring + kBipWarps * kBipStages * kRowFloats;  // [RI][TJ][4]
+  float* lp_s = ring + kBipWarps * kStages * kRowFloats;  // [RI][TJ][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(lp_s + g.RI * TJ * 4);
 
   // blockIdx.x = (chunk * NS + strip) * nbt_groups + sample-tile group
@@ -1117,7 +1164,7 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
   const bool active = bt * 32 < batch;       // whole warp in or out
   const int b = bt * 32 + lane;
 
-  if (threadIdx.x < kBipWarps * kBipStages) mbar_init(&bars[threadIdx.x], 1);
+  if (threadIdx.x < kBipWarps * kStages) mbar_init(&bars[threadIdx.x], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   for (int t = threadIdx.x; t < (i1 - i0) * TJ * 4; t += blockDim.x) {
     const int r = t / (TJ * 4), c = t - r * (TJ * 4);
@@ -1126,19 +1173,22 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
   __syncthreads();
   if (!active) return;
 
-  float* my_ring = ring + w * kBipStages * kRowFloats;
-  uint64_t* my_bar = bars + w * kBipStages;
-  const uint32_t row_bytes = uint32_t(nj) * 4 * 32 * sizeof(float);
+  float* my_ring = ring + w * kStages * kRowFloats;
+  uint64_t* my_bar = bars + w * kStages;
+  const uint32_t in_bytes = uint32_t(nj) * kIn * 32 * sizeof(float);
+  const uint32_t out_bytes = uint32_t(nj) * 2 * 32 * sizeof(float);
   // global float offset of (row i, first factor of the strip) for this sample tile
-  const int64_t tile_base = (int64_t(bt) * a.Es + g.first_msg) * 32;
-  auto row_off = [&](int i) { return tile_base + (int64_t(i) * g.J + j0) * (4 * 32); };
+  const int64_t in_base = (int64_t(bt) * old_rows + (kInFull ? g.first_msg : g.first_cmsg)) * 32;
+  const int64_t out_base = (int64_t(bt) * c_rows + g.first_cmsg) * 32;
+  auto in_off = [&](int i) { return in_base + (int64_t(i) * g.J + j0) * (kIn * 32); };
+  auto out_off = [&](int i) { return out_base + (int64_t(i) * g.J + j0) * (2 * 32); };
   const int nrows = i1 - i0;
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < kBipStages - 1; ++s)
+    for (int s = 0; s < kStages - 1; ++s)
       if (s < nrows) {
-        mbar_expect_tx(&my_bar[s], row_bytes);
-        bulk_g2s(my_ring + s * kRowFloats, m_old + row_off(i0 + s), row_bytes, &my_bar[s]);
+        mbar_expect_tx(&my_bar[s], in_bytes);
+        bulk_g2s(my_ring + s * kRowFloats, m_old + in_off(i0 + s), in_bytes, &my_bar[s]);
       }
   }
 
@@ -1158,7 +1208,7 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
   float Sr0 = SL[rvs * 32], Sr1 = SL[(rvs + 1) * 32];
   for (int r = 0; r < nrows; ++r) {
     const int i = i0 + r;
-    const int stage = r % kBipStages;
+    const int stage = r % kStages;
     float* buf = my_ring + stage * kRowFloats + lane;
     // row sums of the NEXT row: issue the loads before waiting on this row's data
     float nSr0 = 0.f, nSr1 = 0.f;
@@ -1167,21 +1217,28 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
       nSr0 = SL[rvs * 32];
       nSr1 = SL[(rvs + 1) * 32];
     }
-    mbar_wait(&my_bar[stage], (r / kBipStages) & 1);
+    mbar_wait(&my_bar[stage], (r / kStages) & 1);
     const float* lrow = lp_s + r * TJ * 4;
     float ar0 = 0.f, ar1 = 0.f;
 #pragma unroll
     for (int jj = 0; jj < TJ; ++jj) {
       if (jj < nj) {
         const float4 lq = *reinterpret_cast<const float4*>(lrow + 4 * jj);
-        const float mo[4] = {buf[(4 * jj) * 32], buf[(4 * jj + 1) * 32], buf[(4 * jj + 2) * 32],
-                             buf[(4 * jj + 3) * 32]};
+        float mo[4];
+        if (kInFull) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mo[k] = buf[(4 * jj + k) * 32];
+        } else {
+          bin_expand(buf[(2 * jj) * 32], mo[0], mo[1]);
+          bin_expand(buf[(2 * jj + 1) * 32], mo[2], mo[3]);
+        }
         const float Sv[4] = {Sr0, Sr1, Sc0[jj], Sc1[jj]};
         const float lpv[4] = {lq.x, lq.y, lq.z, lq.w};
         float n[4];
         dmax = fmaxf(dmax, pw2_update<kSumProduct, kDelta>(mo, Sv, lpv, a, n));
-#pragma unroll
-        for (int k = 0; k < 4; ++k) buf[(4 * jj + k) * 32] = n[k];
+        // compressed in place: rows 2jj, 2jj+1 of the stage were read already (<= 4jj)
+        buf[(2 * jj) * 32] = n[1] - n[0];
+        buf[(2 * jj + 1) * 32] = n[3] - n[2];
         ar0 += n[0]; ar1 += n[1];
         ac0[jj] += n[2]; ac1[jj] += n[3];
       }
@@ -1193,15 +1250,15 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      bulk_s2g(m_new + row_off(i), my_ring + stage * kRowFloats, row_bytes);
+      bulk_s2g(c_new + out_off(i), my_ring + stage * kRowFloats, out_bytes);
       bulk_commit();
       // refill the stage the PREVIOUS row used once its store has drained
-      const int nr = r + kBipStages - 1;
+      const int nr = r + kStages - 1;
       if (nr < nrows) {
         bulk_wait_read<1>();
-        const int ns = nr % kBipStages;
-        mbar_expect_tx(&my_bar[ns], row_bytes);
-        bulk_g2s(my_ring + ns * kRowFloats, m_old + row_off(i0 + nr), row_bytes, &my_bar[ns]);
+        const int ns = nr % kStages;
+        mbar_expect_tx(&my_bar[ns], in_bytes);
+        bulk_g2s(my_ring + ns * kRowFloats, m_old + in_off(i0 + nr), in_bytes, &my_bar[ns]);
       }
     }
     Sr0 = nSr0;
