@@ -455,6 +455,12 @@ def main():
     dom_es = es if single_kernel else min(plan.dominant_edge_states, es)
     kernel_bytes = bytes_iter * dom_es // es
     achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if n_prof else None
+    # bytes the kernels really have to move: the single-pass path stores a two-state edge as
+    # ONE float between iterations (pgx_plan_compressed_edges), i.e. one float less to read and
+    # one less to write per such edge, sample and iteration than the reference layout
+    fused_run = plan.has_fused_blocks and not args.exact_order and batch > 16 and not lp_batched
+    saved = 8 * plan.compressed_edges * batch if fused_run else 0
+    layout_bytes = bytes_iter - saved
     iter_ms = ms / args.steps / iters
     iter_gbs = bytes_iter / (iter_ms * 1e-3) / 1e9
     line = {
@@ -481,7 +487,15 @@ def main():
                      "edge_states_per_launch": dom_es * batch,
                      # the whole iteration (every kernel of it) against the same peak
                      "iter_ms": iter_ms, "iter_algorithmic_bytes": bytes_iter,
-                     "iter_achieved": iter_gbs, "iter_frac": iter_gbs / peak},
+                     "iter_achieved": iter_gbs, "iter_frac": iter_gbs / peak,
+                     # the same two figures against the bytes of the workspace layout actually
+                     # used (binary-difference storage halves the message bytes): <= 1 by construction
+                     "storage": ("binary-difference, 1 float per two-state edge between iterations"
+                                 if saved else "reference layout, 1 float per edge-state"),
+                     "layout_bytes_per_iter": layout_bytes,
+                     "layout_frac": (layout_bytes * (kernel_bytes / bytes_iter) / (kernel_ms * 1e-3) / 1e9 / peak)
+                     if n_prof else None,
+                     "layout_iter_frac": layout_bytes / (iter_ms * 1e-3) / 1e9 / peak},
         "checksum_max_abs_msg": checksum,
     }
     if world == 1 and not args.no_cpu_baseline:

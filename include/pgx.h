@@ -194,6 +194,13 @@ int64_t pgx_plan_launch_count(const pgx_plan* plan);
 int pgx_plan_set_exact_order(pgx_plan* plan, int enabled);
 /* Number of enum blocks for which the single-pass path is available. */
 int pgx_plan_num_fused_blocks(const pgx_plan* plan);
+/* Edges (per sample) whose messages the single-pass path keeps in binary-difference
+ * storage between iterations: a normalised message of a two-state edge is (n0, n1) with
+ * max(n0, n1) == 0 exactly, so the one float x = n1 - n0 carries both states without loss
+ * (n0 = min(-x, 0), n1 = min(x, 0)).  The ABI arrays keep the reference's layout; only the
+ * workspace between iterations is compressed (half the message traffic, bit-identical
+ * values).  bench.py uses the count for the bytes the kernels actually have to move. */
+int64_t pgx_plan_compressed_edges(const pgx_plan* plan);
 
 /* Specialised launch paths pgx_bp_run may choose from the graph's structure.  Every path
  * computes the same arithmetic in the same order (bit-identical messages); the mask only

@@ -14,7 +14,8 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpgx.so")
+# PGX_LIB: another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("PGX_LIB") or os.path.join(_HERE, "csrc", "libpgx.so")
 BUILD_SCRIPT = os.path.join(_HERE, "csrc", "build.sh")
 
 PGX_OK = 0
@@ -36,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "pgx_plan_launch_count",
     "pgx_plan_set_exact_order",
     "pgx_plan_num_fused_blocks",
+    "pgx_plan_compressed_edges",
     "pgx_plan_disable_paths",
     "pgx_plan_is_lattice",
     "pgx_plan_dominant_edge_states",
@@ -159,6 +161,8 @@ def load() -> ctypes.CDLL:
   lib.pgx_plan_launch_count.restype = ctypes.c_int64
   lib.pgx_plan_num_fused_blocks.argtypes = [vp]
   lib.pgx_plan_num_fused_blocks.restype = ctypes.c_int
+  lib.pgx_plan_compressed_edges.argtypes = [vp]
+  lib.pgx_plan_compressed_edges.restype = ctypes.c_int64
   lib.pgx_plan_set_exact_order.argtypes = [vp, ctypes.c_int]
   lib.pgx_plan_set_exact_order.restype = ctypes.c_int
   lib.pgx_plan_disable_paths.argtypes = [vp, ctypes.c_uint32]
@@ -363,6 +367,11 @@ class Plan:
   def has_fused_blocks(self) -> bool:
     """True when the plan found dense-grid pairwise blocks (single-pass path available)."""
     return bool(self._lib.pgx_plan_num_fused_blocks(self.handle))
+
+  @property
+  def compressed_edges(self) -> int:
+    """Edges per sample the single-pass path stores as one float (binary-difference storage)."""
+    return int(self._lib.pgx_plan_compressed_edges(self.handle))
 
   PATH_LATTICE, PATH_RESIDENT, PATH_PULL, PATH_MERGED_MAX, PATH_LOGICAL_PULL = 1, 2, 4, 8, 16
   PATH_LATTICE_STREAM, PATH_AUX_STREAM, PATH_WIDE_SPLIT = 32, 64, 128

@@ -542,10 +542,11 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
     if (fused && eb.bip >= 0) {
       const pgx::BipDev& g = plan->bips[eb.bip].dev;
       constexpr int TJ = pgx::kBipTJ;
-      const int groups = (mp.nbt + pgx::kBipWarps - 1) / pgx::kBipWarps;
-      const int64_t grid = int64_t(g.NS) * g.NR * groups;
       // c_old == nullptr: first iteration of a run, the input rows are in the full layout
       const bool in_full = c_old == nullptr;
+      const int warps = pgx::bip_warps(in_full);
+      const int groups = (mp.nbt + warps - 1) / warps;
+      const int64_t grid = int64_t(g.NS) * g.NR * groups;
       const size_t smem = pgx::bip_smem_bytes(g.RI, TJ, in_full);
       static bool attr_set[2] = {false, false};
       if (!attr_set[kSum]) {
@@ -559,7 +560,7 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       const float* src = in_full ? m_old : c_old;
       const int64_t src_rows = in_full ? a.Es : plan->c_rows;
 #define PGX_BIP_LAUNCH(DELTA, FULL)                                                                       \
-  pgx::k_enum_pw2_bip<kSum, TJ, DELTA, FULL><<<unsigned(grid), pgx::kBipWarps * 32, smem, st>>>(           \
+  pgx::k_enum_pw2_bip<kSum, TJ, DELTA, FULL><<<unsigned(grid), warps * 32, smem, st>>>(                    \
       mp.batch, groups, g, lp.p, S, src, src_rows, c_new, plan->c_rows, plan->ws.part, plan->part_rows, a)
       if (a.deltas != nullptr) {
         if (in_full) PGX_BIP_LAUNCH(true, true); else PGX_BIP_LAUNCH(true, false);
@@ -1194,6 +1195,7 @@ int pgx_plan_set_exact_order(pgx_plan* plan, int enabled) {
 }
 
 int pgx_plan_num_fused_blocks(const pgx_plan* plan) { return plan ? int(plan->bips.size()) : 0; }
+int64_t pgx_plan_compressed_edges(const pgx_plan* plan) { return plan ? plan->c_rows : 0; }
 
 int pgx_plan_disable_paths(pgx_plan* plan, uint32_t mask) {
   if (!plan) return fail(PGX_ERR_INVALID, "null plan");

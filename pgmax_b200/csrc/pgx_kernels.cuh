@@ -1114,16 +1114,17 @@ struct BipDev {
   const int32_t* col_part; // [J] same for column variables / row chunks
 };
 
-constexpr int kBipWarps = 4;
 constexpr int kBipTJ = 16;
-constexpr int kBipStages = 3;   // ring depth when the input rows are full (4 floats per factor)
-constexpr int kBipStagesC = 4;  // ... when they are compressed (2 floats per factor)
+constexpr int kBipStages = 3;  // ring depth
+// warps (= sample tiles) per CTA: 8 with compressed input rows (two CTAs of 104 KiB per SM, 16
+// warps: the kernel is issue-latency-bound, not bandwidth-bound, below that), 4 with full rows
+__host__ __device__ constexpr int bip_warps(bool in_full) { return in_full ? 4 : 8; }
 
 // dynamic shared memory of k_enum_pw2_bip
 __host__ __device__ constexpr size_t bip_smem_bytes(int RI, int TJ, bool in_full) {
-  return size_t(kBipWarps) * (in_full ? kBipStages * 4 : kBipStagesC * 2) * TJ * 32 * sizeof(float)  // rings
-         + size_t(RI) * TJ * 4 * sizeof(float)                                                       // potentials
-         + size_t(kBipWarps) * (in_full ? kBipStages : kBipStagesC) * sizeof(uint64_t);              // mbarriers
+  return size_t(bip_warps(in_full)) * kBipStages * (in_full ? 4 : 2) * TJ * 32 * sizeof(float)  // rings
+         + size_t(RI) * TJ * 4 * sizeof(float)                                                  // potentials
+         + size_t(bip_warps(in_full)) * kBipStages * sizeof(uint64_t);                          // mbarriers
 }
 
 // Binary-difference storage.  A normalised message of a two-state edge is (n_p, n_r) with
@@ -1136,16 +1137,122 @@ __device__ __forceinline__ void bin_expand(float x, float& n_p, float& n_r) {
   n_r = fminf(x, 0.f);
 }
 
+
+// ---- packed fp32x2 arithmetic (sm_100a FADD2 / FMUL2 / FFMA2: two IEEE fp32 operations per
+// issued instruction; each half rounds exactly like the scalar instruction) -----------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// Scalars of a run in packed form.
+struct RunArgs2 {
+  f32x2 d, one_minus_d, c_exp, c_log, one;
+};
+__device__ __forceinline__ RunArgs2 make_args2(const RunArgs& a) {
+  RunArgs2 r;
+  r.d = pk2(a.d, a.d);
+  r.one_minus_d = pk2(a.one_minus_d, a.one_minus_d);
+  r.c_exp = pk2(a.c_exp, a.c_exp);
+  r.c_log = pk2(a.c_log, a.c_log);
+  r.one = pk2(1.0f, 1.0f);
+  return r;
+}
+
+// Two two-term logsumexps at once: lse(a_i, b_i) given the pairs (a - b) and max(a, b).
+template <bool kSumProduct>
+__device__ __forceinline__ f32x2 lse2_x2(f32x2 diff, f32x2 mx, const RunArgs2& c) {
+  if (!kSumProduct) return mx;
+  float t0, t1;
+  upk2(mul2(diff, c.c_exp), t0, t1);
+  float l0, l1;
+  upk2(add2(pk2(ex2_approx(-fabsf(t0)), ex2_approx(-fabsf(t1))), c.one), l0, l1);
+  return fma2(c.c_log, pk2(lg2_approx(l0), lg2_approx(l1)), mx);
+}
+
+// pw2_update on binary-difference storage, packed: xa / xb are the stored differences of the
+// two edges, Sa / Sb the (state 0, state 1) variable sums, lp01 / lp23 the clipped potentials
+// (0,0),(0,1) / (1,0),(1,1).  Returns the new differences and the normalised new messages
+// na = (n0, n1), nb = (n2, n3) (for the partial sums); same operations and roundings as
+// pw2_update followed by n1 - n0.
+template <bool kSumProduct, bool kDelta>
+__device__ __forceinline__ float pw2_update_bin(float xa, float xb, f32x2 Sa, f32x2 Sb, f32x2 lp01, f32x2 lp23,
+                                                const RunArgs2& c, float& xa_new, float& xb_new, f32x2& na,
+                                                f32x2& nb) {
+  const f32x2 ma = pk2(fminf(-xa, 0.f), fminf(xa, 0.f)), mb = pk2(fminf(-xb, 0.f), fminf(xb, 0.f));
+  const f32x2 qa = sub2(Sa, ma), qb = sub2(Sb, mb);
+  float q0, q1, q2, q3;
+  upk2(qa, q0, q1);
+  upk2(qb, q2, q3);
+  const f32x2 P = add2(pk2(q0 + q2, q0 + q3), lp01);  // (s00, s01)
+  const f32x2 Q = add2(pk2(q1 + q2, q1 + q3), lp23);  // (s10, s11)
+  float s00, s01, s10, s11;
+  upk2(P, s00, s01);
+  upk2(Q, s10, s11);
+  // messages to variable b: lse over the state of a, element-wise on (P, Q)
+  const f32x2 fb = sub2(lse2_x2<kSumProduct>(sub2(P, Q), pk2(fmaxf(s00, s10), fmaxf(s01, s11)), c), qb);
+  // messages to variable a: lse over the state of b, within P and within Q
+  const f32x2 fa = sub2(lse2_x2<kSumProduct>(pk2(s00 - s01, s10 - s11), pk2(fmaxf(s00, s01), fmaxf(s10, s11)), c), qa);
+  f32x2 da, db;
+  if (kSumProduct) {
+    da = fma2(c.d, ma, mul2(c.one_minus_d, fa));
+    db = fma2(c.d, mb, mul2(c.one_minus_d, fb));
+  } else {
+    da = add2(mul2(c.d, ma), mul2(c.one_minus_d, fa));
+    db = add2(mul2(c.d, mb), mul2(c.one_minus_d, fb));
+  }
+  float n0, n1, n2, n3;
+  upk2(da, n0, n1);
+  upk2(db, n2, n3);
+  // (n1 - mx) - (n0 - mx) with mx = max(n0, n1) is n1 - n0 exactly (one term is the exact 0);
+  // the clip of the smaller state at -1e32 becomes a clamp of the difference
+  xa_new = fminf(fmaxf(n1 - n0, kMsgNegInf), -kMsgNegInf);
+  xb_new = fminf(fmaxf(n3 - n2, kMsgNegInf), -kMsgNegInf);
+  na = pk2(fminf(-xa_new, 0.f), fminf(xa_new, 0.f));
+  nb = pk2(fminf(-xb_new, 0.f), fminf(xb_new, 0.f));
+  if (!kDelta) return 0.f;
+  float e0, e1, e2, e3;
+  upk2(sub2(na, ma), e0, e1);
+  upk2(sub2(nb, mb), e2, e3);
+  return fmaxf(fmaxf(fabsf(e0), fabsf(e1)), fmaxf(fabsf(e2), fabsf(e3)));
+}
+
 // kInFull: the input rows are in the full tile-blocked layout (first iteration of a run);
 // the output is always compressed.
 template <bool kSumProduct, int TJ, bool kDelta, bool kInFull>
-__global__ void __launch_bounds__(kBipWarps * 32)
+__global__ void __launch_bounds__(bip_warps(kInFull) * 32)
 k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp,
                const float* __restrict__ S, const float* __restrict__ m_old, int64_t old_rows,
                float* __restrict__ c_new, int64_t c_rows, float* __restrict__ part, int64_t part_rows,
                RunArgs a) {
   constexpr int kIn = kInFull ? 4 : 2;           // floats per factor and sample in the input rows
-  constexpr int kStages = kInFull ? kBipStages : kBipStagesC;
+  constexpr int kStages = kBipStages;
+  constexpr int kBipWarps = bip_warps(kInFull);
   constexpr int kRowFloats = TJ * kIn * 32;      // one input row of a strip for one sample tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw);
@@ -1194,14 +1301,13 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
 
   const float* SL = S + (int64_t(bt) * a.Vs) * 32 + lane;
   float* PL = part + (int64_t(bt) * part_rows) * 32 + lane;
-  float Sc0[TJ], Sc1[TJ], ac0[TJ], ac1[TJ];
+  const RunArgs2 c2 = make_args2(a);
+  f32x2 Sc[TJ], ac[TJ];  // (state 0, state 1) pairs
 #pragma unroll
   for (int jj = 0; jj < TJ; ++jj) {
     const int64_t vs = g.col_vs[min(j0 + jj, g.J - 1)];
-    Sc0[jj] = SL[vs * 32];
-    Sc1[jj] = SL[(vs + 1) * 32];
-    ac0[jj] = 0.f;
-    ac1[jj] = 0.f;
+    Sc[jj] = pk2(SL[vs * 32], SL[(vs + 1) * 32]);
+    ac[jj] = 0ull;
   }
   float dmax = 0.f;
   int64_t rvs = g.row_vs[i0];
@@ -1219,30 +1325,33 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
     }
     mbar_wait(&my_bar[stage], (r / kStages) & 1);
     const float* lrow = lp_s + r * TJ * 4;
-    float ar0 = 0.f, ar1 = 0.f;
+    f32x2 ar = 0ull;
+    const f32x2 Sr = pk2(Sr0, Sr1);
 #pragma unroll
     for (int jj = 0; jj < TJ; ++jj) {
       if (jj < nj) {
         const float4 lq = *reinterpret_cast<const float4*>(lrow + 4 * jj);
-        float mo[4];
-        if (kInFull) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) mo[k] = buf[(4 * jj + k) * 32];
+        float xa, xb;
+        if (kInFull) {  // normalised input: max(m0, m1) == 0, the difference is exact
+          xa = buf[(4 * jj + 1) * 32] - buf[(4 * jj) * 32];
+          xb = buf[(4 * jj + 3) * 32] - buf[(4 * jj + 2) * 32];
         } else {
-          bin_expand(buf[(2 * jj) * 32], mo[0], mo[1]);
-          bin_expand(buf[(2 * jj + 1) * 32], mo[2], mo[3]);
+          xa = buf[(2 * jj) * 32];
+          xb = buf[(2 * jj + 1) * 32];
         }
-        const float Sv[4] = {Sr0, Sr1, Sc0[jj], Sc1[jj]};
-        const float lpv[4] = {lq.x, lq.y, lq.z, lq.w};
-        float n[4];
-        dmax = fmaxf(dmax, pw2_update<kSumProduct, kDelta>(mo, Sv, lpv, a, n));
+        float xan, xbn;
+        f32x2 na, nb;
+        dmax = fmaxf(dmax, pw2_update_bin<kSumProduct, kDelta>(xa, xb, Sr, Sc[jj], pk2(lq.x, lq.y), pk2(lq.z, lq.w),
+                                                               c2, xan, xbn, na, nb));
         // compressed in place: rows 2jj, 2jj+1 of the stage were read already (<= 4jj)
-        buf[(2 * jj) * 32] = n[1] - n[0];
-        buf[(2 * jj + 1) * 32] = n[3] - n[2];
-        ar0 += n[0]; ar1 += n[1];
-        ac0[jj] += n[2]; ac1[jj] += n[3];
+        buf[(2 * jj) * 32] = xan;
+        buf[(2 * jj + 1) * 32] = xbn;
+        ar = add2(ar, na);
+        ac[jj] = add2(ac[jj], nb);
       }
     }
+    float ar0, ar1;
+    upk2(ar, ar0, ar1);
     const int64_t pr = (int64_t(g.row_part[i]) + 2 * js) * 32;
     PL[pr] = ar0;
     PL[pr + 32] = ar1;
@@ -1268,8 +1377,10 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
   for (int jj = 0; jj < TJ; ++jj) {
     if (jj < nj) {
       const int64_t pc = (int64_t(g.col_part[j0 + jj]) + 2 * rc) * 32;
-      PL[pc] = ac0[jj];
-      PL[pc + 32] = ac1[jj];
+      float ac0, ac1;
+      upk2(ac[jj], ac0, ac1);
+      PL[pc] = ac0;
+      PL[pc + 32] = ac1;
     }
   }
   if (kDelta && b < batch) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
