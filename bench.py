@@ -333,6 +333,7 @@ def main():
   ap.add_argument("--iters", type=int, default=None, help="BP iterations per step override")
   ap.add_argument("--size", type=int, default=None, help="grid side of the ising_big workload")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--disable-paths", type=int, default=0, help="PGX_PATH_* mask (A/B runs of launch paths)")
   ap.add_argument("--exact-order", action="store_true",
                   help="force the two-pass serial-summation-order path (pgx_plan_set_exact_order)")
   args = ap.parse_args()
@@ -369,6 +370,7 @@ def main():
                     evidence=rng.gumbel(size=host.evidence.shape).astype(np.float32))
   plan = bp.context.plan
   plan.set_exact_order(args.exact_order)
+  plan.disable_paths(args.disable_paths)
   batch = host.batch_size or 1
   put = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
   dev_arrays = BPArrays(log_potentials=put(host.log_potentials), ftov_msgs=put(host.ftov_msgs),

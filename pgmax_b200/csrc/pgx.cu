@@ -430,7 +430,8 @@ int build_enum_block(pgx_plan* plan, const pgx_enum_block* desc_blocks, const st
   return PGX_OK;
 }
 
-int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT, bool need_part) {
+int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT, bool need_part,
+                     bool need_lbin = false) {
   Workspace& ws = plan->ws;
   const pgx::BatchMap mp = make_map(batch);
   if (ws.batch != batch) {
@@ -456,6 +457,11 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.part), tiled_floats(mp, plan->part_rows) * sizeof(float)));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cA), tiled_floats(mp, plan->c_rows) * sizeof(float)));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cB), tiled_floats(mp, plan->c_rows) * sizeof(float)));
+  }
+  if (need_lbin && ws.cA == nullptr) {
+    const size_t nc = tiled_floats(mp, plan->num_edge_states / 2) * sizeof(float);
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cA), nc));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cB), nc));
   }
   if (need_evT && ws.evT == nullptr)
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.evT), tiled_floats(mp, plan->num_var_states) * sizeof(float)));
@@ -504,7 +510,7 @@ int prof_mark(pgx_plan* plan, cudaStream_t st, int id) {
 template <bool kSum>
 int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::View lp, const float* S,
                const float* m_old, float* m_new, const pgx::RunArgs& a, bool fused, bool lpull, pgx::View ev,
-               cudaStream_t aux, const float* c_old = nullptr, float* c_new = nullptr) {
+               cudaStream_t aux, const float* c_old = nullptr, float* c_new = nullptr, bool lbin = false) {
   int rc;
   const bool merged_max = !kSum && plan->bigmax_units > 0 && !(plan->disabled_paths & PGX_PATH_MERGED_MAX);
   if (merged_max) {
@@ -623,14 +629,19 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
         const int64_t warps = (F + units - 1) / units;
         const dim3 grid(unsigned(std::min<int64_t>((warps + 7) / 8, std::max<int64_t>(1, int64_t(plan->num_sms) * 16 / mp.nbt))),
                         unsigned(mp.nbt));
-#define PGX_LAUNCH_SMALL(NP, U, UNI)                                                                            \
+#define PGX_LAUNCH_SMALL2(NP, U, UNI, BIN)                                                                     \
   do {                                                                                                          \
     if (delta)                                                                                                  \
-      pgx::k_logical_pull_small<kSum, true, NP, U, UNI><<<grid, pgx::kThreads, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, \
-                                                                                        m_new, a);             \
+      pgx::k_logical_pull_small<kSum, true, NP, U, UNI, BIN><<<grid, pgx::kThreads, 0, st>>>(mp.batch, lg->pull, ev, S, \
+                                                                                             m_old, m_new, a); \
     else                                                                                                        \
-      pgx::k_logical_pull_small<kSum, false, NP, U, UNI><<<grid, pgx::kThreads, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, \
-                                                                                         m_new, a);            \
+      pgx::k_logical_pull_small<kSum, false, NP, U, UNI, BIN><<<grid, pgx::kThreads, 0, st>>>(mp.batch, lg->pull, ev, S, \
+                                                                                              m_old, m_new, a); \
+  } while (0)
+#define PGX_LAUNCH_SMALL(NP, U, UNI)                  \
+  do {                                                \
+    if (lbin) PGX_LAUNCH_SMALL2(NP, U, UNI, true);    \
+    else PGX_LAUNCH_SMALL2(NP, U, UNI, false);        \
   } while (0)
         if (un == 1) PGX_LAUNCH_SMALL(1, 2, true);
         else if (un == 2) PGX_LAUNCH_SMALL(2, 2, true);
@@ -638,32 +649,35 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
         else if (un == 4) PGX_LAUNCH_SMALL(4, 1, true);
         else PGX_LAUNCH_SMALL(4, 1, false);
 #undef PGX_LAUNCH_SMALL
+#undef PGX_LAUNCH_SMALL2
         if ((rc = check_launch(plan, "k_logical_pull_small"))) return rc;
         if (id == plan->dominant) plan->dominant_name = "k_logical_pull_small";
       } else {
-        if (plan->disabled_paths & PGX_PATH_WIDE_SPLIT) {
-          const dim3 grid(unsigned((F + 3) / 4), unsigned(mp.nbt));
-          if (delta)
-            pgx::k_logical_pull_wide<kSum, true><<<grid, 128, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, m_new, a);
-          else
-            pgx::k_logical_pull_wide<kSum, false><<<grid, 128, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, m_new, a);
+        const dim3 grid0(unsigned((F + 3) / 4), unsigned(mp.nbt));
+        // two launches: serial accumulation per factor, then a parent-parallel emit
+        const dim3 grid1(unsigned(std::min<int64_t>(F, 1 << 20)), unsigned(mp.nbt));
+        const int64_t warps2 = (lg->num_parents + pgx::kEmitUnits - 1) / pgx::kEmitUnits;
+        const dim3 grid2(unsigned(std::min<int64_t>((warps2 + 7) / 8, std::max<int64_t>(1, int64_t(plan->num_sms) * 16 / mp.nbt))),
+                         unsigned(mp.nbt));
+        const bool split = !(plan->disabled_paths & PGX_PATH_WIDE_SPLIT);
+#define PGX_LAUNCH_WIDE(DELTA, BIN)                                                                              \
+  do {                                                                                                          \
+    if (!split) {                                                                                               \
+      pgx::k_logical_pull_wide<kSum, DELTA, BIN><<<grid0, 128, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, m_new, a); \
+    } else {                                                                                                    \
+      pgx::k_logical_wide_reduce<kSum, DELTA, BIN><<<grid1, 32, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, m_new, \
+                                                                         plan->ws.agg, a);                     \
+      pgx::k_logical_wide_emit<kSum, DELTA, BIN><<<grid2, pgx::kThreads, 0, st>>>(                              \
+          mp.batch, lg->pull, lg->d_parent_factor, lg->num_parents, ev, S, m_old, m_new, plan->ws.agg, a);      \
+    }                                                                                                           \
+  } while (0)
+        if (delta) {
+          if (lbin) PGX_LAUNCH_WIDE(true, true); else PGX_LAUNCH_WIDE(true, false);
         } else {
-          // two launches: serial accumulation per factor, then a parent-parallel emit
-          const dim3 grid1(unsigned(std::min<int64_t>(F, 1 << 20)), unsigned(mp.nbt));
-          const int64_t warps2 = (lg->num_parents + pgx::kEmitUnits - 1) / pgx::kEmitUnits;
-          const dim3 grid2(unsigned(std::min<int64_t>((warps2 + 7) / 8, std::max<int64_t>(1, int64_t(plan->num_sms) * 16 / mp.nbt))),
-                           unsigned(mp.nbt));
-          if (delta) {
-            pgx::k_logical_wide_reduce<kSum, true><<<grid1, 32, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, m_new, plan->ws.agg, a);
-            pgx::k_logical_wide_emit<kSum, true><<<grid2, pgx::kThreads, 0, st>>>(
-                mp.batch, lg->pull, lg->d_parent_factor, lg->num_parents, ev, S, m_old, m_new, plan->ws.agg, a);
-          } else {
-            pgx::k_logical_wide_reduce<kSum, false><<<grid1, 32, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, m_new, plan->ws.agg, a);
-            pgx::k_logical_wide_emit<kSum, false><<<grid2, pgx::kThreads, 0, st>>>(
-                mp.batch, lg->pull, lg->d_parent_factor, lg->num_parents, ev, S, m_old, m_new, plan->ws.agg, a);
-          }
-          ++plan->launches;
+          if (lbin) PGX_LAUNCH_WIDE(false, true); else PGX_LAUNCH_WIDE(false, false);
         }
+#undef PGX_LAUNCH_WIDE
+        if (split) ++plan->launches;
         if ((rc = check_launch(plan, "k_logical_pull_wide"))) return rc;
         if (id == plan->dominant) plan->dominant_name = "k_logical_pull_wide";
       }
@@ -946,7 +960,11 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       const int64_t es_and = plan->and_f.dev.num_factors + desc->and_factors.num_parents;
       plan->aux_group = es_or <= es_and ? -1 : -2;
       plan->aux_needs_s = es_or <= es_and ? plan->or_f.needs_s : plan->and_f.needs_s;
-      if (cudaStreamCreateWithFlags(&plan->aux, cudaStreamNonBlocking) != cudaSuccess ||
+      // highest priority: the group on the auxiliary stream is the one with long serial chains
+      // (few, long-lived warps), it should get free SM slots before the wide grid beside it
+      int prio_lo = 0, prio_hi = 0;
+      cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+      if (cudaStreamCreateWithPriority(&plan->aux, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
           cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
           cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming) != cudaSuccess)
         return bail(fail(PGX_ERR_CUDA, "creating the auxiliary stream failed"));
@@ -1259,9 +1277,14 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   // Single-pass mode: dense-grid pairwise blocks emit per-tile partial sums of the new
   // messages; needs full warps of samples and potentials shared by the batch.
   const bool fused = !plan->bips.empty() && !plan->exact_order && mp.bx_log == 5 && !lpT;
-  if ((rc = ensure_workspace(plan, batch, evT, lpT, fused))) return rc;
-  Workspace& ws = plan->ws;
   const int64_t Es = plan->num_edge_states, Vs = plan->num_var_states, C = plan->num_potentials;
+  // Logical pull path: full sample tiles, 32-bit offsets inside a tile
+  const bool lpull = plan->logical_pull_ok && mp.bx_log == 5 && !(plan->disabled_paths & PGX_PATH_LOGICAL_PULL) &&
+                     Es < (int64_t(1) << 26) && Vs < (int64_t(1) << 26);
+  // ... with the messages in binary-difference storage (such a graph has only two-state edges)
+  const bool lbin = lpull && !(plan->disabled_paths & PGX_PATH_LOGICAL_BIN) && Es == 2 * plan->num_edges;
+  if ((rc = ensure_workspace(plan, batch, evT, lpT, fused, lbin))) return rc;
+  Workspace& ws = plan->ws;
   if (Es == 0) return PGX_OK;
 
   // ---- inputs -> tile-blocked workspace ----------------------------------------------------
@@ -1284,7 +1307,10 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     cur = ftov_in;
     nxt = ws.mA;
   } else if (ftov_in == nullptr) {
-    PGX_CUDA(cudaMemsetAsync(ws.mA, 0, tiled_floats(mp, Es) * sizeof(float), st));  // NC(0) = 0
+    if (lbin)
+      PGX_CUDA(cudaMemsetAsync(ws.cA, 0, tiled_floats(mp, Es / 2) * sizeof(float), st));
+    else
+      PGX_CUDA(cudaMemsetAsync(ws.mA, 0, tiled_floats(mp, Es) * sizeof(float), st));  // NC(0) = 0
   } else {
     if (single) {
       PGX_CUDA(cudaMemcpyAsync(ws.mA, ftov_in, size_t(Es) * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1299,6 +1325,17 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
           mp, plan->num_edges, Es, plan->d_edge_msg_start, ws.mA);
       if ((rc = check_launch(plan, "k_normalize_edges"))) return rc;
     }
+  }
+  // the two buffers the generic loop below ping-pongs between
+  float* const bufA = lbin ? ws.cA : ws.mA;
+  float* const bufB = lbin ? ws.cB : ws.mB;
+  if (lbin) {
+    if (ftov_in != nullptr) {  // normalised full layout -> one float per edge
+      pgx::k_compress_bin<<<plan->num_sms * 8, pgx::kThreads, 0, st>>>(ws.mA, ws.cA, Es / 2, mp.nbt);
+      if ((rc = check_launch(plan, "k_compress_bin"))) return rc;
+    }
+    cur = ws.cA;
+    nxt = ws.cB;
   }
   if (deltas) PGX_CUDA(cudaMemsetAsync(deltas, 0, size_t(batch) * num_iters * sizeof(float), st));
 
@@ -1321,9 +1358,6 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   // cooperative launch.
   // (Large grids keep the two-pass path: re-deriving S per edge costs 4x the gathers and
   // measured slower than k_var_sums + k_enum_pw2 once the graph no longer fits in cache.)
-  // Logical pull path: full sample tiles, 32-bit offsets inside a tile
-  const bool lpull = plan->logical_pull_ok && mp.bx_log == 5 && !(plan->disabled_paths & PGX_PATH_LOGICAL_PULL) &&
-                     Es < (int64_t(1) << 26) && Vs < (int64_t(1) << 26);
   const cudaStream_t aux = (lpull && plan->aux != nullptr && !(plan->disabled_paths & PGX_PATH_AUX_STREAM)) ? plan->aux : nullptr;
   bool pull = false;
   if (plan->pull_ok && !fused && plan->enum_blocks.size() == 1) {
@@ -1489,9 +1523,14 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     if (lpull) {
       if (plan->hi_len > 0) {
         const int64_t per_tile = std::min<int64_t>(plan->hi_len, (int64_t(1) << 30) / mp.nbt);
-        pgx::k_var_sums_list<<<unsigned(per_tile * mp.nbt), 32, 0, st>>>(mp.batch, mp.nbt, Es, Vs, plan->d_vs_csr,
-                                                                      plan->d_var_edge_msg, plan->d_hi_list, plan->hi_len,
-                                                                      ev, cur, ws.S);
+        if (lbin)
+          pgx::k_var_sums_list_bin<<<unsigned(std::max<int64_t>(per_tile / 2, 1) * mp.nbt), 32, 0, st>>>(
+              mp.batch, mp.nbt, Es / 2, Vs, plan->d_vs_csr, plan->d_var_edge_msg, plan->d_hi_list, plan->hi_len, ev, cur,
+              ws.S);
+        else
+          pgx::k_var_sums_list<<<unsigned(per_tile * mp.nbt), 32, 0, st>>>(mp.batch, mp.nbt, Es, Vs, plan->d_vs_csr,
+                                                                        plan->d_var_edge_msg, plan->d_hi_list, plan->hi_len,
+                                                                        ev, cur, ws.S);
         if ((rc = check_launch(plan, "k_var_sums_list"))) return rc;
       }
     } else if (!fused || it == 0) {
@@ -1509,9 +1548,9 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     const float* c_old = (fused && it > 0) ? ((it & 1) ? ws.cA : ws.cB) : nullptr;
     float* c_new = fused ? ((it & 1) ? ws.cB : ws.cA) : nullptr;
     if (temperature == 0.f)
-      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new);
+      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new, lbin);
     else
-      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new);
+      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new, lbin);
     if (rc) return rc;
     if (aux != nullptr) {
       PGX_CUDA(cudaEventRecord(plan->ev_join, aux));
@@ -1525,10 +1564,14 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
       if ((rc = check_launch(plan, "k_var_reduce"))) return rc;
     }
     // ping-pong between the two workspace buffers; the caller's input is never written
-    nxt = (dst == ws.mA) ? ws.mB : ws.mA;
+    nxt = (dst == bufA) ? bufB : bufA;
     cur = dst;
   }
-  if (!single && !fused) {
+  if (lbin) {
+    dim3 grid((unsigned)((Es / 2 + 31) / 32), (unsigned)((mp.batch + 31) / 32)), block(32, 8);
+    pgx::k_expand_bin<<<grid, block, 0, st>>>(cur, Es / 2, 0, Es / 2, ftov_out, Es, 0, mp);
+    if ((rc = check_launch(plan, "k_expand_bin"))) return rc;
+  } else if (!single && !fused) {
     if ((rc = from_tiles(plan, st, cur, ftov_out, Es, mp))) return rc;
   } else if (!single) {
     // the fused blocks' messages are expanded from the compressed array, the rest comes from

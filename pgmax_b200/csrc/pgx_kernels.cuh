@@ -188,7 +188,7 @@ __global__ void k_expand_bin(const float* __restrict__ src, int64_t c_rows, int6
       const int64_t c = c0 + (e >> 1);
       if (c < count) {
         const float x = tile[e >> 1][r];
-        dst[int64_t(b) * N + first_msg + 2 * c0 + e] = (e & 1) ? fminf(x, 0.f) : fminf(-x, 0.f);
+        dst[int64_t(b) * N + first_msg + 2 * c0 + e] = (x != x) ? kMsgNegInf : ((e & 1) ? fminf(x, 0.f) : fminf(-x, 0.f));
       }
     }
   }
@@ -357,6 +357,65 @@ k_var_sums_list(int batch, int nbt, int64_t Es, int64_t Vs, const int2* __restri
         if (k + j < k1) acc += x[j];
     }
     if (live) SL[uint32_t(v) << 5] = acc;
+  }
+}
+
+// K1-list on binary-difference storage: `list` holds the var-states of the listed variables,
+// state 0 and state 1 of a variable adjacent; a warp = the 32 samples of ONE variable and
+// accumulates both sums in one walk (each stored difference is read once).
+__global__ void __launch_bounds__(32)
+k_var_sums_list_bin(int batch, int nbt, int64_t E, int64_t Vs, const int2* __restrict__ vs_csr,
+                    const int32_t* __restrict__ var_edge_msg, const int32_t* __restrict__ list, int64_t list_len,
+                    View ev, const float* __restrict__ c, float* __restrict__ S) {
+  const int lane = threadIdx.x & 31;
+  const int tile_i = int(blockIdx.x % unsigned(nbt));
+  const bool live = tile_i * 32 + lane < batch;
+  const int ll = live ? lane : 0;
+  const size_t tile = tile_i;
+  const float* cL = c + tile * size_t(E) * 32 + ll;
+  float* SL = S + tile * size_t(Vs) * 32 + ll;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + ll : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const int64_t gwarp = blockIdx.x / unsigned(nbt);
+  const int64_t nwarps = gridDim.x / unsigned(nbt);
+  for (int64_t i = gwarp; 2 * i < list_len; i += nwarps) {
+    const int v = list[2 * i];  // var-state of state 0; state 1 is v + 1
+    const int2 r = vs_csr[v];
+    const int k1 = r.x + (r.y >> kVsStateBits);
+    float acc0 = evq[uint32_t(v) << esh], acc1 = evq[uint32_t(v + 1) << esh];
+    int mine = r.x + lane < k1 ? var_edge_msg[r.x + lane] : 0;
+    for (int k = r.x; k < k1; k += kVsListChunk) {
+      const int held = mine;
+      if (k + kVsListChunk + lane < k1) mine = var_edge_msg[k + kVsListChunk + lane];
+      float x[kVsListChunk];
+#pragma unroll
+      for (int j = 0; j < kVsListChunk; ++j) {
+        const int idx = __shfl_sync(0xffffffffu, held, j);
+        x[j] = (k + j < k1) ? cL[(uint32_t(idx) >> 1) << 5] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kVsListChunk; ++j)
+        if (k + j < k1) {
+          const bool fl = x[j] != x[j];  // both states at the floor (load_msg)
+          acc0 += fl ? kMsgNegInf : fminf(-x[j], 0.f);
+          acc1 += fl ? kMsgNegInf : fminf(x[j], 0.f);
+        }
+    }
+    if (live) {
+      SL[uint32_t(v) << 5] = acc0;
+      SL[uint32_t(v + 1) << 5] = acc1;
+    }
+  }
+}
+
+// Full tile-blocked messages (normalised, every edge two states) -> binary-difference storage.
+__global__ void __launch_bounds__(kThreads)
+k_compress_bin(const float* __restrict__ m, float* __restrict__ c, int64_t E, int nbt) {
+  const int64_t total = E * 32 * nbt;  // one float per (tile, edge, sample)
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t row = i >> 5;  // tile * E + e
+    const int l = int(i & 31);
+    c[i] = m[(2 * row + 1) * 32 + l] - m[(2 * row) * 32 + l];
   }
 }
 
@@ -2184,29 +2243,64 @@ struct EdgeIn {
   int32_t kind;    // 0: sums from S; 1: no other edge; 2: other edge first; 3: own edge first
 };
 
-// Issues the (up to) 6 loads of an edge; no data-dependent branch.
+// kBin: the message arrays are in binary-difference storage (one float x = n1 - n0 per edge,
+// every edge of the graph has two states, edge e holds message rows 2e, 2e + 1; see
+// bin_expand): row of an edge = msg >> 1, and (pointed, relevant) = (state 0, state 1) for
+// off = +1, (state 1, state 0) for off = -1.
+template <bool kBin>
+__device__ __forceinline__ size_t msg_rows(const RunArgs& a) { return kBin ? size_t(a.Es) >> 1 : size_t(a.Es); }
+
+// Sum-product closed forms can return an infinite difference (an empty logminusexp); the
+// update then leaves BOTH states of the edge at the clip value -1e32 (inf - inf = NaN, and
+// fmaxf(NaN, -1e32) = -1e32), the one normalised pair whose maximum is not 0.  The stored
+// difference encodes it as NaN (kFloor variants; max-product never produces it).
+// load_msg only LOADS (kBin: the raw difference goes to m_p); expand_msg, called on the
+// consumer side (edge_q), turns it into the two states - no arithmetic sits between the loads
+// of a batch of edges, so they all stay in flight together.
+template <bool kBin, bool kFloor>
+__device__ __forceinline__ void expand_msg(int off, float& m_p, float& m_r) {
+  if (!kBin) return;
+  const float x = m_p;
+  const float xs = off > 0 ? x : -x;  // relevant - pointed
+  m_p = fminf(-xs, 0.f);
+  m_r = fminf(xs, 0.f);
+  if (kFloor && x != x) m_p = m_r = kMsgNegInf;
+}
+
+template <bool kBin, bool kFloor>
+__device__ __forceinline__ void load_msg(const float* __restrict__ mo, int32_t msg, int off, float& m_p, float& m_r) {
+  if (kBin) {
+    m_p = mo[(uint32_t(msg) >> 1) << 5];
+    m_r = 0.f;
+  } else {
+    m_p = mo[uint32_t(msg) << 5];
+    m_r = mo[uint32_t(msg + off) << 5];
+  }
+}
+
+// Issues the (up to) 6 loads of an edge (4 in binary-difference storage); no data-dependent branch.
+template <bool kBin, bool kFloor>
 __device__ __forceinline__ EdgeIn load_edge(const EdgeW& e, int off, const float* __restrict__ mo,
                                             const float* __restrict__ evq, int esh,
                                             const float* __restrict__ SL) {
   EdgeIn r;
   r.msg = e.msg;
   r.kind = e.other == -2 ? 0 : (e.other == -1 ? 1 : (e.other < e.msg ? 2 : 3));
-  r.m_p = mo[uint32_t(e.msg) << 5];
-  r.m_r = mo[uint32_t(e.msg + off) << 5];
+  load_msg<kBin, kFloor>(mo, e.msg, off, r.m_p, r.m_r);
   const bool from_s = e.other == -2;
   r.a_p = *(from_s ? SL + (uint32_t(e.vs) << 5) : evq + (uint32_t(e.vs) << esh));
   r.a_r = *(from_s ? SL + (uint32_t(e.vs + off) << 5) : evq + (uint32_t(e.vs + off) << esh));
   r.o_p = 0.f;
   r.o_r = 0.f;
-  if (e.other >= 0) {
-    r.o_p = mo[uint32_t(e.other) << 5];
-    r.o_r = mo[uint32_t(e.other + off) << 5];
-  }
+  if (e.other >= 0) load_msg<kBin, kFloor>(mo, e.other, off, r.o_p, r.o_r);
   return r;
 }
 // variable -> factor messages (pointed state, relevant state): S - m with S accumulated from
 // the evidence in ascending message index
-__device__ __forceinline__ void edge_q(const EdgeIn& r, float& q_p, float& q_r) {
+template <bool kBin, bool kFloor>
+__device__ __forceinline__ void edge_q(EdgeIn& r, int off, float& q_p, float& q_r) {
+  expand_msg<kBin, kFloor>(off, r.m_p, r.m_r);
+  if (r.kind >= 2) expand_msg<kBin, kFloor>(off, r.o_p, r.o_r);
   float s_p = r.a_p, s_r = r.a_r;
   if (r.kind != 0) {
     const bool other_first = r.kind == 2;
@@ -2223,22 +2317,28 @@ __device__ __forceinline__ void edge_q(const EdgeIn& r, float& q_p, float& q_r) 
 
 // new message (x at the relevant state, 0 at the pointed state): damping, normalisation,
 // clip, store; returns max|new - old| when kDelta
-template <bool kDelta>
+template <bool kDelta, bool kBin, bool kFloor>
 __device__ __forceinline__ float store_edge(float* __restrict__ mn, int off, const EdgeIn& r, float x, float d,
                                             float one_minus_d) {
   float n_p = damp(r.m_p, 0.f, d, one_minus_d), n_r = damp(r.m_r, x, d, one_minus_d);
   const float mx = fmaxf(n_p, n_r);
   n_p = fmaxf(n_p - mx, kMsgNegInf);
   n_r = fmaxf(n_r - mx, kMsgNegInf);
-  mn[uint32_t(r.msg) << 5] = n_p;
-  mn[uint32_t(r.msg + off) << 5] = n_r;
+  if (kBin) {  // one of n_p, n_r is the exact zero: the difference loses nothing
+    float xd = off > 0 ? n_r - n_p : n_p - n_r;
+    if (kFloor && fmaxf(n_p, n_r) < 0.f) xd = __int_as_float(0x7fc00000);  // both states at the floor
+    mn[(uint32_t(r.msg) >> 1) << 5] = xd;
+  } else {
+    mn[uint32_t(r.msg) << 5] = n_p;
+    mn[uint32_t(r.msg + off) << 5] = n_r;
+  }
   return kDelta ? fmaxf(fabsf(n_p - r.m_p), fabsf(n_r - r.m_r)) : 0.f;
 }
 
 // Factors with <= NP parents (AND factors: NP = 2), everything in registers, U factors per
 // warp iteration (their loads are all in flight together).  kUniform: every factor has
 // exactly NP parents.
-template <bool kSumProduct, bool kDelta, int NP, int U, bool kUniform>
+template <bool kSumProduct, bool kDelta, int NP, int U, bool kUniform, bool kBin>
 __global__ void __launch_bounds__(kThreads)
 k_logical_pull_small(int batch, LogicalPullDev w, View ev, const float* __restrict__ S,
                      const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
@@ -2246,8 +2346,8 @@ k_logical_pull_small(int batch, LogicalPullDev w, View ev, const float* __restri
   const int b = blockIdx.y * 32 + lane;
   if (b >= batch) return;
   const size_t tile = blockIdx.y;
-  const float* mo = m_old + tile * size_t(a.Es) * 32 + lane;
-  float* mn = m_new + tile * size_t(a.Es) * 32 + lane;
+  const float* mo = m_old + tile * msg_rows<kBin>(a) * 32 + lane;
+  float* mn = m_new + tile * msg_rows<kBin>(a) * 32 + lane;
   const float* SL = S + tile * size_t(a.Vs) * 32 + lane;
   const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + lane : ev.p;
   const int esh = ev.kind == 1 ? 5 : 0;
@@ -2268,32 +2368,32 @@ k_logical_pull_small(int batch, LogicalPullDev w, View ev, const float* __restri
       if (f < w.num_factors) {
         if (kUniform) { p0[u] = f * NP; np[u] = NP; }
         else { p0[u] = w.parent_ptr[f]; np[u] = int(w.parent_ptr[f + 1] - p0[u]); }
-        ce[u] = load_edge(w.children[f], off, mo, evq, esh, SL);
+        ce[u] = load_edge<kBin, kSumProduct>(w.children[f], off, mo, evq, esh, SL);
 #pragma unroll
         for (int j = 0; j < NP; ++j)
-          if (kUniform || j < np[u]) pe[u][j] = load_edge(w.parents[p0[u] + j], off, mo, evq, esh, SL);
+          if (kUniform || j < np[u]) pe[u][j] = load_edge<kBin, kSumProduct>(w.parents[p0[u] + j], off, mo, evq, esh, SL);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (f0 + u * nwarps < w.num_factors) {
         float c_p, c_r, q_p[NP], q_r[NP];
-        edge_q(ce[u], c_p, c_r);
+        edge_q<kBin, kSumProduct>(ce[u], off, c_p, c_r);
         LogicalAcc A;
         A.istar = p0[u];
 #pragma unroll
         for (int j = 0; j < NP; ++j)
           if (kUniform || j < np[u]) {
-            edge_q(pe[u][j], q_p[j], q_r[j]);
+            edge_q<kBin, kSumProduct>(pe[u][j], off, q_p[j], q_r[j]);
             A.add<kSumProduct>(p0[u] + j, q_r[j], q_p[j], T);
           }
 #pragma unroll
         for (int j = 0; j < NP; ++j)
           if (kUniform || j < np[u]) {
             const float x = A.parent_out<kSumProduct>(p0[u] + j, q_r[j], q_p[j], c_r, c_p, T, np[u] == 1);
-            dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, pe[u][j], x, d, one_minus_d));
+            dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, pe[u][j], x, d, one_minus_d));
           }
-        dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, ce[u], A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
+        dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, ce[u], A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
       }
     }
   }
@@ -2304,7 +2404,7 @@ k_logical_pull_small(int batch, LogicalPullDev w, View ev, const float* __restri
 // wiring of 32 parents is fetched with ONE coalesced load (lane j holds parent i + j) and
 // handed out by shuffles; the parents' loads are issued kParentChunk at a time.  All lanes
 // stay alive for the shuffles; lanes beyond the batch read a valid sample and store nothing.
-template <bool kSumProduct, bool kDelta>
+template <bool kSumProduct, bool kDelta, bool kBin>
 __global__ void __launch_bounds__(128)
 k_logical_pull_wide(int batch, LogicalPullDev w, View ev, const float* __restrict__ S,
                     const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
@@ -2313,8 +2413,8 @@ k_logical_pull_wide(int batch, LogicalPullDev w, View ev, const float* __restric
   const bool live = b_raw < batch;
   const int ll = live ? lane : 0;  // dead lanes shadow sample 0 of the tile (always valid)
   const size_t tile = blockIdx.y;
-  const float* mo = m_old + tile * size_t(a.Es) * 32 + ll;
-  float* mn = m_new + tile * size_t(a.Es) * 32 + ll;
+  const float* mo = m_old + tile * msg_rows<kBin>(a) * 32 + ll;
+  float* mn = m_new + tile * msg_rows<kBin>(a) * 32 + ll;
   const float* SL = S + tile * size_t(a.Vs) * 32 + ll;
   const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + ll : ev.p;
   const int esh = ev.kind == 1 ? 5 : 0;
@@ -2327,14 +2427,14 @@ k_logical_pull_wide(int batch, LogicalPullDev w, View ev, const float* __restric
     int64_t p0, p1;
     if (w.uniform > 0) { p0 = f * w.uniform; p1 = p0 + w.uniform; }
     else { p0 = w.parent_ptr[f]; p1 = w.parent_ptr[f + 1]; }
-    const EdgeIn ce = load_edge(w.children[f], off, mo, evq, esh, SL);
+    EdgeIn ce = load_edge<kBin, kSumProduct>(w.children[f], off, mo, evq, esh, SL);
     LogicalAcc A;
     A.istar = p0;
     const bool single = (p1 - p0) == 1;
     float c_p = 0.f, c_r = 0.f;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-      if (pass == 1) edge_q(ce, c_p, c_r);
+      if (pass == 1) edge_q<kBin, kSumProduct>(ce, off, c_p, c_r);
       EdgeW mine = (p0 + lane < p1) ? w.parents[p0 + lane] : EdgeW{0, 0, -1, 0};
       for (int64_t i32 = p0; i32 < p1; i32 += 32) {
         const EdgeW held = mine;
@@ -2349,26 +2449,26 @@ k_logical_pull_wide(int batch, LogicalPullDev w, View ev, const float* __restric
             e.msg = __shfl_sync(0xffffffffu, held.msg, (c0 + j) & 31);
             e.vs = __shfl_sync(0xffffffffu, held.vs, (c0 + j) & 31);
             e.other = __shfl_sync(0xffffffffu, held.other, (c0 + j) & 31);
-            if (c0 + j < n32) r[j] = load_edge(e, off, mo, evq, esh, SL);
+            if (c0 + j < n32) r[j] = load_edge<kBin, kSumProduct>(e, off, mo, evq, esh, SL);
           }
 #pragma unroll
           for (int j = 0; j < kParentChunk; ++j)
             if (c0 + j < n32) {
               float q_p, q_r;
-              edge_q(r[j], q_p, q_r);
+              edge_q<kBin, kSumProduct>(r[j], off, q_p, q_r);
               const int64_t i = i32 + c0 + j;
               if (pass == 0) {
                 A.add<kSumProduct>(i, q_r, q_p, T);
               } else {
                 const float x = A.parent_out<kSumProduct>(i, q_r, q_p, c_r, c_p, T, single);
-                if (live) dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, r[j], x, d, one_minus_d));
+                if (live) dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, r[j], x, d, one_minus_d));
               }
             }
         }
       }
     }
     if (live)
-      dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
+      dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
   }
   if (kDelta && live) publish_delta(a.deltas, int64_t(b_raw) * a.delta_stride + a.delta_off, dmax);
 }
@@ -2383,8 +2483,8 @@ k_logical_pull_wide(int batch, LogicalPullDev w, View ev, const float* __restric
 // Same arithmetic as k_logical_pull_wide (LogicalAcc), hence bit-identical.
 constexpr int kAggRows = 8;  // acc, Sb, d1, d2, istar - p0 (int bits), c_p, c_r, unused
 
-template <bool kSumProduct, bool kDelta>
-__global__ void __launch_bounds__(32, 16)  // one warp per CTA: a serial chain holds only its own warp
+template <bool kSumProduct, bool kDelta, bool kBin>
+__global__ void __launch_bounds__(32, 22)  // one warp per CTA: a serial chain holds only its own warp
 k_logical_wide_reduce(int batch, LogicalPullDev w, View ev, const float* __restrict__ S,
                       const float* __restrict__ m_old, float* __restrict__ m_new, float* __restrict__ agg,
                       RunArgs a) {
@@ -2393,8 +2493,8 @@ k_logical_wide_reduce(int batch, LogicalPullDev w, View ev, const float* __restr
   const bool live = b_raw < batch;
   const int ll = live ? lane : 0;
   const size_t tile = blockIdx.y;
-  const float* mo = m_old + tile * size_t(a.Es) * 32 + ll;
-  float* mn = m_new + tile * size_t(a.Es) * 32 + ll;
+  const float* mo = m_old + tile * msg_rows<kBin>(a) * 32 + ll;
+  float* mn = m_new + tile * msg_rows<kBin>(a) * 32 + ll;
   const float* SL = S + tile * size_t(a.Vs) * 32 + ll;
   const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + ll : ev.p;
   const int esh = ev.kind == 1 ? 5 : 0;
@@ -2408,7 +2508,7 @@ k_logical_wide_reduce(int batch, LogicalPullDev w, View ev, const float* __restr
     int64_t p0, p1;
     if (w.uniform > 0) { p0 = f * w.uniform; p1 = p0 + w.uniform; }
     else { p0 = w.parent_ptr[f]; p1 = w.parent_ptr[f + 1]; }
-    const EdgeIn ce = load_edge(w.children[f], off, mo, evq, esh, SL);
+    EdgeIn ce = load_edge<kBin, kSumProduct>(w.children[f], off, mo, evq, esh, SL);
     LogicalAcc A;
     A.istar = p0;
     EdgeW mine = (p0 + lane < p1) ? w.parents[p0 + lane] : EdgeW{0, 0, -1, 0};
@@ -2425,24 +2525,24 @@ k_logical_wide_reduce(int batch, LogicalPullDev w, View ev, const float* __restr
           e.msg = __shfl_sync(0xffffffffu, held.msg, (c0 + j) & 31);
           e.vs = __shfl_sync(0xffffffffu, held.vs, (c0 + j) & 31);
           e.other = __shfl_sync(0xffffffffu, held.other, (c0 + j) & 31);
-          if (c0 + j < n32) r[j] = load_edge(e, off, mo, evq, esh, SL);
+          if (c0 + j < n32) r[j] = load_edge<kBin, kSumProduct>(e, off, mo, evq, esh, SL);
         }
 #pragma unroll
         for (int j = 0; j < kParentChunk; ++j)
           if (c0 + j < n32) {
             float q_p, q_r;
-            edge_q(r[j], q_p, q_r);
+            edge_q<kBin, kSumProduct>(r[j], off, q_p, q_r);
             A.add<kSumProduct>(i32 + c0 + j, q_r, q_p, T);
           }
       }
     }
     float c_p, c_r;
-    edge_q(ce, c_p, c_r);
+    edge_q<kBin, kSumProduct>(ce, off, c_p, c_r);
     if (live) {
       float* g = aggL + size_t(f) * kAggRows * 32;
       g[0] = A.acc; g[32] = A.Sb; g[64] = A.d1; g[96] = A.d2;
       g[128] = __int_as_float(int(A.istar - p0)); g[160] = c_p; g[192] = c_r;
-      dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
+      dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
     }
   }
   if (kDelta && live) publish_delta(a.deltas, int64_t(b_raw) * a.delta_stride + a.delta_off, dmax);
@@ -2451,7 +2551,7 @@ k_logical_wide_reduce(int batch, LogicalPullDev w, View ev, const float* __restr
 // parent_factor[i] = factor of parent i (ascending).  kEmitUnits parents per warp iteration.
 constexpr int kEmitUnits = 2;
 
-template <bool kSumProduct, bool kDelta>
+template <bool kSumProduct, bool kDelta, bool kBin>
 __global__ void __launch_bounds__(kThreads)
 k_logical_wide_emit(int batch, LogicalPullDev w, const int32_t* __restrict__ parent_factor, int64_t num_parents,
                     View ev, const float* __restrict__ S, const float* __restrict__ m_old,
@@ -2460,8 +2560,8 @@ k_logical_wide_emit(int batch, LogicalPullDev w, const int32_t* __restrict__ par
   const int b = blockIdx.y * 32 + lane;
   if (b >= batch) return;
   const size_t tile = blockIdx.y;
-  const float* mo = m_old + tile * size_t(a.Es) * 32 + lane;
-  float* mn = m_new + tile * size_t(a.Es) * 32 + lane;
+  const float* mo = m_old + tile * msg_rows<kBin>(a) * 32 + lane;
+  float* mn = m_new + tile * msg_rows<kBin>(a) * 32 + lane;
   const float* SL = S + tile * size_t(a.Vs) * 32 + lane;
   const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + lane : ev.p;
   const int esh = ev.kind == 1 ? 5 : 0;
@@ -2482,7 +2582,7 @@ k_logical_wide_emit(int batch, LogicalPullDev w, const int32_t* __restrict__ par
         const int f = parent_factor[i];
         if (w.uniform > 0) { p0[u] = int64_t(f) * w.uniform; p1[u] = p0[u] + w.uniform; }
         else { p0[u] = w.parent_ptr[f]; p1[u] = w.parent_ptr[f + 1]; }
-        r[u] = load_edge(w.parents[i], off, mo, evq, esh, SL);
+        r[u] = load_edge<kBin, kSumProduct>(w.parents[i], off, mo, evq, esh, SL);
         const float* gp = aggL + size_t(f) * kAggRows * 32;
 #pragma unroll
         for (int k = 0; k < 7; ++k) g[u][k] = gp[k * 32];
@@ -2496,9 +2596,9 @@ k_logical_wide_emit(int batch, LogicalPullDev w, const int32_t* __restrict__ par
         A.acc = g[u][0]; A.Sb = g[u][1]; A.d1 = g[u][2]; A.d2 = g[u][3];
         A.istar = p0[u] + __float_as_int(g[u][4]);
         float q_p, q_r;
-        edge_q(r[u], q_p, q_r);
+        edge_q<kBin, kSumProduct>(r[u], off, q_p, q_r);
         const float x = A.parent_out<kSumProduct>(i, q_r, q_p, g[u][6], g[u][5], T, p1[u] - p0[u] == 1);
-        dmax = fmaxf(dmax, store_edge<kDelta>(mn, off, r[u], x, d, one_minus_d));
+        dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, r[u], x, d, one_minus_d));
       }
     }
   }

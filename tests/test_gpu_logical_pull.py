@@ -97,6 +97,10 @@ def test_pull_equals_two_pass_and_oracle(seed, temperature, batch):
   np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
   np.testing.assert_array_equal(got_d, ref_d)
   assert kinds > 0
+  # the pull kernels on the reference layout (two floats per edge) instead of binary-difference storage
+  full, full_d = _run(bp, arrays, 6, temperature, plan.PATH_LOGICAL_BIN)
+  np.testing.assert_array_equal(got.ftov_msgs, full.ftov_msgs)
+  np.testing.assert_array_equal(got_d, full_d)
   # single-launch wide kernel, everything on one stream
   one, one_d = _run(bp, arrays, 6, temperature, plan.PATH_WIDE_SPLIT | plan.PATH_AUX_STREAM)
   np.testing.assert_array_equal(got.ftov_msgs, one.ftov_msgs)
@@ -127,6 +131,9 @@ def test_pull_deconvolution_batch_40(temperature):
   ref, ref_d = _run(bp, arrays, 12, temperature, plan.PATH_LOGICAL_PULL)
   np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
   np.testing.assert_array_equal(got_d, ref_d)
+  full, full_d = _run(bp, arrays, 12, temperature, plan.PATH_LOGICAL_BIN)
+  np.testing.assert_array_equal(got.ftov_msgs, full.ftov_msgs)
+  np.testing.assert_array_equal(got_d, full_d)
   graph = bp_oracle.graph_from_context(bp.context)
   if temperature == 0.0:
     want, _ = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence,
