@@ -103,6 +103,7 @@ struct Workspace {
   int64_t batch = 0;
   float *mA = nullptr, *mB = nullptr, *S = nullptr, *evT = nullptr, *lpT = nullptr, *part = nullptr;
   float *cA = nullptr, *cB = nullptr;  // compressed (one float per edge) messages of the fused blocks
+  float* row = nullptr;                // one normalised [Es] message vector (initial messages shared by the batch)
   float* agg = nullptr;  // per-factor aggregates of the two-launch wide logical update
   // staging for pgx_infer_host
   float *h_lp = nullptr, *h_ev = nullptr, *h_msgs_in = nullptr, *h_msgs_out = nullptr,
@@ -186,7 +187,7 @@ void free_dev(void* p) {
 
 void free_workspace(Workspace& ws) {
   free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT); free_dev(ws.part);
-  free_dev(ws.agg); free_dev(ws.cA); free_dev(ws.cB);
+  free_dev(ws.agg); free_dev(ws.cA); free_dev(ws.cB); free_dev(ws.row);
   free_dev(ws.h_lp); free_dev(ws.h_ev); free_dev(ws.h_msgs_in); free_dev(ws.h_msgs_out);
   free_dev(ws.h_marg); free_dev(ws.h_deltas); free_dev(ws.h_map); free_dev(ws.h_ties);
   ws = Workspace{};
@@ -436,8 +437,8 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
   const pgx::BatchMap mp = make_map(batch);
   if (ws.batch != batch) {
     free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT); free_dev(ws.part);
-    free_dev(ws.agg); free_dev(ws.cA); free_dev(ws.cB);
-    ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = ws.part = ws.agg = ws.cA = ws.cB = nullptr;
+    free_dev(ws.agg); free_dev(ws.cA); free_dev(ws.cB); free_dev(ws.row);
+    ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = ws.part = ws.agg = ws.cA = ws.cB = ws.row = nullptr;
     ws.batch = batch;
     const size_t nm = tiled_floats(mp, plan->num_edge_states) * sizeof(float);
     const size_t nv = tiled_floats(mp, plan->num_var_states) * sizeof(float);
@@ -457,6 +458,7 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.part), tiled_floats(mp, plan->part_rows) * sizeof(float)));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cA), tiled_floats(mp, plan->c_rows) * sizeof(float)));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cB), tiled_floats(mp, plan->c_rows) * sizeof(float)));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.row), size_t(plan->num_edge_states) * sizeof(float)));
   }
   if (need_lbin && ws.cA == nullptr) {
     const size_t nc = tiled_floats(mp, plan->num_edge_states / 2) * sizeof(float);
@@ -493,6 +495,14 @@ int from_tiles(pgx_plan* plan, cudaStream_t st, const float* src, float* dst, in
   dim3 grid((unsigned)((n_end - n_begin + 31) / 32), (unsigned)((mp.batch + 31) / 32)), block(32, 8);
   pgx::k_from_tiles<<<grid, block, 0, st>>>(src, dst, n, n_begin, n_end, mp);
   return check_launch(plan, "k_from_tiles");
+}
+
+// The fused blocks in ascending message order.
+std::vector<const BipPlan*> bips_by_msg(const pgx_plan* plan) {
+  std::vector<const BipPlan*> order;
+  for (const BipPlan& bp : plan->bips) order.push_back(&bp);
+  std::sort(order.begin(), order.end(), [](const BipPlan* x, const BipPlan* y) { return x->dev.first_msg < y->dev.first_msg; });
+  return order;
 }
 
 // Records a profiling event if `id` is the plan's dominant launch.
@@ -1303,7 +1313,40 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
                         ftov_in != ftov_out;
   const float* cur = ws.mA;
   float* nxt = ws.mB;
-  if (in_place) {
+  // Single-pass mode with initial messages shared by the batch (or absent): ONE [Es] vector is
+  // normalised; the fused blocks' part goes straight to binary-difference storage, only the
+  // other edges' rows are broadcast, and the first variable sums read the shared vector.
+  const bool shared_init = fused && !(ftov_in != nullptr && msgs_batched);
+  if (shared_init) {
+    if (ftov_in == nullptr) {
+      PGX_CUDA(cudaMemsetAsync(ws.row, 0, size_t(Es) * sizeof(float), st));
+    } else {
+      PGX_CUDA(cudaMemcpyAsync(ws.row, ftov_in, size_t(Es) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if ((flags & PGX_RUN_INPUT_NORMALIZED) == 0) {
+        const pgx::BatchMap mp1 = make_map(1);
+        pgx::k_normalize_edges<<<grid_for(plan, mp1, plan->num_edges), pgx::kThreads, 0, st>>>(
+            mp1, plan->num_edges, Es, plan->d_edge_msg_start, ws.row);
+        if ((rc = check_launch(plan, "k_normalize_edges"))) return rc;
+      }
+    }
+    int64_t done = 0;
+    for (const BipPlan* bpp : bips_by_msg(plan)) {
+      const pgx::BipDev& g = bpp->dev;
+      const int64_t count = 2 * int64_t(g.I) * g.J;
+      if (g.first_msg > done) {
+        pgx::k_broadcast_rows_range<<<plan->num_sms * 4, pgx::kThreads, 0, st>>>(ws.row, ws.mA, Es, done, g.first_msg, mp);
+        if ((rc = check_launch(plan, "k_broadcast_rows_range"))) return rc;
+      }
+      pgx::k_broadcast_bin<<<plan->num_sms * 8, pgx::kThreads, 0, st>>>(ws.row, g.first_msg, ws.cB, plan->c_rows, g.first_cmsg,
+                                                                   count, mp.nbt);
+      if ((rc = check_launch(plan, "k_broadcast_bin"))) return rc;
+      done = g.first_msg + 2 * count;
+    }
+    if (Es > done) {
+      pgx::k_broadcast_rows_range<<<plan->num_sms * 4, pgx::kThreads, 0, st>>>(ws.row, ws.mA, Es, done, Es, mp);
+      if ((rc = check_launch(plan, "k_broadcast_rows_range"))) return rc;
+    }
+  } else if (in_place) {
     cur = ftov_in;
     nxt = ws.mA;
   } else if (ftov_in == nullptr) {
@@ -1535,7 +1578,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
       }
     } else if (!fused || it == 0) {
       pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(
-          mp, Vs, Es, plan->d_vs_csr, plan->d_var_edge_msg, ev, cur, ws.S);
+          mp, Vs, Es, plan->d_vs_csr, plan->d_var_edge_msg, ev, shared_init ? ws.row : cur, ws.S, shared_init ? 1 : 0);
       if ((rc = check_launch(plan, "k_var_sums"))) return rc;
     }
     if (aux != nullptr && plan->aux_needs_s) {
@@ -1545,7 +1588,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     // With one sample the last iteration writes straight into the caller's buffer.
     float* dst = (single && it == num_iters - 1) ? ftov_out : nxt;
     // fused blocks keep their messages compressed (ws.cA / ws.cB) after the first iteration
-    const float* c_old = (fused && it > 0) ? ((it & 1) ? ws.cA : ws.cB) : nullptr;
+    const float* c_old = (fused && (it > 0 || shared_init)) ? ((it & 1) ? ws.cA : ws.cB) : nullptr;
     float* c_new = fused ? ((it & 1) ? ws.cB : ws.cA) : nullptr;
     if (temperature == 0.f)
       rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new, lbin);
@@ -1578,10 +1621,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     // the full-layout buffer (message ranges of the blocks are disjoint and ascending)
     const float* c_fin = ((num_iters - 1) & 1) ? ws.cB : ws.cA;
     int64_t done = 0;
-    std::vector<const BipPlan*> order;
-    for (const BipPlan& bp : plan->bips) order.push_back(&bp);
-    std::sort(order.begin(), order.end(), [](const BipPlan* x, const BipPlan* y) { return x->dev.first_msg < y->dev.first_msg; });
-    for (const BipPlan* bpp : order) {
+    for (const BipPlan* bpp : bips_by_msg(plan)) {
       const BipPlan& bp = *bpp;
       const int64_t count = 2 * int64_t(bp.dev.I) * bp.dev.J;
       if ((rc = from_tiles(plan, st, cur, ftov_out, Es, mp, done, bp.dev.first_msg))) return rc;

@@ -204,6 +204,31 @@ __global__ void k_broadcast_rows(const float* __restrict__ src, float* __restric
     dst[i] = src[(i % per_tile) >> mp.bx_log];
 }
 
+// Rows [n_begin, n_end) only.
+__global__ void k_broadcast_rows_range(const float* __restrict__ src, float* __restrict__ dst, int64_t N,
+                                       int64_t n_begin, int64_t n_end, BatchMap mp) {
+  const int64_t per_tile = (n_end - n_begin) << mp.bx_log;
+  const int64_t total = per_tile * mp.nbt;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t tile = i / per_tile, r = i - tile * per_tile;
+    const int64_t n = n_begin + (r >> mp.bx_log);
+    dst[((tile * N + n) << mp.bx_log) + (r & ((1 << mp.bx_log) - 1))] = src[n];
+  }
+}
+
+// A shared, normalised [N] message vector -> binary-difference storage of every sample:
+// compressed rows [c_begin, c_begin + count) <- src[first_msg + 2c + 1] - src[first_msg + 2c].
+__global__ void k_broadcast_bin(const float* __restrict__ src, int64_t first_msg, float* __restrict__ dst,
+                                int64_t c_rows, int64_t c_begin, int64_t count, int nbt) {
+  const int64_t per_tile = count << 5;
+  const int64_t total = per_tile * nbt;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t tile = i / per_tile, r = i - tile * per_tile;
+    const int64_t c = r >> 5;
+    dst[((tile * c_rows + c_begin + c) << 5) + (r & 31)] = src[first_msg + 2 * c + 1] - src[first_msg + 2 * c];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // normalize_and_clip_msgs applied to the INPUT messages (pgmax/infer/bp.py:92-96,
 // 249-259): per edge subtract the max over its states, clip below at -1e32.
@@ -237,7 +262,8 @@ constexpr int kVsLowDeg = 4;   // ... when each has at most this many incident e
 __global__ void __launch_bounds__(kThreads)
 k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int2* __restrict__ vs_csr,
            const int32_t* __restrict__ var_edge_msg, View ev, const float* __restrict__ m,
-           float* __restrict__ S) {
+           float* __restrict__ S, int m_shared = 0) {
+  // m_shared: `m` is ONE [Es] vector shared by every sample (initial messages not batched)
   // vs_csr[v] = (CSR begin, degree << kVsStateBits | state offset within the variable): one
   // 8-byte index load per var-state instead of the chain var-state -> variable -> CSR row.  A thread takes
   // kVsUnits var-states per iteration: their rows are loaded together, and when all of them
@@ -246,7 +272,8 @@ k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int2* __restri
   UnitLoop L = unit_loop(mp, num_var_states);
   if (!L.b_ok) return;
   const LaneView evL = lane_view(ev, mp, L.b);
-  const float* mL = m + lane_off(mp, Es, L.b);
+  const float* mL = m_shared ? m : m + lane_off(mp, Es, L.b);
+  const int msh = m_shared ? 0 : mp.bx_log;
   float* SL = S + lane_off(mp, num_var_states, L.b);
   const int sh = mp.bx_log;
   for (int64_t v0 = L.u; v0 < L.u_end; v0 += kVsUnits * L.step) {
@@ -267,7 +294,7 @@ k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int2* __restri
         acc[u] = v < L.u_end ? evL.at(v) : 0.f;
 #pragma unroll
         for (int j = 0; j < kVsLowDeg; ++j)
-          x[u][j] = (row[u].x + j < row[u].y) ? mL[(int64_t(var_edge_msg[row[u].x + j]) + row[u].z) << sh] : 0.f;
+          x[u][j] = (row[u].x + j < row[u].y) ? mL[(int64_t(var_edge_msg[row[u].x + j]) + row[u].z) << msh] : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < kVsUnits; ++u) {
@@ -292,18 +319,18 @@ k_var_sums(BatchMap mp, int64_t num_var_states, int64_t Es, const int2* __restri
       for (; k + 16 <= k1; k += 16) {
         float x[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = mL[(var_edge_msg[k + j] + st) << sh];
+        for (int j = 0; j < 16; ++j) x[j] = mL[(var_edge_msg[k + j] + st) << msh];
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc += x[j];
       }
       for (; k + 4 <= k1; k += 4) {
-        const float a0 = mL[(var_edge_msg[k] + st) << sh];
-        const float a1 = mL[(var_edge_msg[k + 1] + st) << sh];
-        const float a2 = mL[(var_edge_msg[k + 2] + st) << sh];
-        const float a3 = mL[(var_edge_msg[k + 3] + st) << sh];
+        const float a0 = mL[(var_edge_msg[k] + st) << msh];
+        const float a1 = mL[(var_edge_msg[k + 1] + st) << msh];
+        const float a2 = mL[(var_edge_msg[k + 2] + st) << msh];
+        const float a3 = mL[(var_edge_msg[k + 3] + st) << msh];
         acc += a0; acc += a1; acc += a2; acc += a3;
       }
-      for (; k < k1; ++k) acc += mL[(var_edge_msg[k] + st) << sh];
+      for (; k < k1; ++k) acc += mL[(var_edge_msg[k] + st) << msh];
       SL[v << sh] = acc;
     }
   }
