@@ -72,9 +72,10 @@ struct EnumBlockPlan {
   int bip = -1;  // index into pgx_plan::bips when the block has the dense-grid structure
   int32_t *d_cfg_es = nullptr, *d_t_ptr = nullptr, *d_t_k = nullptr, *d_edge_off = nullptr;
   int32_t *d_fac_edge = nullptr, *d_fac_msg = nullptr, *d_fac_pot = nullptr;
-  uint16_t* d_cfg_b = nullptr;  // partner-state table of the merged max-product launch
-  int2* d_steps = nullptr;      // its step schedule
-  int32_t warp_first[pgx::kBigWarps + 1] = {0};
+  uint32_t* d_rounds = nullptr;    // round schedule of the merged max-product launch
+  int32_t* d_round_ptr = nullptr;  // [num_groups + 1] first round of every lane-group
+  uint32_t* d_rounds_b = nullptr;  // partner states in round order, two rounds per word (permuted-potential path)
+  int num_groups = 0, num_rounds = 0;
   int bigmax = -1;              // index into the plan's BigMaxGroup array, or -1
   int n0 = 0;                   // states of the first variable
 };
@@ -104,6 +105,7 @@ struct Workspace {
   float *mA = nullptr, *mB = nullptr, *S = nullptr, *evT = nullptr, *lpT = nullptr, *part = nullptr;
   float *cA = nullptr, *cB = nullptr;  // compressed (one float per edge) messages of the fused blocks
   float* row = nullptr;                // one normalised [Es] message vector (initial messages shared by the batch)
+  float* lpR = nullptr;                // round-ordered potentials of the merged max-product launch (not per batch)
   float* agg = nullptr;  // per-factor aggregates of the two-launch wide logical update
   // staging for pgx_infer_host
   float *h_lp = nullptr, *h_ev = nullptr, *h_msgs_in = nullptr, *h_msgs_out = nullptr,
@@ -153,6 +155,8 @@ struct pgx_plan {
   pgx::BigMaxGroup* d_bigmax_groups = nullptr;
   int2* d_bigmax_units = nullptr;
   int64_t bigmax_units = 0, bigmax_es = 0;
+  int64_t bigmax_perm_floats = 0;  // size of the round-ordered copy of the potentials
+  bool bigmax_perm_active = false; // this run uses it (set by pgx_bp_run)
   size_t bigmax_smem = 0;
   unsigned int* d_bigmax_counter = nullptr;
   // lattice mode (the whole graph is one 2-D nearest-neighbour lattice block; LatticeDev)
@@ -187,7 +191,7 @@ void free_dev(void* p) {
 
 void free_workspace(Workspace& ws) {
   free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT); free_dev(ws.part);
-  free_dev(ws.agg); free_dev(ws.cA); free_dev(ws.cB); free_dev(ws.row);
+  free_dev(ws.agg); free_dev(ws.cA); free_dev(ws.cB); free_dev(ws.row); free_dev(ws.lpR);
   free_dev(ws.h_lp); free_dev(ws.h_ev); free_dev(ws.h_msgs_in); free_dev(ws.h_msgs_out);
   free_dev(ws.h_marg); free_dev(ws.h_deltas); free_dev(ws.h_map); free_dev(ws.h_ties);
   ws = Workspace{};
@@ -385,31 +389,89 @@ int build_enum_block(pgx_plan* plan, const pgx_enum_block* desc_blocks, const st
     for (int s0 = 0; s0 < edge_off[1] && strict; ++s0)
       for (int k = t_ptr[s0] + 1; k < t_ptr[s0 + 1] && strict; ++k)
         strict = cfg_es[size_t(k) * 2 + 1] > cfg_es[size_t(k - 1) * 2 + 1];
+    // ... and a configuration packs into 32 bits (k: 20 bits, partner state: 12 bits)
+    strict = strict && K < (1 << 20) && ns - edge_off[1] < 4096;
     if (strict) {
-      std::vector<uint16_t> cfg_b(std::max<size_t>(K, 1));
-      for (int k = 0; k < K; ++k) cfg_b[k] = uint16_t(cfg_es[size_t(k) * 2 + 1] - edge_off[1]);
-      if ((rc = upload(cfg_b, &out->d_cfg_b, &plan->device_bytes))) return rc;
-      // step schedule: every state's list cut into runs of <= 32 configurations
-      std::vector<int2> steps;
-      std::vector<int32_t> list_first;  // index of the first step of every non-empty list
-      for (int s0 = 0; s0 < edge_off[1]; ++s0) {
-        const int k0 = t_ptr[s0], k1 = t_ptr[s0 + 1];
-        if (k1 > k0) list_first.push_back(int32_t(steps.size()));
-        for (int k = k0; k < k1; k += 32) {
-          const int cnt = std::min(32, k1 - k);
-          steps.push_back(make_int2(s0 | ((cnt - 1) << 16) | ((k + 32 >= k1 ? 1 : 0) << 21), k));
+      // Round schedule (k_enum_big_maxprod_all): lane l of lane-group g owns state a = 32 g + l of
+      // the first variable and walks its configuration list in rounds; within a round the
+      // partner states of the 32 lanes are pairwise distinct (greedy: a lane whose next partner
+      // state is already taken in this round idles), so the partner-side maxima can be updated
+      // with a plain read-max-write.  Entry = k | partner << 20, 0xffffffff = idle.
+      const int n0 = edge_off[1];
+      const int num_groups = (n0 + 31) / 32;
+      std::vector<uint32_t> rounds;
+      std::vector<uint8_t> idle_bank;  // per entry: the free bank an idle lane's dummy access goes to
+      std::vector<int32_t> round_ptr(num_groups + 1, 0);
+      for (int g = 0; g < num_groups; ++g) {
+        // remaining configurations (k, partner state) of every lane; the order inside a list is
+        // free (max is order-independent), so a lane takes ANY remaining configuration whose
+        // shared-memory bank (partner state mod 32) is still free in this round: distinct banks
+        // = distinct partner states and conflict-free accesses.  Lanes with the most work left
+        // choose first.
+        std::vector<std::pair<int32_t, int32_t>> rem[32];
+        for (int l = 0; l < 32; ++l) {
+          const int a = 32 * g + l;
+          if (a >= n0) continue;
+          for (int k = t_ptr[a + 1] - 1; k >= t_ptr[a]; --k) rem[l].push_back({k, cfg_es[size_t(k) * 2 + 1] - n0});
         }
+        for (;;) {
+          int order[32];
+          size_t left = 0;
+          for (int l = 0; l < 32; ++l) { order[l] = l; left += rem[l].size(); }
+          if (left == 0) break;
+          std::stable_sort(order, order + 32, [&](int x, int y) { return rem[x].size() > rem[y].size(); });
+          uint32_t entry[32];
+          uint32_t banks = 0;
+          for (int l = 0; l < 32; ++l) entry[l] = 0xffffffffu;
+          for (int oi = 0; oi < 32; ++oi) {
+            const int l = order[oi];
+            for (size_t i = rem[l].size(); i-- > 0;) {  // from the back: ascending k first
+              const int32_t pb = rem[l][i].second;
+              if ((banks >> (pb & 31)) & 1u) continue;
+              banks |= 1u << (pb & 31);
+              entry[l] = uint32_t(rem[l][i].first) | (uint32_t(pb) << 20);
+              rem[l].erase(rem[l].begin() + i);
+              break;
+            }
+          }
+          // idle lanes read-max-write a dummy slot n1 + j: give each one a bank nobody uses
+          int fb = 0;
+          for (int l = 0; l < 32; ++l)
+            if (entry[l] == 0xffffffffu) {
+              while ((banks >> fb) & 1u) ++fb;
+              idle_bank.push_back(uint8_t(fb));
+              banks |= 1u << fb;
+            } else {
+              idle_bank.push_back(255);
+            }
+          rounds.insert(rounds.end(), entry, entry + 32);
+        }
+        // even number of rounds per lane-group (the partner states are fetched two rounds at a time)
+        if ((rounds.size() / 32 - size_t(round_ptr[g])) & 1) {
+          rounds.insert(rounds.end(), 32, 0xffffffffu);
+          for (int l = 0; l < 32; ++l) idle_bank.push_back(uint8_t(l));
+        }
+        round_ptr[g + 1] = int32_t(rounds.size() / 32);
       }
-      const int32_t num_steps = int32_t(steps.size());
-      out->warp_first[0] = 0;
-      for (int w = 1; w < pgx::kBigWarps; ++w) {  // cut at the list boundary nearest to an even share
-        const int32_t target = int32_t(int64_t(num_steps) * w / pgx::kBigWarps);
-        auto it = std::lower_bound(list_first.begin(), list_first.end(), target);
-        out->warp_first[w] = it == list_first.end() ? num_steps : *it;
+      if (rounds.empty()) rounds.push_back(0xffffffffu);
+      {
+        // [round pair][lane]: partner state of round 2p | partner state of round 2p + 1 << 16
+        // dummy slot of an idle entry: n1 + j with (n1 + j) mod 32 = its free bank
+        const int n1 = ns - n0;
+        auto pb = [&](size_t i) {
+          if (rounds[i] != 0xffffffffu) return rounds[i] >> 20;
+          const int bank = i < idle_bank.size() ? idle_bank[i] : int(i & 31);
+          return uint32_t(n1 + ((bank - n1) % 32 + 32) % 32);
+        };
+        std::vector<uint32_t> rb(std::max<size_t>(rounds.size() / 2, 32));
+        for (size_t pr = 0; pr + 1 < rounds.size() / 32 + 1 && pr * 64 + 63 < rounds.size(); ++pr)
+          for (size_t l = 0; l < 32; ++l) rb[pr * 32 + l] = pb(pr * 64 + l) | (pb(pr * 64 + 32 + l) << 16);
+        if ((rc = upload(rb, &out->d_rounds_b, &plan->device_bytes))) return rc;
       }
-      out->warp_first[pgx::kBigWarps] = num_steps;
-      if (steps.empty()) steps.push_back(make_int2(0, 0));
-      if ((rc = upload(steps, &out->d_steps, &plan->device_bytes))) return rc;
+      out->num_rounds = int32_t(rounds.size() / 32);
+      if ((rc = upload(rounds, &out->d_rounds, &plan->device_bytes))) return rc;
+      if ((rc = upload(round_ptr, &out->d_round_ptr, &plan->device_bytes))) return rc;
+      out->num_groups = num_groups;
       out->bigmax = 0;  // index assigned by the caller
       out->n0 = edge_off[1];
     }
@@ -528,22 +590,24 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
                      plan->enum_blocks[plan->dominant].bigmax >= 0;
     static bool attr_set = false;
     if (!attr_set) {
-      PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod_all<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod_all<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod_all<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod_all<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod_all<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
     PGX_CUDA(cudaMemsetAsync(plan->d_bigmax_counter, 0, sizeof(unsigned int), st));
     if (dom && (rc = prof_mark(plan, st, plan->dominant))) return rc;
     const int per_sm = int(std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / plan->bigmax_smem)));
     const int64_t grid = std::min<int64_t>(plan->bigmax_units * mp.batch, int64_t(plan->num_sms) * per_sm);
-    if (lp.kind != 1)
-      pgx::k_enum_big_maxprod_all<true><<<unsigned(grid), pgx::kThreads, plan->bigmax_smem, st>>>(
-          mp, plan->d_bigmax_groups, plan->d_bigmax_units, plan->bigmax_units, plan->d_bigmax_counter, plan->d_edge_vs,
-          lp, S, m_old, m_new, a);
-    else
-      pgx::k_enum_big_maxprod_all<false><<<unsigned(grid), pgx::kThreads, plan->bigmax_smem, st>>>(
-          mp, plan->d_bigmax_groups, plan->d_bigmax_units, plan->bigmax_units, plan->d_bigmax_counter, plan->d_edge_vs,
-          lp, S, m_old, m_new, a);
+    const float* lpR = plan->ws.lpR;
+#define PGX_BIGMAX(FLAT, PERM)                                                                                     \
+  pgx::k_enum_big_maxprod_all<FLAT, PERM><<<unsigned(grid), pgx::kThreads, plan->bigmax_smem, st>>>(                \
+      mp, plan->d_bigmax_groups, plan->d_bigmax_units, plan->bigmax_units, plan->d_bigmax_counter, plan->d_edge_vs, \
+      lp, lpR, S, m_old, m_new, a)
+    if (plan->bigmax_perm_active) PGX_BIGMAX(true, true);
+    else if (lp.kind != 1) PGX_BIGMAX(true, false);
+    else PGX_BIGMAX(false, false);
+#undef PGX_BIGMAX
     if ((rc = check_launch(plan, "k_enum_big_maxprod_all"))) return rc;
     if (dom) {
       plan->dominant_name = "k_enum_big_maxprod_all";
@@ -886,9 +950,13 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       plan->bigmax_es += eb.dev.num_factors * eb.dev.ns;
       pgx::BigMaxGroup g;
       g.blk = eb.dev;
-      g.cfg_b = eb.d_cfg_b;
-      g.steps = eb.d_steps;
-      for (int w = 0; w <= pgx::kBigWarps; ++w) g.warp_first[w] = eb.warp_first[w];
+      g.rounds = eb.d_rounds;
+      g.round_ptr = eb.d_round_ptr;
+      g.num_groups = eb.num_groups;
+      g.rounds_b = eb.d_rounds_b;
+      g.num_rounds = eb.num_rounds;
+      g.perm_base = plan->bigmax_perm_floats;
+      plan->bigmax_perm_floats += int64_t(eb.num_rounds) * 32 * eb.dev.num_factors;
       groups.push_back(g);
       for (int64_t f = 0; f < eb.dev.num_factors; ++f) units.push_back({eb.bigmax, int32_t(f), eb.dev.num_configs});
     }
@@ -1177,7 +1245,7 @@ void pgx_plan_destroy(pgx_plan* plan) {
   free_dev(plan->d_var_first_state); free_dev(plan->d_var_ptr); free_dev(plan->d_var_edge_msg);
   for (EnumBlockPlan& eb : plan->enum_blocks) {
     free_dev(eb.d_cfg_es); free_dev(eb.d_t_ptr); free_dev(eb.d_t_k); free_dev(eb.d_edge_off);
-    free_dev(eb.d_fac_edge); free_dev(eb.d_fac_msg); free_dev(eb.d_fac_pot); free_dev(eb.d_cfg_b); free_dev(eb.d_steps);
+    free_dev(eb.d_fac_edge); free_dev(eb.d_fac_msg); free_dev(eb.d_fac_pot); free_dev(eb.d_rounds); free_dev(eb.d_round_ptr); free_dev(eb.d_rounds_b);
   }
   free_dev(plan->d_bigmax_groups); free_dev(plan->d_bigmax_units); free_dev(plan->d_bigmax_counter);
   for (LogicalPlan* lg : {&plan->or_f, &plan->and_f, &plan->pool_f}) {
@@ -1556,6 +1624,18 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
         cur = dst;
       }
     }
+  }
+  // Merged max-product launch (RCN-size factors): with potentials shared by the batch and enough
+  // iterations to amortise it, one pass copies the potentials into round order first.
+  plan->bigmax_perm_active = false;
+  if (temperature == 0.f && plan->bigmax_units > 0 && !(plan->disabled_paths & (PGX_PATH_MERGED_MAX | PGX_PATH_PERM_POTENTIALS)) &&
+      !pull && !lattice && lp.kind == 0 && num_iters >= 3 && plan->bigmax_perm_floats > 0) {
+    if (ws.lpR == nullptr) PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.lpR), size_t(plan->bigmax_perm_floats) * sizeof(float)));
+    const dim3 grid(8, unsigned(std::min<int64_t>(plan->bigmax_units, 65535)));
+    pgx::k_bigmax_permute<true><<<grid, pgx::kThreads, 0, st>>>(mp, plan->d_bigmax_groups, plan->d_bigmax_units,
+                                                              plan->bigmax_units, lp, ws.lpR);
+    if ((rc = check_launch(plan, "k_bigmax_permute"))) return rc;
+    plan->bigmax_perm_active = true;
   }
   for (int it = 0; it < ((pull || lattice) ? 0 : num_iters); ++it) {
     a.delta_off = it;

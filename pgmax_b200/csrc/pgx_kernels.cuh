@@ -1795,18 +1795,21 @@ k_enum_big_maxprod(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ ed
 // K2c-max2: the same update without shared-memory atomics (ATOMS on spread addresses costs
 // ~2 cycles per LANE on this part, which made the kernel above atomics-bound), for ALL such
 // groups of the graph in ONE launch.
-//   * the plan cuts every state's configuration list into STEPS of <= 32 configurations
-//     (a, first k, count, last-of-list): a schedule per configuration table, shared by all
-//     factors of the group, so the kernel carries no list logic;
-//   * a warp executes a contiguous run of steps (runs are cut at list boundaries).  Within a
-//     step all partner states b are distinct, so every warp keeps a PRIVATE copy Mw[warp][b]
-//     of the partner-side maxima and updates it with a plain read-max-write (__syncwarp
-//     between steps); the copies are max-reduced once per factor.  The a-side maximum is a
-//     warp reduction at the end of each list.  max is order-independent: bit-identical to
-//     the other kernels and to the oracle;
-//   * the partner state of a configuration comes from a compact uint16 table (2 B from L2),
-//     the potential from HBM (4 B, streamed once): 6 B per configuration instead of 12;
-//   * loads run one trip (kBigTrip steps) ahead of their use in registers;
+//   * LANE-PER-STATE: lane l of lane-group g owns state a = 32 g + l of the first variable and
+//     walks a's configuration list; its maximum over the list (the a-side message) is a plain
+//     running maximum in a register - no warp reduction, no list logic in the kernel;
+//   * the plan arranges the walk in ROUNDS (one configuration per lane) such that the partner
+//     states b of a round fall into pairwise distinct shared-memory banks (a lane takes any
+//     of its remaining configurations whose bank is free, else idles that round: distinct b
+//     AND conflict-free accesses), so every warp keeps a PRIVATE copy Mw[warp][b] of the partner-side maxima and
+//     updates it with a plain read-max-write (__syncwarp between rounds); the copies are
+//     max-reduced once per factor.  max is order-independent: bit-identical to the other
+//     kernels and to the oracle;
+//   * one 4-byte schedule entry (k | b << 20, coalesced, L2-resident, shared by all factors of
+//     the group) and the 4-byte potential (HBM; a lane streams its own list, so a fetched
+//     sector serves its next 8 rounds out of L1) per configuration; ~20 instructions per
+//     32 configurations;
+//   * loads run one trip (kBigTrip rounds) ahead of their use in registers;
 //   * work units (factor, sample) of all groups are sorted by configuration count
 //     (descending) and handed out through an atomic counter: the launch ends balanced.
 // Dynamic smem: (2 ns + nwarps * (n1 + 32) + 32) floats of the largest group.
@@ -1814,18 +1817,49 @@ k_enum_big_maxprod(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ ed
 constexpr int kBigWarps = kThreads / 32;
 struct BigMaxGroup {
   EnumBlockDev blk;
-  const uint16_t* cfg_b;  // [num_configs] state of variable 1 in configuration k
-  const int2* steps;      // [num_steps] x = a | (count - 1) << 16 | last << 21, y = first k
-  int32_t warp_first[kBigWarps + 1];  // steps [warp_first[w], warp_first[w + 1]) belong to warp w
+  const uint32_t* rounds;    // [num_rounds][32] k | partner state << 20, 0xffffffff = idle
+  const int32_t* round_ptr;  // [num_groups + 1]
+  int32_t num_groups;        // lane-groups = ceil(states of variable 0 / 32)
+  // permuted-potential path: the run starts by copying every factor's (clipped) potentials into
+  // round order, lpR[perm_base + f * 32 * num_rounds + 32 * round + lane] (-inf at idle
+  // entries), so that the hot loop's two loads per configuration - the potential and the
+  // 2-byte partner state - are both coalesced and the loop needs no select at all
+  const uint32_t* rounds_b;  // [num_rounds / 2][32] partner states of rounds 2p, 2p + 1 (16 bits each);
+                             // idle: n1 + j, a dummy slot in a bank no lane of the round uses.  Every lane-group has an
+                             // even number of rounds.
+  int64_t perm_base;
+  int32_t num_rounds;
 };
+
+// One-off per run: potentials -> round order (see BigMaxGroup).
+template <bool kFlatLp>
+__global__ void __launch_bounds__(kThreads)
+k_bigmax_permute(BatchMap mp, const BigMaxGroup* __restrict__ groups, const int2* __restrict__ units,
+                 int64_t num_units, View lp, float* __restrict__ lpR) {
+  for (int64_t u = blockIdx.y; u < num_units; u += gridDim.y) {
+    const int2 uf = units[u];
+    const BigMaxGroup& G = groups[uf.x];
+    const int64_t n = int64_t(G.num_rounds) * 32;
+    const LaneView lpL = lane_view(lp, mp, 0);
+    const float* __restrict__ src = lpL.q + (G.blk.pot_base(uf.y) << lpL.sh);
+    float* __restrict__ dst = lpR + G.perm_base + int64_t(uf.y) * n;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+      const uint32_t e = G.rounds[i];
+      dst[i] = e == 0xffffffffu ? -INFINITY : clip_lp(kFlatLp ? src[e & 0xfffffu] : src[size_t(e & 0xfffffu) << lpL.sh]);
+    }
+  }
+}
 
 constexpr int kBigTrip = 8;
 
-template <bool kFlatLp>  // potentials addressed without a sample-tile shift (shared or batch-major)
-__global__ void __launch_bounds__(kThreads)
+// kFlatLp: potentials addressed without a sample-tile shift (shared or batch-major);
+// kPerm: potentials come from the round-ordered copy lpR (potentials shared by the batch)
+template <bool kFlatLp, bool kPerm>
+__global__ void __launch_bounds__(kThreads, 3)
 k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, const int2* __restrict__ units,
                        int64_t num_units, unsigned int* __restrict__ counter,
-                       const int32_t* __restrict__ edge_vs, View lp, const float* __restrict__ S,
+                       const int32_t* __restrict__ edge_vs, View lp, const float* __restrict__ lpR,
+                       const float* __restrict__ S,
                        const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
   extern __shared__ float smem[];
   __shared__ unsigned int s_unit;
@@ -1866,62 +1900,111 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
     for (int i = threadIdx.x; i < kBigWarps * (n1 + 32); i += blockDim.x) Mw[i] = -INFINITY;
     __syncthreads();
 
-    {  // ---- configurations: this warp's run of steps ----------------------------------------
-      const uint16_t* __restrict__ cb = G.cfg_b;
-      const int2* __restrict__ steps = G.steps;
+    {  // ---- configurations: this warp's lane-groups, round by round ---------------------------
+      const uint32_t* __restrict__ rounds = G.rounds;
       const float* __restrict__ lpu = lpL.q + (pbase << lpL.sh);
       const int lsh = lpL.sh;
-      const uint32_t q_s = smem_u32(q), qb_s = q_s + 4u * n0, M_s = smem_u32(M);
+      const uint32_t qb_s = smem_u32(q) + 4u * n0;
       const uint32_t mw_s = smem_u32(Mw + warp * (n1 + 32));
       const uint32_t dummy_s = mw_s + 4u * (n1 + lane);  // idle lanes read-max-write their own slot
       auto lds_f = [](uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; };
       auto sts_f = [](uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); };
-      const int s_end = G.warp_first[warp + 1];
-      // one trip = kBigTrip steps: lane p < kBigTrip fetches the descriptor of step s + p; every
-      // lane then requests (partner state, potential) of its configuration in each step
-      int2 meta_n = make_int2(0, 0);
-      int rb_n[kBigTrip];
-      float rl_n[kBigTrip];
-      auto request = [&](int s0) {
-        meta_n = (lane < kBigTrip && s0 + lane < s_end) ? __ldg(steps + s0 + lane) : make_int2(0, 0);
+      const float* __restrict__ lpr = lpR + G.perm_base + f * (int64_t(G.num_rounds) * 32) + lane;
+      const uint32_t* __restrict__ rbl = G.rounds_b + lane;
+      // one trip = kPermTrip rounds; the next trip's loads (2 KiB of potentials per warp) are in
+      // flight while this one is consumed: with 24 warps per SM that is ~50 KiB per SM in
+      // flight, what HBM latency x bandwidth asks for
+      constexpr int kPermTrip = 16;
+      for (int grp = warp; kPerm && grp < G.num_groups; grp += kBigWarps) {
+        const int a_own = grp * 32 + lane;
+        const float qa = a_own < n0 ? q[a_own] : 0.f;
+        const int r_end = G.round_ptr[grp + 1];
+        const uint32_t idle2 = uint32_t(n1 + lane) * 0x10001u;
+        uint32_t en_n[kPermTrip / 2];
+        float rl_n[kPermTrip];
+        auto request = [&](int r0) {
 #pragma unroll
-        for (int p = 0; p < kBigTrip; ++p) {
-          const int x = __shfl_sync(0xffffffffu, meta_n.x, p), k0 = __shfl_sync(0xffffffffu, meta_n.y, p);
-          // unconditional loads (idle lanes re-read the step's first configuration, a valid
-          // address; absent steps read configuration 0): no branch between the requests
-          const uint32_t k = uint32_t(k0) + (lane <= ((x >> 16) & 31) ? uint32_t(lane) : 0u);
-          rb_n[p] = int(__ldg(cb + k));
-          rl_n[p] = kFlatLp ? __ldcs(lpu + k) : __ldcs(lpu + (size_t(k) << lsh));
-        }
-      };
-      float best = -INFINITY;
-      int s0 = G.warp_first[warp];
-      if (s0 < s_end) request(s0);
-      for (; s0 < s_end; s0 += kBigTrip) {
-        const int2 meta = meta_n;
-        int rb[kBigTrip];
-        float rl[kBigTrip];
+          for (int p = 0; p < kPermTrip / 2; ++p) {
+            const bool in = r0 + 2 * p < r_end;  // rounds come in pairs
+            en_n[p] = in ? __ldg(rbl + (size_t(r0 + 2 * p) << 4)) : idle2;
+            rl_n[2 * p] = in ? __ldcs(lpr + (size_t(r0 + 2 * p) << 5)) : -INFINITY;
+            rl_n[2 * p + 1] = in ? __ldcs(lpr + (size_t(r0 + 2 * p + 1) << 5)) : -INFINITY;
+          }
+        };
+        float best = -INFINITY;
+        int r0 = G.round_ptr[grp];
+        if (r0 < r_end) request(r0);
+        for (; r0 < r_end; r0 += kPermTrip) {
+          uint32_t en[kPermTrip / 2];
+          float rl[kPermTrip];
 #pragma unroll
-        for (int p = 0; p < kBigTrip; ++p) { rb[p] = rb_n[p]; rl[p] = rl_n[p]; }
-        if (s0 + kBigTrip < s_end) request(s0 + kBigTrip);  // next trip in flight during this one
+          for (int p = 0; p < kPermTrip / 2; ++p) en[p] = en_n[p];
 #pragma unroll
-        for (int p = 0; p < kBigTrip; ++p) {
-          if (s0 + p >= s_end) break;
-          const int x = __shfl_sync(0xffffffffu, meta.x, p);
-          const int a_cur = x & 0xffff;
-          const bool on = lane <= ((x >> 16) & 31);
-          const uint32_t b_s = 4u * uint32_t(rb[p]);
-          const float sk = on ? (lds_f(q_s + 4u * a_cur) + lds_f(qb_s + b_s)) + clip_lp(rl[p]) : -INFINITY;
-          best = fmaxf(best, sk);
-          const uint32_t slot = on ? mw_s + b_s : dummy_s;
-          sts_f(slot, fmaxf(lds_f(slot), sk));
-          __syncwarp();
-          if (x & (1 << 21)) {  // last step of a_cur's list
-            for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
-            if (lane == 0) sts_f(M_s + 4u * a_cur, best);
-            best = -INFINITY;
+          for (int p = 0; p < kPermTrip; ++p) rl[p] = rl_n[p];
+          if (r0 + kPermTrip < r_end) request(r0 + kPermTrip);
+          // idle entries: potential -inf, partner "state" n1 + j = a dummy slot
+          // (the q read lands in M[], finite or -inf: the sum stays -inf).
+          // All q reads of the trip first (read-only: they overlap), then the read-max-write chain.
+          uint32_t b_s[kPermTrip];
+          float sk[kPermTrip];
+#pragma unroll
+          for (int p = 0; p < kPermTrip; ++p) {
+            b_s[p] = ((p & 1) ? (en[p >> 1] >> 16) : (en[p >> 1] & 0xffffu)) << 2;
+            sk[p] = lds_f(qb_s + b_s[p]);
+          }
+#pragma unroll
+          for (int p = 0; p < kPermTrip; ++p) {
+            sk[p] = (qa + sk[p]) + rl[p];
+            best = fmaxf(best, sk[p]);
+          }
+#pragma unroll
+          for (int p = 0; p < kPermTrip; ++p) {
+            const uint32_t slot = mw_s + b_s[p];
+            sts_f(slot, fmaxf(lds_f(slot), sk[p]));
+            asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
           }
         }
+        if (a_own < n0) M[a_own] = best;
+      }
+      for (int grp = warp; !kPerm && grp < G.num_groups; grp += kBigWarps) {
+        const int a_own = grp * 32 + lane;
+        const float qa = a_own < n0 ? q[a_own] : 0.f;
+        const int r_end = G.round_ptr[grp + 1];
+        uint32_t en_n[kBigTrip];
+        float rl_n[kBigTrip];
+        auto request = [&](int r0) {
+#pragma unroll
+          for (int p = 0; p < kBigTrip; ++p)
+            en_n[p] = r0 + p < r_end ? __ldg(rounds + (size_t(r0 + p) << 5) + lane) : 0xffffffffu;
+#pragma unroll
+          for (int p = 0; p < kBigTrip; ++p) {
+            // unconditional loads: idle lanes read configuration 0 of the factor
+            const uint32_t k = en_n[p] == 0xffffffffu ? 0u : (en_n[p] & 0xfffffu);
+            rl_n[p] = kFlatLp ? __ldg(lpu + k) : __ldg(lpu + (size_t(k) << lsh));
+          }
+        };
+        float best = -INFINITY;
+        int r0 = G.round_ptr[grp];
+        if (r0 < r_end) request(r0);
+        for (; r0 < r_end; r0 += kBigTrip) {
+          uint32_t en[kBigTrip];
+          float rl[kBigTrip];
+#pragma unroll
+          for (int p = 0; p < kBigTrip; ++p) { en[p] = en_n[p]; rl[p] = rl_n[p]; }
+          if (r0 + kBigTrip < r_end) request(r0 + kBigTrip);  // next trip in flight during this one
+#pragma unroll
+          for (int p = 0; p < kBigTrip; ++p) {
+            const bool on = en[p] != 0xffffffffu;            // absent rounds of the last trip are idle entries
+            const uint32_t b_s = on ? (en[p] >> 20) << 2 : 0u;  // idle lanes read partner state 0
+            float sk = (qa + lds_f(qb_s + b_s)) + clip_lp(rl[p]);
+            sk = on ? sk : -INFINITY;
+            best = fmaxf(best, sk);
+            const uint32_t slot = on ? mw_s + b_s : dummy_s;
+            sts_f(slot, fmaxf(lds_f(slot), sk));
+            __syncwarp();
+          }
+        }
+        if (a_own < n0) M[a_own] = best;
       }
     }
     __syncthreads();

@@ -80,6 +80,32 @@ def test_config3_rcn_625_state_factors():
   plan.disable_paths(0)
 
 
+def test_config3_rcn_random_potentials_round_ordered_copy():
+  """Non-zero potentials (a few beyond the +-1e6 clip) through the merged launch: the default
+  path reads a round-ordered, clipped copy of the potentials made once per run; it must agree
+  bit for bit with the gather path (copy disabled, or fewer than 3 iterations) and the oracle."""
+  from pgmax_b200.infer.bp_state import BPArrays
+  fg, groups, evidence = models.rcn_model(num_models=1, num_vars=6, radii=(2, 4, 7), extra_edges=2, seed=11)
+  bp = infer.BP(fg.bp_state, temperature=0.0)
+  arrays = bp.init(evidence_updates=evidence)
+  rng = np.random.default_rng(7)
+  lp = (rng.normal(size=arrays.log_potentials.shape) * 2.0).astype(np.float32)
+  lp[rng.integers(0, lp.size, size=50)] = 3e6
+  lp[rng.integers(0, lp.size, size=50)] = -np.inf
+  arrays = BPArrays(log_potentials=lp, ftov_msgs=arrays.ftov_msgs, evidence=arrays.evidence)
+  graph = bp_oracle.graph_from_context(bp.context)
+  plan = bp.context.plan
+  for iters in (2, 6):
+    want, want_d = bp_oracle.run_bp(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, iters, 0.5, 0.0)
+    got, got_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5)
+    np.testing.assert_array_equal(got.ftov_msgs, want)
+    np.testing.assert_array_equal(got_d, want_d)
+    plan.disable_paths(plan.PATH_PERM_POTENTIALS)
+    ref = bp.run(arrays, num_iters=iters, damping=0.5)
+    plan.disable_paths(0)
+    np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
+
+
 def test_config3_rcn_batched_merged_launch():
   """Three samples (different evidence) of a two-model RCN-shaped graph through the merged
   max-product launch: every sample bit-identical to its own single-sample oracle run."""
