@@ -618,6 +618,9 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
     EnumBlockPlan& eb = plan->enum_blocks[bi];
     const int64_t F = eb.dev.num_factors;
     if (merged_max && eb.bigmax >= 0) continue;
+    // fused mode: the blocks outside the dense-grid kernel run beside it on the auxiliary stream
+    const cudaStream_t main_enum_st = st;
+    const cudaStream_t st = (fused && aux != nullptr && !lpull && eb.bip < 0) ? aux : main_enum_st;  // NOLINT
     if ((rc = prof_mark(plan, st, int(bi)))) return rc;
     if (fused && eb.bip >= 0) {
       const pgx::BipDev& g = plan->bips[eb.bip].dev;
@@ -1161,6 +1164,12 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       }
       plan->part_rows = rows;
       plan->bips.resize(grids.size());
+      if (plan->aux == nullptr && plan->enum_blocks.size() > grids.size()) {
+        if (cudaStreamCreateWithFlags(&plan->aux, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming) != cudaSuccess)
+          return bail(fail(PGX_ERR_CUDA, "creating the auxiliary stream failed"));
+      }
       for (size_t gi = 0; gi < grids.size(); ++gi) {
         const Grid& gr = grids[gi];
         EnumBlockPlan& eb = plan->enum_blocks[gr.blk];
@@ -1469,7 +1478,14 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   // cooperative launch.
   // (Large grids keep the two-pass path: re-deriving S per edge costs 4x the gathers and
   // measured slower than k_var_sums + k_enum_pw2 once the graph no longer fits in cache.)
-  const cudaStream_t aux = (lpull && plan->aux != nullptr && !(plan->disabled_paths & PGX_PATH_AUX_STREAM)) ? plan->aux : nullptr;
+  // auxiliary stream: the smaller logical group beside the larger one (pull path), or the
+  // non-fused enum blocks (unary factors of an RBM) beside the fused dense-grid kernel - they
+  // read the same old messages and sums and write disjoint message ranges
+  const bool side_blocks = fused && plan->enum_blocks.size() > plan->bips.size() && plan->or_f.dev.num_factors == 0 &&
+                           plan->and_f.dev.num_factors == 0 && plan->pool_f.dev.num_factors == 0;
+  const cudaStream_t aux = ((lpull || side_blocks) && plan->aux != nullptr && !(plan->disabled_paths & PGX_PATH_AUX_STREAM))
+                               ? plan->aux : nullptr;
+  const bool aux_after_s = lpull ? plan->aux_needs_s : true;
   bool pull = false;
   if (plan->pull_ok && !fused && plan->enum_blocks.size() == 1) {
     const int upw0 = 32 >> mp.bx_log;
@@ -1639,7 +1655,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   }
   for (int it = 0; it < ((pull || lattice) ? 0 : num_iters); ++it) {
     a.delta_off = it;
-    if (aux != nullptr && !plan->aux_needs_s) {
+    if (aux != nullptr && !aux_after_s) {
       PGX_CUDA(cudaEventRecord(plan->ev_fork, st));
       PGX_CUDA(cudaStreamWaitEvent(aux, plan->ev_fork, 0));
     }
@@ -1661,7 +1677,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
           mp, Vs, Es, plan->d_vs_csr, plan->d_var_edge_msg, ev, shared_init ? ws.row : cur, ws.S, shared_init ? 1 : 0);
       if ((rc = check_launch(plan, "k_var_sums"))) return rc;
     }
-    if (aux != nullptr && plan->aux_needs_s) {
+    if (aux != nullptr && aux_after_s) {
       PGX_CUDA(cudaEventRecord(plan->ev_fork, st));
       PGX_CUDA(cudaStreamWaitEvent(aux, plan->ev_fork, 0));
     }
