@@ -164,6 +164,19 @@ int pgx_decode(pgx_plan* plan, void* stream, int64_t batch,
                const float* ftov_msgs, int msgs_batched,
                int32_t* map_out, float* marginals_out, int32_t* tie_count_out);
 
+/* Energy of a decoding (replaces infer.compute_energy, pgmax/infer/energy.py:53-148, and the
+ * per-type compute_energy of pgmax/factor/enum.py:276-323, logical.py:295-358, pool.py:184-239):
+ *   energy = - sum_v evidence[v, state(v)] - sum over EnumFactors of the log potential of the
+ *   configuration the decoding selects; +inf if an EnumFactor has no valid configuration for
+ *   the decoding or an OR / AND / Pool constraint is violated.  Potentials are NOT clipped (as
+ *   in the reference).  map_states: [batch][num_vars] int32 device array in the flat variable
+ *   order (pgx_decode's map_out), or one shared row (map_batched = 0); energy_out: [batch]
+ *   float32.  Sums are formed in a fixed order (deterministic; no float atomics). */
+int pgx_energy(pgx_plan* plan, void* stream, int64_t batch,
+               const float* log_potentials, int lp_batched,
+               const float* evidence, int ev_batched,
+               const int32_t* map_states, int map_batched, float* energy_out);
+
 /* End-to-end call with HOST buffers: H2D copies, pgx_bp_run, pgx_decode, D2H
  * copies, then a stream synchronise.  ftov_in_host may be NULL (zeros);
  * ftov_out_host, marginals_out_host, tie_count_out_host, deltas_out_host may be

@@ -456,3 +456,66 @@ def decode_flat(graph: OracleGraph, beliefs):
       lse = np.log(np.sum(np.exp(x - mx), dtype=F32)) + mx
       marg[bounds[v] : bounds[v + 1]] = np.exp(x - lse)
   return states, marg, np.int32(ties)
+
+
+# ----------------------------------------------------------------------------
+# compute_energy (pgmax/infer/energy.py:53-148 and the per-type compute_energy)
+# ----------------------------------------------------------------------------
+def enum_energy(edge_states_one_hot_decoding, log_potentials, factor_configs_indices,
+                factor_configs_edge_states, num_val_configs, num_factors):
+  """pgmax/factor/enum.py:276-323."""
+  decoded = np.ones((num_val_configs,), dtype=bool)
+  np.multiply.at(decoded, factor_configs_indices,
+                 edge_states_one_hot_decoding[factor_configs_edge_states].astype(bool))
+  lp = np.asarray(log_potentials, dtype=F32)
+  with np.errstate(invalid="ignore"):
+    lp = np.where(np.isinf(lp) & ~decoded, -NEG_INF * np.sign(lp), lp)
+  if int(decoded.sum()) != num_factors:
+    return F32(np.inf)  # invalid decoding
+  return F32(-np.sum(lp[decoded], dtype=F32))
+
+
+def logical_energy(edge_states_one_hot_decoding, parents_factor_indices, parents_msg_indices,
+                   children_edge_states, edge_states_offset, log_potentials=None):
+  """pgmax/factor/logical.py:295-358."""
+  del edge_states_offset, log_potentials
+  num_factors = children_edge_states.shape[0]
+  parents = np.ones((num_factors,), dtype=F32)
+  np.multiply.at(parents, parents_factor_indices, edge_states_one_hot_decoding[parents_msg_indices])
+  children = edge_states_one_hot_decoding[children_edge_states]
+  return F32(np.inf) if np.any(parents != children) else F32(0.0)
+
+
+def pool_energy(edge_states_one_hot_decoding, pool_choices_factor_indices, pool_choices_msg_indices,
+                pool_indicators_edge_states, log_potentials=None):
+  """pgmax/factor/pool.py:184-239."""
+  del log_potentials
+  num_factors = pool_indicators_edge_states.shape[0]
+  choices = np.zeros((num_factors,), dtype=F32)
+  np.add.at(choices, pool_choices_factor_indices, edge_states_one_hot_decoding[pool_choices_msg_indices + 1])
+  indicators = edge_states_one_hot_decoding[pool_indicators_edge_states + 1]
+  return F32(np.inf) if np.any(choices != indicators) else F32(0.0)
+
+
+def compute_energy(graph: OracleGraph, log_potentials, evidence, flat_states):
+  """Energy of the decoding `flat_states` ([num_vars], flat variable order) for ONE sample:
+  one-hot the decoding over the var-states, -sum(one_hot * evidence), plus every factor
+  type's contribution (pgmax/infer/energy.py:103-147)."""
+  log_potentials = np.asarray(log_potentials, dtype=F32)
+  evidence = np.asarray(evidence, dtype=F32)
+  flat_states = np.asarray(flat_states, dtype=np.int64)
+  bounds = np.concatenate([[0], np.cumsum(graph.var_num_states)])
+  one_hot = np.zeros((graph.num_var_states,), dtype=F32)
+  has = graph.var_num_states > 0
+  one_hot[bounds[:-1][has] + flat_states[has]] = 1.0
+  energy = F32(-np.sum(one_hot * evidence, dtype=F32))
+  es_one_hot = one_hot[graph.var_states_for_edge_states]
+  fns = {ENUM: enum_energy, OR: logical_energy, AND: logical_energy, POOL: pool_energy}
+  with np.errstate(invalid="ignore"):
+    for ft in FACTOR_TYPE_ORDER:
+      ms, me = graph.msgs_range[ft]
+      ps, pe = graph.potentials_range[ft]
+      if ms != me:
+        args = dict(graph.inference_arguments[ft])
+        energy = F32(energy + fns[ft](es_one_hot[ms:me], log_potentials=log_potentials[ps:pe], **args))
+  return energy

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "pgx_bp_run_flags",
     "pgx_beliefs",
     "pgx_decode",
+    "pgx_energy",
     "pgx_infer_host",
     "pgx_plan_launch_count",
     "pgx_plan_set_exact_order",
@@ -154,6 +155,8 @@ def load() -> ctypes.CDLL:
   lib.pgx_beliefs.restype = ctypes.c_int
   lib.pgx_decode.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp]
   lib.pgx_decode.restype = ctypes.c_int
+  lib.pgx_energy.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp]
+  lib.pgx_energy.restype = ctypes.c_int
   lib.pgx_infer_host.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp,
                                  ctypes.c_int, i32, f32, f32, vp, vp, vp, vp, vp]
   lib.pgx_infer_host.restype = ctypes.c_int
@@ -429,6 +432,11 @@ class Plan:
              ties: Optional[int]) -> None:
     check(self._lib.pgx_decode(self.handle, stream, batch, ev, int(ev_batched), msgs,
                                int(msgs_batched), map_out, marginals, ties))
+
+  def energy(self, stream: int, batch: int, lp: int, lp_batched: bool, ev: int, ev_batched: bool,
+             map_states: int, map_batched: bool, out: int) -> None:
+    check(self._lib.pgx_energy(self.handle, stream, batch, lp, int(lp_batched), ev, int(ev_batched),
+                               map_states, int(map_batched), out))
 
   def infer_host(self, stream: int, batch: int, lp: int, lp_batched: bool, ev: int,
                  ev_batched: bool, msgs_in: Optional[int], msgs_batched: bool, num_iters: int,

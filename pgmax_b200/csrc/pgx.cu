@@ -157,6 +157,8 @@ struct pgx_plan {
   int64_t bigmax_units = 0, bigmax_es = 0;
   int64_t bigmax_perm_floats = 0;  // size of the round-ordered copy of the potentials
   bool bigmax_perm_active = false; // this run uses it (set by pgx_bp_run)
+  float* d_energy_partial = nullptr;  // pgx_energy scratch
+  int64_t energy_partial_floats = 0;
   size_t bigmax_smem = 0;
   unsigned int* d_bigmax_counter = nullptr;
   // lattice mode (the whole graph is one 2-D nearest-neighbour lattice block; LatticeDev)
@@ -1269,7 +1271,7 @@ void pgx_plan_destroy(pgx_plan* plan) {
   for (BipPlan& bp : plan->bips) {
     free_dev(bp.d_row_vs); free_dev(bp.d_col_vs); free_dev(bp.d_row_part); free_dev(bp.d_col_part);
   }
-  free_dev(plan->d_edge_csr); free_dev(plan->d_grid_bar);
+  free_dev(plan->d_edge_csr); free_dev(plan->d_grid_bar); free_dev(plan->d_energy_partial);
   free_dev(plan->d_rest_ptr); free_dev(plan->d_rest_edge_msg); free_dev(plan->d_part_first);
   free_dev(plan->d_part_count);
   free_workspace(plan->ws);
@@ -1766,6 +1768,63 @@ int pgx_decode(pgx_plan* plan, void* stream, int64_t batch, const float* evidenc
   if (!plan) return fail(PGX_ERR_INVALID, "null plan");
   return decode_impl(plan, static_cast<cudaStream_t>(stream), batch, evidence, ev_batched, ftov_msgs,
                      msgs_batched, nullptr, map_out, marginals_out, tie_count_out);
+}
+
+int pgx_energy(pgx_plan* plan, void* stream, int64_t batch, const float* log_potentials, int lp_batched,
+               const float* evidence, int ev_batched, const int32_t* map_states, int map_batched,
+               float* energy_out) {
+  if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+  PGX_CHECK(batch >= 1 && batch <= 65535, "batch must be in [1, 65535], got %lld", (long long)batch);
+  PGX_CHECK(energy_out != nullptr, "energy_out is null");
+  PGX_CHECK(plan->num_vars == 0 || map_states != nullptr, "map_states is null");
+  PGX_CHECK(plan->num_var_states == 0 || evidence != nullptr, "evidence is null");
+  PGX_CHECK(plan->num_potentials == 0 || log_potentials != nullptr, "log_potentials is null");
+  int rc;
+  if ((rc = check_device(plan))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int slots = 1 + int(plan->enum_blocks.size()) + 3;
+  const int64_t need = batch * slots * pgx::kEnergyChunks;
+  if (plan->energy_partial_floats < need) {
+    free_dev(plan->d_energy_partial);
+    plan->d_energy_partial = nullptr;
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&plan->d_energy_partial), size_t(need) * sizeof(float)));
+    plan->energy_partial_floats = need;
+  }
+  float* partial = plan->d_energy_partial;
+  PGX_CUDA(cudaMemsetAsync(partial, 0, size_t(need) * sizeof(float), st));  // absent factor types contribute 0
+  pgx::EnergyArgs e{};
+  e.map = map_states;
+  e.map_stride = map_batched ? plan->num_vars : 0;
+  e.ev = evidence;
+  e.ev_stride = ev_batched ? plan->num_var_states : 0;
+  e.lp = log_potentials;
+  e.lp_stride = lp_batched ? plan->num_potentials : 0;
+  e.var_first_state = plan->d_var_first_state;
+  e.vs_var = plan->d_vs_var;
+  e.edge_vs = plan->d_edge_vs;
+  const dim3 grid(pgx::kEnergyChunks, unsigned(batch));
+  if (plan->num_vars > 0) {
+    pgx::k_energy_vars<<<grid, pgx::kThreads, 0, st>>>(e, plan->num_vars, partial, slots);
+    if ((rc = check_launch(plan, "k_energy_vars"))) return rc;
+  }
+  int slot = 1;
+  for (const EnumBlockPlan& eb : plan->enum_blocks) {
+    pgx::k_energy_enum<<<grid, pgx::kThreads, 0, st>>>(e, eb.dev, partial, slots, slot++);
+    if ((rc = check_launch(plan, "k_energy_enum"))) return rc;
+  }
+  for (const LogicalPlan* lg : {&plan->or_f, &plan->and_f}) {
+    if (lg->dev.num_factors > 0) {
+      pgx::k_energy_logical<false><<<grid, pgx::kThreads, 0, st>>>(e, lg->dev, partial, slots, slot);
+      if ((rc = check_launch(plan, "k_energy_logical"))) return rc;
+    }
+    ++slot;
+  }
+  if (plan->pool_f.dev.num_factors > 0) {
+    pgx::k_energy_logical<true><<<grid, pgx::kThreads, 0, st>>>(e, plan->pool_f.dev, partial, slots, slot);
+    if ((rc = check_launch(plan, "k_energy_logical"))) return rc;
+  }
+  pgx::k_energy_sum<<<unsigned((batch + 255) / 256), 256, 0, st>>>(partial, slots * pgx::kEnergyChunks, batch, energy_out);
+  return check_launch(plan, "k_energy_sum");
 }
 
 }  // extern "C"

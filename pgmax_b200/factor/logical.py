@@ -173,8 +173,9 @@ class ORFactor(LogicalFactor):
 
   @staticmethod
   def compute_factor_energy(
-      variables: List[Hashable], vars_to_map_states: Dict[Hashable, Any]
+      variables: List[Hashable], vars_to_map_states: Dict[Hashable, Any], **kwargs
   ) -> float:
+    del kwargs  # factor_configs / log_potentials: not used (as in the reference)
     states = np.array([vars_to_map_states[v] for v in variables])
     if bool(np.any(states[:-1])) != bool(states[-1]):
       warnings.warn(
@@ -194,8 +195,9 @@ class ANDFactor(LogicalFactor):
 
   @staticmethod
   def compute_factor_energy(
-      variables: List[Hashable], vars_to_map_states: Dict[Hashable, Any]
+      variables: List[Hashable], vars_to_map_states: Dict[Hashable, Any], **kwargs
   ) -> float:
+    del kwargs  # factor_configs / log_potentials: not used (as in the reference)
     states = np.array([vars_to_map_states[v] for v in variables])
     if bool(np.all(states[:-1])) != bool(states[-1]):
       warnings.warn(

@@ -126,8 +126,9 @@ class PoolFactor(factor.Factor):
 
   @staticmethod
   def compute_factor_energy(
-      variables: List[Hashable], vars_to_map_states: Dict[Hashable, Any]
+      variables: List[Hashable], vars_to_map_states: Dict[Hashable, Any], **kwargs
   ) -> float:
+    del kwargs  # factor_configs / log_potentials: not used (as in the reference)
     states = np.array([vars_to_map_states[v] for v in variables])
     if int(np.sum(states[:-1])) != int(states[-1]):
       warnings.warn(

@@ -13,6 +13,7 @@ from pgmax_b200.infer.bp_state import BPState
 from pgmax_b200.infer.bp_state import Evidence
 from pgmax_b200.infer.bp_state import FToVMessages
 from pgmax_b200.infer.bp_state import LogPotentials
+from pgmax_b200.infer.energy import compute_energy
 from pgmax_b200.infer.inferer import decode_map_states
 from pgmax_b200.infer.inferer import Inferer
 from pgmax_b200.infer.inferer import InfererContext

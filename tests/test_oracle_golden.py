@@ -65,3 +65,44 @@ def test_rbm24_decoded_states_match_reference(num_iters):
     np.testing.assert_allclose(energy, gold[f"energy_cpu_{num_iters}"][idx], rtol=1e-5, atol=1e-5) if same else None
     mismatches += int(not same)
   assert mismatches == 0
+
+
+def test_oracle_energy_matches_reference_rbm_energies():
+  """The oracle's restatement of infer.compute_energy (pgmax/infer/energy.py:53-148) on the
+  decoded states the reference stored, against the energies the reference stored beside them
+  (benchmark/rbm_lib.py:35-61: -(h W v + bh h + bv v), i.e. the PGMax energy with zero evidence)."""
+  gold = np.load(os.path.join(GOLDEN, "rbm24.npz"))
+  for idx in range(0, 50, 7):
+    W, bh, bv = gold["W"][idx], gold["bh"][idx], gold["bv"][idx]
+    fg, hidden, visible = models.rbm_model(W, bh, bv)
+    bp = infer.BP(fg.bp_state, temperature=0.0)
+    graph = bp_oracle.graph_from_context(bp.context)
+    arrays = bp.init()
+    for num_iters in (20, 200):
+      flat = np.concatenate([gold[f"hidden_cpu_{num_iters}"][idx], gold[f"visible_cpu_{num_iters}"][idx]])
+      energy = bp_oracle.compute_energy(graph, arrays.log_potentials, arrays.evidence, flat)
+      np.testing.assert_allclose(energy, gold[f"energy_cpu_{num_iters}"][idx], rtol=1e-5, atol=1e-4)
+
+
+def test_oracle_energy_reference_test_cases():
+  """tests/test_energy.py:75-128 on the oracle: all but one potential -inf -> energy 0 for the
+  decoding [1, 1]; an invalid EnumFactor decoding -> +inf."""
+  from pgmax_b200 import fgraph, fgroup, vgroup
+  variables = vgroup.NDVarArray(num_states=2, shape=(2,))
+  fg = fgraph.FactorGraph(variable_groups=[variables])
+  fg.add_factors(fgroup.PairwiseFactorGroup(
+      variables_for_factors=[[variables[0], variables[1]]],
+      log_potential_matrix=np.array([[-np.inf, -np.inf], [-np.inf, 0.0]])))
+  bp = infer.BP(fg.bp_state, temperature=0.0)
+  graph = bp_oracle.graph_from_context(bp.context)
+  arrays = bp.init()
+  assert bp_oracle.compute_energy(graph, arrays.log_potentials, arrays.evidence, [1, 1]) == 0
+  assert bp_oracle.compute_energy(graph, arrays.log_potentials, arrays.evidence, [0, 1]) == np.inf
+  fg2 = fgraph.FactorGraph(variable_groups=[variables])
+  fg2.add_factors(fgroup.EnumFactorGroup(
+      variables_for_factors=[[variables[0], variables[1]]], factor_configs=np.zeros((1, 2), int)))
+  bp2 = infer.BP(fg2.bp_state, temperature=0.0)
+  graph2 = bp_oracle.graph_from_context(bp2.context)
+  arrays2 = bp2.init()
+  assert bp_oracle.compute_energy(graph2, arrays2.log_potentials, arrays2.evidence, [0, 0]) == 0
+  assert bp_oracle.compute_energy(graph2, arrays2.log_potentials, arrays2.evidence, [1, 0]) == np.inf
