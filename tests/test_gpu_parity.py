@@ -151,6 +151,46 @@ def test_rbm_fused_single_pass_vs_oracle(temperature, shape):
   np.testing.assert_allclose(got.ftov_msgs, want, atol=1e-5)
 
 
+@pytest.mark.parametrize("temperature", [0.0, 1.0])
+@pytest.mark.parametrize("shape", [(12, 20, 37), (6, 9, 288), (33, 70, 64)])
+def test_rbm_fused_initial_messages_and_resume(temperature, shape):
+  """Single-pass path on binary-difference storage, every way messages can enter it:
+  (a) resume: run(5) then run(7) on its (batched, normalised) output == run(12) up to the
+      summation order of the first variable sums (first iteration reads the full layout, the
+      rest the compressed one), and is deterministic;
+  (b) non-zero, un-normalised initial messages shared by the batch ([E_s] vector: normalised
+      once, broadcast compressed) == the same vector tiled to [B, E_s] (full-layout staging);
+  (c) 9 sample tiles (two groups of 8 warps, 7 of them idle) for the batch-288 shape."""
+  from pgmax_b200.infer.bp_state import BPArrays
+  nh, nv, batch = shape
+  bp, arrays = _small_rbm(nh, nv, batch, temperature, scale=0.4)
+  assert bp.context.plan.has_fused_blocks
+  one, one_d = bp.run_with_diffs(arrays, num_iters=12, damping=0.5, temperature=temperature)
+  mid = bp.run(arrays, num_iters=5, damping=0.5, temperature=temperature)
+  assert np.asarray(mid.ftov_msgs).shape == (batch, arrays.ftov_msgs.shape[-1])
+  two, two_d = bp.run_with_diffs(mid, num_iters=7, damping=0.5, temperature=temperature)
+  # (a resumed run forms its first variable sums serially from the messages, the continuous run
+  # from the previous iteration's tiled partial sums: same values up to summation order)
+  np.testing.assert_allclose(one.ftov_msgs, two.ftov_msgs, atol=1e-4)
+  np.testing.assert_allclose(np.asarray(one_d)[:, 5:], two_d, atol=1e-4)
+  again, again_d = bp.run_with_diffs(mid, num_iters=7, damping=0.5, temperature=temperature)
+  np.testing.assert_array_equal(two.ftov_msgs, again.ftov_msgs)  # deterministic
+  np.testing.assert_array_equal(two_d, again_d)
+  rng = np.random.default_rng(3)
+  init = rng.normal(size=arrays.ftov_msgs.shape[-1]).astype(np.float32)
+  shared = BPArrays(log_potentials=arrays.log_potentials, ftov_msgs=init, evidence=arrays.evidence)
+  tiled = BPArrays(log_potentials=arrays.log_potentials, ftov_msgs=np.tile(init, (batch, 1)),
+                   evidence=arrays.evidence)
+  a = bp.run(shared, num_iters=6, damping=0.5, temperature=temperature)
+  b = bp.run(tiled, num_iters=6, damping=0.5, temperature=temperature)
+  np.testing.assert_array_equal(a.ftov_msgs, b.ftov_msgs)
+  # and against the serial-order two-pass path (tree vs serial sums: tolerance, short horizon)
+  bp.context.plan.set_exact_order(True)
+  c = bp.run(shared, num_iters=6, damping=0.5, temperature=temperature)
+  bp.context.plan.set_exact_order(False)
+  np.testing.assert_allclose(a.ftov_msgs, c.ftov_msgs, atol=1e-4)
+
+
 def test_rbm_full_size_fused_properties():
   """BASELINE configs[1] shape (RBM 784 x 500) at batch 64 / 96, sum-product:
   (1) the single-pass path agrees with the serial-order two-pass path over a short horizon
