@@ -149,6 +149,12 @@ struct pgx_plan {
   // (long serial parent chains of wide OR factors hide behind the bandwidth-bound AND kernel)
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // single-pass mode, >= 16 sample tiles: the two halves of the batch run as two independent
+  // per-iteration chains on two streams, so that one half's dense-grid kernel fills the SMs
+  // while the other half is in its short kernels (unary blocks, k_var_reduce) or in the tail of
+  // its own dense-grid launch
+  cudaStream_t half = nullptr;
+  cudaEvent_t ev_half_fork = nullptr, ev_half_join = nullptr;
   int aux_group = 0;          // -1: OR group on aux, -2: AND group, 0: none
   bool aux_needs_s = false;   // that group reads the variable-sum array
   // merged max-product launch over all large sorted pairwise groups (k_enum_big_maxprod_all)
@@ -584,7 +590,8 @@ int prof_mark(pgx_plan* plan, cudaStream_t st, int id) {
 template <bool kSum>
 int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::View lp, const float* S,
                const float* m_old, float* m_new, const pgx::RunArgs& a, bool fused, bool lpull, pgx::View ev,
-               cudaStream_t aux, const float* c_old = nullptr, float* c_new = nullptr, bool lbin = false) {
+               cudaStream_t aux, const float* c_old = nullptr, float* c_new = nullptr, bool lbin = false,
+               float* part_override = nullptr) {
   int rc;
   const bool merged_max = !kSum && plan->bigmax_units > 0 && !(plan->disabled_paths & PGX_PATH_MERGED_MAX);
   if (merged_max) {
@@ -646,7 +653,8 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       const int64_t src_rows = in_full ? a.Es : plan->c_rows;
 #define PGX_BIP_LAUNCH(DELTA, FULL)                                                                       \
   pgx::k_enum_pw2_bip<kSum, TJ, DELTA, FULL><<<unsigned(grid), warps * 32, smem, st>>>(                    \
-      mp.batch, groups, g, lp.p, S, src, src_rows, c_new, plan->c_rows, plan->ws.part, plan->part_rows, a)
+      mp.batch, groups, g, lp.p, S, src, src_rows, c_new, plan->c_rows,                                    \
+      part_override ? part_override : plan->ws.part, plan->part_rows, a)
       if (a.deltas != nullptr) {
         if (in_full) PGX_BIP_LAUNCH(true, true); else PGX_BIP_LAUNCH(true, false);
       } else {
@@ -1166,6 +1174,10 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       }
       plan->part_rows = rows;
       plan->bips.resize(grids.size());
+      if (cudaStreamCreateWithFlags(&plan->half, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&plan->ev_half_fork, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&plan->ev_half_join, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(PGX_ERR_CUDA, "creating the half-batch stream failed"));
       if (plan->aux == nullptr && plan->enum_blocks.size() > grids.size()) {
         if (cudaStreamCreateWithFlags(&plan->aux, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
@@ -1268,6 +1280,9 @@ void pgx_plan_destroy(pgx_plan* plan) {
   if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
   if (plan->ev_join) cudaEventDestroy(plan->ev_join);
   if (plan->aux) cudaStreamDestroy(plan->aux);
+  if (plan->ev_half_fork) cudaEventDestroy(plan->ev_half_fork);
+  if (plan->ev_half_join) cudaEventDestroy(plan->ev_half_join);
+  if (plan->half) cudaStreamDestroy(plan->half);
   for (BipPlan& bp : plan->bips) {
     free_dev(bp.d_row_vs); free_dev(bp.d_col_vs); free_dev(bp.d_row_part); free_dev(bp.d_col_part);
   }
@@ -1485,7 +1500,11 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   // read the same old messages and sums and write disjoint message ranges
   const bool side_blocks = fused && plan->enum_blocks.size() > plan->bips.size() && plan->or_f.dev.num_factors == 0 &&
                            plan->and_f.dev.num_factors == 0 && plan->pool_f.dev.num_factors == 0;
-  const cudaStream_t aux = ((lpull || side_blocks) && plan->aux != nullptr && !(plan->disabled_paths & PGX_PATH_AUX_STREAM))
+  // half-batch pipeline (see pgx_plan::half); not while the profiling events bracket whole launches
+  const bool split = fused && mp.nbt >= 16 && plan->half != nullptr && !plan->profiling &&
+                     !(plan->disabled_paths & PGX_PATH_HALF_BATCH);
+  const cudaStream_t aux = ((lpull || (side_blocks && !split)) && plan->aux != nullptr &&
+                            !(plan->disabled_paths & PGX_PATH_AUX_STREAM))
                                ? plan->aux : nullptr;
   const bool aux_after_s = lpull ? plan->aux_needs_s : true;
   bool pull = false;
@@ -1688,6 +1707,45 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     // fused blocks keep their messages compressed (ws.cA / ws.cB) after the first iteration
     const float* c_old = (fused && (it > 0 || shared_init)) ? ((it & 1) ? ws.cA : ws.cB) : nullptr;
     float* c_new = fused ? ((it & 1) ? ws.cB : ws.cA) : nullptr;
+    if (split) {
+      if (it == 0) {  // the first variable sums (whole batch, main stream) feed both halves
+        PGX_CUDA(cudaEventRecord(plan->ev_half_fork, st));
+        PGX_CUDA(cudaStreamWaitEvent(plan->half, plan->ev_half_fork, 0));
+      }
+      for (int h = 0; h < 2; ++h) {
+        const cudaStream_t sh = h ? plan->half : st;
+        const int tile0 = h ? mp.nbt / 2 : 0, nt = h ? mp.nbt - mp.nbt / 2 : mp.nbt / 2;
+        const pgx::BatchMap mph{int(std::min<int64_t>(batch - int64_t(tile0) * 32, int64_t(nt) * 32)), 5, nt};
+        auto off = [&](int64_t rows) { return size_t(tile0) * size_t(rows) * 32; };
+        pgx::RunArgs ah = a;
+        if (deltas) ah.deltas = deltas + size_t(tile0) * 32 * num_iters;
+        pgx::View evh = ev;
+        if (ev.kind == 1) evh.p += off(Vs);
+        float* S_h = ws.S + off(Vs);
+        float* part_h = ws.part + off(plan->part_rows);
+        const float* c_old_h = c_old ? c_old + off(plan->c_rows) : nullptr;
+        if (temperature == 0.f)
+          rc = launch_f2v<false>(plan, sh, mph, lp, S_h, cur + off(Es), dst + off(Es), ah, fused, false, evh, nullptr,
+                                 c_old_h, c_new + off(plan->c_rows), false, part_h);
+        else
+          rc = launch_f2v<true>(plan, sh, mph, lp, S_h, cur + off(Es), dst + off(Es), ah, fused, false, evh, nullptr,
+                                c_old_h, c_new + off(plan->c_rows), false, part_h);
+        if (rc) return rc;
+        if (it + 1 < num_iters) {
+          pgx::k_var_reduce<<<grid_for(plan, mph, Vs), pgx::kThreads, 0, sh>>>(
+              mph, Vs, Es, plan->part_rows, plan->d_vs_var, plan->d_var_first_state, plan->d_rest_ptr,
+              plan->d_rest_edge_msg, plan->d_part_first, plan->d_part_count, evh, dst + off(Es), part_h, S_h);
+          if ((rc = check_launch(plan, "k_var_reduce"))) return rc;
+        }
+      }
+      if (it == num_iters - 1) {
+        PGX_CUDA(cudaEventRecord(plan->ev_half_join, plan->half));
+        PGX_CUDA(cudaStreamWaitEvent(st, plan->ev_half_join, 0));
+      }
+      nxt = (dst == bufA) ? bufB : bufA;
+      cur = dst;
+      continue;
+    }
     if (temperature == 0.f)
       rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new, lbin);
     else

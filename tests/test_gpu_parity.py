@@ -191,6 +191,26 @@ def test_rbm_fused_initial_messages_and_resume(temperature, shape):
   np.testing.assert_allclose(a.ftov_msgs, c.ftov_msgs, atol=1e-4)
 
 
+@pytest.mark.parametrize("temperature", [0.0, 1.0])
+def test_rbm_fused_half_batch_pipeline_is_bit_identical(temperature):
+  """>= 16 sample tiles: the two halves of the batch run as two pipelined chains on two streams
+  (PGX_PATH_HALF_BATCH).  Samples are independent, so every message and delta must equal the
+  single-chain run bit for bit; 17 tiles = halves of 8 and 9 tiles, the last one partial."""
+  bp, arrays = _small_rbm(6, 9, 530, temperature, scale=0.4)
+  plan = bp.context.plan
+  got, got_d = bp.run_with_diffs(arrays, num_iters=9, damping=0.5, temperature=temperature)
+  plan.disable_paths(plan.PATH_HALF_BATCH)
+  ref, ref_d = bp.run_with_diffs(arrays, num_iters=9, damping=0.5, temperature=temperature)
+  plan.disable_paths(0)
+  np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
+  np.testing.assert_array_equal(got_d, ref_d)
+  one = bp.run(arrays, num_iters=1, damping=0.5, temperature=temperature)
+  plan.disable_paths(plan.PATH_HALF_BATCH)
+  one_ref = bp.run(arrays, num_iters=1, damping=0.5, temperature=temperature)
+  plan.disable_paths(0)
+  np.testing.assert_array_equal(one.ftov_msgs, one_ref.ftov_msgs)
+
+
 def test_rbm_full_size_fused_properties():
   """BASELINE configs[1] shape (RBM 784 x 500) at batch 64 / 96, sum-product:
   (1) the single-pass path agrees with the serial-order two-pass path over a short horizon
