@@ -372,7 +372,7 @@ def main():
   plan.set_exact_order(args.exact_order)
   plan.disable_paths(args.disable_paths)
   batch = host.batch_size or 1
-  put = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+  put = lambda a: torch.from_numpy(np.array(a, dtype=np.float32, order="C")).to(dev)
   dev_arrays = BPArrays(log_potentials=put(host.log_potentials), ftov_msgs=put(host.ftov_msgs),
                         evidence=put(host.evidence))
   es = plan.num_edge_states
@@ -410,7 +410,7 @@ def main():
   checksum = float(out.ftov_msgs.float().abs().max().item())
 
   # ---- end to end through the C ABI with host buffers ---------------------------------------
-  pin = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).pin_memory()
+  pin = lambda a: torch.from_numpy(np.array(a, dtype=np.float32, order="C")).pin_memory()
   h_lp, h_ev = pin(host.log_potentials), pin(host.evidence)
   h_map = torch.empty((batch, plan.num_vars), dtype=torch.int32).pin_memory()
   h_ties = torch.empty((batch,), dtype=torch.int32).pin_memory()
@@ -494,6 +494,10 @@ def main():
                      # used (binary-difference storage halves the message bytes): <= 1 by construction
                      "storage": ("binary-difference, 1 float per two-state edge between iterations"
                                  if saved else "reference layout, 1 float per edge-state"),
+                     "note": ("frac uses SURVEY 8(d)'s algorithmic bytes (two floats read + written per two-state "
+                              "edge); the kernels keep ONE float per such edge between iterations, bit-identical "
+                              "values, so frac > 1 is expected - layout_frac is the fraction of peak on the bytes "
+                              "actually moved, traffic the DRAM bytes ncu measured per launch") if saved else None,
                      "layout_bytes_per_iter": layout_bytes,
                      "layout_frac": (layout_bytes * (kernel_bytes / bytes_iter) / (kernel_ms * 1e-3) / 1e9 / peak)
                      if n_prof else None,

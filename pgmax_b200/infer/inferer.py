@@ -49,7 +49,10 @@ class DeviceBuffers:
     if _is_torch(arr):
       t = arr.to(device=self.device, dtype=torch.float32)
     else:
-      t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(self.device)
+      host = np.ascontiguousarray(arr, dtype=np.float32)
+      if not host.flags.writeable:  # BPArrays are read-only views; torch wants a writable buffer
+        host = host.copy()
+      t = torch.from_numpy(host).to(self.device)
     return t.contiguous()
 
   def out(self, tensor):
