@@ -1529,7 +1529,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     const dim3 grid(unsigned((g.N + pgx::kLatTC - 1) / pgx::kLatTC), unsigned((g.R + pgx::kLatTR - 1) / pgx::kLatTR));
     // large lattices stream through the persistent TMA kernel, small ones (a few tiles per SM)
     // keep the one-tile-per-CTA kernel
-    const int64_t num_tiles = int64_t(grid.x) * grid.y;
+    const int64_t num_tiles = int64_t((g.N + pgx::kLsTC - 1) / pgx::kLsTC) * ((g.R + pgx::kLsTR - 1) / pgx::kLsTR);  // streaming tiles
     const bool stream = num_tiles >= 4 * int64_t(plan->num_sms) && !(plan->disabled_paths & PGX_PATH_LATTICE_STREAM);
     const bool want_delta = deltas != nullptr;
     const int variant = (temperature == 0.f ? 0 : 2) + (want_delta ? 1 : 0);

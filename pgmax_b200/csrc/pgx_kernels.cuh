@@ -982,15 +982,21 @@ __device__ __forceinline__ void fence_proxy_async() {
 //   * 16 consumer warps wait for the tile, form the variable sums, update the factors IN
 //     PLACE in shared memory and hand the tile back; two stages, so the loads of tile i + 1
 //     and the stores of tile i - 1 overlap the arithmetic of tile i.
-// Shared memory: 2 x (message tile 18 x 66 cells + potential tile 16 x 64 cells) x 32 B
-// + 2 sum buffers = 156 KB.
+// Shared memory: 2 x (message tile 6 x 258 cells + potential tile 4 x 256 cells) x 32 B
+// + 2 sum buffers = 185 KB.
 // ---------------------------------------------------------------------------
 constexpr int kLsConsumers = 512;               // 16 warps
 constexpr int kLsThreads = kLsConsumers + 32;   // + producer warp
+// Tile shape: 4 rows x 256 columns, two stages.  The producer's cost is the NUMBER of bulk
+// copies (one per tile row and array, ~2 KB each at 64 columns), not their bytes: measured on
+// Ising 8192^2 (ms per iteration) 16x64x2 stages 1.73, 16x48x3 2.10, 8x64x4 2.08, 8x128x2 1.45,
+// 6x160x2 1.42, 4x256x2 1.415, 4x192x3 1.50, 2x512x2 1.45 - wide, flat tiles (8 KB copies) win;
+// their extra halo rows (6 loaded per 4 updated) are L2 hits, the CTAs sweep the grid together.
 constexpr int kLsStages = 2;
-constexpr int kLsMsgF4 = kLatMR * kLatMC * 2;   // float4 per message stage
-constexpr int kLsLpF4 = kLatTR * kLatTC * 2;    // float4 per potential stage
-constexpr int kLsSumF2 = (kLatTR + 1) * (kLatTC + 1);
+constexpr int kLsTR = 4, kLsTC = 256, kLsMR = kLsTR + 2, kLsMC = kLsTC + 2;
+constexpr int kLsMsgF4 = kLsMR * kLsMC * 2;   // float4 per message stage
+constexpr int kLsLpF4 = kLsTR * kLsTC * 2;    // float4 per potential stage
+constexpr int kLsSumF2 = (kLsTR + 1) * (kLsTC + 1);
 __host__ __device__ constexpr size_t lattice_stream_smem_bytes() {
   return size_t(kLsStages) * (kLsMsgF4 + kLsLpF4) * sizeof(float4) + size_t(2) * kLsSumF2 * sizeof(float2) +
          2 * kLsStages * sizeof(uint64_t);
@@ -1004,7 +1010,7 @@ template <bool kSumProduct, bool kDelta>
 __global__ void __launch_bounds__(kLsThreads, 1)
 k_lattice_stream(LatticeDev g, const float* __restrict__ ev, const float* __restrict__ lp,
                  const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
-  constexpr int TR = kLatTR, TC = kLatTC, MC = kLatMC;
+  constexpr int TR = kLsTR, TC = kLsTC, MC = kLsMC;
   extern __shared__ __align__(128) unsigned char ls_raw[];
   float4* msg_s = reinterpret_cast<float4*>(ls_raw);                       // [stage][MR][MC][2]
   float4* lp_s = msg_s + kLsStages * kLsMsgF4;                             // [stage][TR][TC][2]
@@ -1035,7 +1041,7 @@ k_lattice_stream(LatticeDev g, const float* __restrict__ ev, const float* __rest
       const int64_t tile = blockIdx.x + i * gridDim.x;
       const int ty = int(tile / tiles_x), tx = int(tile - int64_t(ty) * tiles_x);
       const int l0 = ty * TR, j0 = tx * TC;
-      const int stage = int(i & 1);
+      const int stage = int(i % kLsStages);
       float4* ms = msg_s + stage * kLsMsgF4;
       float4* ls = lp_s + stage * kLsLpF4;
       const int ncols = min(TC + 1, N - j0);        // cells from column j0 on (incl. the right halo if inside)
@@ -1043,7 +1049,7 @@ k_lattice_stream(LatticeDev g, const float* __restrict__ ev, const float* __rest
       const int lcols = min(TC, N - j0);
       // rows: sm row rr <-> lattice row l0 - 1 + rr
       int l = l0 - 1 + lane;
-      bool row_ok = lane < kLatMR;
+      bool row_ok = lane < kLsMR;
       if (torus) { row_ok = row_ok && l <= R; l = l < 0 ? R - 1 : (l == R ? 0 : l); }
       else row_ok = row_ok && l >= 0 && l < R;
       const bool lp_ok = lane < TR && l0 + lane < R;
@@ -1063,12 +1069,13 @@ k_lattice_stream(LatticeDev g, const float* __restrict__ ev, const float* __rest
       if (lp_ok)
         bulk_g2s(ls + lane * TC * 2, lp4 + (int64_t(l0 + lane) * N + j0) * 2, uint32_t(lcols) * 32u, &full[stage]);
     };
-    if (my_tiles > 0) load_tile(0);
+    for (int s = 0; s < kLsStages - 1; ++s)
+      if (s < my_tiles) load_tile(s);
     for (int64_t i = 0; i < my_tiles; ++i) {
-      // the other stage's previous stores have been drained below: refill it with tile i + 1
-      if (i + 1 < my_tiles) load_tile(i + 1);
-      const int stage = int(i & 1);
-      mbar_wait(&done[stage], uint32_t(i >> 1) & 1u);
+      // the stage of tile i - 1 has been drained below: refill it with tile i + kLsStages - 1
+      if (i + kLsStages - 1 < my_tiles) load_tile(i + kLsStages - 1);
+      const int stage = int(i % kLsStages);
+      mbar_wait(&done[stage], uint32_t(i / kLsStages) & 1u);
       const int64_t tile = blockIdx.x + i * gridDim.x;
       const int ty = int(tile / tiles_x), tx = int(tile - int64_t(ty) * tiles_x);
       const int l0 = ty * TR, j0 = tx * TC;
@@ -1091,7 +1098,7 @@ k_lattice_stream(LatticeDev g, const float* __restrict__ ev, const float* __rest
     const int64_t tile = blockIdx.x + i * gridDim.x;
     const int ty = int(tile / tiles_x), tx = int(tile - int64_t(ty) * tiles_x);
     const int l0 = ty * TR, j0 = tx * TC;
-    const int stage = int(i & 1);
+    const int stage = int(i % kLsStages);
     float4* sm = msg_s + stage * kLsMsgF4;
     const float4* lq = lp_s + stage * kLsLpF4;
     float2* Ss = sum_s + (i & 1) * kLsSumF2;
@@ -1110,7 +1117,7 @@ k_lattice_stream(LatticeDev g, const float* __restrict__ ev, const float* __rest
         e[k] = __ldg(ev2 + (int64_t(l) * N + j));
       }
     }
-    mbar_wait(&full[stage], uint32_t(i >> 1) & 1u);
+    mbar_wait(&full[stage], uint32_t(i / kLsStages) & 1u);
     // ---- variable sums (same order as k_lattice) -------------------------------------------
 #pragma unroll
     for (int k = 0; k < kVars; ++k) {
