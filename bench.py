@@ -169,7 +169,7 @@ def run_ising_big(args):
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": bytes_iter / iter_s / 1e9 / world, "peak": peak, "unit": "GB/s",
                      "frac": bytes_iter / iter_s / 1e9 / world / peak, "traffic": None,
-                     "kernel": "whole iteration (k_var_sums + k_enum_pw2), per GPU",
+                     "kernel": "whole iteration (k_lattice_stream + the halo exchange when N > 1), per GPU",
                      "algorithmic_bytes_per_launch": bytes_iter // world, "peak_source": peak_src,
                      "iter_ms": iter_s * 1e3},
         "checksum_max_abs_msg": float(msgs.abs().max().item()),
