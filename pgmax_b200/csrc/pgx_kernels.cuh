@@ -1366,12 +1366,7 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
 
   if (threadIdx.x < kBipWarps * kStages) mbar_init(&bars[threadIdx.x], 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  for (int t = threadIdx.x; t < (i1 - i0) * TJ * 4; t += blockDim.x) {
-    const int r = t / (TJ * 4), c = t - r * (TJ * 4);
-    lp_s[t] = (c < nj * 4) ? clip_lp(lp[g.first_pot + 4 * (int64_t(i0 + r) * g.J + j0) + c]) : 0.f;
-  }
   __syncthreads();
-  if (!active) return;
 
   float* my_ring = ring + w * kStages * kRowFloats;
   uint64_t* my_bar = bars + w * kStages;
@@ -1383,7 +1378,7 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
   auto in_off = [&](int i) { return in_base + (int64_t(i) * g.J + j0) * (kIn * 32); };
   auto out_off = [&](int i) { return out_base + (int64_t(i) * g.J + j0) * (2 * 32); };
   const int nrows = i1 - i0;
-  if (lane == 0) {
+  if (active && lane == 0) {
 #pragma unroll
     for (int s = 0; s < kStages - 1; ++s)
       if (s < nrows) {
@@ -1391,6 +1386,13 @@ k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp
         bulk_g2s(my_ring + s * kRowFloats, m_old + in_off(i0 + s), in_bytes, &my_bar[s]);
       }
   }
+  // the chunk's potentials are staged while the first message rows are already in flight
+  for (int t = threadIdx.x; t < (i1 - i0) * TJ * 4; t += blockDim.x) {
+    const int r = t / (TJ * 4), c = t - r * (TJ * 4);
+    lp_s[t] = (c < nj * 4) ? clip_lp(lp[g.first_pot + 4 * (int64_t(i0 + r) * g.J + j0) + c]) : 0.f;
+  }
+  __syncthreads();
+  if (!active) return;
 
   const float* SL = S + (int64_t(bt) * a.Vs) * 32 + lane;
   float* PL = part + (int64_t(bt) * part_rows) * 32 + lane;
