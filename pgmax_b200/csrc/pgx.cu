@@ -1368,7 +1368,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   PGX_CHECK(batch >= 1 && batch < (1 << 24), "batch must be in [1, 2^24), got %lld", (long long)batch);
   PGX_CHECK(num_iters >= 1, "num_iters must be >= 1, got %d", num_iters);
   PGX_CHECK(temperature >= 0.f, "temperature must be >= 0");
-  PGX_CHECK(ftov_out != nullptr, "ftov_out is null");
+  PGX_CHECK(ftov_out != nullptr || plan->num_edge_states == 0, "ftov_out is null");
   PGX_CHECK(plan->num_var_states == 0 || evidence != nullptr, "evidence is null");
   PGX_CHECK(plan->num_potentials == 0 || log_potentials != nullptr, "log_potentials is null");
   int rc;
@@ -1387,9 +1387,12 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
                      Es < (int64_t(1) << 26) && Vs < (int64_t(1) << 26);
   // ... with the messages in binary-difference storage (such a graph has only two-state edges)
   const bool lbin = lpull && !(plan->disabled_paths & PGX_PATH_LOGICAL_BIN) && Es == 2 * plan->num_edges;
+  if (Es == 0) {  // a graph without factors: nothing to update, every delta is 0
+    if (deltas) PGX_CUDA(cudaMemsetAsync(deltas, 0, size_t(batch) * num_iters * sizeof(float), static_cast<cudaStream_t>(stream)));
+    return PGX_OK;
+  }
   if ((rc = ensure_workspace(plan, batch, evT, lpT, fused, lbin))) return rc;
   Workspace& ws = plan->ws;
-  if (Es == 0) return PGX_OK;
 
   // ---- inputs -> tile-blocked workspace ----------------------------------------------------
   pgx::View ev{evidence, Vs, 0}, lp{log_potentials, C, 0};
