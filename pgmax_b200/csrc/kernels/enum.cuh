@@ -1,0 +1,552 @@
+// pgx kernels - K2b / K2c: general EnumFactors, small and RCN-size.  Part of pgx_kernels.cuh (included in this order).
+#pragma once
+
+#include "dense_grid.cuh"
+
+namespace pgx {
+
+// Device-side description of one enum block (see pgx_enum_block in pgx.h).
+// cfg_es[k*arity + a]: edge-state offset (within the factor's message span) that
+// configuration k assigns to variable a.  t_ptr/t_k: for every edge-state offset
+// the ascending list of configurations containing it (the transpose of cfg_es,
+// which the reference never builds; it scatter-maxes over the R expanded rows).
+struct EnumBlockDev {
+  int64_t num_factors;
+  int64_t first_edge, first_msg, first_pot;
+  int32_t arity, num_configs, ns;  // ns = edge-states per factor
+  const int32_t* cfg_es;
+  const int32_t* t_ptr;
+  const int32_t* t_k;
+  const int32_t* edge_off;  // [arity + 1]
+  // per-factor offsets when the block merges several descriptor blocks (else null and the
+  // factors are the arithmetic progression first_* + f * stride)
+  const int32_t* fac_edge;
+  const int32_t* fac_msg;
+  const int32_t* fac_pot;
+  // arity 2 and the configurations are sorted by the first variable's state: the configs of
+  // state a of variable 0 are the contiguous range [t_ptr[a], t_ptr[a + 1]) of k
+  int32_t sorted0;
+  __device__ __forceinline__ int64_t msg_base(int64_t f) const { return fac_msg ? fac_msg[f] : first_msg + f * ns; }
+  __device__ __forceinline__ int64_t edge_base(int64_t f) const { return fac_edge ? fac_edge[f] : first_edge + f * arity; }
+  __device__ __forceinline__ int64_t pot_base(int64_t f) const { return fac_pot ? fac_pot[f] : first_pot + f * num_configs; }
+};
+
+// ---------------------------------------------------------------------------
+// K2b: EnumFactor update, small factors (ns <= 64): one thread per (factor,
+// sample); q staged in a per-thread array, edge-state by edge-state walk of
+// the transposed configuration lists.  Exact ascending-config order for both
+// the max and the sum.
+// ---------------------------------------------------------------------------
+template <bool kSumProduct>
+__global__ void __launch_bounds__(kThreads)
+k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
+             const float* __restrict__ S, const float* __restrict__ m_old,
+             float* __restrict__ m_new, RunArgs a) {
+  UnitLoop L = unit_loop(mp, blk.num_factors);
+  if (!L.b_ok) return;
+  float dmax = 0.f;
+  const int sh = mp.bx_log;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const LaneView lpL = lane_view(lp, mp, L.b);
+  const float T = a.T;
+  float q[kSmallMaxNS];
+  float nv[kSmallMaxNS];
+  for (int64_t f = L.u; f < L.u_end; f += L.step) {
+    const int64_t mbase = blk.msg_base(f);
+    const int64_t ebase = blk.edge_base(f);
+    const int64_t pbase = blk.pot_base(f);
+    for (int e = 0; e < blk.arity; ++e) {
+      const int64_t vs = edge_vs[ebase + e];
+      for (int s = blk.edge_off[e]; s < blk.edge_off[e + 1]; ++s)
+        q[s] = SL[(vs + s - blk.edge_off[e]) << sh] - mo[(mbase + s) << sh];
+    }
+    for (int s = 0; s < blk.ns; ++s) {
+      const int j0 = blk.t_ptr[s], j1 = blk.t_ptr[s + 1];
+      float M = -INFINITY;
+      for (int j = j0; j < j1; ++j) {
+        const int k = blk.t_k[j];
+        float sk = 0.f;
+        for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
+        sk += clip_lp(lpL.at(pbase + k));
+        M = fmaxf(M, sk);
+      }
+      float val = M;
+      if (kSumProduct) {
+        float sum = 0.f;
+        for (int j = j0; j < j1; ++j) {
+          const int k = blk.t_k[j];
+          float sk = 0.f;
+          for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
+          sk += clip_lp(lpL.at(pbase + k));
+          sum += expf((sk - M) / T);
+        }
+        val = T * logf(sum) + M;
+      }
+      nv[s] = damp(mo[(mbase + s) << sh], val - q[s], a.d, a.one_minus_d);
+    }
+    for (int e = 0; e < blk.arity; ++e) {
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      float mx = -INFINITY;
+      for (int s = s0; s < s1; ++s) mx = fmaxf(mx, nv[s]);
+      for (int s = s0; s < s1; ++s) {
+        const float out = fmaxf(nv[s] - mx, kMsgNegInf);
+        const int64_t idx = (mbase + s) << sh;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
+      }
+    }
+  }
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
+// K2c: EnumFactor update, large factors (RCN: 2 x 625 states, up to 375 769
+// configurations): one CTA per (factor, sample).  q and the damped values live
+// in shared memory; threads own edge-states and walk their configuration lists
+// (exact order, no atomics); per-edge max by block reduction.
+// Dynamic smem: 2 * ns floats + 32 floats.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float block_max(float v, float* red) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float r = -INFINITY;
+  for (int i = 0; i < nw; ++i) r = fmaxf(r, red[i]);
+  return r;
+}
+
+template <bool kSumProduct>
+__global__ void __launch_bounds__(kThreads)
+k_enum_big(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
+           const float* __restrict__ S, const float* __restrict__ m_old,
+           float* __restrict__ m_new, RunArgs a) {
+  extern __shared__ float smem[];
+  float* q = smem;
+  float* nv = smem + blk.ns;
+  float* red = smem + 2 * blk.ns;
+  const int sh = mp.bx_log;
+  const float T = a.T;
+  const int64_t total = blk.num_factors * mp.batch;
+  for (int64_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    const int64_t f = unit / mp.batch;
+    const int b = int(unit - f * mp.batch);
+    const int64_t moff = lane_off(mp, a.Es, b);
+    const float* mo = m_old + moff;
+    float* mn = m_new + moff;
+    const float* SL = S + lane_off(mp, a.Vs, b);
+    const LaneView lpL = lane_view(lp, mp, b);
+    const int64_t mbase = blk.msg_base(f);
+    const int64_t ebase = blk.edge_base(f);
+    const int64_t pbase = blk.pot_base(f);
+    __syncthreads();  // previous unit done with q / nv
+    for (int e = 0; e < blk.arity; ++e) {
+      const int64_t vs = edge_vs[ebase + e];
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x)
+        q[s] = SL[(vs + s - s0) << sh] - mo[(mbase + s) << sh];
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < blk.ns; s += blockDim.x) {
+      const int j0 = blk.t_ptr[s], j1 = blk.t_ptr[s + 1];
+      float M = -INFINITY;
+      for (int j = j0; j < j1; ++j) {
+        const int k = blk.t_k[j];
+        float sk = 0.f;
+        for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
+        sk += clip_lp(lpL.at(pbase + k));
+        M = fmaxf(M, sk);
+      }
+      float val = M;
+      if (kSumProduct) {
+        float sum = 0.f;
+        for (int j = j0; j < j1; ++j) {
+          const int k = blk.t_k[j];
+          float sk = 0.f;
+          for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
+          sk += clip_lp(lpL.at(pbase + k));
+          sum += expf((sk - M) / T);
+        }
+        val = T * logf(sum) + M;
+      }
+      nv[s] = damp(mo[(mbase + s) << sh], val - q[s], a.d, a.one_minus_d);
+    }
+    float dmax = 0.f;
+    for (int e = 0; e < blk.arity; ++e) {
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      __syncthreads();
+      float mx = -INFINITY;
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) mx = fmaxf(mx, nv[s]);
+      mx = block_max(mx, red);
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const float out = fmaxf(nv[s] - mx, kMsgNegInf);
+        const int64_t idx = (mbase + s) << sh;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
+      }
+    }
+    if (a.deltas != nullptr) {
+      dmax = block_max(dmax, red);
+      if (threadIdx.x == 0) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2c-max: max-product update of large PAIRWISE factors whose configuration table is
+// sorted by the first variable's state (RCN lateral factors, examples/rcn.ipynb cell
+// 24-26).  Configuration-major: every valid configuration is visited ONCE per
+// iteration (the reference visits each twice, through 5 expanded R-sized arrays):
+// a warp owns a state a of variable 0, its lanes stride the contiguous config range of
+// a (coalesced reads of the table and of the potentials), s_k = (q_a + q_b) + lp_k,
+// the max over k for a by warp shuffle, for the partner states b by an ordered-int
+// atomicMax in shared memory.  max is order-independent, so the result is bit-identical
+// to the edge-state-major kernel and to the oracle.
+// Dynamic smem: 2 * ns floats + 32 floats.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_float_shared(float* addr, float v) {
+  if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_enum_big_maxprod(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
+                   const float* __restrict__ S, const float* __restrict__ m_old,
+                   float* __restrict__ m_new, RunArgs a) {
+  extern __shared__ float smem[];
+  float* q = smem;
+  float* M = smem + blk.ns;
+  float* red = smem + 2 * blk.ns;
+  const int sh = mp.bx_log;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int n0 = blk.edge_off[1];  // states of variable 0
+  const int64_t total = blk.num_factors * mp.batch;
+  for (int64_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    const int64_t f = unit / mp.batch;
+    const int b = int(unit - f * mp.batch);
+    const int64_t moff = lane_off(mp, a.Es, b);
+    const float* mo = m_old + moff;
+    float* mn = m_new + moff;
+    const float* SL = S + lane_off(mp, a.Vs, b);
+    const LaneView lpL = lane_view(lp, mp, b);
+    const int64_t mbase = blk.msg_base(f), ebase = blk.edge_base(f), pbase = blk.pot_base(f);
+    __syncthreads();  // previous unit done with q / M
+    for (int e = 0; e < 2; ++e) {
+      const int64_t vs = edge_vs[ebase + e];
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        q[s] = SL[(vs + s - s0) << sh] - mo[(mbase + s) << sh];
+        M[s] = -INFINITY;
+      }
+    }
+    __syncthreads();
+    for (int s = warp; s < n0; s += nwarp) {
+      const int k0 = blk.t_ptr[s], k1 = blk.t_ptr[s + 1];
+      const float qa = q[s];
+      float best = -INFINITY;
+      for (int k = k0 + lane; k < k1; k += 32) {
+        const int es_b = blk.cfg_es[2 * k + 1];
+        const float sk = (qa + q[es_b]) + clip_lp(lpL.at(pbase + k));
+        best = fmaxf(best, sk);
+        atomic_max_float_shared(&M[es_b], sk);
+      }
+      for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (lane == 0) M[s] = best;
+    }
+    __syncthreads();
+    float dmax = 0.f;
+    for (int e = 0; e < 2; ++e) {
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      float mx = -INFINITY;
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        // f = M - q, damped; M is reused to hold the damped value
+        const float nvs = damp(mo[(mbase + s) << sh], M[s] - q[s], a.d, a.one_minus_d);
+        M[s] = nvs;
+        mx = fmaxf(mx, nvs);
+      }
+      mx = block_max(mx, red);
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const float out = fmaxf(M[s] - mx, kMsgNegInf);
+        const int64_t idx = (mbase + s) << sh;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
+      }
+    }
+    if (a.deltas != nullptr) {
+      dmax = block_max(dmax, red);
+      if (threadIdx.x == 0) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2c-max2: the same update without shared-memory atomics (ATOMS on spread addresses costs
+// ~2 cycles per LANE on this part, which made the kernel above atomics-bound), for ALL such
+// groups of the graph in ONE launch.
+//   * LANE-PER-STATE: lane l of lane-group g owns state a = 32 g + l of the first variable and
+//     walks a's configuration list; its maximum over the list (the a-side message) is a plain
+//     running maximum in a register - no warp reduction, no list logic in the kernel;
+//   * the plan arranges the walk in ROUNDS (one configuration per lane) such that the partner
+//     states b of a round fall into pairwise distinct shared-memory banks (a lane takes any
+//     of its remaining configurations whose bank is free, else idles that round: distinct b
+//     AND conflict-free accesses), so every warp keeps a PRIVATE copy Mw[warp][b] of the partner-side maxima and
+//     updates it with a plain read-max-write (__syncwarp between rounds); the copies are
+//     max-reduced once per factor.  max is order-independent: bit-identical to the other
+//     kernels and to the oracle;
+//   * one 4-byte schedule entry (k | b << 20, coalesced, L2-resident, shared by all factors of
+//     the group) and the 4-byte potential (HBM; a lane streams its own list, so a fetched
+//     sector serves its next 8 rounds out of L1) per configuration; ~20 instructions per
+//     32 configurations;
+//   * loads run one trip (kBigTrip rounds) ahead of their use in registers;
+//   * work units (factor, sample) of all groups are sorted by configuration count
+//     (descending) and handed out through an atomic counter: the launch ends balanced.
+// Dynamic smem: (2 ns + nwarps * (n1 + 32) + 32) floats of the largest group.
+// ---------------------------------------------------------------------------
+constexpr int kBigWarps = kThreads / 32;
+struct BigMaxGroup {
+  EnumBlockDev blk;
+  const uint32_t* rounds;    // [num_rounds][32] k | partner state << 20, 0xffffffff = idle
+  const int32_t* round_ptr;  // [num_groups + 1]
+  int32_t num_groups;        // lane-groups = ceil(states of variable 0 / 32)
+  // permuted-potential path: the run starts by copying every factor's (clipped) potentials into
+  // round order, lpR[perm_base + f * 32 * num_rounds + 32 * round + lane] (-inf at idle
+  // entries), so that the hot loop's two loads per configuration - the potential and the
+  // 2-byte partner state - are both coalesced and the loop needs no select at all
+  const uint32_t* rounds_b;  // [num_rounds / 2][32] partner states of rounds 2p, 2p + 1 (16 bits each);
+                             // idle: n1 + j, a dummy slot in a bank no lane of the round uses.  Every lane-group has an
+                             // even number of rounds.
+  int64_t perm_base;
+  int32_t num_rounds;
+};
+
+// One-off per run: potentials -> round order (see BigMaxGroup).
+template <bool kFlatLp>
+__global__ void __launch_bounds__(kThreads)
+k_bigmax_permute(BatchMap mp, const BigMaxGroup* __restrict__ groups, const int2* __restrict__ units,
+                 int64_t num_units, View lp, float* __restrict__ lpR) {
+  for (int64_t u = blockIdx.y; u < num_units; u += gridDim.y) {
+    const int2 uf = units[u];
+    const BigMaxGroup& G = groups[uf.x];
+    const int64_t n = int64_t(G.num_rounds) * 32;
+    const LaneView lpL = lane_view(lp, mp, 0);
+    const float* __restrict__ src = lpL.q + (G.blk.pot_base(uf.y) << lpL.sh);
+    float* __restrict__ dst = lpR + G.perm_base + int64_t(uf.y) * n;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+      const uint32_t e = G.rounds[i];
+      dst[i] = e == 0xffffffffu ? -INFINITY : clip_lp(kFlatLp ? src[e & 0xfffffu] : src[size_t(e & 0xfffffu) << lpL.sh]);
+    }
+  }
+}
+
+constexpr int kBigTrip = 8;
+
+// kFlatLp: potentials addressed without a sample-tile shift (shared or batch-major);
+// kPerm: potentials come from the round-ordered copy lpR (potentials shared by the batch)
+template <bool kFlatLp, bool kPerm>
+__global__ void __launch_bounds__(kThreads, 3)
+k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, const int2* __restrict__ units,
+                       int64_t num_units, unsigned int* __restrict__ counter,
+                       const int32_t* __restrict__ edge_vs, View lp, const float* __restrict__ lpR,
+                       const float* __restrict__ S,
+                       const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  extern __shared__ float smem[];
+  __shared__ unsigned int s_unit;
+  const int sh = mp.bx_log;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t total = num_units * mp.batch;
+  for (;;) {
+    __syncthreads();  // previous unit done with shared memory (and with s_unit)
+    if (threadIdx.x == 0) s_unit = atomicAdd(counter, 1u);
+    __syncthreads();
+    const int64_t unit = s_unit;
+    if (unit >= total) break;
+    const int64_t u = unit / mp.batch;
+    const int b = int(unit - u * mp.batch);
+    const int2 uf = units[u];
+    const BigMaxGroup& G = groups[uf.x];
+    const EnumBlockDev& blk = G.blk;
+    const int64_t f = uf.y;
+    const int ns = blk.ns, n0 = blk.edge_off[1], n1 = ns - n0;
+    float* q = smem;                       // [ns]
+    float* M = q + ns;                     // [ns] maxima, then damped values
+    float* Mw = M + ns;                    // [kBigWarps][n1 + 32] per-warp partner-side maxima
+    float* red = Mw + kBigWarps * (n1 + 32);
+    const int64_t moff = lane_off(mp, a.Es, b);
+    const float* mo = m_old + moff;
+    float* mn = m_new + moff;
+    const float* SL = S + lane_off(mp, a.Vs, b);
+    const LaneView lpL = lane_view(lp, mp, b);
+    const int64_t mbase = blk.msg_base(f), ebase = blk.edge_base(f), pbase = blk.pot_base(f);
+    for (int e = 0; e < 2; ++e) {
+      const int64_t vs = edge_vs[ebase + e];
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        q[s] = SL[(vs + s - s0) << sh] - mo[(mbase + s) << sh];
+        M[s] = -INFINITY;
+      }
+    }
+    for (int i = threadIdx.x; i < kBigWarps * (n1 + 32); i += blockDim.x) Mw[i] = -INFINITY;
+    __syncthreads();
+
+    {  // ---- configurations: this warp's lane-groups, round by round ---------------------------
+      const uint32_t* __restrict__ rounds = G.rounds;
+      const float* __restrict__ lpu = lpL.q + (pbase << lpL.sh);
+      const int lsh = lpL.sh;
+      const uint32_t qb_s = smem_u32(q) + 4u * n0;
+      const uint32_t mw_s = smem_u32(Mw + warp * (n1 + 32));
+      const uint32_t dummy_s = mw_s + 4u * (n1 + lane);  // idle lanes read-max-write their own slot
+      auto lds_f = [](uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; };
+      auto sts_f = [](uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); };
+      const float* __restrict__ lpr = lpR + G.perm_base + f * (int64_t(G.num_rounds) * 32) + lane;
+      const uint32_t* __restrict__ rbl = G.rounds_b + lane;
+      // one trip = kPermTrip rounds; the next trip's loads (2 KiB of potentials per warp) are in
+      // flight while this one is consumed: with 24 warps per SM that is ~50 KiB per SM in
+      // flight, what HBM latency x bandwidth asks for
+      constexpr int kPermTrip = 16;
+      for (int grp = warp; kPerm && grp < G.num_groups; grp += kBigWarps) {
+        const int a_own = grp * 32 + lane;
+        const float qa = a_own < n0 ? q[a_own] : 0.f;
+        const int r_end = G.round_ptr[grp + 1];
+        const uint32_t idle2 = uint32_t(n1 + lane) * 0x10001u;
+        uint32_t en_n[kPermTrip / 2];
+        float rl_n[kPermTrip];
+        auto request = [&](int r0) {
+#pragma unroll
+          for (int p = 0; p < kPermTrip / 2; ++p) {
+            const bool in = r0 + 2 * p < r_end;  // rounds come in pairs
+            en_n[p] = in ? __ldg(rbl + (size_t(r0 + 2 * p) << 4)) : idle2;
+            rl_n[2 * p] = in ? __ldcs(lpr + (size_t(r0 + 2 * p) << 5)) : -INFINITY;
+            rl_n[2 * p + 1] = in ? __ldcs(lpr + (size_t(r0 + 2 * p + 1) << 5)) : -INFINITY;
+          }
+        };
+        float best = -INFINITY;
+        int r0 = G.round_ptr[grp];
+        if (r0 < r_end) request(r0);
+        for (; r0 < r_end; r0 += kPermTrip) {
+          uint32_t en[kPermTrip / 2];
+          float rl[kPermTrip];
+#pragma unroll
+          for (int p = 0; p < kPermTrip / 2; ++p) en[p] = en_n[p];
+#pragma unroll
+          for (int p = 0; p < kPermTrip; ++p) rl[p] = rl_n[p];
+          if (r0 + kPermTrip < r_end) request(r0 + kPermTrip);
+          // idle entries: potential -inf, partner "state" n1 + j = a dummy slot
+          // (the q read lands in M[], finite or -inf: the sum stays -inf).
+          // All q reads of the trip first (read-only: they overlap), then the read-max-write chain.
+          uint32_t b_s[kPermTrip];
+          float sk[kPermTrip];
+#pragma unroll
+          for (int p = 0; p < kPermTrip; ++p) {
+            b_s[p] = ((p & 1) ? (en[p >> 1] >> 16) : (en[p >> 1] & 0xffffu)) << 2;
+            sk[p] = lds_f(qb_s + b_s[p]);
+          }
+#pragma unroll
+          for (int p = 0; p < kPermTrip; ++p) {
+            sk[p] = (qa + sk[p]) + rl[p];
+            best = fmaxf(best, sk[p]);
+          }
+#pragma unroll
+          for (int p = 0; p < kPermTrip; ++p) {
+            const uint32_t slot = mw_s + b_s[p];
+            sts_f(slot, fmaxf(lds_f(slot), sk[p]));
+            asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+          }
+        }
+        if (a_own < n0) M[a_own] = best;
+      }
+      for (int grp = warp; !kPerm && grp < G.num_groups; grp += kBigWarps) {
+        const int a_own = grp * 32 + lane;
+        const float qa = a_own < n0 ? q[a_own] : 0.f;
+        const int r_end = G.round_ptr[grp + 1];
+        uint32_t en_n[kBigTrip];
+        float rl_n[kBigTrip];
+        auto request = [&](int r0) {
+#pragma unroll
+          for (int p = 0; p < kBigTrip; ++p)
+            en_n[p] = r0 + p < r_end ? __ldg(rounds + (size_t(r0 + p) << 5) + lane) : 0xffffffffu;
+#pragma unroll
+          for (int p = 0; p < kBigTrip; ++p) {
+            // unconditional loads: idle lanes read configuration 0 of the factor
+            const uint32_t k = en_n[p] == 0xffffffffu ? 0u : (en_n[p] & 0xfffffu);
+            rl_n[p] = kFlatLp ? __ldg(lpu + k) : __ldg(lpu + (size_t(k) << lsh));
+          }
+        };
+        float best = -INFINITY;
+        int r0 = G.round_ptr[grp];
+        if (r0 < r_end) request(r0);
+        for (; r0 < r_end; r0 += kBigTrip) {
+          uint32_t en[kBigTrip];
+          float rl[kBigTrip];
+#pragma unroll
+          for (int p = 0; p < kBigTrip; ++p) { en[p] = en_n[p]; rl[p] = rl_n[p]; }
+          if (r0 + kBigTrip < r_end) request(r0 + kBigTrip);  // next trip in flight during this one
+#pragma unroll
+          for (int p = 0; p < kBigTrip; ++p) {
+            const bool on = en[p] != 0xffffffffu;            // absent rounds of the last trip are idle entries
+            const uint32_t b_s = on ? (en[p] >> 20) << 2 : 0u;  // idle lanes read partner state 0
+            float sk = (qa + lds_f(qb_s + b_s)) + clip_lp(rl[p]);
+            sk = on ? sk : -INFINITY;
+            best = fmaxf(best, sk);
+            const uint32_t slot = on ? mw_s + b_s : dummy_s;
+            sts_f(slot, fmaxf(lds_f(slot), sk));
+            __syncwarp();
+          }
+        }
+        if (a_own < n0) M[a_own] = best;
+      }
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < n1; s += blockDim.x) {
+      float v = Mw[s];
+      for (int w = 1; w < kBigWarps; ++w) v = fmaxf(v, Mw[w * (n1 + 32) + s]);
+      M[n0 + s] = v;
+    }
+    __syncthreads();
+    float dmax = 0.f;
+    for (int e = 0; e < 2; ++e) {
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      float mx = -INFINITY;
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const float nvs = damp(mo[(mbase + s) << sh], M[s] - q[s], a.d, a.one_minus_d);
+        M[s] = nvs;
+        mx = fmaxf(mx, nvs);
+      }
+      mx = block_max(mx, red);
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const float out = fmaxf(M[s] - mx, kMsgNegInf);
+        const int64_t idx = (mbase + s) << sh;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
+      }
+    }
+    if (a.deltas != nullptr) {
+      dmax = block_max(dmax, red);
+      if (threadIdx.x == 0) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Writes the two states of a binary edge whose factor->variable message is
+// (0, x) or (x, 0): damping + normalisation + clip + delta.
+//   lo = message index of the edge's state 0; mo / mn are lane pointers.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float write_binary_edge(const float* __restrict__ mo,
+                                                   float* __restrict__ mn, int64_t lo, int sh,
+                                                   float f0, float f1, float d, float one_minus_d) {
+  const int64_t i0 = lo << sh, i1 = (lo + 1) << sh;
+  const float a0 = mo[i0], a1 = mo[i1];
+  float n0 = damp(a0, f0, d, one_minus_d), n1 = damp(a1, f1, d, one_minus_d);
+  const float mx = fmaxf(n0, n1);
+  n0 = fmaxf(n0 - mx, kMsgNegInf);
+  n1 = fmaxf(n1 - mx, kMsgNegInf);
+  mn[i0] = n0;
+  mn[i1] = n1;
+  return fmaxf(fabsf(n0 - a0), fabsf(n1 - a1));
+}
+
+}  // namespace pgx

@@ -1,0 +1,734 @@
+// pgx kernels - K4 / K5: OR, AND and Pool factors.  Part of pgx_kernels.cuh (included in this order).
+#pragma once
+
+#include "enum.cuh"
+
+namespace pgx {
+
+// Device-side logical / pool wiring.  parent_ptr[f]..parent_ptr[f+1] indexes the
+// parents of factor f; *_msg are global message indices of the wiring's "p_i" /
+// "c" state, *_vs the var-state index of that same state.
+struct LogicalDev {
+  int64_t num_factors;
+  const int32_t* parent_ptr;
+  const int32_t* parents_msg;
+  const int32_t* parents_vs;
+  const int32_t* children_msg;
+  const int32_t* children_vs;
+  int32_t off;  // +1 OR / Pool, -1 AND
+  int32_t uniform;  // > 0: every factor has exactly this many parents (parent_ptr[f] = f * uniform)
+};
+
+// ---------------------------------------------------------------------------
+// K4: OR / AND update, closed form from per-factor sums and the two largest
+// parent differences (pgmax/factor/logical.py:561-779).
+// One thread per (factor, sample).  Factors with <= kRegParents parents (the AND
+// factors of the deconvolution graphs have 2) keep the parents' variable->factor
+// messages in registers: every message is read once.  Wider factors (ORs with up
+// to 180 parents) make two passes over the parents, loading kChunk parents' worth
+// of independent gathers at a time.
+// ---------------------------------------------------------------------------
+constexpr int kRegParents = 4;
+constexpr int kParentChunk = 8;
+
+// Arithmetic shared by both paths, exactly App. A.3.
+struct LogicalAcc {
+  float Sb = 0.f, acc = 0.f, d1 = -INFINITY, d2 = -INFINITY;
+  int64_t istar = 0;
+  template <bool kSumProduct>
+  __device__ __forceinline__ void add(int64_t i, float a_i, float b_i, float T) {
+    const float dl = a_i - b_i;
+    Sb += b_i;
+    acc += kSumProduct ? logaddexp_t(a_i, b_i, T) : fmaxf(b_i, a_i);
+    if (dl >= d1) { d2 = d1; d1 = dl; istar = i; }  // first arg-max = LARGEST tied index
+    else if (dl > d2) d2 = dl;
+  }
+  template <bool kSumProduct>
+  __device__ __forceinline__ float child_relevant(float T) const {
+    if (kSumProduct) {
+      float CR = logminusexp_t(acc, Sb, T, 1e-4f);
+      if (T < kTempStabThre) CR = fmaxf(CR, logaddexp_t(Sb + d1, Sb + d2, T));
+      return CR;
+    }
+    return acc + fminf(0.f, d1);
+  }
+  // message difference (relevant - other) to parent i
+  template <bool kSumProduct>
+  __device__ __forceinline__ float parent_out(int64_t i, float a_i, float b_i, float ca, float cb,
+                                              float T, bool single) const {
+    float PR, PO;
+    if (kSumProduct) {
+      const float l_i = logaddexp_t(a_i, b_i, T);
+      const float Lw = acc - l_i, Sw = Sb - b_i;
+      PR = ca + Lw;
+      const float o1 = cb + Sw, o2 = ca + Lw, o3 = ca + Sw;
+      PO = logminusexp_t(logaddexp_t(o1, o2, T), o3, T, 1e-4f);
+      if (T < kTempStabThre) {
+        const float bound = (i == istar) ? (Sw + d2) : (Sw + d1);
+        PO = fmaxf(PO, logaddexp_t(o1, ca + bound, T));
+      }
+    } else {
+      const float mu = fmaxf(b_i, a_i);
+      PR = (acc + ca) - mu;
+      const float o1 = (cb + Sb) - b_i;
+      const float o2 = PR + ((i == istar) ? fminf(0.f, d2) : fminf(0.f, d1));
+      PO = fmaxf(o1, o2);
+    }
+    if (single) { PR = ca; PO = cb; }  // logical.py:739-757
+    return PR - PO;
+  }
+};
+
+// Groups whose factors all have the same number n <= kRegParents of parents (the AND
+// factors of the deconvolution graphs: n = 2).  One thread per (factor, sample), TWO factors
+// per iteration: the wiring of both is loaded first, then all their gathers (2 * 2(n + 1)
+// message / var-sum pairs in flight), then the closed form of App. A.3 for each.
+constexpr int kLogicalUnits = 2;
+
+template <bool kSumProduct>
+__global__ void __launch_bounds__(kThreads)
+k_logical_uniform(BatchMap mp, LogicalDev w, const float* __restrict__ S,
+                  const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  UnitLoop L = unit_loop(mp, w.num_factors);
+  if (!L.b_ok) return;
+  float dmax = 0.f;
+  const int sh = mp.bx_log;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const int off = w.off, n = w.uniform;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  auto write_edge = [&](int64_t pm, float x) {
+    const int64_t lo = (off > 0) ? pm : pm - 1;
+    dmax = fmaxf(dmax, write_binary_edge(mo, mn, lo, sh, off > 0 ? 0.f : x, off > 0 ? x : 0.f, d, one_minus_d));
+  };
+  for (int64_t f0 = L.u; f0 < L.u_end; f0 += kLogicalUnits * L.step) {
+    int32_t c[kLogicalUnits], cvs[kLogicalUnits], pm[kLogicalUnits][kRegParents], pv[kLogicalUnits][kRegParents];
+#pragma unroll
+    for (int u = 0; u < kLogicalUnits; ++u) {
+      const int64_t f = f0 + u * L.step;
+      if (f < L.u_end) {
+        c[u] = w.children_msg[f];
+        cvs[u] = w.children_vs[f];
+#pragma unroll
+        for (int j = 0; j < kRegParents; ++j)
+          if (j < n) { pm[u][j] = w.parents_msg[f * n + j]; pv[u][j] = w.parents_vs[f * n + j]; }
+      }
+    }
+    float ca[kLogicalUnits], cb[kLogicalUnits], av[kLogicalUnits][kRegParents], bv[kLogicalUnits][kRegParents];
+#pragma unroll
+    for (int u = 0; u < kLogicalUnits; ++u) {
+      if (f0 + u * L.step < L.u_end) {
+        ca[u] = SL[int64_t(cvs[u] + off) << sh] - mo[int64_t(c[u] + off) << sh];
+        cb[u] = SL[int64_t(cvs[u]) << sh] - mo[int64_t(c[u]) << sh];
+#pragma unroll
+        for (int j = 0; j < kRegParents; ++j)
+          if (j < n) {
+            av[u][j] = SL[int64_t(pv[u][j] + off) << sh] - mo[int64_t(pm[u][j] + off) << sh];
+            bv[u][j] = SL[int64_t(pv[u][j]) << sh] - mo[int64_t(pm[u][j]) << sh];
+          }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kLogicalUnits; ++u) {
+      const int64_t f = f0 + u * L.step;
+      if (f < L.u_end) {
+        const int64_t p0 = f * n;
+        LogicalAcc A;
+        A.istar = p0;
+#pragma unroll
+        for (int j = 0; j < kRegParents; ++j)
+          if (j < n) A.add<kSumProduct>(p0 + j, av[u][j], bv[u][j], T);
+#pragma unroll
+        for (int j = 0; j < kRegParents; ++j)
+          if (j < n)
+            write_edge(pm[u][j], A.parent_out<kSumProduct>(p0 + j, av[u][j], bv[u][j], ca[u], cb[u], T, n == 1));
+        write_edge(c[u], A.child_relevant<kSumProduct>(T) - A.Sb);
+      }
+    }
+  }
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// kNarrow: every factor of the group has <= kRegParents parents (the wide path is compiled out,
+// which halves the register count and doubles the resident warps).
+template <bool kSumProduct, bool kNarrow>
+__global__ void __launch_bounds__(kThreads)
+k_logical(BatchMap mp, LogicalDev w, const float* __restrict__ S,
+          const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  UnitLoop L = unit_loop(mp, w.num_factors);
+  if (!L.b_ok) return;
+  float dmax = 0.f;
+  const int sh = mp.bx_log;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  // variable->factor message of the wiring's state (at msg index pm / var-state pv) and of
+  // the "relevant" state (+off)
+  auto q_rel = [&](int64_t pm, int64_t pv) { return SL[(pv + off) << sh] - mo[(pm + off) << sh]; };
+  auto q_oth = [&](int64_t pm, int64_t pv) { return SL[pv << sh] - mo[pm << sh]; };
+  auto write_edge = [&](int64_t pm, float x) {  // x = message of the "+off" state; the other state gets 0
+    const int64_t lo = (off > 0) ? pm : pm - 1;
+    dmax = fmaxf(dmax, write_binary_edge(mo, mn, lo, sh, off > 0 ? 0.f : x, off > 0 ? x : 0.f, d, one_minus_d));
+  };
+  // wiring of one factor; fetched one factor ahead so that its (dependent) index loads
+  // overlap the current factor's gathers
+  struct Wiring {
+    int64_t p0, p1;
+    int32_t c, cvs;
+    int32_t pm[kRegParents], pv[kRegParents];
+  };
+  auto load_wiring = [&](int64_t f, Wiring& x) {
+    if (w.uniform > 0) { x.p0 = f * w.uniform; x.p1 = x.p0 + w.uniform; }
+    else { x.p0 = w.parent_ptr[f]; x.p1 = w.parent_ptr[f + 1]; }
+    x.c = w.children_msg[f];
+    x.cvs = w.children_vs[f];
+    if (x.p1 - x.p0 <= kRegParents) {
+#pragma unroll
+      for (int j = 0; j < kRegParents; ++j)
+        if (x.p0 + j < x.p1) { x.pm[j] = w.parents_msg[x.p0 + j]; x.pv[j] = w.parents_vs[x.p0 + j]; }
+    }
+  };
+  Wiring cur_w, next_w;
+  if (L.u < L.u_end) load_wiring(L.u, cur_w);
+  for (int64_t f = L.u; f < L.u_end; f += L.step, cur_w = next_w) {
+    if (f + L.step < L.u_end) load_wiring(f + L.step, next_w);
+    const int64_t p0 = cur_w.p0, p1 = cur_w.p1;
+    const int64_t c = cur_w.c, cvs = cur_w.cvs;
+    const float ca = q_rel(c, cvs), cb = q_oth(c, cvs);
+    const bool single = (p1 - p0) == 1;
+    LogicalAcc A;
+    A.istar = p0;
+    if (kNarrow || p1 - p0 <= kRegParents) {
+      float av[kRegParents], bv[kRegParents];
+#pragma unroll
+      for (int j = 0; j < kRegParents; ++j) {
+        if (p0 + j < p1) {
+          av[j] = q_rel(cur_w.pm[j], cur_w.pv[j]);
+          bv[j] = q_oth(cur_w.pm[j], cur_w.pv[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kRegParents; ++j)
+        if (p0 + j < p1) A.add<kSumProduct>(p0 + j, av[j], bv[j], T);
+#pragma unroll
+      for (int j = 0; j < kRegParents; ++j)
+        if (p0 + j < p1)
+          write_edge(cur_w.pm[j], A.parent_out<kSumProduct>(p0 + j, av[j], bv[j], ca, cb, T, single));
+    } else if (!kNarrow) {
+      // Pass 1: sums in ascending parent order, first / second max of the differences.
+      int64_t i = p0;
+      for (; i + kParentChunk <= p1; i += kParentChunk) {
+        float av[kParentChunk], bv[kParentChunk];
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j) {
+          const int64_t pm = w.parents_msg[i + j], pv = w.parents_vs[i + j];
+          av[j] = q_rel(pm, pv);
+          bv[j] = q_oth(pm, pv);
+        }
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j) A.add<kSumProduct>(i + j, av[j], bv[j], T);
+      }
+      for (; i < p1; ++i) {
+        const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
+        A.add<kSumProduct>(i, q_rel(pm, pv), q_oth(pm, pv), T);
+      }
+      // Pass 2: outgoing messages to the parents.
+      i = p0;
+      for (; i + kParentChunk <= p1; i += kParentChunk) {
+        int64_t pm[kParentChunk];
+        float av[kParentChunk], bv[kParentChunk];
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j) {
+          pm[j] = w.parents_msg[i + j];
+          const int64_t pv = w.parents_vs[i + j];
+          av[j] = q_rel(pm[j], pv);
+          bv[j] = q_oth(pm[j], pv);
+        }
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j)
+          write_edge(pm[j], A.parent_out<kSumProduct>(i + j, av[j], bv[j], ca, cb, T, single));
+      }
+      for (; i < p1; ++i) {
+        const int64_t pm = w.parents_msg[i], pv = w.parents_vs[i];
+        write_edge(pm, A.parent_out<kSumProduct>(i, q_rel(pm, pv), q_oth(pm, pv), ca, cb, T, single));
+      }
+    }
+    write_edge(c, A.child_relevant<kSumProduct>(T) - A.Sb);
+  }
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
+// K4-pull: OR / AND update for full sample tiles (TW = 32: a warp = the 32 samples of ONE
+// factor, every index warp-uniform) that needs the variable-sum array only for HIGH-degree
+// variables.  For a variable with one or two incident edges the kernel re-derives
+// S_v = ev_v + (incident messages in ascending message index) itself - the same additions
+// in the same order as k_var_sums, so results are bit-identical - which removes the S
+// write + gather and the message re-read of k_var_sums for those variables (in the
+// deconvolution graphs: every SW and X variable, 2/3 of all var-states); k_var_sums then
+// only runs over the listed high-degree var-states (S and W).
+// Wiring per edge (EdgeW, one 16-byte load): msg = message index of the state the
+// reference's wiring points at (state 0 for OR, state 1 for AND), vs = var-state of that
+// state, other = message index (same state) of the variable's only other edge, -1 if the
+// variable has no other edge, -2 if its sum is to be read from S.
+// All loads of a factor are issued before the first use (no data-dependent branch between
+// them); addresses are 32-bit offsets from per-lane bases.
+// ---------------------------------------------------------------------------
+struct EdgeW {
+  int32_t msg, vs, other, pad;
+};
+
+struct LogicalPullDev {
+  int64_t num_factors;
+  const int32_t* parent_ptr;  // [F + 1] (null when uniform)
+  const EdgeW* parents;       // [P]
+  const EdgeW* children;      // [F]
+  int32_t off;                // +1 OR, -1 AND
+  int32_t uniform;            // > 0: every factor has this many parents
+};
+
+// What stays live per edge between the loads and their use: 8 registers.
+struct EdgeIn {
+  float m_p, m_r;  // old messages: pointed state, relevant (+off) state
+  float a_p, a_r;  // S (kind 0) or evidence
+  float o_p, o_r;  // the other edge's messages (kinds 2, 3)
+  int32_t msg;
+  int32_t kind;    // 0: sums from S; 1: no other edge; 2: other edge first; 3: own edge first
+};
+
+// kBin: the message arrays are in binary-difference storage (one float x = n1 - n0 per edge,
+// every edge of the graph has two states, edge e holds message rows 2e, 2e + 1; see
+// bin_expand): row of an edge = msg >> 1, and (pointed, relevant) = (state 0, state 1) for
+// off = +1, (state 1, state 0) for off = -1.
+template <bool kBin>
+__device__ __forceinline__ size_t msg_rows(const RunArgs& a) { return kBin ? size_t(a.Es) >> 1 : size_t(a.Es); }
+
+// Sum-product closed forms can return an infinite difference (an empty logminusexp); the
+// update then leaves BOTH states of the edge at the clip value -1e32 (inf - inf = NaN, and
+// fmaxf(NaN, -1e32) = -1e32), the one normalised pair whose maximum is not 0.  The stored
+// difference encodes it as NaN (kFloor variants; max-product never produces it).
+// load_msg only LOADS (kBin: the raw difference goes to m_p); expand_msg, called on the
+// consumer side (edge_q), turns it into the two states - no arithmetic sits between the loads
+// of a batch of edges, so they all stay in flight together.
+template <bool kBin, bool kFloor>
+__device__ __forceinline__ void expand_msg(int off, float& m_p, float& m_r) {
+  if (!kBin) return;
+  const float x = m_p;
+  const float xs = off > 0 ? x : -x;  // relevant - pointed
+  m_p = fminf(-xs, 0.f);
+  m_r = fminf(xs, 0.f);
+  if (kFloor && x != x) m_p = m_r = kMsgNegInf;
+}
+
+template <bool kBin, bool kFloor>
+__device__ __forceinline__ void load_msg(const float* __restrict__ mo, int32_t msg, int off, float& m_p, float& m_r) {
+  if (kBin) {
+    m_p = mo[(uint32_t(msg) >> 1) << 5];
+    m_r = 0.f;
+  } else {
+    m_p = mo[uint32_t(msg) << 5];
+    m_r = mo[uint32_t(msg + off) << 5];
+  }
+}
+
+// Issues the (up to) 6 loads of an edge (4 in binary-difference storage); no data-dependent branch.
+template <bool kBin, bool kFloor>
+__device__ __forceinline__ EdgeIn load_edge(const EdgeW& e, int off, const float* __restrict__ mo,
+                                            const float* __restrict__ evq, int esh,
+                                            const float* __restrict__ SL) {
+  EdgeIn r;
+  r.msg = e.msg;
+  r.kind = e.other == -2 ? 0 : (e.other == -1 ? 1 : (e.other < e.msg ? 2 : 3));
+  load_msg<kBin, kFloor>(mo, e.msg, off, r.m_p, r.m_r);
+  const bool from_s = e.other == -2;
+  r.a_p = *(from_s ? SL + (uint32_t(e.vs) << 5) : evq + (uint32_t(e.vs) << esh));
+  r.a_r = *(from_s ? SL + (uint32_t(e.vs + off) << 5) : evq + (uint32_t(e.vs + off) << esh));
+  r.o_p = 0.f;
+  r.o_r = 0.f;
+  if (e.other >= 0) load_msg<kBin, kFloor>(mo, e.other, off, r.o_p, r.o_r);
+  return r;
+}
+// variable -> factor messages (pointed state, relevant state): S - m with S accumulated from
+// the evidence in ascending message index
+template <bool kBin, bool kFloor>
+__device__ __forceinline__ void edge_q(EdgeIn& r, int off, float& q_p, float& q_r) {
+  expand_msg<kBin, kFloor>(off, r.m_p, r.m_r);
+  if (r.kind >= 2) expand_msg<kBin, kFloor>(off, r.o_p, r.o_r);
+  float s_p = r.a_p, s_r = r.a_r;
+  if (r.kind != 0) {
+    const bool other_first = r.kind == 2;
+    s_p += other_first ? r.o_p : r.m_p;
+    s_r += other_first ? r.o_r : r.m_r;
+    if (r.kind >= 2) {
+      s_p += other_first ? r.m_p : r.o_p;
+      s_r += other_first ? r.m_r : r.o_r;
+    }
+  }
+  q_p = s_p - r.m_p;
+  q_r = s_r - r.m_r;
+}
+
+// new message (x at the relevant state, 0 at the pointed state): damping, normalisation,
+// clip, store; returns max|new - old| when kDelta
+template <bool kDelta, bool kBin, bool kFloor>
+__device__ __forceinline__ float store_edge(float* __restrict__ mn, int off, const EdgeIn& r, float x, float d,
+                                            float one_minus_d) {
+  float n_p = damp(r.m_p, 0.f, d, one_minus_d), n_r = damp(r.m_r, x, d, one_minus_d);
+  const float mx = fmaxf(n_p, n_r);
+  n_p = fmaxf(n_p - mx, kMsgNegInf);
+  n_r = fmaxf(n_r - mx, kMsgNegInf);
+  if (kBin) {  // one of n_p, n_r is the exact zero: the difference loses nothing
+    float xd = off > 0 ? n_r - n_p : n_p - n_r;
+    if (kFloor && fmaxf(n_p, n_r) < 0.f) xd = __int_as_float(0x7fc00000);  // both states at the floor
+    mn[(uint32_t(r.msg) >> 1) << 5] = xd;
+  } else {
+    mn[uint32_t(r.msg) << 5] = n_p;
+    mn[uint32_t(r.msg + off) << 5] = n_r;
+  }
+  return kDelta ? fmaxf(fabsf(n_p - r.m_p), fabsf(n_r - r.m_r)) : 0.f;
+}
+
+// Factors with <= NP parents (AND factors: NP = 2), everything in registers, U factors per
+// warp iteration (their loads are all in flight together).  kUniform: every factor has
+// exactly NP parents.
+template <bool kSumProduct, bool kDelta, int NP, int U, bool kUniform, bool kBin>
+__global__ void __launch_bounds__(kThreads)
+k_logical_pull_small(int batch, LogicalPullDev w, View ev, const float* __restrict__ S,
+                     const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y * 32 + lane;
+  if (b >= batch) return;
+  const size_t tile = blockIdx.y;
+  const float* mo = m_old + tile * msg_rows<kBin>(a) * 32 + lane;
+  float* mn = m_new + tile * msg_rows<kBin>(a) * 32 + lane;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + lane;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + lane : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float dmax = 0.f;
+  for (int64_t f0 = gwarp; f0 < w.num_factors; f0 += U * nwarps) {
+    EdgeIn ce[U], pe[U][NP];
+    int np[U];
+    int64_t p0[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t f = f0 + u * nwarps;
+      np[u] = 0;
+      p0[u] = 0;
+      if (f < w.num_factors) {
+        if (kUniform) { p0[u] = f * NP; np[u] = NP; }
+        else { p0[u] = w.parent_ptr[f]; np[u] = int(w.parent_ptr[f + 1] - p0[u]); }
+        ce[u] = load_edge<kBin, kSumProduct>(w.children[f], off, mo, evq, esh, SL);
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+          if (kUniform || j < np[u]) pe[u][j] = load_edge<kBin, kSumProduct>(w.parents[p0[u] + j], off, mo, evq, esh, SL);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (f0 + u * nwarps < w.num_factors) {
+        float c_p, c_r, q_p[NP], q_r[NP];
+        edge_q<kBin, kSumProduct>(ce[u], off, c_p, c_r);
+        LogicalAcc A;
+        A.istar = p0[u];
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+          if (kUniform || j < np[u]) {
+            edge_q<kBin, kSumProduct>(pe[u][j], off, q_p[j], q_r[j]);
+            A.add<kSumProduct>(p0[u] + j, q_r[j], q_p[j], T);
+          }
+#pragma unroll
+        for (int j = 0; j < NP; ++j)
+          if (kUniform || j < np[u]) {
+            const float x = A.parent_out<kSumProduct>(p0[u] + j, q_r[j], q_p[j], c_r, c_p, T, np[u] == 1);
+            dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, pe[u][j], x, d, one_minus_d));
+          }
+        dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, ce[u], A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
+      }
+    }
+  }
+  if (kDelta) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// Any number of parents (OR factors with up to hundreds): two passes over the parents.  The
+// wiring of 32 parents is fetched with ONE coalesced load (lane j holds parent i + j) and
+// handed out by shuffles; the parents' loads are issued kParentChunk at a time.  All lanes
+// stay alive for the shuffles; lanes beyond the batch read a valid sample and store nothing.
+template <bool kSumProduct, bool kDelta, bool kBin>
+__global__ void __launch_bounds__(128)
+k_logical_pull_wide(int batch, LogicalPullDev w, View ev, const float* __restrict__ S,
+                    const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int b_raw = blockIdx.y * 32 + lane;
+  const bool live = b_raw < batch;
+  const int ll = live ? lane : 0;  // dead lanes shadow sample 0 of the tile (always valid)
+  const size_t tile = blockIdx.y;
+  const float* mo = m_old + tile * msg_rows<kBin>(a) * 32 + ll;
+  float* mn = m_new + tile * msg_rows<kBin>(a) * 32 + ll;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + ll;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + ll : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float dmax = 0.f;
+  for (int64_t f = gwarp; f < w.num_factors; f += nwarps) {
+    int64_t p0, p1;
+    if (w.uniform > 0) { p0 = f * w.uniform; p1 = p0 + w.uniform; }
+    else { p0 = w.parent_ptr[f]; p1 = w.parent_ptr[f + 1]; }
+    EdgeIn ce = load_edge<kBin, kSumProduct>(w.children[f], off, mo, evq, esh, SL);
+    LogicalAcc A;
+    A.istar = p0;
+    const bool single = (p1 - p0) == 1;
+    float c_p = 0.f, c_r = 0.f;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass == 1) edge_q<kBin, kSumProduct>(ce, off, c_p, c_r);
+      EdgeW mine = (p0 + lane < p1) ? w.parents[p0 + lane] : EdgeW{0, 0, -1, 0};
+      for (int64_t i32 = p0; i32 < p1; i32 += 32) {
+        const EdgeW held = mine;
+        if (i32 + 32 + lane < p1) mine = w.parents[i32 + 32 + lane];  // next 32, in flight during this block
+        const int n32 = int(min(int64_t(32), p1 - i32));
+#pragma unroll 1
+        for (int c0 = 0; c0 < n32; c0 += kParentChunk) {
+          EdgeIn r[kParentChunk];
+#pragma unroll
+          for (int j = 0; j < kParentChunk; ++j) {
+            EdgeW e;
+            e.msg = __shfl_sync(0xffffffffu, held.msg, (c0 + j) & 31);
+            e.vs = __shfl_sync(0xffffffffu, held.vs, (c0 + j) & 31);
+            e.other = __shfl_sync(0xffffffffu, held.other, (c0 + j) & 31);
+            if (c0 + j < n32) r[j] = load_edge<kBin, kSumProduct>(e, off, mo, evq, esh, SL);
+          }
+#pragma unroll
+          for (int j = 0; j < kParentChunk; ++j)
+            if (c0 + j < n32) {
+              float q_p, q_r;
+              edge_q<kBin, kSumProduct>(r[j], off, q_p, q_r);
+              const int64_t i = i32 + c0 + j;
+              if (pass == 0) {
+                A.add<kSumProduct>(i, q_r, q_p, T);
+              } else {
+                const float x = A.parent_out<kSumProduct>(i, q_r, q_p, c_r, c_p, T, single);
+                if (live) dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, r[j], x, d, one_minus_d));
+              }
+            }
+        }
+      }
+    }
+    if (live)
+      dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
+  }
+  if (kDelta && live) publish_delta(a.deltas, int64_t(b_raw) * a.delta_stride + a.delta_off, dmax);
+}
+
+// The wide update split in two launches, so that only the part that must be serial is:
+//   pass 1 (k_logical_wide_reduce): one warp per (factor, sample tile) walks the parents once,
+//     accumulating the sums in ascending parent order and the two largest differences, writes
+//     the child's message and the factor's aggregates [F][8][32 samples] (tile-blocked);
+//   pass 2 (k_logical_wide_emit): one warp per (PARENT, sample tile) - fully parallel,
+//     bandwidth-bound - re-derives its own variable -> factor message and emits the message to
+//     the parent from the aggregates.
+// Same arithmetic as k_logical_pull_wide (LogicalAcc), hence bit-identical.
+constexpr int kAggRows = 8;  // acc, Sb, d1, d2, istar - p0 (int bits), c_p, c_r, unused
+
+template <bool kSumProduct, bool kDelta, bool kBin>
+__global__ void __launch_bounds__(32, 22)  // one warp per CTA: a serial chain holds only its own warp
+k_logical_wide_reduce(int batch, LogicalPullDev w, View ev, const float* __restrict__ S,
+                      const float* __restrict__ m_old, float* __restrict__ m_new, float* __restrict__ agg,
+                      RunArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int b_raw = blockIdx.y * 32 + lane;
+  const bool live = b_raw < batch;
+  const int ll = live ? lane : 0;
+  const size_t tile = blockIdx.y;
+  const float* mo = m_old + tile * msg_rows<kBin>(a) * 32 + ll;
+  float* mn = m_new + tile * msg_rows<kBin>(a) * 32 + ll;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + ll;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + ll : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  float* aggL = agg + tile * size_t(w.num_factors) * kAggRows * 32 + ll;
+  const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float dmax = 0.f;
+  for (int64_t f = gwarp; f < w.num_factors; f += nwarps) {
+    int64_t p0, p1;
+    if (w.uniform > 0) { p0 = f * w.uniform; p1 = p0 + w.uniform; }
+    else { p0 = w.parent_ptr[f]; p1 = w.parent_ptr[f + 1]; }
+    EdgeIn ce = load_edge<kBin, kSumProduct>(w.children[f], off, mo, evq, esh, SL);
+    LogicalAcc A;
+    A.istar = p0;
+    EdgeW mine = (p0 + lane < p1) ? w.parents[p0 + lane] : EdgeW{0, 0, -1, 0};
+    for (int64_t i32 = p0; i32 < p1; i32 += 32) {
+      const EdgeW held = mine;
+      if (i32 + 32 + lane < p1) mine = w.parents[i32 + 32 + lane];
+      const int n32 = int(min(int64_t(32), p1 - i32));
+#pragma unroll 1
+      for (int c0 = 0; c0 < n32; c0 += kParentChunk) {
+        EdgeIn r[kParentChunk];
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j) {
+          EdgeW e;
+          e.msg = __shfl_sync(0xffffffffu, held.msg, (c0 + j) & 31);
+          e.vs = __shfl_sync(0xffffffffu, held.vs, (c0 + j) & 31);
+          e.other = __shfl_sync(0xffffffffu, held.other, (c0 + j) & 31);
+          if (c0 + j < n32) r[j] = load_edge<kBin, kSumProduct>(e, off, mo, evq, esh, SL);
+        }
+#pragma unroll
+        for (int j = 0; j < kParentChunk; ++j)
+          if (c0 + j < n32) {
+            float q_p, q_r;
+            edge_q<kBin, kSumProduct>(r[j], off, q_p, q_r);
+            A.add<kSumProduct>(i32 + c0 + j, q_r, q_p, T);
+          }
+      }
+    }
+    float c_p, c_r;
+    edge_q<kBin, kSumProduct>(ce, off, c_p, c_r);
+    if (live) {
+      float* g = aggL + size_t(f) * kAggRows * 32;
+      g[0] = A.acc; g[32] = A.Sb; g[64] = A.d1; g[96] = A.d2;
+      g[128] = __int_as_float(int(A.istar - p0)); g[160] = c_p; g[192] = c_r;
+      dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
+    }
+  }
+  if (kDelta && live) publish_delta(a.deltas, int64_t(b_raw) * a.delta_stride + a.delta_off, dmax);
+}
+
+// parent_factor[i] = factor of parent i (ascending).  kEmitUnits parents per warp iteration.
+constexpr int kEmitUnits = 2;
+
+template <bool kSumProduct, bool kDelta, bool kBin>
+__global__ void __launch_bounds__(kThreads)
+k_logical_wide_emit(int batch, LogicalPullDev w, const int32_t* __restrict__ parent_factor, int64_t num_parents,
+                    View ev, const float* __restrict__ S, const float* __restrict__ m_old,
+                    float* __restrict__ m_new, const float* __restrict__ agg, RunArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.y * 32 + lane;
+  if (b >= batch) return;
+  const size_t tile = blockIdx.y;
+  const float* mo = m_old + tile * msg_rows<kBin>(a) * 32 + lane;
+  float* mn = m_new + tile * msg_rows<kBin>(a) * 32 + lane;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + lane;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + lane : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const float* aggL = agg + tile * size_t(w.num_factors) * kAggRows * 32 + lane;
+  const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float dmax = 0.f;
+  for (int64_t i0 = gwarp; i0 < num_parents; i0 += kEmitUnits * nwarps) {
+    EdgeIn r[kEmitUnits];
+    float g[kEmitUnits][7];
+    int64_t p0[kEmitUnits], p1[kEmitUnits];
+#pragma unroll
+    for (int u = 0; u < kEmitUnits; ++u) {
+      const int64_t i = i0 + u * nwarps;
+      if (i < num_parents) {
+        const int f = parent_factor[i];
+        if (w.uniform > 0) { p0[u] = int64_t(f) * w.uniform; p1[u] = p0[u] + w.uniform; }
+        else { p0[u] = w.parent_ptr[f]; p1[u] = w.parent_ptr[f + 1]; }
+        r[u] = load_edge<kBin, kSumProduct>(w.parents[i], off, mo, evq, esh, SL);
+        const float* gp = aggL + size_t(f) * kAggRows * 32;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) g[u][k] = gp[k * 32];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kEmitUnits; ++u) {
+      const int64_t i = i0 + u * nwarps;
+      if (i < num_parents) {
+        LogicalAcc A;
+        A.acc = g[u][0]; A.Sb = g[u][1]; A.d1 = g[u][2]; A.d2 = g[u][3];
+        A.istar = p0[u] + __float_as_int(g[u][4]);
+        float q_p, q_r;
+        edge_q<kBin, kSumProduct>(r[u], off, q_p, q_r);
+        const float x = A.parent_out<kSumProduct>(i, q_r, q_p, g[u][6], g[u][5], T, p1[u] - p0[u] == 1);
+        dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, r[u], x, d, one_minus_d));
+      }
+    }
+  }
+  if (kDelta) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
+// K5: Pool update (pgmax/factor/pool.py:328-474).
+// ---------------------------------------------------------------------------
+template <bool kSumProduct>
+__global__ void __launch_bounds__(kThreads)
+k_pool(BatchMap mp, LogicalDev w, const float* __restrict__ S, const float* __restrict__ m_old,
+       float* __restrict__ m_new, RunArgs a) {
+  UnitLoop L = unit_loop(mp, w.num_factors);
+  if (!L.b_ok) return;
+  float dmax = 0.f;
+  const int sh = mp.bx_log;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  // difference (state 1 - state 0) of the variable->factor message of a binary edge
+  auto diff = [&](int64_t pm, int64_t pv) {
+    return (SL[(pv + 1) << sh] - mo[(pm + 1) << sh]) - (SL[pv << sh] - mo[pm << sh]);
+  };
+  for (int64_t f = L.u; f < L.u_end; f += L.step) {
+    const int64_t p0 = w.parent_ptr[f], p1 = w.parent_ptr[f + 1];
+    const int64_t c = w.children_msg[f], cvs = w.children_vs[f];
+    const float D = diff(c, cvs);
+    float d1 = -INFINITY, d2 = -INFINITY;
+    int64_t istar = p0;
+    for (int64_t i = p0; i < p1; ++i) {
+      const float dl = diff(w.parents_msg[i], w.parents_vs[i]);
+      if (dl >= d1) { d2 = d1; d1 = dl; istar = i; }
+      else if (dl > d2) d2 = dl;
+    }
+    const bool single = (p1 - p0) == 1;
+    float out_ind = d1, G = 0.f, out_star = 0.f;
+    if (kSumProduct) {
+      // logsumexp over the choices with the precomputed max, and over the set where
+      // the arg-max choice is replaced by -D (own max), both in ascending order.
+      float sum = 0.f, mx2 = -INFINITY;
+      for (int64_t i = p0; i < p1; ++i) {
+        const float dl = diff(w.parents_msg[i], w.parents_vs[i]);
+        sum += expf((dl - d1) / T);
+        mx2 = fmaxf(mx2, (i == istar) ? -D : dl);
+      }
+      out_ind = T * logf(sum) + d1;
+      G = logaddexp_t(out_ind, -D, T);
+      float sum2 = 0.f;
+      for (int64_t i = p0; i < p1; ++i) {
+        const float dl = diff(w.parents_msg[i], w.parents_vs[i]);
+        sum2 += expf((((i == istar) ? -D : dl) - mx2) / T);
+      }
+      out_star = -(T * logf(sum2) + mx2);
+    }
+    for (int64_t i = p0; i < p1; ++i) {
+      const int64_t pm = w.parents_msg[i];
+      float x;
+      if (kSumProduct) {
+        const float dl = diff(pm, w.parents_vs[i]);
+        x = (i == istar) ? out_star : -logminusexp_t(G, dl, T, 1e-30f);
+      } else {
+        x = fminf(D, -((i == istar) ? d2 : d1));
+      }
+      if (single) x = D;  // pool.py:430-450
+      dmax = fmaxf(dmax, write_binary_edge(mo, mn, pm, sh, 0.f, x, d, one_minus_d));
+    }
+    dmax = fmaxf(dmax, write_binary_edge(mo, mn, c, sh, 0.f, out_ind, d, one_minus_d));
+  }
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+}  // namespace pgx
