@@ -458,6 +458,76 @@ k_logical_pull_small(int batch, LogicalPullDev w, View ev, const float* __restri
   if (kDelta) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
 }
 
+// The same update for UNIFORM groups (every factor has exactly NP parents) with the wiring
+// staged in shared memory: a CTA owns a contiguous range of `chunk` factors and fetches their
+// wiring (children and parents are contiguous arrays) with one coalesced sweep.  In the
+// kernel above every warp iteration is two dependent round trips - wiring from L2, then the
+// rows it points at from HBM; here the first one is paid once per CTA.  Same arithmetic.
+constexpr int kPullChunk = 256;  // factors per CTA
+
+template <bool kSumProduct, bool kDelta, int NP, int U, bool kBin>
+__global__ void __launch_bounds__(kThreads)
+k_logical_pull_small_staged(int batch, LogicalPullDev w, View ev, const float* __restrict__ S,
+                            const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  __shared__ int4 wsm_child[kPullChunk];
+  __shared__ int4 wsm_par[kPullChunk * NP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y * 32 + lane;
+  const int64_t fbase = int64_t(blockIdx.x) * kPullChunk;
+  const int nfac = int(min(int64_t(kPullChunk), w.num_factors - fbase));
+  {
+    const int4* gc = reinterpret_cast<const int4*>(w.children + fbase);
+    const int4* gp = reinterpret_cast<const int4*>(w.parents + fbase * NP);
+    for (int t = threadIdx.x; t < nfac; t += blockDim.x) wsm_child[t] = gc[t];
+    for (int t = threadIdx.x; t < nfac * NP; t += blockDim.x) wsm_par[t] = gp[t];
+  }
+  __syncthreads();
+  if (b >= batch) return;
+  const size_t tile = blockIdx.y;
+  const float* mo = m_old + tile * msg_rows<kBin>(a) * 32 + lane;
+  float* mn = m_new + tile * msg_rows<kBin>(a) * 32 + lane;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + lane;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + lane : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  const EdgeW* sc = reinterpret_cast<const EdgeW*>(wsm_child);
+  const EdgeW* sp = reinterpret_cast<const EdgeW*>(wsm_par);
+  constexpr int kWarps = kThreads / 32;
+  float dmax = 0.f;
+  for (int j0 = warp * U; j0 < nfac; j0 += kWarps * U) {
+    EdgeIn ce[U], pe[U][NP];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (j0 + u < nfac) {
+        ce[u] = load_edge<kBin, kSumProduct>(sc[j0 + u], off, mo, evq, esh, SL);
+#pragma unroll
+        for (int j = 0; j < NP; ++j) pe[u][j] = load_edge<kBin, kSumProduct>(sp[(j0 + u) * NP + j], off, mo, evq, esh, SL);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (j0 + u < nfac) {
+        const int64_t p0 = (fbase + j0 + u) * NP;
+        float c_p, c_r, q_p[NP], q_r[NP];
+        edge_q<kBin, kSumProduct>(ce[u], off, c_p, c_r);
+        LogicalAcc A;
+        A.istar = p0;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          edge_q<kBin, kSumProduct>(pe[u][j], off, q_p[j], q_r[j]);
+          A.add<kSumProduct>(p0 + j, q_r[j], q_p[j], T);
+        }
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const float x = A.parent_out<kSumProduct>(p0 + j, q_r[j], q_p[j], c_r, c_p, T, NP == 1);
+          dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, pe[u][j], x, d, one_minus_d));
+        }
+        dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, ce[u], A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
+      }
+  }
+  if (kDelta) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+}
+
 // Any number of parents (OR factors with up to hundreds): two passes over the parents.  The
 // wiring of 32 parents is fetched with ONE coalesced load (lane j holds parent i + j) and
 // handed out by shuffles; the parents' loads are issued kParentChunk at a time.  All lanes

@@ -730,11 +730,34 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
     if (lbin) PGX_LAUNCH_SMALL2(NP, U, UNI, true);    \
     else PGX_LAUNCH_SMALL2(NP, U, UNI, false);        \
   } while (0)
-        if (un == 1) PGX_LAUNCH_SMALL(1, 2, true);
+#define PGX_LAUNCH_STAGED2(NP, U, BIN)                                                                          \
+  do {                                                                                                          \
+    if (delta)                                                                                                  \
+      pgx::k_logical_pull_small_staged<kSum, true, NP, U, BIN><<<sgrid, pgx::kThreads, 0, st>>>(mp.batch, lg->pull, ev, \
+                                                                                             S, m_old, m_new, a); \
+    else                                                                                                        \
+      pgx::k_logical_pull_small_staged<kSum, false, NP, U, BIN><<<sgrid, pgx::kThreads, 0, st>>>(mp.batch, lg->pull, ev, \
+                                                                                              S, m_old, m_new, a); \
+  } while (0)
+#define PGX_LAUNCH_STAGED(NP, U)                    \
+  do {                                              \
+    if (lbin) PGX_LAUNCH_STAGED2(NP, U, true);      \
+    else PGX_LAUNCH_STAGED2(NP, U, false);          \
+  } while (0)
+        // uniform groups: wiring staged in shared memory, a contiguous factor range per CTA
+        const bool staged = un >= 1 && un <= 4 && !(plan->disabled_paths & PGX_PATH_STAGED_WIRING);
+        const dim3 sgrid(unsigned((F + pgx::kPullChunk - 1) / pgx::kPullChunk), unsigned(mp.nbt));
+        if (staged && un == 1) PGX_LAUNCH_STAGED(1, 2);
+        else if (staged && un == 2) PGX_LAUNCH_STAGED(2, 2);
+        else if (staged && un == 3) PGX_LAUNCH_STAGED(3, 1);
+        else if (staged && un == 4) PGX_LAUNCH_STAGED(4, 1);
+        else if (un == 1) PGX_LAUNCH_SMALL(1, 2, true);
         else if (un == 2) PGX_LAUNCH_SMALL(2, 2, true);
         else if (un == 3) PGX_LAUNCH_SMALL(3, 1, true);
         else if (un == 4) PGX_LAUNCH_SMALL(4, 1, true);
         else PGX_LAUNCH_SMALL(4, 1, false);
+#undef PGX_LAUNCH_STAGED
+#undef PGX_LAUNCH_STAGED2
 #undef PGX_LAUNCH_SMALL
 #undef PGX_LAUNCH_SMALL2
         if ((rc = check_launch(plan, "k_logical_pull_small"))) return rc;

@@ -101,6 +101,11 @@ def test_pull_equals_two_pass_and_oracle(seed, temperature, batch):
   full, full_d = _run(bp, arrays, 6, temperature, plan.PATH_LOGICAL_BIN)
   np.testing.assert_array_equal(got.ftov_msgs, full.ftov_msgs)
   np.testing.assert_array_equal(got_d, full_d)
+  # the small-factor kernel with its wiring read from global memory per warp iteration
+  # instead of staged per CTA
+  unstaged, unstaged_d = _run(bp, arrays, 6, temperature, plan.PATH_STAGED_WIRING)
+  np.testing.assert_array_equal(got.ftov_msgs, unstaged.ftov_msgs)
+  np.testing.assert_array_equal(got_d, unstaged_d)
   # single-launch wide kernel, everything on one stream
   one, one_d = _run(bp, arrays, 6, temperature, plan.PATH_WIDE_SPLIT | plan.PATH_AUX_STREAM)
   np.testing.assert_array_equal(got.ftov_msgs, one.ftov_msgs)
