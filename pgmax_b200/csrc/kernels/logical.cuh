@@ -733,6 +733,73 @@ k_logical_wide_emit(int batch, LogicalPullDev w, const int32_t* __restrict__ par
   if (kDelta) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
 }
 
+constexpr int kEmitChunk = 512;  // parents per CTA of the staged emit kernel
+
+template <bool kSumProduct, bool kDelta, bool kBin>
+__global__ void __launch_bounds__(kThreads)
+k_logical_wide_emit_staged(int batch, LogicalPullDev w, const int32_t* __restrict__ parent_factor, int64_t num_parents,
+                    View ev, const float* __restrict__ S, const float* __restrict__ m_old,
+                    float* __restrict__ m_new, const float* __restrict__ agg, RunArgs a) {
+  // a CTA owns the contiguous parent range [pbase, pbase + kEmitChunk): wiring and factor index
+  // are staged in shared memory with one coalesced sweep (see k_logical_pull_small_staged)
+  __shared__ int4 wsm[kEmitChunk];
+  __shared__ int32_t fsm[kEmitChunk];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y * 32 + lane;
+  const int64_t pbase = int64_t(blockIdx.x) * kEmitChunk;
+  const int npar = int(min(int64_t(kEmitChunk), num_parents - pbase));
+  for (int t = threadIdx.x; t < npar; t += blockDim.x) {
+    wsm[t] = reinterpret_cast<const int4*>(w.parents + pbase)[t];
+    fsm[t] = parent_factor[pbase + t];
+  }
+  __syncthreads();
+  if (b >= batch) return;
+  const EdgeW* sw = reinterpret_cast<const EdgeW*>(wsm);
+  const size_t tile = blockIdx.y;
+  const float* mo = m_old + tile * msg_rows<kBin>(a) * 32 + lane;
+  float* mn = m_new + tile * msg_rows<kBin>(a) * 32 + lane;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + lane;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + lane : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const float* aggL = agg + tile * size_t(w.num_factors) * kAggRows * 32 + lane;
+  const int off = w.off;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  constexpr int kWarps = kThreads / 32;
+  float dmax = 0.f;
+  for (int j0 = warp * kEmitUnits; j0 < npar; j0 += kWarps * kEmitUnits) {
+    EdgeIn r[kEmitUnits];
+    float g[kEmitUnits][7];
+    int64_t p0[kEmitUnits], p1[kEmitUnits];
+#pragma unroll
+    for (int u = 0; u < kEmitUnits; ++u) {
+      const int j = j0 + u;
+      if (j < npar) {
+        const int f = fsm[j];
+        if (w.uniform > 0) { p0[u] = int64_t(f) * w.uniform; p1[u] = p0[u] + w.uniform; }
+        else { p0[u] = w.parent_ptr[f]; p1[u] = w.parent_ptr[f + 1]; }
+        r[u] = load_edge<kBin, kSumProduct>(sw[j], off, mo, evq, esh, SL);
+        const float* gp = aggL + size_t(f) * kAggRows * 32;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) g[u][k] = gp[k * 32];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kEmitUnits; ++u) {
+      const int64_t i = pbase + j0 + u;
+      if (j0 + u < npar) {
+        LogicalAcc A;
+        A.acc = g[u][0]; A.Sb = g[u][1]; A.d1 = g[u][2]; A.d2 = g[u][3];
+        A.istar = p0[u] + __float_as_int(g[u][4]);
+        float q_p, q_r;
+        edge_q<kBin, kSumProduct>(r[u], off, q_p, q_r);
+        const float x = A.parent_out<kSumProduct>(i, q_r, q_p, g[u][6], g[u][5], T, p1[u] - p0[u] == 1);
+        dmax = fmaxf(dmax, store_edge<kDelta, kBin, kSumProduct>(mn, off, r[u], x, d, one_minus_d));
+      }
+    }
+  }
+  if (kDelta) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+}
+
 // ---------------------------------------------------------------------------
 // K5: Pool update (pgmax/factor/pool.py:328-474).
 // ---------------------------------------------------------------------------

@@ -770,6 +770,8 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
         const dim3 grid2(unsigned(std::min<int64_t>((warps2 + 7) / 8, std::max<int64_t>(1, int64_t(plan->num_sms) * 16 / mp.nbt))),
                          unsigned(mp.nbt));
         const bool split = !(plan->disabled_paths & PGX_PATH_WIDE_SPLIT);
+        const bool stage_emit = !(plan->disabled_paths & PGX_PATH_STAGED_WIRING);
+        const dim3 grid2s(unsigned((lg->num_parents + pgx::kEmitChunk - 1) / pgx::kEmitChunk), unsigned(mp.nbt));
 #define PGX_LAUNCH_WIDE(DELTA, BIN)                                                                              \
   do {                                                                                                          \
     if (!split) {                                                                                               \
@@ -777,8 +779,12 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
     } else {                                                                                                    \
       pgx::k_logical_wide_reduce<kSum, DELTA, BIN><<<grid1, 32, 0, st>>>(mp.batch, lg->pull, ev, S, m_old, m_new, \
                                                                          plan->ws.agg, a);                     \
-      pgx::k_logical_wide_emit<kSum, DELTA, BIN><<<grid2, pgx::kThreads, 0, st>>>(                              \
-          mp.batch, lg->pull, lg->d_parent_factor, lg->num_parents, ev, S, m_old, m_new, plan->ws.agg, a);      \
+      if (stage_emit)                                                                                           \
+        pgx::k_logical_wide_emit_staged<kSum, DELTA, BIN><<<grid2s, pgx::kThreads, 0, st>>>(                    \
+            mp.batch, lg->pull, lg->d_parent_factor, lg->num_parents, ev, S, m_old, m_new, plan->ws.agg, a);    \
+      else                                                                                                      \
+        pgx::k_logical_wide_emit<kSum, DELTA, BIN><<<grid2, pgx::kThreads, 0, st>>>(                            \
+            mp.batch, lg->pull, lg->d_parent_factor, lg->num_parents, ev, S, m_old, m_new, plan->ws.agg, a);    \
     }                                                                                                           \
   } while (0)
         if (delta) {
