@@ -148,3 +148,146 @@ def test_ragged_num_states_flat_layout():
   assert beliefs[varray].shape == (3, 4) and np.isneginf(beliefs[varray][0, 2:]).all()
   decoded = infer.decode_map_states(beliefs)
   assert set(decoded[vdict].keys()) == {"a", "b", "c"}
+
+
+def test_single_and_empty_factor_groups():
+  """fgroup.py:60-140 (tests/fgroup/test_fgroup.py:24-49)."""
+  with pytest.raises(ValueError, match="Cannot create a FactorGroup with no Factor."):
+    fgroup.ORFactorGroup(variables_for_factors=[])
+  A = vgroup.NDVarArray(num_states=2, shape=(10,))  # pylint: disable=invalid-name
+  B = vgroup.NDVarArray(num_states=2, shape=(10,))  # pylint: disable=invalid-name
+  first, second = (A[0], B[0]), (A[1], B[1])
+  or0 = fgroup.ORFactorGroup(variables_for_factors=[first])
+  with pytest.raises(ValueError, match="SingleFactorGroup should only contain one factor. Got 2"):
+    fgroup.SingleFactorGroup(variables_for_factors=[first, second], single_factor=or0)
+  or1 = fgroup.ORFactorGroup(variables_for_factors=[second])
+  assert (or0 < or1) in (True, False)  # factor groups are orderable
+
+
+def test_enum_factor_group_shapes_and_lookup():
+  """fgroup/enum.py:60-207 (tests/fgroup/test_fgroup.py:52-135)."""
+  vg = vgroup.NDVarArray(shape=(2, 2), num_states=3)
+  triples = [[vg[0, 0], vg[0, 1], vg[1, 1]], [vg[0, 1], vg[1, 0], vg[1, 1]]]
+  with pytest.raises(ValueError, match=re.escape("Expected log potentials shape: (1,) or (2, 1). Got (3, 2)")):
+    fgroup.EnumFactorGroup(variables_for_factors=triples, factor_configs=np.zeros((1, 3), dtype=int),
+                           log_potentials=np.zeros((3, 2)))
+  with pytest.raises(ValueError, match=re.escape("Potentials should be floats")):
+    fgroup.EnumFactorGroup(variables_for_factors=triples, factor_configs=np.zeros((1, 3), dtype=int),
+                           log_potentials=np.zeros((2, 1), dtype=int))
+  group = fgroup.EnumFactorGroup(variables_for_factors=triples, factor_configs=np.zeros((1, 3), dtype=int))
+  missing = [vg[0, 0], vg[1, 1]]
+  with pytest.raises(ValueError, match=re.escape(
+      f"The queried factor connected to the set of variables {frozenset(missing)} is not present in the"
+      " factor group.")):
+    _ = group[missing]
+  assert group[[vg[0, 1], vg[1, 0], vg[1, 1]]] == group.factors[1]
+  with pytest.raises(ValueError, match=re.escape("data should be of shape (2, 1) or (2, 9) or (1,). Got (4, 5).")):
+    group.flatten(np.zeros((4, 5)))
+  assert np.all(group.flatten(np.ones(1)) == np.ones(2))
+  assert np.all(group.flatten(np.ones((2, 9))) == np.ones(18))
+  with pytest.raises(ValueError, match=re.escape("Can only unflatten 1D array. Got a 3D array.")):
+    group.unflatten(np.ones((1, 2, 3)))
+  with pytest.raises(ValueError, match=re.escape(
+      "flat_data should be compatible with shape (2, 1) or (2, 9). Got (30,)")):
+    group.unflatten(np.zeros(30))
+  assert np.all(group.unflatten(np.arange(2)) == np.array([[0], [1]]))
+  assert np.all(group.unflatten(np.ones(18)) == np.ones((2, 9)))
+
+
+def test_pairwise_factor_group_shapes():
+  """fgroup/enum.py:210-435 (tests/fgroup/test_fgroup.py:138-230)."""
+  vg = vgroup.NDVarArray(shape=(2, 2), num_states=3)
+  with pytest.raises(ValueError, match=re.escape("log_potential_matrix should be either a 2D array")):
+    fgroup.PairwiseFactorGroup([[vg[0, 0], vg[1, 1]]], np.zeros((1,), dtype=float))
+  with pytest.raises(ValueError, match=re.escape("Potential matrix should be floats")):
+    fgroup.PairwiseFactorGroup([[vg[0, 0], vg[1, 1]]], np.zeros((3, 3), dtype=int))
+  with pytest.raises(ValueError, match=re.escape(
+      "Expected log_potential_matrix for 1 factors. Got log_potential_matrix for 2 factors.")):
+    fgroup.PairwiseFactorGroup([[vg[0, 0], vg[1, 1]]], np.zeros((2, 3, 3), dtype=float))
+  with pytest.raises(ValueError, match=re.escape(
+      "All pairwise factors should connect to exactly 2 variables. Got a factor connecting to 3 variables")):
+    fgroup.PairwiseFactorGroup([[vg[0, 0], vg[1, 1], vg[0, 1]]], np.zeros((3, 3), dtype=float))
+  pair = [vg[0, 0], vg[1, 1]]
+  with pytest.raises(ValueError, match=re.escape(f"The specified pairwise factor {pair}")):
+    fgroup.PairwiseFactorGroup([pair], np.zeros((4, 4), dtype=float))
+  group = fgroup.PairwiseFactorGroup([[vg[0, 0], vg[1, 1]], [vg[1, 0], vg[0, 1]]])
+  with pytest.raises(ValueError, match=re.escape(
+      "data should be of shape (2, 3, 3) or (2, 6) or (3, 3). Got (4, 4).")):
+    group.flatten(np.zeros((4, 4)))
+  assert np.all(group.flatten(np.zeros((3, 3))) == np.zeros(2 * 3 * 3))
+  assert np.all(group.flatten(np.zeros((2, 6))) == np.zeros(12))
+  with pytest.raises(ValueError, match="Can only unflatten 1D array. Got a 2D array"):
+    group.unflatten(np.zeros((10, 20)))
+  assert np.all(group.unflatten(np.zeros(2 * 3 * 3)) == np.zeros((2, 3, 3)))
+  assert np.all(group.unflatten(np.zeros(2 * 6)) == np.zeros((2, 6)))
+  with pytest.raises(ValueError, match=re.escape(
+      "flat_data should be compatible with shape (2, 3, 3) or (2, 6). Got (10,).")):
+    group.unflatten(np.zeros(10))
+
+
+def test_var_dict_checks():
+  """vgroup/vdict.py (tests/vgroup/test_vgroup.py:24-88)."""
+  with pytest.raises(ValueError, match=re.escape("Expected num_states shape (3,). Got (4,).")):
+    vgroup.VarDict(variable_names=(0, 1, 2), num_states=np.full((4,), 2))
+  with pytest.raises(ValueError, match=re.escape("num_states should be an integer or a NumPy array of dtype int")):
+    vgroup.VarDict(variable_names=(0, 1, 2), num_states=np.full((3,), 2, dtype=np.float32))
+  vd = vgroup.VarDict(variable_names=(0, 1, 2), num_states=15)
+  with pytest.raises(ValueError, match="data is referring to a non-existent variable 3"):
+    vd.flatten({3: np.zeros(10)})
+  with pytest.raises(ValueError, match=re.escape(
+      "Variable 2 expects a data array of shape (15,) or (1,). Got (10,).")):
+    vd.flatten({2: np.zeros(10)})
+  with pytest.raises(ValueError, match="Can only unflatten 1D array. Got a 2D array."):
+    vd.unflatten(np.zeros((10, 20)), True)
+  per_var = vd.unflatten(np.zeros(3), False)
+  assert set(per_var.keys()) == {0, 1, 2} and all(np.all(v == 0) for v in per_var.values())
+  with pytest.raises(ValueError, match=re.escape(
+      "flat_data should be shape (num_variable_states(=45),). Got (100,)")):
+    vd.unflatten(np.zeros(100), True)
+  with pytest.raises(ValueError, match=re.escape("flat_data should be shape (num_variables(=3),). Got (100,)")):
+    vd.unflatten(np.zeros(100), False)
+
+
+def test_nd_var_array_checks():
+  """vgroup/varray.py (tests/vgroup/test_vgroup.py:91-187)."""
+  max_size = int(vgroup.vgroup.MAX_SIZE)
+  with pytest.raises(ValueError, match=re.escape(
+      f"Currently only support NDVarArray of size smaller than {max_size}. Got {max_size + 1}")):
+    vgroup.NDVarArray(shape=(max_size + 1,), num_states=2)
+  with pytest.raises(ValueError, match=re.escape("Expected num_states shape (2, 2). Got (2, 3).")):
+    vgroup.NDVarArray(shape=(2, 2), num_states=np.full((2, 3), 2))
+  with pytest.raises(ValueError, match=re.escape("num_states should be an integer or a NumPy array of dtype int")):
+    vgroup.NDVarArray(shape=(2, 2), num_states=np.full((2, 3), 2, dtype=np.float32))
+  grid = vgroup.NDVarArray(shape=(5, 5), num_states=2)
+  assert len(grid[:3, :3]) == 9
+  ragged = vgroup.NDVarArray(shape=(2, 2), num_states=np.array([[1, 2], [3, 4]]))
+  assert repr(grid) and repr(ragged)
+  assert (grid < ragged) in (True, False)
+  with pytest.raises(ValueError, match=re.escape("data should be of shape (2, 2) or (2, 2, 4). Got (3, 3).")):
+    ragged.flatten(np.zeros((3, 3)))
+  assert np.all(ragged.flatten(np.array([[1, 2], [3, 4]])) == np.array([1, 2, 3, 4]))
+  assert np.all(ragged.flatten(np.zeros((2, 2, 4))) == np.zeros((10,)))
+  # deliberate extension: a 2-D input is (batch, flat) - the leading batch axis that replaces
+  # jax.vmap (SURVEY 3.5); anything beyond that is rejected with the reference's message
+  assert ragged.unflatten(np.zeros((3, 10)), True).shape == (3, 2, 2, 4)
+  with pytest.raises(ValueError, match="Can only unflatten 1D array. Got a 3D array."):
+    ragged.unflatten(np.zeros((2, 3, 4)), True)
+  with pytest.raises(ValueError, match=re.escape("flat_data size should be equal to 10. Got size 12.")):
+    ragged.unflatten(np.zeros((12,)), True)
+  with pytest.raises(ValueError, match=re.escape("flat_data size should be equal to 4. Got size 12.")):
+    ragged.unflatten(np.zeros((12,)), False)
+  assert np.all(ragged.unflatten(np.zeros(4), False) == np.zeros((2, 2)))
+  padded = ragged.unflatten(np.zeros(10), True)
+  assert padded.shape == (2, 2, 4)
+  assert np.all(padded[0, 0, :1] == 0) and np.all(padded[0, 1, :2] == 0)
+  assert np.all(padded[1, 0, :3] == 0) and np.all(padded[1, 1] == 0)
+
+
+def test_nd_var_array_repr():
+  """tests/vgroup/test_vgroup.py:190-201."""
+  assert repr(vgroup.NDVarArray(shape=(0,), num_states=np.zeros((0,), int))).startswith(
+      "NDVarArray(shape=(0,), num_states=[]")
+  assert repr(vgroup.NDVarArray(shape=(2,), num_states=np.array([2, 2]))).startswith(
+      "NDVarArray(shape=(2,), num_states=2")
+  assert repr(vgroup.NDVarArray(shape=(2,), num_states=np.array([2, 3]))).startswith(
+      "NDVarArray(shape=(2,), min_num_states=2, max_num_states=3")
