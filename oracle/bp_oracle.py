@@ -56,6 +56,9 @@ class OracleGraph:
   potentials_range: Dict[str, Tuple[int, int]]
   inference_arguments: Dict[str, Dict[str, Any]]
   var_num_states: np.ndarray  # per variable, for decode / marginals
+  # smooth dual LP-MAP only (oracle/sdlp_oracle.py): factor of every edge-state, number of factors
+  factor_indices_for_edge_states: Optional[np.ndarray] = None
+  num_factors: int = 0
 
 
 def graph_from_context(context) -> OracleGraph:
@@ -80,6 +83,8 @@ def graph_from_context(context) -> OracleGraph:
           [vg.num_states.reshape(-1) for vg in fg_state.variable_groups]
           + [np.empty((0,), dtype=np.int64)]
       ),
+      factor_indices_for_edge_states=np.asarray(context.factor_indices_for_edge_states),
+      num_factors=context.num_factors,
   )
 
 
@@ -93,6 +98,13 @@ def graph_from_flat(flat) -> OracleGraph:
   edge_of_es = np.repeat(np.arange(edge_ns.shape[0]), edge_ns)
   vs_of_es = edge_vs[edge_of_es] + (np.arange(num_es) - edge_msg_start[edge_of_es])
   cfg_idx, cfg_es = [], []
+  factor_of_edge = np.zeros((edge_ns.shape[0],), dtype=np.int64)
+  factor_shift = 0
+  for blk in flat.enum_blocks:
+    arity = np.asarray(blk.factor_configs).shape[1]
+    factor_of_edge[blk.first_edge : blk.first_edge + blk.num_factors * arity] = factor_shift + np.repeat(
+        np.arange(blk.num_factors), arity)
+    factor_shift += blk.num_factors
   for blk in flat.enum_blocks:
     cfg = np.asarray(blk.factor_configs, dtype=np.int64)
     K, A = cfg.shape
@@ -118,6 +130,8 @@ def graph_from_flat(flat) -> OracleGraph:
       potentials_range={ENUM: (0, int(flat.num_potentials)), OR: (0, 0), AND: (0, 0), POOL: (0, 0)},
       inference_arguments={ENUM: enum_args, OR: {}, AND: {}, POOL: {}},
       var_num_states=np.asarray(flat.var_num_states, dtype=np.int64),
+      factor_indices_for_edge_states=factor_of_edge[edge_of_es],
+      num_factors=factor_shift,
   )
 
 

@@ -313,3 +313,42 @@ def deconv_evidence(groups, batch, seed=0, pW=0.25, pS=1e-75, pX=1e-100):
   uX = np.zeros((batch,) + X.shape + (2,)); uX[..., 0] = (2 * imgs - 1) * logit(pX)
   return {S: uS + rng.gumbel(size=uS.shape), W: uW + rng.gumbel(size=uW.shape),
           SW: np.zeros((batch,) + SW.shape + (2,)), X: uX}
+
+
+def sdlp_ising_model(grid_size: int = 4, num_states: int = 3, seed: int = 0, scale: float = 0.01):
+  """The "fully connected" categorical Ising model of tests/lp/test_dual_lp.py:44-66: pairwise
+  factors between (i, j) and every (k, l) with k > i and l > j, potentials scale * N(0, 1)."""
+  rng = np.random.RandomState(1000 + seed)
+  variables = vgroup.NDVarArray(num_states=num_states, shape=(grid_size, grid_size))
+  fg = fgraph.FactorGraph(variable_groups=variables)
+  pairs = [[variables[i, j], variables[k, l]]
+           for i in range(grid_size) for j in range(grid_size)
+           for k in range(i + 1, grid_size) for l in range(j + 1, grid_size)]
+  fg.add_factors(fgroup.PairwiseFactorGroup(
+      variables_for_factors=pairs,
+      log_potential_matrix=scale * rng.normal(size=(len(pairs), num_states, num_states))))
+  return fg, variables
+
+
+def sdlp_line_model(line_length: int = 20, seed: int = 0):
+  """Line sparsification with ORFactors (tests/lp/test_dual_lp.py:152-195): bottom variables are
+  on, each is explained by any of its (up to) 3 closest top variables; top variables prefer off."""
+  rng = np.random.RandomState(seed)
+  top = vgroup.NDVarArray(num_states=2, shape=(line_length,))
+  bottom = vgroup.NDVarArray(num_states=2, shape=(line_length,))
+  fg = fgraph.FactorGraph(variable_groups=[top, bottom])
+  vff = []
+  for f in range(line_length):
+    parents = [top[f]]
+    if f >= 1:
+      parents.append(top[f - 1])
+    if f <= line_length - 2:
+      parents.append(top[f + 1])
+    vff.append(parents + [bottom[f]])
+  fg.add_factors(fgroup.ORFactorGroup(vff))
+  ev_bottom = np.zeros((line_length, 2))
+  ev_bottom[..., 0] = -10_000
+  ev_top = np.zeros((line_length, 2))
+  ev_top[..., 1] = -100
+  evidence = {top: ev_top + rng.gumbel(size=ev_top.shape), bottom: ev_bottom}
+  return fg, top, bottom, evidence

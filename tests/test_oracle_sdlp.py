@@ -1,0 +1,89 @@
+"""Pins the oracle's restatement of the smooth dual LP-MAP solver (pgmax/infer/dual_lp.py)
+through the reference's own property tests (no GPU, no stored JAX outputs exist):
+
+  * tests/lp/test_dual_lp.py:30-135 - fully connected 3-state Ising model with a tight
+    relaxation: the dual upper bound meets the energy of the decoded primal (rtol 5e-3),
+    for accelerated gradient descent (T = 1e-3) and subgradient descent (T = 0);
+  * tests/lp/test_dual_lp.py:139-235 - line sparsification with ORFactors: (L + 3) // 3
+    top variables switch on, bounds meet;
+  * the closed-form gradient (dual_lp.py:213-217) equals a central finite difference of the
+    objective on graphs mixing Enum and OR / AND / Pool factors.
+"""
+
+import numpy as np
+import pytest
+
+import models
+from oracle import bp_oracle
+from oracle import sdlp_oracle
+from pgmax_b200 import infer
+
+RTOL = 5e-3  # tests/lp/test_dual_lp.py:27
+
+
+def _bounds(graph, arrays, msgs):
+  upper, _, _, _ = sdlp_oracle.smooth_dual_objval_and_grad(
+      graph, msgs, arrays.log_potentials, arrays.evidence, 0.0)
+  beliefs = bp_oracle.flat_beliefs(graph, msgs, arrays.evidence)
+  states, _, _ = bp_oracle.decode_flat(graph, beliefs)
+  lower = -bp_oracle.compute_energy(graph, arrays.log_potentials, arrays.evidence, states)
+  return upper, lower, states
+
+
+@pytest.mark.parametrize("seed,temp", [(0, 1e-3), (1, 0.0)])
+def test_dual_bounds_meet_on_tight_ising(seed, temp):
+  fg, variables = models.sdlp_ising_model(seed=seed)
+  rng = np.random.RandomState(seed)
+  bp = infer.BP(fg.bp_state)
+  arrays = bp.init(evidence_updates={variables: rng.gumbel(size=(4, 4, 3))})
+  graph = bp_oracle.graph_from_context(bp.context)
+  msgs, objvals = sdlp_oracle.run_with_objvals(
+      graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, temp, 3000)
+  upper, lower, _ = _bounds(graph, arrays, msgs)
+  assert np.isclose(lower, upper, rtol=RTOL)
+  assert objvals[-1] <= objvals[0]
+
+
+def test_line_sparsification_with_or_factors():
+  fg, top, bottom, evidence = models.sdlp_line_model(seed=0)
+  bp = infer.BP(fg.bp_state)
+  arrays = bp.init(evidence_updates=evidence)
+  graph = bp_oracle.graph_from_context(bp.context)
+  msgs, _ = sdlp_oracle.run_with_objvals(
+      graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 1e-3, 5000)
+  upper, lower, states = _bounds(graph, arrays, msgs)
+  assert states[:20].sum() == (20 + 3) // 3
+  assert np.isclose(lower, upper, rtol=RTOL)
+
+
+@pytest.mark.parametrize("kind", ["or", "and", "pool"])
+def test_gradient_is_the_finite_difference_of_the_objective(kind):
+  data = models.logical_pair(kind, seed=3)
+  entry = data["graphs"][0]  # half `kind` factors, half EnumFactors
+  bp = infer.BP(entry[0].bp_state)
+  arrays = models.init_logical(bp, entry, data)
+  graph = bp_oracle.graph_from_context(bp.context)
+  temp, h = 1.0, 2e-2
+  msgs = np.asarray(arrays.ftov_msgs, dtype=np.float32)
+  _, grad, _, _ = sdlp_oracle.smooth_dual_objval_and_grad(
+      graph, msgs, arrays.log_potentials, arrays.evidence, temp)
+  rng = np.random.RandomState(0)
+  for e in rng.choice(msgs.shape[0], size=12, replace=False):
+    vals = []
+    for sign in (1.0, -1.0):
+      moved = msgs.copy()
+      moved[e] += sign * h
+      vals.append(float(sdlp_oracle.smooth_dual_objval_and_grad(
+          graph, moved, arrays.log_potentials, arrays.evidence, temp)[0]))
+    assert abs((vals[0] - vals[1]) / (2 * h) - grad[e]) < 2e-2, (e, vals, grad[e])
+
+
+def test_argument_checks():
+  fg, _ = models.sdlp_ising_model(seed=0)
+  bp = infer.BP(fg.bp_state)
+  arrays = bp.init()
+  graph = bp_oracle.graph_from_context(bp.context)
+  with pytest.raises(ValueError, match="has to be between 0.0 and 1.0"):
+    sdlp_oracle.run_with_objvals(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 1.01, 1)
+  with pytest.raises(ValueError, match="learning rate must be smaller"):
+    sdlp_oracle.run_with_objvals(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 0.01, 1, lr=0.1)
