@@ -177,6 +177,47 @@ int pgx_energy(pgx_plan* plan, void* stream, int64_t batch,
                const float* evidence, int ev_batched,
                const int32_t* map_states, int map_batched, float* energy_out);
 
+/* ---- Smooth dual LP-MAP (replaces SDLP, pgmax/infer/dual_lp.py:60-463) ------------------
+ *
+ * Factor membership of the edges (the reference's factor_indices_for_edge_states,
+ * pgmax/infer/inferer.py:76-98; edges of one factor are contiguous in every wiring the
+ * reference compiles): edges [factor_edge_start[f], factor_edge_start[f + 1]) belong to
+ * factor f.  host array, [num_factors + 1].  Required once before any pgx_sdlp_* call; the
+ * BP entry points do not need it. */
+int pgx_plan_set_factors(pgx_plan* plan, int64_t num_factors, const int32_t* factor_edge_start);
+
+/* One evaluation of smooth_dual_objval_and_grad (dual_lp.py:67-237) at the dual messages
+ * ftov_msgs: the BP updates on vtof = -ftov_msgs with normalize=False and the UNCLIPPED
+ * potentials, per-variable and per-edge softmax / logsumexp at logsumexp_temp (arg-max / max
+ * with ties to the largest index for logsumexp_temp == 0, update_utils.py:26-64,102-131).
+ *   objval_out     [batch]             sum_v L_v + sum_f max over the factor's edges of L_e
+ *   grad_out       [batch, E_s] / NULL (sub)gradient with respect to the dual messages
+ *   bp_updates_out [batch, E_s] / NULL the BP updates   (get_bp_updates, dual_lp.py:411-445)
+ *   edge_vals_out  [batch, num_edges] / NULL  L_e: the per-edge logsumexp (max)
+ * get_primal_upper_bound (dual_lp.py:366-378) is this call at logsumexp_temp == 0. */
+int pgx_sdlp_objval_and_grad(pgx_plan* plan, void* stream, int64_t batch,
+                             const float* log_potentials, int lp_batched,
+                             const float* evidence, int ev_batched,
+                             const float* ftov_msgs, int msgs_batched, float logsumexp_temp,
+                             float* objval_out, float* grad_out, float* bp_updates_out,
+                             float* edge_vals_out);
+
+/* run_with_objvals (dual_lp.py:239-324): num_iters steps of accelerated gradient descent
+ * (logsumexp_temp > 0) or subgradient descent (== 0) on the dual messages, all enqueued on
+ * `stream` with no host synchronisation:
+ *   eta' = m - steps[it] * grad;   m' = eta' + momenta[it] * (eta' - eta);   eta starts as m.
+ * steps / momenta are HOST arrays [num_iters] holding the reference's fp32 scalars
+ * (lr or lr / sqrt(it + 1), and (it + 1) / (it + 4); dual_lp.py:293-309) - the caller owns the
+ * learning-rate policy and its argument checks, as the Python reference does.
+ * ftov_in may be NULL (zeros).  objvals (may be NULL) [batch, num_iters] receives the
+ * objective BEFORE each step.  ftov_out [batch, E_s] may alias ftov_in. */
+int pgx_sdlp_run(pgx_plan* plan, void* stream, int64_t batch,
+                 const float* log_potentials, int lp_batched,
+                 const float* evidence, int ev_batched,
+                 const float* ftov_in, int msgs_batched, float* ftov_out, float* objvals,
+                 int32_t num_iters, const float* steps, const float* momenta,
+                 float logsumexp_temp);
+
 /* End-to-end call with HOST buffers: H2D copies, pgx_bp_run, pgx_decode, D2H
  * copies, then a stream synchronise.  ftov_in_host may be NULL (zeros);
  * ftov_out_host, marginals_out_host, tie_count_out_host, deltas_out_host may be

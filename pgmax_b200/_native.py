@@ -35,6 +35,9 @@ EXPORTED_SYMBOLS = (
     "pgx_decode",
     "pgx_energy",
     "pgx_infer_host",
+    "pgx_plan_set_factors",
+    "pgx_sdlp_objval_and_grad",
+    "pgx_sdlp_run",
     "pgx_plan_launch_count",
     "pgx_plan_set_exact_order",
     "pgx_plan_num_fused_blocks",
@@ -160,6 +163,14 @@ def load() -> ctypes.CDLL:
   lib.pgx_infer_host.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp,
                                  ctypes.c_int, i32, f32, f32, vp, vp, vp, vp, vp]
   lib.pgx_infer_host.restype = ctypes.c_int
+  lib.pgx_plan_set_factors.argtypes = [vp, i64, _i32p]
+  lib.pgx_plan_set_factors.restype = ctypes.c_int
+  lib.pgx_sdlp_objval_and_grad.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp,
+                                           ctypes.c_int, f32, vp, vp, vp, vp]
+  lib.pgx_sdlp_objval_and_grad.restype = ctypes.c_int
+  lib.pgx_sdlp_run.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int,
+                               vp, vp, i32, _f32p, _f32p, f32]
+  lib.pgx_sdlp_run.restype = ctypes.c_int
   lib.pgx_plan_launch_count.argtypes = [vp]
   lib.pgx_plan_launch_count.restype = ctypes.c_int64
   lib.pgx_plan_num_fused_blocks.argtypes = [vp]
@@ -437,6 +448,29 @@ class Plan:
              map_states: int, map_batched: bool, out: int) -> None:
     check(self._lib.pgx_energy(self.handle, stream, batch, lp, int(lp_batched), ev, int(ev_batched),
                                map_states, int(map_batched), out))
+
+  def set_factors(self, factor_edge_start) -> None:
+    """Factor membership of the edges ([num_factors + 1] offsets), needed by the sdlp_* calls."""
+    starts = _i32(factor_edge_start)
+    check(self._lib.pgx_plan_set_factors(self.handle, int(starts.shape[0]) - 1, _ptr(starts)))
+
+  def sdlp_objval_and_grad(self, stream: int, batch: int, lp: int, lp_batched: bool, ev: int,
+                           ev_batched: bool, msgs: int, msgs_batched: bool, logsumexp_temp: float,
+                           objval: int, grad: Optional[int], bp_updates: Optional[int],
+                           edge_vals: Optional[int]) -> None:
+    check(self._lib.pgx_sdlp_objval_and_grad(self.handle, stream, batch, lp, int(lp_batched), ev,
+                                             int(ev_batched), msgs, int(msgs_batched),
+                                             logsumexp_temp, objval, grad, bp_updates, edge_vals))
+
+  def sdlp_run(self, stream: int, batch: int, lp: int, lp_batched: bool, ev: int, ev_batched: bool,
+               msgs_in: Optional[int], msgs_batched: bool, msgs_out: int, objvals: Optional[int],
+               steps: np.ndarray, momenta: np.ndarray, logsumexp_temp: float) -> None:
+    steps = np.ascontiguousarray(steps, dtype=np.float32)
+    momenta = np.ascontiguousarray(momenta, dtype=np.float32)
+    check(self._lib.pgx_sdlp_run(self.handle, stream, batch, lp, int(lp_batched), ev,
+                                 int(ev_batched), msgs_in, int(msgs_batched), msgs_out, objvals,
+                                 int(steps.shape[0]), steps.ctypes.data_as(_f32p),
+                                 momenta.ctypes.data_as(_f32p), logsumexp_temp))
 
   def infer_host(self, stream: int, batch: int, lp: int, lp_batched: bool, ev: int,
                  ev_batched: bool, msgs_in: Optional[int], msgs_batched: bool, num_iters: int,

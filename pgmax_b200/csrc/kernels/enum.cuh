@@ -36,8 +36,11 @@ struct EnumBlockDev {
 // sample); q staged in a per-thread array, edge-state by edge-state walk of
 // the transposed configuration lists.  Exact ascending-config order for both
 // the max and the sum.
+// kRaw (smooth dual LP-MAP, pgmax/infer/dual_lp.py:119-140): the variable->factor message is
+// -m_old, the potentials are NOT clipped, and the update is written as is (normalize=False,
+// no damping, no delta); S is unused.
 // ---------------------------------------------------------------------------
-template <bool kSumProduct>
+template <bool kSumProduct, bool kRaw = false>
 __global__ void __launch_bounds__(kThreads)
 k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
              const float* __restrict__ S, const float* __restrict__ m_old,
@@ -61,7 +64,7 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
     for (int e = 0; e < blk.arity; ++e) {
       const int64_t vs = edge_vs[ebase + e];
       for (int s = blk.edge_off[e]; s < blk.edge_off[e + 1]; ++s)
-        q[s] = SL[(vs + s - blk.edge_off[e]) << sh] - mo[(mbase + s) << sh];
+        q[s] = kRaw ? -mo[(mbase + s) << sh] : SL[(vs + s - blk.edge_off[e]) << sh] - mo[(mbase + s) << sh];
     }
     for (int s = 0; s < blk.ns; ++s) {
       const int j0 = blk.t_ptr[s], j1 = blk.t_ptr[s + 1];
@@ -70,7 +73,7 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
         const int k = blk.t_k[j];
         float sk = 0.f;
         for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
-        sk += clip_lp(lpL.at(pbase + k));
+        sk += kRaw ? lpL.at(pbase + k) : clip_lp(lpL.at(pbase + k));
         M = fmaxf(M, sk);
       }
       float val = M;
@@ -80,26 +83,30 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
           const int k = blk.t_k[j];
           float sk = 0.f;
           for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
-          sk += clip_lp(lpL.at(pbase + k));
+          sk += kRaw ? lpL.at(pbase + k) : clip_lp(lpL.at(pbase + k));
           sum += expf((sk - M) / T);
         }
         val = T * logf(sum) + M;
       }
-      nv[s] = damp(mo[(mbase + s) << sh], val - q[s], a.d, a.one_minus_d);
+      nv[s] = kRaw ? val - q[s] : damp(mo[(mbase + s) << sh], val - q[s], a.d, a.one_minus_d);
     }
-    for (int e = 0; e < blk.arity; ++e) {
-      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
-      float mx = -INFINITY;
-      for (int s = s0; s < s1; ++s) mx = fmaxf(mx, nv[s]);
-      for (int s = s0; s < s1; ++s) {
-        const float out = fmaxf(nv[s] - mx, kMsgNegInf);
-        const int64_t idx = (mbase + s) << sh;
-        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
-        mn[idx] = out;
+    if constexpr (kRaw) {
+      for (int s = 0; s < blk.ns; ++s) mn[(mbase + s) << sh] = nv[s];
+    } else {
+      for (int e = 0; e < blk.arity; ++e) {
+        const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+        float mx = -INFINITY;
+        for (int s = s0; s < s1; ++s) mx = fmaxf(mx, nv[s]);
+        for (int s = s0; s < s1; ++s) {
+          const float out = fmaxf(nv[s] - mx, kMsgNegInf);
+          const int64_t idx = (mbase + s) << sh;
+          dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+          mn[idx] = out;
+        }
       }
     }
   }
-  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+  if (!kRaw) publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
 }
 
 // ---------------------------------------------------------------------------
@@ -120,7 +127,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return r;
 }
 
-template <bool kSumProduct>
+template <bool kSumProduct, bool kRaw = false>  // kRaw: see k_enum_small
 __global__ void __launch_bounds__(kThreads)
 k_enum_big(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
            const float* __restrict__ S, const float* __restrict__ m_old,
@@ -148,7 +155,7 @@ k_enum_big(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, V
       const int64_t vs = edge_vs[ebase + e];
       const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
       for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x)
-        q[s] = SL[(vs + s - s0) << sh] - mo[(mbase + s) << sh];
+        q[s] = kRaw ? -mo[(mbase + s) << sh] : SL[(vs + s - s0) << sh] - mo[(mbase + s) << sh];
     }
     __syncthreads();
     for (int s = threadIdx.x; s < blk.ns; s += blockDim.x) {
@@ -158,7 +165,7 @@ k_enum_big(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, V
         const int k = blk.t_k[j];
         float sk = 0.f;
         for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
-        sk += clip_lp(lpL.at(pbase + k));
+        sk += kRaw ? lpL.at(pbase + k) : clip_lp(lpL.at(pbase + k));
         M = fmaxf(M, sk);
       }
       float val = M;
@@ -168,12 +175,16 @@ k_enum_big(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, V
           const int k = blk.t_k[j];
           float sk = 0.f;
           for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
-          sk += clip_lp(lpL.at(pbase + k));
+          sk += kRaw ? lpL.at(pbase + k) : clip_lp(lpL.at(pbase + k));
           sum += expf((sk - M) / T);
         }
         val = T * logf(sum) + M;
       }
-      nv[s] = damp(mo[(mbase + s) << sh], val - q[s], a.d, a.one_minus_d);
+      nv[s] = kRaw ? val - q[s] : damp(mo[(mbase + s) << sh], val - q[s], a.d, a.one_minus_d);
+    }
+    if (kRaw) {  // every thread wrote nv[s] for the states it now stores
+      for (int s = threadIdx.x; s < blk.ns; s += blockDim.x) mn[(mbase + s) << sh] = nv[s];
+      continue;
     }
     float dmax = 0.f;
     for (int e = 0; e < blk.arity; ++e) {

@@ -115,6 +115,13 @@ struct Workspace {
           n_ties = 0;
 };
 
+// pgx_sdlp_*: per-batch-size buffers of the smooth dual LP-MAP solver (tile-blocked)
+struct SdlpWorkspace {
+  int64_t batch = 0;
+  float *eta = nullptr, *P = nullptr, *vval = nullptr, *eval = nullptr, *grad = nullptr;
+  double* partial = nullptr;
+};
+
 }  // namespace
 
 struct pgx_plan {
@@ -135,6 +142,10 @@ struct pgx_plan {
   std::vector<EnumBlockPlan> enum_blocks;
   LogicalPlan or_f, and_f, pool_f;
   Workspace ws;
+  // smooth dual LP-MAP (pgx_sdlp_*): edges [d_factor_edge_start[f], [f + 1]) belong to factor f
+  int64_t num_factors = 0;
+  int32_t* d_factor_edge_start = nullptr;
+  SdlpWorkspace sdlp;
   // pull mode (every factor is a pairwise-binary enum factor on low-degree variables)
   bool pull_ok = false;
   int2* d_edge_csr = nullptr;          // [num_edges] CSR row (begin, end) of the edge's variable
@@ -1319,6 +1330,9 @@ void pgx_plan_destroy(pgx_plan* plan) {
   free_dev(plan->d_rest_ptr); free_dev(plan->d_rest_edge_msg); free_dev(plan->d_part_first);
   free_dev(plan->d_part_count);
   free_workspace(plan->ws);
+  free_dev(plan->d_factor_edge_start);
+  free_dev(plan->sdlp.eta); free_dev(plan->sdlp.P); free_dev(plan->sdlp.vval); free_dev(plan->sdlp.eval);
+  free_dev(plan->sdlp.grad); free_dev(plan->sdlp.partial);
   for (cudaEvent_t e : plan->prof_events) cudaEventDestroy(e);
   delete plan;
 }
@@ -1984,3 +1998,5 @@ int pgx_infer_host(pgx_plan* plan, void* stream, int64_t batch, const float* lp_
 }
 
 }  // extern "C"
+
+#include "pgx_sdlp.cuh"

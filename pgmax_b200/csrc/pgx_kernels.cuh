@@ -31,3 +31,4 @@
 #include "kernels/enum.cuh"
 #include "kernels/logical.cuh"
 #include "kernels/decode_energy.cuh"
+#include "kernels/sdlp.cuh"

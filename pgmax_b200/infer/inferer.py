@@ -99,6 +99,21 @@ class InfererContext:
     return self._flat_arrays()[:, 2]
 
   @property
+  def factor_edge_start(self) -> np.ndarray:
+    """[num_factors + 1] offsets: edges [start[f], start[f + 1]) belong to factor f (the edges of
+    a factor are contiguous in every compiled wiring; the per-edge form of column 2 above)."""
+    shift, ids = 0, []
+    for ft in factor.FACTOR_TYPES:
+      w = self.wiring[ft]
+      ids.append(np.asarray(w.edge_factor, dtype=np.int64) + shift)
+      shift += w.num_factors
+    ids = np.concatenate(ids) if ids else np.zeros((0,), dtype=np.int64)
+    if ids.size and np.any(np.diff(ids) < 0):
+      raise ValueError("The edges of a factor must be contiguous in the flat layout")
+    counts = np.bincount(ids, minlength=self.num_factors)
+    return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+
+  @property
   def inference_arguments(self) -> Dict[Any, Dict[str, Any]]:
     return {ft: self.wiring[ft].get_inference_arguments() for ft in factor.FACTOR_TYPES}
 

@@ -291,3 +291,33 @@ def test_nd_var_array_repr():
       "NDVarArray(shape=(2,), num_states=2")
   assert repr(vgroup.NDVarArray(shape=(2,), num_states=np.array([2, 3]))).startswith(
       "NDVarArray(shape=(2,), min_num_states=2, max_num_states=3")
+
+
+def test_sdlp_facade_without_a_device():
+  """build_inferer dispatch (pgmax/infer/__init__.py:34-40), the SDLP argument checks
+  (pgmax/infer/dual_lp.py:266-277; tests/lp/test_dual_lp.py:70-90) and the host-side pieces:
+  factor membership of the edges and the per-iteration fp32 scalars."""
+  from pgmax_b200.infer import dual_lp
+  import models
+
+  fg, variables = models.sdlp_ising_model()
+  sdlp = infer.build_inferer(fg.bp_state, backend="sdlp")
+  assert isinstance(sdlp, infer.SmoothDualLP)
+  with pytest.raises(NotImplementedError, match="Inferer other is not supported."):
+    infer.build_inferer(fg.bp_state, backend="other")
+  arrays = sdlp.init()
+  with pytest.raises(ValueError, match="has to be between 0.0 and 1.0"):
+    sdlp.run(arrays, logsumexp_temp=1.01, num_iters=1)
+  with pytest.raises(ValueError, match="the learning rate must be smaller than the log sum-exp temperature"):
+    sdlp.run(arrays, logsumexp_temp=0.01, num_iters=1, lr=0.1)
+  ctx = sdlp.context
+  starts = ctx.factor_edge_start
+  assert starts.shape == (ctx.num_factors + 1,) and starts[0] == 0 and starts[-1] == ctx.num_edges
+  # the same membership as the reference's per-edge-state column (inferer.py:76-98)
+  edge_of_es, factor_of_es = ctx.edge_indices_for_edge_states, ctx.factor_indices_for_edge_states
+  np.testing.assert_array_equal(np.searchsorted(starts, edge_of_es, side="right") - 1, factor_of_es)
+  steps, momenta = dual_lp.step_schedule(4, 0.01, 0.0)
+  np.testing.assert_allclose(steps, 0.01 / np.sqrt(np.arange(1, 5)), rtol=1e-6)
+  np.testing.assert_allclose(momenta, np.arange(1, 5) / np.arange(4, 8), rtol=1e-6)
+  steps, _ = dual_lp.step_schedule(4, 0.25, 0.5)
+  assert np.all(steps == np.float32(0.25))
