@@ -277,6 +277,7 @@ int64_t pgx_plan_compressed_edges(const pgx_plan* plan);
 #define PGX_PATH_PERM_POTENTIALS 512u /* merged max-product launch reads a round-ordered copy of the potentials */
 #define PGX_PATH_HALF_BATCH 1024u /* single-pass mode: the two halves of a batch of >= 16 sample tiles as two pipelined chains on two streams */
 #define PGX_PATH_STAGED_WIRING 2048u /* uniform OR / AND groups: wiring of a CTA's factor range staged in shared memory */
+#define PGX_PATH_TAIL_SPLIT 4096u /* OR / AND graphs: <= 8 samples beyond the last full tile of 32 run on their own stream */
 #define PGX_PATH_LOGICAL_BIN 256u /* ... with the messages in binary-difference storage (one float per edge) */
 int pgx_plan_disable_paths(pgx_plan* plan, uint32_t mask);
 /* 1 if the lattice path is available for this plan. */

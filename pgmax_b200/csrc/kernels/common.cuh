@@ -13,6 +13,7 @@ constexpr float kTempStabThre = 0.5f;  // pgmax/factor/logical.py:33
 constexpr float kLn2 = 0.69314718055994530942f;
 constexpr int kThreads = 256;
 constexpr int kSmallMaxNS = 64;        // enum "small" kernel: edge-states per factor
+constexpr int kTailMaxSamples = 8;     // a batch tail of at most this many samples runs beside the full tiles (pgx.cu)
 
 // How threads map onto (graph element, sample) pairs.
 struct BatchMap {

@@ -148,3 +148,34 @@ def test_pull_deconvolution_batch_40(temperature):
     one, _ = _run(bp, got, 1, temperature, 0)
     want, _ = bp_oracle.run_bp_batched(graph, got.log_potentials, got.ftov_msgs, got.evidence, 1, 0.5, temperature)
     _close_to_oracle(one.ftov_msgs, want, temperature, atol=2e-4)
+
+
+@pytest.mark.parametrize("temperature", [0.0, 0.5])
+@pytest.mark.parametrize("batch", [33, 36])
+def test_batch_tail_runs_beside_the_full_tiles(temperature, batch):
+  """PATH_TAIL_SPLIT: the <= 8 samples beyond the last full tile of 32 go through a second plan
+  (generic kernels) on its own stream.  Bit-identical to the unsplit run - messages, deltas,
+  batched initial messages (second run), launch count includes the tail's kernels."""
+  fg, groups = models.deconv_model(im_height=9, im_width=8, n_feat=2, feat_height=3, feat_width=3)
+  evidence = models.deconv_evidence(groups, batch=batch)
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  arrays = bp.init(evidence_updates=evidence)
+  plan = bp.context.plan
+  before = plan.launch_count
+  ref, ref_d = _run(bp, arrays, 7, temperature, plan.PATH_TAIL_SPLIT)
+  unsplit_launches = plan.launch_count - before
+  before = plan.launch_count
+  got, got_d = _run(bp, arrays, 7, temperature, 0)
+  split_launches = plan.launch_count - before
+  np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
+  np.testing.assert_array_equal(got_d, ref_d)
+  ref2, ref2_d = _run(bp, ref, 5, temperature, plan.PATH_TAIL_SPLIT)
+  got2, got2_d = _run(bp, got, 5, temperature, 0)
+  np.testing.assert_array_equal(got2.ftov_msgs, ref2.ftov_msgs)
+  np.testing.assert_array_equal(got2_d, ref2_d)
+  assert split_launches > unsplit_launches  # the tail's kernels are counted
+  # decode of the split run's messages against the oracle's decode of the same messages
+  graph = bp_oracle.graph_from_context(bp.context)
+  states, _, _ = bp.context.decode(got2)
+  want_states, _, _ = bp_oracle.decode_flat(graph, bp_oracle.flat_beliefs(graph, got2.ftov_msgs, got2.evidence))
+  np.testing.assert_array_equal(states, want_states)
