@@ -228,4 +228,21 @@ k_normalize_edges(BatchMap mp, int64_t num_edges, int64_t Es,
   }
 }
 
+// One sample, wide edges (RCN: 625 states): a warp per edge, lanes stride the edge's contiguous
+// states (coalesced; the thread-per-edge kernel above walks them with a stride of one edge
+// between neighbouring threads).  max is order-independent: same values.
+__global__ void __launch_bounds__(kThreads)
+k_normalize_edges_warp(int64_t num_edges, const int32_t* __restrict__ edge_msg_start, float* __restrict__ m) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gwarp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t e = gwarp; e < num_edges; e += nwarps) {
+    const int64_t s0 = edge_msg_start[e], s1 = edge_msg_start[e + 1];
+    float mx = -INFINITY;
+    for (int64_t s = s0 + lane; s < s1; s += 32) mx = fmaxf(mx, m[s]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int64_t s = s0 + lane; s < s1; s += 32) m[s] = fmaxf(m[s] - mx, kMsgNegInf);
+  }
+}
+
 }  // namespace pgx

@@ -624,6 +624,19 @@ int from_tiles(pgx_plan* plan, cudaStream_t st, const float* src, float* dst, in
   return check_launch(plan, "k_from_tiles");
 }
 
+// normalize_and_clip_msgs on the staged input messages (bp.py:92-96), in place.
+int normalize_edges(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, float* m) {
+  if (plan->num_edges == 0) return PGX_OK;
+  if (mp.batch == 1 && plan->num_edge_states >= 16 * plan->num_edges) {  // wide edges: a warp per edge
+    const int64_t blocks = std::min<int64_t>((plan->num_edges + 7) / 8, int64_t(plan->num_sms) * 16);
+    pgx::k_normalize_edges_warp<<<unsigned(blocks), pgx::kThreads, 0, st>>>(plan->num_edges, plan->d_edge_msg_start, m);
+    return check_launch(plan, "k_normalize_edges_warp");
+  }
+  pgx::k_normalize_edges<<<grid_for(plan, mp, plan->num_edges), pgx::kThreads, 0, st>>>(
+      mp, plan->num_edges, plan->num_edge_states, plan->d_edge_msg_start, m);
+  return check_launch(plan, "k_normalize_edges");
+}
+
 // The fused blocks in ascending message order.
 std::vector<const BipPlan*> bips_by_msg(const pgx_plan* plan) {
   std::vector<const BipPlan*> order;
@@ -1550,10 +1563,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     } else {
       PGX_CUDA(cudaMemcpyAsync(ws.row, ftov_in, size_t(Es) * sizeof(float), cudaMemcpyDeviceToDevice, st));
       if ((flags & PGX_RUN_INPUT_NORMALIZED) == 0) {
-        const pgx::BatchMap mp1 = make_map(1);
-        pgx::k_normalize_edges<<<grid_for(plan, mp1, plan->num_edges), pgx::kThreads, 0, st>>>(
-            mp1, plan->num_edges, Es, plan->d_edge_msg_start, ws.row);
-        if ((rc = check_launch(plan, "k_normalize_edges"))) return rc;
+        if ((rc = normalize_edges(plan, st, make_map(1), ws.row))) return rc;
       }
     }
     int64_t done = 0;
@@ -1591,9 +1601,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
       if ((rc = check_launch(plan, "k_broadcast_rows"))) return rc;
     }
     if ((flags & PGX_RUN_INPUT_NORMALIZED) == 0) {
-      pgx::k_normalize_edges<<<grid_for(plan, mp, plan->num_edges), pgx::kThreads, 0, st>>>(
-          mp, plan->num_edges, Es, plan->d_edge_msg_start, ws.mA);
-      if ((rc = check_launch(plan, "k_normalize_edges"))) return rc;
+      if ((rc = normalize_edges(plan, st, mp, ws.mA))) return rc;
     }
   }
   // the two buffers the generic loop below ping-pongs between

@@ -106,6 +106,26 @@ def test_config3_rcn_random_potentials_round_ordered_copy():
     np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
 
 
+def test_config3_rcn_unnormalised_initial_messages():
+  """One sample, 625-state edges, random (un-normalised, some below the -1e32 clip) initial
+  messages: the input normalisation (bp.py:92-96) runs as a warp per edge
+  (k_normalize_edges_warp); bit-identical to the oracle after 1 and 4 iterations."""
+  from pgmax_b200.infer.bp_state import BPArrays
+  fg, groups, evidence = models.rcn_model(num_models=1, num_vars=6, radii=(2, 4), extra_edges=2, seed=13)
+  bp = infer.BP(fg.bp_state, temperature=0.0)
+  arrays = bp.init(evidence_updates=evidence)
+  rng = np.random.default_rng(3)
+  msgs = (rng.normal(size=arrays.ftov_msgs.shape) * 3.0).astype(np.float32)
+  msgs[rng.integers(0, msgs.size, size=40)] = -3e33
+  arrays = BPArrays(log_potentials=arrays.log_potentials, ftov_msgs=msgs, evidence=arrays.evidence)
+  graph = bp_oracle.graph_from_context(bp.context)
+  for iters in (1, 4):
+    want, want_d = bp_oracle.run_bp(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, iters, 0.5, 0.0)
+    got, got_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5)
+    np.testing.assert_array_equal(got.ftov_msgs, want)
+    np.testing.assert_array_equal(got_d, want_d)
+
+
 def test_config3_rcn_batched_merged_launch():
   """Three samples (different evidence) of a two-model RCN-shaped graph through the merged
   max-product launch: every sample bit-identical to its own single-sample oracle run."""
