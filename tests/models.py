@@ -352,3 +352,55 @@ def sdlp_line_model(line_length: int = 20, seed: int = 0):
   ev_top[..., 1] = -100
   evidence = {top: ev_top + rng.gumbel(size=ev_top.shape), bottom: ev_bottom}
   return fg, top, bottom, evidence
+
+
+def sdlp_pool_model(n_layers: int = 4, choices_per_pool: int = 2):
+  """Hierarchy of PoolFactors (tests/lp/test_bp_for_lp.py:288-315): layer n holds 2^n pool
+  variables; every variable of layer n is the indicator of a pool over 2 choices of layer n + 1."""
+  per_layer = [choices_per_pool**i for i in range(n_layers)]
+  cum = np.insert(np.cumsum(per_layer), 0, 0)
+  variables = vgroup.NDVarArray(num_states=2, shape=(int(cum[-1]),))
+  fg = fgraph.FactorGraph(variable_groups=[variables])
+  vff = []
+  for layer in range(n_layers - 1):
+    start = cum[layer + 1]
+    for indicator in range(cum[layer], cum[layer + 1]):
+      vff.append([variables[start + c] for c in range(choices_per_pool)] + [variables[indicator]])
+      start += choices_per_pool
+  fg.add_factors(fgroup.PoolFactorGroup(vff))
+  return fg, variables
+
+
+def lp_bp_cases():
+  """(name, graph, evidence updates, factor type) of the reference's three
+  convergence / consistency tests (tests/lp/test_bp_for_lp.py:28-391), one seed each."""
+  cases = []
+  fg, variables = sdlp_ising_model(seed=7, scale=1.0)
+  rng = np.random.RandomState(0)
+  cases.append(("enum", fg, {variables: rng.gumbel(size=(4, 4, 3))}, factor.EnumFactor))
+  fg, top, bottom, evidence = sdlp_line_model(seed=1)
+  cases.append(("or", fg, evidence, factor.ORFactor))
+  fg, variables = sdlp_pool_model()
+  updates = np.random.RandomState(2).gumbel(size=(variables.shape[0], 2))
+  updates[0, 1] = 10
+  cases.append(("pool", fg, {variables: updates}, factor.PoolFactor))
+  return cases
+
+
+def check_lp_bp_properties(get_bp_updates, context, temperature, atol=1e-5):
+  """The two properties of tests/lp/test_bp_for_lp.py: (1) the BP updates at a very low temperature
+  are within `temperature` of the max-product updates; (2) the max / logsumexp of a factor's
+  outgoing messages over its configurations is the same at every edge of the factor."""
+  updates_t0, maxes_t0 = get_bp_updates(0.0)
+  updates_t, lse_t = get_bp_updates(temperature)
+  np.testing.assert_allclose(updates_t0, updates_t, atol=temperature, rtol=0)
+  edge_of_es = np.asarray(context.edge_indices_for_edge_states)
+  factor_of_es = np.asarray(context.factor_indices_for_edge_states)
+  factor_of_edge = np.zeros((context.num_edges,), dtype=np.int64)
+  factor_of_edge[edge_of_es] = factor_of_es
+  for vals in (np.asarray(maxes_t0), np.asarray(lse_t)):
+    lo = np.full((context.num_factors,), np.inf)
+    hi = np.full((context.num_factors,), -np.inf)
+    np.minimum.at(lo, factor_of_edge, vals)
+    np.maximum.at(hi, factor_of_edge, vals)
+    np.testing.assert_allclose(lo, hi, atol=atol, rtol=1e-6)

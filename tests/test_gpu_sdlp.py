@@ -166,3 +166,14 @@ def test_zero_iterations_and_shared_messages():
   out, objvals = sdlp.run_with_objvals(arrays, logsumexp_temp=0.5, num_iters=0)
   assert np.asarray(objvals).shape == (3, 0)
   np.testing.assert_array_equal(np.asarray(out.ftov_msgs), np.zeros((3, arrays.ftov_msgs.shape[-1]), np.float32))
+
+
+@pytest.mark.parametrize("temperature", [1e-3, 0.01])
+def test_low_temperature_updates_and_per_factor_consistency(temperature):
+  """tests/lp/test_bp_for_lp.py:28-391 through sdlp.get_bp_updates on the device."""
+  for name, fg, evidence, ftype in models.lp_bp_cases():
+    sdlp = infer.build_inferer(fg.bp_state, backend="sdlp")
+    rng = np.random.RandomState(11)
+    arrays = sdlp.init(evidence_updates=evidence,
+                       ftov_msgs_updates={ftype: rng.normal(size=fg.bp_state.ftov_msgs.value.shape)})
+    models.check_lp_bp_properties(lambda temp: sdlp.get_bp_updates(arrays, temp), sdlp.context, temperature)

@@ -87,3 +87,22 @@ def test_argument_checks():
     sdlp_oracle.run_with_objvals(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 1.01, 1)
   with pytest.raises(ValueError, match="learning rate must be smaller"):
     sdlp_oracle.run_with_objvals(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 0.01, 1, lr=0.1)
+
+
+@pytest.mark.parametrize("temperature", [1e-3, 0.01])
+def test_low_temperature_updates_and_per_factor_consistency(temperature):
+  """tests/lp/test_bp_for_lp.py:28-391 on the oracle (EnumFactors, ORFactors, PoolFactors):
+  pins the normalize=False branches of the closed-form updates at T > 0 to their T = 0 limit."""
+  for name, fg, evidence, ftype in models.lp_bp_cases():
+    bp = infer.BP(fg.bp_state)
+    rng = np.random.RandomState(11)
+    arrays = bp.init(evidence_updates=evidence,
+                     ftov_msgs_updates={ftype: rng.normal(size=fg.bp_state.ftov_msgs.value.shape)})
+    graph = bp_oracle.graph_from_context(bp.context)
+
+    def get_bp_updates(temp):
+      _, _, updates, edge_vals = sdlp_oracle.smooth_dual_objval_and_grad(
+          graph, arrays.ftov_msgs, arrays.log_potentials, arrays.evidence, temp)
+      return updates, edge_vals
+
+    models.check_lp_bp_properties(get_bp_updates, bp.context, temperature)
