@@ -43,6 +43,19 @@ struct LogicalAcc {
     if (dl >= d1) { d2 = d1; d1 = dl; istar = i; }  // first arg-max = LARGEST tied index
     else if (dl > d2) d2 = dl;
   }
+  // add() under a predicate, with selects only (no divergent-branch bookkeeping in unrolled loops)
+  template <bool kSumProduct>
+  __device__ __forceinline__ void add_if(bool on, int64_t i, float a_i, float b_i, float T) {
+    const float dl = a_i - b_i;
+    const float Sb1 = Sb + b_i;
+    const float acc1 = acc + (kSumProduct ? logaddexp_t(a_i, b_i, T) : fmaxf(b_i, a_i));
+    const bool ge = on && dl >= d1, gt = on && !(dl >= d1) && dl > d2;
+    Sb = on ? Sb1 : Sb;
+    acc = on ? acc1 : acc;
+    d2 = ge ? d1 : (gt ? dl : d2);
+    d1 = ge ? dl : d1;
+    istar = ge ? i : istar;
+  }
   template <bool kSumProduct>
   __device__ __forceinline__ float child_relevant(float T) const {
     if (kSumProduct) {
@@ -348,27 +361,24 @@ __device__ __forceinline__ EdgeIn load_edge(const EdgeW& e, int off, const float
   const bool from_s = e.other == -2;
   r.a_p = *(from_s ? SL + (uint32_t(e.vs) << 5) : evq + (uint32_t(e.vs) << esh));
   r.a_r = *(from_s ? SL + (uint32_t(e.vs + off) << 5) : evq + (uint32_t(e.vs + off) << esh));
-  r.o_p = 0.f;
-  r.o_r = 0.f;
-  if (e.other >= 0) load_msg<kBin, kFloor>(mo, e.other, off, r.o_p, r.o_r);
+  // unconditional: an edge without a second edge re-reads its own row (a hit) and edge_q ignores it
+  load_msg<kBin, kFloor>(mo, e.other >= 0 ? e.other : e.msg, off, r.o_p, r.o_r);
   return r;
 }
 // variable -> factor messages (pointed state, relevant state): S - m with S accumulated from
 // the evidence in ascending message index
 template <bool kBin, bool kFloor>
 __device__ __forceinline__ void edge_q(EdgeIn& r, int off, float& q_p, float& q_r) {
+  // branch-free (selects): the same additions in the same order as the nested ifs it replaces
   expand_msg<kBin, kFloor>(off, r.m_p, r.m_r);
-  if (r.kind >= 2) expand_msg<kBin, kFloor>(off, r.o_p, r.o_r);
-  float s_p = r.a_p, s_r = r.a_r;
-  if (r.kind != 0) {
-    const bool other_first = r.kind == 2;
-    s_p += other_first ? r.o_p : r.m_p;
-    s_r += other_first ? r.o_r : r.m_r;
-    if (r.kind >= 2) {
-      s_p += other_first ? r.m_p : r.o_p;
-      s_r += other_first ? r.m_r : r.o_r;
-    }
-  }
+  expand_msg<kBin, kFloor>(off, r.o_p, r.o_r);
+  const bool from_s = r.kind == 0, two = r.kind >= 2, other_first = r.kind == 2;
+  const float f_p = other_first ? r.o_p : r.m_p, f_r = other_first ? r.o_r : r.m_r;
+  const float g_p = other_first ? r.m_p : r.o_p, g_r = other_first ? r.m_r : r.o_r;
+  float s_p = from_s ? r.a_p : r.a_p + f_p;
+  float s_r = from_s ? r.a_r : r.a_r + f_r;
+  s_p = two ? s_p + g_p : s_p;
+  s_r = two ? s_r + g_r : s_r;
   q_p = s_p - r.m_p;
   q_r = s_r - r.m_r;
 }
@@ -646,22 +656,24 @@ k_logical_wide_reduce(int batch, LogicalPullDev w, View ev, const float* __restr
       const int n32 = int(min(int64_t(32), p1 - i32));
 #pragma unroll 1
       for (int c0 = 0; c0 < n32; c0 += kParentChunk) {
+        // the loads of a chunk are unconditional (slots past the last parent re-read the last
+        // parent): no divergent-branch bookkeeping between them, the whole chunk stays in registers
         EdgeIn r[kParentChunk];
 #pragma unroll
         for (int j = 0; j < kParentChunk; ++j) {
+          const int src = min(c0 + j, n32 - 1);
           EdgeW e;
-          e.msg = __shfl_sync(0xffffffffu, held.msg, (c0 + j) & 31);
-          e.vs = __shfl_sync(0xffffffffu, held.vs, (c0 + j) & 31);
-          e.other = __shfl_sync(0xffffffffu, held.other, (c0 + j) & 31);
-          if (c0 + j < n32) r[j] = load_edge<kBin, kSumProduct>(e, off, mo, evq, esh, SL);
+          e.msg = __shfl_sync(0xffffffffu, held.msg, src);
+          e.vs = __shfl_sync(0xffffffffu, held.vs, src);
+          e.other = __shfl_sync(0xffffffffu, held.other, src);
+          r[j] = load_edge<kBin, kSumProduct>(e, off, mo, evq, esh, SL);
         }
 #pragma unroll
-        for (int j = 0; j < kParentChunk; ++j)
-          if (c0 + j < n32) {
-            float q_p, q_r;
-            edge_q<kBin, kSumProduct>(r[j], off, q_p, q_r);
-            A.add<kSumProduct>(i32 + c0 + j, q_r, q_p, T);
-          }
+        for (int j = 0; j < kParentChunk; ++j) {
+          float q_p, q_r;
+          edge_q<kBin, kSumProduct>(r[j], off, q_p, q_r);
+          A.add_if<kSumProduct>(c0 + j < n32, i32 + c0 + j, q_r, q_p, T);
+        }
       }
     }
     float c_p, c_r;
