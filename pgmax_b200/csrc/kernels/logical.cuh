@@ -621,8 +621,16 @@ k_logical_pull_wide(int batch, LogicalPullDev w, View ev, const float* __restric
 // Same arithmetic as k_logical_pull_wide (LogicalAcc), hence bit-identical.
 constexpr int kAggRows = 8;  // acc, Sb, d1, d2, istar - p0 (int bits), c_p, c_r, unused
 
+#ifndef PGX_REDUCE_CHUNK
+#define PGX_REDUCE_CHUNK 8
+#endif
+#ifndef PGX_REDUCE_WARPS
+#define PGX_REDUCE_WARPS 22
+#endif
+constexpr int kReduceChunk = PGX_REDUCE_CHUNK;  // parents gathered together by a reduce warp
+
 template <bool kSumProduct, bool kDelta, bool kBin>
-__global__ void __launch_bounds__(32, 22)  // one warp per CTA: a serial chain holds only its own warp
+__global__ void __launch_bounds__(32, PGX_REDUCE_WARPS)  // one warp per CTA: a serial chain holds only its own warp
 k_logical_wide_reduce(int batch, LogicalPullDev w, View ev, const float* __restrict__ S,
                       const float* __restrict__ m_old, float* __restrict__ m_new, float* __restrict__ agg,
                       RunArgs a) {
@@ -655,12 +663,12 @@ k_logical_wide_reduce(int batch, LogicalPullDev w, View ev, const float* __restr
       if (i32 + 32 + lane < p1) mine = w.parents[i32 + 32 + lane];
       const int n32 = int(min(int64_t(32), p1 - i32));
 #pragma unroll 1
-      for (int c0 = 0; c0 < n32; c0 += kParentChunk) {
+      for (int c0 = 0; c0 < n32; c0 += kReduceChunk) {
         // the loads of a chunk are unconditional (slots past the last parent re-read the last
         // parent): no divergent-branch bookkeeping between them, the whole chunk stays in registers
-        EdgeIn r[kParentChunk];
+        EdgeIn r[kReduceChunk];
 #pragma unroll
-        for (int j = 0; j < kParentChunk; ++j) {
+        for (int j = 0; j < kReduceChunk; ++j) {
           const int src = min(c0 + j, n32 - 1);
           EdgeW e;
           e.msg = __shfl_sync(0xffffffffu, held.msg, src);
@@ -669,7 +677,7 @@ k_logical_wide_reduce(int batch, LogicalPullDev w, View ev, const float* __restr
           r[j] = load_edge<kBin, kSumProduct>(e, off, mo, evq, esh, SL);
         }
 #pragma unroll
-        for (int j = 0; j < kParentChunk; ++j) {
+        for (int j = 0; j < kReduceChunk; ++j) {
           float q_p, q_r;
           edge_q<kBin, kSumProduct>(r[j], off, q_p, q_r);
           A.add_if<kSumProduct>(c0 + j < n32, i32 + c0 + j, q_r, q_p, T);
