@@ -224,6 +224,11 @@ class ClockSampler:
   def stop(self):
     if self.proc is None:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    late = not self.lines
+    if late:  # timed region shorter than nvidia-smi's start-up + one period: take the first sample now
+      deadline = time.time() + 1.5
+      while not self.lines and time.time() < deadline:
+        time.sleep(0.02)
     self.proc.terminate()
     self.thread.join(timeout=2)
     sm, mx, reasons = [], [], set()
@@ -241,7 +246,8 @@ class ClockSampler:
           reasons.add(n)
     return {"sm_mhz": statistics.median(sm) if sm else None,
             "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-            "samples": len(sm)}
+            "samples": len(sm),
+            **({"note": "timed region shorter than one sampling period: sampled right after it"} if late else {})}
 
 
 # ----------------------------------------------------------------------------------------
