@@ -149,10 +149,30 @@ def run_ising_big(args):
   ms = e0.elapsed_time(e1)
   clocks = sampler.stop()
   launches = runner.engine.plan.launch_count - launches0
+  # End to end: every step copies the strip's evidence from pinned host memory and reads the
+  # step's metric (max |message|) back; device time between barriers, max over ranks.
+  e2e_ms, e2e_note = None, None
+  try:
+    ev_host = ev_own.cpu().pin_memory()
+    ev_dev = torch.empty_like(ev_own)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    f0.record()
+    for _ in range(args.steps):
+      ev_dev.copy_(ev_host, non_blocking=True)
+      out, _ = runner.run(ev_dev, iters, 0.5, T)
+      metric = float(out.abs().max().item())  # 4-byte device -> host read, synchronises the step
+    f1.record()
+    barrier()
+    e2e_ms = f0.elapsed_time(f1)
+    h2d_bytes, d2h_bytes = ev_host.numel() * 4, 4
+  except Exception as exc:  # pylint: disable=broad-except
+    e2e_note = f"end-to-end leg failed: {exc}"
   if world > 1:
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, e2e_ms if e2e_ms is not None else -1.0], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    ms = float(t[0].item())
+    e2e_ms = float(t[1].item()) if e2e_ms is not None and float(t[1].item()) > 0 else None
   if rank == 0:
     es = 8 * n * n
     bytes_iter = 17 * es  # 4 * (2 + 0.25 + 1 + 1) * E_s, SURVEY.md 8(d)
@@ -174,6 +194,12 @@ def run_ising_big(args):
                      "iter_ms": iter_s * 1e3},
         "checksum_max_abs_msg": float(msgs.abs().max().item()),
     }
+    if e2e_ms is not None:
+      line["e2e"] = {"value": es * iters * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                     "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
+                     "ms_per_step": e2e_ms / args.steps}
+    else:
+      line["e2e"] = {"value": None, "unit": UNIT, "note": e2e_note}
     print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
