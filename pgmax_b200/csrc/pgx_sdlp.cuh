@@ -20,8 +20,7 @@ int ensure_sdlp(pgx_plan* plan, int64_t batch, bool need_eta, bool need_grad) {
   SdlpWorkspace& w = plan->sdlp;
   const pgx::BatchMap mp = make_map(batch);
   if (w.batch != batch) {
-    free_sdlp(w);
-    w.batch = batch;
+    free_sdlp(w);  // leaves w.batch == 0: a failed allocation below is retried by the next call
     int64_t slots = 0;
     sdlp_objval_grid(plan, mp, &slots);
     const size_t padded = size_t(mp.nbt) << mp.bx_log;
@@ -29,6 +28,7 @@ int ensure_sdlp(pgx_plan* plan, int64_t batch, bool need_eta, bool need_grad) {
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.vval), tiled_floats(mp, plan->num_vars) * sizeof(float)));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.eval), tiled_floats(mp, plan->num_edges) * sizeof(float)));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.partial), size_t(slots) * padded * sizeof(double)));
+    w.batch = batch;
   }
   if (need_eta && w.eta == nullptr)
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.eta), tiled_floats(mp, plan->num_edge_states) * sizeof(float)));
