@@ -404,3 +404,18 @@ def check_lp_bp_properties(get_bp_updates, context, temperature, atol=1e-5):
     np.minimum.at(lo, factor_of_edge, vals)
     np.maximum.at(hi, factor_of_edge, vals)
     np.testing.assert_allclose(lo, hi, atol=atol, rtol=1e-6)
+
+
+def sdlp_and_model(num_rows: int = 10, num_cols: int = 5, p_on: float = 0.8, seed: int = 0):
+  """ANDFactors finding the rows of a binary matrix that are all ones
+  (tests/lp/test_dual_lp.py:242-281).  Returns (fg, matrix, all_ones, evidence updates, ground truth)."""
+  rng = np.random.RandomState(seed)
+  matrix = vgroup.NDVarArray(num_states=2, shape=(num_rows, num_cols))
+  all_ones = vgroup.NDVarArray(num_states=2, shape=(num_rows,))
+  fg = fgraph.FactorGraph(variable_groups=[matrix, all_ones])
+  fg.add_factors(fgroup.ANDFactorGroup(
+      [[matrix[r, c] for c in range(num_cols)] + [all_ones[r]] for r in range(num_rows)]))
+  obs = rng.binomial(1, p_on, (num_rows, num_cols))
+  evidence = np.zeros((num_rows, num_cols, 2))
+  evidence[..., 1] = 1_000 * (2 * obs - 1)
+  return fg, matrix, all_ones, {matrix: evidence}, np.all(obs, axis=1).astype(int)

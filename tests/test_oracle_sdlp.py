@@ -6,6 +6,10 @@ through the reference's own property tests (no GPU, no stored JAX outputs exist)
     for accelerated gradient descent (T = 1e-3) and subgradient descent (T = 0);
   * tests/lp/test_dual_lp.py:139-235 - line sparsification with ORFactors: (L + 3) // 3
     top variables switch on, bounds meet;
+  * tests/lp/test_dual_lp.py:231-306 - ANDFactors finding the all-ones rows of a matrix;
+    tests/lp/test_dual_lp.py:309-402 - a hierarchy of PoolFactors (one variable per layer on);
+  * tests/lp/test_bp_for_lp.py:28-391 - the BP updates at T = 1e-3 / 0.01 are within T of the
+    max-product updates, and the per-edge max / logsumexp is the same at every edge of a factor;
   * the closed-form gradient (dual_lp.py:213-217) equals a central finite difference of the
     objective on graphs mixing Enum and OR / AND / Pool factors.
 """
@@ -106,3 +110,35 @@ def test_low_temperature_updates_and_per_factor_consistency(temperature):
       return updates, edge_vals
 
     models.check_lp_bp_properties(get_bp_updates, bp.context, temperature)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_and_factors_rows_of_ones(seed):
+  """tests/lp/test_dual_lp.py:231-306 on the oracle: the decoded `all_ones` variables are the rows
+  of the observed matrix that are all ones, and the bounds meet."""
+  fg, matrix, all_ones, evidence, truth = models.sdlp_and_model(seed=seed)
+  bp = infer.BP(fg.bp_state)
+  arrays = bp.init(evidence_updates=evidence)
+  graph = bp_oracle.graph_from_context(bp.context)
+  msgs, _ = sdlp_oracle.run_with_objvals(
+      graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 1e-3, 5000)
+  upper, lower, states = _bounds(graph, arrays, msgs)
+  np.testing.assert_array_equal(states[50:], truth)
+  assert np.isclose(lower, upper, rtol=RTOL)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_pool_factor_hierarchy(seed):
+  """tests/lp/test_dual_lp.py:309-402 on the oracle: with the root forced on, exactly one variable
+  per layer switches on, and the bounds meet."""
+  fg, variables = models.sdlp_pool_model()
+  updates = np.random.RandomState(seed).gumbel(size=(variables.shape[0], 2))
+  updates[0, 1] = 1_000
+  bp = infer.BP(fg.bp_state)
+  arrays = bp.init(evidence_updates={variables: updates})
+  graph = bp_oracle.graph_from_context(bp.context)
+  msgs, _ = sdlp_oracle.run_with_objvals(
+      graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 1e-3, 5000)
+  upper, lower, states = _bounds(graph, arrays, msgs)
+  assert states.sum() == 4  # n_layers
+  assert np.isclose(lower, upper, rtol=RTOL)
