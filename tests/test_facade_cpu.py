@@ -321,3 +321,40 @@ def test_sdlp_facade_without_a_device():
   np.testing.assert_allclose(momenta, np.arange(1, 5) / np.arange(4, 8), rtol=1e-6)
   steps, _ = dual_lp.step_schedule(4, 0.25, 0.5)
   assert np.all(steps == np.float32(0.25))
+
+
+def test_heretic_model_construction_and_marginals():
+  """tests/test_pgmax.py:424-475 ("heretic" model): 9 PairwiseFactorGroups between 17-state hidden
+  and 3-state pixel variables, evidence set per group and per variable, 7056 factors; one
+  sum-product iteration (here on the oracle - the device run is in the GPU suite) and
+  get_marginals sums to one."""
+  from oracle import bp_oracle
+  from pgmax_b200.infer import inferer
+
+  im_size = (30, 30)
+  pixel_vars = vgroup.NDVarArray(shape=im_size, num_states=3)
+  hidden_vars = vgroup.NDVarArray(shape=(im_size[0] - 2, im_size[1] - 2), num_states=17)
+  fg = fgraph.FactorGraph([pixel_vars, hidden_vars])
+  w_pot = np.random.RandomState(0).normal(size=(17, 3, 3, 3))
+  for k_row in range(3):
+    for k_col in range(3):
+      fg.add_factors(fgroup.PairwiseFactorGroup(
+          variables_for_factors=[[hidden_vars[r, c], pixel_vars[r + k_row, c + k_col]]
+                                 for r in range(28) for c in range(28)],
+          log_potential_matrix=w_pot[:, :, k_row, k_col]))
+  bp_state = fg.bp_state
+  bp_state.evidence[pixel_vars] = np.zeros((30, 30, 3))
+  bp_state.evidence[pixel_vars[0, 0]] = np.array([0.0, 0.0, 0.0])
+  assert bp_state.evidence[pixel_vars[0, 0]].shape == (3,)
+  assert bp_state.evidence[hidden_vars[0, 0]].shape == (17,)
+  assert isinstance(bp_state.evidence.value, np.ndarray)
+  assert len(sum(fg.factors.values(), ())) == 7056
+  bp = infer.build_inferer(bp_state, backend="bp")
+  arrays = bp.init()
+  graph = bp_oracle.graph_from_context(bp.context)
+  msgs, _ = bp_oracle.run_bp(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 1, 0.5, 1.0)
+  beliefs = inferer.unflatten_beliefs(bp_oracle.flat_beliefs(graph, msgs, arrays.evidence),
+                                      bp_state.fg_state.variable_groups)
+  marginals = infer.get_marginals(beliefs)
+  np.testing.assert_allclose(marginals[pixel_vars].sum(axis=-1), 1.0, atol=1e-6)
+  np.testing.assert_allclose(marginals[hidden_vars].sum(axis=-1), 1.0, atol=1e-6)
