@@ -106,3 +106,22 @@ def test_oracle_energy_reference_test_cases():
   arrays2 = bp2.init()
   assert bp_oracle.compute_energy(graph2, arrays2.log_potentials, arrays2.evidence, [0, 0]) == 0
   assert bp_oracle.compute_energy(graph2, arrays2.log_potentials, arrays2.evidence, [1, 0]) == np.inf
+
+
+def test_oracle_divergent_system_decodes_correctly():
+  """tests/test_clipping.py:24-58 on the oracle: 45 equality factors over 10 binary variables,
+  damping 0, 100 max-product iterations - the messages run into the -1e32 clip and the
+  decoding must still be all ones (the MSG_NEG_INF / NEG_INF split, utils/__init__.py:26-37)."""
+  from pgmax_b200 import fgraph, fgroup, infer, vgroup
+
+  pg_vars = vgroup.NDVarArray(num_states=2, shape=(10,))
+  pairs = [[pg_vars[i], pg_vars[j]] for i in range(10) for j in range(i + 1, 10)]
+  fg = fgraph.FactorGraph(pg_vars)
+  fg.add_factors(fgroup.EnumFactorGroup(variables_for_factors=pairs, factor_configs=np.array([[0, 0], [1, 1]])))
+  bp = infer.BP(fg.bp_state)
+  arrays = bp.init(evidence_updates={pg_vars: np.transpose([np.zeros(10), np.ones(10)])})
+  graph = bp_oracle.graph_from_context(bp.context)
+  msgs, _ = bp_oracle.run_bp(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 100, 0.0, 0.0)
+  assert np.isfinite(msgs).all() and msgs.min() >= -1e32
+  states, _, _ = bp_oracle.decode_flat(graph, bp_oracle.flat_beliefs(graph, msgs, arrays.evidence))
+  assert np.all(states == 1)
