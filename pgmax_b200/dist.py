@@ -10,7 +10,10 @@ CPU tests).  Two modes, as the north-star names them:
 * one giant Ising grid is split into row strips: ``ising_strip`` builds the local
   graph of a rank directly in array form (no per-factor Python objects: the 8192^2
   torus has 134 M factors) and ``StripRunner`` runs BP with ONE halo exchange per
-  iteration.
+  iteration;
+* any other single graph of EnumFactors is cut by factors: ``partition_flat`` /
+  ``PartitionRunner`` (end of this file), one all-reduce of the shared variables'
+  partial sums per iteration.
 
 Halo exchange (torus of n x n variables, variable (i, j) owns the vertical factor
 [(i, j), (i+1, j)] and the horizontal factor [(i, j), (i, j+1)], as
@@ -249,3 +252,186 @@ class StripRunner:
     ev_local = self.torch.zeros(self.strip.num_var_states, dtype=self.torch.float32, device=self.device)
     self._exchange(ev_own, msgs, ev_local)
     return self.engine.beliefs(ev_local, msgs)[: ev_own.shape[0]]
+
+
+# ----------------------------------------------------------------------------------------
+# general partition of one graph of EnumFactors
+# ----------------------------------------------------------------------------------------
+def flat_from_state(fg_state) -> _native.FlatGraph:
+  """FlatGraph of a compiled FactorGraphState that holds EnumFactors only (any arity, ragged
+  numbers of states); graphs with OR / AND / Pool factors are not partitioned yet."""
+  from pgmax_b200 import factor  # pylint: disable=g-import-not-at-top
+
+  for ft in (factor.ORFactor, factor.ANDFactor, factor.PoolFactor):
+    if fg_state.wiring[ft].num_edges:
+      raise NotImplementedError("partition_flat covers graphs of EnumFactors only")
+  w = fg_state.wiring[factor.EnumFactor]
+  var_states = np.concatenate([vg.num_states.reshape(-1) for vg in fg_state.variable_groups]
+                              + [np.empty((0,), dtype=np.int64)])
+  return _native.FlatGraph(
+      var_num_states=var_states.astype(np.int32),
+      edge_var_start=np.asarray(w.edge_var_start, dtype=np.int32),
+      edge_num_states=np.asarray(w.edge_num_states, dtype=np.int32),
+      num_potentials=int(fg_state.log_potentials.shape[0]),
+      enum_blocks=[_native.FlatEnumBlock(num_factors=b.num_factors, factor_configs=np.asarray(b.factor_configs),
+                                         first_edge=b.first_edge, first_potential=b.first_config)
+                   for b in w.blocks])
+
+
+@dataclasses.dataclass
+class GraphPart:
+  """Local graph of one rank of a factor-partitioned graph + the index arrays that tie it to the
+  single graph.  The factors (all blocks, in block order) are cut into contiguous, balanced
+  ranges; a rank's local graph holds its factors and every variable they touch.  Variables touched by more than
+  one rank are "shared": their variable sums need the other ranks' messages."""
+
+  rank: int
+  world: int
+  flat: _native.FlatGraph
+  potential_index: np.ndarray   # [C_local] global potential of every local potential
+  msg_index: np.ndarray         # [E_s local] global message of every local message
+  var_state_index: np.ndarray   # [V_s local] global var-state of every local var-state
+  shared_local_vs: np.ndarray   # local var-states of the shared variables this rank touches
+  shared_slot: np.ndarray       # their slot in the dense exchange vector
+  num_shared: int               # length of the exchange vector (var-states of ALL shared variables)
+
+
+def _block_ranges(flat: _native.FlatGraph, world: int, rank: int):
+  """Per block: (factor lo, factor hi) of this rank.  The factors of all blocks, in block order,
+  are cut into `world` contiguous balanced ranges (graphs made of many small factor groups are
+  balanced too); a block's range is its intersection with the rank's range."""
+  counts = [int(b.num_factors) for b in flat.enum_blocks]
+  lo, hi = shard_bounds(sum(counts), world, rank)
+  out, first = [], 0
+  for n in counts:
+    out.append((min(max(lo - first, 0), n), min(max(hi - first, 0), n)))
+    first += n
+  return out
+
+
+def partition_flat(flat: _native.FlatGraph, world: int, rank: int) -> GraphPart:
+  """Rank `rank`'s part of `flat` (vectorised; every rank derives the same shared-variable list)."""
+  var_ns = np.asarray(flat.var_num_states, dtype=np.int64)
+  var_start = np.concatenate([[0], np.cumsum(var_ns)])
+  edge_vs = np.asarray(flat.edge_var_start, dtype=np.int64)
+  edge_ns = np.asarray(flat.edge_num_states, dtype=np.int64)
+  edge_var = np.searchsorted(var_start, edge_vs, side="right") - 1
+  edge_msg_start = np.cumsum(edge_ns) - edge_ns
+
+  def edges_of(r):
+    """Global edge ids of rank r, block by block (ascending)."""
+    parts = []
+    for b, (lo, hi) in zip(flat.enum_blocks, _block_ranges(flat, world, r)):
+      arity = int(np.asarray(b.factor_configs).shape[1])
+      parts.append(np.arange(b.first_edge + lo * arity, b.first_edge + hi * arity, dtype=np.int64))
+    return np.concatenate(parts) if parts else np.zeros((0,), dtype=np.int64)
+
+  touched = [np.unique(edge_var[edges_of(r)]) for r in range(world)]
+  counts = np.zeros((var_ns.shape[0],), dtype=np.int64)
+  for t in touched:
+    counts[t] += 1
+  shared_vars = np.flatnonzero(counts > 1)
+  shared_ns = var_ns[shared_vars]
+  shared_first_slot = np.cumsum(shared_ns) - shared_ns
+
+  my_edges = edges_of(rank)
+  my_vars = touched[rank]                                  # ascending global ids = local order
+  local_of_var = np.full((var_ns.shape[0],), -1, dtype=np.int64)
+  local_of_var[my_vars] = np.arange(my_vars.shape[0])
+  local_ns = var_ns[my_vars]
+  local_var_start = np.cumsum(local_ns) - local_ns
+  # state 0 of an edge always sits at its variable's first state in this layout
+  local_edge_vs = local_var_start[local_of_var[edge_var[my_edges]]] + (edge_vs[my_edges] - var_start[edge_var[my_edges]])
+
+  blocks, pot_parts, first_edge, first_pot = [], [], 0, 0
+  for b, (lo, hi) in zip(flat.enum_blocks, _block_ranges(flat, world, rank)):
+    cfg = np.asarray(b.factor_configs)
+    k, arity = int(cfg.shape[0]), int(cfg.shape[1])
+    if hi > lo:
+      blocks.append(_native.FlatEnumBlock(num_factors=hi - lo, factor_configs=cfg, first_edge=first_edge,
+                                          first_potential=first_pot))
+      pot_parts.append(np.arange(b.first_potential + lo * k, b.first_potential + hi * k, dtype=np.int64))
+      first_edge += (hi - lo) * arity
+      first_pot += (hi - lo) * k
+  potential_index = np.concatenate(pot_parts) if pot_parts else np.zeros((0,), dtype=np.int64)
+
+  def expand(starts, sizes):
+    """Concatenation of arange(start, start + size) for every (start, size)."""
+    total = int(sizes.sum())
+    if total == 0:
+      return np.zeros((0,), dtype=np.int64)
+    offs = np.arange(total) - np.repeat(np.cumsum(sizes) - sizes, sizes)
+    return np.repeat(starts, sizes) + offs
+
+  msg_index = expand(edge_msg_start[my_edges], edge_ns[my_edges])
+  var_state_index = expand(var_start[my_vars], local_ns)
+  mine_shared = shared_vars[np.isin(shared_vars, my_vars)]
+  pos = np.searchsorted(shared_vars, mine_shared)
+  shared_local_vs = expand(local_var_start[local_of_var[mine_shared]], var_ns[mine_shared])
+  shared_slot = expand(shared_first_slot[pos], shared_ns[pos])
+  local_flat = _native.FlatGraph(
+      var_num_states=local_ns.astype(np.int32), edge_var_start=local_edge_vs.astype(np.int32),
+      edge_num_states=edge_ns[my_edges].astype(np.int32), num_potentials=int(potential_index.shape[0]),
+      enum_blocks=blocks)
+  return GraphPart(rank=rank, world=world, flat=local_flat, potential_index=potential_index, msg_index=msg_index,
+                   var_state_index=var_state_index, shared_local_vs=shared_local_vs, shared_slot=shared_slot,
+                   num_shared=int(shared_ns.sum()))
+
+
+class PartitionRunner:
+  """Loopy BP on one part of a factor-partitioned graph.
+
+  Per iteration ONE collective: every rank adds up, per state of every shared variable, the
+  messages of its own factors (the engine's beliefs with zero evidence), the partial sums are
+  all-reduced over a dense vector of the shared var-states (NCCL over NVLink on the box; gloo in
+  the CPU tests), and a rank's local evidence of a shared variable becomes
+  ``ev + (total - own partial)`` - so that the local variable sum is the full S_v and the local
+  iteration is exactly the single-GPU kernel sequence on the local graph.  As with the row strips
+  the summation order of shared variables differs from the single graph's: results agree to fp32
+  rounding, not bit for bit.  `engine` as in StripRunner.
+  """
+
+  def __init__(self, part: GraphPart, engine, device, group=None):
+    import torch  # pylint: disable=g-import-not-at-top
+
+    self.torch = torch
+    self.part, self.engine, self.device, self.group = part, engine, torch.device(device), group
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+    self.shared_local_vs = to(part.shared_local_vs)
+    self.shared_slot = to(part.shared_slot)
+    self.num_local_vs = int(np.asarray(part.flat.var_num_states, dtype=np.int64).sum())
+    self.num_msgs = int(np.asarray(part.flat.edge_num_states, dtype=np.int64).sum())
+    self.zero_ev = torch.zeros(self.num_local_vs, dtype=torch.float32, device=self.device)
+    self.buf = torch.zeros(max(part.num_shared, 1), dtype=torch.float32, device=self.device)
+
+  def _local_evidence(self, ev, msgs):
+    """Evidence of the local graph for the coming iteration (ev: evidence of the local variables)."""
+    if self.part.world == 1 or self.part.num_shared == 0:
+      return ev
+    import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+
+    partial = self.engine.beliefs(self.zero_ev, msgs)[self.shared_local_vs]
+    self.buf.zero_()
+    self.buf[self.shared_slot] = partial
+    dist.all_reduce(self.buf, group=self.group)
+    ev_local = ev.clone()
+    ev_local[self.shared_local_vs] = ev[self.shared_local_vs] + (self.buf[self.shared_slot] - partial)
+    return ev_local
+
+  def run(self, lp_local, ev_local_vars, num_iters: int, damping: float = 0.5, temperature: float = 0.0, msgs=None):
+    """lp_local: potentials of the local factors (global[potential_index]); ev_local_vars: evidence
+    of the local variables (global[var_state_index]).  Returns the local messages."""
+    torch = self.torch
+    lp = torch.as_tensor(lp_local, dtype=torch.float32, device=self.device).reshape(-1)
+    ev = torch.as_tensor(ev_local_vars, dtype=torch.float32, device=self.device).reshape(-1)
+    cur = torch.zeros(self.num_msgs, dtype=torch.float32, device=self.device) if msgs is None else msgs
+    nxt = torch.empty_like(cur)
+    for _ in range(max(int(num_iters), 1)):
+      self.engine.step(lp, self._local_evidence(ev, cur), cur, nxt, float(damping), float(temperature))
+      cur, nxt = nxt, cur
+    return cur
+
+  def beliefs(self, ev_local_vars, msgs):
+    """Beliefs of the local variables (full sums: one more exchange)."""
+    ev = self.torch.as_tensor(ev_local_vars, dtype=self.torch.float32, device=self.device).reshape(-1)
+    return self.engine.beliefs(self._local_evidence(ev, msgs), msgs)

@@ -176,13 +176,26 @@ class EnumFactor(factor.Factor):
     var_start, num_states, factors = factor.edge_table_for(
         variables_for_factors, vars_to_starts
     )
-    block = EnumBlock(
-        num_factors=num_factors,
-        factor_configs=np.ascontiguousarray(factor_configs, dtype=np.int64),
-        first_edge=0,
-        first_config=0,
-    )
-    return EnumWiring(var_start, num_states, factors, [block])
+    # One block per run of consecutive factors whose variables have the same numbers of states:
+    # inside a block the message / potential offsets are arithmetic progressions (pgx_enum_block).
+    # The reference allows one group to span variables with different numbers of states
+    # (tests/fgraph/test_fgraph.py:285-333); such a group becomes several blocks that share the
+    # configuration table, in the reference's factor order.
+    configs = np.ascontiguousarray(factor_configs, dtype=np.int64)
+    signature = np.asarray(num_states, dtype=np.int64).reshape(num_factors, num_variables)
+    breaks = np.flatnonzero(np.any(signature[1:] != signature[:-1], axis=1)) + 1
+    starts = np.concatenate([[0], breaks]).astype(np.int64)
+    ends = np.concatenate([breaks, [num_factors]]).astype(np.int64)
+    blocks = [
+        EnumBlock(
+            num_factors=int(hi - lo),
+            factor_configs=configs,
+            first_edge=int(lo) * num_variables,
+            first_config=int(lo) * int(configs.shape[0]),
+        )
+        for lo, hi in zip(starts, ends)
+    ]
+    return EnumWiring(var_start, num_states, factors, blocks)
 
   @staticmethod
   def compute_factor_energy(

@@ -121,3 +121,79 @@ def test_batch_sharding_needs_no_collective_and_gathers_in_order():
   out = manager.dict()
   mp.spawn(_batch_worker, args=(2, _free_port(), out), nprocs=2, join=True)
   assert out[0] and out[1]
+
+
+# ---- general factor partition (pdist.partition_flat / PartitionRunner) ----------------------
+def _general_graph(which):
+  """(FactorGraph, evidence updates) of an irregular EnumFactor graph."""
+  if which == "cut":
+    fg, bp_state, grid_vars, additional_vars = models.cut_model()
+    return fg, None
+  rng = np.random.default_rng(5)
+  from pgmax_b200 import fgraph, fgroup, vgroup
+  num_states = rng.integers(2, 6, size=(14,))
+  variables = vgroup.NDVarArray(num_states=num_states, shape=(14,))
+  fg = fgraph.FactorGraph(variable_groups=variables)
+  pairs = [(int(a), int(b)) for a in range(14) for b in range(a + 1, 14) if rng.random() < 0.3]
+  for a, b in pairs:  # ragged numbers of states: one single-factor group per pair
+    fg.add_factors(fgroup.PairwiseFactorGroup(
+        variables_for_factors=[[variables[a], variables[b]]],
+        log_potential_matrix=rng.normal(size=(int(num_states[a]), int(num_states[b])))))
+  triple_cfg = np.array([[0, 0, 0], [1, 1, 0], [0, 1, 1], [1, 0, 1]])
+  fg.add_factors(fgroup.EnumFactorGroup(
+      variables_for_factors=[[variables[0], variables[5], variables[9]], [variables[3], variables[5], variables[12]]],
+      factor_configs=triple_cfg, log_potentials=rng.normal(size=(2, 4))))
+  return fg, {variables: rng.gumbel(size=(14, int(num_states.max())))}
+
+
+def _partition_worker(rank, world, port, which, temperature, iters, out):
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    fg, evidence = _general_graph(which)
+    bp = infer.BP(fg.bp_state, temperature=temperature)
+    arrays = bp.init(evidence_updates=evidence) if evidence is not None else bp.init()
+    flat = pdist.flat_from_state(fg.bp_state.fg_state)
+    part = pdist.partition_flat(flat, world, rank)
+    runner = pdist.PartitionRunner(part, OracleStepEngine(part.flat), "cpu")
+    lp = np.asarray(arrays.log_potentials, np.float32)
+    ev = np.asarray(arrays.evidence, np.float32)
+    msgs = runner.run(lp[part.potential_index], ev[part.var_state_index], iters, 0.5, temperature)
+    beliefs = runner.beliefs(ev[part.var_state_index], msgs)
+    graph = bp_oracle.graph_from_context(bp.context)
+    want, _ = bp_oracle.run_bp(graph, lp, arrays.ftov_msgs, ev, iters, 0.5, temperature)
+    want_b = bp_oracle.flat_beliefs(graph, want, ev)
+    finite = np.isfinite(want_b[part.var_state_index])
+    out[rank] = (float(np.max(np.abs(msgs.numpy() - want[part.msg_index]))),
+                 float(np.max(np.abs(beliefs.numpy()[finite] - want_b[part.var_state_index][finite]))),
+                 int(part.num_shared), int(part.msg_index.shape[0]))
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,which,temperature", [(2, "cut", 0.0), (3, "cut", 1.0), (2, "ragged", 1.0),
+                                                      (3, "ragged", 0.0)])
+def test_factor_partition_matches_single_graph(world, which, temperature):
+  manager = mp.Manager()
+  out = manager.dict()
+  mp.spawn(_partition_worker, args=(world, _free_port(), which, temperature, 10, out), nprocs=world, join=True)
+  assert sorted(out.keys()) == list(range(world))
+  total_msgs = 0
+  for rank in range(world):
+    err_m, err_b, num_shared, num_msgs = out[rank]
+    assert num_shared > 0
+    assert err_m <= 1e-5 and err_b <= 2e-5, (rank, err_m, err_b)
+    total_msgs += num_msgs
+  fg, _ = _general_graph(which)
+  assert total_msgs == fg.bp_state.ftov_msgs.value.shape[0]  # every message is owned by exactly one rank
+
+
+def test_partition_index_arrays_single_rank():
+  """world == 1: the part IS the graph (identity index arrays, nothing shared)."""
+  fg, _ = _general_graph("ragged")
+  flat = pdist.flat_from_state(fg.bp_state.fg_state)
+  part = pdist.partition_flat(flat, 1, 0)
+  np.testing.assert_array_equal(part.msg_index, np.arange(fg.bp_state.ftov_msgs.value.shape[0]))
+  np.testing.assert_array_equal(part.potential_index, np.arange(fg.bp_state.log_potentials.value.shape[0]))
+  assert part.num_shared == 0 and part.shared_local_vs.size == 0
+  np.testing.assert_array_equal(part.flat.edge_var_start, flat.edge_var_start)

@@ -164,3 +164,40 @@ def test_wiring_logical_group_vs_small_groups_vs_single_factors(kind):
   assert len(fg3.factor_groups[factor_cls]) == 10
   assert len(fg1.factors) == len(fg2.factors) == len(fg3.factors)
   _assert_same_flat([fg1, fg2, fg3])
+
+
+def test_group_over_variables_with_different_numbers_of_states_is_split_into_uniform_blocks():
+  """One EnumFactorGroup may span variables with different numbers of states (its configurations
+  only have to be valid for all of them).  The device ABI wants arithmetic message / potential
+  offsets inside a block (pgx_enum_block), so the group compiles to one block per run of factors
+  with the same state signature - same flat arrays as the reference layout, same factor order."""
+  from oracle import bp_oracle
+
+  num_states = np.array([2, 2, 3, 3, 3, 4, 2])
+  variables = vgroup.NDVarArray(num_states=num_states, shape=(7,))
+  fg = fgraph.FactorGraph(variable_groups=variables)
+  pairs = [(0, 1), (0, 6), (2, 3), (3, 4), (5, 2), (1, 6)]  # signatures (2,2) (2,2) (3,3) (3,3) (4,3) (2,2)
+  configs = np.array([[0, 0], [1, 1], [0, 1]])
+  rng = np.random.RandomState(0)
+  fg.add_factors(fgroup.EnumFactorGroup(
+      variables_for_factors=[[variables[a], variables[b]] for a, b in pairs],
+      factor_configs=configs, log_potentials=rng.normal(size=(len(pairs), 3))))
+  wiring = fg.bp_state.fg_state.wiring[factor.EnumFactor]
+  assert [(b.num_factors, b.first_edge, b.first_config) for b in wiring.blocks] == [
+      (2, 0, 0), (2, 4, 6), (1, 8, 12), (1, 10, 15)]
+  # the reference-format rows are those of the same factors added one by one
+  fg_single = fgraph.FactorGraph(variable_groups=variables)
+  lp = np.asarray(fg.bp_state.log_potentials.value).reshape(len(pairs), 3)
+  for (a, b), pot in zip(pairs, lp):
+    fg_single.add_factors(factor.EnumFactor(variables=[variables[a], variables[b]], factor_configs=configs,
+                                            log_potentials=pot))
+  _assert_same_flat([fg, fg_single])
+  # and the flat-graph form the oracle / the device plan consume gives the same update
+  bp = infer.BP(fg.bp_state)
+  arrays = bp.init(evidence_updates={variables: rng.gumbel(size=(7, 4))})
+  from pgmax_b200 import dist as pdist
+  g_ctx = bp_oracle.graph_from_context(bp.context)
+  g_flat = bp_oracle.graph_from_flat(pdist.flat_from_state(fg.bp_state.fg_state))
+  want, _ = bp_oracle.run_bp(g_ctx, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 5, 0.5, 1.0)
+  got, _ = bp_oracle.run_bp(g_flat, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 5, 0.5, 1.0)
+  np.testing.assert_array_equal(got, want)

@@ -1,0 +1,38 @@
+"""GPU: one EnumFactorGroup over variables with different numbers of states (split into uniform
+blocks by the host mirror, pgmax_b200/factor/enum.py compile_wiring) against the oracle.  Runs
+last in the suite (file name): added after the round's last GPU session, validated on CPU only
+(the device sees nothing new - the blocks look like separate factor groups)."""
+
+import numpy as np
+import pytest
+
+from oracle import bp_oracle
+from pgmax_b200 import fgraph, fgroup, infer, vgroup
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("temperature", [0.0, 1.0])
+@pytest.mark.parametrize("batch", [None, 3])
+def test_ragged_enum_factor_group(temperature, batch):
+  num_states = np.array([2, 2, 3, 3, 3, 4, 2])
+  variables = vgroup.NDVarArray(num_states=num_states, shape=(7,))
+  fg = fgraph.FactorGraph(variable_groups=variables)
+  pairs = [(0, 1), (0, 6), (2, 3), (3, 4), (5, 2), (1, 6)]
+  rng = np.random.RandomState(0)
+  fg.add_factors(fgroup.EnumFactorGroup(
+      variables_for_factors=[[variables[a], variables[b]] for a, b in pairs],
+      factor_configs=np.array([[0, 0], [1, 1], [0, 1]]), log_potentials=rng.normal(size=(len(pairs), 3))))
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  shape = (7, 4) if batch is None else (batch, 7, 4)
+  arrays = bp.init(evidence_updates={variables: rng.gumbel(size=shape)})
+  got, got_d = bp.run_with_diffs(arrays, num_iters=8, damping=0.5, temperature=temperature)
+  graph = bp_oracle.graph_from_context(bp.context)
+  want, want_d = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 8, 0.5,
+                                          temperature)
+  atol = 1e-6 if temperature == 0.0 else 1e-5
+  got_m, want_m = np.asarray(got.ftov_msgs), np.asarray(want)
+  floor = want_m <= -1e31
+  np.testing.assert_array_equal(got_m <= -1e31, floor)
+  np.testing.assert_allclose(got_m[~floor], want_m[~floor], atol=atol)
+  np.testing.assert_allclose(got_d, want_d, atol=atol)
