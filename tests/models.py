@@ -255,6 +255,8 @@ def rcn_model(num_models=20, num_vars=80, hps=12, vps=12, radii=(2, 3, 5, 8), ex
     order = rng.permutation(num_vars)
     for k in range(1, num_vars):  # random spanning tree
       pairs.add((int(order[rng.integers(k)]), int(order[k])))
+    if num_vars - 1 + extra_edges > num_vars * (num_vars - 1) // 2:
+      raise ValueError("more edges requested than distinct variable pairs exist")
     while len(pairs) < num_vars - 1 + extra_edges:
       i, j = rng.integers(num_vars, size=2)
       if i != j and (int(i), int(j)) not in pairs and (int(j), int(i)) not in pairs:
