@@ -25,8 +25,8 @@ as fancy assignment (last write wins, as XLA:CPU).
 
 Pinned against the reference's own known answers (tests/test_oracle_golden.py):
 the 84 golden messages + MAP states of tests/test_pgmax.py:63-152,252-265, the
-decoded states stored in benchmark/precomputed_results/ (fixtures under
-tests/golden/), and the reference's OR/AND/Pool-vs-Enum equivalence tests.
+decoded states stored in benchmark/precomputed_results/ for RBMs of 24, 40, 100 and 200
+units (fixtures under tests/golden/), and the reference's OR/AND/Pool-vs-Enum equivalence tests.
 """
 
 import dataclasses

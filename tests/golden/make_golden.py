@@ -17,6 +17,9 @@ benchmark results hold for the BP path:
                    max-product BP, CPU and GPU back-ends, batch size 1
                    (harness benchmark/rbm_lib.py:135-214).  All 24-unit files are
                    identical between the reference's CPU and GPU back-ends.
+  rbm_large.npz    the same for the first 4 RBMs of n_units 40, 100 and 200 after 20 iterations
+                   (the short horizon on which the reference's CPU and GPU back-ends agree,
+                   SURVEY.md §8c), batch size 1.
 """
 
 import ast
@@ -110,7 +113,25 @@ def lift_rbm24(ref_root: str) -> None:
   print("rbm24.npz:", {k: v.shape for k, v in out.items()})
 
 
+def lift_rbm_large(ref_root: str, sizes=(40, 100, 200), count: int = 4) -> None:
+  folder = os.path.join(ref_root, "benchmark", "precomputed_results")
+  out = {}
+  for n in sizes:
+    for idx in range(count):
+      w = _load(os.path.join(folder, f"n_units_{n}_rbm_idx_{idx}_weights.joblib"))
+      for key, arr in zip(("W", "bh", "bv"), (w[0], w[1], w[2]) if not isinstance(w, dict) else (w["W"], w["bh"], w["bv"])):
+        out[f"{key}_{n}_{idx}"] = np.asarray(arr)
+      for backend in ("cpu", "gpu"):
+        r = _load(os.path.join(folder, f"n_units_{n}_rbm_idx_{idx}_pgmax_{backend}_num_iters_20_batch_size_1.joblib"))
+        out[f"hidden_{backend}_{n}_{idx}"] = np.asarray(r["hidden"]).astype(np.int64).reshape(-1)
+        out[f"visible_{backend}_{n}_{idx}"] = np.asarray(r["visible"]).astype(np.int64).reshape(-1)
+        out[f"energy_{backend}_{n}_{idx}"] = np.array(float(np.asarray(r["energy"]).reshape(-1)[0]))
+  np.savez_compressed(os.path.join(HERE, "rbm_large.npz"), **out)
+  print("rbm_large.npz:", len(out), "arrays")
+
+
 if __name__ == "__main__":
   root = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
   lift_e2e_sanity(root)
   lift_rbm24(root)
+  lift_rbm_large(root)

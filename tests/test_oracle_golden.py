@@ -125,3 +125,27 @@ def test_oracle_divergent_system_decodes_correctly():
   assert np.isfinite(msgs).all() and msgs.min() >= -1e32
   states, _, _ = bp_oracle.decode_flat(graph, bp_oracle.flat_beliefs(graph, msgs, arrays.evidence))
   assert np.all(states == 1)
+
+
+@pytest.mark.parametrize("n_units", [40, 100, 200])
+def test_rbm_large_decoded_states_match_reference(n_units):
+  """benchmark/precomputed_results/n_units_{40,100,200}: decoded states and energies after 20
+  max-product iterations (the horizon on which the reference's CPU and GPU back-ends agree,
+  SURVEY.md §8c) - the oracle reproduces them exactly."""
+  gold = np.load(os.path.join(GOLDEN, "rbm_large.npz"))
+  for idx in range(4):
+    W, bh, bv = (gold[f"{k}_{n_units}_{idx}"] for k in ("W", "bh", "bv"))
+    np.testing.assert_array_equal(gold[f"hidden_cpu_{n_units}_{idx}"], gold[f"hidden_gpu_{n_units}_{idx}"])
+    np.testing.assert_array_equal(gold[f"visible_cpu_{n_units}_{idx}"], gold[f"visible_gpu_{n_units}_{idx}"])
+    fg, hidden, visible = models.rbm_model(W, bh, bv)
+    bp = infer.BP(fg.bp_state, temperature=0.0)
+    graph = bp_oracle.graph_from_context(bp.context)
+    arrays = bp.init()
+    msgs, _ = bp_oracle.run_bp(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence,
+                               num_iters=20, damping=0.5, temperature=0.0)
+    states, _, _ = bp_oracle.decode_flat(graph, bp_oracle.flat_beliefs(graph, msgs, arrays.evidence))
+    pred_h, pred_v = states[: bh.shape[0]], states[bh.shape[0] :]
+    np.testing.assert_array_equal(pred_h, gold[f"hidden_cpu_{n_units}_{idx}"])
+    np.testing.assert_array_equal(pred_v, gold[f"visible_cpu_{n_units}_{idx}"])
+    np.testing.assert_allclose(models.rbm_energy(pred_h, pred_v, W, bh, bv), gold[f"energy_cpu_{n_units}_{idx}"],
+                               rtol=1e-5, atol=1e-4)
