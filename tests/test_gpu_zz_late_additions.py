@@ -1,4 +1,7 @@
-"""GPU: one EnumFactorGroup over variables with different numbers of states (split into uniform
+"""GPU tests added after the round's last GPU session (validated against the oracle on CPU only; the file
+name makes them run last).
+
+One EnumFactorGroup over variables with different numbers of states (split into uniform
 blocks by the host mirror, pgmax_b200/factor/enum.py compile_wiring) against the oracle.  Runs
 last in the suite (file name): added after the round's last GPU session, validated on CPU only
 (the device sees nothing new - the blocks look like separate factor groups)."""
@@ -36,3 +39,23 @@ def test_ragged_enum_factor_group(temperature, batch):
   np.testing.assert_array_equal(got_m <= -1e31, floor)
   np.testing.assert_allclose(got_m[~floor], want_m[~floor], atol=atol)
   np.testing.assert_allclose(got_d, want_d, atol=atol)
+
+
+@pytest.mark.parametrize("n_units", [40, 100, 200])
+def test_rbm_large_reference_decodings(n_units):
+  """The reference's stored decodings of 40-, 100- and 200-unit RBMs after 20 max-product
+  iterations (tests/golden/rbm_large.npz, benchmark/precomputed_results/): one sample, serial
+  summation order - the device decodes the same states (as it does for the 24-unit RBMs in
+  test_gpu_parity.py::test_rbm24_reference_decodings)."""
+  import os
+  import models
+
+  gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rbm_large.npz"))
+  for idx in range(4):
+    W, bh, bv = (gold[f"{k}_{n_units}_{idx}"] for k in ("W", "bh", "bv"))
+    fg, hidden, visible = models.rbm_model(W, bh, bv)
+    bp = infer.BP(fg.bp_state, temperature=0.0)
+    out = bp.run(bp.init(), num_iters=20, damping=0.5)
+    states = bp.get_map_states(out)
+    np.testing.assert_array_equal(states[hidden], gold[f"hidden_cpu_{n_units}_{idx}"])
+    np.testing.assert_array_equal(states[visible], gold[f"visible_cpu_{n_units}_{idx}"])
