@@ -59,3 +59,52 @@ def test_rbm_large_reference_decodings(n_units):
     states = bp.get_map_states(out)
     np.testing.assert_array_equal(states[hidden], gold[f"hidden_cpu_{n_units}_{idx}"])
     np.testing.assert_array_equal(states[visible], gold[f"visible_cpu_{n_units}_{idx}"])
+
+
+def _partition_worker(rank, world, port, temperature, iters, out):
+  import os
+  import torch
+  import torch.distributed as dist
+  import models
+  from pgmax_b200 import dist as pdist
+
+  os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+  torch.cuda.set_device(rank)
+  dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+  try:
+    fg, bp_state, _, _ = models.cut_model()
+    bp = infer.BP(bp_state, temperature=temperature)
+    arrays = bp.init()
+    flat = pdist.flat_from_state(bp_state.fg_state)
+    part = pdist.partition_flat(flat, world, rank)
+    dev = f"cuda:{rank}"
+    runner = pdist.PartitionRunner(part, pdist.PgxStepEngine(part.flat, dev), dev)
+    lp = np.asarray(arrays.log_potentials, np.float32)
+    ev = np.asarray(arrays.evidence, np.float32)
+    msgs = runner.run(lp[part.potential_index], ev[part.var_state_index], iters, 0.5, temperature)
+    graph = bp_oracle.graph_from_context(bp.context)
+    want, _ = bp_oracle.run_bp(graph, lp, arrays.ftov_msgs, ev, iters, 0.5, temperature)
+    out[rank] = float(np.max(np.abs(msgs.cpu().numpy() - want[part.msg_index])))
+  finally:
+    dist.destroy_process_group()
+
+
+def _gpu_count():
+  import torch
+  return torch.cuda.device_count()
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("temperature", [0.0, 1.0])
+def test_factor_partition_two_gpus_match_single_graph(temperature):
+  """pdist.partition_flat / PartitionRunner over NCCL on 2 GPUs (the gloo / oracle-engine version
+  of this test runs on CPU in tests/test_dist_gloo.py)."""
+  import socket
+  import torch.multiprocessing as mp
+
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+  out = mp.Manager().dict()
+  mp.spawn(_partition_worker, args=(2, port, temperature, 10, out), nprocs=2, join=True)
+  assert max(out.values()) <= 1e-5, dict(out)
