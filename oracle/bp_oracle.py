@@ -29,6 +29,7 @@ decoded states stored in benchmark/precomputed_results/ for RBMs of 24, 40, 100 
 units (fixtures under tests/golden/), and the reference's OR/AND/Pool-vs-Enum equivalence tests.
 """
 
+import contextlib
 import dataclasses
 from typing import Any, Dict, Optional, Tuple
 
@@ -39,6 +40,23 @@ NEG_INF = F32(-np.inf)            # pgmax/utils/__init__.py:37
 MSG_NEG_INF = F32(-1e32)          # pgmax/utils/__init__.py:26
 LOG_POTENTIAL_MAX_ABS = F32(1e6)  # pgmax/utils/__init__.py:32
 TEMPERATURE_STABILITY_THRE = 0.5  # pgmax/factor/logical.py:33
+
+
+
+@contextlib.contextmanager
+def precision(dtype):
+  """fp64 ARBITER (not a restatement of anything the reference runs): inside
+  ``with precision(np.float64)`` every array this module creates and every operation it
+  performs is float64, from the same fp32 inputs.  Tests use it to tell summation-order
+  noise from real differences: |fp32 path - fp64| of the device against |fp32 oracle - fp64|
+  of the serial restatement itself."""
+  global F32
+  saved, F32 = F32, dtype
+  try:
+    yield
+  finally:
+    F32 = saved
+
 
 ENUM, OR, AND, POOL = "enum", "or", "and", "pool"
 FACTOR_TYPE_ORDER = (ENUM, OR, AND, POOL)  # pgmax/factor/__init__.py:37-43
@@ -414,6 +432,23 @@ def run_bp(graph: OracleGraph, log_potentials, ftov_msgs, evidence, num_iters,
     msgs, delta = bp_update(graph, msgs, ev, lp, damping, T)
     deltas.append(delta)
   return msgs, np.asarray(deltas, dtype=F32)
+
+
+def run_bp_trajectory(graph: OracleGraph, log_potentials, ftov_msgs, evidence, num_iters,
+                      damping=0.5, temperature=0.0):
+  """run_bp for ONE sample that also returns the messages after every iteration:
+  [num_iters, E_s] (the same updates in the same order as run_bp)."""
+  temperature = float(temperature)
+  T = temperature if temperature == 0.0 else F32(temperature)
+  lp = np.clip(np.asarray(log_potentials, dtype=F32), -LOG_POTENTIAL_MAX_ABS, LOG_POTENTIAL_MAX_ABS)
+  ev = np.asarray(evidence, dtype=F32)
+  msgs = normalize_and_clip_msgs(
+      np.asarray(ftov_msgs, dtype=F32), graph.edge_indices_for_edge_states, graph.num_edges)
+  out = []
+  for _ in range(max(int(num_iters), 1)):
+    msgs, _ = bp_update(graph, msgs, ev, lp, damping, T)
+    out.append(msgs)
+  return np.stack(out)
 
 
 def run_bp_batched(graph, log_potentials, ftov_msgs, evidence, num_iters, damping=0.5,

@@ -65,6 +65,10 @@ int upload(const std::vector<T>& host, T** dev, int64_t* bytes) {
 }
 
 enum EnumVariant { kPw2 = 0, kSmall = 1, kBig = 2 };
+// groups of kernels whose shared-memory attribute has been raised (pgx_plan::attr_done)
+enum AttrGroup { kAttrBigMax = 0, kAttrBipMax = 1, kAttrBipSum = 2, kAttrBigEnumMax = 3, kAttrBigEnumSum = 4,
+                 kAttrMaxProd = 5, kAttrLattice = 6, kAttrSdlpMax = 7, kAttrSdlpSum = 8, kAttrLatticeBin = 9,
+                 kAttrOrAnd = 10 };
 
 struct EnumBlockPlan {
   pgx::EnumBlockDev dev{};
@@ -223,7 +227,10 @@ struct pgx_plan {
   float* d_energy_partial = nullptr;  // pgx_energy scratch
   int64_t energy_partial_floats = 0;
   size_t bigmax_smem = 0;
-  unsigned int* d_bigmax_counter = nullptr;
+  unsigned int* d_bigmax_counter = nullptr;  // [2]: one work counter per chain of the half-batch pipeline
+  // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remembered per plan (a plan
+  // lives on one device), bit = kAttr* below
+  uint32_t attr_done = 0;
   // lattice mode (the whole graph is one 2-D nearest-neighbour lattice block; LatticeDev)
   bool lattice_ok = false;
   pgx::LatticeDev lattice{};
@@ -566,13 +573,14 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
     free_dev(ws.mA); free_dev(ws.mB); free_dev(ws.S); free_dev(ws.evT); free_dev(ws.lpT); free_dev(ws.part);
     free_dev(ws.agg); free_dev(ws.cA); free_dev(ws.cB); free_dev(ws.row);
     ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = ws.part = ws.agg = ws.cA = ws.cB = ws.row = nullptr;
-    ws.batch = batch;
+    ws.batch = -1;  // valid only once every allocation below has succeeded (a failed call is retried in full)
     const size_t nm = tiled_floats(mp, plan->num_edge_states) * sizeof(float);
     const size_t nv = tiled_floats(mp, plan->num_var_states) * sizeof(float);
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.mA), nm));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.mB), nm));
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.S), nv));
     PGX_CUDA(cudaMemset(ws.S, 0, nv));  // padded sample slots stay finite
+    ws.batch = batch;
   }
   if (plan->logical_pull_ok && mp.bx_log == 5 && ws.agg == nullptr) {
     int64_t wide = 0;  // factors of the groups that take the two-launch wide update
@@ -581,16 +589,23 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
     if (wide > 0)
       PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.agg), size_t(wide) * pgx::kAggRows * 32 * mp.nbt * sizeof(float)));
   }
-  if (need_part && ws.part == nullptr) {
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.part), tiled_floats(mp, plan->part_rows) * sizeof(float)));
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cA), tiled_floats(mp, plan->c_rows) * sizeof(float)));
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cB), tiled_floats(mp, plan->c_rows) * sizeof(float)));
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.row), size_t(plan->num_edge_states) * sizeof(float)));
+  // lazily allocated buffers: each guarded by its own pointer (a failed allocation leaves the rest retryable)
+  auto lazy = [](float** p, size_t bytes) -> int {
+    if (*p != nullptr) return PGX_OK;
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(p), bytes));
+    return PGX_OK;
+  };
+  int rc;
+  if (need_part) {
+    if ((rc = lazy(&ws.part, tiled_floats(mp, plan->part_rows) * sizeof(float)))) return rc;
+    if ((rc = lazy(&ws.cA, tiled_floats(mp, plan->c_rows) * sizeof(float)))) return rc;
+    if ((rc = lazy(&ws.cB, tiled_floats(mp, plan->c_rows) * sizeof(float)))) return rc;
+    if ((rc = lazy(&ws.row, size_t(plan->num_edge_states) * sizeof(float)))) return rc;
   }
-  if (need_lbin && ws.cA == nullptr) {
+  if (need_lbin) {
     const size_t nc = tiled_floats(mp, plan->num_edge_states / 2) * sizeof(float);
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cA), nc));
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.cB), nc));
+    if ((rc = lazy(&ws.cA, nc))) return rc;
+    if ((rc = lazy(&ws.cB, nc))) return rc;
   }
   if (need_evT && ws.evT == nullptr)
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.evT), tiled_floats(mp, plan->num_var_states) * sizeof(float)));
@@ -661,27 +676,32 @@ template <bool kSum>
 int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::View lp, const float* S,
                const float* m_old, float* m_new, const pgx::RunArgs& a, bool fused, bool lpull, pgx::View ev,
                cudaStream_t aux, const float* c_old = nullptr, float* c_new = nullptr, bool lbin = false,
-               float* part_override = nullptr) {
+               float* part_override = nullptr, int chain = 0) {
   int rc;
+  auto attr_needed = [plan](int group) {
+    const bool need = !((plan->attr_done >> group) & 1u);
+    plan->attr_done |= 1u << group;
+    return need;
+  };
   const bool merged_max = !kSum && plan->bigmax_units > 0 && !(plan->disabled_paths & PGX_PATH_MERGED_MAX);
   if (merged_max) {
     const bool dom = plan->dominant >= 0 && size_t(plan->dominant) < plan->enum_blocks.size() &&
                      plan->enum_blocks[plan->dominant].bigmax >= 0;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (attr_needed(kAttrBigMax)) {
       PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod_all<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod_all<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod_all<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
     }
-    PGX_CUDA(cudaMemsetAsync(plan->d_bigmax_counter, 0, sizeof(unsigned int), st));
+    // the two chains of the half-batch pipeline run this launch concurrently: a counter each
+    unsigned int* const counter = plan->d_bigmax_counter + chain;
+    PGX_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
     if (dom && (rc = prof_mark(plan, st, plan->dominant))) return rc;
     const int per_sm = int(std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / plan->bigmax_smem)));
     const int64_t grid = std::min<int64_t>(plan->bigmax_units * mp.batch, int64_t(plan->num_sms) * per_sm);
     const float* lpR = plan->ws.lpR;
 #define PGX_BIGMAX(FLAT, PERM)                                                                                     \
   pgx::k_enum_big_maxprod_all<FLAT, PERM><<<unsigned(grid), pgx::kThreads, plan->bigmax_smem, st>>>(                \
-      mp, plan->d_bigmax_groups, plan->d_bigmax_units, plan->bigmax_units, plan->d_bigmax_counter, plan->d_edge_vs, \
+      mp, plan->d_bigmax_groups, plan->d_bigmax_units, plan->bigmax_units, counter, plan->d_edge_vs, \
       lp, lpR, S, m_old, m_new, a)
     if (plan->bigmax_perm_active) PGX_BIGMAX(true, true);
     else if (lp.kind != 1) PGX_BIGMAX(true, false);
@@ -710,14 +730,12 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       const int groups = (mp.nbt + warps - 1) / warps;
       const int64_t grid = int64_t(g.NS) * g.NR * groups;
       const size_t smem = pgx::bip_smem_bytes(g.RI, TJ, in_full);
-      static bool attr_set[2] = {false, false};
-      if (!attr_set[kSum]) {
+      if (attr_needed(kSum ? kAttrBipSum : kAttrBipMax)) {
 #define PGX_BIP_ATTR(DELTA, FULL)                                                                          \
   PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pw2_bip<kSum, TJ, DELTA, FULL>,                                 \
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, int(pgx::bip_smem_bytes(32, TJ, FULL))))
         PGX_BIP_ATTR(true, true); PGX_BIP_ATTR(true, false); PGX_BIP_ATTR(false, true); PGX_BIP_ATTR(false, false);
 #undef PGX_BIP_ATTR
-        attr_set[kSum] = true;
       }
       const float* src = in_full ? m_old : c_old;
       const int64_t src_rows = in_full ? a.Es : plan->c_rows;
@@ -747,17 +765,11 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       const size_t smem = size_t(2 * eb.dev.ns + 32) * sizeof(float);
       const int64_t units = F * mp.batch;
       const int grid = int(std::min<int64_t>(units, int64_t(plan->num_sms) * 8));
-      static bool big_attr[2] = {false, false};
-      if (!big_attr[kSum]) {
+      if (attr_needed(kSum ? kAttrBigEnumSum : kAttrBigEnumMax))
         PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big<kSum>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        big_attr[kSum] = true;
-      }
       if (!kSum && eb.dev.sorted0) {
-        static bool mp_attr = false;
-        if (!mp_attr) {
+        if (attr_needed(kAttrMaxProd))
           PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_maxprod, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-          mp_attr = true;
-        }
         pgx::k_enum_big_maxprod<<<grid, pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old,
                                                                    m_new, a);
         if ((rc = check_launch(plan, "k_enum_big_maxprod"))) return rc;
@@ -892,12 +904,23 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
   return PGX_OK;
 }
 
-int check_device(pgx_plan* plan) {
-  int dev = -1;
-  if (cudaGetDevice(&dev) != cudaSuccess) return fail(PGX_ERR_NO_DEVICE, "no CUDA device");
-  if (dev != plan->device) PGX_CUDA(cudaSetDevice(plan->device));
-  return PGX_OK;
-}
+// Makes the plan's device current for the duration of an entry point and restores the caller's
+// device on exit (a caller that holds plans on several GPUs keeps its own current device).
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  int enter(const pgx_plan* plan) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return fail(PGX_ERR_NO_DEVICE, "no CUDA device");
+    if (prev != plan->device) {
+      PGX_CUDA(cudaSetDevice(plan->device));
+      switched = true;
+    }
+    return PGX_OK;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
 
 }  // namespace
 
@@ -1079,7 +1102,7 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       PGX_TRY(upload(groups, &plan->d_bigmax_groups, &plan->device_bytes));
       PGX_TRY(upload(u2, &plan->d_bigmax_units, &plan->device_bytes));
       plan->bigmax_units = int64_t(units.size());
-      if (cudaMalloc(reinterpret_cast<void**>(&plan->d_bigmax_counter), sizeof(unsigned int)) != cudaSuccess)
+      if (cudaMalloc(reinterpret_cast<void**>(&plan->d_bigmax_counter), 2 * sizeof(unsigned int)) != cudaSuccess)
         return bail(fail(PGX_ERR_CUDA, "cudaMalloc failed"));
     }
   }
@@ -1485,7 +1508,8 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   PGX_CHECK(plan->num_var_states == 0 || evidence != nullptr, "evidence is null");
   PGX_CHECK(plan->num_potentials == 0 || log_potentials != nullptr, "log_potentials is null");
   int rc;
-  if ((rc = check_device(plan))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(plan))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const pgx::BatchMap mp = make_map(batch);
   PGX_CHECK(tiled_floats(mp, plan->num_edge_states) < (size_t(1) << 40), "workspace too large");
@@ -1679,14 +1703,13 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
                                      pgx::k_lattice<true, true>};
     static const LatFn stream_fn[4] = {pgx::k_lattice_stream<false, false>, pgx::k_lattice_stream<false, true>,
                                        pgx::k_lattice_stream<true, false>, pgx::k_lattice_stream<true, true>};
-    static bool lat_attr = false;
-    if (!lat_attr) {
+    if (!((plan->attr_done >> kAttrLattice) & 1u)) {
+      plan->attr_done |= 1u << kAttrLattice;
       for (int v = 0; v < 4; ++v) {
         PGX_CUDA(cudaFuncSetAttribute(tile_fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, int(pgx::lattice_smem_bytes())));
         PGX_CUDA(cudaFuncSetAttribute(stream_fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       int(pgx::lattice_stream_smem_bytes())));
       }
-      lat_attr = true;
     }
     plan->dominant_name = stream ? "k_lattice_stream" : "k_lattice";
     for (int it = 0; it < num_iters; ++it) {
@@ -1867,10 +1890,10 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
         const float* c_old_h = c_old ? c_old + off(plan->c_rows) : nullptr;
         if (temperature == 0.f)
           rc = launch_f2v<false>(plan, sh, mph, lp, S_h, cur + off(Es), dst + off(Es), ah, fused, false, evh, nullptr,
-                                 c_old_h, c_new + off(plan->c_rows), false, part_h);
+                                 c_old_h, c_new + off(plan->c_rows), false, part_h, h);
         else
           rc = launch_f2v<true>(plan, sh, mph, lp, S_h, cur + off(Es), dst + off(Es), ah, fused, false, evh, nullptr,
-                                c_old_h, c_new + off(plan->c_rows), false, part_h);
+                                c_old_h, c_new + off(plan->c_rows), false, part_h, h);
         if (rc) return rc;
         if (it + 1 < num_iters) {
           pgx::k_var_reduce<<<grid_for(plan, mph, Vs), pgx::kThreads, 0, sh>>>(
@@ -1940,7 +1963,8 @@ static int decode_impl(pgx_plan* plan, cudaStream_t st, int64_t batch, const flo
   PGX_CHECK(plan->num_var_states == 0 || evidence != nullptr, "evidence is null");
   PGX_CHECK(plan->num_edge_states == 0 || ftov_msgs != nullptr, "ftov_msgs is null");
   int rc;
-  if ((rc = check_device(plan))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(plan))) return rc;
   if (ties) PGX_CUDA(cudaMemsetAsync(ties, 0, size_t(batch) * sizeof(int32_t), st));
   if (plan->num_vars == 0) return PGX_OK;
   const pgx::BatchMap mp = make_map(batch);
@@ -1979,7 +2003,8 @@ int pgx_energy(pgx_plan* plan, void* stream, int64_t batch, const float* log_pot
   PGX_CHECK(plan->num_var_states == 0 || evidence != nullptr, "evidence is null");
   PGX_CHECK(plan->num_potentials == 0 || log_potentials != nullptr, "log_potentials is null");
   int rc;
-  if ((rc = check_device(plan))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(plan))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int slots = 1 + int(plan->enum_blocks.size()) + 3;
   const int64_t need = batch * slots * pgx::kEnergyChunks;
@@ -2050,7 +2075,8 @@ int pgx_infer_host(pgx_plan* plan, void* stream, int64_t batch, const float* lp_
   if (!plan) return fail(PGX_ERR_INVALID, "null plan");
   PGX_CHECK(batch >= 1, "batch must be >= 1");
   int rc;
-  if ((rc = check_device(plan))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(plan))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   Workspace& ws = plan->ws;
   const int64_t n_lp = plan->num_potentials * (lp_batched ? batch : 1);

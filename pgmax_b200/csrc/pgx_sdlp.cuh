@@ -52,10 +52,10 @@ int launch_f2v_raw(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx
     } else {
       const size_t smem = size_t(2 * eb.dev.ns + 32) * sizeof(float);
       const int grid = int(std::min<int64_t>(F * mp.batch, int64_t(plan->num_sms) * 8));
-      static bool attr[2] = {false, false};
-      if (!attr[kSum]) {
+      const int group = kSum ? kAttrSdlpSum : kAttrSdlpMax;
+      if (!((plan->attr_done >> group) & 1u)) {
+        plan->attr_done |= 1u << group;
         PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big<kSum, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr[kSum] = true;
       }
       pgx::k_enum_big<kSum, true><<<grid, pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs, lp, nullptr, m, upd, a);
       if ((rc = check_launch(plan, "k_enum_big<raw>"))) return rc;
@@ -140,7 +140,8 @@ int sdlp_stage(pgx_plan* plan, cudaStream_t st, int64_t batch, const float* log_
   PGX_CHECK(plan->num_var_states == 0 || evidence != nullptr, "evidence is null");
   PGX_CHECK(plan->num_potentials == 0 || log_potentials != nullptr, "log_potentials is null");
   int rc;
-  if ((rc = check_device(plan))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(plan))) return rc;
   const pgx::BatchMap mp = make_map(batch);
   const bool single = batch == 1;
   const bool evT = !single && ev_batched, lpT = !single && lp_batched;
@@ -195,7 +196,8 @@ int pgx_plan_set_factors(pgx_plan* plan, int64_t num_factors, const int32_t* fac
     PGX_CHECK(factor_edge_start[f] <= factor_edge_start[f + 1], "factor_edge_start must be non-decreasing (factor %lld)",
               (long long)f);
   int rc;
-  if ((rc = check_device(plan))) return rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(plan))) return rc;
   free_dev(plan->d_factor_edge_start);
   plan->d_factor_edge_start = nullptr;
   free_sdlp(plan->sdlp);

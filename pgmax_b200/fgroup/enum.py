@@ -76,7 +76,9 @@ class EnumFactorGroup(fgroup.FactorGroup):
 
   def flatten(self, data) -> np.ndarray:
     """(num_configs,) | (F, num_configs) | (F, num_edge_states) -> flat
-    (pgmax/fgroup/enum.py:118-156); one extra leading axis = batch."""
+    (pgmax/fgroup/enum.py:118-156); one extra leading axis = batch.  The reference's shapes
+    are matched FIRST: a (B, num_configs) array with B == num_factors is per-factor data, not a
+    batch of shared rows (pass (B, F, num_configs) to say "batch" unambiguously)."""
     data = _as_host(data)
     nf, nc, width = self.num_factors, self.factor_configs.shape[0], self._message_width()
     if data.shape == (nc,):
@@ -178,7 +180,8 @@ class PairwiseFactorGroup(fgroup.FactorGroup):
 
   def flatten(self, data) -> np.ndarray:
     """(n0, n1) | (F, n0, n1) | (F, n0 + n1) -> flat (pgmax/fgroup/enum.py:345-381);
-    one extra leading axis = batch."""
+    one extra leading axis = batch.  The reference's shapes are matched first: a (B, n0, n1)
+    array with B == num_factors is per-factor data (pass (B, F, n0, n1) for a batch)."""
     data = _as_host(data)
     nf = self.num_factors
     pair = tuple(self.log_potential_matrix.shape[-2:])

@@ -38,8 +38,12 @@ class BPArrays:
   def __post_init__(self):
     for field in dataclasses.fields(self):
       value = getattr(self, field.name)
-      if isinstance(value, np.ndarray):
-        value.flags.writeable = False
+      if isinstance(value, np.ndarray) and value.flags.writeable:
+        # a read-only VIEW: the caller's own buffer stays writable (the reference's arrays are
+        # immutable jnp arrays, pgmax/infer/bp_state.py:45-48; ours alias user memory)
+        view = value.view()
+        view.flags.writeable = False
+        object.__setattr__(self, field.name, view)
 
   @property
   def batch_size(self) -> Optional[int]:

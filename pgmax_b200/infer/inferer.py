@@ -242,9 +242,17 @@ class InfererContext:
     out, start = {}, 0
     for vg in self.bp_state.fg_state.variable_groups:
       n = int(np.prod(vg.num_states.shape))
-      out[vg] = vg.unflatten(flat_states[..., start : start + n], False)
+      out[vg] = _unflatten(vg, flat_states[..., start : start + n], False)
       start += n
     return out
+
+
+def _unflatten(vg, flat, per_state: bool):
+  """vg.unflatten, or its batched form for [B, n] data (VarDict.unflatten itself keeps the
+  reference's 1-D-only contract)."""
+  if getattr(flat, "ndim", 1) == 2 and hasattr(vg, "unflatten_batch"):
+    return vg.unflatten_batch(flat, per_state)
+  return vg.unflatten(flat, per_state)
 
 
 def unflatten_beliefs(flat_beliefs, variable_groups: Sequence[vgroup.VarGroup]) -> Dict[Hashable, Any]:
@@ -252,7 +260,7 @@ def unflatten_beliefs(flat_beliefs, variable_groups: Sequence[vgroup.VarGroup]) 
   beliefs, start = {}, 0
   for vg in variable_groups:
     length = int(vg.num_states.sum())
-    beliefs[vg] = vg.unflatten(flat_beliefs[..., start : start + length], True)
+    beliefs[vg] = _unflatten(vg, flat_beliefs[..., start : start + length], True)
     start += length
   return beliefs
 

@@ -69,16 +69,28 @@ class VarDict(vgroup.VarGroup):
   def unflatten(
       self, flat_data, per_state: bool
   ) -> Dict[Hashable, np.ndarray]:
-    """Flat vector -> dict (reference pgmax/vgroup/vdict.py:129-189)."""
+    """Flat vector -> dict (reference pgmax/vgroup/vdict.py:129-189; 1-D input only, as
+    the reference - the batch axis goes through unflatten_batch)."""
     flat_data = _as_host(flat_data)
     if flat_data.ndim != 1:
       raise ValueError(
           f"Can only unflatten 1D array. Got a {flat_data.ndim}D array."
       )
+    return self._unflatten(flat_data, per_state)
+
+  def unflatten_batch(self, flat_data, per_state: bool) -> Dict[Hashable, np.ndarray]:
+    """[B, flat] -> dict of arrays with a leading batch axis (the batch axis that replaces
+    jax.vmap; used by InfererContext.get_beliefs / unflatten_states)."""
+    flat_data = _as_host(flat_data)
+    if flat_data.ndim != 2:
+      raise ValueError(f"Can only unflatten a (batch, flat) array. Got a {flat_data.ndim}D array.")
+    return self._unflatten(flat_data, per_state)
+
+  def _unflatten(self, flat_data, per_state: bool) -> Dict[Hashable, np.ndarray]:
     num_variables = len(self.variable_names)
     if per_state:
       total = int(self.num_states.sum())
-      if flat_data.shape[0] != total:
+      if flat_data.shape[-1] != total:
         raise ValueError(
             "flat_data should be shape "
             f"(num_variable_states(={total}),). Got "
@@ -86,13 +98,13 @@ class VarDict(vgroup.VarGroup):
         )
       bounds = np.concatenate([[0], np.cumsum(self.num_states)])
       return {
-          name: flat_data[bounds[i] : bounds[i + 1]]
+          name: flat_data[..., bounds[i] : bounds[i + 1]]
           for i, name in enumerate(self.variable_names)
       }
-    if flat_data.shape[0] != num_variables:
+    if flat_data.shape[-1] != num_variables:
       raise ValueError(
           "flat_data should be shape "
           f"(num_variables(={num_variables}),). Got "
           f"{flat_data.shape}"
       )
-    return dict(zip(self.variable_names, flat_data))
+    return {name: flat_data[..., i] for i, name in enumerate(self.variable_names)}

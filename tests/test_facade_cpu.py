@@ -358,3 +358,37 @@ def test_heretic_model_construction_and_marginals():
   marginals = infer.get_marginals(beliefs)
   np.testing.assert_allclose(marginals[pixel_vars].sum(axis=-1), 1.0, atol=1e-6)
   np.testing.assert_allclose(marginals[hidden_vars].sum(axis=-1), 1.0, atol=1e-6)
+
+
+def test_vardict_unflatten_batch_keeps_the_batch_axis():
+  """The batch axis that replaces jax.vmap reaches a VarDict as [B, n] arrays (through
+  get_beliefs / unflatten_states -> VarDict.unflatten_batch); VarDict.unflatten itself keeps the
+  reference's 1-D contract (pgmax/vgroup/vdict.py:129-189, test_var_dict_checks above)."""
+  vd = vgroup.VarDict(variable_names=("a", "b"), num_states=np.array([2, 3]))
+  flat = np.arange(10, dtype=np.float32).reshape(2, 5)
+  out = vd.unflatten_batch(flat, True)
+  np.testing.assert_array_equal(out["a"], flat[:, :2])
+  np.testing.assert_array_equal(out["b"], flat[:, 2:])
+  per_var = vd.unflatten_batch(np.array([[0, 2], [1, 1]]), False)
+  np.testing.assert_array_equal(per_var["a"], [0, 1])
+  np.testing.assert_array_equal(per_var["b"], [2, 1])
+  beliefs = infer.inferer.unflatten_beliefs(flat, [vd])
+  np.testing.assert_array_equal(beliefs[vd]["b"], flat[:, 2:])
+  with pytest.raises(ValueError, match="batch, flat"):
+    vd.unflatten_batch(np.zeros((2, 2, 5)), True)
+  with pytest.raises(ValueError, match="flat_data should be shape"):
+    vd.unflatten_batch(np.zeros((2, 4)), True)
+
+
+def test_bp_arrays_do_not_freeze_the_callers_buffers():
+  """BPArrays are immutable like the reference's (pgmax/infer/bp_state.py:45-48) but hold
+  read-only VIEWS: the arrays the user passed in stay writable."""
+  from pgmax_b200.infer.bp_state import BPArrays
+  lp, msgs, ev = (np.zeros(4, np.float32) for _ in range(3))
+  arrays = BPArrays(log_potentials=lp, ftov_msgs=msgs, evidence=ev)
+  assert not arrays.evidence.flags.writeable
+  with pytest.raises(ValueError):
+    arrays.evidence[0] = 1.0
+  ev[0] = 2.0  # still the caller's buffer
+  assert lp.flags.writeable and msgs.flags.writeable and ev.flags.writeable
+  assert arrays.evidence[0] == 2.0

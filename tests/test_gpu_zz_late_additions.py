@@ -108,3 +108,72 @@ def test_factor_partition_two_gpus_match_single_graph(temperature):
   out = mp.Manager().dict()
   mp.spawn(_partition_worker, args=(2, port, temperature, 10, out), nprocs=2, join=True)
   assert max(out.values()) <= 1e-5, dict(out)
+
+
+@pytest.mark.parametrize("temperature", [0.0])
+def test_half_batch_pipeline_with_merged_max_product_blocks(temperature):
+  """A dense pairwise-binary grid (single-pass kernel, half-batch pipeline at >= 16 sample tiles)
+  in the same graph as large sorted pairwise EnumFactors (merged max-product launch, work units
+  handed out through an atomic counter): the two half-batch chains run that launch concurrently,
+  each on its own counter.  Pipeline on == pipeline off, bit for bit, and == the oracle for a few
+  samples of both halves."""
+  rng = np.random.RandomState(0)
+  rows = vgroup.NDVarArray(num_states=2, shape=(6,))
+  cols = vgroup.NDVarArray(num_states=2, shape=(9,))
+  wide = vgroup.NDVarArray(num_states=40, shape=(4,))
+  fg = fgraph.FactorGraph(variable_groups=[rows, cols, wide])
+  lpm = np.zeros((54, 2, 2))
+  lpm[:, 1, 1] = 0.4 * rng.normal(size=54)
+  fg.add_factors(fgroup.PairwiseFactorGroup(
+      variables_for_factors=[[rows[i], cols[j]] for i in range(6) for j in range(9)], log_potential_matrix=lpm))
+  configs = np.stack(np.meshgrid(np.arange(40), np.arange(40), indexing="ij"), axis=-1).reshape(-1, 2)
+  configs = configs[np.abs(configs[:, 0] - configs[:, 1]) <= 9]  # banded, sorted by the first state
+  pairs = [(0, 1), (1, 2), (2, 3), (3, 0), (0, 2)]
+  fg.add_factors(fgroup.EnumFactorGroup(
+      variables_for_factors=[[wide[a], wide[b]] for a, b in pairs], factor_configs=configs,
+      log_potentials=rng.normal(size=(len(pairs), configs.shape[0]))))
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  batch = 530
+  arrays = bp.init(evidence_updates={rows: rng.gumbel(size=(batch, 6, 2)), cols: rng.gumbel(size=(batch, 9, 2)),
+                                     wide: rng.gumbel(size=(batch, 4, 40))})
+  plan = bp.context.plan
+  assert plan.has_fused_blocks
+  got, got_d = bp.run_with_diffs(arrays, num_iters=7, damping=0.5, temperature=temperature)
+  plan.disable_paths(plan.PATH_HALF_BATCH)
+  ref, ref_d = bp.run_with_diffs(arrays, num_iters=7, damping=0.5, temperature=temperature)
+  plan.disable_paths(0)
+  np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
+  np.testing.assert_array_equal(got_d, ref_d)
+  graph = bp_oracle.graph_from_context(bp.context)
+  for b in (0, 255, 256, 529):
+    want, _ = bp_oracle.run_bp(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence[b], 7, 0.5, temperature)
+    np.testing.assert_allclose(np.asarray(got.ftov_msgs)[b], want, atol=1e-5)
+
+
+def test_batched_beliefs_and_map_states_with_a_vardict():
+  """The batch axis through get_beliefs / get_map_states on a graph that holds a VarDict
+  (VarDict.unflatten keeps the leading batch axis, as NDVarArray.unflatten does)."""
+  rng = np.random.RandomState(1)
+  names = ("a", "b", "c")
+  vd = vgroup.VarDict(variable_names=names, num_states=3)
+  arr = vgroup.NDVarArray(num_states=3, shape=(2,))
+  fg = fgraph.FactorGraph(variable_groups=[vd, arr])
+  fg.add_factors(fgroup.PairwiseFactorGroup(
+      variables_for_factors=[[vd["a"], vd["b"]], [vd["b"], vd["c"]], [vd["c"], arr[0]], [arr[0], arr[1]]],
+      log_potential_matrix=rng.normal(size=(4, 3, 3))))
+  bp = infer.BP(fg.bp_state, temperature=0.0)
+  ev_arr = rng.gumbel(size=(5, 2, 3))
+  arrays = bp.init(evidence_updates={arr: ev_arr})
+  out = bp.run(arrays, num_iters=10, damping=0.5)
+  beliefs = bp.get_beliefs(out)
+  states = bp.get_map_states(out)
+  assert beliefs[arr].shape == (5, 2, 3) and states[arr].shape == (5, 2)
+  for name in names:
+    assert beliefs[vd][name].shape == (5, 3) and states[vd][name].shape == (5,)
+  for b in range(5):
+    one = bp.init(evidence_updates={arr: ev_arr[b]})
+    one_out = bp.run(one, num_iters=10, damping=0.5)
+    one_beliefs, one_states = bp.get_beliefs(one_out), bp.get_map_states(one_out)
+    for name in names:
+      np.testing.assert_array_equal(beliefs[vd][name][b], one_beliefs[vd][name])
+      assert states[vd][name][b] == one_states[vd][name]
