@@ -278,6 +278,7 @@ int64_t pgx_plan_compressed_edges(const pgx_plan* plan);
 #define PGX_PATH_HALF_BATCH 1024u /* single-pass mode: the two halves of a batch of >= 16 sample tiles as two pipelined chains on two streams */
 #define PGX_PATH_STAGED_WIRING 2048u /* uniform OR / AND groups: wiring of a CTA's factor range staged in shared memory */
 #define PGX_PATH_TAIL_SPLIT 4096u /* OR / AND graphs: <= 8 samples beyond the last full tile of 32 run on their own stream */
+#define PGX_PATH_LATTICE_BIN 8192u /* large single-sample lattices on binary-difference storage (k_lattice_bin) */
 #define PGX_PATH_LOGICAL_BIN 256u /* ... with the messages in binary-difference storage (one float per edge) */
 int pgx_plan_disable_paths(pgx_plan* plan, uint32_t mask);
 /* 1 if the lattice path is available for this plan. */
@@ -301,6 +302,39 @@ const char* pgx_last_error(void);
 
 /* Library / build information: "pgx <version> sm_100a ..." */
 const char* pgx_build_info(void);
+
+/* ---- Row strips of ONE 2-D lattice across the GPUs of a box ----------------------------------
+ *
+ * BASELINE.json configs[4] / SURVEY.md 8(e) row 2 (the reference has no multi-GPU path; the graph
+ * is the torus examples/ising_model.ipynb cell 12 builds, scaled): one process per GPU, rank g owns
+ * `rows` consecutive rows of the n_rows x n_cols torus and their factors (variable (i, j) owns the
+ * vertical factor to (i + 1, j) and the horizontal factor to (i, j + 1)); each iteration exchanges
+ * the boundary messages with NCCL send/recv (ring) on a side stream while the interior rows are
+ * updated; all iterations of a run are ONE CUDA graph launch.  world == 1: the whole torus, no NCCL.
+ *
+ * Arrays (device, fp32, the reference's flat layout restricted to the strip):
+ *   log_potentials [8 * rows * n_cols]  4 per factor, factor 2 * (l * n_cols + j) + t (t = 0 vertical)
+ *   evidence_own   [2 * rows * n_cols]
+ *   msgs_in / out  [8 * rows * n_cols]  (msgs_in may be NULL: zero messages; normalised on entry)
+ * The NCCL communicator is created from a 128-byte unique id the caller obtains on rank 0
+ * (pgx_nccl_unique_id) and broadcasts with whatever it has (torch.distributed in dist.py). */
+typedef struct pgx_strip pgx_strip;
+#define PGX_NCCL_ID_BYTES 128
+#define PGX_STRIP_NO_GRAPH 1u   /* enqueue the launches directly instead of replaying a CUDA graph */
+#define PGX_STRIP_NO_OVERLAP 2u /* wait for the halo before any row is updated (A/B of the overlap) */
+int pgx_nccl_unique_id(void* id_out);
+int pgx_strip_create(int64_t n_cols, int64_t rows, int rank, int world, const void* nccl_id,
+                     pgx_strip** out_strip);
+void pgx_strip_destroy(pgx_strip* strip);
+int pgx_strip_run(pgx_strip* strip, void* stream, const float* log_potentials,
+                  const float* evidence_own, const float* msgs_in, float* msgs_out,
+                  int32_t num_iters, float damping, float temperature, uint32_t flags);
+/* beliefs_out [2 * rows * n_cols] = evidence + incoming messages of the owned variables (one more
+ * boundary exchange). */
+int pgx_strip_beliefs(pgx_strip* strip, void* stream, const float* evidence_own, const float* msgs,
+                      float* beliefs_out);
+int64_t pgx_strip_launch_count(const pgx_strip* strip);       /* kernels + exchanges enqueued so far */
+int64_t pgx_strip_graph_launch_count(const pgx_strip* strip); /* cudaGraphLaunch calls so far */
 
 #ifdef __cplusplus
 }

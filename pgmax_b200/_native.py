@@ -49,6 +49,13 @@ EXPORTED_SYMBOLS = (
     "pgx_plan_profile_read",
     "pgx_last_error",
     "pgx_build_info",
+    "pgx_nccl_unique_id",
+    "pgx_strip_create",
+    "pgx_strip_destroy",
+    "pgx_strip_run",
+    "pgx_strip_beliefs",
+    "pgx_strip_launch_count",
+    "pgx_strip_graph_launch_count",
 )
 
 
@@ -190,6 +197,20 @@ def load() -> ctypes.CDLL:
   lib.pgx_plan_profile_read.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(ctypes.c_char_p)]
   lib.pgx_plan_profile_read.restype = ctypes.c_int
+  lib.pgx_nccl_unique_id.argtypes = [vp]
+  lib.pgx_nccl_unique_id.restype = ctypes.c_int
+  lib.pgx_strip_create.argtypes = [i64, i64, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(vp)]
+  lib.pgx_strip_create.restype = ctypes.c_int
+  lib.pgx_strip_destroy.argtypes = [vp]
+  lib.pgx_strip_destroy.restype = None
+  lib.pgx_strip_run.argtypes = [vp, vp, vp, vp, vp, vp, i32, f32, f32, ctypes.c_uint32]
+  lib.pgx_strip_run.restype = ctypes.c_int
+  lib.pgx_strip_beliefs.argtypes = [vp, vp, vp, vp, vp]
+  lib.pgx_strip_beliefs.restype = ctypes.c_int
+  lib.pgx_strip_launch_count.argtypes = [vp]
+  lib.pgx_strip_launch_count.restype = ctypes.c_int64
+  lib.pgx_strip_graph_launch_count.argtypes = [vp]
+  lib.pgx_strip_graph_launch_count.restype = ctypes.c_int64
   lib.pgx_last_error.argtypes = []
   lib.pgx_last_error.restype = ctypes.c_char_p
   lib.pgx_build_info.argtypes = []
@@ -390,7 +411,7 @@ class Plan:
   PATH_LATTICE, PATH_RESIDENT, PATH_PULL, PATH_MERGED_MAX, PATH_LOGICAL_PULL = 1, 2, 4, 8, 16
   PATH_LATTICE_STREAM, PATH_AUX_STREAM, PATH_WIDE_SPLIT, PATH_LOGICAL_BIN = 32, 64, 128, 256
   PATH_PERM_POTENTIALS, PATH_HALF_BATCH, PATH_STAGED_WIRING = 512, 1024, 2048
-  PATH_TAIL_SPLIT = 4096
+  PATH_TAIL_SPLIT, PATH_LATTICE_BIN = 4096, 8192
 
   def disable_paths(self, mask: int) -> None:
     """Pin the launch path (PGX_PATH_* bits of include/pgx.h); all paths are bit-identical."""
@@ -482,3 +503,52 @@ class Plan:
                                    int(ev_batched), msgs_in, int(msgs_batched), num_iters,
                                    damping, temperature, map_out, marginals, ties, msgs_out,
                                    deltas))
+
+
+NCCL_ID_BYTES = 128
+STRIP_NO_GRAPH, STRIP_NO_OVERLAP = 1, 2
+
+
+def nccl_unique_id() -> bytes:
+  """A fresh NCCL unique id (call on ONE rank and broadcast the bytes)."""
+  buf = ctypes.create_string_buffer(NCCL_ID_BYTES)
+  check(load().pgx_nccl_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+  return buf.raw
+
+
+class Strip:
+  """Owns a pgx_strip: one rank's row strip of a 2-D lattice (include/pgx.h, pgx_strip_*)."""
+
+  def __init__(self, n_cols: int, rows: int, rank: int = 0, world: int = 1, nccl_id: Optional[bytes] = None):
+    lib = load()
+    if world > 1 and (nccl_id is None or len(nccl_id) != NCCL_ID_BYTES):
+      raise ValueError(f"a strip of a world of {world} needs the {NCCL_ID_BYTES}-byte NCCL unique id")
+    handle = ctypes.c_void_p()
+    id_buf = ctypes.create_string_buffer(nccl_id, NCCL_ID_BYTES) if nccl_id is not None else None
+    check(lib.pgx_strip_create(int(n_cols), int(rows), int(rank), int(world),
+                               ctypes.cast(id_buf, ctypes.c_void_p) if id_buf is not None else None,
+                               ctypes.byref(handle)))
+    self._lib, self.handle = lib, handle
+    self.n_cols, self.rows, self.rank, self.world = int(n_cols), int(rows), int(rank), int(world)
+
+  def __del__(self):
+    handle = getattr(self, "handle", None)
+    if handle:
+      self._lib.pgx_strip_destroy(handle)
+      self.handle = None
+
+  def run(self, stream: int, lp: int, ev_own: int, msgs_in: Optional[int], msgs_out: int, num_iters: int,
+          damping: float, temperature: float, flags: int = 0) -> None:
+    check(self._lib.pgx_strip_run(self.handle, stream, lp, ev_own, msgs_in, msgs_out, int(num_iters),
+                                  float(damping), float(temperature), int(flags)))
+
+  def beliefs(self, stream: int, ev_own: int, msgs: int, out: int) -> None:
+    check(self._lib.pgx_strip_beliefs(self.handle, stream, ev_own, msgs, out))
+
+  @property
+  def launch_count(self) -> int:
+    return int(self._lib.pgx_strip_launch_count(self.handle))
+
+  @property
+  def graph_launch_count(self) -> int:
+    return int(self._lib.pgx_strip_graph_launch_count(self.handle))

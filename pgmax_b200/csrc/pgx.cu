@@ -922,6 +922,98 @@ struct DeviceGuard {
   }
 };
 
+// A lattice launch on binary-difference storage: variant (max / sum-product, with / without
+// deltas), persistent grid of one CTA per SM.
+using LbCfgDefault = pgx::LbCfg<4, 256, 3>;
+using LbFn = void (*)(pgx::LatticeBinArgs, const float*, const float*, const float4*, float4*, pgx::RunArgs);
+
+int launch_lattice_bin(pgx_plan* plan_or_null, uint32_t* attr_done, int num_sms, cudaStream_t st,
+                       const pgx::LatticeBinArgs& g, const float* ev, const float* lp, const float* c_old, float* c_new,
+                       const pgx::RunArgs& a, bool sum_product, bool want_delta) {
+  static const LbFn fns[4] = {pgx::k_lattice_bin<false, false, LbCfgDefault>, pgx::k_lattice_bin<false, true, LbCfgDefault>,
+                              pgx::k_lattice_bin<true, false, LbCfgDefault>, pgx::k_lattice_bin<true, true, LbCfgDefault>};
+  if (!((*attr_done >> kAttrLatticeBin) & 1u)) {
+    *attr_done |= 1u << kAttrLatticeBin;
+    for (int v = 0; v < 4; ++v)
+      PGX_CUDA(cudaFuncSetAttribute(fns[v], cudaFuncAttributeMaxDynamicSharedMemorySize, int(LbCfgDefault::smem_bytes())));
+  }
+  const int tiles_x = (g.N + LbCfgDefault::TC - 1) / LbCfgDefault::TC;
+  int64_t tiles = 0;
+  for (int s = 0; s < 2; ++s)
+    tiles += int64_t(tiles_x) * std::max(0, (g.seg_end[s] - g.seg_begin[s] + LbCfgDefault::TR - 1) / LbCfgDefault::TR);
+  if (tiles == 0) return PGX_OK;
+  const unsigned grid = unsigned(std::min<int64_t>(tiles, num_sms));
+  fns[(sum_product ? 2 : 0) + (want_delta ? 1 : 0)]<<<grid, pgx::kLbThreads, LbCfgDefault::smem_bytes(), st>>>(
+      g, ev, lp, reinterpret_cast<const float4*>(c_old), reinterpret_cast<float4*>(c_new), a);
+  if (plan_or_null) return check_launch(plan_or_null, "k_lattice_bin");
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(PGX_ERR_CUDA, "launch of k_lattice_bin failed: %s", cudaGetErrorString(err));
+  return PGX_OK;
+}
+
+pgx::RunArgs make_run_args(float damping, float temperature, float* deltas, int32_t num_iters, int64_t Es, int64_t Vs) {
+  pgx::RunArgs a{};
+  a.d = damping;
+  a.one_minus_d = 1.0f - damping;
+  a.T = temperature;
+  if (temperature > 0.f) {
+    a.c_exp = float(1.4426950408889634 / double(temperature));
+    a.c_log = float(0.6931471805599453 * double(temperature));
+  }
+  a.deltas = deltas;
+  a.delta_stride = num_iters;
+  a.Es = Es;
+  a.Vs = Vs;
+  return a;
+}
+
+// pgx_bp_run for one sample of a large 2-D lattice: normalise + compress the input messages
+// once, num_iters launches of k_lattice_bin ping-ponging between the two compressed buffers,
+// expand once into the caller's buffer.
+int run_lattice_bin(pgx_plan* plan, cudaStream_t st, const float* log_potentials, const float* evidence,
+                    const float* ftov_in, float* ftov_out, float* deltas, int32_t num_iters, float damping,
+                    float temperature) {
+  int rc;
+  Workspace& ws = plan->ws;
+  const pgx::LatticeDev& lat = plan->lattice;
+  const int64_t cells = int64_t(lat.R) * lat.N;
+  const unsigned ew_grid = unsigned(plan->num_sms * 8);
+  if (ftov_in == nullptr) {
+    PGX_CUDA(cudaMemsetAsync(ws.cA, 0, size_t(cells) * sizeof(float4), st));  // NC(0) = 0
+  } else {
+    pgx::k_lattice_compress<<<ew_grid, pgx::kThreads, 0, st>>>(reinterpret_cast<const float4*>(ftov_in + lat.first_msg),
+                                                               reinterpret_cast<float4*>(ws.cA), cells);
+    if ((rc = check_launch(plan, "k_lattice_compress"))) return rc;
+  }
+  if (deltas) PGX_CUDA(cudaMemsetAsync(deltas, 0, size_t(num_iters) * sizeof(float), st));
+  pgx::RunArgs a = make_run_args(damping, temperature, deltas, num_iters, plan->num_edge_states, plan->num_var_states);
+  pgx::LatticeBinArgs g{};
+  g.R = lat.R;
+  g.N = lat.N;
+  g.torus = lat.torus;
+  g.seg_begin[0] = 0;
+  g.seg_end[0] = lat.R;
+  g.up_add = nullptr;
+  g.ghost_ev = nullptr;
+  plan->dominant_name = "k_lattice_bin";
+  const float* cur = ws.cA;
+  float* nxt = ws.cB;
+  for (int it = 0; it < num_iters; ++it) {
+    a.delta_off = it;
+    if ((rc = prof_mark(plan, st, 0))) return rc;
+    if ((rc = launch_lattice_bin(plan, &plan->attr_done, plan->num_sms, st, g, evidence, log_potentials + lat.first_pot, cur,
+                                 nxt, a, temperature > 0.f, deltas != nullptr)))
+      return rc;
+    if ((rc = prof_mark(plan, st, 0))) return rc;
+    const float* t = cur;
+    cur = nxt;
+    nxt = const_cast<float*>(t);
+  }
+  pgx::k_lattice_expand<<<ew_grid, pgx::kThreads, 0, st>>>(reinterpret_cast<const float4*>(cur),
+                                                           reinterpret_cast<float4*>(ftov_out + lat.first_msg), cells);
+  return check_launch(plan, "k_lattice_expand");
+}
+
 }  // namespace
 
 extern "C" {
@@ -1558,8 +1650,21 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     if (deltas) PGX_CUDA(cudaMemsetAsync(deltas, 0, size_t(batch) * num_iters * sizeof(float), static_cast<cudaStream_t>(stream)));
     return PGX_OK;
   }
-  if ((rc = ensure_workspace(plan, batch, evT, lpT, fused, lbin))) return rc;
+  // Large single-sample lattices run on binary-difference storage (k_lattice_bin): decided here
+  // because the compressed buffers belong to the workspace.
+  bool lat_bin = false;
+  if (plan->lattice_ok && single &&
+      !(plan->disabled_paths & (PGX_PATH_LATTICE | PGX_PATH_LATTICE_STREAM | PGX_PATH_LATTICE_BIN))) {
+    const pgx::LatticeDev& g = plan->lattice;
+    const int64_t num_tiles = int64_t((g.N + pgx::kLsTC - 1) / pgx::kLsTC) * ((g.R + pgx::kLsTR - 1) / pgx::kLsTR);
+    const auto misaligned = [](const void* p, uintptr_t mask) { return (reinterpret_cast<uintptr_t>(p) & mask) != 0; };
+    lat_bin = num_tiles >= 4 * int64_t(plan->num_sms) && !misaligned(ftov_in, 15) && !misaligned(ftov_out, 15) &&
+              !misaligned(log_potentials, 15) && !misaligned(evidence, 7);
+  }
+  if ((rc = ensure_workspace(plan, batch, evT, lpT, fused, lbin || lat_bin))) return rc;
   Workspace& ws = plan->ws;
+  if (lat_bin) return run_lattice_bin(plan, st, log_potentials, evidence, ftov_in, ftov_out, deltas, num_iters, damping,
+                                      temperature);
 
   // ---- inputs -> tile-blocked workspace ----------------------------------------------------
   pgx::View ev{evidence, Vs, 0}, lp{log_potentials, C, 0};
@@ -2121,3 +2226,4 @@ int pgx_infer_host(pgx_plan* plan, void* stream, int64_t batch, const float* lp_
 }  // extern "C"
 
 #include "pgx_sdlp.cuh"
+#include "pgx_strip.cuh"

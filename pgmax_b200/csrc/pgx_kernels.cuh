@@ -28,6 +28,7 @@
 #include "kernels/pairwise.cuh"
 #include "kernels/lattice.cuh"
 #include "kernels/dense_grid.cuh"
+#include "kernels/lattice_bin.cuh"
 #include "kernels/enum.cuh"
 #include "kernels/logical.cuh"
 #include "kernels/decode_energy.cuh"

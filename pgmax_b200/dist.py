@@ -186,8 +186,79 @@ class PgxStepEngine:
     return out
 
 
+class NativeStripRunner:
+  """Row strip `rank` of `world` of the n x n Ising torus on this rank's GPU, through
+  pgx_strip_* (include/pgx.h): the local iteration, the halo pack, the NCCL send/recv ring on
+  a side stream and the overlap with the interior rows all live in the library, and a run of
+  `num_iters` iterations is ONE CUDA graph launch.  torch.distributed is used once, to
+  broadcast the NCCL unique id of the library's own communicator.
+
+  The strip's arrays never exist on the host: potentials are generated on the device.
+  """
+
+  def __init__(self, n: int, rank: int = 0, world: int = 1, device="cuda:0", group=None, coupling: float = 0.8):
+    import torch  # pylint: disable=g-import-not-at-top
+
+    self.torch = torch
+    self.n, self.rank, self.world = int(n), int(rank), int(world)
+    self.device = torch.device(device)
+    self.row0, row1 = shard_bounds(n, world, rank)
+    self.rows = row1 - self.row0
+    if self.rows < 2:
+      raise ValueError("every strip needs at least 2 rows")
+    nccl_id = None
+    if world > 1:
+      import torch.distributed as dist  # pylint: disable=g-import-not-at-top
+
+      buf = torch.zeros(_native.NCCL_ID_BYTES, dtype=torch.uint8, device=self.device)
+      if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(_native.nccl_unique_id()), dtype=torch.uint8))
+      dist.broadcast(buf, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+      nccl_id = bytes(buf.cpu().numpy().tobytes())
+    with torch.cuda.device(self.device):
+      self.strip = _native.Strip(n, self.rows, rank, world, nccl_id)
+      pattern = torch.tensor([1.0, -1.0, -1.0, 1.0], dtype=torch.float32, device=self.device) * float(coupling)
+      self.lp = pattern.repeat(2 * self.rows * self.n)
+      self._out = torch.empty(self.num_msgs, dtype=torch.float32, device=self.device)
+
+  @property
+  def num_msgs(self) -> int:
+    return 8 * self.rows * self.n
+
+  @property
+  def global_msg_range(self) -> Tuple[int, int]:
+    return 8 * self.row0 * self.n, 8 * (self.row0 + self.rows) * self.n
+
+  def _stream(self) -> int:
+    return self.torch.cuda.current_stream(self.device).cuda_stream
+
+  def run(self, evidence_own, num_iters: int, damping: float = 0.5, temperature: float = 0.0, msgs=None,
+          out=None, flags: int = 0):
+    """evidence_own: [rows * n * 2] device tensor (read in place).  Returns (messages
+    [8 * rows * n], evidence_own).  Without `out` the messages land in a buffer the runner
+    owns and reuses (the next run overwrites it); the same (evidence, msgs, out) buffers and
+    scalars replay the same CUDA graph."""
+    torch = self.torch
+    ev = torch.as_tensor(evidence_own, dtype=torch.float32, device=self.device).reshape(-1)
+    if not ev.is_contiguous():
+      ev = ev.contiguous()
+    dst = self._out if out is None else out
+    self.strip.run(self._stream(), self.lp.data_ptr(), ev.data_ptr(), None if msgs is None else msgs.data_ptr(),
+                   dst.data_ptr(), max(int(num_iters), 1), float(damping), float(temperature), flags)
+    return dst, ev
+
+  def beliefs(self, ev_own, msgs):
+    """Beliefs of the owned variables [rows * n * 2] (one more boundary exchange)."""
+    out = self.torch.empty(2 * self.rows * self.n, dtype=self.torch.float32, device=self.device)
+    self.strip.beliefs(self._stream(), ev_own.data_ptr(), msgs.data_ptr(), out.data_ptr())
+    return out
+
+
 class StripRunner:
-  """Loopy BP on one row strip with a per-iteration halo exchange.
+  """Loopy BP on one row strip with a per-iteration halo exchange: the HOST-SIDE statement of
+  the protocol (index arrays of ising_strip + torch.distributed p2p), kept as the executable
+  specification the gloo tests run on CPU with an oracle-backed engine; on GPUs the product
+  path is NativeStripRunner.
 
   `engine` does the local iteration (PgxStepEngine on a GPU; the tests inject an
   oracle-backed engine on CPU tensors, which is how the N > 1 host logic is covered

@@ -5,9 +5,12 @@ benchmark/rbm.py:31,138-140), Gumbel evidence, damping 0.5; the run is
 pgmax/infer/bp.py:85-155.  Per ITERATION (1..5), for T = 0 and T = 1:
 
   (a) exact_order (two-pass, serial summation order), T = 0: bit-exact with the oracle;
-  (b) exact_order, T = 1: within the north-star's 1e-5 for the first K_EXACT_T1 iterations
-      (the only difference is the ex2/lg2 two-term logsumexp, 1.7e-7 per message, which this
-      chaotic model then amplifies);
+  (b) exact_order, T = 1: within the north-star's 1e-5 for the first K_EXACT_T1 = 1 iteration
+      (measured 9.5e-7; the only difference is the ex2/lg2 two-term logsumexp, 1.7e-7 per
+      message).  From iteration 2 on NO fp32 implementation can meet 1e-5 against another one
+      on this model: the oracle itself is 1.6e-5 away from the fp64 recursion after 2
+      iterations, 1.5e-4 after 3, 5.8e-4 after 5 (measured, profiles/r02_parity_config1.json) -
+      so later iterations are bounded relative to that noise, like (c);
   (c) the fused single-pass kernel (k_enum_pw2_bip: tree-order partial sums on
       binary-difference storage - the kernel bench.py times): its distance to an fp64 run of the
       same recursion is bounded by the fp32 serial oracle's own distance to fp64,
@@ -36,7 +39,7 @@ pytestmark = pytest.mark.gpu
 NH, NV, ITERS = 500, 784, 5
 BATCH = 64
 PICK = (0, 21, 42, 63)          # samples compared with the oracle (two sample tiles)
-K_EXACT_T1 = 2                  # iterations the serial-order path stays within 1e-5 of the oracle at T = 1
+K_EXACT_T1 = 1                  # iterations the serial-order path stays within 1e-5 of the oracle at T = 1
 RECORD = {}
 
 
@@ -88,7 +91,7 @@ def _save_record():
 def test_config1_rbm_784x500_vs_oracle(rbm, temperature):
   bp, plan = rbm["bp"], rbm["bp"].context.plan
   arrays = bp.init(evidence_updates={rbm["hidden"]: rbm["ev_h"][:BATCH], rbm["visible"]: rbm["ev_v"][:BATCH]})
-  assert plan.has_fused_blocks and plan.compressed_edges == NH * NV
+  assert plan.has_fused_blocks and plan.compressed_edges == 2 * NH * NV  # two edges per pairwise factor
   plan.set_exact_order(True)
   exact = _device_trajectory(bp, arrays, temperature, ITERS, PICK)
   plan.set_exact_order(False)
@@ -115,11 +118,12 @@ def test_config1_rbm_784x500_vs_oracle(rbm, temperature):
   if temperature > 0.0:
     # (b) serial order at T = 1: north-star tolerance over the first K iterations
     assert np.all(worst["exact_vs_oracle"][:K_EXACT_T1] <= 1e-5), worst["exact_vs_oracle"]
+    assert np.all(worst["exact_vs_fp64"] <= 2.0 * worst["oracle_vs_fp64"] + 2e-6), worst["exact_vs_fp64"]
   # (c) fused path: no further from the fp64 recursion than 2x the fp32 oracle itself
   bound = 2.0 * worst["oracle_vs_fp64"] + 2e-6
   assert np.all(worst["fused_vs_fp64"] <= bound), (worst["fused_vs_fp64"], bound)
   # and the first iteration is within the north-star tolerance of the oracle outright
-  assert worst["fused_vs_oracle"][0] <= 3e-5, worst["fused_vs_oracle"]
+  assert worst["fused_vs_oracle"][0] <= 1e-5, worst["fused_vs_oracle"]
 
 
 def test_config1_rbm_batch_1024_half_batch_pipeline(rbm):
