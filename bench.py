@@ -106,13 +106,93 @@ def build_workload(name: str, batch_override=None, iters_override=None):
               temperature=temperature, batch=batch or 1)
 
 
-def run_ising_big(args):
-  """BASELINE.json configs[4]: one n x n Ising torus (default 8192), sum-product T=1,
-  200 iterations, row strips across the ranks with a per-iteration halo exchange
-  (pgmax_b200/dist.py).  Strong scaling: the graph is fixed, ranks split it."""
+def strip_record(args, dev, rank, world, n, iters, steps, warmup, sampler_index=None, flags=0):
+  """One n x n Ising torus (BASELINE.json configs[4]: n = 8192), sum-product T = 1, damping 0.5,
+  split into row strips across `world` ranks through pgx_strip_* (NCCL halo ring per iteration on
+  a side stream, interior rows overlapped, all iterations of a run ONE CUDA graph launch).
+  Strong scaling: the graph is fixed.  Returns the timing record of this rank (max over ranks is
+  taken by the caller)."""
   import torch
   import torch.distributed as dist
   from pgmax_b200 import dist as pdist
+
+  T = 1.0
+  runner = pdist.NativeStripRunner(n, rank, world, dev)
+  gen = torch.Generator(device=dev).manual_seed(rank)
+  u = torch.rand(runner.rows * n * 2, generator=gen, device=dev).clamp_(1e-7, 1 - 1e-7)
+  ev_own = -torch.log(-torch.log(u))  # Gumbel(0, 1), generated on the device
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(warmup):
+    msgs, _ = runner.run(ev_own, iters, 0.5, T, flags=flags)
+  barrier()
+  launches0 = runner.strip.launch_count
+  sampler = ClockSampler(sampler_index) if sampler_index is not None else None
+  if sampler:
+    sampler.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  for _ in range(steps):
+    msgs, _ = runner.run(ev_own, iters, 0.5, T, flags=flags)
+  e1.record()
+  barrier()
+  ms = e0.elapsed_time(e1)
+  clocks = sampler.stop() if sampler else None
+  launches = runner.strip.launch_count - launches0
+  # end to end: every step copies the strip's evidence from pinned host memory and reads the
+  # step's metric (max |message|) back; device time between barriers
+  ev_host = ev_own.cpu().pin_memory()
+  ev_dev = torch.empty_like(ev_own)
+  for _ in range(min(warmup, 1)):
+    runner.run(ev_dev.copy_(ev_host, non_blocking=True), iters, 0.5, T, flags=flags)
+  f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  f0.record()
+  for _ in range(steps):
+    ev_dev.copy_(ev_host, non_blocking=True)
+    out, _ = runner.run(ev_dev, iters, 0.5, T, flags=flags)
+    metric = float(out.abs().max().item())  # 4-byte device -> host read, synchronises the step
+  f1.record()
+  barrier()
+  e2e_ms = f0.elapsed_time(f1)
+  checksum = float(msgs.abs().max().item())
+  del runner
+  return dict(ms=ms, e2e_ms=e2e_ms, launches=launches, clocks=clocks, checksum=checksum,
+              h2d=ev_host.numel() * 4, d2h=4, metric=metric)
+
+
+def strip_line_fields(n, iters, steps, world, ms, e2e_ms, rec):
+  """Metric, roofline and e2e fields of a strip run (ms already max over ranks)."""
+  es = 8 * n * n
+  bytes_iter = 17 * es   # 4 * (2 + 0.25 + 1 + 1) * E_s, SURVEY.md 8(d)
+  moved_iter = 9 * es    # binary-difference storage: 16 + 16 B messages, 32 B potentials, 8 B evidence per cell
+  iter_s = ms * 1e-3 / steps / iters
+  peak, peak_src = hbm_peak()
+  return {
+      "value": es * iters * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "ms_per_step": ms / steps,
+      "iter_ms": iter_s * 1e3, "edge_states": es, "iters": iters,
+      "frac": bytes_iter / iter_s / 1e9 / world / peak,
+      "layout_frac": moved_iter / iter_s / 1e9 / world / peak,
+      "algorithmic_bytes_per_iter_per_gpu": bytes_iter // world, "layout_bytes_per_iter_per_gpu": moved_iter // world,
+      "peak": peak, "peak_source": peak_src,
+      "e2e": {"value": es * iters * steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": rec["h2d"] * world,
+              "d2h_bytes_per_step": rec["d2h"] * world, "ms_per_step": e2e_ms / steps},
+      "gpu_launches": rec["launches"], "graph_launches_per_step": 1,
+      "checksum_max_abs_msg": rec["checksum"],
+      "parallelism": (f"row strips x{world}, NCCL send/recv halo ring per iteration on a side stream, interior rows "
+                      "overlapped, one CUDA graph per run") if world > 1 else "one GPU, one CUDA graph per run",
+  }
+
+
+def run_ising_big(args):
+  """`--workload ising_big`: the strip workload as the main line (strong scaling)."""
+  import torch
+  import torch.distributed as dist
 
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -121,85 +201,33 @@ def run_ising_big(args):
   dev = torch.device("cuda", local_rank)
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-  n = args.size or 8192
-  iters = args.iters or 200
-  T = 1.0
-  strip = pdist.ising_strip(n, rank, world)
-  runner = pdist.StripRunner(strip, pdist.PgxStepEngine(strip.flat, dev), dev)
-  gen = torch.Generator(device=dev).manual_seed(rank)
-  u = torch.rand(strip.rows * n * 2, generator=gen, device=dev).clamp_(1e-7, 1 - 1e-7)
-  ev_own = -torch.log(-torch.log(u))  # Gumbel(0, 1), generated on the device
-  def barrier():
-    if world > 1:
-      dist.barrier()
-    torch.cuda.synchronize()
-  msgs = None
-  for _ in range(args.warmup):
-    msgs, _ = runner.run(ev_own, min(iters, 5), 0.5, T)
-  launches0 = runner.engine.plan.launch_count
-  sampler = ClockSampler(local_rank)
-  sampler.start()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  barrier()
-  e0.record()
-  for _ in range(args.steps):
-    msgs, _ = runner.run(ev_own, iters, 0.5, T)
-  e1.record()
-  barrier()
-  ms = e0.elapsed_time(e1)
-  clocks = sampler.stop()
-  launches = runner.engine.plan.launch_count - launches0
-  # End to end: every step copies the strip's evidence from pinned host memory and reads the
-  # step's metric (max |message|) back; device time between barriers, max over ranks.
-  e2e_ms, e2e_note = None, None
-  try:
-    ev_host = ev_own.cpu().pin_memory()
-    ev_dev = torch.empty_like(ev_own)
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    f0.record()
-    for _ in range(args.steps):
-      ev_dev.copy_(ev_host, non_blocking=True)
-      out, _ = runner.run(ev_dev, iters, 0.5, T)
-      metric = float(out.abs().max().item())  # 4-byte device -> host read, synchronises the step
-    f1.record()
-    barrier()
-    e2e_ms = f0.elapsed_time(f1)
-    h2d_bytes, d2h_bytes = ev_host.numel() * 4, 4
-  except Exception as exc:  # pylint: disable=broad-except
-    e2e_note = f"end-to-end leg failed: {exc}"
+  n, iters = args.size or 8192, args.iters or 200
+  rec = strip_record(args, dev, rank, world, n, iters, args.steps, args.warmup, sampler_index=local_rank,
+                     flags=args.strip_flags)
+  ms, e2e_ms = rec["ms"], rec["e2e_ms"]
   if world > 1:
-    t = torch.tensor([ms, e2e_ms if e2e_ms is not None else -1.0], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t[0].item())
-    e2e_ms = float(t[1].item()) if e2e_ms is not None and float(t[1].item()) > 0 else None
+    ms, e2e_ms = t.tolist()
   if rank == 0:
-    es = 8 * n * n
-    bytes_iter = 17 * es  # 4 * (2 + 0.25 + 1 + 1) * E_s, SURVEY.md 8(d)
-    iter_s = ms * 1e-3 / args.steps / iters
-    peak, peak_src = hbm_peak()
+    f = strip_line_fields(n, iters, args.steps, world, ms, e2e_ms, rec)
     line = {
-        "metric": METRIC, "value": es * iters * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"Ising {n}x{n} torus, single graph, sum-product T=1", "iters": iters,
-                   "damping": 0.5, "temperature": T, "edge_states": es,
-                   "parallelism": f"row strips x{world}, halo exchange per iteration (NCCL send/recv)"},
-        "gpu_launches": launches, "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": bytes_iter / iter_s / 1e9 / world, "peak": peak, "unit": "GB/s",
-                     "frac": bytes_iter / iter_s / 1e9 / world / peak, "traffic": None,
-                     "kernel": "whole iteration (k_lattice_stream + the halo exchange when N > 1), per GPU",
-                     "algorithmic_bytes_per_launch": bytes_iter // world, "peak_source": peak_src,
-                     "iter_ms": iter_s * 1e3},
-        "checksum_max_abs_msg": float(msgs.abs().max().item()),
+        "metric": METRIC, "value": f["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": f["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"Ising {n}x{n} torus, single graph, sum-product T=1", "iters": iters, "damping": 0.5,
+                   "temperature": 1.0, "edge_states": f["edge_states"], "parallelism": f["parallelism"],
+                   "l2": "working set larger than L2" if 4 * f["edge_states"] > 126e6 else "L2-resident working set"},
+        "e2e": f["e2e"], "gpu_launches": f["gpu_launches"], "clocks": rec["clocks"],
+        "roofline": {"bound": "hbm", "achieved": f["algorithmic_bytes_per_iter_per_gpu"] / (f["iter_ms"] * 1e-3) / 1e9,
+                     "peak": f["peak"], "unit": "GB/s", "frac": f["frac"], "traffic": None,
+                     "kernel": "k_lattice_bin (whole iteration incl. the halo exchange when N > 1), per GPU",
+                     "algorithmic_bytes_per_launch": f["algorithmic_bytes_per_iter_per_gpu"], "peak_source": f["peak_source"],
+                     "iter_ms": f["iter_ms"], "layout_frac": f["layout_frac"],
+                     "layout_bytes_per_iter": f["layout_bytes_per_iter_per_gpu"],
+                     "storage": "binary-difference, 1 float per two-state edge between iterations"},
+        "checksum_max_abs_msg": f["checksum_max_abs_msg"],
     }
-    if e2e_ms is not None:
-      line["e2e"] = {"value": es * iters * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
-                     "h2d_bytes_per_step": h2d_bytes * world, "d2h_bytes_per_step": d2h_bytes * world,
-                     "ms_per_step": e2e_ms / args.steps}
-    else:
-      line["e2e"] = {"value": None, "unit": UNIT, "note": e2e_note}
     print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
@@ -354,6 +382,200 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------
+def traffic_entry(workload, kernel, batch, grid):
+  """DRAM bytes per launch of `kernel` from this round's ncu --set full captures
+  (profiles/r02_traffic.json, written by profiles/make_traffic.py from the .ncu-rep files): only
+  if the capture was taken on the same kernel, batch and launch grid; otherwise None."""
+  try:
+    table = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+  except (OSError, ValueError):
+    return None
+  entry = table.get(f"{workload}:{kernel}")
+  if not entry or entry.get("batch") != batch or (grid and entry.get("grid") not in (None, grid)):
+    return None
+  return entry
+
+
+def oracle_parity(wl, host, dev_run, iters=2, sample=0):
+  """Checker, outside every timed region: `iters` iterations of the workload on the device
+  (the timed batch, the benchmarked path) against the CPU oracle for ONE sample."""
+  from oracle import bp_oracle  # test infrastructure: used here as the checker only
+  bp = wl["bp"]
+  graph = bp_oracle.graph_from_context(bp.context)
+  got = dev_run(iters)
+  pick = (lambda a: np.asarray(a)[sample]) if host.batch_size else (lambda a: np.asarray(a))
+  row = lambda a: np.asarray(a)[sample] if np.asarray(a).ndim == 2 else np.asarray(a)
+  want, _ = bp_oracle.run_bp(graph, row(host.log_potentials), row(host.ftov_msgs), row(host.evidence), iters,
+                             wl["damping"], wl["temperature"])
+  got = pick(got)
+  floor = want <= -1e31
+  return {"parity_max_abs": float(np.max(np.abs(got[~floor] - want[~floor]))) if (~floor).any() else 0.0,
+          "parity_iters": iters, "parity_sample": sample,
+          "parity_floor_mismatch": int(np.sum((got <= -1e31) != floor))}
+
+
+def measure(args, name, dev, rank, world, local_rank, batch=None, iters=None, steps=None, warmup=None,
+            shard_seed=None, with_clocks=True, parity_iters=2):
+  """Times one plan-based workload on this rank: device-resident steps (CUDA events), the
+  dominant kernel's launches (events around each one, separate pass), the end-to-end leg through
+  pgx_infer_host with pinned host buffers, and the oracle spot-check.  Returns this rank's
+  record; the caller reduces times over ranks."""
+  import torch
+  import torch.distributed as dist
+  from pgmax_b200.infer.bp_state import BPArrays
+
+  steps, warmup = steps or args.steps, warmup if warmup is not None else args.warmup
+  wl = build_workload(name, batch_override=batch, iters_override=iters)
+  bp, iters, damping, T = wl["bp"], wl["iters"], wl["damping"], wl["temperature"]
+  host = wl["arrays"]
+  if shard_seed is not None and host.evidence.ndim == 2:  # every rank draws its own shard of samples
+    rng = np.random.default_rng(shard_seed)
+    host = BPArrays(log_potentials=host.log_potentials, ftov_msgs=host.ftov_msgs,
+                    evidence=rng.gumbel(size=host.evidence.shape).astype(np.float32))
+  plan = bp.context.plan
+  plan.set_exact_order(args.exact_order)
+  plan.disable_paths(args.disable_paths)
+  batch = host.batch_size or 1
+  put = lambda a: torch.from_numpy(np.array(a, dtype=np.float32, order="C")).to(dev)
+  dev_arrays = BPArrays(log_potentials=put(host.log_potentials), ftov_msgs=put(host.ftov_msgs),
+                        evidence=put(host.evidence))
+  es = plan.num_edge_states
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  for _ in range(warmup):
+    out = bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
+  barrier()
+  launches0 = plan.launch_count
+  sampler = ClockSampler(local_rank) if with_clocks else None
+  if sampler:
+    sampler.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  barrier()
+  e0.record()
+  for _ in range(steps):
+    out = bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
+  e1.record()
+  barrier()
+  ms = e0.elapsed_time(e1)
+  clocks = sampler.stop() if sampler else None
+  launches = plan.launch_count - launches0
+  # roofline pass: the same step once more with CUDA events around every launch of the dominant
+  # kernel (kept out of the timed region above)
+  plan.profile_enable(True)
+  bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
+  torch.cuda.synchronize()
+  n_prof, prof_ms, prof_name = plan.profile_read()
+  plan.profile_enable(False)
+  checksum = float(out.ftov_msgs.float().abs().max().item())
+
+  # end to end through the C ABI with host buffers
+  pin = lambda a: torch.from_numpy(np.array(a, dtype=np.float32, order="C")).pin_memory()
+  h_lp, h_ev = pin(host.log_potentials), pin(host.evidence)
+  h_map = torch.empty((batch, plan.num_vars), dtype=torch.int32).pin_memory()
+  h_ties = torch.empty((batch,), dtype=torch.int32).pin_memory()
+  stream = torch.cuda.current_stream(dev).cuda_stream
+
+  def e2e_step():
+    plan.infer_host(stream, batch, h_lp.data_ptr(), h_lp.ndim == 2, h_ev.data_ptr(), h_ev.ndim == 2,
+                    None, False, iters, damping, T, h_map.data_ptr(), None, h_ties.data_ptr(), None, None)
+
+  for _ in range(min(warmup, 2)):
+    e2e_step()
+  barrier()
+  e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  t0 = time.perf_counter()
+  e2.record()
+  for _ in range(steps):
+    e2e_step()
+  e3.record()
+  barrier()
+  e2e_ms = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+  parity = None
+  if rank == 0 and parity_iters:
+    try:
+      parity = oracle_parity(wl, host, lambda k: bp.run(dev_arrays, num_iters=k, damping=damping, temperature=T)
+                             .ftov_msgs.cpu().numpy(), iters=parity_iters)
+    except Exception as err:  # pylint: disable=broad-except
+      parity = {"parity_max_abs": None, "parity_note": "check failed: " + repr(err)[-200:]}
+  lp_batched = host.log_potentials.ndim == 2
+  fused_run = plan.has_fused_blocks and not args.exact_order and batch > 16 and not lp_batched
+  return dict(wl=wl, plan=plan, ms=ms, e2e_ms=e2e_ms, launches=launches, clocks=clocks, n_prof=n_prof, prof_ms=prof_ms,
+              prof_name=prof_name, checksum=checksum, batch=batch, iters=iters, es=es, steps=steps, warmup=warmup,
+              h2d=4 * (h_lp.numel() + h_ev.numel()), d2h=4 * (h_map.numel() + h_ties.numel()), parity=parity,
+              lp_batched=lp_batched, fused_run=fused_run, damping=damping, temperature=T)
+
+
+def roofline_of(name, rec, ms):
+  """The roofline object of a measured workload (ms: max over ranks of the timed region)."""
+  plan, batch, iters, es, steps = rec["plan"], rec["batch"], rec["iters"], rec["es"], rec["steps"]
+  peak, peak_src = hbm_peak()
+  bytes_iter = algorithmic_bytes_per_iter(plan, batch, rec["lp_batched"])
+  n_prof, prof_name = rec["n_prof"], rec["prof_name"]
+  kernel_ms = rec["prof_ms"] / max(n_prof, 1)
+  # the dominant launch updates dom_es of the es edge-states: its share of the iteration's
+  # algorithmic bytes (single-kernel iterations: all of them)
+  single_kernel = prof_name in ("k_enum_pw2_bip", "k_lattice", "k_lattice_stream", "k_lattice_bin", "k_enum_pw2_pull")
+  dom_es = es if single_kernel else min(plan.dominant_edge_states, es)
+  kernel_bytes = bytes_iter * dom_es // es
+  achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if n_prof else None
+  # bytes the kernels really have to move: binary-difference storage keeps ONE float per two-state
+  # edge between iterations, i.e. one float less to read and one less to write per such edge,
+  # sample and iteration than the reference layout
+  if rec["fused_run"]:
+    saved = 8 * plan.compressed_edges * batch
+  elif prof_name == "k_lattice_bin":
+    saved = 8 * (es // 2) + 4 * es  # + the incidence index this kernel does not read
+  else:
+    saved = 0
+  layout_bytes = bytes_iter - saved
+  iter_ms = ms / steps / iters
+  iter_gbs = bytes_iter / (iter_ms * 1e-3) / 1e9
+  entry = traffic_entry(name, prof_name, batch, plan.dominant_grid) if n_prof else None
+  traffic = entry["bytes"] if entry else None
+  return {
+      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+      # first-class: the DRAM bytes ncu measured for this kernel (same name, batch and grid) over the
+      # launch time measured in THIS run, against the same peak - a true fraction of bandwidth
+      "physical_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if (traffic and n_prof) else None,
+      "traffic_source": entry.get("source") if entry else None,
+      "kernel": prof_name, "kernel_ms": kernel_ms, "launches_timed": n_prof, "kernel_grid": plan.dominant_grid,
+      "algorithmic_bytes_per_launch": kernel_bytes, "peak_source": peak_src,
+      "edge_states_per_launch": dom_es * batch,
+      "iter_ms": iter_ms, "iter_algorithmic_bytes": bytes_iter, "iter_achieved": iter_gbs, "iter_frac": iter_gbs / peak,
+      "storage": ("binary-difference, 1 float per two-state edge between iterations" if saved
+                  else "reference layout, 1 float per edge-state"),
+      "note": ("frac follows SURVEY 8(d): ALGORITHMIC bytes (two floats read + written per two-state edge) / time / "
+               "peak; the kernels keep ONE float per such edge between iterations (bit-identical values), so frac "
+               "can exceed 1 - layout_frac is the same on the bytes of the layout actually used, physical_frac on "
+               "the DRAM bytes ncu measured") if saved else None,
+      "layout_bytes_per_iter": layout_bytes,
+      "layout_frac": (layout_bytes * (kernel_bytes / bytes_iter) / (kernel_ms * 1e-3) / 1e9 / peak) if n_prof else None,
+      "layout_iter_frac": layout_bytes / (iter_ms * 1e-3) / 1e9 / peak,
+  }
+
+
+def compact_record(name, rec, world=1):
+  """Short form of a measured workload for the `other_workloads` / `rbm_strong` sub-records."""
+  r = roofline_of(name, rec, rec["ms"])
+  msgs = rec["es"] * rec["batch"] * rec["iters"] * rec["steps"] * world
+  out = {
+      "workload": rec["wl"]["label"], "batch": rec["batch"], "iters": rec["iters"], "temperature": rec["temperature"],
+      "value": msgs / (rec["ms"] * 1e-3), "unit": UNIT, "ms_per_step": rec["ms"] / rec["steps"], "iter_ms": r["iter_ms"],
+      "e2e_value": msgs / (rec["e2e_ms"] * 1e-3), "gpu_launches": rec["launches"],
+      "kernel": r["kernel"], "kernel_ms": r["kernel_ms"], "frac": r["frac"], "iter_frac": r["iter_frac"],
+      "layout_frac": r["layout_frac"], "layout_iter_frac": r["layout_iter_frac"], "physical_frac": r["physical_frac"],
+      "traffic": r["traffic"], "storage": r["storage"], "clocks": rec["clocks"], "checksum_max_abs_msg": rec["checksum"],
+  }
+  if rec["parity"]:
+    out.update(rec["parity"])
+  return out
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -365,6 +587,9 @@ def main():
   ap.add_argument("--iters", type=int, default=None, help="BP iterations per step override")
   ap.add_argument("--size", type=int, default=None, help="grid side of the ising_big workload")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-extras", action="store_true",
+                  help="skip the sub-records (other_workloads at N = 1; rbm_strong and strips at N > 1)")
+  ap.add_argument("--strip-flags", type=int, default=0, help="PGX_STRIP_* flags (A/B: 1 no graph, 2 no overlap)")
   ap.add_argument("--disable-paths", type=int, default=0, help="PGX_PATH_* mask (A/B runs of launch paths)")
   ap.add_argument("--exact-order", action="store_true",
                   help="force the two-pass serial-summation-order path (pgx_plan_set_exact_order)")
@@ -380,7 +605,6 @@ def main():
   import torch
   import torch.distributed as dist
   from pgmax_b200 import _native
-  from pgmax_b200.infer.bp_state import BPArrays
 
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -392,150 +616,113 @@ def main():
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 
-  wl = build_workload(args.workload, batch_override=args.batch, iters_override=args.iters)
-  bp, iters, damping, T = wl["bp"], wl["iters"], wl["damping"], wl["temperature"]
-  # every rank draws its own shard of samples (weak scaling: per-GPU batch fixed)
-  host = wl["arrays"]
-  if world > 1 and host.evidence.ndim == 2:
-    rng = np.random.default_rng(100 + rank)
-    host = BPArrays(log_potentials=host.log_potentials, ftov_msgs=host.ftov_msgs,
-                    evidence=rng.gumbel(size=host.evidence.shape).astype(np.float32))
-  plan = bp.context.plan
-  plan.set_exact_order(args.exact_order)
-  plan.disable_paths(args.disable_paths)
-  batch = host.batch_size or 1
-  put = lambda a: torch.from_numpy(np.array(a, dtype=np.float32, order="C")).to(dev)
-  dev_arrays = BPArrays(log_potentials=put(host.log_potentials), ftov_msgs=put(host.ftov_msgs),
-                        evidence=put(host.evidence))
-  es = plan.num_edge_states
-  msgs_per_step = es * batch * iters
-
-  def barrier():
-    if world > 1:
-      dist.barrier()
-    torch.cuda.synchronize()
-
-  # ---- device-resident timing ------------------------------------------------------------
-  for _ in range(args.warmup):
-    out = bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
-  barrier()
-  launches0 = plan.launch_count
-  sampler = ClockSampler(local_rank)
-  sampler.start()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  barrier()
-  e0.record()
-  for _ in range(args.steps):
-    out = bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
-  e1.record()
-  barrier()
-  ms = e0.elapsed_time(e1)
-  clocks = sampler.stop()
-  launches = plan.launch_count - launches0
-  # roofline pass: the same step once more with CUDA events around every launch of the
-  # dominant kernel (kept out of the timed region above)
-  plan.profile_enable(True)
-  bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
-  torch.cuda.synchronize()
-  n_prof, prof_ms, prof_name = plan.profile_read()
-  plan.profile_enable(False)
-  checksum = float(out.ftov_msgs.float().abs().max().item())
-
-  # ---- end to end through the C ABI with host buffers ---------------------------------------
-  pin = lambda a: torch.from_numpy(np.array(a, dtype=np.float32, order="C")).pin_memory()
-  h_lp, h_ev = pin(host.log_potentials), pin(host.evidence)
-  h_map = torch.empty((batch, plan.num_vars), dtype=torch.int32).pin_memory()
-  h_ties = torch.empty((batch,), dtype=torch.int32).pin_memory()
-  stream = torch.cuda.current_stream(dev).cuda_stream
-
-  def e2e_step():
-    plan.infer_host(stream, batch, h_lp.data_ptr(), h_lp.ndim == 2, h_ev.data_ptr(), h_ev.ndim == 2,
-                    None, False, iters, damping, T, h_map.data_ptr(), None, h_ties.data_ptr(), None, None)
-
-  for _ in range(min(args.warmup, 2)):
-    e2e_step()
-  barrier()
-  e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  t0 = time.perf_counter()
-  e2.record()
-  for _ in range(args.steps):
-    e2e_step()
-  e3.record()
-  barrier()
-  e2e_ms = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
-  h2d = 4 * (h_lp.numel() + h_ev.numel())
-  d2h = 4 * (h_map.numel() + h_ties.numel())
-
-  if world > 1:
-    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+  def reduce_max(*vals):
+    if world == 1:
+      return list(vals)
+    t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = t.tolist()
+    return t.tolist()
 
+  # ---- the main line: weak scaling, per-GPU batch fixed, every rank its own shard of samples -----
+  rec = measure(args, args.workload, dev, rank, world, local_rank, batch=args.batch, iters=args.iters,
+                shard_seed=(100 + rank) if world > 1 else None)
+  ms, e2e_ms = reduce_max(rec["ms"], rec["e2e_ms"])
+  wl, plan, batch, iters, es = rec["wl"], rec["plan"], rec["batch"], rec["iters"], rec["es"]
+  msgs_per_step = es * batch * iters
+  line = None
   if rank == 0:
-    peak, peak_src = hbm_peak()
-    lp_batched = host.log_potentials.ndim == 2
-    bytes_iter = algorithmic_bytes_per_iter(plan, batch, lp_batched)
-    traffic = None
-    try:
-      entry = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(f"{args.workload}:{prof_name}")
-      if entry and batch == 1024:
-        traffic = entry["bytes"]
-    except (OSError, ValueError):
-      pass
-    kernel_ms = prof_ms / max(n_prof, 1)
-    # the dominant launch updates dom_es of the es edge-states: its share of the iteration's
-    # algorithmic bytes (single-kernel iterations: all of them)
-    single_kernel = prof_name in ("k_enum_pw2_bip", "k_lattice", "k_enum_pw2_pull")
-    dom_es = es if single_kernel else min(plan.dominant_edge_states, es)
-    kernel_bytes = bytes_iter * dom_es // es
-    achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if n_prof else None
-    # bytes the kernels really have to move: the single-pass path stores a two-state edge as
-    # ONE float between iterations (pgx_plan_compressed_edges), i.e. one float less to read and
-    # one less to write per such edge, sample and iteration than the reference layout
-    fused_run = plan.has_fused_blocks and not args.exact_order and batch > 16 and not lp_batched
-    saved = 8 * plan.compressed_edges * batch if fused_run else 0
-    layout_bytes = bytes_iter - saved
-    iter_ms = ms / args.steps / iters
-    iter_gbs = bytes_iter / (iter_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": msgs_per_step * args.steps * world / (ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["label"], "batch_per_gpu": batch, "global_batch": batch * world,
-                   "iters": iters, "damping": damping, "temperature": T, "edge_states": es,
+                   "iters": iters, "damping": rec["damping"], "temperature": rec["temperature"], "edge_states": es,
                    "l2": "working set (2 x %.2f GB of messages) larger than L2" % (4e-9 * es * batch)
                    if 8 * es * batch > 126e6 else "L2-resident working set (reported, not an HBM figure)",
-                   "summation_order": "serial (two-pass)" if args.exact_order or not plan.has_fused_blocks
-                   or batch <= 16 else "tiled partial sums (single pass)",
+                   "summation_order": "tiled partial sums (single pass)" if rec["fused_run"] else "serial (two-pass)",
                    "parallelism": f"batch-sharded x{world}, no collective"},
         "e2e": {"value": msgs_per_step * args.steps * world / (e2e_ms * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "h2d_bytes_per_step": rec["h2d"], "d2h_bytes_per_step": rec["d2h"],
                 "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": launches,
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                     "kernel": prof_name, "kernel_ms": kernel_ms, "launches_timed": n_prof,
-                     "algorithmic_bytes_per_launch": kernel_bytes, "peak_source": peak_src,
-                     "edge_states_per_launch": dom_es * batch,
-                     # the whole iteration (every kernel of it) against the same peak
-                     "iter_ms": iter_ms, "iter_algorithmic_bytes": bytes_iter,
-                     "iter_achieved": iter_gbs, "iter_frac": iter_gbs / peak,
-                     # the same two figures against the bytes of the workspace layout actually
-                     # used (binary-difference storage halves the message bytes): <= 1 by construction
-                     "storage": ("binary-difference, 1 float per two-state edge between iterations"
-                                 if saved else "reference layout, 1 float per edge-state"),
-                     "note": ("frac uses SURVEY 8(d)'s algorithmic bytes (two floats read + written per two-state "
-                              "edge); the kernels keep ONE float per such edge between iterations, bit-identical "
-                              "values, so frac > 1 is expected - layout_frac is the fraction of peak on the bytes "
-                              "actually moved, traffic the DRAM bytes ncu measured per launch") if saved else None,
-                     "layout_bytes_per_iter": layout_bytes,
-                     "layout_frac": (layout_bytes * (kernel_bytes / bytes_iter) / (kernel_ms * 1e-3) / 1e9 / peak)
-                     if n_prof else None,
-                     "layout_iter_frac": layout_bytes / (iter_ms * 1e-3) / 1e9 / peak},
-        "checksum_max_abs_msg": checksum,
+        "gpu_launches": rec["launches"],
+        "clocks": rec["clocks"],
+        "roofline": roofline_of(args.workload, rec, ms),
+        "checksum_max_abs_msg": rec["checksum"],
     }
+    if rec["parity"]:
+      line.update(rec["parity"])
+      line["parity_note"] = ("sample 0 of the timed batch, benchmarked path, vs oracle/bp_oracle.py (NumPy fp32, serial "
+                             "order), outside the timed region; the oracle's own distance to an fp64 run of this "
+                             "recursion is 1.6e-5 after 2 iterations on the RBM (tests/test_gpu_config1_rbm.py)")
+  del rec, plan, wl
+  torch.cuda.empty_cache()
+
+  # ---- sub-records ---------------------------------------------------------------------------
+  if not args.no_extras and args.workload == "rbm" and args.batch is None and args.iters is None:
+    quick = dict(steps=2, warmup=3)
+    if world == 1:
+      others = {}
+      for name in ("ising50", "deconv", "rcn"):
+        try:
+          r = measure(args, name, dev, rank, world, local_rank, parity_iters=2 if name != "rcn" else 0, **quick)
+          others[name] = compact_record(name, r)
+          del r
+        except Exception as err:  # pylint: disable=broad-except
+          others[name] = {"error": repr(err)[-300:]}
+        torch.cuda.empty_cache()
+      try:
+        n_big, it_big = 8192, 200
+        r = strip_record(args, dev, 0, 1, n_big, it_big, 2, 2, sampler_index=local_rank)
+        f = strip_line_fields(n_big, it_big, 2, 1, r["ms"], r["e2e_ms"], r)
+        f["clocks"] = r["clocks"]
+        f["workload"] = f"Ising {n_big}x{n_big} torus, single graph, sum-product T=1, one GPU"
+        others["ising_big"] = f
+      except Exception as err:  # pylint: disable=broad-except
+        others["ising_big"] = {"error": repr(err)[-300:]}
+      line["other_workloads"] = others
+    else:
+      # (1) BASELINE configs[1] as it is worded: batch 1024 sharded over the GPUs (strong scaling);
+      #     T1 = the main line's per-GPU time (every rank ran the full batch of 1024 there)
+      try:
+        per = (1024 + world - 1) // world
+        r = measure(args, "rbm", dev, rank, world, local_rank, batch=per, shard_seed=200 + rank, parity_iters=0,
+                    with_clocks=rank == 0, **quick)
+        s_ms, s_e2e = reduce_max(r["ms"], r["e2e_ms"])
+        if rank == 0:
+          r["ms"], r["e2e_ms"] = s_ms, s_e2e
+          c = compact_record("rbm", r, world)
+          c["global_batch"], c["scaling"] = per * world, "strong"
+          c["efficiency_vs_same_session_n1"] = (ms / args.steps) / (world * s_ms / r["steps"]) * (per * world / 1024.0)
+          c["parallelism"] = f"batch 1024 sharded x{world} ({per} samples per GPU), no collective"
+          line["rbm_strong"] = c
+        del r
+      except Exception as err:  # pylint: disable=broad-except
+        if rank == 0:
+          line["rbm_strong"] = {"error": repr(err)[-300:]}
+      torch.cuda.empty_cache()
+      # (2) BASELINE configs[4]: Ising 8192^2 in row strips with the NCCL halo ring (strong scaling);
+      #     T1 = the whole torus on rank 0's GPU in the same session
+      try:
+        n_big, it_big = 8192, 200
+        r = strip_record(args, dev, rank, world, n_big, it_big, 2, 2, sampler_index=local_rank if rank == 0 else None)
+        s_ms, s_e2e = reduce_max(r["ms"], r["e2e_ms"])
+        one = None
+        if rank == 0:
+          one = strip_record(args, dev, 0, 1, n_big, it_big, 2, 1)
+        dist.barrier()
+        if rank == 0:
+          f = strip_line_fields(n_big, it_big, 2, world, s_ms, s_e2e, r)
+          f["clocks"], f["scaling"] = r["clocks"], "strong"
+          f["workload"] = f"Ising {n_big}x{n_big} torus, single graph, sum-product T=1"
+          f["n1_iter_ms_same_session"] = one["ms"] / 2 / it_big
+          f["efficiency_vs_same_session_n1"] = one["ms"] / (world * s_ms)
+          line["strips"] = f
+      except Exception as err:  # pylint: disable=broad-except
+        if rank == 0:
+          line["strips"] = {"error": repr(err)[-300:]}
+
+  if rank == 0:
     if world == 1 and not args.no_cpu_baseline:
       try:
         sub = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",

@@ -294,6 +294,8 @@ int pgx_plan_is_lattice(const pgx_plan* plan);
 int pgx_plan_profile_enable(pgx_plan* plan, int enabled);
 /* Edge-states (per sample) the dominant launch updates: the units of its roofline figure. */
 int64_t pgx_plan_dominant_edge_states(const pgx_plan* plan);
+/* CTAs of the dominant kernel's most recent launch (0 before the first run). */
+int64_t pgx_plan_dominant_grid(const pgx_plan* plan);
 int pgx_plan_profile_read(pgx_plan* plan, int64_t* num_launches, double* total_ms,
                           const char** kernel_name);
 

@@ -45,6 +45,7 @@ EXPORTED_SYMBOLS = (
     "pgx_plan_disable_paths",
     "pgx_plan_is_lattice",
     "pgx_plan_dominant_edge_states",
+    "pgx_plan_dominant_grid",
     "pgx_plan_profile_enable",
     "pgx_plan_profile_read",
     "pgx_last_error",
@@ -192,6 +193,8 @@ def load() -> ctypes.CDLL:
   lib.pgx_plan_is_lattice.restype = ctypes.c_int
   lib.pgx_plan_dominant_edge_states.argtypes = [vp]
   lib.pgx_plan_dominant_edge_states.restype = ctypes.c_int64
+  lib.pgx_plan_dominant_grid.argtypes = [vp]
+  lib.pgx_plan_dominant_grid.restype = ctypes.c_int64
   lib.pgx_plan_profile_enable.argtypes = [vp, ctypes.c_int]
   lib.pgx_plan_profile_enable.restype = ctypes.c_int
   lib.pgx_plan_profile_read.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double),
@@ -420,6 +423,11 @@ class Plan:
   @property
   def dominant_edge_states(self) -> int:
     return int(self._lib.pgx_plan_dominant_edge_states(self.handle))
+
+  @property
+  def dominant_grid(self) -> int:
+    """CTAs of the dominant kernel's most recent launch."""
+    return int(self._lib.pgx_plan_dominant_grid(self.handle))
 
   @property
   def is_lattice(self) -> bool:

@@ -40,44 +40,66 @@ struct LatticeBinArgs {
   const float* ghost_ev;  // [2 N] evidence of the ghost row (torus = 0), or null: row R of the evidence array
 };
 
-template <int TR_, int TC_, int STAGES_>
+template <int TR_, int TC_, int STAGES_, int CONSUMERS_ = 512, int CTAS_ = 1>
 struct LbCfg {
   static constexpr int TR = TR_, TC = TC_, kStages = STAGES_;
+  static constexpr int kCtasPerSm = CTAS_;             // resident CTAs per SM the kernel is built for
+  static constexpr int kConsumers = CONSUMERS_;        // consumer threads (+ one producer warp)
+  static constexpr int kThreads = kConsumers + 32;
+  static constexpr int kRpp = kConsumers / TC;         // tile rows the consumers cover side by side
   static constexpr int MR = TR + 2, MC = TC + 2;
   static constexpr int kMsgF4 = MR * MC;        // float4 per message stage (one per cell)
   static constexpr int kLpF4 = TR * TC * 2;     // float4 per potential stage (two factors per cell)
   static constexpr int kSumF2 = (TR + 1) * (TC + 1);
+  static_assert(kConsumers % TC == 0 && TC % 32 == 0, "a warp must not straddle tile rows");
   static constexpr size_t smem_bytes() {
     return size_t(kStages) * (kMsgF4 + kLpF4) * sizeof(float4) + size_t(2) * kSumF2 * sizeof(float2) +
            2 * kStages * sizeof(uint64_t);
   }
 };
-constexpr int kLbConsumers = 512;              // 16 warps
-constexpr int kLbThreads = kLbConsumers + 32;  // + producer warp
 
 __device__ __forceinline__ f32x2 bin_pair(float x) { return pk2(fminf(-x, 0.f), fminf(x, 0.f)); }
 
-// Tile i of this CTA -> (first owner row, rows of the tile that are updated, first column).
+// Tile -> (first owner row, rows of the tile that are updated, first column).
 struct LbTile {
   int l0, rows, j0;
 };
 template <class Cfg>
-__device__ __forceinline__ LbTile lb_tile(const LatticeBinArgs& g, int64_t tile, int tiles_x, int ty0) {
-  const int ty = int(tile / tiles_x), tx = int(tile - int64_t(ty) * tiles_x);
+__device__ __forceinline__ LbTile lb_tile(const LatticeBinArgs& g, unsigned tile, unsigned tiles_x, int ty0) {
+  const unsigned ty = tile / tiles_x, tx = tile - ty * tiles_x;
   LbTile t;
-  const int s = ty < ty0 ? 0 : 1;
-  const int tyl = s == 0 ? ty : ty - ty0;
-  t.l0 = g.seg_begin[s] + tyl * Cfg::TR;
-  t.rows = min(Cfg::TR, g.seg_end[s] - t.l0);
-  t.j0 = tx * Cfg::TC;
+  const bool first = int(ty) < ty0;  // (selects, not array indexing: the struct stays in constant memory)
+  const int tyl = first ? int(ty) : int(ty) - ty0;
+  t.l0 = (first ? g.seg_begin[0] : g.seg_begin[1]) + tyl * Cfg::TR;
+  t.rows = min(Cfg::TR, (first ? g.seg_end[0] : g.seg_end[1]) - t.l0);
+  t.j0 = int(tx) * Cfg::TC;
   return t;
 }
 
-template <bool kSumProduct, bool kDelta, class Cfg>
-__global__ void __launch_bounds__(kLbThreads, 1)
+__device__ __forceinline__ void mbar_wait_u32(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+
+// kClip: clip the potentials to +-1e6 on the fly (bp.py:85-87); the host passes false when it has
+// checked that every potential of the run is already inside the range (the usual case).
+template <bool kSumProduct, bool kDelta, class Cfg, bool kClip = true>
+__global__ void __launch_bounds__(Cfg::kThreads, Cfg::kCtasPerSm)
 k_lattice_bin(LatticeBinArgs g, const float* __restrict__ ev, const float* __restrict__ lp,
               const float4* __restrict__ c_old, float4* __restrict__ c_new, RunArgs a) {
   constexpr int TR = Cfg::TR, TC = Cfg::TC, MC = Cfg::MC, MR = Cfg::MR, kStages = Cfg::kStages;
+  constexpr int kCons = Cfg::kConsumers, kRpp = Cfg::kRpp;
   extern __shared__ __align__(128) unsigned char lb_raw[];
   float4* msg_s = reinterpret_cast<float4*>(lb_raw);                         // [stage][MR][MC]
   float4* lp_s = msg_s + kStages * Cfg::kMsgF4;                              // [stage][TR][TC][2]
@@ -86,28 +108,28 @@ k_lattice_bin(LatticeBinArgs g, const float* __restrict__ ev, const float* __res
   uint64_t* done = full + kStages;                                           // [stage] tile updated
   const int R = g.R, N = g.N;
   const bool torus = g.torus != 0;
-  const int tiles_x = (N + TC - 1) / TC;
+  const unsigned tiles_x = unsigned((N + TC - 1) / TC);
   const int ty0 = max(0, (g.seg_end[0] - g.seg_begin[0] + TR - 1) / TR);
   const int ty1 = max(0, (g.seg_end[1] - g.seg_begin[1] + TR - 1) / TR);
-  const int64_t num_tiles = int64_t(tiles_x) * (ty0 + ty1);
-  const int64_t my_tiles = (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const unsigned num_tiles = tiles_x * unsigned(ty0 + ty1);
+  const int my_tiles = blockIdx.x < num_tiles ? int((num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&done[s], kLbConsumers);
+      mbar_init(&done[s], kCons);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const float4* lp4 = reinterpret_cast<const float4*>(lp);
 
-  if (threadIdx.x >= kLbConsumers) {
+  if (threadIdx.x >= kCons) {
     // ------------------------------- producer warp ---------------------------------------
     const int lane = threadIdx.x & 31;
-    auto load_tile = [&](int64_t i) {
-      const LbTile t = lb_tile<Cfg>(g, blockIdx.x + i * gridDim.x, tiles_x, ty0);
+    auto load_tile = [&](int i) {
+      const LbTile t = lb_tile<Cfg>(g, blockIdx.x + unsigned(i) * gridDim.x, tiles_x, ty0);
       const int l0 = t.l0, j0 = t.j0;
-      const int stage = int(i % kStages);
+      const int stage = i % kStages;
       float4* ms = msg_s + stage * Cfg::kMsgF4;
       float4* ls = lp_s + stage * Cfg::kLpF4;
       const int ncols = min(TC + 1, N - j0);        // cells from column j0 on (incl. the right halo if inside)
@@ -137,12 +159,12 @@ k_lattice_bin(LatticeBinArgs g, const float* __restrict__ ev, const float* __res
     };
     for (int s = 0; s < kStages - 1; ++s)
       if (s < my_tiles) load_tile(s);
-    for (int64_t i = 0; i < my_tiles; ++i) {
+    for (int i = 0; i < my_tiles; ++i) {
       // the stage of tile i - 1 has been drained below: refill it with tile i + kStages - 1
       if (i + kStages - 1 < my_tiles) load_tile(i + kStages - 1);
-      const int stage = int(i % kStages);
+      const int stage = i % kStages;
       mbar_wait(&done[stage], uint32_t(i / kStages) & 1u);
-      const LbTile t = lb_tile<Cfg>(g, blockIdx.x + i * gridDim.x, tiles_x, ty0);
+      const LbTile t = lb_tile<Cfg>(g, blockIdx.x + unsigned(i) * gridDim.x, tiles_x, ty0);
       const int lcols = min(TC, N - t.j0);
       if (lane < t.rows) {
         bulk_s2g(c_new + int64_t(t.l0 + lane) * N + t.j0, msg_s + stage * Cfg::kMsgF4 + (lane + 1) * MC + 1,
@@ -156,77 +178,161 @@ k_lattice_bin(LatticeBinArgs g, const float* __restrict__ ev, const float* __res
   }
 
   // --------------------------------- consumer warps -----------------------------------------
+  // Thread -> (tile row r0 + k * kRpp, tile column cc): the column is fixed, a warp never
+  // straddles rows, so every row condition below is warp-uniform.  Column TC of the sums (the
+  // right halo) is an extra variable for the threads tid <= TR (row tid).
   const float2* ev2 = reinterpret_cast<const float2*>(ev);
   const float2* up2 = reinterpret_cast<const float2*>(g.up_add);
   const float2* ghost2 = reinterpret_cast<const float2*>(g.ghost_ev);
   const RunArgs2 c2 = make_args2(a);
+  const int tid = threadIdx.x;
+  const int cc = tid % TC, r0 = tid / TC;
+  constexpr int kSumPass = (TR + 1 + kRpp - 1) / kRpp;
+  constexpr int kFacPass = (TR + kRpp - 1) / kRpp;
   float dmax = 0.f;
-  for (int64_t i = 0; i < my_tiles; ++i) {
-    const LbTile t = lb_tile<Cfg>(g, blockIdx.x + i * gridDim.x, tiles_x, ty0);
-    const int l0 = t.l0, j0 = t.j0;
-    const int stage = int(i % kStages);
+
+  // Tiles of this CTA: tile index blockIdx.x + i * gridDim.x, coordinates advanced incrementally.
+  struct Cursor {
+    unsigned ty, tx;
+  };
+  const unsigned step_y = gridDim.x / tiles_x, step_x = gridDim.x - step_y * tiles_x;
+  auto tile_at = [&](const Cursor& c) {
+    LbTile t;
+    const bool first = int(c.ty) < ty0;  // (selects, not array indexing: the struct stays in constant memory)
+    const int tyl = first ? int(c.ty) : int(c.ty) - ty0;
+    t.l0 = (first ? g.seg_begin[0] : g.seg_begin[1]) + tyl * TR;
+    t.rows = min(TR, (first ? g.seg_end[0] : g.seg_end[1]) - t.l0);
+    t.j0 = int(c.tx) * TC;
+    return t;
+  };
+  auto advance = [&](Cursor& c) {
+    c.ty += step_y;
+    c.tx += step_x;
+    if (c.tx >= tiles_x) { c.tx -= tiles_x; ++c.ty; }
+  };
+  // An interior tile touches no lattice border: every variable of its (TR + 1) x (TC + 1) sums is
+  // an owner variable with all four neighbours in place (no wrap, no ghost, no halo addend).
+  auto is_interior = [&](const LbTile& t) {
+    return t.rows == TR && t.l0 >= 1 && t.l0 + TR <= R - 1 && t.j0 >= 1 && t.j0 + TC <= N - 1;
+  };
+
+  // evidence (+ halo addend) of variable (l0 + rr, j0 + c) of tile t; zeros if it is not needed
+  auto ev_at = [&](const LbTile& t, int rr, int c) {
+    int l = t.l0 + rr, j = t.j0 + c;
+    float2 e = make_float2(0.f, 0.f);
+    if (rr <= t.rows && l <= R && j <= N) {
+      if (j == N) j = 0;
+      if (torus && l == R) l = 0;
+      e = (ghost2 != nullptr && l == R) ? __ldg(ghost2 + j) : __ldg(ev2 + (int64_t(l) * N + j));
+      if (up2 != nullptr && l == 0 && !torus) {  // halo: messages from the strip above
+        const float2 u = __ldg(up2 + j);
+        e.x += u.x;
+        e.y += u.y;
+      }
+    }
+    return e;
+  };
+  // S of variable (l0 + rr, j0 + c) from the staged messages: evidence first, then the incident
+  // messages in ascending message index, wrap-around neighbours last (the order of k_lattice)
+  auto var_sum = [&](const LbTile& t, const float4* sm, int rr, int c, float2 e) {
+    int l = t.l0 + rr;
+    const int j = t.j0 + c;
+    if (torus && l == R) l = 0;
+    const bool has_own = l < R;
+    const bool has_up = torus || l > 0;
+    const bool up_wrap = torus && l == 0;
+    const bool left_wrap = j == 0 || j == N;
+    // cell of column j0 + c sits at sm column c + 1, except the wrapped right halo
+    const int col = (j == N) ? (N - t.j0) + 1 : c + 1;
+    const float4 own = sm[(rr + 1) * MC + col];
+    const float up = sm[rr * MC + col].y;                // V factor of the row above: its b edge
+    const float left = sm[(rr + 1) * MC + col - 1].w;    // H factor of the left neighbour: its b edge
+    f32x2 s = pk2(e.x, e.y);
+    if (has_up && !up_wrap) s = add2(s, bin_pair(up));
+    if (has_own && !left_wrap) s = add2(s, bin_pair(left));
+    if (has_own) { s = add2(s, bin_pair(own.x)); s = add2(s, bin_pair(own.z)); }
+    if (has_own && left_wrap) s = add2(s, bin_pair(left));
+    if (up_wrap) s = add2(s, bin_pair(up));
+    float s0, s1;
+    upk2(s, s0, s1);
+    return make_float2(s0, s1);
+  };
+  // the same for an interior tile: up, left, own V, own H - the ascending message order
+  auto var_sum_interior = [&](const float4* sm, int rr, int c, float2 e) {
+    const float4 own = sm[(rr + 1) * MC + c + 1];
+    const float up = sm[rr * MC + c + 1].y;
+    const float left = sm[(rr + 1) * MC + c].w;
+    f32x2 s = add2(pk2(e.x, e.y), bin_pair(up));
+    s = add2(s, bin_pair(left));
+    s = add2(s, bin_pair(own.x));
+    s = add2(s, bin_pair(own.z));
+    float s0, s1;
+    upk2(s, s0, s1);
+    return make_float2(s0, s1);
+  };
+  auto load_evidence = [&](const LbTile& t, float2 (&e)[kSumPass], float2& e_x) {
+    if (is_interior(t)) {
+      const float2* base = ev2 + (int64_t(t.l0) * N + t.j0);
+#pragma unroll
+      for (int k = 0; k < kSumPass; ++k)
+        if (r0 + k * kRpp <= TR) e[k] = __ldg(base + ((r0 + k * kRpp) * N + cc));
+      if (tid <= TR) e_x = __ldg(base + (tid * N + TC));
+    } else {
+#pragma unroll
+      for (int k = 0; k < kSumPass; ++k) e[k] = ev_at(t, r0 + k * kRpp, cc);
+      if (tid <= TR) e_x = ev_at(t, tid, TC);
+    }
+  };
+
+  const uint32_t full_u32 = smem_u32(full), done_u32 = smem_u32(done);
+  float2 e[kSumPass], e_x = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < kSumPass; ++k) e[k] = make_float2(0.f, 0.f);
+  Cursor cur{blockIdx.x / tiles_x, blockIdx.x % tiles_x};
+  LbTile t = tile_at(cur);
+  if (my_tiles > 0) load_evidence(t, e, e_x);
+  for (int i = 0; i < my_tiles; ++i) {
+    const int stage = i % kStages;
     float4* sm = msg_s + stage * Cfg::kMsgF4;
     const float4* lq = lp_s + stage * Cfg::kLpF4;
     float2* Ss = sum_s + (i & 1) * Cfg::kSumF2;
-    // evidence of this thread's variables: requested before the wait
-    constexpr int kVars = (Cfg::kSumF2 + kLbConsumers - 1) / kLbConsumers;
-    float2 e[kVars];
+    const bool interior = is_interior(t);
+    mbar_wait_u32(full_u32 + stage * 8, uint32_t(i / kStages) & 1u);
+    // ---- variable sums ------------------------------------------------------------------------
+    if (interior) {
 #pragma unroll
-    for (int k = 0; k < kVars; ++k) {
-      const int tt = threadIdx.x + k * kLbConsumers;
-      const int rr = tt / (TC + 1), cc = tt - rr * (TC + 1);
-      int l = l0 + rr, j = j0 + cc;
-      e[k] = make_float2(0.f, 0.f);
-      if (tt < Cfg::kSumF2 && rr <= t.rows && l <= R && j <= N) {
-        if (j == N) j = 0;
-        if (torus && l == R) l = 0;
-        e[k] = (ghost2 != nullptr && l == R) ? __ldg(ghost2 + j) : __ldg(ev2 + (int64_t(l) * N + j));
-        if (up2 != nullptr && l == 0 && !torus) {  // halo: messages from the strip above
-          const float2 u = __ldg(up2 + j);
-          e[k].x += u.x;
-          e[k].y += u.y;
-        }
+      for (int k = 0; k < kSumPass; ++k) {
+        const int rr = r0 + k * kRpp;
+        if (rr <= TR) Ss[rr * (TC + 1) + cc] = var_sum_interior(sm, rr, cc, e[k]);
       }
-    }
-    mbar_wait(&full[stage], uint32_t(i / kStages) & 1u);
-    // ---- variable sums (same order as k_lattice) -------------------------------------------
+      if (tid <= TR) Ss[tid * (TC + 1) + TC] = var_sum_interior(sm, tid, TC, e_x);
+    } else {
 #pragma unroll
-    for (int k = 0; k < kVars; ++k) {
-      const int tt = threadIdx.x + k * kLbConsumers;
-      const int rr = tt / (TC + 1), cc = tt - rr * (TC + 1);
-      int l = l0 + rr, j = j0 + cc;
-      if (tt >= Cfg::kSumF2 || rr > t.rows || l > R || j > N) continue;
-      if (j == N) j = 0;
-      if (torus && l == R) l = 0;
-      const bool has_own = l < R;
-      const bool has_up = torus || l > 0;
-      const bool up_wrap = torus && l == 0;
-      const bool left_wrap = j == 0;
-      // cell of column j0 + cc sits at sm column cc + 1, except the wrapped right halo
-      const int col = (j0 + cc == N) ? (N - j0) + 1 : cc + 1;
-      const float4 own = sm[(rr + 1) * MC + col];
-      const float up = sm[rr * MC + col].y;                // V factor of the row above: its b edge
-      const float left = sm[(rr + 1) * MC + col - 1].w;    // H factor of the left neighbour: its b edge
-      f32x2 s = pk2(e[k].x, e[k].y);
-      if (has_up && !up_wrap) s = add2(s, bin_pair(up));
-      if (has_own && !left_wrap) s = add2(s, bin_pair(left));
-      if (has_own) { s = add2(s, bin_pair(own.x)); s = add2(s, bin_pair(own.z)); }
-      if (has_own && left_wrap) s = add2(s, bin_pair(left));
-      if (up_wrap) s = add2(s, bin_pair(up));
-      float s0, s1;
-      upk2(s, s0, s1);
-      Ss[tt] = make_float2(s0, s1);
+      for (int k = 0; k < kSumPass; ++k) {
+        const int rr = r0 + k * kRpp;
+        if (rr <= t.rows && t.l0 + rr <= R && t.j0 + cc <= N) Ss[rr * (TC + 1) + cc] = var_sum(t, sm, rr, cc, e[k]);
+      }
+      if (tid <= TR && tid <= t.rows && t.l0 + tid <= R && t.j0 + TC <= N) Ss[tid * (TC + 1) + TC] = var_sum(t, sm, tid, TC, e_x);
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(kLbConsumers) : "memory");
+    // the next tile's evidence: in flight during this tile's factor phase
+    const LbTile t_now = t;
+    if (i + 1 < my_tiles) {
+      advance(cur);
+      t = tile_at(cur);
+      load_evidence(t, e, e_x);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kCons) : "memory");
     // ---- the two factors of every cell, in place ---------------------------------------------
-    constexpr int kCells = TR * TC / kLbConsumers;
-    static_assert(TR * TC % kLbConsumers == 0, "tile cells must divide over the consumer threads");
 #pragma unroll
-    for (int k = 0; k < kCells; ++k) {
-      const int cell = threadIdx.x + k * kLbConsumers;
-      const int rr = cell / TC, cc = cell - rr * TC;
-      if (rr < t.rows && j0 + cc < N) {
-        const float4 lv = lq[cell * 2], lh = lq[cell * 2 + 1];
+    for (int k = 0; k < kFacPass; ++k) {
+      const int rr = r0 + k * kRpp;
+      if (rr < t_now.rows && t_now.j0 + cc < N) {
+        const int cell = rr * TC + cc;
+        float4 lv = lq[cell * 2], lh = lq[cell * 2 + 1];
+        if (kClip) {
+          lv = make_float4(clip_lp(lv.x), clip_lp(lv.y), clip_lp(lv.z), clip_lp(lv.w));
+          lh = make_float4(clip_lp(lh.x), clip_lp(lh.y), clip_lp(lh.z), clip_lp(lh.w));
+        }
         float4* slot = sm + (rr + 1) * MC + cc + 1;
         const float4 x = *slot;
         const float2 sa = Ss[rr * (TC + 1) + cc];
@@ -235,17 +341,15 @@ k_lattice_bin(LatticeBinArgs g, const float* __restrict__ ev, const float* __res
         const f32x2 Sa = pk2(sa.x, sa.y);
         float4 o;
         f32x2 na, nb;
-        dmax = fmaxf(dmax, pw2_update_bin<kSumProduct, kDelta>(
-                               x.x, x.y, Sa, pk2(sv.x, sv.y), pk2(clip_lp(lv.x), clip_lp(lv.y)),
-                               pk2(clip_lp(lv.z), clip_lp(lv.w)), c2, o.x, o.y, na, nb));
-        dmax = fmaxf(dmax, pw2_update_bin<kSumProduct, kDelta>(
-                               x.z, x.w, Sa, pk2(sh.x, sh.y), pk2(clip_lp(lh.x), clip_lp(lh.y)),
-                               pk2(clip_lp(lh.z), clip_lp(lh.w)), c2, o.z, o.w, na, nb));
+        dmax = fmaxf(dmax, pw2_update_bin<kSumProduct, kDelta>(x.x, x.y, Sa, pk2(sv.x, sv.y), pk2(lv.x, lv.y),
+                                                               pk2(lv.z, lv.w), c2, o.x, o.y, na, nb));
+        dmax = fmaxf(dmax, pw2_update_bin<kSumProduct, kDelta>(x.z, x.w, Sa, pk2(sh.x, sh.y), pk2(lh.x, lh.y),
+                                                               pk2(lh.z, lh.w), c2, o.z, o.w, na, nb));
         *slot = o;
       }
     }
     fence_proxy_async();
-    mbar_arrive(&done[stage]);
+    mbar_arrive_u32(done_u32 + stage * 8);
   }
   if (kDelta) {
     for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));

@@ -68,7 +68,9 @@ enum EnumVariant { kPw2 = 0, kSmall = 1, kBig = 2 };
 // groups of kernels whose shared-memory attribute has been raised (pgx_plan::attr_done)
 enum AttrGroup { kAttrBigMax = 0, kAttrBipMax = 1, kAttrBipSum = 2, kAttrBigEnumMax = 3, kAttrBigEnumSum = 4,
                  kAttrMaxProd = 5, kAttrLattice = 6, kAttrSdlpMax = 7, kAttrSdlpSum = 8, kAttrLatticeBin = 9,
-                 kAttrOrAnd = 10 };
+                 kAttrLatticeBinV1 = 10, kAttrLatticeBinV2 = 11, kAttrLatticeBinV3 = 12, kAttrLatticeBinV4 = 13,
+                 kAttrLatticeBinV5 = 14, kAttrLatticeBinV6 = 15, kAttrLatticeBinV7 = 16, kAttrLatticeBinV8 = 17,
+                 kAttrLatticeBinV9 = 18, kAttrOrAnd = 19 };
 
 struct EnumBlockPlan {
   pgx::EnumBlockDev dev{};
@@ -250,6 +252,7 @@ struct pgx_plan {
   bool profiling = false;
   int dominant = 0;
   int64_t dominant_es = 0;  // edge-states the dominant launch updates
+  int64_t dominant_grid = 0;  // CTAs of its last launch (bench.py matches ncu captures by kernel, batch and grid)
   const char* dominant_name = "";
   std::vector<cudaEvent_t> prof_events;  // pairs (begin, end)
   size_t prof_used = 0;
@@ -710,6 +713,7 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
     if ((rc = check_launch(plan, "k_enum_big_maxprod_all"))) return rc;
     if (dom) {
       plan->dominant_name = "k_enum_big_maxprod_all";
+      plan->dominant_grid = grid;
       if ((rc = prof_mark(plan, st, plan->dominant))) return rc;
     }
   }
@@ -750,7 +754,7 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       }
 #undef PGX_BIP_LAUNCH
       if ((rc = check_launch(plan, "k_enum_pw2_bip"))) return rc;
-      if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2_bip";
+      if (int(bi) == plan->dominant) { plan->dominant_name = "k_enum_pw2_bip"; plan->dominant_grid = grid; }
     } else if (eb.variant == kPw2) {
       pgx::k_enum_pw2<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
           mp, F, eb.dev.first_edge, eb.dev.first_msg, eb.dev.first_pot, plan->d_edge_vs, lp, S, m_old,
@@ -843,7 +847,10 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
 #undef PGX_LAUNCH_SMALL
 #undef PGX_LAUNCH_SMALL2
         if ((rc = check_launch(plan, "k_logical_pull_small"))) return rc;
-        if (id == plan->dominant) plan->dominant_name = "k_logical_pull_small";
+        if (id == plan->dominant) {
+          plan->dominant_name = "k_logical_pull_small";
+          plan->dominant_grid = staged ? int64_t(sgrid.x) * sgrid.y : int64_t(grid.x) * grid.y;
+        }
       } else {
         const dim3 grid0(unsigned((F + 3) / 4), unsigned(mp.nbt));
         // two launches: serial accumulation per factor, then a parent-parallel emit
@@ -924,27 +931,58 @@ struct DeviceGuard {
 
 // A lattice launch on binary-difference storage: variant (max / sum-product, with / without
 // deltas), persistent grid of one CTA per SM.
-using LbCfgDefault = pgx::LbCfg<4, 256, 3>;
+// Tile shape / ring depth / consumer threads / CTAs per SM of k_lattice_bin.  Measured on Ising 8192^2
+// (ms per iteration, profiles/r02_d_lattice_variants.txt): 4x128 tiles, 2 stages, 8 consumer warps, THREE
+// independent CTAs per SM 0.830; 4x256x3 stages, 16 warps, one CTA 0.871; 6x256x2, 24 warps, one CTA 0.876;
+// 4x128x2, 12 warps x 3 CTAs 0.872; 4x64x3, 8 warps x 4 CTAs 0.939; 2x256x3, 16 warps x 2 CTAs 0.980 - several
+// small pipelines whose phases drift apart hide the barrier / mbarrier waits of one another.
+using LbCfgDefault = pgx::LbCfg<4, 128, 2, 256, 3>;
+using LbCfgV1 = pgx::LbCfg<4, 256, 3, 512, 1>;  // PGX_LB_VARIANT=1 (A/B)
 using LbFn = void (*)(pgx::LatticeBinArgs, const float*, const float*, const float4*, float4*, pgx::RunArgs);
+
+template <class Cfg>
+int launch_lattice_bin_cfg(uint32_t* attr_done, int attr_bit, int num_sms, cudaStream_t st, const pgx::LatticeBinArgs& g,
+                           const float* ev, const float* lp, const float* c_old, float* c_new, const pgx::RunArgs& a,
+                           bool sum_product, bool want_delta) {
+  static const LbFn fns[4] = {pgx::k_lattice_bin<false, false, Cfg>, pgx::k_lattice_bin<false, true, Cfg>,
+                              pgx::k_lattice_bin<true, false, Cfg>, pgx::k_lattice_bin<true, true, Cfg>};
+  if (!((*attr_done >> attr_bit) & 1u)) {
+    *attr_done |= 1u << attr_bit;
+    for (int v = 0; v < 4; ++v)
+      PGX_CUDA(cudaFuncSetAttribute(fns[v], cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::smem_bytes())));
+  }
+  const int tiles_x = (g.N + Cfg::TC - 1) / Cfg::TC;
+  int64_t tiles = 0;
+  for (int s = 0; s < 2; ++s) tiles += int64_t(tiles_x) * std::max(0, (g.seg_end[s] - g.seg_begin[s] + Cfg::TR - 1) / Cfg::TR);
+  if (tiles == 0) return PGX_OK;
+  PGX_CHECK(tiles < (int64_t(1) << 31), "lattice too large for 32-bit tile indices");
+  const unsigned grid = unsigned(std::min<int64_t>(tiles, int64_t(num_sms) * Cfg::kCtasPerSm));
+  fns[(sum_product ? 2 : 0) + (want_delta ? 1 : 0)]<<<grid, Cfg::kThreads, Cfg::smem_bytes(), st>>>(
+      g, ev, lp, reinterpret_cast<const float4*>(c_old), reinterpret_cast<float4*>(c_new), a);
+  return PGX_OK;
+}
 
 int launch_lattice_bin(pgx_plan* plan_or_null, uint32_t* attr_done, int num_sms, cudaStream_t st,
                        const pgx::LatticeBinArgs& g, const float* ev, const float* lp, const float* c_old, float* c_new,
                        const pgx::RunArgs& a, bool sum_product, bool want_delta) {
-  static const LbFn fns[4] = {pgx::k_lattice_bin<false, false, LbCfgDefault>, pgx::k_lattice_bin<false, true, LbCfgDefault>,
-                              pgx::k_lattice_bin<true, false, LbCfgDefault>, pgx::k_lattice_bin<true, true, LbCfgDefault>};
-  if (!((*attr_done >> kAttrLatticeBin) & 1u)) {
-    *attr_done |= 1u << kAttrLatticeBin;
-    for (int v = 0; v < 4; ++v)
-      PGX_CUDA(cudaFuncSetAttribute(fns[v], cudaFuncAttributeMaxDynamicSharedMemorySize, int(LbCfgDefault::smem_bytes())));
+  static const int variant = [] {
+    const char* v = getenv("PGX_LB_VARIANT");
+    return v ? atoi(v) : 0;
+  }();
+  int rc;
+#define PGX_LB_CASE(V, CFG)                                                                                           \
+  case V:                                                                                                             \
+    rc = launch_lattice_bin_cfg<CFG>(attr_done, kAttrLatticeBin + V, num_sms, st, g, ev, lp, c_old, c_new, a, sum_product, \
+                                     want_delta);                                                                     \
+    break
+  switch (variant) {
+    PGX_LB_CASE(1, LbCfgV1);
+    default:
+      rc = launch_lattice_bin_cfg<LbCfgDefault>(attr_done, kAttrLatticeBin, num_sms, st, g, ev, lp, c_old, c_new, a,
+                                                sum_product, want_delta);
   }
-  const int tiles_x = (g.N + LbCfgDefault::TC - 1) / LbCfgDefault::TC;
-  int64_t tiles = 0;
-  for (int s = 0; s < 2; ++s)
-    tiles += int64_t(tiles_x) * std::max(0, (g.seg_end[s] - g.seg_begin[s] + LbCfgDefault::TR - 1) / LbCfgDefault::TR);
-  if (tiles == 0) return PGX_OK;
-  const unsigned grid = unsigned(std::min<int64_t>(tiles, num_sms));
-  fns[(sum_product ? 2 : 0) + (want_delta ? 1 : 0)]<<<grid, pgx::kLbThreads, LbCfgDefault::smem_bytes(), st>>>(
-      g, ev, lp, reinterpret_cast<const float4*>(c_old), reinterpret_cast<float4*>(c_new), a);
+#undef PGX_LB_CASE
+  if (rc) return rc;
   if (plan_or_null) return check_launch(plan_or_null, "k_lattice_bin");
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(PGX_ERR_CUDA, "launch of k_lattice_bin failed: %s", cudaGetErrorString(err));
@@ -996,6 +1034,9 @@ int run_lattice_bin(pgx_plan* plan, cudaStream_t st, const float* log_potentials
   g.up_add = nullptr;
   g.ghost_ev = nullptr;
   plan->dominant_name = "k_lattice_bin";
+  plan->dominant_grid = std::min<int64_t>(int64_t((lat.N + LbCfgDefault::TC - 1) / LbCfgDefault::TC) *
+                                              ((lat.R + LbCfgDefault::TR - 1) / LbCfgDefault::TR),
+                                          int64_t(plan->num_sms) * LbCfgDefault::kCtasPerSm);
   const float* cur = ws.cA;
   float* nxt = ws.cB;
   for (int it = 0; it < num_iters; ++it) {
@@ -1556,6 +1597,7 @@ int pgx_plan_disable_paths(pgx_plan* plan, uint32_t mask) {
 int pgx_plan_is_lattice(const pgx_plan* plan) { return plan && plan->lattice_ok ? 1 : 0; }
 
 int64_t pgx_plan_dominant_edge_states(const pgx_plan* plan) { return plan ? plan->dominant_es : 0; }
+int64_t pgx_plan_dominant_grid(const pgx_plan* plan) { return plan ? plan->dominant_grid : 0; }
 
 int pgx_plan_profile_enable(pgx_plan* plan, int enabled) {
   if (!plan) return fail(PGX_ERR_INVALID, "null plan");
@@ -1817,6 +1859,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
       }
     }
     plan->dominant_name = stream ? "k_lattice_stream" : "k_lattice";
+    plan->dominant_grid = stream ? std::min<int64_t>(num_tiles, plan->num_sms) : int64_t(grid.x) * grid.y;
     for (int it = 0; it < num_iters; ++it) {
       a.delta_off = it;
       float* dst = (it == num_iters - 1) ? ftov_out : nxt;
