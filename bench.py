@@ -39,6 +39,17 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
 
 import numpy as np  # noqa: E402
 
+# stdout carries the ONE JSON line and nothing else: everything other code (NCCL's version banner,
+# library warnings) writes to fd 1 goes to stderr instead.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+  _JSON_OUT.write(json.dumps(line) + "\n")
+  _JSON_OUT.flush()
+
+
 METRIC = "bp_messages_updated_per_sec"
 UNIT = "edge_states/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
@@ -228,7 +239,7 @@ def run_ising_big(args):
                      "storage": "binary-difference, 1 float per two-state edge between iterations"},
         "checksum_max_abs_msg": f["checksum_max_abs_msg"],
     }
-    print(json.dumps(line))
+    emit(line)
   if world > 1:
     dist.destroy_process_group()
 
@@ -376,7 +387,7 @@ def run_reference(args):
       "gpu_launches": 0,
       "note": "NumPy fp32 restatement of the reference's run_bp (oracle/bp_oracle.py); JAX is not installable here",
   }
-  print(json.dumps(line))
+  emit(line)
 
 
 # ----------------------------------------------------------------------------------------
@@ -415,7 +426,7 @@ def oracle_parity(wl, host, dev_run, iters=2, sample=0):
 
 
 def measure(args, name, dev, rank, world, local_rank, batch=None, iters=None, steps=None, warmup=None,
-            shard_seed=None, with_clocks=True, parity_iters=2):
+            shard_seed=None, with_clocks=True, parity_iters=2, min_seconds=0.0):
   """Times one plan-based workload on this rank: device-resident steps (CUDA events), the
   dominant kernel's launches (events around each one, separate pass), the end-to-end leg through
   pgx_infer_host with pinned host buffers, and the oracle spot-check.  Returns this rank's
@@ -449,6 +460,11 @@ def measure(args, name, dev, rank, world, local_rank, batch=None, iters=None, st
   for _ in range(warmup):
     out = bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
   barrier()
+  if min_seconds:  # short workloads: enough steps for >= 3 clock samples (nvidia-smi period 100 ms)
+    t0 = time.perf_counter()
+    bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
+    torch.cuda.synchronize()
+    steps = max(steps, min(2000, int(min_seconds / max(time.perf_counter() - t0, 1e-5)) + 1))
   launches0 = plan.launch_count
   sampler = ClockSampler(local_rank) if with_clocks else None
   if sampler:
@@ -487,13 +503,14 @@ def measure(args, name, dev, rank, world, local_rank, batch=None, iters=None, st
     e2e_step()
   barrier()
   e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e2e_steps = min(steps, 50)
   t0 = time.perf_counter()
   e2.record()
-  for _ in range(steps):
+  for _ in range(e2e_steps):
     e2e_step()
   e3.record()
   barrier()
-  e2e_ms = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
+  e2e_ms = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0)) * steps / e2e_steps  # scaled to `steps`
   parity = None
   if rank == 0 and parity_iters:
     try:
@@ -660,7 +677,7 @@ def main():
 
   # ---- sub-records ---------------------------------------------------------------------------
   if not args.no_extras and args.workload == "rbm" and args.batch is None and args.iters is None:
-    quick = dict(steps=2, warmup=3)
+    quick = dict(steps=2, warmup=3, min_seconds=0.8)
     if world == 1:
       others = {}
       for name in ("ising50", "deconv", "rcn"):
@@ -733,7 +750,7 @@ def main():
       except (IndexError, ValueError, KeyError, subprocess.TimeoutExpired) as err:
         line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
                                 "sample": "failed: " + repr(err)[-300:]}
-    print(json.dumps(line))
+    emit(line)
   if world > 1:
     dist.destroy_process_group()
 

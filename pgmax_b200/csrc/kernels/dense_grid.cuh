@@ -41,13 +41,16 @@ constexpr int kBipTJ = 16;
 constexpr int kBipStages = 3;  // ring depth
 // warps (= sample tiles) per CTA: 8 with compressed input rows (two CTAs of 104 KiB per SM, 16
 // warps: the kernel is issue-latency-bound, not bandwidth-bound, below that), 4 with full rows
-__host__ __device__ constexpr int bip_warps(bool in_full) { return in_full ? 4 : 8; }
+// (kNarrow: 4 warps also with compressed input - batches whose last group of 8 sample tiles would
+// be at most half full, e.g. the 128-sample shards of a batch of 1024 split over 8 GPUs: the idle
+// warps of an 8-warp CTA would still hold half of the SM's shared memory)
+__host__ __device__ constexpr int bip_warps(bool in_full, bool narrow = false) { return (in_full || narrow) ? 4 : 8; }
 
 // dynamic shared memory of k_enum_pw2_bip
-__host__ __device__ constexpr size_t bip_smem_bytes(int RI, int TJ, bool in_full) {
-  return size_t(bip_warps(in_full)) * kBipStages * (in_full ? 4 : 2) * TJ * 32 * sizeof(float)  // rings
-         + size_t(RI) * TJ * 4 * sizeof(float)                                                  // potentials
-         + size_t(bip_warps(in_full)) * kBipStages * sizeof(uint64_t);                          // mbarriers
+__host__ __device__ constexpr size_t bip_smem_bytes(int RI, int TJ, bool in_full, bool narrow = false) {
+  return size_t(bip_warps(in_full, narrow)) * kBipStages * (in_full ? 4 : 2) * TJ * 32 * sizeof(float)  // rings
+         + size_t(RI) * TJ * 4 * sizeof(float)                                                          // potentials
+         + size_t(bip_warps(in_full, narrow)) * kBipStages * sizeof(uint64_t);                          // mbarriers
 }
 
 // Binary-difference storage.  A normalised message of a two-state edge is (n_p, n_r) with
@@ -167,15 +170,15 @@ __device__ __forceinline__ float pw2_update_bin(float xa, float xb, f32x2 Sa, f3
 
 // kInFull: the input rows are in the full tile-blocked layout (first iteration of a run);
 // the output is always compressed.
-template <bool kSumProduct, int TJ, bool kDelta, bool kInFull>
-__global__ void __launch_bounds__(bip_warps(kInFull) * 32)
+template <bool kSumProduct, int TJ, bool kDelta, bool kInFull, bool kNarrow = false>
+__global__ void __launch_bounds__(bip_warps(kInFull, kNarrow) * 32)
 k_enum_pw2_bip(int batch, int nbt_groups, BipDev g, const float* __restrict__ lp,
                const float* __restrict__ S, const float* __restrict__ m_old, int64_t old_rows,
                float* __restrict__ c_new, int64_t c_rows, float* __restrict__ part, int64_t part_rows,
                RunArgs a) {
   constexpr int kIn = kInFull ? 4 : 2;           // floats per factor and sample in the input rows
   constexpr int kStages = kBipStages;
-  constexpr int kBipWarps = bip_warps(kInFull);
+  constexpr int kBipWarps = bip_warps(kInFull, kNarrow);
   constexpr int kRowFloats = TJ * kIn * 32;      // one input row of a strip for one sample tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* ring = reinterpret_cast<float*>(smem_raw);

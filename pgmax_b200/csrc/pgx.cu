@@ -730,27 +730,35 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       constexpr int TJ = pgx::kBipTJ;
       // c_old == nullptr: first iteration of a run, the input rows are in the full layout
       const bool in_full = c_old == nullptr;
-      const int warps = pgx::bip_warps(in_full);
+      // 4-warp CTAs when the last group of 8 sample tiles would be at most half full and the batch is
+      // small enough for that to matter (strong-scaled shards: 128 samples = 4 tiles)
+      const bool narrow = !in_full && mp.nbt <= 12 && ((mp.nbt + 7) / 8) * 8 - mp.nbt >= 4;
+      const int warps = pgx::bip_warps(in_full, narrow);
       const int groups = (mp.nbt + warps - 1) / warps;
       const int64_t grid = int64_t(g.NS) * g.NR * groups;
-      const size_t smem = pgx::bip_smem_bytes(g.RI, TJ, in_full);
+      const size_t smem = pgx::bip_smem_bytes(g.RI, TJ, in_full, narrow);
       if (attr_needed(kSum ? kAttrBipSum : kAttrBipMax)) {
-#define PGX_BIP_ATTR(DELTA, FULL)                                                                          \
-  PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pw2_bip<kSum, TJ, DELTA, FULL>,                                 \
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, int(pgx::bip_smem_bytes(32, TJ, FULL))))
-        PGX_BIP_ATTR(true, true); PGX_BIP_ATTR(true, false); PGX_BIP_ATTR(false, true); PGX_BIP_ATTR(false, false);
+#define PGX_BIP_ATTR(DELTA, FULL, NARROW)                                                                   \
+  PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pw2_bip<kSum, TJ, DELTA, FULL, NARROW>,                          \
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, int(pgx::bip_smem_bytes(32, TJ, FULL, NARROW))))
+        PGX_BIP_ATTR(true, true, false); PGX_BIP_ATTR(true, false, false); PGX_BIP_ATTR(false, true, false);
+        PGX_BIP_ATTR(false, false, false); PGX_BIP_ATTR(true, false, true); PGX_BIP_ATTR(false, false, true);
 #undef PGX_BIP_ATTR
       }
       const float* src = in_full ? m_old : c_old;
       const int64_t src_rows = in_full ? a.Es : plan->c_rows;
-#define PGX_BIP_LAUNCH(DELTA, FULL)                                                                       \
-  pgx::k_enum_pw2_bip<kSum, TJ, DELTA, FULL><<<unsigned(grid), warps * 32, smem, st>>>(                    \
+#define PGX_BIP_LAUNCH(DELTA, FULL, NARROW)                                                                 \
+  pgx::k_enum_pw2_bip<kSum, TJ, DELTA, FULL, NARROW><<<unsigned(grid), warps * 32, smem, st>>>(              \
       mp.batch, groups, g, lp.p, S, src, src_rows, c_new, plan->c_rows,                                    \
       part_override ? part_override : plan->ws.part, plan->part_rows, a)
       if (a.deltas != nullptr) {
-        if (in_full) PGX_BIP_LAUNCH(true, true); else PGX_BIP_LAUNCH(true, false);
+        if (in_full) PGX_BIP_LAUNCH(true, true, false);
+        else if (narrow) PGX_BIP_LAUNCH(true, false, true);
+        else PGX_BIP_LAUNCH(true, false, false);
       } else {
-        if (in_full) PGX_BIP_LAUNCH(false, true); else PGX_BIP_LAUNCH(false, false);
+        if (in_full) PGX_BIP_LAUNCH(false, true, false);
+        else if (narrow) PGX_BIP_LAUNCH(false, false, true);
+        else PGX_BIP_LAUNCH(false, false, false);
       }
 #undef PGX_BIP_LAUNCH
       if ((rc = check_launch(plan, "k_enum_pw2_bip"))) return rc;

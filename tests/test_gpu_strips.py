@@ -119,7 +119,9 @@ def _native_worker(rank, world, port, n, temperature, iters, out):
     whole, ev_all = single.run(evidence.reshape(-1), iters, 0.5, temperature)
     whole_b = single.beliefs(ev_all, whole).cpu().numpy()
     lo, hi = runner.global_msg_range
-    out[rank] = (float(np.max(np.abs(got - whole.cpu().numpy()[lo:hi]))), same,
+    want = whole.cpu().numpy()[lo:hi]
+    # messages reach |m| ~ 10 (one fp32 ulp = 9.5e-7): the error is measured relative to max(1, |m|)
+    out[rank] = (float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want)))), same,
                  float(np.max(np.abs(beliefs - whole_b[lo // 4 : hi // 4]))))
   finally:
     dist.destroy_process_group()
