@@ -145,6 +145,7 @@ def strip_record(args, dev, rank, world, n, iters, steps, warmup, sampler_index=
   sampler = ClockSampler(sampler_index) if sampler_index is not None else None
   if sampler:
     sampler.start()
+    sampler.wait_first()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   barrier()
   e0.record()
@@ -271,7 +272,16 @@ class ClockSampler:
   def __init__(self, index: int):
     self.index, self.proc, self.lines = index, None, []
 
+  def wait_first(self, timeout=2.0):
+    """Blocks until nvidia-smi has delivered its first sample (its start-up takes a few hundred
+    ms), then marks the start of the timed region: stop() reports the samples after the mark."""
+    deadline = time.time() + timeout
+    while self.proc is not None and not self.lines and time.time() < deadline:
+      time.sleep(0.01)
+    self.mark = len(self.lines)
+
   def start(self):
+    self.mark = 0
     try:
       self.proc = subprocess.Popen(
           ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
@@ -298,7 +308,8 @@ class ClockSampler:
     self.thread.join(timeout=2)
     sm, mx, reasons = [], [], set()
     names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for line in self.lines:
+    lines = self.lines[self.mark:] if len(self.lines) > self.mark else self.lines[-1:]
+    for line in lines:
       parts = [p.strip() for p in line.split(",")]
       if len(parts) < 6:
         continue
@@ -469,6 +480,7 @@ def measure(args, name, dev, rank, world, local_rank, batch=None, iters=None, st
   sampler = ClockSampler(local_rank) if with_clocks else None
   if sampler:
     sampler.start()
+    sampler.wait_first()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   barrier()
   e0.record()
