@@ -93,6 +93,23 @@ def build_workload(name: str, batch_override=None, iters_override=None):
     bp = infer.BP(fg.bp_state, temperature=temperature)
     evidence = {variables: ev.astype(np.float32)}
     label = "Ising 50x50 torus, pairwise EnumFactors, T=0.05"
+  elif name == "ising50_batch":
+    # a NON-special-cased pairwise graph: the same torus at batch 1024 (no lattice / resident path:
+    # those are one-sample paths) - generic variable-sum + pairwise kernels, sum-product
+    batch, iters, temperature = batch_override or 1024, 200, 1.0
+    fg, variables, ev = models.ising_model(n=50, batch=batch)
+    bp = infer.BP(fg.bp_state, temperature=temperature)
+    evidence = {variables: ev.astype(np.float32)}
+    label = "Ising 50x50 torus batched (generic pairwise path), sum-product T=1"
+  elif name == "heretic":
+    # tests/test_pgmax.py:424-475: 17-state x 3-state pairwise EnumFactors (multi-state enum kernel)
+    batch, iters, temperature = batch_override or 256, 100, 1.0
+    fg, pixel_vars, hidden_vars = models.heretic_model()
+    bp = infer.BP(fg.bp_state, temperature=temperature)
+    rng = np.random.default_rng(0)
+    evidence = {pixel_vars: rng.gumbel(size=(batch, 30, 30, 3)).astype(np.float32),
+                hidden_vars: rng.gumbel(size=(batch, 28, 28, 17)).astype(np.float32)}
+    label = "'heretic' model: 7 056 pairwise EnumFactors of 17 x 3 states (generic enum path), sum-product T=1"
   elif name == "deconv":
     # examples/pmp_binary_deconvolution.ipynb shape: one 28x28 image per graph, 5 features 6x6,
     # 100 synthetic images batched, max-product, 100 iterations
@@ -468,15 +485,21 @@ def measure(args, name, dev, rank, world, local_rank, batch=None, iters=None, st
       dist.barrier()
     torch.cuda.synchronize()
 
-  for _ in range(warmup):
+  plan.enable_graphs(not args.no_graph)
+  # (the previous result is dropped before every run: the allocator then hands the same output
+  # buffer back, the call signature repeats and the run is one CUDA graph replay)
+  out = None
+  for _ in range(max(warmup, 3)):
+    out = None
     out = bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
   barrier()
   if min_seconds:  # short workloads: enough steps for >= 3 clock samples (nvidia-smi period 100 ms)
     t0 = time.perf_counter()
-    bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
+    out = None
+    out = bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
     torch.cuda.synchronize()
     steps = max(steps, min(2000, int(min_seconds / max(time.perf_counter() - t0, 1e-5)) + 1))
-  launches0 = plan.launch_count
+  launches0, graphs0 = plan.launch_count, plan.graph_launch_count
   sampler = ClockSampler(local_rank) if with_clocks else None
   if sampler:
     sampler.start()
@@ -485,12 +508,13 @@ def measure(args, name, dev, rank, world, local_rank, batch=None, iters=None, st
   barrier()
   e0.record()
   for _ in range(steps):
+    out = None
     out = bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
   e1.record()
   barrier()
   ms = e0.elapsed_time(e1)
   clocks = sampler.stop() if sampler else None
-  launches = plan.launch_count - launches0
+  launches, graph_launches = plan.launch_count - launches0, plan.graph_launch_count - graphs0
   # roofline pass: the same step once more with CUDA events around every launch of the dominant
   # kernel (kept out of the timed region above)
   plan.profile_enable(True)
@@ -532,7 +556,7 @@ def measure(args, name, dev, rank, world, local_rank, batch=None, iters=None, st
       parity = {"parity_max_abs": None, "parity_note": "check failed: " + repr(err)[-200:]}
   lp_batched = host.log_potentials.ndim == 2
   fused_run = plan.has_fused_blocks and not args.exact_order and batch > 16 and not lp_batched
-  return dict(wl=wl, plan=plan, ms=ms, e2e_ms=e2e_ms, launches=launches, clocks=clocks, n_prof=n_prof, prof_ms=prof_ms,
+  return dict(wl=wl, plan=plan, ms=ms, e2e_ms=e2e_ms, launches=launches, graph_launches=graph_launches, clocks=clocks, n_prof=n_prof, prof_ms=prof_ms,
               prof_name=prof_name, checksum=checksum, batch=batch, iters=iters, es=es, steps=steps, warmup=warmup,
               h2d=4 * (h_lp.numel() + h_ev.numel()), d2h=4 * (h_map.numel() + h_ties.numel()), parity=parity,
               lp_batched=lp_batched, fused_run=fused_run, damping=damping, temperature=T)
@@ -596,6 +620,7 @@ def compact_record(name, rec, world=1):
       "workload": rec["wl"]["label"], "batch": rec["batch"], "iters": rec["iters"], "temperature": rec["temperature"],
       "value": msgs / (rec["ms"] * 1e-3), "unit": UNIT, "ms_per_step": rec["ms"] / rec["steps"], "iter_ms": r["iter_ms"],
       "e2e_value": msgs / (rec["e2e_ms"] * 1e-3), "gpu_launches": rec["launches"],
+      "graph_launches": rec["graph_launches"], "steps": rec["steps"],
       "kernel": r["kernel"], "kernel_ms": r["kernel_ms"], "frac": r["frac"], "iter_frac": r["iter_frac"],
       "layout_frac": r["layout_frac"], "layout_iter_frac": r["layout_iter_frac"], "physical_frac": r["physical_frac"],
       "traffic": r["traffic"], "storage": r["storage"], "clocks": rec["clocks"], "checksum_max_abs_msg": rec["checksum"],
@@ -618,6 +643,8 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-extras", action="store_true",
                   help="skip the sub-records (other_workloads at N = 1; rbm_strong and strips at N > 1)")
+  ap.add_argument("--no-graph", action="store_true",
+                  help="enqueue every launch directly instead of replaying one CUDA graph per run (A/B)")
   ap.add_argument("--strip-flags", type=int, default=0, help="PGX_STRIP_* flags (A/B: 1 no graph, 2 no overlap)")
   ap.add_argument("--disable-paths", type=int, default=0, help="PGX_PATH_* mask (A/B runs of launch paths)")
   ap.add_argument("--exact-order", action="store_true",
@@ -675,6 +702,7 @@ def main():
                 "h2d_bytes_per_step": rec["h2d"], "d2h_bytes_per_step": rec["d2h"],
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": rec["launches"],
+        "graph_launches": rec["graph_launches"],
         "clocks": rec["clocks"],
         "roofline": roofline_of(args.workload, rec, ms),
         "checksum_max_abs_msg": rec["checksum"],
@@ -692,9 +720,9 @@ def main():
     quick = dict(steps=2, warmup=3, min_seconds=0.8)
     if world == 1:
       others = {}
-      for name in ("ising50", "deconv", "rcn"):
+      for name in ("ising50", "deconv", "rcn", "ising50_batch", "heretic"):
         try:
-          r = measure(args, name, dev, rank, world, local_rank, parity_iters=2 if name != "rcn" else 0, **quick)
+          r = measure(args, name, dev, rank, world, local_rank, parity_iters=0 if name == "rcn" else 2, **quick)
           others[name] = compact_record(name, r)
           del r
         except Exception as err:  # pylint: disable=broad-except

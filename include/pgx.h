@@ -141,6 +141,14 @@ int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch,
  * place with no staging copy.  This is the step function of callers that must
  * touch the evidence between iterations (multi-GPU halo exchange, dist.py). */
 #define PGX_RUN_INPUT_NORMALIZED 1u
+/* One launch per run (the reference's loop is one device-side lax.scan, bp.py:142-146): the
+ * SECOND call with the same signature - buffers, batch, iteration count, damping, temperature,
+ * flags, path mask - captures the launch sequence of all iterations in a CUDA graph, and that
+ * call and every later one with the signature is a single cudaGraphLaunch on `stream`.  (The
+ * first call runs directly: it sizes the workspace, and a signature that never repeats never pays
+ * for a capture.)  Skipped when `stream` is itself being captured (the caller's graph then holds
+ * the launches), under pgx_plan_profile_enable, with PGX_GRAPH=0 in the environment, or with: */
+#define PGX_RUN_NO_GRAPH 2u
 int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch,
                      const float* log_potentials, int lp_batched,
                      const float* evidence, int ev_batched,
@@ -283,6 +291,9 @@ int64_t pgx_plan_compressed_edges(const pgx_plan* plan);
 int pgx_plan_disable_paths(pgx_plan* plan, uint32_t mask);
 /* 1 if the lattice path is available for this plan. */
 int pgx_plan_is_lattice(const pgx_plan* plan);
+/* CUDA-graph replay of repeated runs (see PGX_RUN_NO_GRAPH): on by default. */
+int pgx_plan_enable_graphs(pgx_plan* plan, int enabled);
+int64_t pgx_plan_graph_launch_count(const pgx_plan* plan); /* cudaGraphLaunch calls so far */
 
 /* Device-time instrumentation for the roofline figure (bench.py).  While
  * enabled, pgx_bp_run brackets, in every iteration, the launch of the plan's

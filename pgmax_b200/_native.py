@@ -44,6 +44,8 @@ EXPORTED_SYMBOLS = (
     "pgx_plan_compressed_edges",
     "pgx_plan_disable_paths",
     "pgx_plan_is_lattice",
+    "pgx_plan_enable_graphs",
+    "pgx_plan_graph_launch_count",
     "pgx_plan_dominant_edge_states",
     "pgx_plan_dominant_grid",
     "pgx_plan_profile_enable",
@@ -191,6 +193,10 @@ def load() -> ctypes.CDLL:
   lib.pgx_plan_disable_paths.restype = ctypes.c_int
   lib.pgx_plan_is_lattice.argtypes = [vp]
   lib.pgx_plan_is_lattice.restype = ctypes.c_int
+  lib.pgx_plan_enable_graphs.argtypes = [vp, ctypes.c_int]
+  lib.pgx_plan_enable_graphs.restype = ctypes.c_int
+  lib.pgx_plan_graph_launch_count.argtypes = [vp]
+  lib.pgx_plan_graph_launch_count.restype = ctypes.c_int64
   lib.pgx_plan_dominant_edge_states.argtypes = [vp]
   lib.pgx_plan_dominant_edge_states.restype = ctypes.c_int64
   lib.pgx_plan_dominant_grid.argtypes = [vp]
@@ -432,6 +438,14 @@ class Plan:
   @property
   def is_lattice(self) -> bool:
     return bool(self._lib.pgx_plan_is_lattice(self.handle))
+
+  def enable_graphs(self, enabled: bool) -> None:
+    """CUDA-graph replay of repeated pgx_bp_run signatures (on by default)."""
+    check(self._lib.pgx_plan_enable_graphs(self.handle, int(enabled)))
+
+  @property
+  def graph_launch_count(self) -> int:
+    return int(self._lib.pgx_plan_graph_launch_count(self.handle))
 
   def set_exact_order(self, enabled: bool) -> None:
     """Force the two-pass, serial-summation-order path (see pgx_plan_set_exact_order)."""

@@ -256,6 +256,25 @@ struct pgx_plan {
   const char* dominant_name = "";
   std::vector<cudaEvent_t> prof_events;  // pairs (begin, end)
   size_t prof_used = 0;
+  // One CUDA graph per repeated call signature of pgx_bp_run (pgx_bp_run_flags): the launch
+  // sequence of all iterations is captured the SECOND time the same (buffers, batch, iteration
+  // count, scalars, path mask) is seen and replayed with one cudaGraphLaunch from then on.
+  struct RunGraph {
+    const void *lp, *ev, *in, *out, *deltas;
+    int64_t batch;
+    int32_t iters, lp_b, ev_b, in_b;
+    float damping, temperature;
+    uint32_t flags, paths;
+    bool exact;
+    cudaGraphExec_t exec;  // null: seen once, not captured yet
+    int64_t launches;      // kernels + copies one replay runs
+    int64_t epoch;         // workspace generation the graph's internal pointers belong to
+  };
+  int64_t ws_epoch = 0;    // bumped whenever a workspace buffer is (re)allocated: cached graphs go stale
+  std::vector<RunGraph> run_graphs;
+  cudaStream_t cap_stream = nullptr;
+  int64_t graph_launches = 0;
+  bool graphs_enabled = true;
 };
 
 namespace {
@@ -577,6 +596,7 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
     free_dev(ws.agg); free_dev(ws.cA); free_dev(ws.cB); free_dev(ws.row);
     ws.mA = ws.mB = ws.S = ws.evT = ws.lpT = ws.part = ws.agg = ws.cA = ws.cB = ws.row = nullptr;
     ws.batch = -1;  // valid only once every allocation below has succeeded (a failed call is retried in full)
+    ++plan->ws_epoch;
     const size_t nm = tiled_floats(mp, plan->num_edge_states) * sizeof(float);
     const size_t nv = tiled_floats(mp, plan->num_var_states) * sizeof(float);
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.mA), nm));
@@ -589,13 +609,16 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
     int64_t wide = 0;  // factors of the groups that take the two-launch wide update
     for (const LogicalPlan* lg : {&plan->or_f, &plan->and_f})
       if (lg->max_parents > pgx::kRegParents) wide = std::max<int64_t>(wide, lg->dev.num_factors);
-    if (wide > 0)
+    if (wide > 0) {
       PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.agg), size_t(wide) * pgx::kAggRows * 32 * mp.nbt * sizeof(float)));
+      ++plan->ws_epoch;
+    }
   }
   // lazily allocated buffers: each guarded by its own pointer (a failed allocation leaves the rest retryable)
-  auto lazy = [](float** p, size_t bytes) -> int {
+  auto lazy = [plan](float** p, size_t bytes) -> int {
     if (*p != nullptr) return PGX_OK;
     PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(p), bytes));
+    ++plan->ws_epoch;
     return PGX_OK;
   };
   int rc;
@@ -610,10 +633,8 @@ int ensure_workspace(pgx_plan* plan, int64_t batch, bool need_evT, bool need_lpT
     if ((rc = lazy(&ws.cA, nc))) return rc;
     if ((rc = lazy(&ws.cB, nc))) return rc;
   }
-  if (need_evT && ws.evT == nullptr)
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.evT), tiled_floats(mp, plan->num_var_states) * sizeof(float)));
-  if (need_lpT && ws.lpT == nullptr)
-    PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.lpT), tiled_floats(mp, plan->num_potentials) * sizeof(float)));
+  if (need_evT && (rc = lazy(&ws.evT, tiled_floats(mp, plan->num_var_states) * sizeof(float)))) return rc;
+  if (need_lpT && (rc = lazy(&ws.lpT, tiled_floats(mp, plan->num_potentials) * sizeof(float)))) return rc;
   return PGX_OK;
 }
 
@@ -1566,6 +1587,9 @@ void pgx_plan_destroy(pgx_plan* plan) {
   free_dev(plan->sdlp.eta); free_dev(plan->sdlp.P); free_dev(plan->sdlp.vval); free_dev(plan->sdlp.eval);
   free_dev(plan->sdlp.grad); free_dev(plan->sdlp.partial);
   for (cudaEvent_t e : plan->prof_events) cudaEventDestroy(e);
+  for (pgx_plan::RunGraph& g : plan->run_graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (plan->cap_stream) cudaStreamDestroy(plan->cap_stream);
   delete plan;
 }
 
@@ -1604,6 +1628,14 @@ int pgx_plan_disable_paths(pgx_plan* plan, uint32_t mask) {
 
 int pgx_plan_is_lattice(const pgx_plan* plan) { return plan && plan->lattice_ok ? 1 : 0; }
 
+int pgx_plan_enable_graphs(pgx_plan* plan, int enabled) {
+  if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+  plan->graphs_enabled = enabled != 0;
+  return PGX_OK;
+}
+
+int64_t pgx_plan_graph_launch_count(const pgx_plan* plan) { return plan ? plan->graph_launches : 0; }
+
 int64_t pgx_plan_dominant_edge_states(const pgx_plan* plan) { return plan ? plan->dominant_es : 0; }
 int64_t pgx_plan_dominant_grid(const pgx_plan* plan) { return plan ? plan->dominant_grid : 0; }
 
@@ -1638,11 +1670,98 @@ int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch, const float* log_pot
                           msgs_batched, ftov_out, deltas, num_iters, damping, temperature, 0);
 }
 
+static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const float* log_potentials, int lp_batched,
+                          const float* evidence, int ev_batched, const float* ftov_in, int msgs_batched,
+                          float* ftov_out, float* deltas, int32_t num_iters, float damping, float temperature,
+                          uint32_t flags);
+
 int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* log_potentials, int lp_batched,
                      const float* evidence, int ev_batched, const float* ftov_in, int msgs_batched,
                      float* ftov_out, float* deltas, int32_t num_iters, float damping, float temperature,
                      uint32_t flags) {
   if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  static const bool env_off = [] {
+    const char* v = getenv("PGX_GRAPH");
+    return v != nullptr && v[0] == '0';
+  }();
+  const bool eligible = plan->graphs_enabled && !env_off && !plan->profiling && !(flags & PGX_RUN_NO_GRAPH) && num_iters >= 2 &&
+                        plan->num_edge_states > 0 && cudaStreamIsCapturing(st, &capturing) == cudaSuccess &&
+                        capturing == cudaStreamCaptureStatusNone;
+  if (!eligible)
+    return bp_run_enqueue(plan, stream, batch, log_potentials, lp_batched, evidence, ev_batched, ftov_in, msgs_batched,
+                          ftov_out, deltas, num_iters, damping, temperature, flags);
+  int rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(plan))) return rc;
+  const auto epoch_now = [plan] { return plan->ws_epoch + (plan->tail ? plan->tail->ws_epoch : 0); };
+  pgx_plan::RunGraph* hit = nullptr;
+  for (pgx_plan::RunGraph& g : plan->run_graphs)
+    if (g.lp == log_potentials && g.ev == evidence && g.in == ftov_in && g.out == ftov_out && g.deltas == deltas &&
+        g.batch == batch && g.iters == num_iters && g.lp_b == lp_batched && g.ev_b == ev_batched && g.in_b == msgs_batched &&
+        g.damping == damping && g.temperature == temperature && g.flags == flags && g.paths == plan->disabled_paths &&
+        g.exact == plan->exact_order)
+      hit = &g;
+  if (hit == nullptr) {
+    // first sight: run directly (this also sizes the workspace) and remember the signature
+    if (plan->run_graphs.size() >= 16) {
+      if (plan->run_graphs.front().exec) cudaGraphExecDestroy(plan->run_graphs.front().exec);
+      plan->run_graphs.erase(plan->run_graphs.begin());
+    }
+    plan->run_graphs.push_back(pgx_plan::RunGraph{log_potentials, evidence, ftov_in, ftov_out, deltas, batch, num_iters,
+                                                  lp_batched, ev_batched, msgs_batched, damping, temperature, flags,
+                                                  plan->disabled_paths, plan->exact_order, nullptr, 0, 0});
+    return bp_run_enqueue(plan, stream, batch, log_potentials, lp_batched, evidence, ev_batched, ftov_in, msgs_batched,
+                          ftov_out, deltas, num_iters, damping, temperature, flags);
+  }
+  if (hit->exec != nullptr && hit->epoch != epoch_now()) {  // the workspace moved since the capture
+    cudaGraphExecDestroy(hit->exec);
+    hit->exec = nullptr;
+  }
+  if (hit->exec == nullptr) {
+    if (plan->cap_stream == nullptr) PGX_CUDA(cudaStreamCreateWithFlags(&plan->cap_stream, cudaStreamNonBlocking));
+    const int64_t own0 = plan->launches, tail0 = plan->tail ? plan->tail->launches : 0;
+    PGX_CUDA(cudaStreamBeginCapture(plan->cap_stream, cudaStreamCaptureModeRelaxed));
+    rc = bp_run_enqueue(plan, plan->cap_stream, batch, log_potentials, lp_batched, evidence, ev_batched, ftov_in,
+                        msgs_batched, ftov_out, deltas, num_iters, damping, temperature, flags);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t err = cudaStreamEndCapture(plan->cap_stream, &graph);
+    const int64_t captured = (plan->launches - own0) + (plan->tail ? plan->tail->launches - tail0 : 0);
+    plan->launches = own0;  // nothing ran yet: a replay adds `captured` to this plan's counter
+    if (plan->tail) plan->tail->launches = tail0;
+    if (rc != PGX_OK || err != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      // not capturable here: this signature stays on the direct path
+      hit->flags |= 0x80000000u;  // never matches again
+      if (rc != PGX_OK) return rc;
+      return bp_run_enqueue(plan, stream, batch, log_potentials, lp_batched, evidence, ev_batched, ftov_in, msgs_batched,
+                            ftov_out, deltas, num_iters, damping, temperature, flags);
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ierr = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ierr != cudaSuccess) {
+      cudaGetLastError();
+      hit->flags |= 0x80000000u;
+      return bp_run_enqueue(plan, stream, batch, log_potentials, lp_batched, evidence, ev_batched, ftov_in, msgs_batched,
+                            ftov_out, deltas, num_iters, damping, temperature, flags);
+    }
+    hit->exec = exec;
+    hit->launches = captured;
+    hit->epoch = epoch_now();
+  }
+  PGX_CUDA(cudaGraphLaunch(hit->exec, st));
+  plan->launches += hit->launches;
+  ++plan->graph_launches;
+  return PGX_OK;
+}
+
+static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const float* log_potentials, int lp_batched,
+                          const float* evidence, int ev_batched, const float* ftov_in, int msgs_batched,
+                          float* ftov_out, float* deltas, int32_t num_iters, float damping, float temperature,
+                          uint32_t flags) {
   PGX_CHECK(batch >= 1 && batch < (1 << 24), "batch must be in [1, 2^24), got %lld", (long long)batch);
   PGX_CHECK(num_iters >= 1, "num_iters must be >= 1, got %d", num_iters);
   PGX_CHECK(temperature >= 0.f, "temperature must be >= 0");
@@ -1987,7 +2106,10 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
   plan->bigmax_perm_active = false;
   if (temperature == 0.f && plan->bigmax_units > 0 && !(plan->disabled_paths & (PGX_PATH_MERGED_MAX | PGX_PATH_PERM_POTENTIALS)) &&
       !pull && !lattice && lp.kind == 0 && num_iters >= 3 && plan->bigmax_perm_floats > 0) {
-    if (ws.lpR == nullptr) PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.lpR), size_t(plan->bigmax_perm_floats) * sizeof(float)));
+    if (ws.lpR == nullptr) {
+      PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.lpR), size_t(plan->bigmax_perm_floats) * sizeof(float)));
+      ++plan->ws_epoch;
+    }
     const dim3 grid(8, unsigned(std::min<int64_t>(plan->bigmax_units, 65535)));
     pgx::k_bigmax_permute<true><<<grid, pgx::kThreads, 0, st>>>(mp, plan->d_bigmax_groups, plan->d_bigmax_units,
                                                               plan->bigmax_units, lp, ws.lpR);

@@ -152,6 +152,25 @@ def rbm_model(W, bh, bv):
   return fg, hidden, visible
 
 
+def heretic_model(seed: int = 0):
+  """The reference's e2e "heretic" model (tests/test_pgmax.py:424-475): 28 x 28 hidden variables
+  of 17 states, 30 x 30 pixel variables of 3 states, 9 PairwiseFactorGroups (one per offset of a
+  3 x 3 window) with a shared 17 x 3 potential matrix each: 7 056 factors of 20 edge-states.
+  Returns (fg, pixel_vars, hidden_vars)."""
+  im_size = (30, 30)
+  pixel_vars = vgroup.NDVarArray(shape=im_size, num_states=3)
+  hidden_vars = vgroup.NDVarArray(shape=(im_size[0] - 2, im_size[1] - 2), num_states=17)
+  fg = fgraph.FactorGraph([pixel_vars, hidden_vars])
+  w_pot = np.random.RandomState(seed).normal(size=(17, 3, 3, 3))
+  for k_row in range(3):
+    for k_col in range(3):
+      fg.add_factors(fgroup.PairwiseFactorGroup(
+          variables_for_factors=[[hidden_vars[r, c], pixel_vars[r + k_row, c + k_col]]
+                                 for r in range(28) for c in range(28)],
+          log_potential_matrix=w_pot[:, :, k_row, k_col]))
+  return fg, pixel_vars, hidden_vars
+
+
 def rbm_energy(hidden, visible, W, bh, bv):
   """Energy of an RBM configuration (benchmark/rbm_lib.py calc_energies)."""
   return -(hidden @ bh) - (visible @ bv) - hidden @ W @ visible
