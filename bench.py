@@ -571,7 +571,8 @@ def roofline_of(name, rec, ms):
   kernel_ms = rec["prof_ms"] / max(n_prof, 1)
   # the dominant launch updates dom_es of the es edge-states: its share of the iteration's
   # algorithmic bytes (single-kernel iterations: all of them)
-  single_kernel = prof_name in ("k_enum_pw2_bip", "k_lattice", "k_lattice_stream", "k_lattice_bin", "k_enum_pw2_pull")
+  single_kernel = prof_name in ("k_enum_pw2_bip", "k_lattice", "k_lattice_stream", "k_lattice_bin", "k_enum_pw2_pull",
+                                "k_or_and_fused")
   dom_es = es if single_kernel else min(plan.dominant_edge_states, es)
   kernel_bytes = bytes_iter * dom_es // es
   achieved = kernel_bytes / (kernel_ms * 1e-3) / 1e9 if n_prof else None

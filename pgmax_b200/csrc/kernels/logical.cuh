@@ -821,6 +821,188 @@ k_logical_wide_emit_staged(int batch, LogicalPullDev w, const int32_t* __restric
 }
 
 // ---------------------------------------------------------------------------
+// K4-fused: OR factors whose every parent is the degree-2 child of exactly one two-parent AND
+// factor (the deconvolution model of examples/pmp_binary_deconvolution.ipynb: X = OR_i(S_i AND
+// W_i); every SW variable sits between one AND factor and one OR factor).  The AND update of
+// SW_i and the OR update both need the SAME rows - the two messages into SW_i and its evidence -
+// so ONE kernel does both per OR factor and sample tile, and every row is read once:
+//
+//   phase A (all warps, parent-parallel): per parent i load the two messages of SW_i, its
+//            evidence, the two messages and variable sums of the AND factor's parents; finish
+//            the AND factor (three stores); park SW_i's variable -> OR-factor messages
+//            (a_i, b_i) in shared memory;
+//   phase B (warp 0): the OR factor's sums and top-2 differences in ASCENDING parent order from
+//            shared memory (the serial order of the reference's segment sums, ~12 instructions
+//            per parent and no memory latency), the child's message;
+//   phase C (all warps): the OR factor's messages to its parents.
+//
+// Same helpers (edge_q / LogicalAcc / store_edge) and the same operations in the same order as
+// k_logical_pull_small + k_logical_wide_reduce / _emit: bit-identical (tested); the edge kinds are
+// compile-time constants here (no selects), nothing is gathered twice, one launch replaces four
+// and the second stream.  Binary-difference storage, full sample tiles.  The pairing is found at
+// plan time (pgx.cu); graphs that do not have it keep the separate kernels.
+// ---------------------------------------------------------------------------
+struct FusedW {
+  int32_t mO, mA;      // rows (edge indices) of the OR-parent edge and of the AND-child edge of SW_i
+  int32_t ev0;         // var-state of SW_i's state 0
+  int32_t ms, mw;      // rows of the AND factor's two parent edges
+  int32_t Ss0, Sw0;    // var-states (state 0) of those parents: their sums come from S
+  int32_t f_and;       // the AND factor (its parents have the global parent indices 2 f, 2 f + 1)
+};
+
+struct OrAndFusedDev {
+  int64_t num_or;
+  const int32_t* parent_ptr;  // [num_or + 1]
+  const FusedW* w;            // [P], OR parent order
+  const EdgeW* or_children;   // [num_or]
+  int32_t max_parents;
+};
+
+constexpr int kFusedWarps = 8;
+__host__ __device__ constexpr size_t orand_fused_smem(int max_parents) {
+  return (size_t(max_parents) * 2 + 8) * 32 * sizeof(float);
+}
+
+template <bool kSumProduct, bool kDelta>
+__global__ void __launch_bounds__(kFusedWarps * 32)
+k_or_and_fused(int batch, OrAndFusedDev g, View ev, const float* __restrict__ S, const float* __restrict__ m_old,
+               float* __restrict__ m_new, RunArgs a) {
+  extern __shared__ float fz[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y * 32 + lane;
+  const size_t tile = blockIdx.y;
+  // lanes beyond the batch stay alive for the barriers: they work on the (allocated, padded)
+  // sample slots of the last tile and publish no delta
+  const float* mo = m_old + tile * (size_t(a.Es) >> 1) * 32 + lane;
+  float* mn = m_new + tile * (size_t(a.Es) >> 1) * 32 + lane;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + lane;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + lane : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
+  const int64_t gf = blockIdx.x;
+  const int p0 = g.parent_ptr[gf], p1 = g.parent_ptr[gf + 1];
+  float* stash = fz + lane;                              // [parent][2][32]
+  float* agg = fz + size_t(g.max_parents) * 64 + lane;   // [8][32]
+  float dmax = 0.f;
+  constexpr int U = 2;
+
+  // ---- phase A ---------------------------------------------------------------------------------
+  for (int i0 = p0 + warp; i0 < p1; i0 += kFusedWarps * U) {
+    FusedW w[U];
+    float xO[U], xA[U], e0[U], e1[U], xs[U], xw[U], Ss0[U], Ss1[U], Sw0[U], Sw1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * kFusedWarps;
+      if (i < p1) {
+        const int4* src = reinterpret_cast<const int4*>(g.w + i);
+        const int4 lo = src[0], hi = src[1];
+        w[u] = FusedW{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i0 + u * kFusedWarps < p1) {
+        xO[u] = mo[uint32_t(w[u].mO) << 5];
+        xA[u] = mo[uint32_t(w[u].mA) << 5];
+        e0[u] = evq[uint32_t(w[u].ev0) << esh];
+        e1[u] = evq[uint32_t(w[u].ev0 + 1) << esh];
+        xs[u] = mo[uint32_t(w[u].ms) << 5];
+        xw[u] = mo[uint32_t(w[u].mw) << 5];
+        Ss0[u] = SL[uint32_t(w[u].Ss0) << 5];
+        Ss1[u] = SL[uint32_t(w[u].Ss0 + 1) << 5];
+        Sw0[u] = SL[uint32_t(w[u].Sw0) << 5];
+        Sw1[u] = SL[uint32_t(w[u].Sw0 + 1) << 5];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * kFusedWarps;
+      if (i < p1) {
+        // SW_i as parent of the OR factor (off = +1: pointed state 0; its own edge has the smaller
+        // message index: kind 3) -> (a_i, b_i) = (relevant, pointed) variable -> factor messages
+        EdgeIn po;
+        po.m_p = xO[u]; po.m_r = 0.f; po.a_p = e0[u]; po.a_r = e1[u]; po.o_p = xA[u]; po.o_r = 0.f;
+        po.msg = w[u].mO << 1; po.kind = 3;
+        float ob, oa;
+        edge_q<true, kSumProduct>(po, 1, ob, oa);
+        stash[size_t(i - p0) * 64] = oa;
+        stash[size_t(i - p0) * 64 + 32] = ob;
+        // the AND factor (off = -1: pointed state 1): child SW_i (the OR edge comes first: kind 2),
+        // parents with sums from S (kind 0)
+        EdgeIn ce, ps, pw;
+        ce.m_p = xA[u]; ce.m_r = 0.f; ce.a_p = e1[u]; ce.a_r = e0[u]; ce.o_p = xO[u]; ce.o_r = 0.f;
+        ce.msg = (w[u].mA << 1) + 1; ce.kind = 2;
+        ps.m_p = xs[u]; ps.m_r = 0.f; ps.a_p = Ss1[u]; ps.a_r = Ss0[u]; ps.o_p = xs[u]; ps.o_r = 0.f;
+        ps.msg = (w[u].ms << 1) + 1; ps.kind = 0;
+        pw.m_p = xw[u]; pw.m_r = 0.f; pw.a_p = Sw1[u]; pw.a_r = Sw0[u]; pw.o_p = xw[u]; pw.o_r = 0.f;
+        pw.msg = (w[u].mw << 1) + 1; pw.kind = 0;
+        float c_p, c_r, s_p, s_r, w_p, w_r;
+        edge_q<true, kSumProduct>(ce, -1, c_p, c_r);
+        edge_q<true, kSumProduct>(ps, -1, s_p, s_r);
+        edge_q<true, kSumProduct>(pw, -1, w_p, w_r);
+        const int64_t q0 = int64_t(w[u].f_and) * 2;
+        LogicalAcc A;
+        A.istar = q0;
+        A.add<kSumProduct>(q0, s_r, s_p, T);
+        A.add<kSumProduct>(q0 + 1, w_r, w_p, T);
+        const float x_s = A.parent_out<kSumProduct>(q0, s_r, s_p, c_r, c_p, T, false);
+        const float x_w = A.parent_out<kSumProduct>(q0 + 1, w_r, w_p, c_r, c_p, T, false);
+        dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, -1, ps, x_s, d, one_minus_d));
+        dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, -1, pw, x_w, d, one_minus_d));
+        dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, -1, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d,
+                                                                  one_minus_d));
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase B ---------------------------------------------------------------------------------
+  if (warp == 0) {
+    EdgeIn ce = load_edge<true, kSumProduct>(g.or_children[gf], 1, mo, evq, esh, SL);
+    LogicalAcc A;
+    A.istar = p0;
+    for (int i = p0; i < p1; ++i) A.add<kSumProduct>(i, stash[size_t(i - p0) * 64], stash[size_t(i - p0) * 64 + 32], T);
+    float c_p, c_r;
+    edge_q<true, kSumProduct>(ce, 1, c_p, c_r);
+    agg[0] = A.acc; agg[32] = A.Sb; agg[64] = A.d1; agg[96] = A.d2; agg[128] = __int_as_float(int(A.istar));
+    agg[160] = c_p; agg[192] = c_r;
+    dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, 1, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
+  }
+  __syncthreads();
+  // ---- phase C ---------------------------------------------------------------------------------
+  {
+    LogicalAcc A;
+    A.acc = agg[0]; A.Sb = agg[32]; A.d1 = agg[64]; A.d2 = agg[96]; A.istar = __float_as_int(agg[128]);
+    const float c_p = agg[160], c_r = agg[192];
+    const bool single = p1 - p0 == 1;
+    for (int i0 = p0 + warp; i0 < p1; i0 += kFusedWarps * U) {
+      int32_t row[U];
+      float xO[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * kFusedWarps;
+        if (i < p1) row[u] = g.w[i].mO;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i0 + u * kFusedWarps < p1) xO[u] = mo[uint32_t(row[u]) << 5];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * kFusedWarps;
+        if (i < p1) {
+          const float oa = stash[size_t(i - p0) * 64], ob = stash[size_t(i - p0) * 64 + 32];
+          EdgeIn po;
+          po.m_p = xO[u]; po.m_r = 0.f; po.msg = row[u] << 1;
+          expand_msg<true, kSumProduct>(1, po.m_p, po.m_r);
+          const float x = A.parent_out<kSumProduct>(i, oa, ob, c_r, c_p, T, single);
+          dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, 1, po, x, d, one_minus_d));
+        }
+      }
+    }
+  }
+  if (kDelta && b < batch) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
 // K5: Pool update (pgmax/factor/pool.py:328-474).
 // ---------------------------------------------------------------------------
 template <bool kSumProduct>

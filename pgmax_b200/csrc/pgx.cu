@@ -70,7 +70,7 @@ enum AttrGroup { kAttrBigMax = 0, kAttrBipMax = 1, kAttrBipSum = 2, kAttrBigEnum
                  kAttrMaxProd = 5, kAttrLattice = 6, kAttrSdlpMax = 7, kAttrSdlpSum = 8, kAttrLatticeBin = 9,
                  kAttrLatticeBinV1 = 10, kAttrLatticeBinV2 = 11, kAttrLatticeBinV3 = 12, kAttrLatticeBinV4 = 13,
                  kAttrLatticeBinV5 = 14, kAttrLatticeBinV6 = 15, kAttrLatticeBinV7 = 16, kAttrLatticeBinV8 = 17,
-                 kAttrLatticeBinV9 = 18, kAttrOrAnd = 19 };
+                 kAttrLatticeBinV9 = 18, kAttrOrAndMax = 19, kAttrOrAndSum = 20 };
 
 struct EnumBlockPlan {
   pgx::EnumBlockDev dev{};
@@ -101,6 +101,7 @@ struct LogicalPlan {
   int32_t* d_parent_factor = nullptr;  // [P] factor of every parent (two-launch wide update)
   int64_t num_parents = 0;
   std::vector<int32_t> h_ptr, h_pmsg, h_pvs, h_cmsg, h_cvs;  // host copies, dropped after plan creation
+  std::vector<pgx::EdgeW> h_pw, h_cw;                         // packed pull wiring (same)
   bool needs_s = false;  // some edge reads its variable's sum from S
   int32_t *d_parent_ptr = nullptr, *d_parents_msg = nullptr, *d_parents_vs = nullptr, *d_children_msg = nullptr,
           *d_children_vs = nullptr;
@@ -208,6 +209,10 @@ struct pgx_plan {
   bool logical_pull_ok = false;
   int32_t* d_hi_list = nullptr;
   int64_t hi_len = 0;
+  // fused OR + AND launch (k_or_and_fused): every OR parent is the degree-2 child of one two-parent AND factor
+  bool orand_fused_ok = false;
+  pgx::OrAndFusedDev orand{};
+  pgx::FusedW* d_fused_w = nullptr;
   // the smaller of the OR / AND groups runs on an auxiliary stream beside the larger one
   // (long serial parent chains of wide OR factors hide behind the bandwidth-bound AND kernel)
   cudaStream_t aux = nullptr;
@@ -817,9 +822,30 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
   }
   int lid = -1;
   const cudaStream_t main_st = st;
+  const bool orand_fused = lpull && lbin && plan->orand_fused_ok && !(plan->disabled_paths & PGX_PATH_ORAND_FUSED);
+  if (orand_fused) {
+    // one launch for both groups: CTA per (OR factor, sample tile)
+    const size_t smem = pgx::orand_fused_smem(plan->orand.max_parents);
+    if (attr_needed(kSum ? kAttrOrAndSum : kAttrOrAndMax)) {
+      PGX_CUDA(cudaFuncSetAttribute(pgx::k_or_and_fused<kSum, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      PGX_CUDA(cudaFuncSetAttribute(pgx::k_or_and_fused<kSum, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    }
+    const dim3 grid(unsigned(plan->orand.num_or), unsigned(mp.nbt));
+    if ((rc = prof_mark(plan, st, plan->dominant))) return rc;
+    if (a.deltas != nullptr)
+      pgx::k_or_and_fused<kSum, true><<<grid, pgx::kFusedWarps * 32, smem, st>>>(mp.batch, plan->orand, ev, S, m_old, m_new, a);
+    else
+      pgx::k_or_and_fused<kSum, false><<<grid, pgx::kFusedWarps * 32, smem, st>>>(mp.batch, plan->orand, ev, S, m_old, m_new, a);
+    if ((rc = check_launch(plan, "k_or_and_fused"))) return rc;
+    if (plan->dominant < 0) {
+      plan->dominant_name = "k_or_and_fused";
+      plan->dominant_grid = int64_t(grid.x) * grid.y;
+    }
+    if ((rc = prof_mark(plan, st, plan->dominant))) return rc;
+  }
   for (LogicalPlan* lg : {&plan->or_f, &plan->and_f}) {
     const int id = lid--;
-    if (lg->dev.num_factors == 0) continue;
+    if (lg->dev.num_factors == 0 || orand_fused) continue;
     const cudaStream_t st = (lpull && aux != nullptr && id == plan->aux_group) ? aux : main_st;  // NOLINT
     if ((rc = prof_mark(plan, st, id))) return rc;
     if (lpull) {
@@ -1304,6 +1330,8 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       for (const pgx::EdgeW& e : cw) lg->needs_s = lg->needs_s || e.other == -2;
       PGX_TRY(upload(pw, &lg->d_parents_w, &plan->device_bytes));
       PGX_TRY(upload(cw, &lg->d_children_w, &plan->device_bytes));
+      lg->h_pw = pw;
+      lg->h_cw = cw;
       {
         std::vector<int32_t> pf(pw.size());
         for (int64_t f = 0; f < lg->dev.num_factors; ++f)
@@ -1330,6 +1358,45 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
     PGX_TRY(upload(hi, &plan->d_hi_list, &plan->device_bytes));
     plan->hi_len = int64_t(hi.size());
     plan->logical_pull_ok = true;
+    {
+      // Pairing for k_or_and_fused: every OR parent edge belongs to a variable with exactly two
+      // edges whose other edge is the child edge of a two-parent AND factor (each AND factor used
+      // once, all of them used), the OR edge has the smaller message index, the AND factors'
+      // parents take their sums from S, and every edge has two states.
+      const LogicalPlan& orp = plan->or_f;
+      const LogicalPlan& andp = plan->and_f;
+      bool ok = orp.dev.num_factors > 0 && andp.dev.num_factors > 0 && andp.dev.uniform == 2 &&
+                int64_t(orp.h_pw.size()) == andp.dev.num_factors && plan->num_edge_states == 2 * plan->num_edges &&
+                orp.max_parents <= 800;
+      std::vector<pgx::FusedW> fw;
+      if (ok) {
+        std::unordered_map<int32_t, int32_t> and_of_child;  // state-0 message index of the AND child edge -> factor
+        and_of_child.reserve(andp.h_cw.size() * 2);
+        for (size_t f = 0; f < andp.h_cw.size(); ++f) and_of_child[andp.h_cw[f].msg - 1] = int32_t(f);
+        std::vector<uint8_t> used(andp.h_cw.size(), 0);
+        fw.resize(orp.h_pw.size());
+        for (size_t i = 0; i < orp.h_pw.size() && ok; ++i) {
+          const pgx::EdgeW& e = orp.h_pw[i];  // msg / other: state-0 message indices
+          auto it = e.other >= 0 ? and_of_child.find(e.other) : and_of_child.end();
+          ok = it != and_of_child.end() && !used[it->second] && e.msg < e.other;
+          if (!ok) break;
+          const int32_t f = it->second;
+          used[f] = 1;
+          const pgx::EdgeW &ps = andp.h_pw[2 * size_t(f)], &pw2 = andp.h_pw[2 * size_t(f) + 1];
+          ok = ps.other == -2 && pw2.other == -2 && andp.h_cw[f].vs - 1 == e.vs;
+          fw[i] = pgx::FusedW{e.msg >> 1, andp.h_cw[f].msg >> 1, e.vs, ps.msg >> 1, pw2.msg >> 1, ps.vs - 1, pw2.vs - 1, f};
+        }
+      }
+      if (ok) {
+        PGX_TRY(upload(fw, &plan->d_fused_w, &plan->device_bytes));
+        plan->orand.num_or = orp.dev.num_factors;
+        plan->orand.parent_ptr = orp.d_parent_ptr;
+        plan->orand.w = plan->d_fused_w;
+        plan->orand.or_children = orp.d_children_w;
+        plan->orand.max_parents = int32_t(orp.max_parents);
+        plan->orand_fused_ok = true;
+      }
+    }
     if (plan->or_f.dev.num_factors > 0 && plan->and_f.dev.num_factors > 0) {
       const int64_t es_or = plan->or_f.dev.num_factors + desc->or_factors.num_parents;
       const int64_t es_and = plan->and_f.dev.num_factors + desc->and_factors.num_parents;
@@ -1346,7 +1413,7 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
     }
   }
   for (LogicalPlan* lg : {&plan->or_f, &plan->and_f, &plan->pool_f}) {
-    lg->h_ptr = {}; lg->h_pmsg = {}; lg->h_pvs = {}; lg->h_cmsg = {}; lg->h_cvs = {};
+    lg->h_ptr = {}; lg->h_pmsg = {}; lg->h_pvs = {}; lg->h_cmsg = {}; lg->h_cvs = {}; lg->h_pw = {}; lg->h_cw = {};
   }
   {  // pull mode: all factors pairwise-binary, every variable of degree <= kPullMaxDegree
     constexpr int64_t kPullMaxDegree = pgx::kPullMaxDegree;
@@ -1564,7 +1631,7 @@ void pgx_plan_destroy(pgx_plan* plan) {
     free_dev(lg->d_children_msg); free_dev(lg->d_children_vs);
     free_dev(lg->d_parents_w); free_dev(lg->d_children_w); free_dev(lg->d_parent_factor);
   }
-  free_dev(plan->d_hi_list);
+  free_dev(plan->d_hi_list); free_dev(plan->d_fused_w);
   if (plan->ev_fork) cudaEventDestroy(plan->ev_fork);
   if (plan->ev_join) cudaEventDestroy(plan->ev_join);
   if (plan->aux) cudaStreamDestroy(plan->aux);
@@ -1686,7 +1753,14 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     const char* v = getenv("PGX_GRAPH");
     return v != nullptr && v[0] == '0';
   }();
+  // OR / AND graphs on the pull path run their two groups on two streams of different PRIORITY
+  // (the long serial OR chains get free SM slots first); a captured graph does not keep that
+  // scheduling and measured slower (deconvolution, B = 100: 0.295 ms per iteration replayed
+  // against 0.260 enqueued, profiles/r02_h_graph_ab.txt): such runs stay on the direct path.
+  const bool priority_streams = plan->logical_pull_ok && plan->aux != nullptr && batch >= 32 &&
+                                !(plan->orand_fused_ok && !(plan->disabled_paths & (PGX_PATH_ORAND_FUSED | PGX_PATH_LOGICAL_BIN)));
   const bool eligible = plan->graphs_enabled && !env_off && !plan->profiling && !(flags & PGX_RUN_NO_GRAPH) && num_iters >= 2 &&
+                        !priority_streams &&
                         plan->num_edge_states > 0 && cudaStreamIsCapturing(st, &capturing) == cudaSuccess &&
                         capturing == cudaStreamCaptureStatusNone;
   if (!eligible)
@@ -1942,7 +2016,8 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
   // half-batch pipeline (see pgx_plan::half); not while the profiling events bracket whole launches
   const bool split = fused && mp.nbt >= 16 && plan->half != nullptr && !plan->profiling &&
                      !(plan->disabled_paths & PGX_PATH_HALF_BATCH);
-  const cudaStream_t aux = ((lpull || (side_blocks && !split)) && plan->aux != nullptr &&
+  const bool orand_fused = lpull && lbin && plan->orand_fused_ok && !(plan->disabled_paths & PGX_PATH_ORAND_FUSED);
+  const cudaStream_t aux = ((lpull || (side_blocks && !split)) && plan->aux != nullptr && !orand_fused &&
                             !(plan->disabled_paths & PGX_PATH_AUX_STREAM))
                                ? plan->aux : nullptr;
   const bool aux_after_s = lpull ? plan->aux_needs_s : true;

@@ -77,14 +77,19 @@ def test_graph_replay_rbm_single_pass_two_streams(temperature):
     _check(*_three_runs(bp, arrays, 9, temperature))
 
 
-def test_graph_replay_deconvolution_with_batch_tail():
-  """OR / AND pull kernels on two streams + the batch tail on a third (a second plan): all of it
-  in one graph; batch 40 = one full tile + a tail of 8."""
+def test_deconvolution_stays_on_the_direct_path_at_full_tiles():
+  """OR / AND graphs: small batches (generic kernels, one stream) replay a graph; from one full
+  sample tile on, the OR and AND groups run on two streams of different priority, which a captured
+  graph does not preserve (measured slower, pgx.cu) - those runs are enqueued directly.  Same bits
+  either way."""
   fg, groups = models.deconv_model(im_height=10, im_width=10, n_feat=3, feat_height=3, feat_width=3)
-  evidence = models.deconv_evidence(groups, batch=40)
   bp = infer.BP(fg.bp_state, temperature=0.0)
-  arrays = bp.init(evidence_updates=evidence)
+  arrays = bp.init(evidence_updates=models.deconv_evidence(groups, batch=5))
   _check(*_three_runs(bp, arrays, 6, 0.0))
+  arrays = bp.init(evidence_updates=models.deconv_evidence(groups, batch=40))
+  results, graphs, launches = _three_runs(bp, arrays, 6, 0.0)
+  assert graphs == [0, 0, 0] and launches[0] == launches[2]
+  np.testing.assert_array_equal(results[2][0], results[0][0])
 
 
 def test_graph_replay_rcn_merged_max_product():

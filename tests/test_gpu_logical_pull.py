@@ -179,3 +179,55 @@ def test_batch_tail_runs_beside_the_full_tiles(temperature, batch):
   states, _, _ = bp.context.decode(got2)
   want_states, _, _ = bp_oracle.decode_flat(graph, bp_oracle.flat_beliefs(graph, got2.ftov_msgs, got2.evidence))
   np.testing.assert_array_equal(states, want_states)
+
+
+@pytest.mark.parametrize("temperature", [0.0, 0.5])
+@pytest.mark.parametrize("batch", [32, 40, 70])
+def test_fused_or_and_launch_is_bit_identical(temperature, batch):
+  """k_or_and_fused (one launch per iteration for graphs whose OR parents are the degree-2
+  children of two-parent AND factors: the deconvolution model) against the separate AND / OR
+  reduce / OR emit kernels (PATH_ORAND_FUSED disabled): same helpers, same order of operations,
+  so every message and delta is identical; partial last tiles (batch 70 = 2 tiles + a tail of 6,
+  batch 40 = one tile + a tail of 8) included."""
+  fg, groups = models.deconv_model(im_height=9, im_width=8, n_feat=2, feat_height=3, feat_width=3)
+  evidence = models.deconv_evidence(groups, batch=batch)
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  arrays = bp.init(evidence_updates=evidence)
+  plan = bp.context.plan
+  before = plan.launch_count
+  got, got_d = _run(bp, arrays, 9, temperature, 0)
+  fused_launches = plan.launch_count - before
+  before = plan.launch_count
+  ref, ref_d = _run(bp, arrays, 9, temperature, plan.PATH_ORAND_FUSED)
+  separate_launches = plan.launch_count - before
+  np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
+  np.testing.assert_array_equal(got_d, ref_d)
+  assert fused_launches < separate_launches
+  # un-normalised batched initial messages, no tail split
+  rng = np.random.default_rng(5)
+  from pgmax_b200.infer.bp_state import BPArrays
+  init = BPArrays(log_potentials=arrays.log_potentials, evidence=arrays.evidence,
+                  ftov_msgs=rng.normal(size=(batch, arrays.ftov_msgs.shape[-1])).astype(np.float32))
+  a, a_d = _run(bp, init, 4, temperature, plan.PATH_TAIL_SPLIT)
+  b, b_d = _run(bp, init, 4, temperature, plan.PATH_TAIL_SPLIT | plan.PATH_ORAND_FUSED)
+  np.testing.assert_array_equal(a.ftov_msgs, b.ftov_msgs)
+  np.testing.assert_array_equal(a_d, b_d)
+
+
+def test_fused_or_and_full_size_deconvolution():
+  """configs[2] graph (28 x 28, 95 220 AND + 784 OR factors of up to 180 parents), 32 images,
+  3 max-product iterations: fused launch == separate kernels bit for bit, and the oracle for two
+  of the samples."""
+  fg, groups = models.deconv_model()
+  evidence = models.deconv_evidence(groups, batch=32)
+  bp = infer.BP(fg.bp_state, temperature=0.0)
+  arrays = bp.init(evidence_updates=evidence)
+  plan = bp.context.plan
+  got, got_d = _run(bp, arrays, 3, 0.0, 0)
+  ref, ref_d = _run(bp, arrays, 3, 0.0, plan.PATH_ORAND_FUSED)
+  np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
+  np.testing.assert_array_equal(got_d, ref_d)
+  graph = bp_oracle.graph_from_context(bp.context)
+  for b in (0, 31):
+    want, _ = bp_oracle.run_bp(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence[b], 3, 0.5, 0.0)
+    np.testing.assert_allclose(np.asarray(got.ftov_msgs)[b], want, rtol=2e-6, atol=2e-4)
