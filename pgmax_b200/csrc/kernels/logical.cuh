@@ -858,16 +858,17 @@ struct OrAndFusedDev {
   int32_t max_parents;
 };
 
-constexpr int kFusedWarps = 8;
+constexpr int kFusedWarps = 16;
+// dynamic shared memory: wiring [P] (32 B each), parked (a_i, b_i, old OR message) [P][3][32], aggregates [20][32]
 __host__ __device__ constexpr size_t orand_fused_smem(int max_parents) {
-  return (size_t(max_parents) * 2 + 8) * 32 * sizeof(float);
+  return size_t(max_parents) * sizeof(FusedW) + (size_t(max_parents) * 3 + 20) * 32 * sizeof(float);
 }
 
 template <bool kSumProduct, bool kDelta>
-__global__ void __launch_bounds__(kFusedWarps * 32)
+__global__ void __launch_bounds__(kFusedWarps * 32, 2)
 k_or_and_fused(int batch, OrAndFusedDev g, View ev, const float* __restrict__ S, const float* __restrict__ m_old,
                float* __restrict__ m_new, RunArgs a) {
-  extern __shared__ float fz[];
+  extern __shared__ __align__(16) unsigned char fz_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y * 32 + lane;
   const size_t tile = blockIdx.y;
@@ -881,122 +882,151 @@ k_or_and_fused(int batch, OrAndFusedDev g, View ev, const float* __restrict__ S,
   const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
   const int64_t gf = blockIdx.x;
   const int p0 = g.parent_ptr[gf], p1 = g.parent_ptr[gf + 1];
-  float* stash = fz + lane;                              // [parent][2][32]
-  float* agg = fz + size_t(g.max_parents) * 64 + lane;   // [8][32]
+  const int n = p1 - p0;
+  int4* wsm = reinterpret_cast<int4*>(fz_raw);                                             // [max_parents][2]
+  float* stash = reinterpret_cast<float*>(fz_raw + size_t(g.max_parents) * sizeof(FusedW)) + lane;  // [parent][3][32]
+  float* agg = stash + size_t(g.max_parents) * 96;                                         // [8][32]
   float dmax = 0.f;
-  constexpr int U = 2;
 
-  // ---- phase A ---------------------------------------------------------------------------------
-  for (int i0 = p0 + warp; i0 < p1; i0 += kFusedWarps * U) {
-    FusedW w[U];
-    float xO[U], xA[U], e0[U], e1[U], xs[U], xw[U], Ss0[U], Ss1[U], Sw0[U], Sw1[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * kFusedWarps;
-      if (i < p1) {
-        const int4* src = reinterpret_cast<const int4*>(g.w + i);
-        const int4 lo = src[0], hi = src[1];
-        w[u] = FusedW{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (i0 + u * kFusedWarps < p1) {
-        xO[u] = mo[uint32_t(w[u].mO) << 5];
-        xA[u] = mo[uint32_t(w[u].mA) << 5];
-        e0[u] = evq[uint32_t(w[u].ev0) << esh];
-        e1[u] = evq[uint32_t(w[u].ev0 + 1) << esh];
-        xs[u] = mo[uint32_t(w[u].ms) << 5];
-        xw[u] = mo[uint32_t(w[u].mw) << 5];
-        Ss0[u] = SL[uint32_t(w[u].Ss0) << 5];
-        Ss1[u] = SL[uint32_t(w[u].Ss0 + 1) << 5];
-        Sw0[u] = SL[uint32_t(w[u].Sw0) << 5];
-        Sw1[u] = SL[uint32_t(w[u].Sw0 + 1) << 5];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = i0 + u * kFusedWarps;
-      if (i < p1) {
-        // SW_i as parent of the OR factor (off = +1: pointed state 0; its own edge has the smaller
-        // message index: kind 3) -> (a_i, b_i) = (relevant, pointed) variable -> factor messages
-        EdgeIn po;
-        po.m_p = xO[u]; po.m_r = 0.f; po.a_p = e0[u]; po.a_r = e1[u]; po.o_p = xA[u]; po.o_r = 0.f;
-        po.msg = w[u].mO << 1; po.kind = 3;
-        float ob, oa;
-        edge_q<true, kSumProduct>(po, 1, ob, oa);
-        stash[size_t(i - p0) * 64] = oa;
-        stash[size_t(i - p0) * 64 + 32] = ob;
-        // the AND factor (off = -1: pointed state 1): child SW_i (the OR edge comes first: kind 2),
-        // parents with sums from S (kind 0)
-        EdgeIn ce, ps, pw;
-        ce.m_p = xA[u]; ce.m_r = 0.f; ce.a_p = e1[u]; ce.a_r = e0[u]; ce.o_p = xO[u]; ce.o_r = 0.f;
-        ce.msg = (w[u].mA << 1) + 1; ce.kind = 2;
-        ps.m_p = xs[u]; ps.m_r = 0.f; ps.a_p = Ss1[u]; ps.a_r = Ss0[u]; ps.o_p = xs[u]; ps.o_r = 0.f;
-        ps.msg = (w[u].ms << 1) + 1; ps.kind = 0;
-        pw.m_p = xw[u]; pw.m_r = 0.f; pw.a_p = Sw1[u]; pw.a_r = Sw0[u]; pw.o_p = xw[u]; pw.o_r = 0.f;
-        pw.msg = (w[u].mw << 1) + 1; pw.kind = 0;
-        float c_p, c_r, s_p, s_r, w_p, w_r;
-        edge_q<true, kSumProduct>(ce, -1, c_p, c_r);
-        edge_q<true, kSumProduct>(ps, -1, s_p, s_r);
-        edge_q<true, kSumProduct>(pw, -1, w_p, w_r);
-        const int64_t q0 = int64_t(w[u].f_and) * 2;
-        LogicalAcc A;
-        A.istar = q0;
-        A.add<kSumProduct>(q0, s_r, s_p, T);
-        A.add<kSumProduct>(q0 + 1, w_r, w_p, T);
-        const float x_s = A.parent_out<kSumProduct>(q0, s_r, s_p, c_r, c_p, T, false);
-        const float x_w = A.parent_out<kSumProduct>(q0 + 1, w_r, w_p, c_r, c_p, T, false);
-        dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, -1, ps, x_s, d, one_minus_d));
-        dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, -1, pw, x_w, d, one_minus_d));
-        dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, -1, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d,
-                                                                  one_minus_d));
-      }
-    }
+  // the factor's wiring: one coalesced sweep (the per-parent round trip below is then data only)
+  {
+    const int4* src = reinterpret_cast<const int4*>(g.w + p0);
+    for (int t = threadIdx.x; t < 2 * n; t += blockDim.x) wsm[t] = src[t];
   }
   __syncthreads();
+
+  // ---- phase A ---------------------------------------------------------------------------------
+  // software-pipelined: the ten loads of the warp's NEXT parent are in flight while the current
+  // one is computed (the kernel is bound by memory latency, not by bytes)
+  struct Raw {
+    FusedW w;
+    float xO, xA, e0, e1, xs, xw, Ss0, Ss1, Sw0, Sw1;
+  };
+  auto fetch = [&](int j, Raw& r) {
+    const int4 lo = wsm[2 * j], hi = wsm[2 * j + 1];
+    r.w = FusedW{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    r.xO = mo[uint32_t(r.w.mO) << 5];
+    r.xA = mo[uint32_t(r.w.mA) << 5];
+    r.e0 = evq[uint32_t(r.w.ev0) << esh];
+    r.e1 = evq[uint32_t(r.w.ev0 + 1) << esh];
+    r.xs = mo[uint32_t(r.w.ms) << 5];
+    r.xw = mo[uint32_t(r.w.mw) << 5];
+    r.Ss0 = SL[uint32_t(r.w.Ss0) << 5];
+    r.Ss1 = SL[uint32_t(r.w.Ss0 + 1) << 5];
+    r.Sw0 = SL[uint32_t(r.w.Sw0) << 5];
+    r.Sw1 = SL[uint32_t(r.w.Sw0 + 1) << 5];
+  };
+  Raw cur, nxt;
+  if (warp < n) fetch(warp, cur);
+  for (int j = warp; j < n; j += kFusedWarps) {
+    if (j + kFusedWarps < n) fetch(j + kFusedWarps, nxt);
+    {
+      const Raw& r = cur;
+      // SW_i as parent of the OR factor (off = +1: pointed state 0; its own edge has the smaller
+      // message index: kind 3) -> (a_i, b_i) = (relevant, pointed) variable -> factor messages
+      EdgeIn po;
+      po.m_p = r.xO; po.m_r = 0.f; po.a_p = r.e0; po.a_r = r.e1; po.o_p = r.xA; po.o_r = 0.f;
+      po.msg = r.w.mO << 1; po.kind = 3;
+      float ob, oa;
+      edge_q<true, kSumProduct>(po, 1, ob, oa);
+      stash[size_t(j) * 96] = oa;
+      stash[size_t(j) * 96 + 32] = ob;
+      stash[size_t(j) * 96 + 64] = r.xO;
+      // the AND factor (off = -1: pointed state 1): child SW_i (the OR edge comes first: kind 2),
+      // parents with sums from S (kind 0)
+      EdgeIn ce, ps, pw;
+      ce.m_p = r.xA; ce.m_r = 0.f; ce.a_p = r.e1; ce.a_r = r.e0; ce.o_p = r.xO; ce.o_r = 0.f;
+      ce.msg = (r.w.mA << 1) + 1; ce.kind = 2;
+      ps.m_p = r.xs; ps.m_r = 0.f; ps.a_p = r.Ss1; ps.a_r = r.Ss0; ps.o_p = r.xs; ps.o_r = 0.f;
+      ps.msg = (r.w.ms << 1) + 1; ps.kind = 0;
+      pw.m_p = r.xw; pw.m_r = 0.f; pw.a_p = r.Sw1; pw.a_r = r.Sw0; pw.o_p = r.xw; pw.o_r = 0.f;
+      pw.msg = (r.w.mw << 1) + 1; pw.kind = 0;
+      float c_p, c_r, s_p, s_r, w_p, w_r;
+      edge_q<true, kSumProduct>(ce, -1, c_p, c_r);
+      edge_q<true, kSumProduct>(ps, -1, s_p, s_r);
+      edge_q<true, kSumProduct>(pw, -1, w_p, w_r);
+      const int64_t q0 = int64_t(r.w.f_and) * 2;
+      LogicalAcc A;
+      A.istar = q0;
+      A.add<kSumProduct>(q0, s_r, s_p, T);
+      A.add<kSumProduct>(q0 + 1, w_r, w_p, T);
+      const float x_s = A.parent_out<kSumProduct>(q0, s_r, s_p, c_r, c_p, T, false);
+      const float x_w = A.parent_out<kSumProduct>(q0 + 1, w_r, w_p, c_r, c_p, T, false);
+      dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, -1, ps, x_s, d, one_minus_d));
+      dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, -1, pw, x_w, d, one_minus_d));
+      dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, -1, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d,
+                                                                one_minus_d));
+    }
+    cur = nxt;
+  }
+  // the OR factor's child edge: requested by warp 6 before the barrier, consumed after it
+  EdgeIn child;
+  if (warp == 6) child = load_edge<true, kSumProduct>(g.or_children[gf], 1, mo, evq, esh, SL);
+  __syncthreads();
   // ---- phase B ---------------------------------------------------------------------------------
-  if (warp == 0) {
-    EdgeIn ce = load_edge<true, kSumProduct>(g.or_children[gf], 1, mo, evq, esh, SL);
-    LogicalAcc A;
-    A.istar = p0;
-    for (int i = p0; i < p1; ++i) A.add<kSumProduct>(i, stash[size_t(i - p0) * 64], stash[size_t(i - p0) * 64 + 32], T);
+  // The two sums must be formed in ascending parent order (fp32 rounding): one warp each, a bare
+  // chain of dependent additions.  The two largest differences are exact selections, so four warps
+  // scan a quarter of the parents each and the quarters are merged after the barrier (first
+  // arg-max = LARGEST tied index, second maximum counting duplicates - LogicalAcc::add's rule).
+  if (warp == 0 || warp == 1) {
+    float sum = 0.f;
+    int j = 0;
+    for (; j + 8 <= n; j += 8) {
+      float va[8], vb[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { vb[k] = stash[size_t(j + k) * 96 + 32]; va[k] = warp == 0 ? 0.f : stash[size_t(j + k) * 96]; }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += warp == 0 ? vb[k] : (kSumProduct ? logaddexp_t(va[k], vb[k], T) : fmaxf(vb[k], va[k]));
+    }
+    for (; j < n; ++j) {
+      const float vb = stash[size_t(j) * 96 + 32], va = stash[size_t(j) * 96];
+      sum += warp == 0 ? vb : (kSumProduct ? logaddexp_t(va, vb, T) : fmaxf(vb, va));
+    }
+    agg[warp == 0 ? 32 : 0] = sum;  // Sb / acc
+  } else if (warp >= 2 && warp < 6) {
+    const int q = warp - 2, per = (n + 3) / 4;
+    const int j0 = q * per, j1 = min(n, j0 + per);
+    float d1 = -INFINITY, d2 = -INFINITY;
+    int istar = p0;
+    for (int j = j0; j < j1; ++j) {
+      const float dl = stash[size_t(j) * 96] - stash[size_t(j) * 96 + 32];
+      if (dl >= d1) { d2 = d1; d1 = dl; istar = p0 + j; }
+      else if (dl > d2) d2 = dl;
+    }
+    float* seg = agg + (8 + 3 * q) * 32;  // rows 8.. of the aggregate area
+    seg[0] = d1; seg[32] = d2; seg[64] = __int_as_float(istar);
+  } else if (warp == 6) {
     float c_p, c_r;
-    edge_q<true, kSumProduct>(ce, 1, c_p, c_r);
-    agg[0] = A.acc; agg[32] = A.Sb; agg[64] = A.d1; agg[96] = A.d2; agg[128] = __int_as_float(int(A.istar));
+    edge_q<true, kSumProduct>(child, 1, c_p, c_r);  // (expands child.m_p / m_r in place for store_edge below)
     agg[160] = c_p; agg[192] = c_r;
-    dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, 1, ce, A.child_relevant<kSumProduct>(T) - A.Sb, d, one_minus_d));
   }
   __syncthreads();
   // ---- phase C ---------------------------------------------------------------------------------
   {
     LogicalAcc A;
-    A.acc = agg[0]; A.Sb = agg[32]; A.d1 = agg[64]; A.d2 = agg[96]; A.istar = __float_as_int(agg[128]);
+    A.acc = agg[0]; A.Sb = agg[32];
+    A.d1 = -INFINITY; A.d2 = -INFINITY; A.istar = p0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // quarters in ascending parent order (empty ones skipped)
+      if (q * ((n + 3) / 4) >= n) continue;
+      const float* seg = agg + (8 + 3 * q) * 32;
+      const float sd1 = seg[0], sd2 = seg[32];
+      const int sidx = __float_as_int(seg[64]);
+      if (sd1 >= A.d1) { A.d2 = fmaxf(A.d1, sd2); A.d1 = sd1; A.istar = sidx; }
+      else A.d2 = fmaxf(A.d2, sd1);
+    }
     const float c_p = agg[160], c_r = agg[192];
-    const bool single = p1 - p0 == 1;
-    for (int i0 = p0 + warp; i0 < p1; i0 += kFusedWarps * U) {
-      int32_t row[U];
-      float xO[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * kFusedWarps;
-        if (i < p1) row[u] = g.w[i].mO;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (i0 + u * kFusedWarps < p1) xO[u] = mo[uint32_t(row[u]) << 5];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * kFusedWarps;
-        if (i < p1) {
-          const float oa = stash[size_t(i - p0) * 64], ob = stash[size_t(i - p0) * 64 + 32];
-          EdgeIn po;
-          po.m_p = xO[u]; po.m_r = 0.f; po.msg = row[u] << 1;
-          expand_msg<true, kSumProduct>(1, po.m_p, po.m_r);
-          const float x = A.parent_out<kSumProduct>(i, oa, ob, c_r, c_p, T, single);
-          dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, 1, po, x, d, one_minus_d));
-        }
-      }
+    const bool single = n == 1;
+    if (warp == 6)
+      dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, 1, child, A.child_relevant<kSumProduct>(T) - A.Sb, d,
+                                                                one_minus_d));
+    for (int j = warp; j < n; j += kFusedWarps) {
+      const float oa = stash[size_t(j) * 96], ob = stash[size_t(j) * 96 + 32];
+      EdgeIn po;
+      po.m_p = stash[size_t(j) * 96 + 64]; po.m_r = 0.f; po.msg = wsm[2 * j].x << 1;
+      expand_msg<true, kSumProduct>(1, po.m_p, po.m_r);
+      const float x = A.parent_out<kSumProduct>(p0 + j, oa, ob, c_r, c_p, T, single);
+      dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, 1, po, x, d, one_minus_d));
     }
   }
   if (kDelta && b < batch) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);

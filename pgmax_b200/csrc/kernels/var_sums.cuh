@@ -191,6 +191,66 @@ k_var_sums_list_bin(int batch, int nbt, int64_t E, int64_t Vs, const int2* __res
   }
 }
 
+// K1-list for VERY high-degree variables (the W variables of the deconvolution model: 529 edges
+// each) on binary-difference storage: a CTA per (variable, sample tile).  A single warp walking such
+// a list pays the memory latency once per 32 edges, 17 times in a row; here the CTA's warps gather
+// kVsBigSuper edges' rows into shared memory at once (every load of the super-chunk in flight) and
+// warp 0 then adds them from shared memory in ascending message index - the same additions in the
+// same order, hence bit-identical to k_var_sums_list_bin.
+constexpr int kVsBigWarps = 8;
+constexpr int kVsBigSuper = kVsBigWarps * 32;  // edges per super-chunk
+constexpr int kVsBigDegree = 96;               // variables with at least this many edges take this kernel
+
+__global__ void __launch_bounds__(kVsBigWarps * 32)
+k_var_sums_big_bin(int batch, int nbt, int64_t E, int64_t Vs, const int2* __restrict__ vs_csr,
+                   const int32_t* __restrict__ var_edge_msg, const int32_t* __restrict__ list, View ev,
+                   const float* __restrict__ c, float* __restrict__ S) {
+  __shared__ float xs[kVsBigSuper][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile_i = int(blockIdx.x % unsigned(nbt));
+  const int64_t i = blockIdx.x / unsigned(nbt);
+  const bool live = tile_i * 32 + lane < batch;
+  const int ll = live ? lane : 0;
+  const size_t tile = tile_i;
+  const float* cL = c + tile * size_t(E) * 32 + ll;
+  float* SL = S + tile * size_t(Vs) * 32 + ll;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + ll : ev.p;
+  const int esh = ev.kind == 1 ? 5 : 0;
+  const int v = list[2 * i];  // var-state of state 0; state 1 is v + 1
+  const int2 r = vs_csr[v];
+  const int k1 = r.x + (r.y >> kVsStateBits);
+  float acc0 = 0.f, acc1 = 0.f;
+  if (warp == 0) { acc0 = evq[uint32_t(v) << esh]; acc1 = evq[uint32_t(v + 1) << esh]; }
+  for (int k0 = r.x; k0 < k1; k0 += kVsBigSuper) {
+    // warp w gathers edges k0 + 32 w .. + 31: one coalesced index load, 32 row loads in flight
+    const int kb = k0 + warp * 32;
+    const int mine = kb + lane < k1 ? var_edge_msg[kb + lane] : 0;
+    float x[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int idx = __shfl_sync(0xffffffffu, mine, j);
+      x[j] = (kb + j < k1) ? cL[(uint32_t(idx) >> 1) << 5] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) xs[warp * 32 + j][lane] = x[j];
+    __syncthreads();
+    if (warp == 0) {
+      const int n = min(kVsBigSuper, k1 - k0);
+      for (int j = 0; j < n; ++j) {
+        const float xv = xs[j][lane];
+        const bool fl = xv != xv;  // both states at the floor (load_msg)
+        acc0 += fl ? kMsgNegInf : fminf(-xv, 0.f);
+        acc1 += fl ? kMsgNegInf : fminf(xv, 0.f);
+      }
+    }
+    __syncthreads();
+  }
+  if (warp == 0 && live) {
+    SL[uint32_t(v) << 5] = acc0;
+    SL[uint32_t(v + 1) << 5] = acc1;
+  }
+}
+
 // Full tile-blocked messages (normalised, every edge two states) -> binary-difference storage.
 __global__ void __launch_bounds__(kThreads)
 k_compress_bin(const float* __restrict__ m, float* __restrict__ c, int64_t E, int nbt) {

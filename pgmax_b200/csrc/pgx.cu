@@ -209,6 +209,7 @@ struct pgx_plan {
   bool logical_pull_ok = false;
   int32_t* d_hi_list = nullptr;
   int64_t hi_len = 0;
+  int64_t hi_big = 0;  // leading variables of the list with >= kVsBigDegree edges (two-state variables only)
   // fused OR + AND launch (k_or_and_fused): every OR parent is the degree-2 child of one two-parent AND factor
   bool orand_fused_ok = false;
   pgx::OrAndFusedDev orand{};
@@ -1357,6 +1358,12 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
     });
     PGX_TRY(upload(hi, &plan->d_hi_list, &plan->device_bytes));
     plan->hi_len = int64_t(hi.size());
+    if (plan->num_edge_states == 2 * plan->num_edges)  // binary variables: list entries come in (state 0, state 1) pairs
+      for (size_t k = 0; k + 1 < hi.size(); k += 2) {
+        const int32_t var = vs_var[hi[k]];
+        if (var_ptr[var + 1] - var_ptr[var] < pgx::kVsBigDegree) break;
+        ++plan->hi_big;
+      }
     plan->logical_pull_ok = true;
     {
       // Pairing for k_or_and_fused: every OR parent edge belongs to a variable with exactly two
@@ -1861,8 +1868,12 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
   const bool lbin = lpull && !(plan->disabled_paths & PGX_PATH_LOGICAL_BIN) && Es == 2 * plan->num_edges;
   // Batch tail: a few samples beyond the last full tile run through the tail plan on its own stream.
   const int64_t tail_n = batch & 31;
+  // (not with the fused OR + AND launch: there one more - partial - tile costs less than the tail
+  // plan's generic kernels, whose serial wide-OR update then bounds the iteration: deconvolution
+  // B = 100, 0.235 ms per iteration split against 0.227 as four tiles)
+  const bool fused_orand_run = lbin && plan->orand_fused_ok && !(plan->disabled_paths & PGX_PATH_ORAND_FUSED);
   if (lpull && batch > 32 && tail_n != 0 && tail_n <= pgx::kTailMaxSamples && plan->desc_copy != nullptr &&
-      !(plan->disabled_paths & PGX_PATH_TAIL_SPLIT)) {
+      !fused_orand_run && !(plan->disabled_paths & PGX_PATH_TAIL_SPLIT)) {
     const int64_t main_n = batch - tail_n;
     if (plan->tail == nullptr) {
       if ((rc = pgx_plan_create(&plan->desc_copy->desc, &plan->tail))) return rc;
@@ -2200,15 +2211,39 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
     if (lpull) {
       if (plan->hi_len > 0) {
         const int64_t per_tile = std::min<int64_t>(plan->hi_len, (int64_t(1) << 30) / mp.nbt);
-        if (lbin)
-          pgx::k_var_sums_list_bin<<<unsigned(std::max<int64_t>(per_tile / 2, 1) * mp.nbt), 32, 0, st>>>(
-              mp.batch, mp.nbt, Es / 2, Vs, plan->d_vs_csr, plan->d_var_edge_msg, plan->d_hi_list, plan->hi_len, ev, cur,
-              ws.S);
-        else
+        if (lbin) {
+          // the list is sorted by degree, longest first: its first hi_big variables (>= kVsBigDegree edges)
+          // take the cooperative kernel, the rest a warp each
+          const int64_t big = (plan->disabled_paths & PGX_PATH_VARSUM_COOP) ? 0 : plan->hi_big;
+          // ... on the auxiliary stream beside the warp-per-variable launch when that stream is free
+          // (fused OR + AND path: nothing else uses it)
+          const bool side = big > 0 && plan->aux != nullptr && plan->orand_fused_ok &&
+                            !(plan->disabled_paths & (PGX_PATH_ORAND_FUSED | PGX_PATH_AUX_STREAM));
+          if (big > 0) {
+            const cudaStream_t sb = side ? plan->aux : st;
+            if (side) {
+              PGX_CUDA(cudaEventRecord(plan->ev_fork, st));
+              PGX_CUDA(cudaStreamWaitEvent(plan->aux, plan->ev_fork, 0));
+            }
+            pgx::k_var_sums_big_bin<<<unsigned(big * mp.nbt), pgx::kVsBigWarps * 32, 0, sb>>>(
+                mp.batch, mp.nbt, Es / 2, Vs, plan->d_vs_csr, plan->d_var_edge_msg, plan->d_hi_list, ev, cur, ws.S);
+            if ((rc = check_launch(plan, "k_var_sums_big_bin"))) return rc;
+            if (side) PGX_CUDA(cudaEventRecord(plan->ev_join, plan->aux));
+          }
+          const int64_t rest = plan->hi_len - 2 * big;
+          if (rest > 0) {
+            pgx::k_var_sums_list_bin<<<unsigned(std::max<int64_t>(std::min<int64_t>(per_tile, rest) / 2, 1) * mp.nbt), 32, 0, st>>>(
+                mp.batch, mp.nbt, Es / 2, Vs, plan->d_vs_csr, plan->d_var_edge_msg, plan->d_hi_list + 2 * big, rest, ev,
+                cur, ws.S);
+            if ((rc = check_launch(plan, "k_var_sums_list"))) return rc;
+          }
+          if (side) PGX_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
+        } else {
           pgx::k_var_sums_list<<<unsigned(per_tile * mp.nbt), 32, 0, st>>>(mp.batch, mp.nbt, Es, Vs, plan->d_vs_csr,
                                                                         plan->d_var_edge_msg, plan->d_hi_list, plan->hi_len,
                                                                         ev, cur, ws.S);
-        if ((rc = check_launch(plan, "k_var_sums_list"))) return rc;
+          if ((rc = check_launch(plan, "k_var_sums_list"))) return rc;
+        }
       }
     } else if (!fused || it == 0) {
       pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(

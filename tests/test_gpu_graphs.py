@@ -77,19 +77,26 @@ def test_graph_replay_rbm_single_pass_two_streams(temperature):
     _check(*_three_runs(bp, arrays, 9, temperature))
 
 
-def test_deconvolution_stays_on_the_direct_path_at_full_tiles():
-  """OR / AND graphs: small batches (generic kernels, one stream) replay a graph; from one full
-  sample tile on, the OR and AND groups run on two streams of different priority, which a captured
-  graph does not preserve (measured slower, pgx.cu) - those runs are enqueued directly.  Same bits
-  either way."""
+def test_graph_replay_deconvolution():
+  """OR / AND graphs: small batches (generic kernels, one stream) and the fused OR + AND launch
+  (full sample tiles + the batch tail on a second stream and a second plan) replay a graph.  With
+  the fused launch disabled the OR and AND groups run on two streams of different PRIORITY, which
+  a captured graph does not preserve (measured slower, pgx.cu): those runs are enqueued directly.
+  Same bits either way."""
   fg, groups = models.deconv_model(im_height=10, im_width=10, n_feat=3, feat_height=3, feat_width=3)
   bp = infer.BP(fg.bp_state, temperature=0.0)
+  plan = bp.context.plan
   arrays = bp.init(evidence_updates=models.deconv_evidence(groups, batch=5))
   _check(*_three_runs(bp, arrays, 6, 0.0))
   arrays = bp.init(evidence_updates=models.deconv_evidence(groups, batch=40))
+  fused = _three_runs(bp, arrays, 6, 0.0)
+  _check(*fused)
+  plan.disable_paths(plan.PATH_ORAND_FUSED)
   results, graphs, launches = _three_runs(bp, arrays, 6, 0.0)
+  plan.disable_paths(0)
   assert graphs == [0, 0, 0] and launches[0] == launches[2]
   np.testing.assert_array_equal(results[2][0], results[0][0])
+  np.testing.assert_array_equal(results[0][0], fused[0][0][0])
 
 
 def test_graph_replay_rcn_merged_max_product():

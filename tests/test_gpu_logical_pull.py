@@ -161,16 +161,19 @@ def test_batch_tail_runs_beside_the_full_tiles(temperature, batch):
   bp = infer.BP(fg.bp_state, temperature=temperature)
   arrays = bp.init(evidence_updates=evidence)
   plan = bp.context.plan
+  # (the fused OR + AND launch takes a partial tile instead of splitting the tail: the split is
+  # the separate kernels' mechanism)
+  sep = plan.PATH_ORAND_FUSED
   before = plan.launch_count
-  ref, ref_d = _run(bp, arrays, 7, temperature, plan.PATH_TAIL_SPLIT)
+  ref, ref_d = _run(bp, arrays, 7, temperature, sep | plan.PATH_TAIL_SPLIT)
   unsplit_launches = plan.launch_count - before
   before = plan.launch_count
-  got, got_d = _run(bp, arrays, 7, temperature, 0)
+  got, got_d = _run(bp, arrays, 7, temperature, sep)
   split_launches = plan.launch_count - before
   np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
   np.testing.assert_array_equal(got_d, ref_d)
-  ref2, ref2_d = _run(bp, ref, 5, temperature, plan.PATH_TAIL_SPLIT)
-  got2, got2_d = _run(bp, got, 5, temperature, 0)
+  ref2, ref2_d = _run(bp, ref, 5, temperature, sep | plan.PATH_TAIL_SPLIT)
+  got2, got2_d = _run(bp, got, 5, temperature, sep)
   np.testing.assert_array_equal(got2.ftov_msgs, ref2.ftov_msgs)
   np.testing.assert_array_equal(got2_d, ref2_d)
   assert split_launches > unsplit_launches  # the tail's kernels are counted
@@ -225,6 +228,11 @@ def test_fused_or_and_full_size_deconvolution():
   plan = bp.context.plan
   got, got_d = _run(bp, arrays, 3, 0.0, 0)
   ref, ref_d = _run(bp, arrays, 3, 0.0, plan.PATH_ORAND_FUSED)
+  np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
+  np.testing.assert_array_equal(got_d, ref_d)
+  # the W variables (529 edges each) through one warp per variable instead of the cooperative
+  # shared-memory gather (k_var_sums_big_bin): the same additions in the same order
+  ref, ref_d = _run(bp, arrays, 3, 0.0, plan.PATH_VARSUM_COOP)
   np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
   np.testing.assert_array_equal(got_d, ref_d)
   graph = bp_oracle.graph_from_context(bp.context)
