@@ -149,6 +149,10 @@ int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch,
  * for a capture.)  Skipped when `stream` is itself being captured (the caller's graph then holds
  * the launches), under pgx_plan_profile_enable, with PGX_GRAPH=0 in the environment, or with: */
 #define PGX_RUN_NO_GRAPH 2u
+/* The caller guarantees that log_potentials (same pointer) holds the same values as in this
+ * plan's previous run: per-run preprocessing of the potentials (the round-ordered copy of the
+ * merged max-product launch) is reused instead of redone. */
+#define PGX_RUN_POTENTIALS_UNCHANGED 4u
 int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch,
                      const float* log_potentials, int lp_batched,
                      const float* evidence, int ev_batched,

@@ -463,12 +463,14 @@ class Plan:
 
   # The methods below take raw device pointers (ints) so that any owner of device
   # memory (torch tensors here) can call them.
+  RUN_INPUT_NORMALIZED, RUN_NO_GRAPH, RUN_POTENTIALS_UNCHANGED = 1, 2, 4
+
   def bp_run(self, stream: int, batch: int, lp: int, lp_batched: bool, ev: int, ev_batched: bool,
              msgs_in: Optional[int], msgs_batched: bool, msgs_out: int, deltas: Optional[int],
-             num_iters: int, damping: float, temperature: float) -> None:
-    check(self._lib.pgx_bp_run(self.handle, stream, batch, lp, int(lp_batched), ev, int(ev_batched),
-                               msgs_in, int(msgs_batched), msgs_out, deltas, num_iters,
-                               damping, temperature))
+             num_iters: int, damping: float, temperature: float, flags: int = 0) -> None:
+    check(self._lib.pgx_bp_run_flags(self.handle, stream, batch, lp, int(lp_batched), ev, int(ev_batched),
+                                     msgs_in, int(msgs_batched), msgs_out, deltas, num_iters,
+                                     damping, temperature, int(flags)))
 
   def bp_step(self, stream: int, lp: int, ev: int, msgs_in: int, msgs_out: int, damping: float,
               temperature: float, num_iters: int = 1) -> None:

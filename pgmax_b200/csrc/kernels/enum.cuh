@@ -332,6 +332,10 @@ struct BigMaxGroup {
                              // even number of rounds.
   int64_t perm_base;
   int32_t num_rounds;
+  // lane l of lane-group g owns state lane_state[32 g + l] of the first variable (n0 = none): the
+  // plan groups states with lists of similar length (and distinct shared-memory banks) so that the
+  // lanes of a group finish together - fewer idle slots in the round schedule
+  const int32_t* lane_state;
 };
 
 // One-off per run: potentials -> round order (see BigMaxGroup).
@@ -419,7 +423,7 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
       // flight, what HBM latency x bandwidth asks for
       constexpr int kPermTrip = 16;
       for (int grp = warp; kPerm && grp < G.num_groups; grp += kBigWarps) {
-        const int a_own = grp * 32 + lane;
+        const int a_own = G.lane_state[grp * 32 + lane];
         const float qa = a_own < n0 ? q[a_own] : 0.f;
         const int r_end = G.round_ptr[grp + 1];
         const uint32_t idle2 = uint32_t(n1 + lane) * 0x10001u;
@@ -470,7 +474,7 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
         if (a_own < n0) M[a_own] = best;
       }
       for (int grp = warp; !kPerm && grp < G.num_groups; grp += kBigWarps) {
-        const int a_own = grp * 32 + lane;
+        const int a_own = G.lane_state[grp * 32 + lane];
         const float qa = a_own < n0 ? q[a_own] : 0.f;
         const int r_end = G.round_ptr[grp + 1];
         uint32_t en_n[kBigTrip];

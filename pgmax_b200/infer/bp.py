@@ -56,7 +56,7 @@ def BP(bp_state: BPState, temperature: Optional[float] = 0.0) -> BeliefPropagati
 
     # The reference runs one update for num_iters <= 1 (bp.py:142-146).
     num_iters = max(int(num_iters), 1)
-    buf = DeviceBuffers(bp_arrays, context._device())
+    buf = DeviceBuffers(bp_arrays, context._device(), context.lp_cache)
     plan = context.plan
     batch = buf.batch or 1
     out = torch.empty((batch, plan.num_edge_states), dtype=torch.float32, device=buf.device)
@@ -64,7 +64,8 @@ def BP(bp_state: BPState, temperature: Optional[float] = 0.0) -> BeliefPropagati
     stream = torch.cuda.current_stream(buf.device).cuda_stream
     plan.bp_run(stream, batch, buf.lp.data_ptr(), buf.lp.ndim == 2, buf.ev.data_ptr(),
                 buf.ev.ndim == 2, buf.msgs.data_ptr(), buf.msgs.ndim == 2, out.data_ptr(),
-                deltas.data_ptr(), num_iters, float(damping), float(temperature))
+                deltas.data_ptr(), num_iters, float(damping), float(temperature),
+                flags=plan.RUN_POTENTIALS_UNCHANGED if buf.lp_unchanged else 0)
     if buf.batch is None:
       out, deltas = out[0], deltas[0]
     new_arrays = BPArrays(
@@ -84,14 +85,15 @@ def BP(bp_state: BPState, temperature: Optional[float] = 0.0) -> BeliefPropagati
     import torch  # pylint: disable=g-import-not-at-top
 
     num_iters = max(int(num_iters), 1)
-    buf = DeviceBuffers(bp_arrays, context._device())
+    buf = DeviceBuffers(bp_arrays, context._device(), context.lp_cache)
     plan = context.plan
     batch = buf.batch or 1
     out = torch.empty((batch, plan.num_edge_states), dtype=torch.float32, device=buf.device)
     stream = torch.cuda.current_stream(buf.device).cuda_stream
     plan.bp_run(stream, batch, buf.lp.data_ptr(), buf.lp.ndim == 2, buf.ev.data_ptr(),
                 buf.ev.ndim == 2, buf.msgs.data_ptr(), buf.msgs.ndim == 2, out.data_ptr(),
-                None, num_iters, float(damping), float(temperature))
+                None, num_iters, float(damping), float(temperature),
+                flags=plan.RUN_POTENTIALS_UNCHANGED if buf.lp_unchanged else 0)
     return BPArrays(
         log_potentials=bp_arrays.log_potentials,
         ftov_msgs=buf.out(out if buf.batch is not None else out[0]),

@@ -33,16 +33,35 @@ class Inferer:
 class DeviceBuffers:
   """Moves BPArrays fields to fp32 CUDA tensors and remembers what came from the host."""
 
-  def __init__(self, bp_arrays: BPArrays, device):
+  def __init__(self, bp_arrays: BPArrays, device, lp_cache: Optional[dict] = None):
     import torch  # pylint: disable=g-import-not-at-top
 
     self.torch = torch
     self.device = device
     self.from_host = not _is_torch(bp_arrays.ftov_msgs)
     self.batch = bp_arrays.batch_size
-    self.lp = self._put(bp_arrays.log_potentials)
+    self.lp, self.lp_unchanged = self._put_potentials(bp_arrays.log_potentials, lp_cache)
     self.ev = self._put(bp_arrays.evidence)
     self.msgs = self._put(bp_arrays.ftov_msgs)
+
+  def _put_potentials(self, arr, cache: Optional[dict]):
+    """Potentials on the device + whether they are KNOWN to be what the previous run of this
+    inferer used (same immutable host array object -> the cached device copy is reused, no
+    upload; same device tensor, same torch version counter): per-run preprocessing of the
+    potentials is then skipped (PGX_RUN_POTENTIALS_UNCHANGED)."""
+    if cache is None:
+      return self._put(arr), False
+    if _is_torch(arr):
+      t = self._put(arr)
+      key = ("torch", t.data_ptr(), int(getattr(arr, "_version", -1)), tuple(t.shape), t is arr or t.data_ptr() == arr.data_ptr())
+      unchanged = key[-1] and cache.get("key") == key
+      cache.update(key=key, host=None, dev=None)
+      return t, bool(unchanged)
+    if cache.get("host") is arr and not arr.flags.writeable and cache.get("dev") is not None:
+      return cache["dev"], True
+    t = self._put(arr)
+    cache.update(key=None, host=arr if not arr.flags.writeable else None, dev=t)
+    return t, False
 
   def _put(self, arr):
     torch = self.torch
@@ -77,6 +96,7 @@ class InfererContext:
     self.num_factors = sum(w.num_factors for w in self.wiring.values())
     self._flat = None
     self._plan = None
+    self.lp_cache = {}  # DeviceBuffers._put_potentials
 
   # ---- reference-format views (oracle / tests), pgmax/infer/inferer.py:76-98 ----
   def _flat_arrays(self) -> np.ndarray:
