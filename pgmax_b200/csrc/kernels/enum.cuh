@@ -361,21 +361,31 @@ constexpr int kBigTrip = 8;
 
 // kFlatLp: potentials addressed without a sample-tile shift (shared or batch-major);
 // kPerm: potentials come from the round-ordered copy lpR (potentials shared by the batch)
+#ifndef PGX_BIGMAX_CTAS
+#define PGX_BIGMAX_CTAS 3
+#endif
 template <bool kFlatLp, bool kPerm>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, PGX_BIGMAX_CTAS)
 k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, const int2* __restrict__ units,
                        int64_t num_units, unsigned int* __restrict__ counter,
                        const int32_t* __restrict__ edge_vs, View lp, const float* __restrict__ lpR,
                        const float* __restrict__ S,
                        const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
   extern __shared__ float smem[];
-  __shared__ unsigned int s_unit;
+  __shared__ unsigned int s_unit, s_grp;
   const int sh = mp.bx_log;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = num_units * mp.batch;
+  // lane-groups of a unit are handed to the warps dynamically (20 groups over 8 warps as a static
+  // 3 / 2 split leaves the CTA waiting for its slowest warp a fifth of the time)
+  auto next_group = [&]() {
+    unsigned int gi = 0;
+    if (lane == 0) gi = atomicAdd(&s_grp, 1u);
+    return int(__shfl_sync(0xffffffffu, gi, 0));
+  };
   for (;;) {
     __syncthreads();  // previous unit done with shared memory (and with s_unit)
-    if (threadIdx.x == 0) s_unit = atomicAdd(counter, 1u);
+    if (threadIdx.x == 0) { s_unit = atomicAdd(counter, 1u); s_grp = 0; }
     __syncthreads();
     const int64_t unit = s_unit;
     if (unit >= total) break;
@@ -422,20 +432,31 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
       // flight while this one is consumed: with 24 warps per SM that is ~50 KiB per SM in
       // flight, what HBM latency x bandwidth asks for
       constexpr int kPermTrip = 16;
-      for (int grp = warp; kPerm && grp < G.num_groups; grp += kBigWarps) {
+      for (int grp = kPerm ? next_group() : G.num_groups; kPerm && grp < G.num_groups; grp = next_group()) {
         const int a_own = G.lane_state[grp * 32 + lane];
         const float qa = a_own < n0 ? q[a_own] : 0.f;
         const int r_end = G.round_ptr[grp + 1];
-        const uint32_t idle2 = uint32_t(n1 + lane) * 0x10001u;
+        const uint32_t idle2 = uint32_t((n1 + lane) << 2) * 0x10001u;  // (table entries are byte offsets: state << 2)
         uint32_t en_n[kPermTrip / 2];
         float rl_n[kPermTrip];
+        // full trips issue their 24 loads without a predicate; only a group's last, partial trip
+        // pays for the bounds checks
         auto request = [&](int r0) {
+          if (r0 + kPermTrip <= r_end) {
 #pragma unroll
-          for (int p = 0; p < kPermTrip / 2; ++p) {
-            const bool in = r0 + 2 * p < r_end;  // rounds come in pairs
-            en_n[p] = in ? __ldg(rbl + (size_t(r0 + 2 * p) << 4)) : idle2;
-            rl_n[2 * p] = in ? __ldcs(lpr + (size_t(r0 + 2 * p) << 5)) : -INFINITY;
-            rl_n[2 * p + 1] = in ? __ldcs(lpr + (size_t(r0 + 2 * p + 1) << 5)) : -INFINITY;
+            for (int p = 0; p < kPermTrip / 2; ++p) {
+              en_n[p] = __ldg(rbl + (size_t(r0 + 2 * p) << 4));
+              rl_n[2 * p] = __ldcs(lpr + (size_t(r0 + 2 * p) << 5));
+              rl_n[2 * p + 1] = __ldcs(lpr + (size_t(r0 + 2 * p + 1) << 5));
+            }
+          } else {
+#pragma unroll
+            for (int p = 0; p < kPermTrip / 2; ++p) {
+              const bool in = r0 + 2 * p < r_end;  // rounds come in pairs
+              en_n[p] = in ? __ldg(rbl + (size_t(r0 + 2 * p) << 4)) : idle2;
+              rl_n[2 * p] = in ? __ldcs(lpr + (size_t(r0 + 2 * p) << 5)) : -INFINITY;
+              rl_n[2 * p + 1] = in ? __ldcs(lpr + (size_t(r0 + 2 * p + 1) << 5)) : -INFINITY;
+            }
           }
         };
         float best = -INFINITY;
@@ -456,7 +477,7 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
           float sk[kPermTrip];
 #pragma unroll
           for (int p = 0; p < kPermTrip; ++p) {
-            b_s[p] = ((p & 1) ? (en[p >> 1] >> 16) : (en[p >> 1] & 0xffffu)) << 2;
+            b_s[p] = (p & 1) ? (en[p >> 1] >> 16) : (en[p >> 1] & 0xffffu);  // byte offset of the partner state
             sk[p] = lds_f(qb_s + b_s[p]);
           }
 #pragma unroll
@@ -473,7 +494,7 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
         }
         if (a_own < n0) M[a_own] = best;
       }
-      for (int grp = warp; !kPerm && grp < G.num_groups; grp += kBigWarps) {
+      for (int grp = !kPerm ? next_group() : G.num_groups; !kPerm && grp < G.num_groups; grp = next_group()) {
         const int a_own = G.lane_state[grp * 32 + lane];
         const float qa = a_own < n0 ? q[a_own] : 0.f;
         const int r_end = G.round_ptr[grp + 1];

@@ -630,7 +630,7 @@ int build_enum_block(pgx_plan* plan, const pgx_enum_block* desc_blocks, const st
         };
         std::vector<uint32_t> rb(std::max<size_t>(rounds.size() / 2, 32));
         for (size_t pr = 0; pr + 1 < rounds.size() / 32 + 1 && pr * 64 + 63 < rounds.size(); ++pr)
-          for (size_t l = 0; l < 32; ++l) rb[pr * 32 + l] = pb(pr * 64 + l) | (pb(pr * 64 + 32 + l) << 16);
+          for (size_t l = 0; l < 32; ++l) rb[pr * 32 + l] = (pb(pr * 64 + l) << 2) | (pb(pr * 64 + 32 + l) << 18);  // byte offsets
         if ((rc = upload(rb, &out->d_rounds_b, &plan->device_bytes))) return rc;
       }
       out->num_rounds = int32_t(rounds.size() / 32);
