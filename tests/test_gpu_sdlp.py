@@ -8,6 +8,8 @@ softmax argument is divided by T, so one fp32 ulp of a message moves the gradien
 ~1e-3 * |g|: gradient compared at 2e-3 there, objective and logsumexps stay at 1e-5 relative.
 """
 
+import os
+
 import numpy as np
 import pytest
 
@@ -18,6 +20,22 @@ from pgmax_b200 import fgraph, fgroup, infer, vgroup
 
 pytestmark = pytest.mark.gpu
 RTOL = 5e-3  # tests/lp/test_dual_lp.py:27
+# LP optima of the reference's test models from an independent solver (tests/golden/make_sdlp_golden.py)
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdlp_lp.npz"))
+
+
+def _check_lp(name, sdlp, decoded, upper, lower):
+  """tests/lp/test_dual_lp.py:123,221,304,395 (bound == LP optimum, rtol 5e-3) against the committed
+  HiGHS optimum; the relaxations are tight, so the device's decoding is the LP's integral solution."""
+  objval = float(GOLD[f"{name}_objval"])
+  assert np.isclose(objval, upper, rtol=RTOL), (objval, upper)
+  assert np.isclose(objval, lower, rtol=RTOL), (objval, lower)
+  info = sdlp.context.bp_state.fg_state
+  states = np.concatenate([np.asarray(decoded[vg]).reshape(-1) for vg in info.variable_groups])
+  bounds = np.concatenate([[0], np.cumsum(np.concatenate([vg.num_states.reshape(-1) for vg in info.variable_groups]))])
+  lp_states = np.array([int(np.argmax(GOLD[f"{name}_solution"][bounds[v] : bounds[v + 1]]))
+                        for v in range(len(bounds) - 1)])
+  np.testing.assert_array_equal(states, lp_states)
 
 
 def _tols(temp):
@@ -142,6 +160,7 @@ def test_dual_bounds_meet_on_tight_ising(seed, temp):
   lower = sdlp.get_map_lower_bound(arrays, decoded)
   assert np.isclose(lower, upper, rtol=RTOL)
   assert np.isclose(lower, sdlp.get_map_lower_bound(arrays, decoded, debug_mode=True))
+  _check_lp(f"ising_{seed}", sdlp, decoded, upper, lower)
 
 
 def test_line_sparsification():
@@ -156,6 +175,27 @@ def test_line_sparsification():
     upper = sdlp.get_primal_upper_bound(arrays)
     lower = sdlp.get_map_lower_bound(arrays, decoded)
     assert np.isclose(lower, upper, rtol=RTOL)
+    _check_lp(f"line_{seed}", sdlp, decoded, upper, lower)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_and_and_pool_models_reach_the_lp_optimum(seed):
+  """tests/lp/test_dual_lp.py:231-402 on the device: ANDFactors (rows of ones) and the PoolFactor
+  hierarchy, bounds and decodings against the LP fixture."""
+  fg, matrix, all_ones, evidence, truth = models.sdlp_and_model(seed=seed)
+  sdlp = infer.build_inferer(fg.bp_state, backend="sdlp")
+  arrays = sdlp.run(sdlp.init(evidence_updates=evidence), logsumexp_temp=1e-3, lr=None, num_iters=5000)
+  decoded, _ = sdlp.decode_primal_unaries(arrays)
+  np.testing.assert_array_equal(np.asarray(decoded[all_ones]).reshape(-1), truth)
+  _check_lp(f"and_{seed}", sdlp, decoded, sdlp.get_primal_upper_bound(arrays), sdlp.get_map_lower_bound(arrays, decoded))
+  fg, variables = models.sdlp_pool_model()
+  updates = np.random.RandomState(seed).gumbel(size=(variables.shape[0], 2))
+  updates[0, 1] = 1_000
+  sdlp = infer.build_inferer(fg.bp_state, backend="sdlp")
+  arrays = sdlp.run(sdlp.init(evidence_updates={variables: updates}), logsumexp_temp=1e-3, lr=None, num_iters=5000)
+  decoded, _ = sdlp.decode_primal_unaries(arrays)
+  assert int(np.asarray(decoded[variables]).sum()) == 4
+  _check_lp(f"pool_{seed}", sdlp, decoded, sdlp.get_primal_upper_bound(arrays), sdlp.get_map_lower_bound(arrays, decoded))
 
 
 def test_zero_iterations_and_shared_messages():

@@ -14,6 +14,9 @@ through the reference's own property tests (no GPU, no stored JAX outputs exist)
     objective on graphs mixing Enum and OR / AND / Pool factors.
 """
 
+import os
+import sys
+
 import numpy as np
 import pytest
 
@@ -23,6 +26,31 @@ from oracle import sdlp_oracle
 from pgmax_b200 import infer
 
 RTOL = 5e-3  # tests/lp/test_dual_lp.py:27
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdlp_lp.npz"))
+
+
+def _check_lp(name, graph, upper, lower, states):
+  """The reference's known answer (tests/lp/test_dual_lp.py:123,221,304,395: the dual's primal
+  upper bound equals the LP optimum, rtol 5e-3) against the committed optimum of an independent
+  LP solver (tests/golden/sdlp_lp.npz, SciPy HiGHS on the program of pgmax/utils/primal_lp.py);
+  the relaxations are tight, so the decoding must also BE the LP's (integral) solution."""
+  objval = float(GOLD[f"{name}_objval"])
+  assert np.isclose(objval, upper, rtol=RTOL), (objval, upper)
+  assert np.isclose(objval, lower, rtol=RTOL), (objval, lower)
+  bounds = np.concatenate([[0], np.cumsum(graph.var_num_states)])
+  lp_states = np.array([int(np.argmax(GOLD[f"{name}_solution"][bounds[v] : bounds[v + 1]]))
+                        for v in range(len(bounds) - 1)])
+  np.testing.assert_array_equal(states, lp_states)
+
+
+def test_lp_fixture_is_what_the_solver_returns():
+  """tests/golden/sdlp_lp.npz == a fresh HiGHS solve of oracle/primal_lp_oracle.py's program."""
+  from oracle import primal_lp_oracle
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+  import make_sdlp_golden
+  for name, fg, evidence in make_sdlp_golden.cases():
+    _, objval = primal_lp_oracle.primal_lp_solver(fg, evidence)
+    assert np.isclose(objval, float(GOLD[f"{name}_objval"]), rtol=1e-9, atol=1e-9), name
 
 
 def _bounds(graph, arrays, msgs):
@@ -43,9 +71,10 @@ def test_dual_bounds_meet_on_tight_ising(seed, temp):
   graph = bp_oracle.graph_from_context(bp.context)
   msgs, objvals = sdlp_oracle.run_with_objvals(
       graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, temp, 3000)
-  upper, lower, _ = _bounds(graph, arrays, msgs)
+  upper, lower, states = _bounds(graph, arrays, msgs)
   assert np.isclose(lower, upper, rtol=RTOL)
   assert objvals[-1] <= objvals[0]
+  _check_lp(f"ising_{seed}", graph, upper, lower, states)
 
 
 def test_line_sparsification_with_or_factors():
@@ -58,6 +87,7 @@ def test_line_sparsification_with_or_factors():
   upper, lower, states = _bounds(graph, arrays, msgs)
   assert states[:20].sum() == (20 + 3) // 3
   assert np.isclose(lower, upper, rtol=RTOL)
+  _check_lp("line_0", graph, upper, lower, states)
 
 
 @pytest.mark.parametrize("kind", ["or", "and", "pool"])
@@ -125,6 +155,7 @@ def test_and_factors_rows_of_ones(seed):
   upper, lower, states = _bounds(graph, arrays, msgs)
   np.testing.assert_array_equal(states[50:], truth)
   assert np.isclose(lower, upper, rtol=RTOL)
+  _check_lp(f"and_{seed}", graph, upper, lower, states)
 
 
 @pytest.mark.parametrize("seed", [0, 1])
@@ -142,3 +173,4 @@ def test_pool_factor_hierarchy(seed):
   upper, lower, states = _bounds(graph, arrays, msgs)
   assert states.sum() == 4  # n_layers
   assert np.isclose(lower, upper, rtol=RTOL)
+  _check_lp(f"pool_{seed}", graph, upper, lower, states)
