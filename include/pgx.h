@@ -322,6 +322,25 @@ const char* pgx_last_error(void);
 /* Library / build information: "pgx <version> sm_100a ..." */
 const char* pgx_build_info(void);
 
+/* ---- Reverse mode through bp.run ---------------------------------------------------------------
+ *
+ * What jax.grad gives the reference (pgmax/infer/bp.py:98 @jax.checkpoint on the update;
+ * examples/grid_mrf.ipynb cells 15-16: value_and_grad of a loss of the marginals with respect to
+ * the log potentials): the vector-Jacobian product of
+ *     ftov_out = run(log_potentials, evidence, ftov_in; num_iters, damping, temperature)
+ * at the cotangent g_ftov_out [batch, E_s].  Sum-product only (temperature > 0), graphs of
+ * EnumFactors with at most 64 edge-states per factor; PGX_ERR_UNSUPPORTED otherwise.  Outputs (any
+ * may be NULL): g_lp_out [batch, C] if lp_batched else [C] (summed over the batch), g_ev_out
+ * likewise with V_s, g_ftov_in_out likewise with E_s.  The iterations are re-run keeping every
+ * iterate ((num_iters + 1) x batch x E_s floats of scratch); synchronises `stream` before
+ * returning. */
+int pgx_bp_run_vjp(pgx_plan* plan, void* stream, int64_t batch,
+                   const float* log_potentials, int lp_batched,
+                   const float* evidence, int ev_batched,
+                   const float* ftov_in, int msgs_batched,
+                   const float* g_ftov_out, int32_t num_iters, float damping, float temperature,
+                   float* g_lp_out, float* g_ev_out, float* g_ftov_in_out);
+
 /* ---- Row strips of ONE 2-D lattice across the GPUs of a box ----------------------------------
  *
  * BASELINE.json configs[4] / SURVEY.md 8(e) row 2 (the reference has no multi-GPU path; the graph

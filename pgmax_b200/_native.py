@@ -52,6 +52,7 @@ EXPORTED_SYMBOLS = (
     "pgx_plan_profile_read",
     "pgx_last_error",
     "pgx_build_info",
+    "pgx_bp_run_vjp",
     "pgx_nccl_unique_id",
     "pgx_strip_create",
     "pgx_strip_destroy",
@@ -206,6 +207,9 @@ def load() -> ctypes.CDLL:
   lib.pgx_plan_profile_read.argtypes = [vp, ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(ctypes.c_char_p)]
   lib.pgx_plan_profile_read.restype = ctypes.c_int
+  lib.pgx_bp_run_vjp.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp, i32, f32, f32,
+                                 vp, vp, vp]
+  lib.pgx_bp_run_vjp.restype = ctypes.c_int
   lib.pgx_nccl_unique_id.argtypes = [vp]
   lib.pgx_nccl_unique_id.restype = ctypes.c_int
   lib.pgx_strip_create.argtypes = [i64, i64, ctypes.c_int, ctypes.c_int, vp, ctypes.POINTER(vp)]
@@ -471,6 +475,13 @@ class Plan:
     check(self._lib.pgx_bp_run_flags(self.handle, stream, batch, lp, int(lp_batched), ev, int(ev_batched),
                                      msgs_in, int(msgs_batched), msgs_out, deltas, num_iters,
                                      damping, temperature, int(flags)))
+
+  def bp_run_vjp(self, stream: int, batch: int, lp: int, lp_batched: bool, ev: int, ev_batched: bool,
+                 msgs_in: Optional[int], msgs_batched: bool, g_out: int, num_iters: int, damping: float,
+                 temperature: float, g_lp: Optional[int], g_ev: Optional[int], g_msgs_in: Optional[int]) -> None:
+    """Vector-Jacobian product of bp_run at the cotangent g_out of the final messages."""
+    check(self._lib.pgx_bp_run_vjp(self.handle, stream, batch, lp, int(lp_batched), ev, int(ev_batched), msgs_in,
+                                   int(msgs_batched), g_out, num_iters, damping, temperature, g_lp, g_ev, g_msgs_in))
 
   def bp_step(self, stream: int, lp: int, ev: int, msgs_in: int, msgs_out: int, damping: float,
               temperature: float, num_iters: int = 1) -> None:

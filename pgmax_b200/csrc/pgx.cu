@@ -2581,3 +2581,4 @@ int pgx_infer_host(pgx_plan* plan, void* stream, int64_t batch, const float* lp_
 
 #include "pgx_sdlp.cuh"
 #include "pgx_strip.cuh"
+#include "pgx_vjp.cuh"

@@ -33,3 +33,4 @@
 #include "kernels/logical.cuh"
 #include "kernels/decode_energy.cuh"
 #include "kernels/sdlp.cuh"
+#include "kernels/vjp.cuh"

@@ -5,6 +5,7 @@ the reference (pgmax/infer/__init__.py:34-40): "bp" is the B200 hot path, "sdlp"
 the smooth dual LP-MAP solver on the same plan and kernels.
 """
 
+from pgmax_b200.infer import grad
 from pgmax_b200.infer.bp import BeliefPropagation
 from pgmax_b200.infer.bp import BP
 from pgmax_b200.infer.bp import get_marginals
