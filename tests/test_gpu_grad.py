@@ -74,7 +74,7 @@ def test_value_and_grad_of_the_grid_mrf_loss(damping):
   flat = lambda ms: np.concatenate([np.tile(m.reshape(-1), len(g.variables_for_factors)) for g, m in zip(groups, ms)])
   with bp_oracle.precision(np.float64):
     want = _oracle_loss(graph, flat(mats), evidence.astype(np.float64), targets, iters, damping, ns)
-    assert abs(float(loss) - want) < 1e-5
+    assert abs(float(loss.detach()) - want) < 1e-5
     h = 1e-4
     checked = 0
     for g_idx in range(len(groups)):
