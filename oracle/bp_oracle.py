@@ -111,7 +111,7 @@ def graph_from_flat(flat) -> OracleGraph:
   block descriptors into the reference's per-row arrays (pgmax/factor/enum.py:364-394)."""
   edge_ns = np.asarray(flat.edge_num_states, dtype=np.int64)
   edge_vs = np.asarray(flat.edge_var_start, dtype=np.int64)
-  edge_msg_start = np.cumsum(edge_ns) - edge_ns
+  edge_msg_start = np.concatenate([np.cumsum(edge_ns) - edge_ns, [int(edge_ns.sum())]])
   num_es = int(edge_ns.sum())
   edge_of_es = np.repeat(np.arange(edge_ns.shape[0]), edge_ns)
   vs_of_es = edge_vs[edge_of_es] + (np.arange(num_es) - edge_msg_start[edge_of_es])
@@ -139,14 +139,41 @@ def graph_from_flat(flat) -> OracleGraph:
       num_val_configs=int(flat.num_potentials),
       num_factors=int(sum(b.num_factors for b in flat.enum_blocks)),
   )
+  # OR / AND / Pool factors (FlatLogical, global message indices): their message slices follow
+  # the Enum slice in type order; a factor's edges are contiguous (parents, then the child)
+  enum_edges = int(sum(b.num_factors * np.asarray(b.factor_configs).shape[1] for b in flat.enum_blocks))
+  msgs_range = {ENUM: (0, int(edge_msg_start[enum_edges]) if enum_edges < edge_ns.shape[0] else num_es)}
+  args = {ENUM: enum_args}
+  first_edge, start = enum_edges, msgs_range[ENUM][1]
+  for name, ft in (("or_factors", OR), ("and_factors", AND), ("pool_factors", POOL)):
+    lg = getattr(flat, name, None)
+    if lg is None or lg.num_factors == 0:
+      msgs_range[ft], args[ft] = (start, start), {}
+      continue
+    pf = np.asarray(lg.parents_factor, dtype=np.int64)
+    n_edges = int(pf.shape[0]) + lg.num_factors
+    end = int(edge_msg_start[first_edge + n_edges]) if first_edge + n_edges < edge_ns.shape[0] else num_es
+    msgs_range[ft] = (start, end)
+    counts = np.bincount(pf, minlength=lg.num_factors) + 1
+    factor_of_edge[first_edge : first_edge + n_edges] = factor_shift + np.repeat(np.arange(lg.num_factors), counts)
+    factor_shift += lg.num_factors
+    parents = np.stack([pf, np.asarray(lg.parents_msg, dtype=np.int64) - start], axis=1)
+    children = np.asarray(lg.children_msg, dtype=np.int64) - start
+    if ft == POOL:
+      args[ft] = dict(pool_choices_factor_indices=parents[:, 0], pool_choices_msg_indices=parents[:, 1],
+                      pool_indicators_edge_states=children)
+    else:
+      args[ft] = dict(parents_factor_indices=parents[:, 0], parents_msg_indices=parents[:, 1],
+                      children_edge_states=children, edge_states_offset=1 if ft == OR else -1)
+    first_edge, start = first_edge + n_edges, end
   return OracleGraph(
       var_states_for_edge_states=vs_of_es,
       edge_indices_for_edge_states=edge_of_es,
       num_edges=int(edge_ns.shape[0]),
       num_var_states=int(np.asarray(flat.var_num_states, dtype=np.int64).sum()),
-      msgs_range={ENUM: (0, num_es), OR: (0, 0), AND: (0, 0), POOL: (0, 0)},
+      msgs_range=msgs_range,
       potentials_range={ENUM: (0, int(flat.num_potentials)), OR: (0, 0), AND: (0, 0), POOL: (0, 0)},
-      inference_arguments={ENUM: enum_args, OR: {}, AND: {}, POOL: {}},
+      inference_arguments=args,
       var_num_states=np.asarray(flat.var_num_states, dtype=np.int64),
       factor_indices_for_edge_states=factor_of_edge[edge_of_es],
       num_factors=factor_shift,

@@ -272,16 +272,33 @@ class FlatEnumBlock:
 
 
 @dataclasses.dataclass
+class FlatLogical:
+  """One pgx_logical_desc in host arrays: the OR, AND or Pool factors of a graph
+  (pgmax/factor/logical.py:264-291, pool.py:168-180).  Message indices are GLOBAL."""
+
+  parents_factor: np.ndarray  # [P] factor of every parent / pool choice, ascending
+  parents_msg: np.ndarray     # [P] message index of the wiring's state (state 0; state 1 for AND)
+  children_msg: np.ndarray    # [F] same for the child / pool indicator
+
+  @property
+  def num_factors(self) -> int:
+    return int(np.asarray(self.children_msg).shape[0])
+
+
+@dataclasses.dataclass
 class FlatGraph:
   """A compiled factor graph as the flat arrays of pgx_graph_desc,
-  for graphs generated directly in array form (no per-factor Python objects).
-  Only EnumFactor blocks; logical / pool factors go through FactorGraphState."""
+  for graphs generated or partitioned directly in array form (no per-factor Python objects).
+  Edges are ordered by factor type (Enum, OR, AND, Pool), as in the reference."""
 
   var_num_states: np.ndarray   # [num_vars]
   edge_var_start: np.ndarray   # [num_edges] var-state index of the edge's state 0
   edge_num_states: np.ndarray  # [num_edges]
   num_potentials: int
   enum_blocks: List[FlatEnumBlock]
+  or_factors: Optional[FlatLogical] = None
+  and_factors: Optional[FlatLogical] = None
+  pool_factors: Optional[FlatLogical] = None
 
 
 class Plan:
@@ -324,9 +341,15 @@ class Plan:
     desc.num_enum_blocks = len(flat.enum_blocks)
     desc.enum_blocks = blocks
     for name in ("or_factors", "and_factors", "pool_factors"):
-      empty = LogicalDescC()
-      empty.edge_states_offset = -1 if name == "and_factors" else 1
-      setattr(desc, name, empty)
+      d = LogicalDescC()
+      d.edge_states_offset = -1 if name == "and_factors" else 1
+      lg = getattr(flat, name)
+      if lg is not None and lg.num_factors:
+        pf, pm, cm = _i32(lg.parents_factor), _i32(lg.parents_msg), _i32(lg.children_msg)
+        keep.extend([pf, pm, cm])
+        d.num_factors, d.num_parents = int(cm.shape[0]), int(pf.shape[0])
+        d.parents_factor, d.parents_msg, d.children_msg = _ptr(pf), _ptr(pm), _ptr(cm)
+      setattr(desc, name, d)
 
   @staticmethod
   def _fill_from_state(desc, keep, fg_state):

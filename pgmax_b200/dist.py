@@ -11,7 +11,7 @@ CPU tests).  Two modes, as the north-star names them:
   graph of a rank directly in array form (no per-factor Python objects: the 8192^2
   torus has 134 M factors) and ``StripRunner`` runs BP with ONE halo exchange per
   iteration;
-* any other single graph of EnumFactors is cut by factors: ``partition_flat`` /
+* any other single graph (EnumFactors, OR, AND, Pool) is cut by factors: ``partition_flat`` /
   ``PartitionRunner`` (end of this file), one all-reduce of the shared variables'
   partial sums per iteration.
 
@@ -329,24 +329,36 @@ class StripRunner:
 # general partition of one graph of EnumFactors
 # ----------------------------------------------------------------------------------------
 def flat_from_state(fg_state) -> _native.FlatGraph:
-  """FlatGraph of a compiled FactorGraphState that holds EnumFactors only (any arity, ragged
-  numbers of states); graphs with OR / AND / Pool factors are not partitioned yet."""
+  """FlatGraph of a compiled FactorGraphState: EnumFactors of any arity (ragged numbers of
+  states), OR, AND and Pool factors - the arrays Plan builds its pgx_graph_desc from."""
   from pgmax_b200 import factor  # pylint: disable=g-import-not-at-top
 
-  for ft in (factor.ORFactor, factor.ANDFactor, factor.PoolFactor):
-    if fg_state.wiring[ft].num_edges:
-      raise NotImplementedError("partition_flat covers graphs of EnumFactors only")
-  w = fg_state.wiring[factor.EnumFactor]
+  wirings = [fg_state.wiring[ft] for ft in factor.FACTOR_TYPES]
   var_states = np.concatenate([vg.num_states.reshape(-1) for vg in fg_state.variable_groups]
                               + [np.empty((0,), dtype=np.int64)])
+  ranges = fg_state.factor_type_to_msgs_range
+
+  def logical(ft, parents, children):
+    if children.shape[0] == 0:
+      return None
+    start = ranges[ft][0]
+    return _native.FlatLogical(parents_factor=np.asarray(parents[:, 0], dtype=np.int64),
+                               parents_msg=np.asarray(parents[:, 1], dtype=np.int64) + start,
+                               children_msg=np.asarray(children, dtype=np.int64) + start)
+
+  w = fg_state.wiring[factor.EnumFactor]
+  w_or, w_and, w_pool = (fg_state.wiring[ft] for ft in (factor.ORFactor, factor.ANDFactor, factor.PoolFactor))
   return _native.FlatGraph(
       var_num_states=var_states.astype(np.int32),
-      edge_var_start=np.asarray(w.edge_var_start, dtype=np.int32),
-      edge_num_states=np.asarray(w.edge_num_states, dtype=np.int32),
+      edge_var_start=np.concatenate([np.asarray(x.edge_var_start, dtype=np.int64) for x in wirings]).astype(np.int32),
+      edge_num_states=np.concatenate([np.asarray(x.edge_num_states, dtype=np.int64) for x in wirings]).astype(np.int32),
       num_potentials=int(fg_state.log_potentials.shape[0]),
       enum_blocks=[_native.FlatEnumBlock(num_factors=b.num_factors, factor_configs=np.asarray(b.factor_configs),
                                          first_edge=b.first_edge, first_potential=b.first_config)
-                   for b in w.blocks])
+                   for b in w.blocks],
+      or_factors=logical(factor.ORFactor, w_or.parents_edge_states, w_or.children_edge_states),
+      and_factors=logical(factor.ANDFactor, w_and.parents_edge_states, w_and.children_edge_states),
+      pool_factors=logical(factor.PoolFactor, w_pool.pool_choices_edge_states, w_pool.pool_indicators_edge_states))
 
 
 @dataclasses.dataclass
@@ -367,11 +379,41 @@ class GraphPart:
   num_shared: int               # length of the exchange vector (var-states of ALL shared variables)
 
 
-def _block_ranges(flat: _native.FlatGraph, world: int, rank: int):
-  """Per block: (factor lo, factor hi) of this rank.  The factors of all blocks, in block order,
+_LOGICAL_FIELDS = (("or_factors", 0), ("and_factors", 1), ("pool_factors", 0))  # (name, state the wiring points at)
+
+
+def _segments(flat: _native.FlatGraph):
+  """The factors of the graph as segments in message order: one per enum block, then the OR, AND
+  and Pool factors.  Per segment: (kind, factor count, first-edge offsets [count + 1])."""
+  edge_ns = np.asarray(flat.edge_num_states, dtype=np.int64)
+  edge_msg_start = np.cumsum(edge_ns) - edge_ns
+  out = []
+  for b in flat.enum_blocks:
+    arity = int(np.asarray(b.factor_configs).shape[1])
+    out.append(("enum", int(b.num_factors), b.first_edge + arity * np.arange(b.num_factors + 1, dtype=np.int64), b))
+  first_edge = int(sum(s[1] * np.asarray(s[3].factor_configs).shape[1] for s in out))
+  for name, rel in _LOGICAL_FIELDS:
+    lg = getattr(flat, name, None)
+    if lg is None or lg.num_factors == 0:
+      continue
+    pf = np.asarray(lg.parents_factor, dtype=np.int64)
+    counts = np.bincount(pf, minlength=lg.num_factors) + 1  # parents + the child
+    starts = first_edge + np.concatenate([[0], np.cumsum(counts)])
+    # the reference's layout: a factor's edges are contiguous, parents in order, child last
+    parent_edge = np.repeat(starts[:-1], counts - 1) + (np.arange(pf.shape[0]) - np.repeat(np.cumsum(counts - 1) - (counts - 1), counts - 1))
+    if (np.any(np.diff(pf) < 0) or np.any(edge_msg_start[parent_edge] + rel != np.asarray(lg.parents_msg))
+        or np.any(edge_msg_start[starts[1:] - 1] + rel != np.asarray(lg.children_msg))):
+      raise NotImplementedError(f"{name}: the edges of a factor are not contiguous (parents, then the child)")
+    out.append((name, lg.num_factors, starts, lg))
+    first_edge = int(starts[-1])
+  return out
+
+
+def _segment_ranges(segments, world: int, rank: int):
+  """Per segment: (factor lo, factor hi) of this rank.  The factors of all segments, in order,
   are cut into `world` contiguous balanced ranges (graphs made of many small factor groups are
-  balanced too); a block's range is its intersection with the rank's range."""
-  counts = [int(b.num_factors) for b in flat.enum_blocks]
+  balanced too); a segment's range is its intersection with the rank's range."""
+  counts = [s[1] for s in segments]
   lo, hi = shard_bounds(sum(counts), world, rank)
   out, first = [], 0
   for n in counts:
@@ -388,13 +430,12 @@ def partition_flat(flat: _native.FlatGraph, world: int, rank: int) -> GraphPart:
   edge_ns = np.asarray(flat.edge_num_states, dtype=np.int64)
   edge_var = np.searchsorted(var_start, edge_vs, side="right") - 1
   edge_msg_start = np.cumsum(edge_ns) - edge_ns
+  segments = _segments(flat)
 
   def edges_of(r):
-    """Global edge ids of rank r, block by block (ascending)."""
-    parts = []
-    for b, (lo, hi) in zip(flat.enum_blocks, _block_ranges(flat, world, r)):
-      arity = int(np.asarray(b.factor_configs).shape[1])
-      parts.append(np.arange(b.first_edge + lo * arity, b.first_edge + hi * arity, dtype=np.int64))
+    """Global edge ids of rank r, segment by segment (ascending)."""
+    parts = [np.arange(seg[2][lo], seg[2][hi], dtype=np.int64)
+             for seg, (lo, hi) in zip(segments, _segment_ranges(segments, world, r))]
     return np.concatenate(parts) if parts else np.zeros((0,), dtype=np.int64)
 
   touched = [np.unique(edge_var[edges_of(r)]) for r in range(world)]
@@ -414,18 +455,6 @@ def partition_flat(flat: _native.FlatGraph, world: int, rank: int) -> GraphPart:
   # state 0 of an edge always sits at its variable's first state in this layout
   local_edge_vs = local_var_start[local_of_var[edge_var[my_edges]]] + (edge_vs[my_edges] - var_start[edge_var[my_edges]])
 
-  blocks, pot_parts, first_edge, first_pot = [], [], 0, 0
-  for b, (lo, hi) in zip(flat.enum_blocks, _block_ranges(flat, world, rank)):
-    cfg = np.asarray(b.factor_configs)
-    k, arity = int(cfg.shape[0]), int(cfg.shape[1])
-    if hi > lo:
-      blocks.append(_native.FlatEnumBlock(num_factors=hi - lo, factor_configs=cfg, first_edge=first_edge,
-                                          first_potential=first_pot))
-      pot_parts.append(np.arange(b.first_potential + lo * k, b.first_potential + hi * k, dtype=np.int64))
-      first_edge += (hi - lo) * arity
-      first_pot += (hi - lo) * k
-  potential_index = np.concatenate(pot_parts) if pot_parts else np.zeros((0,), dtype=np.int64)
-
   def expand(starts, sizes):
     """Concatenation of arange(start, start + size) for every (start, size)."""
     total = int(sizes.sum())
@@ -434,7 +463,28 @@ def partition_flat(flat: _native.FlatGraph, world: int, rank: int) -> GraphPart:
     offs = np.arange(total) - np.repeat(np.cumsum(sizes) - sizes, sizes)
     return np.repeat(starts, sizes) + offs
 
-  msg_index = expand(edge_msg_start[my_edges], edge_ns[my_edges])
+  msg_index = expand(edge_msg_start[my_edges], edge_ns[my_edges])   # ascending
+  blocks, pot_parts, logical, first_edge, first_pot = [], [], {}, 0, 0
+  for seg, (lo, hi) in zip(segments, _segment_ranges(segments, world, rank)):
+    kind, _, starts, obj = seg
+    if hi <= lo:
+      continue
+    if kind == "enum":
+      cfg = np.asarray(obj.factor_configs)
+      k, arity = int(cfg.shape[0]), int(cfg.shape[1])
+      blocks.append(_native.FlatEnumBlock(num_factors=hi - lo, factor_configs=cfg, first_edge=first_edge,
+                                          first_potential=first_pot))
+      pot_parts.append(np.arange(obj.first_potential + lo * k, obj.first_potential + hi * k, dtype=np.int64))
+      first_pot += (hi - lo) * k
+    else:
+      pf = np.asarray(obj.parents_factor, dtype=np.int64)
+      sel = (pf >= lo) & (pf < hi)
+      to_local = lambda g: np.searchsorted(msg_index, np.asarray(g, dtype=np.int64))
+      logical[kind] = _native.FlatLogical(parents_factor=pf[sel] - lo,
+                                          parents_msg=to_local(np.asarray(obj.parents_msg)[sel]),
+                                          children_msg=to_local(np.asarray(obj.children_msg)[lo:hi]))
+    first_edge += int(starts[hi] - starts[lo])
+  potential_index = np.concatenate(pot_parts) if pot_parts else np.zeros((0,), dtype=np.int64)
   var_state_index = expand(var_start[my_vars], local_ns)
   mine_shared = shared_vars[np.isin(shared_vars, my_vars)]
   pos = np.searchsorted(shared_vars, mine_shared)
@@ -443,7 +493,8 @@ def partition_flat(flat: _native.FlatGraph, world: int, rank: int) -> GraphPart:
   local_flat = _native.FlatGraph(
       var_num_states=local_ns.astype(np.int32), edge_var_start=local_edge_vs.astype(np.int32),
       edge_num_states=edge_ns[my_edges].astype(np.int32), num_potentials=int(potential_index.shape[0]),
-      enum_blocks=blocks)
+      enum_blocks=blocks, or_factors=logical.get("or_factors"), and_factors=logical.get("and_factors"),
+      pool_factors=logical.get("pool_factors"))
   return GraphPart(rank=rank, world=world, flat=local_flat, potential_index=potential_index, msg_index=msg_index,
                    var_state_index=var_state_index, shared_local_vs=shared_local_vs, shared_slot=shared_slot,
                    num_shared=int(shared_ns.sum()))

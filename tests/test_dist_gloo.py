@@ -125,7 +125,16 @@ def test_batch_sharding_needs_no_collective_and_gathers_in_order():
 
 # ---- general factor partition (pdist.partition_flat / PartitionRunner) ----------------------
 def _general_graph(which):
-  """(FactorGraph, evidence updates) of an irregular EnumFactor graph."""
+  """(FactorGraph, evidence updates) of an irregular graph: EnumFactors ("cut", "ragged"), a random
+  network of OR + AND factors on shared leaves ("logical"), a hierarchy of PoolFactors ("pool")."""
+  if which == "logical":
+    import test_gpu_logical_pull
+    fg, groups = test_gpu_logical_pull.random_logical_network(0)
+    rng = np.random.default_rng(2)
+    return fg, {g: rng.gumbel(size=g.shape + (2,)) * 2.0 for g in groups.values()}
+  if which == "pool":
+    fg, variables = models.sdlp_pool_model()
+    return fg, {variables: np.random.default_rng(4).gumbel(size=(variables.shape[0], 2))}
   if which == "cut":
     fg, bp_state, grid_vars, additional_vars = models.cut_model()
     return fg, None
@@ -172,7 +181,8 @@ def _partition_worker(rank, world, port, which, temperature, iters, out):
 
 
 @pytest.mark.parametrize("world,which,temperature", [(2, "cut", 0.0), (3, "cut", 1.0), (2, "ragged", 1.0),
-                                                      (3, "ragged", 0.0)])
+                                                      (3, "ragged", 0.0), (2, "logical", 0.0), (3, "logical", 0.0),
+                                                      (2, "pool", 0.0), (3, "pool", 0.8)])
 def test_factor_partition_matches_single_graph(world, which, temperature):
   manager = mp.Manager()
   out = manager.dict()

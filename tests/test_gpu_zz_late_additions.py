@@ -61,7 +61,7 @@ def test_rbm_large_reference_decodings(n_units):
     np.testing.assert_array_equal(states[visible], gold[f"visible_cpu_{n_units}_{idx}"])
 
 
-def _partition_worker(rank, world, port, temperature, iters, out):
+def _partition_worker(rank, world, port, temperature, iters, out, which="cut"):
   import os
   import torch
   import torch.distributed as dist
@@ -72,9 +72,17 @@ def _partition_worker(rank, world, port, temperature, iters, out):
   torch.cuda.set_device(rank)
   dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
   try:
-    fg, bp_state, _, _ = models.cut_model()
-    bp = infer.BP(bp_state, temperature=temperature)
-    arrays = bp.init()
+    if which == "cut":
+      fg, bp_state, _, _ = models.cut_model()
+      bp = infer.BP(bp_state, temperature=temperature)
+      arrays = bp.init()
+    else:  # OR + AND network on shared leaves (tests/test_gpu_logical_pull.py)
+      import test_gpu_logical_pull
+      fg, groups = test_gpu_logical_pull.random_logical_network(1)
+      bp_state = fg.bp_state
+      bp = infer.BP(bp_state, temperature=temperature)
+      rng = np.random.default_rng(2)
+      arrays = bp.init(evidence_updates={g: rng.gumbel(size=g.shape + (2,)) * 2.0 for g in groups.values()})
     flat = pdist.flat_from_state(bp_state.fg_state)
     part = pdist.partition_flat(flat, world, rank)
     dev = f"cuda:{rank}"
@@ -108,6 +116,10 @@ def test_factor_partition_two_gpus_match_single_graph(temperature):
   out = mp.Manager().dict()
   mp.spawn(_partition_worker, args=(2, port, temperature, 10, out), nprocs=2, join=True)
   assert max(out.values()) <= 1e-5, dict(out)
+  if temperature == 0.0:  # OR / AND factors cut across the two ranks
+    out = mp.Manager().dict()
+    mp.spawn(_partition_worker, args=(2, port, temperature, 10, out, "logical"), nprocs=2, join=True)
+    assert max(out.values()) <= 2e-5, dict(out)
 
 
 @pytest.mark.parametrize("temperature", [0.0])
