@@ -1,24 +1,31 @@
 #!/usr/bin/env bash
-# Runs ON THE GPU BOX (gpurun -- 'bash profiles/final.sh <tag>'): the whole GPU test suite, the
-# bench line of every workload (the default one with its CPU arm), smoke(), and the ncu launch
-# lists of the workloads whose launch sequence changed.  Ordered by importance: the box time
-# may run out before the last steps.
+# Runs ON THE GPU BOX (gpurun -- 'bash profiles/final.sh <tag>'): the whole GPU test suite, the default
+# bench line (all five configurations + generic-path workloads + the CPU arm), smoke(), and one
+# `ncu --set full` capture of the dominant kernel of every configuration (named so that
+# profiles/make_traffic.py can turn them into profiles/r02_traffic.json) plus launch lists.
+# Ordered by importance: the box time may run out before the last steps.
 set -u
-tag="${1:-r01_o}"
+tag="${1:-r02_z}"
 out=gpurun_out
 mkdir -p $out
 t0=$(date +%s)
 stamp() { echo "[$(( $(date +%s) - t0 )) s] $*"; }
-timeout 400 python -m pytest tests -m gpu -q 2>&1 | tail -5 | tee $out/${tag}_pytest_gpu.txt
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -5 | tee $out/${tag}_pytest_gpu.txt
 stamp pytest
-timeout 200 python bench.py > $out/${tag}_bench_rbm.json 2> $out/${tag}_bench_rbm.err; stamp "bench rbm"; head -c 600 $out/${tag}_bench_rbm.json; echo
-for w in deconv rcn ising50; do
-  timeout 200 python bench.py --no-cpu-baseline --workload $w > $out/${tag}_bench_$w.json 2> /dev/null; stamp "bench $w"; head -c 300 $out/${tag}_bench_$w.json; echo
-done
+timeout 400 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; stamp "bench"; head -c 400 $out/${tag}_bench.json; echo
 timeout 100 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2; stamp smoke
-B="--steps 1 --warmup 1 --no-cpu-baseline"
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_deconv.csv python bench.py $B --workload deconv > /dev/null 2>&1; stamp "launches deconv"
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file $out/${tag}_launches_rcn.csv python bench.py $B --workload rcn > /dev/null 2>&1; stamp "launches rcn"
-timeout 240 ncu --set full --clock-control none --import-source on --launch-skip 60 -c 14 -f -o $out/${tag}_deconv python bench.py $B --workload deconv > $out/${tag}_full_deconv.log 2>&1; stamp "full deconv"
-timeout 300 python bench.py --no-cpu-baseline --workload ising_big > $out/${tag}_bench_ising_big.json 2> /dev/null; stamp "bench ising_big"; head -c 300 $out/${tag}_bench_ising_big.json; echo
-ls -la $out | tail -12
+B="--steps 1 --warmup 1 --no-cpu-baseline --no-extras --no-graph"
+cap() {  # workload batch kernel-regex launch-skip extra-args
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:"$3" --launch-skip $4 -c 1 -f \
+    -o $out/${tag}_$1_b$2 python bench.py $B --workload $1 ${5:-} > $out/${tag}_$1_ncu.log 2>&1
+  stamp "full $1"
+}
+cap rbm 1024 k_enum_pw2_bip 20
+cap deconv 100 k_or_and_fused 10
+cap rcn 1 k_enum_big_maxprod_all 5
+cap ising_big 1 k_lattice_bin 3 "--iters 10 --strip-flags 1"
+for w in rbm deconv rcn; do
+  timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 40 -c 120 --csv \
+    --log-file $out/${tag}_launches_$w.csv python bench.py $B --workload $w > /dev/null 2>&1; stamp "launches $w"
+done
+ls -la $out | tail -16
