@@ -202,7 +202,11 @@ def strip_line_fields(n, iters, steps, world, ms, e2e_ms, rec):
   moved_iter = 9 * es    # binary-difference storage: 16 + 16 B messages, 32 B potentials, 8 B evidence per cell
   iter_s = ms * 1e-3 / steps / iters
   peak, peak_src = hbm_peak()
+  # DRAM bytes ncu measured for one launch over the whole torus (one GPU, same grid): only then
+  entry = traffic_entry("ising_big", "k_lattice_bin", 1, None) if (world == 1 and n == 8192) else None
   return {
+      "traffic": entry["bytes"] if entry else None,
+      "physical_frac": (entry["bytes"] / iter_s / 1e9 / peak) if entry else None,
       "value": es * iters * steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "ms_per_step": ms / steps,
       "iter_ms": iter_s * 1e3, "edge_states": es, "iters": iters,
       "frac": bytes_iter / iter_s / 1e9 / world / peak,
@@ -249,7 +253,8 @@ def run_ising_big(args):
                    "l2": "working set larger than L2" if 4 * f["edge_states"] > 126e6 else "L2-resident working set"},
         "e2e": f["e2e"], "gpu_launches": f["gpu_launches"], "clocks": rec["clocks"],
         "roofline": {"bound": "hbm", "achieved": f["algorithmic_bytes_per_iter_per_gpu"] / (f["iter_ms"] * 1e-3) / 1e9,
-                     "peak": f["peak"], "unit": "GB/s", "frac": f["frac"], "traffic": None,
+                     "peak": f["peak"], "unit": "GB/s", "frac": f["frac"], "traffic": f["traffic"],
+                     "physical_frac": f["physical_frac"],
                      "kernel": "k_lattice_bin (whole iteration incl. the halo exchange when N > 1), per GPU",
                      "algorithmic_bytes_per_launch": f["algorithmic_bytes_per_iter_per_gpu"], "peak_source": f["peak_source"],
                      "iter_ms": f["iter_ms"], "layout_frac": f["layout_frac"],
