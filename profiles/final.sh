@@ -10,10 +10,12 @@ out=gpurun_out
 mkdir -p $out
 t0=$(date +%s)
 stamp() { echo "[$(( $(date +%s) - t0 )) s] $*"; }
+if [ "${2:-all}" != "captures" ]; then
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -5 | tee $out/${tag}_pytest_gpu.txt
 stamp pytest
 timeout 400 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; stamp "bench"; head -c 400 $out/${tag}_bench.json; echo
 timeout 100 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2; stamp smoke
+fi
 B="--steps 1 --warmup 1 --no-cpu-baseline --no-extras --no-graph"
 cap() {  # workload batch kernel-regex launch-skip extra-args
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:"$3" --launch-skip $4 -c 1 -f \
@@ -28,4 +30,11 @@ for w in rbm deconv rcn; do
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 40 -c 120 --csv \
     --log-file $out/${tag}_launches_$w.csv python bench.py $B --workload $w > /dev/null 2>&1; stamp "launches $w"
 done
-ls -la $out | tail -16
+# gpurun copies at most 64 MiB back: the reports are summarised here and only the text travels
+python profiles/make_traffic.py $out/${tag}_*_b*.ncu-rep > $out/${tag}_traffic.log 2>&1; cp profiles/r02_traffic.json $out/r02_traffic.json
+for w in rbm_b1024 deconv_b100 rcn_b1 ising_big_b1; do
+  python profiles/summarize.py $out/${tag}_$w.ncu-rep > $out/${tag}_full_$w.txt 2>&1
+  python profiles/source_hot.py $out/${tag}_$w.ncu-rep 30 > $out/${tag}_source_$w.txt 2>&1
+done
+rm -f $out/${tag}_*.ncu-rep
+ls -la $out | tail -24
