@@ -22,7 +22,7 @@ cap() {  # workload batch kernel-regex launch-skip extra-args
     -o $out/${tag}_$1_b$2 python bench.py $B --workload $1 ${5:-} > $out/${tag}_$1_ncu.log 2>&1
   stamp "full $1"
 }
-cap rbm 1024 k_enum_pw2_bip 20
+cap rbm 1024 k_enum_pw2_bip 20 "--disable-paths 1024"  # one launch per iteration over the whole batch, as in bench.py's roofline pass
 cap deconv 100 k_or_and_fused 10
 cap rcn 1 k_enum_big_maxprod_all 5
 cap ising_big 1 k_lattice_bin 3 "--iters 10 --strip-flags 1"
@@ -33,7 +33,7 @@ done
 # gpurun copies at most 64 MiB back: the reports are summarised here and only the text travels
 python profiles/make_traffic.py $out/${tag}_*_b*.ncu-rep > $out/${tag}_traffic.log 2>&1; cp profiles/r02_traffic.json $out/r02_traffic.json
 for w in rbm_b1024 deconv_b100 rcn_b1 ising_big_b1; do
-  python profiles/summarize.py $out/${tag}_$w.ncu-rep > $out/${tag}_full_$w.txt 2>&1
+  python profiles/summarize.py $out/${tag}_$w.ncu-rep > $out/${tag}_$w.txt 2>&1
   python profiles/source_hot.py $out/${tag}_$w.ncu-rep 30 > $out/${tag}_source_$w.txt 2>&1
 done
 rm -f $out/${tag}_*.ncu-rep
