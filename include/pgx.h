@@ -153,6 +153,12 @@ int pgx_bp_run(pgx_plan* plan, void* stream, int64_t batch,
  * plan's previous run: per-run preprocessing of the potentials (the round-ordered copy of the
  * merged max-product launch) is reused instead of redone. */
 #define PGX_RUN_POTENTIALS_UNCHANGED 4u
+/* Leave the variable sums of the FINAL messages (= the beliefs) in the plan's workspace for
+ * pgx_decode_last_run: the fused decode then reads no message at all.  Honoured by the batched
+ * two-pass / single-pass / pull paths (pgx_decode_last_run fails for the others: decode from the
+ * messages then).  With PGX_RUN_SKIP_OUTPUT a run that left the sums does not write ftov_out. */
+#define PGX_RUN_FINAL_SUMS 8u
+#define PGX_RUN_SKIP_OUTPUT 16u
 int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch,
                      const float* log_potentials, int lp_batched,
                      const float* evidence, int ev_batched,
@@ -175,6 +181,11 @@ int pgx_decode(pgx_plan* plan, void* stream, int64_t batch,
                const float* evidence, int ev_batched,
                const float* ftov_msgs, int msgs_batched,
                int32_t* map_out, float* marginals_out, int32_t* tie_count_out);
+
+/* pgx_decode on the sums the last pgx_bp_run_flags(..., PGX_RUN_FINAL_SUMS) of this plan left behind
+ * (same outputs and rules as pgx_decode; PGX_ERR_INVALID if that run left none for `batch`). */
+int pgx_decode_last_run(pgx_plan* plan, void* stream, int64_t batch,
+                        int32_t* map_out, float* marginals_out, int32_t* tie_count_out);
 
 /* Energy of a decoding (replaces infer.compute_energy, pgmax/infer/energy.py:53-148, and the
  * per-type compute_energy of pgmax/factor/enum.py:276-323, logical.py:295-358, pool.py:184-239):

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "pgx_bp_run_flags",
     "pgx_beliefs",
     "pgx_decode",
+    "pgx_decode_last_run",
     "pgx_energy",
     "pgx_infer_host",
     "pgx_plan_set_factors",
@@ -169,6 +170,8 @@ def load() -> ctypes.CDLL:
   lib.pgx_beliefs.restype = ctypes.c_int
   lib.pgx_decode.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp, vp, vp]
   lib.pgx_decode.restype = ctypes.c_int
+  lib.pgx_decode_last_run.argtypes = [vp, vp, i64, vp, vp, vp]
+  lib.pgx_decode_last_run.restype = ctypes.c_int
   lib.pgx_energy.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp, ctypes.c_int, vp]
   lib.pgx_energy.restype = ctypes.c_int
   lib.pgx_infer_host.argtypes = [vp, vp, i64, vp, ctypes.c_int, vp, ctypes.c_int, vp,
@@ -490,7 +493,7 @@ class Plan:
 
   # The methods below take raw device pointers (ints) so that any owner of device
   # memory (torch tensors here) can call them.
-  RUN_INPUT_NORMALIZED, RUN_NO_GRAPH, RUN_POTENTIALS_UNCHANGED = 1, 2, 4
+  RUN_INPUT_NORMALIZED, RUN_NO_GRAPH, RUN_POTENTIALS_UNCHANGED, RUN_FINAL_SUMS, RUN_SKIP_OUTPUT = 1, 2, 4, 8, 16
 
   def bp_run(self, stream: int, batch: int, lp: int, lp_batched: bool, ev: int, ev_batched: bool,
              msgs_in: Optional[int], msgs_batched: bool, msgs_out: int, deltas: Optional[int],

@@ -55,6 +55,39 @@ k_decode(BatchMap mp, int64_t num_vars, int64_t num_var_states,
   if (ties != nullptr && ntie > 0) atomicAdd(ties + b, ntie);
 }
 
+// K6 from the variable sums a run left behind (PGX_RUN_FINAL_SUMS: S = evidence + final messages,
+// tile-blocked, i.e. the beliefs): the same arg-max / tie / softmax rules, no message is read.
+__global__ void __launch_bounds__(kThreads)
+k_decode_sums(BatchMap mp, int64_t num_vars, int64_t num_var_states, const int32_t* __restrict__ var_first_state,
+              const float* __restrict__ S, int32_t* __restrict__ map_out, float* __restrict__ marginals,
+              int32_t* __restrict__ ties) {
+  UnitLoop L = unit_loop(mp, num_vars);
+  if (!L.b_ok) return;
+  const int b = L.b;
+  const float* SL = S + lane_off(mp, num_var_states, b);
+  const int sh = mp.bx_log;
+  int ntie = 0;
+  for (int64_t var = L.u; var < L.u_end; var += L.step) {
+    const int64_t v0 = var_first_state[var], v1 = var_first_state[var + 1];
+    float best = -INFINITY, second = -INFINITY;
+    int arg = 0;
+    for (int64_t v = v0; v < v1; ++v) {
+      const float acc = SL[v << sh];
+      if (acc > best) { second = best; best = acc; arg = int(v - v0); }
+      else if (acc > second) second = acc;
+    }
+    if (map_out) map_out[int64_t(b) * num_vars + var] = arg;
+    if (v1 - v0 >= 2 && best == second) ++ntie;
+    if (marginals) {
+      float sum = 0.f;
+      for (int64_t v = v0; v < v1; ++v) sum += expf(SL[v << sh] - best);
+      const float lse = best + logf(sum);
+      for (int64_t v = v0; v < v1; ++v) marginals[int64_t(b) * num_var_states + v] = expf(SL[v << sh] - lse);
+    }
+  }
+  if (ties != nullptr && ntie > 0) atomicAdd(ties + b, ntie);
+}
+
 // ---------------------------------------------------------------------------
 // K7: energy of a decoding (pgmax/infer/energy.py:53-148 and the per-type compute_energy:
 // factor/enum.py:276-323, logical.py:295-358, pool.py:184-239).  One thread per (unit, sample),

@@ -277,10 +277,12 @@ struct pgx_plan {
     cudaGraphExec_t exec;  // null: seen once, not captured yet
     int64_t launches;      // kernels + copies one replay runs
     int64_t epoch;         // workspace generation the graph's internal pointers belong to
+    int64_t sums_batch;    // final_sums_batch the captured run leaves behind
   };
   int64_t ws_epoch = 0;    // bumped whenever a workspace buffer is (re)allocated: cached graphs go stale
   std::vector<RunGraph> run_graphs;
   cudaStream_t cap_stream = nullptr;
+  int64_t final_sums_batch = 0;  // batch whose FINAL variable sums (= beliefs) the last run left in ws.S (PGX_RUN_FINAL_SUMS)
   int64_t graph_launches = 0;
   bool graphs_enabled = true;
 };
@@ -1858,7 +1860,7 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     }
     plan->run_graphs.push_back(pgx_plan::RunGraph{log_potentials, evidence, ftov_in, ftov_out, deltas, batch, num_iters,
                                                   lp_batched, ev_batched, msgs_batched, damping, temperature, flags,
-                                                  plan->disabled_paths, plan->exact_order, nullptr, 0, 0});
+                                                  plan->disabled_paths, plan->exact_order, nullptr, 0, 0, 0});
     return bp_run_enqueue(plan, stream, batch, log_potentials, lp_batched, evidence, ev_batched, ftov_in, msgs_batched,
                           ftov_out, deltas, num_iters, damping, temperature, flags);
   }
@@ -1898,8 +1900,10 @@ int pgx_bp_run_flags(pgx_plan* plan, void* stream, int64_t batch, const float* l
     hit->exec = exec;
     hit->launches = captured;
     hit->epoch = epoch_now();
+    hit->sums_batch = plan->final_sums_batch;
   }
   PGX_CUDA(cudaGraphLaunch(hit->exec, st));
+  plan->final_sums_batch = hit->sums_batch;
   plan->launches += hit->launches;
   ++plan->graph_launches;
   return PGX_OK;
@@ -1912,7 +1916,7 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
   PGX_CHECK(batch >= 1 && batch < (1 << 24), "batch must be in [1, 2^24), got %lld", (long long)batch);
   PGX_CHECK(num_iters >= 1, "num_iters must be >= 1, got %d", num_iters);
   PGX_CHECK(temperature >= 0.f, "temperature must be >= 0");
-  PGX_CHECK(ftov_out != nullptr || plan->num_edge_states == 0, "ftov_out is null");
+  PGX_CHECK(ftov_out != nullptr || plan->num_edge_states == 0 || (flags & PGX_RUN_SKIP_OUTPUT), "ftov_out is null");
   PGX_CHECK(plan->num_var_states == 0 || evidence != nullptr, "evidence is null");
   PGX_CHECK(plan->num_potentials == 0 || log_potentials != nullptr, "log_potentials is null");
   int rc;
@@ -1920,6 +1924,7 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
   if ((rc = device_guard.enter(plan))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const pgx::BatchMap mp = make_map(batch);
+  plan->final_sums_batch = 0;
   PGX_CHECK(tiled_floats(mp, plan->num_edge_states) < (size_t(1) << 40), "workspace too large");
   const bool single = batch == 1;
   const bool evT = !single && ev_batched, lpT = !single && lp_batched;
@@ -2389,6 +2394,25 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
     nxt = (dst == bufA) ? bufB : bufA;
     cur = dst;
   }
+  // PGX_RUN_FINAL_SUMS: the variable sums of the FINAL messages - the beliefs - are left in the
+  // workspace for pgx_decode_last_run (batched two-pass / single-pass / pull paths; the others
+  // simply do not set final_sums_batch and the caller decodes from the messages)
+  plan->final_sums_batch = 0;
+  if ((flags & PGX_RUN_FINAL_SUMS) && !single && !lpull && !lattice) {
+    if (fused) {
+      pgx::k_var_reduce<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(
+          mp, Vs, Es, plan->part_rows, plan->d_vs_var, plan->d_var_first_state, plan->d_rest_ptr,
+          plan->d_rest_edge_msg, plan->d_part_first, plan->d_part_count, ev, cur, ws.part, ws.S);
+      if ((rc = check_launch(plan, "k_var_reduce"))) return rc;
+    } else {
+      pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(mp, Vs, Es, plan->d_vs_csr, plan->d_var_edge_msg,
+                                                                       ev, cur, ws.S, 0);
+      if ((rc = check_launch(plan, "k_var_sums"))) return rc;
+    }
+    plan->final_sums_batch = batch;
+    if (flags & PGX_RUN_SKIP_OUTPUT) return PGX_OK;  // the caller only wants the decoding
+  }
+  PGX_CHECK(ftov_out != nullptr, "ftov_out is null");
   if (lbin) {
     dim3 grid((unsigned)((Es / 2 + 31) / 32), (unsigned)((mp.batch + 31) / 32)), block(32, 8);
     pgx::k_expand_bin<<<grid, block, 0, st>>>(cur, Es / 2, 0, Es / 2, ftov_out, Es, 0, mp);
@@ -2450,6 +2474,23 @@ int pgx_decode(pgx_plan* plan, void* stream, int64_t batch, const float* evidenc
   if (!plan) return fail(PGX_ERR_INVALID, "null plan");
   return decode_impl(plan, static_cast<cudaStream_t>(stream), batch, evidence, ev_batched, ftov_msgs,
                      msgs_batched, nullptr, map_out, marginals_out, tie_count_out);
+}
+
+int pgx_decode_last_run(pgx_plan* plan, void* stream, int64_t batch, int32_t* map_out, float* marginals_out,
+                        int32_t* tie_count_out) {
+  if (!plan) return fail(PGX_ERR_INVALID, "null plan");
+  PGX_CHECK(plan->final_sums_batch == batch && batch >= 1,
+            "the last pgx_bp_run on this plan left no final sums for a batch of %lld (PGX_RUN_FINAL_SUMS)", (long long)batch);
+  int rc;
+  DeviceGuard device_guard;
+  if ((rc = device_guard.enter(plan))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tie_count_out) PGX_CUDA(cudaMemsetAsync(tie_count_out, 0, size_t(batch) * sizeof(int32_t), st));
+  if (plan->num_vars == 0) return PGX_OK;
+  const pgx::BatchMap mp = make_map(batch);
+  pgx::k_decode_sums<<<grid_for(plan, mp, plan->num_vars), pgx::kThreads, 0, st>>>(
+      mp, plan->num_vars, plan->num_var_states, plan->d_var_first_state, plan->ws.S, map_out, marginals_out, tie_count_out);
+  return check_launch(plan, "k_decode_sums");
 }
 
 int pgx_energy(pgx_plan* plan, void* stream, int64_t batch, const float* log_potentials, int lp_batched,
@@ -2554,14 +2595,22 @@ int pgx_infer_host(pgx_plan* plan, void* stream, int64_t batch, const float* lp_
   if (n_lp) PGX_CUDA(cudaMemcpyAsync(ws.h_lp, lp_h, size_t(n_lp) * 4, cudaMemcpyHostToDevice, st));
   if (n_ev) PGX_CUDA(cudaMemcpyAsync(ws.h_ev, ev_h, size_t(n_ev) * 4, cudaMemcpyHostToDevice, st));
   if (n_in) PGX_CUDA(cudaMemcpyAsync(ws.h_msgs_in, msgs_h, size_t(n_in) * 4, cudaMemcpyHostToDevice, st));
-  if ((rc = pgx_bp_run(plan, stream, batch, ws.h_lp, lp_batched, ws.h_ev, ev_batched,
-                       msgs_h ? ws.h_msgs_in : nullptr, msgs_batched, ws.h_msgs_out,
-                       deltas_h ? ws.h_deltas : nullptr, num_iters, damping, temperature)))
+  // the decoding comes from the variable sums of the final messages where the path leaves them
+  // (no second read of the messages); the messages themselves are only materialised in the ABI
+  // layout when the caller asks for them
+  const uint32_t flags = PGX_RUN_FINAL_SUMS | (msgs_out_h ? 0u : PGX_RUN_SKIP_OUTPUT);
+  if ((rc = pgx_bp_run_flags(plan, stream, batch, ws.h_lp, lp_batched, ws.h_ev, ev_batched,
+                             msgs_h ? ws.h_msgs_in : nullptr, msgs_batched, ws.h_msgs_out,
+                             deltas_h ? ws.h_deltas : nullptr, num_iters, damping, temperature, flags)))
     return rc;
   if (map_h || marg_h || ties_h) {
-    if ((rc = pgx_decode(plan, stream, batch, ws.h_ev, ev_batched, ws.h_msgs_out, 1, map_h ? ws.h_map : nullptr,
-                         marg_h ? ws.h_marg : nullptr, ties_h ? ws.h_ties : nullptr)))
-      return rc;
+    if (plan->final_sums_batch == batch)
+      rc = pgx_decode_last_run(plan, stream, batch, map_h ? ws.h_map : nullptr, marg_h ? ws.h_marg : nullptr,
+                               ties_h ? ws.h_ties : nullptr);
+    else
+      rc = pgx_decode(plan, stream, batch, ws.h_ev, ev_batched, ws.h_msgs_out, 1, map_h ? ws.h_map : nullptr,
+                      marg_h ? ws.h_marg : nullptr, ties_h ? ws.h_ties : nullptr);
+    if (rc) return rc;
   }
   if (map_h)
     PGX_CUDA(cudaMemcpyAsync(map_h, ws.h_map, size_t(plan->num_vars) * batch * 4, cudaMemcpyDeviceToHost, st));

@@ -333,6 +333,42 @@ def test_infer_host_end_to_end():
   np.testing.assert_allclose(res["marginals"], marg, atol=0)
 
 
+@pytest.mark.parametrize("temperature", [0.0, 1.0])
+def test_infer_host_decodes_from_the_final_variable_sums(temperature):
+  """pgx_infer_host without a message output (the benchmark's end-to-end call): the run leaves the
+  variable sums of the final messages in the workspace (PGX_RUN_FINAL_SUMS), the decode reads
+  those and the messages are never written in the ABI layout (PGX_RUN_SKIP_OUTPUT).  Generic
+  batched path: identical to decoding the run's messages (same serial sums); single-pass RBM path
+  (tree-order partial sums): identical MAP away from near-ties, marginals to 1e-5; one sample and
+  OR / AND graphs fall back to decoding from the messages."""
+  fg, variables, evidence = models.ising_model(n=10, batch=40)
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  arrays = bp.init(evidence_updates={variables: evidence})
+  for _ in range(3):  # direct, captured, replayed
+    res = bp.infer_host(arrays, num_iters=12, damping=0.5, marginals=True)
+    got = bp.run(arrays, num_iters=12, damping=0.5)
+    states, marg, ties = bp.context.decode(got, marginals=True)
+    np.testing.assert_array_equal(res["flat_map_states"], states)
+    np.testing.assert_array_equal(res["tie_counts"], ties)
+    np.testing.assert_array_equal(res["marginals"], marg)
+    assert res["ftov_msgs"] is None
+  bp, arrays = _small_rbm(9, 14, 70, temperature, scale=0.3)
+  assert bp.context.plan.has_fused_blocks
+  res = bp.infer_host(arrays, num_iters=10, damping=0.5, marginals=True)
+  got = bp.run(arrays, num_iters=10, damping=0.5, temperature=temperature)
+  states, marg, _ = bp.context.decode(got, marginals=True)
+  np.testing.assert_allclose(res["marginals"], marg, atol=1e-5)
+  beliefs = np.asarray(bp.context.flat_beliefs(got)).reshape(70, -1, 2)
+  clear = np.abs(beliefs[..., 0] - beliefs[..., 1]) > 1e-4
+  assert np.array_equal(res["flat_map_states"][clear], states[clear])
+  one, _, ev1 = models.ising_model(n=6)
+  bp1 = infer.BP(one.bp_state, temperature=temperature)
+  a1 = bp1.init(evidence_updates={_: ev1})
+  r1 = bp1.infer_host(a1, num_iters=8, damping=0.5)
+  s1, _, _ = bp1.context.decode(bp1.run(a1, num_iters=8, damping=0.5))
+  np.testing.assert_array_equal(r1["flat_map_states"], s1)
+
+
 def test_split_run_equals_single_run():
   """Resume contract: run(a)+run(b) == run(a+b) because NC is idempotent."""
   fg, variables, evidence = models.ising_model(n=8)
