@@ -526,6 +526,7 @@ def measure(args, name, dev, rank, world, local_rank, batch=None, iters=None, st
   bp.run(dev_arrays, num_iters=iters, damping=damping, temperature=T)
   torch.cuda.synchronize()
   n_prof, prof_ms, prof_name = plan.profile_read()
+  prof_grid = plan.dominant_grid  # CTAs of the launches just timed (later runs may use another launch shape)
   plan.profile_enable(False)
   checksum = float(out.ftov_msgs.float().abs().max().item())
 
@@ -561,7 +562,8 @@ def measure(args, name, dev, rank, world, local_rank, batch=None, iters=None, st
       parity = {"parity_max_abs": None, "parity_note": "check failed: " + repr(err)[-200:]}
   lp_batched = host.log_potentials.ndim == 2
   fused_run = plan.has_fused_blocks and not args.exact_order and batch > 16 and not lp_batched
-  return dict(wl=wl, plan=plan, ms=ms, e2e_ms=e2e_ms, launches=launches, graph_launches=graph_launches, clocks=clocks, n_prof=n_prof, prof_ms=prof_ms,
+  return dict(wl=wl, plan=plan, ms=ms, e2e_ms=e2e_ms, launches=launches, graph_launches=graph_launches, clocks=clocks,
+              prof_grid=prof_grid, n_prof=n_prof, prof_ms=prof_ms,
               prof_name=prof_name, checksum=checksum, batch=batch, iters=iters, es=es, steps=steps, warmup=warmup,
               h2d=4 * (h_lp.numel() + h_ev.numel()), d2h=4 * (h_map.numel() + h_ties.numel()), parity=parity,
               lp_batched=lp_batched, fused_run=fused_run, damping=damping, temperature=T)
@@ -593,7 +595,7 @@ def roofline_of(name, rec, ms):
   layout_bytes = bytes_iter - saved
   iter_ms = ms / steps / iters
   iter_gbs = bytes_iter / (iter_ms * 1e-3) / 1e9
-  entry = traffic_entry(name, prof_name, batch, plan.dominant_grid) if n_prof else None
+  entry = traffic_entry(name, prof_name, batch, rec["prof_grid"]) if n_prof else None
   traffic = entry["bytes"] if entry else None
   return {
       "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -602,7 +604,7 @@ def roofline_of(name, rec, ms):
       # launch time measured in THIS run, against the same peak - a true fraction of bandwidth
       "physical_frac": (traffic / (kernel_ms * 1e-3) / 1e9 / peak) if (traffic and n_prof) else None,
       "traffic_source": entry.get("source") if entry else None,
-      "kernel": prof_name, "kernel_ms": kernel_ms, "launches_timed": n_prof, "kernel_grid": plan.dominant_grid,
+      "kernel": prof_name, "kernel_ms": kernel_ms, "launches_timed": n_prof, "kernel_grid": rec["prof_grid"],
       "algorithmic_bytes_per_launch": kernel_bytes, "peak_source": peak_src,
       "edge_states_per_launch": dom_es * batch,
       "iter_ms": iter_ms, "iter_algorithmic_bytes": bytes_iter, "iter_achieved": iter_gbs, "iter_frac": iter_gbs / peak,
