@@ -27,10 +27,13 @@ namespace pgx {
 //   * row segments: a launch updates the owner rows [seg_begin[s], seg_end[s]), s = 0, 1, only
 //     (a strip's interior rows in one launch while the halo exchange is in flight, its first
 //     and last row in a second launch once the halo has landed);
-//   * up_add: [2 N] values added to the evidence of row 0 (torus = 0): the messages into the
-//     strip's first row from the vertical factors of the strip above;
-//   * torus = 0: a ghost row R below the last owner row, whose evidence (ghost_ev, or row R of
-//     the evidence array) is the partial variable sum of the strip below's first row.
+//   * up_add: [2 N] messages into the strip's first row from the vertical factors of the strip
+//     above, added to row 0's sums right after the evidence (or last, on the strip that holds the
+//     torus' row 0: up_last) - the position the single graph's ascending message order gives them;
+//   * torus = 0: a ghost row R below the last owner row; its evidence and the messages of the next
+//     strip's own factors arrive unsummed (ghost_terms) and are added in the single graph's order,
+//     so that N strips are BIT-IDENTICAL to one graph (ghost_ev / row R of the evidence array: the
+//     plain partial-sum form, kept for callers that pre-sum).
 // ---------------------------------------------------------------------------
 struct LatticeBinArgs {
   int32_t R, N;        // owner rows, columns
@@ -38,6 +41,15 @@ struct LatticeBinArgs {
   int32_t seg_begin[2], seg_end[2];  // owner-row ranges this launch updates (empty: begin >= end)
   const float* up_add; // [2 N] or null
   const float* ghost_ev;  // [2 N] evidence of the ghost row (torus = 0), or null: row R of the evidence array
+  // Row strips, exact single-graph summation order (pgx_strip_*): the ghost row's terms arrive
+  // UNSUMMED, ghost_terms[8 j .. 8 j + 4] = (ev0, ev1, left H.b, own V.a, own H.a) of the next
+  // strip's first row (compressed messages), so that the ghost variable's sum is formed exactly as
+  // the single graph forms it (evidence, the message from above, left, own V, own H; the left
+  // neighbour last in column 0); and on the strip that holds the torus' row 0 the message from
+  // above - the largest message index of the variable - is added LAST (up_last).
+  const float* ghost_terms;  // [8 N] or null
+  int32_t up_last;
+  int32_t ghost_up_last;  // the ghost row is the torus' row 0 (last strip): there too the message from above comes last
 };
 
 template <int TR_, int TC_, int STAGES_, int CONSUMERS_ = 512, int CTAS_ = 1>
@@ -223,8 +235,9 @@ k_lattice_bin(LatticeBinArgs g, const float* __restrict__ ev, const float* __res
     if (rr <= t.rows && l <= R && j <= N) {
       if (j == N) j = 0;
       if (torus && l == R) l = 0;
-      e = (ghost2 != nullptr && l == R) ? __ldg(ghost2 + j) : __ldg(ev2 + (int64_t(l) * N + j));
-      if (up2 != nullptr && l == 0 && !torus) {  // halo: messages from the strip above
+      if (g.ghost_terms != nullptr && l == R) e = __ldg(reinterpret_cast<const float2*>(g.ghost_terms + 8 * int64_t(j)));
+      else e = (ghost2 != nullptr && l == R) ? __ldg(ghost2 + j) : __ldg(ev2 + (int64_t(l) * N + j));
+      if (up2 != nullptr && l == 0 && !torus && !g.up_last) {  // halo: messages from the strip above
         const float2 u = __ldg(up2 + j);
         e.x += u.x;
         e.y += u.y;
@@ -247,12 +260,28 @@ k_lattice_bin(LatticeBinArgs g, const float* __restrict__ ev, const float* __res
     const float4 own = sm[(rr + 1) * MC + col];
     const float up = sm[rr * MC + col].y;                // V factor of the row above: its b edge
     const float left = sm[(rr + 1) * MC + col - 1].w;    // H factor of the left neighbour: its b edge
+    const bool ghost = !has_own && g.ghost_terms != nullptr;
     f32x2 s = pk2(e.x, e.y);
-    if (has_up && !up_wrap) s = add2(s, bin_pair(up));
+    if (has_up && !up_wrap && !(ghost && g.ghost_up_last)) s = add2(s, bin_pair(up));
     if (has_own && !left_wrap) s = add2(s, bin_pair(left));
     if (has_own) { s = add2(s, bin_pair(own.x)); s = add2(s, bin_pair(own.z)); }
     if (has_own && left_wrap) s = add2(s, bin_pair(left));
     if (up_wrap) s = add2(s, bin_pair(up));
+    if (ghost) {
+      // ghost variable = first row of the next strip: its own strip's terms after the message from above
+      const int jj = j == N ? 0 : j;
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(g.ghost_terms + 8 * int64_t(jj)));  // ev0, ev1, left, own V
+      const float own_h = __ldg(g.ghost_terms + 8 * int64_t(jj) + 4);
+      if (!left_wrap) s = add2(s, bin_pair(t4.z));
+      s = add2(s, bin_pair(t4.w));
+      s = add2(s, bin_pair(own_h));
+      if (left_wrap) s = add2(s, bin_pair(t4.z));
+      if (g.ghost_up_last) s = add2(s, bin_pair(up));
+    }
+    if (g.up_last && up2 != nullptr && l == 0 && !torus) {  // the torus' row 0: the message from row n - 1 comes last
+      const float2 u = __ldg(up2 + (j == N ? 0 : j));
+      s = add2(s, pk2(u.x, u.y));
+    }
     float s0, s1;
     upk2(s, s0, s1);
     return make_float2(s0, s1);
@@ -385,13 +414,13 @@ k_lattice_expand(const float4* __restrict__ c, float4* __restrict__ m, int64_t c
 // Row strips (pgx_strip_*): what a rank sends each iteration, from the compressed messages.
 //   down[2 j .. 2 j + 1] = the message of the last row's vertical factor into the variable
 //                          below (owned by the next rank), both states;
-//   up[2 j .. 2 j + 1]   = ev + (messages into the first row's variable j from THIS rank's
-//                          factors, ascending message index): the ghost evidence of the
-//                          previous rank, whose own vertical message completes the sum.
+//   up[8 j .. 8 j + 4]   = (ev0, ev1, left H.b, own V.a, own H.a) of the first row's variable j,
+//                          UNSUMMED: the previous rank adds them to its ghost variable in the
+//                          single graph's order (LatticeBinArgs::ghost_terms).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 k_strip_pack(int32_t R, int32_t N, const float* __restrict__ ev, const float4* __restrict__ c,
-             float2* __restrict__ down, float2* __restrict__ up) {
+             float2* __restrict__ down, float4* __restrict__ up) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
   const float xb = c[int64_t(R - 1) * N + j].y;
@@ -399,14 +428,8 @@ k_strip_pack(int32_t R, int32_t N, const float* __restrict__ ev, const float4* _
   const float4 own = c[j];
   const float left = c[j == 0 ? N - 1 : j - 1].w;
   const float2 e = reinterpret_cast<const float2*>(ev)[j];
-  f32x2 s = pk2(e.x, e.y);
-  if (j != 0) s = add2(s, bin_pair(left));
-  s = add2(s, bin_pair(own.x));
-  s = add2(s, bin_pair(own.z));
-  if (j == 0) s = add2(s, bin_pair(left));
-  float s0, s1;
-  upk2(s, s0, s1);
-  up[j] = make_float2(s0, s1);
+  up[2 * j] = make_float4(e.x, e.y, left, own.x);
+  up[2 * j + 1] = make_float4(own.z, 0.f, 0.f, 0.f);
 }
 
 // Beliefs of the owned variables of a strip (or of the whole torus when torus = 1) from the
@@ -421,7 +444,7 @@ k_lattice_bin_beliefs(LatticeBinArgs g, const float* __restrict__ ev, const floa
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < cells; i += int64_t(gridDim.x) * blockDim.x) {
     const int l = int(i / g.N), j = int(i - int64_t(l) * g.N);
     float2 e = ev2[i];
-    if (up2 != nullptr && l == 0 && !torus) { e.x += up2[j].x; e.y += up2[j].y; }
+    if (up2 != nullptr && l == 0 && !torus && !g.up_last) { e.x += up2[j].x; e.y += up2[j].y; }
     const bool has_up = torus || l > 0;
     const bool up_wrap = torus && l == 0;
     const bool left_wrap = j == 0;
@@ -435,6 +458,7 @@ k_lattice_bin_beliefs(LatticeBinArgs g, const float* __restrict__ ev, const floa
     s = add2(s, bin_pair(own.z));
     if (left_wrap) s = add2(s, bin_pair(left));
     if (up_wrap) s = add2(s, bin_pair(up));
+    if (g.up_last && up2 != nullptr && l == 0 && !torus) s = add2(s, pk2(up2[j].x, up2[j].y));
     float s0, s1;
     upk2(s, s0, s1);
     out[i] = make_float2(s0, s1);

@@ -1156,6 +1156,7 @@ int run_lattice_bin(pgx_plan* plan, cudaStream_t st, const float* log_potentials
   g.seg_end[0] = lat.R;
   g.up_add = nullptr;
   g.ghost_ev = nullptr;
+  g.ghost_terms = nullptr;
   plan->dominant_name = "k_lattice_bin";
   plan->dominant_grid = std::min<int64_t>(int64_t((lat.N + LbCfgDefault::TC - 1) / LbCfgDefault::TC) *
                                               ((lat.R + LbCfgDefault::TR - 1) / LbCfgDefault::TR),

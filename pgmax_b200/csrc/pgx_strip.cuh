@@ -10,9 +10,11 @@
 // only on the previous iteration's messages, so ONE simultaneous exchange per iteration suffices:
 //
 //   g -> g+1 : the boundary factors' messages into the first row of g+1 (2 n floats), which g+1
-//              adds to that row's evidence (LatticeBinArgs::up_add);
-//   g+1 -> g : ev + (messages from g+1's own factors) of its first row (2 n floats): the
-//              evidence of g's ghost row, whose sum g completes with its own vertical message.
+//              adds to that row's sums where the single graph's message order puts them
+//              (LatticeBinArgs::up_add / up_last);
+//   g+1 -> g : evidence and the three messages from g+1's own factors of its first row, UNSUMMED
+//              (5 of 8 n floats): g adds them to its ghost row after its own vertical message, in
+//              the single graph's order (LatticeBinArgs::ghost_terms).
 //
 // Per iteration, on the strip's own streams (all of it captured ONCE per (buffers, iteration
 // count, damping, temperature) in a CUDA graph and replayed with one cudaGraphLaunch per run):
@@ -23,9 +25,9 @@
 //   main : wait for the exchange; k_lattice_bin on rows 0 and rows - 1
 //
 // Messages stay in binary-difference storage between iterations (lattice_bin.cuh); the ABI arrays
-// are the reference's flat layout.  The summation order of the two boundary rows differs from the
-// single-graph order (partial sums), so N-rank results agree with one rank to fp32 rounding
-// (<= 1e-6 in the tests), not bit for bit.  NCCL is resolved at run time from the process
+// are the reference's flat layout.  Every variable sum - the boundary rows' included - is formed in
+// the single graph's order, so N ranks are BIT-IDENTICAL to one rank (and, for max-product, to the
+// oracle) at any horizon; asserted by the tests.  NCCL is resolved at run time from the process
 // (torch's bundled libnccl.so.2, or the system one): the library does not link against it.
 
 #include <dlfcn.h>
@@ -131,7 +133,10 @@ pgx::LatticeBinArgs strip_args(const pgx_strip* s) {
   g.N = int32_t(s->N);
   g.torus = s->world == 1 ? 1 : 0;
   g.up_add = s->world == 1 ? nullptr : s->up_add;
-  g.ghost_ev = s->world == 1 ? nullptr : s->ghost;
+  g.ghost_ev = nullptr;
+  g.ghost_terms = s->world == 1 ? nullptr : s->ghost;
+  g.up_last = s->rank == 0 ? 1 : 0;  // the strip that holds the torus' row 0
+  g.ghost_up_last = s->rank == s->world - 1 ? 1 : 0;  // ... and the strip whose ghost row it is
   return g;
 }
 
@@ -142,17 +147,17 @@ int strip_exchange(pgx_strip* s, cudaStream_t st, const float* ev_own, const flo
   int rc;
   pgx::k_strip_pack<<<unsigned((s->N + pgx::kThreads - 1) / pgx::kThreads), pgx::kThreads, 0, st>>>(
       int32_t(s->R), int32_t(s->N), ev_own, reinterpret_cast<const float4*>(c), reinterpret_cast<float2*>(s->send_down),
-      reinterpret_cast<float2*>(s->send_up));
+      reinterpret_cast<float4*>(s->send_up));
   if ((rc = strip_launch_ok(s, "k_strip_pack"))) return rc;
   PGX_CUDA(cudaEventRecord(s->e_pack, st));
   PGX_CUDA(cudaStreamWaitEvent(s->s_comm, s->e_pack, 0));
   const int down = (s->rank + 1) % s->world, up = (s->rank + s->world - 1) % s->world;
-  const size_t n = size_t(2 * s->N);
+  const size_t n = size_t(2 * s->N), n_up = size_t(8 * s->N);
   PGX_NCCL(api, api->GroupStart());
   PGX_NCCL(api, api->Send(s->send_down, n, ncclFloat, down, s->comm, s->s_comm));
-  PGX_NCCL(api, api->Send(s->send_up, n, ncclFloat, up, s->comm, s->s_comm));
+  PGX_NCCL(api, api->Send(s->send_up, n_up, ncclFloat, up, s->comm, s->s_comm));
   PGX_NCCL(api, api->Recv(s->up_add, n, ncclFloat, up, s->comm, s->s_comm));
-  PGX_NCCL(api, api->Recv(s->ghost, n, ncclFloat, down, s->comm, s->s_comm));
+  PGX_NCCL(api, api->Recv(s->ghost, n_up, ncclFloat, down, s->comm, s->s_comm));
   PGX_NCCL(api, api->GroupEnd());
   ++s->launches;
   PGX_CUDA(cudaEventRecord(s->e_comm, s->s_comm));
@@ -270,7 +275,7 @@ int pgx_strip_create(int64_t n_cols, int64_t rows, int rank, int world, const vo
   const size_t cbytes = size_t(rows) * size_t(n_cols) * sizeof(float4);
   PGX_STRIP_TRY(cudaMalloc(reinterpret_cast<void**>(&s->cA), cbytes));
   PGX_STRIP_TRY(cudaMalloc(reinterpret_cast<void**>(&s->cB), cbytes));
-  const size_t hbytes = size_t(2 * n_cols) * sizeof(float);
+  const size_t hbytes = size_t(8 * n_cols) * sizeof(float);  // (the two "up" buffers use all 8 floats per column)
   for (float** p : {&s->send_down, &s->send_up, &s->up_add, &s->ghost}) {
     PGX_STRIP_TRY(cudaMalloc(reinterpret_cast<void**>(p), hbytes));
     PGX_STRIP_TRY(cudaMemset(*p, 0, hbytes));
