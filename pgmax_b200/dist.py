@@ -30,11 +30,11 @@ suffices:
             ghost is the full S_v and q = S_v - m is the boundary variable->factor
             message.
 
-A rank's local BP iteration is then exactly the single-GPU kernel sequence on the
-local graph (pgx_bp_run_flags with PGX_RUN_INPUT_NORMALIZED, messages read in
-place).  The summation order of the boundary rows differs from the single-graph
-order (partial sums), so multi-rank results agree with the single graph to fp32
-rounding (<= 1e-6 in the tests), not bit for bit.
+That is the protocol as the host-side StripRunner states it (and as the gloo tests run it
+on CPU): the boundary rows are summed from partial sums, so its results agree with the
+single graph to fp32 rounding.  The product path, NativeStripRunner / pgx_strip_*, sends
+the g+1 -> g terms UNSUMMED and forms every boundary sum in the single graph's order:
+N strips are bit-identical to one graph (csrc/pgx_strip.cuh).
 """
 
 import dataclasses
