@@ -110,6 +110,47 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
 }
 
 // ---------------------------------------------------------------------------
+// K2b-unary: EnumFactors over ONE variable whose configurations are all its states in order (the
+// bias factors of an RBM, benchmark/rbm_lib.py:141-158).  Every edge-state is in exactly one
+// configuration, so the general update collapses to  f_s = ((0 + q_s) + lp_s) - q_s  for max- AND
+// sum-product (the logsumexp of one term is T log(exp(0)) + M = M exactly): the same operations as
+// k_enum_small performs for such a factor, without its per-thread arrays and list walks -
+// bit-identical (tested), a quarter of its time on the RBM's 1 284 unary factors.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+k_enum_unary(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
+             const float* __restrict__ S, const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  UnitLoop L = unit_loop(mp, blk.num_factors);
+  if (!L.b_ok) return;
+  float dmax = 0.f;
+  const int sh = mp.bx_log, ns = blk.ns;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const LaneView lpL = lane_view(lp, mp, L.b);
+  for (int64_t f = L.u; f < L.u_end; f += L.step) {
+    const int64_t mbase = blk.msg_base(f), pbase = blk.pot_base(f);
+    const int64_t vs = edge_vs[blk.edge_base(f)];
+    auto damped = [&](int s) {
+      const float m = mo[(mbase + s) << sh];
+      const float q = SL[(vs + s) << sh] - m;
+      const float M = (0.f + q) + clip_lp(lpL.at(pbase + s));
+      return damp(m, M - q, a.d, a.one_minus_d);
+    };
+    float mx = -INFINITY;
+    for (int s = 0; s < ns; ++s) mx = fmaxf(mx, damped(s));
+    for (int s = 0; s < ns; ++s) {
+      const float out = fmaxf(damped(s) - mx, kMsgNegInf);
+      const int64_t idx = (mbase + s) << sh;
+      dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+      mn[idx] = out;
+    }
+  }
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
 // K2c: EnumFactor update, large factors (RCN: 2 x 625 states, up to 375 769
 // configurations): one CTA per (factor, sample).  q and the damped values live
 // in shared memory; threads own edge-states and walk their configuration lists

@@ -64,7 +64,7 @@ int upload(const std::vector<T>& host, T** dev, int64_t* bytes) {
   return PGX_OK;
 }
 
-enum EnumVariant { kPw2 = 0, kSmall = 1, kBig = 2 };
+enum EnumVariant { kPw2 = 0, kSmall = 1, kBig = 2, kUnary = 3 };
 // groups of kernels whose shared-memory attribute has been raised (pgx_plan::attr_done)
 enum AttrGroup { kAttrBigMax = 0, kAttrBipMax = 1, kAttrBipSum = 2, kAttrBigEnumMax = 3, kAttrBigEnumSum = 4,
                  kAttrMaxProd = 5, kAttrLattice = 6, kAttrSdlpMax = 7, kAttrSdlpSum = 8, kAttrLatticeBin = 9,
@@ -456,7 +456,9 @@ int build_enum_block(pgx_plan* plan, const pgx_enum_block* desc_blocks, const st
       A == 2 && K == 4 && ns == 4 && b.configs[0] == 0 && b.configs[1] == 0 && b.configs[2] == 0 &&
       b.configs[3] == 1 && b.configs[4] == 1 && b.configs[5] == 0 && b.configs[6] == 1 &&
       b.configs[7] == 1;
-  out->variant = full_binary_pair ? kPw2 : (ns <= pgx::kSmallMaxNS ? kSmall : kBig);
+  bool full_unary = A == 1 && K == ns;  // one variable, configuration k = state k
+  for (int k = 0; k < K && full_unary; ++k) full_unary = b.configs[k] == k;
+  out->variant = full_binary_pair ? kPw2 : (full_unary ? kUnary : (ns <= pgx::kSmallMaxNS ? kSmall : kBig));
   if (out->variant == kBig && size_t(2 * ns + 32) * sizeof(float) > 227 * 1024)
     return fail(PGX_ERR_UNSUPPORTED, "enum block %d: %d edge-states per factor exceed shared memory",
                 idx, ns);
@@ -863,7 +865,10 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
           m_new, a);
       if ((rc = check_launch(plan, "k_enum_pw2"))) return rc;
       if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2";
-    } else if (eb.variant == kSmall) {
+    } else if (eb.variant == kUnary && !(plan->disabled_paths & PGX_PATH_ENUM_UNARY)) {
+      pgx::k_enum_unary<<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old, m_new, a);
+      if ((rc = check_launch(plan, "k_enum_unary"))) return rc;
+    } else if (eb.variant == kSmall || (eb.variant == kUnary && eb.dev.ns <= pgx::kSmallMaxNS)) {
       pgx::k_enum_small<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
           mp, eb.dev, plan->d_edge_vs, lp, S, m_old, m_new, a);
       if ((rc = check_launch(plan, "k_enum_small"))) return rc;
@@ -1664,7 +1669,7 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
   }
   {  // dominant launch = most edge-states
     int64_t best = -1;
-    static const char* const kEnumNames[] = {"k_enum_pw2", "k_enum_small", "k_enum_big"};
+    static const char* const kEnumNames[] = {"k_enum_pw2", "k_enum_small", "k_enum_big", "k_enum_unary"};
     // (with the single-pass path active the pw2 launch of a dense-grid block is k_enum_pw2_bip)
     for (size_t i = 0; i < plan->enum_blocks.size(); ++i) {
       const int64_t es = plan->enum_blocks[i].dev.num_factors * plan->enum_blocks[i].dev.ns;

@@ -230,3 +230,43 @@ def test_round_ordered_potentials_are_reused_only_while_unchanged():
   t.copy_(torch.from_numpy(lp2))
   for _ in range(3):
     np.testing.assert_array_equal(bp.run(d1, num_iters=4, damping=0.5).ftov_msgs.cpu().numpy(), want["lp2"])
+
+
+@pytest.mark.parametrize("temperature", [0.0, 0.7])
+@pytest.mark.parametrize("batch", [None, 6, 70])
+def test_unary_enum_closed_form_is_bit_identical(temperature, batch):
+  """k_enum_unary (one-variable EnumFactors over all states: f = ((0 + q) + lp) - q) against the
+  general small-factor kernel (PATH_ENUM_UNARY disabled): the same operations, bit-identical, for
+  2-state and 5-state unary factors (potentials beyond the +-1e6 clip included) beside pairwise
+  ones, one sample / small batch / single-pass RBM path; and against the oracle."""
+  import models
+  rng = np.random.RandomState(5)
+  a = vgroup.NDVarArray(num_states=2, shape=(6,))
+  b = vgroup.NDVarArray(num_states=5, shape=(4,))
+  fg = fgraph.FactorGraph(variable_groups=[a, b])
+  lp_a = rng.normal(size=(6, 2))
+  lp_a[2, 1] = 3e6
+  fg.add_factors(fgroup.EnumFactorGroup(variables_for_factors=[[a[i]] for i in range(6)],
+                                        factor_configs=np.arange(2)[:, None], log_potentials=lp_a))
+  fg.add_factors(fgroup.EnumFactorGroup(variables_for_factors=[[b[i]] for i in range(4)],
+                                        factor_configs=np.arange(5)[:, None], log_potentials=rng.normal(size=(4, 5))))
+  fg.add_factors(fgroup.PairwiseFactorGroup(variables_for_factors=[[a[i], b[i % 4]] for i in range(6)],
+                                            log_potential_matrix=rng.normal(size=(6, 2, 5))))
+  graphs = [(fg, {a: (6, 2), b: (4, 5)})]
+  W, bh, bv = 0.4 * rng.normal(size=(5, 7)), rng.logistic(size=5), rng.logistic(size=7)
+  rbm, hidden, visible = models.rbm_model(W, bh, bv)
+  graphs.append((rbm, {hidden: (5, 2), visible: (7, 2)}))
+  lead = () if batch is None else (batch,)
+  for graph_fg, shapes in graphs:
+    bp = infer.BP(graph_fg.bp_state, temperature=temperature)
+    arrays = bp.init(evidence_updates={vg: rng.gumbel(size=lead + shp) for vg, shp in shapes.items()})
+    plan = bp.context.plan
+    got, got_d = bp.run_with_diffs(arrays, num_iters=8, damping=0.5, temperature=temperature)
+    plan.disable_paths(plan.PATH_ENUM_UNARY)
+    ref, ref_d = bp.run_with_diffs(arrays, num_iters=8, damping=0.5, temperature=temperature)
+    plan.disable_paths(0)
+    np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs)
+    np.testing.assert_array_equal(got_d, ref_d)
+    graph = bp_oracle.graph_from_context(bp.context)
+    want, _ = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 8, 0.5, temperature)
+    np.testing.assert_allclose(got.ftov_msgs, want, atol=1e-6 if temperature == 0.0 else 1e-5)
