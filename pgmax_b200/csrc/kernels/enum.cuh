@@ -472,7 +472,10 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
       // one trip = kPermTrip rounds; the next trip's loads (2 KiB of potentials per warp) are in
       // flight while this one is consumed: with 24 warps per SM that is ~50 KiB per SM in
       // flight, what HBM latency x bandwidth asks for
-      constexpr int kPermTrip = 16;
+#ifndef PGX_PERM_TRIP
+#define PGX_PERM_TRIP 16
+#endif
+      constexpr int kPermTrip = PGX_PERM_TRIP;
       for (int grp = kPerm ? next_group() : G.num_groups; kPerm && grp < G.num_groups; grp = next_group()) {
         const int a_own = G.lane_state[grp * 32 + lane];
         const float qa = a_own < n0 ? q[a_own] : 0.f;

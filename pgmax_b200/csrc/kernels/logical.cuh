@@ -864,36 +864,51 @@ __host__ __device__ constexpr size_t orand_fused_smem(int max_parents) {
   return size_t(max_parents) * sizeof(FusedW) + (size_t(max_parents) * 3 + 20) * 32 * sizeof(float);
 }
 
-template <bool kSumProduct, bool kDelta>
+// kPack > 1: the batch's last, partial sample tile.  With 32 / kPack or fewer samples in it a warp
+// would idle most of its lanes, so kPack OR factors share one CTA: lane = (factor slot, sample),
+// every per-factor quantity (parent range, wiring, chains of phase B) becomes per-lane instead of
+// warp-uniform, loops run to the longest of the CTA's factors under a predicate.  Same operations
+// per (factor, sample) in the same order: bit-identical to the kPack = 1 kernel (tested).
+template <bool kSumProduct, bool kDelta, int kPack>
 __global__ void __launch_bounds__(kFusedWarps * 32, 2)
-k_or_and_fused(int batch, OrAndFusedDev g, View ev, const float* __restrict__ S, const float* __restrict__ m_old,
+k_or_and_fused(int batch, int tile0, OrAndFusedDev g, View ev, const float* __restrict__ S, const float* __restrict__ m_old,
                float* __restrict__ m_new, RunArgs a) {
   extern __shared__ __align__(16) unsigned char fz_raw[];
+  constexpr bool kPacked = kPack > 1;
+  constexpr int kGroup = 32 / kPack;  // samples per factor slot
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.y * 32 + lane;
-  const size_t tile = blockIdx.y;
+  const int smp = kPacked ? (lane & (kGroup - 1)) : lane;
+  const size_t tile = size_t(tile0) + blockIdx.y;
+  const int b = int(tile) * 32 + smp;
   // lanes beyond the batch stay alive for the barriers: they work on the (allocated, padded)
   // sample slots of the last tile and publish no delta
-  const float* mo = m_old + tile * (size_t(a.Es) >> 1) * 32 + lane;
-  float* mn = m_new + tile * (size_t(a.Es) >> 1) * 32 + lane;
-  const float* SL = S + tile * size_t(a.Vs) * 32 + lane;
-  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + lane : ev.p;
+  const float* mo = m_old + tile * (size_t(a.Es) >> 1) * 32 + smp;
+  float* mn = m_new + tile * (size_t(a.Es) >> 1) * 32 + smp;
+  const float* SL = S + tile * size_t(a.Vs) * 32 + smp;
+  const float* evq = ev.kind == 1 ? ev.p + tile * size_t(ev.n_rows) * 32 + smp : ev.p;
   const int esh = ev.kind == 1 ? 5 : 0;
   const float T = a.T, d = a.d, one_minus_d = a.one_minus_d;
-  const int64_t gf = blockIdx.x;
+  const int64_t gf_raw = kPacked ? int64_t(blockIdx.x) * kPack + lane / kGroup : int64_t(blockIdx.x);
+  const bool f_ok = !kPacked || gf_raw < g.num_or;
+  const int64_t gf = f_ok ? gf_raw : g.num_or - 1;
   const int p0 = g.parent_ptr[gf], p1 = g.parent_ptr[gf + 1];
-  const int n = p1 - p0;
+  const int n = f_ok ? p1 - p0 : 0;
+  // trip count of the parent loops: the factor's own count, or the longest of the CTA's factors
+  const int n_top = kPacked ? int(__reduce_max_sync(0xffffffffu, unsigned(n))) : n;
   int4* wsm = reinterpret_cast<int4*>(fz_raw);                                             // [max_parents][2]
   float* stash = reinterpret_cast<float*>(fz_raw + size_t(g.max_parents) * sizeof(FusedW)) + lane;  // [parent][3][32]
   float* agg = stash + size_t(g.max_parents) * 96;                                         // [8][32]
   float dmax = 0.f;
 
-  // the factor's wiring: one coalesced sweep (the per-parent round trip below is then data only)
-  {
-    const int4* src = reinterpret_cast<const int4*>(g.w + p0);
-    for (int t = threadIdx.x; t < 2 * n; t += blockDim.x) wsm[t] = src[t];
+  // the factor's wiring: one coalesced sweep (the per-parent round trip below is then data only);
+  // packed lanes read their own factor's records from global memory (L2-resident, one address
+  // per factor slot)
+  const int4* wsrc = reinterpret_cast<const int4*>(g.w + p0);
+  if (!kPacked) {
+    for (int t = threadIdx.x; t < 2 * n; t += blockDim.x) wsm[t] = wsrc[t];
+    __syncthreads();
   }
-  __syncthreads();
+  auto wire = [&](int t) { return kPacked ? __ldg(wsrc + t) : wsm[t]; };
 
   // ---- phase A ---------------------------------------------------------------------------------
   // software-pipelined: the ten loads of the warp's NEXT parent are in flight while the current
@@ -903,7 +918,7 @@ k_or_and_fused(int batch, OrAndFusedDev g, View ev, const float* __restrict__ S,
     float xO, xA, e0, e1, xs, xw, Ss0, Ss1, Sw0, Sw1;
   };
   auto fetch = [&](int j, Raw& r) {
-    const int4 lo = wsm[2 * j], hi = wsm[2 * j + 1];
+    const int4 lo = wire(2 * j), hi = wire(2 * j + 1);
     r.w = FusedW{lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     r.xO = mo[uint32_t(r.w.mO) << 5];
     r.xA = mo[uint32_t(r.w.mA) << 5];
@@ -918,9 +933,9 @@ k_or_and_fused(int batch, OrAndFusedDev g, View ev, const float* __restrict__ S,
   };
   Raw cur, nxt;
   if (warp < n) fetch(warp, cur);
-  for (int j = warp; j < n; j += kFusedWarps) {
+  for (int j = warp; j < n_top; j += kFusedWarps) {
     if (j + kFusedWarps < n) fetch(j + kFusedWarps, nxt);
-    {
+    if (j < n) {
       const Raw& r = cur;
       // SW_i as parent of the OR factor (off = +1: pointed state 0; its own edge has the smaller
       // message index: kind 3) -> (a_i, b_i) = (relevant, pointed) variable -> factor messages
@@ -971,27 +986,34 @@ k_or_and_fused(int batch, OrAndFusedDev g, View ev, const float* __restrict__ S,
   if (warp == 0 || warp == 1) {
     float sum = 0.f;
     int j = 0;
-    for (; j + 8 <= n; j += 8) {
-      float va[8], vb[8];
+    if (!kPacked) {
+      for (; j + 8 <= n; j += 8) {
+        float va[8], vb[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { vb[k] = stash[size_t(j + k) * 96 + 32]; va[k] = warp == 0 ? 0.f : stash[size_t(j + k) * 96]; }
+        for (int k = 0; k < 8; ++k) { vb[k] = stash[size_t(j + k) * 96 + 32]; va[k] = warp == 0 ? 0.f : stash[size_t(j + k) * 96]; }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) sum += warp == 0 ? vb[k] : (kSumProduct ? logaddexp_t(va[k], vb[k], T) : fmaxf(vb[k], va[k]));
+        for (int k = 0; k < 8; ++k) sum += warp == 0 ? vb[k] : (kSumProduct ? logaddexp_t(va[k], vb[k], T) : fmaxf(vb[k], va[k]));
+      }
     }
-    for (; j < n; ++j) {
+    for (; j < n_top; ++j) {
       const float vb = stash[size_t(j) * 96 + 32], va = stash[size_t(j) * 96];
-      sum += warp == 0 ? vb : (kSumProduct ? logaddexp_t(va, vb, T) : fmaxf(vb, va));
+      const float term = warp == 0 ? vb : (kSumProduct ? logaddexp_t(va, vb, T) : fmaxf(vb, va));
+      if (j < n) sum += term;
     }
     agg[warp == 0 ? 32 : 0] = sum;  // Sb / acc
   } else if (warp >= 2 && warp < 6) {
     const int q = warp - 2, per = (n + 3) / 4;
+    const int per_top = (n_top + 3) / 4;
     const int j0 = q * per, j1 = min(n, j0 + per);
     float d1 = -INFINITY, d2 = -INFINITY;
     int istar = p0;
-    for (int j = j0; j < j1; ++j) {
-      const float dl = stash[size_t(j) * 96] - stash[size_t(j) * 96 + 32];
-      if (dl >= d1) { d2 = d1; d1 = dl; istar = p0 + j; }
-      else if (dl > d2) d2 = dl;
+    for (int t = 0; t < per_top; ++t) {
+      const int j = j0 + t;
+      if (j < j1) {
+        const float dl = stash[size_t(j) * 96] - stash[size_t(j) * 96 + 32];
+        if (dl >= d1) { d2 = d1; d1 = dl; istar = p0 + j; }
+        else if (dl > d2) d2 = dl;
+      }
     }
     float* seg = agg + (8 + 3 * q) * 32;  // rows 8.. of the aggregate area
     seg[0] = d1; seg[32] = d2; seg[64] = __int_as_float(istar);
@@ -1017,16 +1039,18 @@ k_or_and_fused(int batch, OrAndFusedDev g, View ev, const float* __restrict__ S,
     }
     const float c_p = agg[160], c_r = agg[192];
     const bool single = n == 1;
-    if (warp == 6)
+    if (warp == 6 && f_ok)
       dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, 1, child, A.child_relevant<kSumProduct>(T) - A.Sb, d,
                                                                 one_minus_d));
-    for (int j = warp; j < n; j += kFusedWarps) {
-      const float oa = stash[size_t(j) * 96], ob = stash[size_t(j) * 96 + 32];
-      EdgeIn po;
-      po.m_p = stash[size_t(j) * 96 + 64]; po.m_r = 0.f; po.msg = wsm[2 * j].x << 1;
-      expand_msg<true, kSumProduct>(1, po.m_p, po.m_r);
-      const float x = A.parent_out<kSumProduct>(p0 + j, oa, ob, c_r, c_p, T, single);
-      dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, 1, po, x, d, one_minus_d));
+    for (int j = warp; j < n_top; j += kFusedWarps) {
+      if (j < n) {
+        const float oa = stash[size_t(j) * 96], ob = stash[size_t(j) * 96 + 32];
+        EdgeIn po;
+        po.m_p = stash[size_t(j) * 96 + 64]; po.m_r = 0.f; po.msg = wire(2 * j).x << 1;
+        expand_msg<true, kSumProduct>(1, po.m_p, po.m_r);
+        const float x = A.parent_out<kSumProduct>(p0 + j, oa, ob, c_r, c_p, T, single);
+        dmax = fmaxf(dmax, store_edge<kDelta, true, kSumProduct>(mn, 1, po, x, d, one_minus_d));
+      }
     }
   }
   if (kDelta && b < batch) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);

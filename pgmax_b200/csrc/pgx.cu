@@ -900,16 +900,54 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
     // one launch for both groups: CTA per (OR factor, sample tile)
     const size_t smem = pgx::orand_fused_smem(plan->orand.max_parents);
     if (attr_needed(kSum ? kAttrOrAndSum : kAttrOrAndMax)) {
-      PGX_CUDA(cudaFuncSetAttribute(pgx::k_or_and_fused<kSum, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      PGX_CUDA(cudaFuncSetAttribute(pgx::k_or_and_fused<kSum, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+#define PGX_FUSED_ATTR(PACK)                                                                                                     \
+  PGX_CUDA(cudaFuncSetAttribute(pgx::k_or_and_fused<kSum, true, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); \
+  PGX_CUDA(cudaFuncSetAttribute(pgx::k_or_and_fused<kSum, false, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)))
+      PGX_FUSED_ATTR(1); PGX_FUSED_ATTR(2); PGX_FUSED_ATTR(4); PGX_FUSED_ATTR(8);
+#undef PGX_FUSED_ATTR
     }
-    const dim3 grid(unsigned(plan->orand.num_or), unsigned(mp.nbt));
+    // A short batch tail (<= 16 samples in the last tile) takes the packed variant: 2 / 4 / 8 OR
+    // factors per CTA instead of a tile of mostly idle lanes - beside the full tiles, on the
+    // auxiliary stream when there is one.
+    const int tail_n = mp.batch & 31;
+    const int pack = (tail_n == 0 || tail_n > 16 || (plan->disabled_paths & PGX_PATH_TAIL_SPLIT)) ? 1
+                     : tail_n <= 4 ? 8 : tail_n <= 8 ? 4 : 2;
+    const int full_tiles = pack > 1 ? mp.batch / 32 : int(mp.nbt);
+    const dim3 grid(unsigned(plan->orand.num_or), unsigned(full_tiles));
+    const dim3 grid_tail(unsigned((plan->orand.num_or + pack - 1) / pack), 1);
+    const bool tail_side = pack > 1 && full_tiles > 0 && plan->aux != nullptr && !(plan->disabled_paths & PGX_PATH_AUX_STREAM);
+    const cudaStream_t st_tail = tail_side ? plan->aux : st;
+    const bool delta = a.deltas != nullptr;
     if ((rc = prof_mark(plan, st, plan->dominant))) return rc;
-    if (a.deltas != nullptr)
-      pgx::k_or_and_fused<kSum, true><<<grid, pgx::kFusedWarps * 32, smem, st>>>(mp.batch, plan->orand, ev, S, m_old, m_new, a);
-    else
-      pgx::k_or_and_fused<kSum, false><<<grid, pgx::kFusedWarps * 32, smem, st>>>(mp.batch, plan->orand, ev, S, m_old, m_new, a);
-    if ((rc = check_launch(plan, "k_or_and_fused"))) return rc;
+    if (pack > 1) {
+      if (tail_side) {
+        PGX_CUDA(cudaEventRecord(plan->ev_fork, st));
+        PGX_CUDA(cudaStreamWaitEvent(plan->aux, plan->ev_fork, 0));
+      }
+#define PGX_FUSED_TAIL(PACK)                                                                                           \
+  if (delta)                                                                                                           \
+    pgx::k_or_and_fused<kSum, true, PACK><<<grid_tail, pgx::kFusedWarps * 32, smem, st_tail>>>(mp.batch, full_tiles,   \
+                                                                                                plan->orand, ev, S,    \
+                                                                                                m_old, m_new, a);      \
+  else                                                                                                                 \
+    pgx::k_or_and_fused<kSum, false, PACK><<<grid_tail, pgx::kFusedWarps * 32, smem, st_tail>>>(mp.batch, full_tiles,  \
+                                                                                                 plan->orand, ev, S,   \
+                                                                                                 m_old, m_new, a)
+      if (pack == 8) { PGX_FUSED_TAIL(8); }
+      else if (pack == 4) { PGX_FUSED_TAIL(4); }
+      else { PGX_FUSED_TAIL(2); }
+#undef PGX_FUSED_TAIL
+      if ((rc = check_launch(plan, "k_or_and_fused(tail)"))) return rc;
+      if (tail_side) PGX_CUDA(cudaEventRecord(plan->ev_join, plan->aux));
+    }
+    if (full_tiles > 0) {
+      if (delta)
+        pgx::k_or_and_fused<kSum, true, 1><<<grid, pgx::kFusedWarps * 32, smem, st>>>(mp.batch, 0, plan->orand, ev, S, m_old, m_new, a);
+      else
+        pgx::k_or_and_fused<kSum, false, 1><<<grid, pgx::kFusedWarps * 32, smem, st>>>(mp.batch, 0, plan->orand, ev, S, m_old, m_new, a);
+    }
+    if (full_tiles > 0 && (rc = check_launch(plan, "k_or_and_fused"))) return rc;
+    if (tail_side) PGX_CUDA(cudaStreamWaitEvent(st, plan->ev_join, 0));
     if (plan->dominant < 0) {
       plan->dominant_name = "k_or_and_fused";
       plan->dominant_grid = int64_t(grid.x) * grid.y;

@@ -217,6 +217,32 @@ def test_fused_or_and_launch_is_bit_identical(temperature, batch):
   np.testing.assert_array_equal(a_d, b_d)
 
 
+@pytest.mark.parametrize("temperature", [0.0, 0.5])
+@pytest.mark.parametrize("batch,pack", [(20, 1), (36, 8), (39, 4), (44, 2), (80, 2), (100, 8)])
+def test_fused_or_and_packed_batch_tail(temperature, batch, pack):
+  """A last tile of <= 16 samples runs as k_or_and_fused<kPack> - 8 / 4 / 2 OR factors per CTA,
+  lane = (factor slot, sample) - beside the full tiles (pgx.cu, launch_f2v).  63 OR factors (not
+  a multiple of the pack: the last CTA has idle factor slots).  Bit-identical to the whole-tile
+  launch (PATH_TAIL_SPLIT disabled: every tile through kPack = 1) and to the separate kernels;
+  the CUDA graph replays both launches."""
+  del pack  # documents which variant the batch selects
+  fg, groups = models.deconv_model(im_height=7, im_width=9, n_feat=2, feat_height=3, feat_width=3)
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  arrays = bp.init(evidence_updates=models.deconv_evidence(groups, batch=batch))
+  plan = bp.context.plan
+  got, got_d = _run(bp, arrays, 7, temperature, 0)
+  whole, whole_d = _run(bp, arrays, 7, temperature, plan.PATH_TAIL_SPLIT)
+  np.testing.assert_array_equal(got.ftov_msgs, whole.ftov_msgs)
+  np.testing.assert_array_equal(got_d, whole_d)
+  sep, sep_d = _run(bp, arrays, 7, temperature, plan.PATH_ORAND_FUSED | plan.PATH_TAIL_SPLIT)
+  np.testing.assert_array_equal(got.ftov_msgs, sep.ftov_msgs)
+  np.testing.assert_array_equal(got_d, sep_d)
+  again, again_d = _run(bp, arrays, 7, temperature, 0)   # second / third call: captured graph
+  again, again_d = _run(bp, arrays, 7, temperature, 0)
+  np.testing.assert_array_equal(got.ftov_msgs, again.ftov_msgs)
+  np.testing.assert_array_equal(got_d, again_d)
+
+
 def test_fused_or_and_full_size_deconvolution():
   """configs[2] graph (28 x 28, 95 220 AND + 784 OR factors of up to 180 parents), 32 images,
   3 max-product iterations: fused launch == separate kernels bit for bit, and the oracle for two
