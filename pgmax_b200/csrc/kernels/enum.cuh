@@ -402,8 +402,11 @@ constexpr int kBigTrip = 8;
 
 // kFlatLp: potentials addressed without a sample-tile shift (shared or batch-major);
 // kPerm: potentials come from the round-ordered copy lpR (potentials shared by the batch)
+// CTAs per SM (register cap) and rounds per trip, A/B-measured on the RCN graph (B = 1, kernel
+// ms; profiles/r02_z_rcn_ab.txt): (16, 3) 0.201 - (8, 4) 0.185 - (12, 4) 0.179 - (10, 5) 0.173 -
+// (12, 5) 0.233 (spills) - (8, 6) 0.187.  Occupancy wins until the trip's registers spill.
 #ifndef PGX_BIGMAX_CTAS
-#define PGX_BIGMAX_CTAS 3
+#define PGX_BIGMAX_CTAS 5
 #endif
 template <bool kFlatLp, bool kPerm>
 __global__ void __launch_bounds__(kThreads, PGX_BIGMAX_CTAS)
@@ -469,11 +472,11 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
       auto sts_f = [](uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); };
       const float* __restrict__ lpr = lpR + G.perm_base + f * (int64_t(G.num_rounds) * 32) + lane;
       const uint32_t* __restrict__ rbl = G.rounds_b + lane;
-      // one trip = kPermTrip rounds; the next trip's loads (2 KiB of potentials per warp) are in
-      // flight while this one is consumed: with 24 warps per SM that is ~50 KiB per SM in
+      // one trip = kPermTrip rounds; the next trip's loads (1.25 KiB of potentials per warp) are
+      // in flight while this one is consumed: with 40 warps per SM that is ~50 KiB per SM in
       // flight, what HBM latency x bandwidth asks for
 #ifndef PGX_PERM_TRIP
-#define PGX_PERM_TRIP 16
+#define PGX_PERM_TRIP 10
 #endif
       constexpr int kPermTrip = PGX_PERM_TRIP;
       for (int grp = kPerm ? next_group() : G.num_groups; kPerm && grp < G.num_groups; grp = next_group()) {
@@ -483,7 +486,7 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
         const uint32_t idle2 = uint32_t((n1 + lane) << 2) * 0x10001u;  // (table entries are byte offsets: state << 2)
         uint32_t en_n[kPermTrip / 2];
         float rl_n[kPermTrip];
-        // full trips issue their 24 loads without a predicate; only a group's last, partial trip
+        // full trips issue their loads without a predicate; only a group's last, partial trip
         // pays for the bounds checks
         auto request = [&](int r0) {
           if (r0 + kPermTrip <= r_end) {
