@@ -118,14 +118,16 @@ def build_workload(name: str, batch_override=None, iters_override=None):
     bp = infer.BP(fg.bp_state, temperature=temperature)
     evidence = {k: v.astype(np.float32) for k, v in models.deconv_evidence(groups, batch).items()}
     label = "binary deconvolution 28x28, 95 220 AND + 784 OR factors, max-product"
-  elif name == "rcn":
+  elif name in ("rcn", "rcn_sum"):
     # examples/rcn.ipynb shape: 20 models x 80 variables of 625 states, large-config pairwise
-    # EnumFactors (perturb radius 2..8), max-product, 30 iterations
-    batch, iters, temperature = batch_override, 30, 0.0
+    # EnumFactors (perturb radius 2..8), max-product, 30 iterations; rcn_sum: the same graph,
+    # sum-product at T = 1 (not a reference configuration: the T > 0 sibling of the RCN kernel)
+    batch, iters, temperature = batch_override, 30, (0.0 if name == "rcn" else 1.0)
     fg, groups, evidence = models.rcn_model()
     bp = infer.BP(fg.bp_state, temperature=temperature)
     evidence = {k: v.astype(np.float32) for k, v in evidence.items()}
-    label = "RCN-shaped: 20 x 80 variables of 625 states, 3 180 large-config EnumFactors, max-product"
+    label = ("RCN-shaped: 20 x 80 variables of 625 states, 3 180 large-config EnumFactors, " +
+             ("max-product" if name == "rcn" else "sum-product T=1"))
   else:
     raise ValueError(f"unknown workload {name}")
   iters = iters_override or iters
@@ -728,9 +730,9 @@ def main():
     quick = dict(steps=2, warmup=3, min_seconds=0.8)
     if world == 1:
       others = {}
-      for name in ("ising50", "deconv", "rcn", "ising50_batch", "heretic"):
+      for name in ("ising50", "deconv", "rcn", "rcn_sum", "ising50_batch", "heretic"):
         try:
-          r = measure(args, name, dev, rank, world, local_rank, parity_iters=0 if name == "rcn" else 2, **quick)
+          r = measure(args, name, dev, rank, world, local_rank, parity_iters=0 if name.startswith("rcn") else 2, **quick)
           others[name] = compact_record(name, r)
           del r
         except Exception as err:  # pylint: disable=broad-except

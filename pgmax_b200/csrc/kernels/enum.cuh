@@ -614,6 +614,198 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
 }
 
 // ---------------------------------------------------------------------------
+// K2c-sum: the SUM-product update (T > 0) of the same large sorted pairwise groups on the same
+// lane-per-state round schedule and the same round-ordered potentials (k_bigmax_permute): every
+// configuration is read ONCE per iteration.  The reference takes logsumexp over each
+// edge-state's configurations with the maximum first (pgmax/factor/enum.py:451-475,
+// jax.ops.segment_max then segment_sum of exp); visiting a configuration once means the maximum
+// is not known when its term is added, so both sides keep a running (maximum m, sum s of
+// exp((s_k - m) / T)) pair and rescale s when m grows ("online" logsumexp - the same value up to
+// fp32 rounding of the rescaling factors; tested against the oracle at the tolerance of the other
+// sum-product paths):
+//   * a-side (the lane's own state): registers; one rescale per trip, one ex2 per configuration;
+//   * b-side: per-warp private arrays Mw / Sw (conflict-free by the round schedule, as in the
+//     max-product kernel): read m, s - update - write back, warp barrier between rounds; the warps'
+//     pairs are merged once per factor.
+// exp((x - m) / T) = ex2((x - m) * log2(e) / T): MUFU.EX2, two per configuration.
+// Dynamic smem: (2 ns + 2 nwarps (n1 + 32) + 32) floats of the largest group.
+// Measured on the RCN graph at T = 1, B = 1 (profiles/r02_z_rcn_sum_ab.txt): 0.270 ms per launch
+// (0.44 of the HBM peak on the algorithmic bytes; the instruction mix - two MUFU and five
+// shared-memory accesses per configuration - bounds it, not the trip length: 0.270 - 0.290 ms
+// over trips of 4 - 12 rounds and 3 - 4 CTAs per SM) against 2.07 ms for the thread-per-edge-state
+// kernel k_enum_big, which walks every configuration list twice per side.
+// ---------------------------------------------------------------------------
+#ifndef PGX_BIGSUM_CTAS
+#define PGX_BIGSUM_CTAS 4
+#endif
+#ifndef PGX_SUM_TRIP
+#define PGX_SUM_TRIP 6
+#endif
+__global__ void __launch_bounds__(kThreads, PGX_BIGSUM_CTAS)
+k_enum_big_sumprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, const int2* __restrict__ units,
+                       int64_t num_units, unsigned int* __restrict__ counter, const int32_t* __restrict__ edge_vs,
+                       const float* __restrict__ lpR, const float* __restrict__ S, const float* __restrict__ m_old,
+                       float* __restrict__ m_new, RunArgs a) {
+  extern __shared__ float smem[];
+  __shared__ unsigned int s_unit, s_grp;
+  const int sh = mp.bx_log;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t total = num_units * mp.batch;
+  const float T = a.T, c = 1.4426950408889634f / T;
+  constexpr float kLow = -3.0e38f;  // "no configuration yet": finite, so that (-inf) - kLow is -inf, not NaN
+  constexpr int kTrip = PGX_SUM_TRIP;
+  auto next_group = [&]() {
+    unsigned int gi = 0;
+    if (lane == 0) gi = atomicAdd(&s_grp, 1u);
+    return int(__shfl_sync(0xffffffffu, gi, 0));
+  };
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) { s_unit = atomicAdd(counter, 1u); s_grp = 0; }
+    __syncthreads();
+    const int64_t unit = s_unit;
+    if (unit >= total) break;
+    const int64_t u = unit / mp.batch;
+    const int b = int(unit - u * mp.batch);
+    const int2 uf = units[u];
+    const BigMaxGroup& G = groups[uf.x];
+    const EnumBlockDev& blk = G.blk;
+    const int64_t f = uf.y;
+    const int ns = blk.ns, n0 = blk.edge_off[1], n1 = ns - n0;
+    const int wstride = n1 + 32;
+    float* q = smem;                        // [ns]
+    float* M = q + ns;                      // [ns] logsumexp values, then damped values
+    float* Mw = M + ns;                     // [kBigWarps][n1 + 32] per-warp partner-side maxima
+    float* Sw = Mw + kBigWarps * wstride;   // [kBigWarps][n1 + 32] ... and sums
+    float* red = Sw + kBigWarps * wstride;
+    const int64_t moff = lane_off(mp, a.Es, b);
+    const float* mo = m_old + moff;
+    float* mn = m_new + moff;
+    const float* SL = S + lane_off(mp, a.Vs, b);
+    const int64_t mbase = blk.msg_base(f), ebase = blk.edge_base(f);
+    for (int e = 0; e < 2; ++e) {
+      const int64_t vs = edge_vs[ebase + e];
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        q[s] = SL[(vs + s - s0) << sh] - mo[(mbase + s) << sh];
+        M[s] = 0.f;  // (idle schedule entries read their "q" from here: anything but NaN / +inf)
+      }
+    }
+    for (int i = threadIdx.x; i < kBigWarps * wstride; i += blockDim.x) { Mw[i] = kLow; Sw[i] = 0.f; }
+    __syncthreads();
+    {
+      const uint32_t qb_s = smem_u32(q) + 4u * n0;
+      const uint32_t mw_s = smem_u32(Mw + warp * wstride);
+      const uint32_t sw_off = 4u * kBigWarps * wstride;  // Sw slot = Mw slot + this
+      auto lds_f = [](uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; };
+      auto sts_f = [](uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); };
+      const float* __restrict__ lpr = lpR + G.perm_base + f * (int64_t(G.num_rounds) * 32) + lane;
+      const uint32_t* __restrict__ rbl = G.rounds_b + lane;
+      for (int grp = next_group(); grp < G.num_groups; grp = next_group()) {
+        const int a_own = G.lane_state[grp * 32 + lane];
+        const float qa = a_own < n0 ? q[a_own] : 0.f;
+        const int r_end = G.round_ptr[grp + 1];
+        const uint32_t idle2 = uint32_t((n1 + lane) << 2) * 0x10001u;
+        uint32_t en_n[kTrip / 2];
+        float rl_n[kTrip];
+        auto request = [&](int r0) {
+          if (r0 + kTrip <= r_end) {
+#pragma unroll
+            for (int p = 0; p < kTrip / 2; ++p) {
+              en_n[p] = __ldg(rbl + (size_t(r0 + 2 * p) << 4));
+              rl_n[2 * p] = __ldcs(lpr + (size_t(r0 + 2 * p) << 5));
+              rl_n[2 * p + 1] = __ldcs(lpr + (size_t(r0 + 2 * p + 1) << 5));
+            }
+          } else {
+#pragma unroll
+            for (int p = 0; p < kTrip / 2; ++p) {
+              const bool in = r0 + 2 * p < r_end;  // rounds come in pairs
+              en_n[p] = in ? __ldg(rbl + (size_t(r0 + 2 * p) << 4)) : idle2;
+              rl_n[2 * p] = in ? __ldcs(lpr + (size_t(r0 + 2 * p) << 5)) : -INFINITY;
+              rl_n[2 * p + 1] = in ? __ldcs(lpr + (size_t(r0 + 2 * p + 1) << 5)) : -INFINITY;
+            }
+          }
+        };
+        float m_a = kLow, s_a = 0.f;
+        int r0 = G.round_ptr[grp];
+        if (r0 < r_end) request(r0);
+        for (; r0 < r_end; r0 += kTrip) {
+          uint32_t en[kTrip / 2];
+          float rl[kTrip];
+#pragma unroll
+          for (int p = 0; p < kTrip / 2; ++p) en[p] = en_n[p];
+#pragma unroll
+          for (int p = 0; p < kTrip; ++p) rl[p] = rl_n[p];
+          if (r0 + kTrip < r_end) request(r0 + kTrip);
+          uint32_t b_s[kTrip];
+          float sk[kTrip];
+#pragma unroll
+          for (int p = 0; p < kTrip; ++p) {
+            b_s[p] = (p & 1) ? (en[p >> 1] >> 16) : (en[p >> 1] & 0xffffu);
+            sk[p] = lds_f(qb_s + b_s[p]);
+          }
+          float mt = -INFINITY;
+#pragma unroll
+          for (int p = 0; p < kTrip; ++p) {
+            sk[p] = (qa + sk[p]) + rl[p];  // idle entries: -inf
+            mt = fmaxf(mt, sk[p]);
+          }
+          // a-side: one rescale per trip
+          const float hi = fmaxf(m_a, mt);
+          s_a *= ex2_approx((m_a - hi) * c);
+          m_a = hi;
+#pragma unroll
+          for (int p = 0; p < kTrip; ++p) s_a += ex2_approx((sk[p] - hi) * c);
+          // b-side: read (m, s) - update - write, round by round
+#pragma unroll
+          for (int p = 0; p < kTrip; ++p) {
+            const uint32_t slot = mw_s + b_s[p];
+            const float m = lds_f(slot), sm = lds_f(slot + sw_off);
+            const float x = sk[p];
+            const float top = fmaxf(m, x);
+            const float e = ex2_approx((fminf(m, x) - top) * c);
+            sts_f(slot, top);
+            sts_f(slot + sw_off, x > m ? sm * e + 1.f : sm + e);
+            asm volatile("bar.warp.sync 0xffffffff;" ::: "memory");
+          }
+        }
+        if (a_own < n0) M[a_own] = T * logf(s_a) + m_a;  // no configuration: log(0) = -inf
+      }
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < n1; s += blockDim.x) {
+      float m = Mw[s];
+      for (int w = 1; w < kBigWarps; ++w) m = fmaxf(m, Mw[w * wstride + s]);
+      float sum = 0.f;
+      for (int w = 0; w < kBigWarps; ++w) sum += Sw[w * wstride + s] * ex2_approx((Mw[w * wstride + s] - m) * c);
+      M[n0 + s] = T * logf(sum) + m;
+    }
+    __syncthreads();
+    float dmax = 0.f;
+    for (int e = 0; e < 2; ++e) {
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      float mx = -INFINITY;
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const float nvs = damp(mo[(mbase + s) << sh], M[s] - q[s], a.d, a.one_minus_d);
+        M[s] = nvs;
+        mx = fmaxf(mx, nvs);
+      }
+      mx = block_max(mx, red);
+      for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+        const float out = fmaxf(M[s] - mx, kMsgNegInf);
+        const int64_t idx = (mbase + s) << sh;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
+      }
+    }
+    if (a.deltas != nullptr) {
+      dmax = block_max(dmax, red);
+      if (threadIdx.x == 0) publish_delta(a.deltas, int64_t(b) * a.delta_stride + a.delta_off, dmax);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Writes the two states of a binary edge whose factor->variable message is
 // (0, x) or (x, 0): damping + normalisation + clip + delta.
 //   lo = message index of the edge's state 0; mo / mn are lane pointers.

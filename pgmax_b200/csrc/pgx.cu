@@ -70,7 +70,7 @@ enum AttrGroup { kAttrBigMax = 0, kAttrBipMax = 1, kAttrBipSum = 2, kAttrBigEnum
                  kAttrMaxProd = 5, kAttrLattice = 6, kAttrSdlpMax = 7, kAttrSdlpSum = 8, kAttrLatticeBin = 9,
                  kAttrLatticeBinV1 = 10, kAttrLatticeBinV2 = 11, kAttrLatticeBinV3 = 12, kAttrLatticeBinV4 = 13,
                  kAttrLatticeBinV5 = 14, kAttrLatticeBinV6 = 15, kAttrLatticeBinV7 = 16, kAttrLatticeBinV8 = 17,
-                 kAttrLatticeBinV9 = 18, kAttrOrAndMax = 19, kAttrOrAndSum = 20 };
+                 kAttrLatticeBinV9 = 18, kAttrOrAndMax = 19, kAttrOrAndSum = 20, kAttrBigSum = 21 };
 
 struct EnumBlockPlan {
   pgx::EnumBlockDev dev{};
@@ -236,7 +236,7 @@ struct pgx_plan {
   const float* lpR_src = nullptr;  // potentials buffer the round-ordered copy was made from (PGX_RUN_POTENTIALS_UNCHANGED)
   float* d_energy_partial = nullptr;  // pgx_energy scratch
   int64_t energy_partial_floats = 0;
-  size_t bigmax_smem = 0;
+  size_t bigmax_smem = 0, bigsum_smem = 0;  // dynamic shared memory of the merged max- / sum-product launch
   unsigned int* d_bigmax_counter = nullptr;  // [2]: one work counter per chain of the half-batch pipeline
   // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remembered per plan (a plan
   // lives on one device), bit = kAttr* below
@@ -813,10 +813,33 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       if ((rc = prof_mark(plan, st, plan->dominant))) return rc;
     }
   }
+  // ... and its sum-product sibling, on the round-ordered potentials only
+  const bool merged_sum = kSum && plan->bigmax_units > 0 && plan->bigmax_perm_active && plan->bigsum_smem <= 200 * 1024 &&
+                          !(plan->disabled_paths & PGX_PATH_MERGED_MAX);
+  if (merged_sum) {
+    const bool dom = plan->dominant >= 0 && size_t(plan->dominant) < plan->enum_blocks.size() &&
+                     plan->enum_blocks[plan->dominant].bigmax >= 0;
+    if (attr_needed(kAttrBigSum))
+      PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_big_sumprod_all, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    unsigned int* const counter = plan->d_bigmax_counter + chain;
+    PGX_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    if (dom && (rc = prof_mark(plan, st, plan->dominant))) return rc;
+    const int per_sm = int(std::max<size_t>(1, std::min<size_t>(6, (227 * 1024) / (plan->bigsum_smem + 1024))));
+    const int64_t grid = std::min<int64_t>(plan->bigmax_units * mp.batch, int64_t(plan->num_sms) * per_sm);
+    pgx::k_enum_big_sumprod_all<<<unsigned(grid), pgx::kThreads, plan->bigsum_smem, st>>>(
+        mp, plan->d_bigmax_groups, plan->d_bigmax_units, plan->bigmax_units, counter, plan->d_edge_vs, plan->ws.lpR, S,
+        m_old, m_new, a);
+    if ((rc = check_launch(plan, "k_enum_big_sumprod_all"))) return rc;
+    if (dom) {
+      plan->dominant_name = "k_enum_big_sumprod_all";
+      plan->dominant_grid = grid;
+      if ((rc = prof_mark(plan, st, plan->dominant))) return rc;
+    }
+  }
   for (size_t bi = 0; bi < plan->enum_blocks.size(); ++bi) {
     EnumBlockPlan& eb = plan->enum_blocks[bi];
     const int64_t F = eb.dev.num_factors;
-    if (merged_max && eb.bigmax >= 0) continue;
+    if ((merged_max || merged_sum) && eb.bigmax >= 0) continue;
     // fused mode: the blocks outside the dense-grid kernel run beside it on the auxiliary stream
     const cudaStream_t main_enum_st = st;
     const cudaStream_t st = (fused && aux != nullptr && !lpull && eb.bip < 0) ? aux : main_enum_st;  // NOLINT
@@ -1382,6 +1405,7 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       if (smem > 200 * 1024 || eb.dev.num_factors >= INT32_MAX) { eb.bigmax = -1; continue; }
       eb.bigmax = int(groups.size());
       plan->bigmax_smem = std::max(plan->bigmax_smem, smem);
+      plan->bigsum_smem = std::max(plan->bigsum_smem, smem + size_t(nwarp) * (eb.dev.ns - eb.n0 + 32) * sizeof(float));
       plan->bigmax_es += eb.dev.num_factors * eb.dev.ns;
       pgx::BigMaxGroup g;
       g.blk = eb.dev;
@@ -2305,7 +2329,7 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
   // Merged max-product launch (RCN-size factors): with potentials shared by the batch and enough
   // iterations to amortise it, one pass copies the potentials into round order first.
   plan->bigmax_perm_active = false;
-  if (temperature == 0.f && plan->bigmax_units > 0 && !(plan->disabled_paths & (PGX_PATH_MERGED_MAX | PGX_PATH_PERM_POTENTIALS)) &&
+  if (plan->bigmax_units > 0 && !(plan->disabled_paths & (PGX_PATH_MERGED_MAX | PGX_PATH_PERM_POTENTIALS)) &&
       !pull && !lattice && lp.kind == 0 && num_iters >= 3 && plan->bigmax_perm_floats > 0) {
     if (ws.lpR == nullptr) {
       PGX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws.lpR), size_t(plan->bigmax_perm_floats) * sizeof(float)));

@@ -270,3 +270,67 @@ def test_unary_enum_closed_form_is_bit_identical(temperature, batch):
     graph = bp_oracle.graph_from_context(bp.context)
     want, _ = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 8, 0.5, temperature)
     np.testing.assert_allclose(got.ftov_msgs, want, atol=1e-6 if temperature == 0.0 else 1e-5)
+
+
+@pytest.mark.parametrize("temperature", [1.0, 0.3])
+@pytest.mark.parametrize("batch", [None, 3])
+@pytest.mark.parametrize("extreme", [False, True])
+def test_rcn_size_factors_sum_product_one_pass(temperature, batch, extreme):
+  """k_enum_big_sumprod_all: sum-product (T > 0) of RCN-size sorted pairwise factors on the round
+  schedule of the max-product launch - one visit per configuration, running (max, sum) pairs
+  ("online" logsumexp) instead of the reference's max-then-sum (pgmax/factor/enum.py:451-475).
+  Random potentials; `extreme`: some beyond the +-1e6 clip and some -inf (states left without a
+  finite configuration included) - messages of magnitude 1e6 there, so that case is held to the
+  fp32 oracle relatively; the plain case absolutely, judged by the fp64 oracle.  Also against
+  the generic thread-per-edge-state kernel (PATH_MERGED_MAX disabled); replayed from the CUDA
+  graph bit for bit."""
+  import models
+  from pgmax_b200.infer.bp_state import BPArrays
+
+  fg, groups, evidence = models.rcn_model(num_models=1, num_vars=6, radii=(2, 4, 7), extra_edges=2, seed=11)
+  rng = np.random.default_rng(3)
+  if batch is not None:
+    evidence = {vg: np.stack([np.where(rng.random(ev.shape) < 0.05, 1.0, -1.0) for _ in range(batch)])
+                for vg, ev in evidence.items()}
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  arrays = bp.init(evidence_updates=evidence)
+  lp = (rng.normal(size=arrays.log_potentials.shape) * 2.0).astype(np.float32)
+  if extreme:
+    lp[rng.integers(0, lp.size, size=50)] = 3e6
+    lp[rng.integers(0, lp.size, size=50)] = -np.inf
+  arrays = BPArrays(log_potentials=lp, ftov_msgs=arrays.ftov_msgs, evidence=arrays.evidence)
+  plan = bp.context.plan
+  iters = 6
+  before = plan.launch_count
+  got, got_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
+  merged = plan.launch_count - before
+  plan.disable_paths(plan.PATH_MERGED_MAX)
+  before = plan.launch_count
+  ref, ref_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
+  per_group = plan.launch_count - before
+  plan.disable_paths(0)
+  assert merged < per_group                  # one launch for all 7 factor groups (+ the permute pass)
+  graph = bp_oracle.graph_from_context(bp.context)
+  want, _ = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, iters, 0.5,
+                                     temperature)
+  with bp_oracle.precision(np.float64):
+    exact, _ = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, iters, 0.5,
+                                        temperature)
+  got_m, ref_m = np.asarray(got.ftov_msgs, np.float64), np.asarray(ref.ftov_msgs, np.float64)
+  want_m, exact_m = np.asarray(want, np.float64).reshape(got_m.shape), np.asarray(exact, np.float64).reshape(got_m.shape)
+  floor = exact_m <= -1e31
+  np.testing.assert_array_equal(got_m <= -1e31, floor)
+  err_got = np.abs(got_m - exact_m)[~floor].max()
+  err_ref = np.abs(ref_m - exact_m)[~floor].max()
+  err_oracle = np.abs(want_m - exact_m)[~floor].max()
+  print(f"vs fp64: one-pass kernel {err_got:.3g}, generic kernel {err_ref:.3g}, fp32 oracle {err_oracle:.3g}")
+  if extreme:
+    np.testing.assert_allclose(got_m[~floor], want_m[~floor], rtol=2e-6, atol=4e-5)
+    assert err_got <= 2.0 * err_oracle, (err_got, err_oracle)
+  else:
+    assert err_got <= max(2e-5, 2.0 * err_oracle), (err_got, err_oracle)
+    np.testing.assert_allclose(got_m, want_m, atol=4e-5)
+  for _ in range(2):                         # capture, replay
+    again, again_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
+    np.testing.assert_array_equal(again.ftov_msgs, got.ftov_msgs)
+    np.testing.assert_array_equal(again_d, got_d)
