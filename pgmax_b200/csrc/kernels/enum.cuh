@@ -1,6 +1,8 @@
 // pgx kernels - K2b / K2c: general EnumFactors, small and RCN-size.  Part of pgx_kernels.cuh (included in this order).
 #pragma once
 
+#include <type_traits>
+
 #include "dense_grid.cuh"
 
 namespace pgx {
@@ -40,11 +42,17 @@ struct EnumBlockDev {
 // -m_old, the potentials are NOT clipped, and the update is written as is (normalize=False,
 // no damping, no delta); S is unused.
 // ---------------------------------------------------------------------------
-template <bool kSumProduct, bool kRaw = false>
+// kSmem: the two per-thread arrays live in dynamic shared memory, one column per thread
+// ([2 ns][blockDim] floats: conflict-free, sized by the block's ns) instead of two 64-float local
+// arrays - 512 B of local memory per thread is 1 MB per SM at full occupancy, four times the L1,
+// so the dynamically indexed walks went to L2 (the 17 x 3-state "heretic" factors: 1.28 ms per
+// iteration before).  Same operations in the same order: bit-identical.
+template <bool kSumProduct, bool kRaw = false, bool kSmem = false>
 __global__ void __launch_bounds__(kThreads)
 k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
              const float* __restrict__ S, const float* __restrict__ m_old,
              float* __restrict__ m_new, RunArgs a) {
+  extern __shared__ float es_cols[];
   UnitLoop L = unit_loop(mp, blk.num_factors);
   if (!L.b_ok) return;
   float dmax = 0.f;
@@ -55,8 +63,18 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
   const float* SL = S + lane_off(mp, a.Vs, L.b);
   const LaneView lpL = lane_view(lp, mp, L.b);
   const float T = a.T;
-  float q[kSmallMaxNS];
-  float nv[kSmallMaxNS];
+  struct Local { float v[kSmallMaxNS]; };
+  struct Column {
+    float* p;
+    __device__ __forceinline__ float& operator[](int s) const { return p[s * kThreads]; }
+  };
+  typename std::conditional<kSmem, Column, Local>::type q_store, nv_store;
+  if constexpr (kSmem) {
+    q_store.p = es_cols + threadIdx.x;
+    nv_store.p = es_cols + size_t(blk.ns) * kThreads + threadIdx.x;
+  }
+  auto q = [&](int s) -> float& { if constexpr (kSmem) return q_store[s]; else return q_store.v[s]; };
+  auto nv = [&](int s) -> float& { if constexpr (kSmem) return nv_store[s]; else return nv_store.v[s]; };
   for (int64_t f = L.u; f < L.u_end; f += L.step) {
     const int64_t mbase = blk.msg_base(f);
     const int64_t ebase = blk.edge_base(f);
@@ -64,7 +82,7 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
     for (int e = 0; e < blk.arity; ++e) {
       const int64_t vs = edge_vs[ebase + e];
       for (int s = blk.edge_off[e]; s < blk.edge_off[e + 1]; ++s)
-        q[s] = kRaw ? -mo[(mbase + s) << sh] : SL[(vs + s - blk.edge_off[e]) << sh] - mo[(mbase + s) << sh];
+        q(s) = kRaw ? -mo[(mbase + s) << sh] : SL[(vs + s - blk.edge_off[e]) << sh] - mo[(mbase + s) << sh];
     }
     for (int s = 0; s < blk.ns; ++s) {
       const int j0 = blk.t_ptr[s], j1 = blk.t_ptr[s + 1];
@@ -72,7 +90,7 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
       for (int j = j0; j < j1; ++j) {
         const int k = blk.t_k[j];
         float sk = 0.f;
-        for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
+        for (int e = 0; e < blk.arity; ++e) sk += q(blk.cfg_es[k * blk.arity + e]);
         sk += kRaw ? lpL.at(pbase + k) : clip_lp(lpL.at(pbase + k));
         M = fmaxf(M, sk);
       }
@@ -82,23 +100,23 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
         for (int j = j0; j < j1; ++j) {
           const int k = blk.t_k[j];
           float sk = 0.f;
-          for (int e = 0; e < blk.arity; ++e) sk += q[blk.cfg_es[k * blk.arity + e]];
+          for (int e = 0; e < blk.arity; ++e) sk += q(blk.cfg_es[k * blk.arity + e]);
           sk += kRaw ? lpL.at(pbase + k) : clip_lp(lpL.at(pbase + k));
           sum += expf((sk - M) / T);
         }
         val = T * logf(sum) + M;
       }
-      nv[s] = kRaw ? val - q[s] : damp(mo[(mbase + s) << sh], val - q[s], a.d, a.one_minus_d);
+      nv(s) = kRaw ? val - q(s) : damp(mo[(mbase + s) << sh], val - q(s), a.d, a.one_minus_d);
     }
     if constexpr (kRaw) {
-      for (int s = 0; s < blk.ns; ++s) mn[(mbase + s) << sh] = nv[s];
+      for (int s = 0; s < blk.ns; ++s) mn[(mbase + s) << sh] = nv(s);
     } else {
       for (int e = 0; e < blk.arity; ++e) {
         const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
         float mx = -INFINITY;
-        for (int s = s0; s < s1; ++s) mx = fmaxf(mx, nv[s]);
+        for (int s = s0; s < s1; ++s) mx = fmaxf(mx, nv(s));
         for (int s = s0; s < s1; ++s) {
-          const float out = fmaxf(nv[s] - mx, kMsgNegInf);
+          const float out = fmaxf(nv(s) - mx, kMsgNegInf);
           const int64_t idx = (mbase + s) << sh;
           dmax = fmaxf(dmax, fabsf(out - mo[idx]));
           mn[idx] = out;
@@ -107,6 +125,94 @@ k_enum_small(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
     }
   }
   if (!kRaw) publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
+// K2b-cm: the same update CONFIGURATION-major.  k_enum_small walks, for every edge-state, the
+// list of configurations that contain it: every configuration's score s_k is formed arity times
+// per pass, behind three index loads each.  Here a thread walks its factor's configurations once
+// per pass - s_k once, then arity read-max-write (pass 1) / read-add-write (pass 2) updates of
+// per-thread shared-memory columns M[], Z[] - which visits the terms of every edge-state in the
+// same ascending configuration order as the lists do:
+//   * max-product: the same maxima (order-independent): bit-identical to k_enum_small;
+//   * sum-product: the same order of additions; exp((s_k - M) / T) is ex2((s_k - M) * log2(e) / T)
+//     (MUFU.EX2, relative error 2^-22, the approximation the pairwise kernels already use,
+//     pairwise.cuh) instead of expf of a division: within the sum-product tolerance (tested), and
+//     a fifth of the instructions.
+// Dynamic smem: (2 or 3) * ns * blockDim floats.
+// ---------------------------------------------------------------------------
+// kArity: 2 / 3 = compile-time arity (the walks over a configuration's variables unroll; with a
+// run-time arity those loops were two thirds of the instructions), 0 = any.
+template <bool kSumProduct, int kArity>
+__global__ void __launch_bounds__(kThreads)
+k_enum_small_cm(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
+                const float* __restrict__ S, const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  extern __shared__ float es_cols[];
+  UnitLoop L = unit_loop(mp, blk.num_factors);
+  if (!L.b_ok) return;
+  float dmax = 0.f;
+  const int sh = mp.bx_log, ns = blk.ns, arity = kArity > 0 ? kArity : blk.arity, C = blk.num_configs;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const LaneView lpL = lane_view(lp, mp, L.b);
+  const float T = a.T, c = 1.4426950408889634f / T;
+  float* q = es_cols + threadIdx.x;          // [ns] columns, stride kThreads
+  float* M = q + size_t(ns) * kThreads;      // maxima, then the damped values
+  float* Z = M + size_t(ns) * kThreads;      // sums (sum-product only)
+  const int32_t* __restrict__ cfg = blk.cfg_es;
+  for (int64_t f = L.u; f < L.u_end; f += L.step) {
+    const int64_t mbase = blk.msg_base(f), ebase = blk.edge_base(f), pbase = blk.pot_base(f);
+    for (int e = 0; e < arity; ++e) {
+      const int64_t vs = edge_vs[ebase + e];
+      for (int s = blk.edge_off[e]; s < blk.edge_off[e + 1]; ++s) {
+        q[s * kThreads] = SL[(vs + s - blk.edge_off[e]) << sh] - mo[(mbase + s) << sh];
+        M[s * kThreads] = -INFINITY;
+        if (kSumProduct) Z[s * kThreads] = 0.f;
+      }
+    }
+    auto score = [&](int k) {
+      float sk = 0.f;
+#pragma unroll
+      for (int e = 0; e < arity; ++e) sk += q[cfg[k * arity + e] * kThreads];
+      return sk + clip_lp(lpL.at(pbase + k));
+    };
+    for (int k = 0; k < C; ++k) {
+      const float sk = score(k);
+#pragma unroll
+      for (int e = 0; e < arity; ++e) {
+        float* slot = M + cfg[k * arity + e] * kThreads;
+        *slot = fmaxf(*slot, sk);
+      }
+    }
+    if (kSumProduct) {
+      for (int k = 0; k < C; ++k) {
+        const float sk = score(k);
+#pragma unroll
+        for (int e = 0; e < arity; ++e) {
+          const int es = cfg[k * arity + e] * kThreads;
+          Z[es] += ex2_approx((sk - M[es]) * c);
+        }
+      }
+    }
+    for (int s = 0; s < ns; ++s) {
+      const float val = kSumProduct ? T * logf(Z[s * kThreads]) + M[s * kThreads] : M[s * kThreads];
+      M[s * kThreads] = damp(mo[(mbase + s) << sh], val - q[s * kThreads], a.d, a.one_minus_d);
+    }
+    for (int e = 0; e < arity; ++e) {
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      float mx = -INFINITY;
+      for (int s = s0; s < s1; ++s) mx = fmaxf(mx, M[s * kThreads]);
+      for (int s = s0; s < s1; ++s) {
+        const float out = fmaxf(M[s * kThreads] - mx, kMsgNegInf);
+        const int64_t idx = (mbase + s) << sh;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
+      }
+    }
+  }
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
 }
 
 // ---------------------------------------------------------------------------
@@ -626,7 +732,8 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
 //   * a-side (the lane's own state): registers; one rescale per trip, one ex2 per configuration;
 //   * b-side: per-warp private arrays Mw / Sw (conflict-free by the round schedule, as in the
 //     max-product kernel): read m, s - update - write back, warp barrier between rounds; the warps'
-//     pairs are merged once per factor.
+//     pairs are merged once per factor, in warp order (lane-groups are handed to the warps
+//     statically: run-to-run deterministic).
 // exp((x - m) / T) = ex2((x - m) * log2(e) / T): MUFU.EX2, two per configuration.
 // Dynamic smem: (2 ns + 2 nwarps (n1 + 32) + 32) floats of the largest group.
 // Measured on the RCN graph at T = 1, B = 1 (profiles/r02_z_rcn_sum_ab.txt): 0.270 ms per launch
@@ -647,21 +754,16 @@ k_enum_big_sumprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
                        const float* __restrict__ lpR, const float* __restrict__ S, const float* __restrict__ m_old,
                        float* __restrict__ m_new, RunArgs a) {
   extern __shared__ float smem[];
-  __shared__ unsigned int s_unit, s_grp;
+  __shared__ unsigned int s_unit;
   const int sh = mp.bx_log;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t total = num_units * mp.batch;
   const float T = a.T, c = 1.4426950408889634f / T;
   constexpr float kLow = -3.0e38f;  // "no configuration yet": finite, so that (-inf) - kLow is -inf, not NaN
   constexpr int kTrip = PGX_SUM_TRIP;
-  auto next_group = [&]() {
-    unsigned int gi = 0;
-    if (lane == 0) gi = atomicAdd(&s_grp, 1u);
-    return int(__shfl_sync(0xffffffffu, gi, 0));
-  };
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) { s_unit = atomicAdd(counter, 1u); s_grp = 0; }
+    if (threadIdx.x == 0) s_unit = atomicAdd(counter, 1u);
     __syncthreads();
     const int64_t unit = s_unit;
     if (unit >= total) break;
@@ -701,7 +803,13 @@ k_enum_big_sumprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
       auto sts_f = [](uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); };
       const float* __restrict__ lpr = lpR + G.perm_base + f * (int64_t(G.num_rounds) * 32) + lane;
       const uint32_t* __restrict__ rbl = G.rounds_b + lane;
-      for (int grp = next_group(); grp < G.num_groups; grp = next_group()) {
+      // STATIC hand-out of the lane-groups (boustrophedon over the warps; the plan orders the groups
+      // by list length): which warp adds which terms into its private (m, s) arrays fixes the fp32
+      // rounding of the merged sums, so a dynamic hand-out (as in the max-product kernel, where
+      // the order cannot matter) would make runs differ in the last bits
+      for (int pass = 0; pass * kBigWarps < G.num_groups; ++pass) {
+        const int grp = pass * kBigWarps + ((pass & 1) ? kBigWarps - 1 - warp : warp);
+        if (grp >= G.num_groups) continue;
         const int a_own = G.lane_state[grp * 32 + lane];
         const float qa = a_own < n0 ? q[a_own] : 0.f;
         const int r_end = G.round_ptr[grp + 1];

@@ -70,7 +70,8 @@ enum AttrGroup { kAttrBigMax = 0, kAttrBipMax = 1, kAttrBipSum = 2, kAttrBigEnum
                  kAttrMaxProd = 5, kAttrLattice = 6, kAttrSdlpMax = 7, kAttrSdlpSum = 8, kAttrLatticeBin = 9,
                  kAttrLatticeBinV1 = 10, kAttrLatticeBinV2 = 11, kAttrLatticeBinV3 = 12, kAttrLatticeBinV4 = 13,
                  kAttrLatticeBinV5 = 14, kAttrLatticeBinV6 = 15, kAttrLatticeBinV7 = 16, kAttrLatticeBinV8 = 17,
-                 kAttrLatticeBinV9 = 18, kAttrOrAndMax = 19, kAttrOrAndSum = 20, kAttrBigSum = 21 };
+                 kAttrLatticeBinV9 = 18, kAttrOrAndMax = 19, kAttrOrAndSum = 20, kAttrBigSum = 21, kAttrEnumSmallMax = 22,
+                 kAttrEnumSmallSum = 23, kAttrEnumCmMax = 24, kAttrEnumCmSum = 25 };
 
 struct EnumBlockPlan {
   pgx::EnumBlockDev dev{};
@@ -892,7 +893,33 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       pgx::k_enum_unary<<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old, m_new, a);
       if ((rc = check_launch(plan, "k_enum_unary"))) return rc;
     } else if (eb.variant == kSmall || (eb.variant == kUnary && eb.dev.ns <= pgx::kSmallMaxNS)) {
-      pgx::k_enum_small<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
+      // configuration-major walk (k_enum_small_cm) while its three columns leave room for two CTAs per SM
+      if (eb.dev.ns <= 32 && !(plan->disabled_paths & PGX_PATH_ENUM_CONFIG_MAJOR)) {
+        const size_t smem = size_t(kSum ? 3 : 2) * eb.dev.ns * pgx::kThreads * sizeof(float);
+        if (attr_needed(kSum ? kAttrEnumCmSum : kAttrEnumCmMax)) {
+          const int most = int(size_t(3) * 32 * pgx::kThreads * sizeof(float));
+          PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_small_cm<kSum, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+          PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_small_cm<kSum, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+          PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_small_cm<kSum, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+        }
+#define PGX_ENUM_CM(ARITY)                                                                                              \
+  pgx::k_enum_small_cm<kSum, ARITY><<<grid_for(plan, mp, F), pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs, lp, \
+                                                                                         S, m_old, m_new, a)
+        if (eb.dev.arity == 2) PGX_ENUM_CM(2);
+        else if (eb.dev.arity == 3) PGX_ENUM_CM(3);
+        else PGX_ENUM_CM(0);
+#undef PGX_ENUM_CM
+        if ((rc = check_launch(plan, "k_enum_small_cm"))) return rc;
+        if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_small_cm";
+        if ((rc = prof_mark(plan, st, int(bi)))) return rc;
+        continue;
+      }
+      // per-thread columns of q / damped values in shared memory (kernels/enum.cuh)
+      const size_t smem = size_t(2) * eb.dev.ns * pgx::kThreads * sizeof(float);
+      if (attr_needed(kSum ? kAttrEnumSmallSum : kAttrEnumSmallMax))
+        PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_small<kSum, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      int(size_t(2) * pgx::kSmallMaxNS * pgx::kThreads * sizeof(float))));
+      pgx::k_enum_small<kSum, false, true><<<grid_for(plan, mp, F), pgx::kThreads, smem, st>>>(
           mp, eb.dev, plan->d_edge_vs, lp, S, m_old, m_new, a);
       if ((rc = check_launch(plan, "k_enum_small"))) return rc;
     } else {

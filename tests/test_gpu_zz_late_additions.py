@@ -334,3 +334,68 @@ def test_rcn_size_factors_sum_product_one_pass(temperature, batch, extreme):
     again, again_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
     np.testing.assert_array_equal(again.ftov_msgs, got.ftov_msgs)
     np.testing.assert_array_equal(again_d, got_d)
+
+
+@pytest.mark.parametrize("temperature", [0.0, 1.0, 0.4])
+@pytest.mark.parametrize("batch", [None, 5, 70])
+def test_small_enum_configuration_major_walk(temperature, batch):
+  """k_enum_small_cm (small EnumFactors, <= 32 edge-states: one walk over the configurations per
+  pass, per-thread shared-memory columns) against k_enum_small (PATH_ENUM_CONFIG_MAJOR disabled:
+  per-edge-state list walks) and the oracle, on 17 x 3-state pairwise factors (the reference's
+  "heretic" test model, tests/test_pgmax.py:424-475, cut to 8 x 8 hidden variables), ragged
+  three-variable factors with a sparse configuration table (edge-states in one configuration only
+  / in none), and potentials beyond the clip.  Max-product: bit-identical.  Sum-product: ex2
+  instead of expf, same order of additions - at the sum-product tolerance, judged by fp64."""
+  from pgmax_b200.infer.bp_state import BPArrays
+  rng = np.random.default_rng(2)
+  pixels = vgroup.NDVarArray(shape=(10, 10), num_states=3)
+  hidden = vgroup.NDVarArray(shape=(8, 8), num_states=17)
+  extra = vgroup.NDVarArray(shape=(6,), num_states=np.array([2, 4, 3, 2, 4, 3]))
+  fg = fgraph.FactorGraph([pixels, hidden, extra])
+  for dr in range(3):
+    for dc in range(3):
+      fg.add_factors(fgroup.PairwiseFactorGroup(
+          variables_for_factors=[[hidden[r, c], pixels[r + dr, c + dc]] for r in range(8) for c in range(8)],
+          log_potential_matrix=rng.normal(size=(17, 3))))
+  # sparse three-variable table over (2, 4, 3) states: state 3 of the middle variable is in no configuration
+  configs = np.array([[0, 0, 0], [0, 1, 2], [1, 2, 1], [1, 0, 2], [0, 2, 0], [1, 1, 1]])
+  fg.add_factors(fgroup.EnumFactorGroup(
+      variables_for_factors=[[extra[0], extra[1], extra[2]], [extra[3], extra[4], extra[5]]],
+      factor_configs=configs, log_potentials=rng.normal(size=(2, 6))))
+  fg.add_factors(fgroup.EnumFactorGroup(variables_for_factors=[[extra[0], pixels[0, 0]]],
+                                        factor_configs=np.array([[0, 0], [1, 1], [1, 2]])))
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  lead = () if batch is None else (batch,)
+  arrays = bp.init(evidence_updates={pixels: rng.gumbel(size=lead + (10, 10, 3)),
+                                     hidden: rng.gumbel(size=lead + (8, 8, 17)),
+                                     extra: rng.gumbel(size=lead + (6, 4))})
+  lp = np.array(arrays.log_potentials, dtype=np.float32)
+  lp[rng.integers(0, lp.size, size=4)] = -3e6
+  arrays = BPArrays(log_potentials=lp, ftov_msgs=arrays.ftov_msgs, evidence=arrays.evidence)
+  plan = bp.context.plan
+  iters = 7
+  got, got_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
+  plan.disable_paths(plan.PATH_ENUM_CONFIG_MAJOR)
+  ref, ref_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
+  plan.disable_paths(0)
+  graph = bp_oracle.graph_from_context(bp.context)
+  want, want_d = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, iters, 0.5,
+                                          temperature)
+  got_m, ref_m = np.asarray(got.ftov_msgs, np.float64), np.asarray(ref.ftov_msgs, np.float64)
+  want_m = np.asarray(want, np.float64).reshape(got_m.shape)
+  if temperature == 0.0:
+    np.testing.assert_array_equal(got_m, ref_m)
+    np.testing.assert_array_equal(got_d, ref_d)
+    np.testing.assert_array_equal(got_m, want_m)
+    return
+  with bp_oracle.precision(np.float64):
+    exact, _ = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, iters, 0.5,
+                                        temperature)
+  exact_m = np.asarray(exact, np.float64).reshape(got_m.shape)
+  floor = exact_m <= -1e31
+  np.testing.assert_array_equal(got_m <= -1e31, floor)
+  err_got, err_ref = np.abs(got_m - exact_m)[~floor].max(), np.abs(ref_m - exact_m)[~floor].max()
+  err_oracle = np.abs(want_m - exact_m)[~floor].max()
+  print(f"vs fp64: configuration-major {err_got:.3g}, list walk {err_ref:.3g}, fp32 oracle {err_oracle:.3g}")
+  assert err_got <= max(1e-5, 2.0 * err_oracle), (err_got, err_oracle)
+  np.testing.assert_allclose(got_m[~floor], want_m[~floor], atol=2e-5, rtol=2e-6)
