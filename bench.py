@@ -590,6 +590,8 @@ def roofline_of(name, rec, ms):
   # sample and iteration than the reference layout
   if rec["fused_run"]:
     saved = 8 * plan.compressed_edges * batch
+  elif prof_name == "k_enum_pw2_bin":
+    saved = 8 * (es // 2) * batch   # generic two-pass path on binary-difference storage
   elif prof_name == "k_lattice_bin":
     saved = 8 * (es // 2) + 4 * es  # + the incidence index this kernel does not read
   else:

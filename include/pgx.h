@@ -292,7 +292,7 @@ int64_t pgx_plan_compressed_edges(const pgx_plan* plan);
 #define PGX_PATH_LATTICE 1u
 #define PGX_PATH_RESIDENT 2u
 #define PGX_PATH_PULL 4u
-#define PGX_PATH_MERGED_MAX 8u /* one launch for all large sorted pairwise max-product groups */
+#define PGX_PATH_MERGED_MAX 8u /* one launch for all large sorted pairwise groups (k_enum_big_maxprod_all; T > 0 on round-ordered potentials: k_enum_big_sumprod_all) */
 #define PGX_PATH_LATTICE_STREAM 32u /* persistent TMA variant of the lattice kernel (large lattices) */
 #define PGX_PATH_AUX_STREAM 64u /* the smaller of the OR / AND groups on an auxiliary stream */
 #define PGX_PATH_WIDE_SPLIT 128u /* wide OR / AND update as a serial reduce launch + a parent-parallel emit launch */
@@ -300,11 +300,12 @@ int64_t pgx_plan_compressed_edges(const pgx_plan* plan);
 #define PGX_PATH_PERM_POTENTIALS 512u /* merged max-product launch reads a round-ordered copy of the potentials */
 #define PGX_PATH_HALF_BATCH 1024u /* single-pass mode: the two halves of a batch of >= 16 sample tiles as two pipelined chains on two streams */
 #define PGX_PATH_STAGED_WIRING 2048u /* uniform OR / AND groups: wiring of a CTA's factor range staged in shared memory */
-#define PGX_PATH_TAIL_SPLIT 4096u /* OR / AND graphs: <= 8 samples beyond the last full tile of 32 run on their own stream */
+#define PGX_PATH_TAIL_SPLIT 4096u /* OR / AND graphs: a short batch tail beyond the last full tile of 32 samples runs beside the full tiles (fused path: packed k_or_and_fused launch, <= 16 samples; separate kernels: second plan, <= 8 samples) */
 #define PGX_PATH_ORAND_FUSED 16384u /* OR factors over degree-2 children of two-parent AND factors: one fused launch (k_or_and_fused) */
 #define PGX_PATH_VARSUM_COOP 32768u /* sums of very high-degree variables: a CTA per variable gathers through shared memory */
 #define PGX_PATH_ENUM_UNARY 65536u /* one-variable EnumFactors over all states: closed form (k_enum_unary) instead of k_enum_small */
 #define PGX_PATH_ENUM_CONFIG_MAJOR 131072u /* small EnumFactors (<= 32 edge-states): configuration-major walk (k_enum_small_cm) instead of k_enum_small */
+#define PGX_PATH_GENERIC_BIN 262144u /* all-binary pairwise graphs on the generic two-pass path: binary-difference storage (k_var_sums_bin + k_enum_pw2_bin) */
 #define PGX_PATH_LATTICE_BIN 8192u /* large single-sample lattices on binary-difference storage (k_lattice_bin) */
 #define PGX_PATH_LOGICAL_BIN 256u /* ... with the messages in binary-difference storage (one float per edge) */
 int pgx_plan_disable_paths(pgx_plan* plan, uint32_t mask);

@@ -256,6 +256,39 @@ k_enum_unary(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs,
   publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
 }
 
+// K2b-unary on binary-difference storage (two-state variable; see k_enum_pw2_bin): row = edge index.
+__global__ void __launch_bounds__(kThreads)
+k_enum_unary_bin(BatchMap mp, EnumBlockDev blk, int64_t E, const int32_t* __restrict__ edge_vs, View lp,
+                 const float* __restrict__ S, const float* __restrict__ c_old, float* __restrict__ c_new, RunArgs a) {
+  UnitLoop L = unit_loop(mp, blk.num_factors);
+  if (!L.b_ok) return;
+  float dmax = 0.f;
+  const int64_t coff = lane_off(mp, E, L.b);
+  const float* co = c_old + coff;
+  float* cn = c_new + coff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const LaneView lpL = lane_view(lp, mp, L.b);
+  for (int64_t f = L.u; f < L.u_end; f += L.step) {
+    const int64_t row = blk.msg_base(f) >> 1, pbase = blk.pot_base(f);
+    const int64_t vs = edge_vs[blk.edge_base(f)];
+    float m[2];
+    expand_bin(co[row << 5], m[0], m[1]);
+    float n[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const float q = SL[(vs + s) << 5] - m[s];
+      const float M = (0.f + q) + clip_lp(lpL.at(pbase + s));
+      n[s] = damp(m[s], M - q, a.d, a.one_minus_d);
+    }
+    const float mx = fmaxf(n[0], n[1]);
+    n[0] = fmaxf(n[0] - mx, kMsgNegInf);
+    n[1] = fmaxf(n[1] - mx, kMsgNegInf);
+    dmax = fmaxf(dmax, fmaxf(fabsf(n[0] - m[0]), fabsf(n[1] - m[1])));
+    cn[row << 5] = n[1] - n[0];
+  }
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
 // ---------------------------------------------------------------------------
 // K2c: EnumFactor update, large factors (RCN: 2 x 625 states, up to 375 769
 // configurations): one CTA per (factor, sample).  q and the damped values live

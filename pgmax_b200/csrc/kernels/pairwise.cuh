@@ -153,6 +153,51 @@ k_enum_pw2(BatchMap mp, int64_t num_factors, int64_t first_edge, int64_t first_m
 }
 
 // ---------------------------------------------------------------------------
+// K2a-bin: the same update with the messages in binary-difference storage (graphs whose every
+// edge has two states; full sample tiles): a normalised message is (0, x) or (-x, 0), so ONE float
+// x = m1 - m0 per edge is kept between iterations (NaN = both states at the -1e32 floor) - half
+// the message bytes of k_var_sums + k_enum_pw2, which are bandwidth-bound.  Expanding is exact and
+// the arithmetic on the expanded values is pw2_update's: bit-identical to k_enum_pw2 (tested).
+// c_old / c_new: [tile][E][32], row = edge index.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void expand_bin(float x, float& m0, float& m1) {
+  const bool fl = x != x;
+  m0 = fl ? kMsgNegInf : fminf(-x, 0.f);
+  m1 = fl ? kMsgNegInf : fminf(x, 0.f);
+}
+
+template <bool kSumProduct>
+__global__ void __launch_bounds__(kThreads)
+k_enum_pw2_bin(BatchMap mp, int64_t num_factors, int64_t first_edge, int64_t first_pot, int64_t E,
+               const int32_t* __restrict__ edge_vs, View lp, const float* __restrict__ S,
+               const float* __restrict__ c_old, float* __restrict__ c_new, RunArgs a) {
+  UnitLoop L = unit_loop(mp, num_factors);
+  if (!L.b_ok) return;
+  float dmax = 0.f;
+  const int64_t coff = lane_off(mp, E, L.b);
+  const float* co = c_old + coff;
+  float* cn = c_new + coff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const LaneView lpL = lane_view(lp, mp, L.b);
+  for (int64_t f = L.u; f < L.u_end; f += L.step) {
+    const int64_t e = first_edge + 2 * f;
+    const int64_t vs0 = edge_vs[e], vs1 = edge_vs[e + 1];
+    const float x0 = co[e << 5], x1 = co[(e + 1) << 5];
+    const float Sv[4] = {SL[vs0 << 5], SL[(vs0 + 1) << 5], SL[vs1 << 5], SL[(vs1 + 1) << 5]};
+    const int64_t pb = first_pot + 4 * f;
+    const float lpv[4] = {clip_lp(lpL.at(pb)), clip_lp(lpL.at(pb + 1)), clip_lp(lpL.at(pb + 2)),
+                          clip_lp(lpL.at(pb + 3))};
+    float m[4], n[4];
+    expand_bin(x0, m[0], m[1]);
+    expand_bin(x1, m[2], m[3]);
+    dmax = fmaxf(dmax, pw2_update<kSumProduct>(m, Sv, lpv, a, n));
+    cn[e << 5] = n[1] - n[0];
+    cn[(e + 1) << 5] = n[3] - n[2];
+  }
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
 // K2a-pull: pairwise-binary block on LOW-DEGREE variables (grids: Ising).  One
 // pass per iteration without a var-sum array: every (factor, sample) thread
 // re-derives the sums of its two variables by walking their incident-edge lists

@@ -251,6 +251,77 @@ k_var_sums_big_bin(int batch, int nbt, int64_t E, int64_t Vs, const int2* __rest
   }
 }
 
+// K1-bin: the sums of ALL variables of a graph whose variables are all binary, messages in
+// binary-difference storage (k_enum_pw2_bin): thread per (variable, sample), both states' sums in
+// one walk, every stored difference read once.  The same additions in the same order as
+// k_var_sums on the expanded messages: bit-identical.
+__global__ void __launch_bounds__(kThreads)
+k_var_sums_bin(BatchMap mp, int64_t num_vars, int64_t E, int64_t Vs, const int2* __restrict__ vs_csr,
+               const int32_t* __restrict__ var_edge_msg, View ev, const float* __restrict__ c,
+               float* __restrict__ S) {
+  UnitLoop L = unit_loop(mp, num_vars);
+  if (!L.b_ok) return;
+  const LaneView evL = lane_view(ev, mp, L.b);
+  const float* cL = c + lane_off(mp, E, L.b);
+  float* SL = S + lane_off(mp, Vs, L.b);
+  auto add = [](float x, float& acc0, float& acc1) {
+    const bool fl = x != x;  // both states at the floor
+    acc0 += fl ? kMsgNegInf : fminf(-x, 0.f);
+    acc1 += fl ? kMsgNegInf : fminf(x, 0.f);
+  };
+  for (int64_t u0 = L.u; u0 < L.u_end; u0 += kVsUnits * L.step) {
+    int2 row[kVsUnits];  // (begin, end) of the variable's incident edges
+    bool low = true;
+#pragma unroll
+    for (int u = 0; u < kVsUnits; ++u) {
+      const int64_t v = 2 * (u0 + u * L.step);
+      const int2 r = u0 + u * L.step < L.u_end ? vs_csr[v] : make_int2(0, 0);
+      row[u] = make_int2(r.x, r.x + (r.y >> kVsStateBits));
+      low = low && (row[u].y - row[u].x <= kVsLowDeg);
+    }
+    if (low) {
+      float a0[kVsUnits], a1[kVsUnits], x[kVsUnits][kVsLowDeg];
+#pragma unroll
+      for (int u = 0; u < kVsUnits; ++u) {
+        const int64_t v = 2 * (u0 + u * L.step);
+        const bool on = u0 + u * L.step < L.u_end;
+        a0[u] = on ? evL.at(v) : 0.f;
+        a1[u] = on ? evL.at(v + 1) : 0.f;
+#pragma unroll
+        for (int j = 0; j < kVsLowDeg; ++j)
+          x[u][j] = (row[u].x + j < row[u].y) ? cL[int64_t(var_edge_msg[row[u].x + j] >> 1) << 5] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kVsUnits; ++u) {
+#pragma unroll
+        for (int j = 0; j < kVsLowDeg; ++j)
+          if (row[u].x + j < row[u].y) add(x[u][j], a0[u], a1[u]);
+        const int64_t v = 2 * (u0 + u * L.step);
+        if (u0 + u * L.step < L.u_end) { SL[v << 5] = a0[u]; SL[(v + 1) << 5] = a1[u]; }
+      }
+      continue;
+    }
+#pragma unroll 1
+    for (int u = 0; u < kVsUnits; ++u) {
+      if (u0 + u * L.step >= L.u_end) break;
+      const int64_t v = 2 * (u0 + u * L.step);
+      float acc0 = evL.at(v), acc1 = evL.at(v + 1);
+      int64_t k = row[u].x;
+      const int64_t k1 = row[u].y;
+      for (; k + 16 <= k1; k += 16) {  // independent loads 16 at a time, added in ascending order
+        float x[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = cL[int64_t(var_edge_msg[k + j] >> 1) << 5];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) add(x[j], acc0, acc1);
+      }
+      for (; k < k1; ++k) add(cL[int64_t(var_edge_msg[k] >> 1) << 5], acc0, acc1);
+      SL[v << 5] = acc0;
+      SL[(v + 1) << 5] = acc1;
+    }
+  }
+}
+
 // Full tile-blocked messages (normalised, every edge two states) -> binary-difference storage.
 __global__ void __launch_bounds__(kThreads)
 k_compress_bin(const float* __restrict__ m, float* __restrict__ c, int64_t E, int nbt) {

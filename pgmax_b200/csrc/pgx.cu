@@ -203,6 +203,9 @@ struct pgx_plan {
   SdlpWorkspace sdlp;
   // pull mode (every factor is a pairwise-binary enum factor on low-degree variables)
   bool pull_ok = false;
+  // every variable and edge is binary and every factor a pairwise-binary or unary EnumFactor: the generic
+  // two-pass path can keep its messages in binary-difference storage (k_var_sums_bin + k_enum_pw2_bin)
+  bool gbin_ok = false;
   int2* d_edge_csr = nullptr;          // [num_edges] CSR row (begin, end) of the edge's variable
   unsigned int* d_grid_bar = nullptr;  // barrier counter of the persistent kernel
   int coop_blocks_per_sm[2] = {0, 0};  // occupancy of k_enum_pw2_pull_resident<false / true, coop>
@@ -776,7 +779,7 @@ template <bool kSum>
 int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::View lp, const float* S,
                const float* m_old, float* m_new, const pgx::RunArgs& a, bool fused, bool lpull, pgx::View ev,
                cudaStream_t aux, const float* c_old = nullptr, float* c_new = nullptr, bool lbin = false,
-               float* part_override = nullptr, int chain = 0) {
+               float* part_override = nullptr, int chain = 0, bool gbin = false) {
   int rc;
   auto attr_needed = [plan](int group) {
     const bool need = !((plan->attr_done >> group) & 1u);
@@ -884,11 +887,22 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       if ((rc = check_launch(plan, "k_enum_pw2_bip"))) return rc;
       if (int(bi) == plan->dominant) { plan->dominant_name = "k_enum_pw2_bip"; plan->dominant_grid = grid; }
     } else if (eb.variant == kPw2) {
-      pgx::k_enum_pw2<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
-          mp, F, eb.dev.first_edge, eb.dev.first_msg, eb.dev.first_pot, plan->d_edge_vs, lp, S, m_old,
-          m_new, a);
-      if ((rc = check_launch(plan, "k_enum_pw2"))) return rc;
-      if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2";
+      if (gbin) {  // m_old / m_new are the one-float-per-edge arrays
+        pgx::k_enum_pw2_bin<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
+            mp, F, eb.dev.first_edge, eb.dev.first_pot, a.Es / 2, plan->d_edge_vs, lp, S, m_old, m_new, a);
+        if ((rc = check_launch(plan, "k_enum_pw2_bin"))) return rc;
+        if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2_bin";
+      } else {
+        pgx::k_enum_pw2<kSum><<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(
+            mp, F, eb.dev.first_edge, eb.dev.first_msg, eb.dev.first_pot, plan->d_edge_vs, lp, S, m_old,
+            m_new, a);
+        if ((rc = check_launch(plan, "k_enum_pw2"))) return rc;
+        if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pw2";
+      }
+    } else if (gbin) {  // (gbin_ok: the only other blocks are unary factors of two-state variables)
+      pgx::k_enum_unary_bin<<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(mp, eb.dev, a.Es / 2, plan->d_edge_vs, lp, S,
+                                                                            m_old, m_new, a);
+      if ((rc = check_launch(plan, "k_enum_unary_bin"))) return rc;
     } else if (eb.variant == kUnary && !(plan->disabled_paths & PGX_PATH_ENUM_UNARY)) {
       pgx::k_enum_unary<<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old, m_new, a);
       if ((rc = check_launch(plan, "k_enum_unary"))) return rc;
@@ -1611,6 +1625,16 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
       plan->pull_ok = true;
     }
   }
+  // binary-difference storage on the generic two-pass path (k_var_sums_bin / k_enum_pw2_bin / k_enum_unary_bin)
+  {
+    bool ok = plan->num_edge_states == 2 * plan->num_edges && plan->num_var_states == 2 * plan->num_vars &&
+              plan->num_edges > 0 && plan->bips.empty() && plan->or_f.dev.num_factors == 0 &&
+              plan->and_f.dev.num_factors == 0 && plan->pool_f.dev.num_factors == 0;
+    for (const EnumBlockPlan& eb : plan->enum_blocks)
+      ok = ok && (eb.variant == kPw2 || (eb.variant == kUnary && eb.dev.ns == 2));
+    for (int64_t v = 0; v < plan->num_vars && ok; ++v) ok = desc->var_num_states[v] == 2;  // var-states of v: 2v, 2v + 1
+    plan->gbin_ok = ok;
+  }
   // lattice mode: ONE pairwise-binary block whose factor 2u + t joins variable u with the
   // variable one row below (t = 0) / one column to the right, wrapping (t = 1), and nothing else
   if (plan->enum_blocks.size() == 1 && plan->enum_blocks[0].variant == kPw2 && plan->or_f.dev.num_factors == 0 &&
@@ -2032,6 +2056,19 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
                      Es < (int64_t(1) << 26) && Vs < (int64_t(1) << 26);
   // ... with the messages in binary-difference storage (such a graph has only two-state edges)
   const bool lbin = lpull && !(plan->disabled_paths & PGX_PATH_LOGICAL_BIN) && Es == 2 * plan->num_edges;
+  // Pull mode (small pairwise-binary graphs on low-degree variables, see below) is decided here: the
+  // choice of message storage depends on it.
+  bool pull_early = false;
+  if (plan->pull_ok && !fused && plan->enum_blocks.size() == 1 && !(plan->disabled_paths & PGX_PATH_PULL)) {
+    const int upw0 = 32 >> mp.bx_log;
+    const int64_t warps0 = ((plan->enum_blocks[0].dev.num_factors + upw0 - 1) / upw0) * mp.nbt;
+    const int ks0 = temperature == 0.f ? 0 : 1;
+    pull_early = warps0 * 32 <= int64_t(plan->coop_blocks_per_sm[ks0]) * plan->num_sms * pgx::kThreads;
+  }
+  // Generic two-pass path of an all-binary pairwise graph, full sample tiles: binary-difference storage
+  const bool gbin = plan->gbin_ok && mp.bx_log == 5 && !fused && !lpull && !pull_early &&
+                    !(plan->disabled_paths & PGX_PATH_GENERIC_BIN);
+  const bool cbin = lbin || gbin;  // messages live in ws.cA / ws.cB, one float per edge
   // Batch tail: a few samples beyond the last full tile run through the tail plan on its own stream.
   const int64_t tail_n = batch & 31;
   // (not with the fused OR + AND launch: there one more - partial - tile costs less than the tail
@@ -2081,7 +2118,7 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
     lat_bin = num_tiles >= 4 * int64_t(plan->num_sms) && !misaligned(ftov_in, 15) && !misaligned(ftov_out, 15) &&
               !misaligned(log_potentials, 15) && !misaligned(evidence, 7);
   }
-  if ((rc = ensure_workspace(plan, batch, evT, lpT, fused, lbin || lat_bin))) return rc;
+  if ((rc = ensure_workspace(plan, batch, evT, lpT, fused, cbin || lat_bin))) return rc;
   Workspace& ws = plan->ws;
   if (lat_bin) return run_lattice_bin(plan, st, log_potentials, evidence, ftov_in, ftov_out, deltas, num_iters, damping,
                                       temperature);
@@ -2136,7 +2173,7 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
     cur = ftov_in;
     nxt = ws.mA;
   } else if (ftov_in == nullptr) {
-    if (lbin)
+    if (cbin)
       PGX_CUDA(cudaMemsetAsync(ws.cA, 0, tiled_floats(mp, Es / 2) * sizeof(float), st));
     else
       PGX_CUDA(cudaMemsetAsync(ws.mA, 0, tiled_floats(mp, Es) * sizeof(float), st));  // NC(0) = 0
@@ -2154,9 +2191,9 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
     }
   }
   // the two buffers the generic loop below ping-pongs between
-  float* const bufA = lbin ? ws.cA : ws.mA;
-  float* const bufB = lbin ? ws.cB : ws.mB;
-  if (lbin) {
+  float* const bufA = cbin ? ws.cA : ws.mA;
+  float* const bufB = cbin ? ws.cB : ws.mB;
+  if (cbin) {
     if (ftov_in != nullptr) {  // normalised full layout -> one float per edge
       pgx::k_compress_bin<<<plan->num_sms * 8, pgx::kThreads, 0, st>>>(ws.mA, ws.cA, Es / 2, mp.nbt);
       if ((rc = check_launch(plan, "k_compress_bin"))) return rc;
@@ -2198,17 +2235,10 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
                             !(plan->disabled_paths & PGX_PATH_AUX_STREAM))
                                ? plan->aux : nullptr;
   const bool aux_after_s = lpull ? plan->aux_needs_s : true;
-  bool pull = false;
-  if (plan->pull_ok && !fused && plan->enum_blocks.size() == 1) {
-    const int upw0 = 32 >> mp.bx_log;
-    const int64_t warps0 = ((plan->enum_blocks[0].dev.num_factors + upw0 - 1) / upw0) * mp.nbt;
-    const int ks0 = temperature == 0.f ? 0 : 1;
-    pull = warps0 * 32 <= int64_t(plan->coop_blocks_per_sm[ks0]) * plan->num_sms * pgx::kThreads;
-  }
+  bool pull = pull_early;
   // Lattice mode (one sample): one index-free kernel per iteration, bit-identical to the
   // two-pass path.  Graphs small enough for the resident kernels keep those (no launches).
   bool lattice = false;
-  if (plan->disabled_paths & PGX_PATH_PULL) pull = false;
   const bool use_resident = pull && num_iters >= 2 && !plan->profiling && !(plan->disabled_paths & PGX_PATH_RESIDENT);
   if (plan->lattice_ok && single && !(plan->disabled_paths & PGX_PATH_LATTICE) && !use_resident) {
     const auto misaligned = [](const void* p, uintptr_t mask) { return (reinterpret_cast<uintptr_t>(p) & mask) != 0; };
@@ -2416,6 +2446,10 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
           if ((rc = check_launch(plan, "k_var_sums_list"))) return rc;
         }
       }
+    } else if (gbin) {
+      pgx::k_var_sums_bin<<<grid_for(plan, mp, plan->num_vars), pgx::kThreads, 0, st>>>(
+          mp, plan->num_vars, Es / 2, Vs, plan->d_vs_csr, plan->d_var_edge_msg, ev, cur, ws.S);
+      if ((rc = check_launch(plan, "k_var_sums_bin"))) return rc;
     } else if (!fused || it == 0) {
       pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(
           mp, Vs, Es, plan->d_vs_csr, plan->d_var_edge_msg, ev, shared_init ? ws.row : cur, ws.S, shared_init ? 1 : 0);
@@ -2470,9 +2504,9 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
       continue;
     }
     if (temperature == 0.f)
-      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new, lbin);
+      rc = launch_f2v<false>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new, lbin, nullptr, 0, gbin);
     else
-      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new, lbin);
+      rc = launch_f2v<true>(plan, st, mp, lp, ws.S, cur, dst, a, fused, lpull, ev, aux, c_old, c_new, lbin, nullptr, 0, gbin);
     if (rc) return rc;
     if (aux != nullptr) {
       PGX_CUDA(cudaEventRecord(plan->ev_join, aux));
@@ -2499,6 +2533,10 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
           mp, Vs, Es, plan->part_rows, plan->d_vs_var, plan->d_var_first_state, plan->d_rest_ptr,
           plan->d_rest_edge_msg, plan->d_part_first, plan->d_part_count, ev, cur, ws.part, ws.S);
       if ((rc = check_launch(plan, "k_var_reduce"))) return rc;
+    } else if (gbin) {
+      pgx::k_var_sums_bin<<<grid_for(plan, mp, plan->num_vars), pgx::kThreads, 0, st>>>(
+          mp, plan->num_vars, Es / 2, Vs, plan->d_vs_csr, plan->d_var_edge_msg, ev, cur, ws.S);
+      if ((rc = check_launch(plan, "k_var_sums_bin"))) return rc;
     } else {
       pgx::k_var_sums<<<grid_for(plan, mp, Vs), pgx::kThreads, 0, st>>>(mp, Vs, Es, plan->d_vs_csr, plan->d_var_edge_msg,
                                                                        ev, cur, ws.S, 0);
@@ -2508,7 +2546,7 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
     if (flags & PGX_RUN_SKIP_OUTPUT) return PGX_OK;  // the caller only wants the decoding
   }
   PGX_CHECK(ftov_out != nullptr, "ftov_out is null");
-  if (lbin) {
+  if (cbin) {
     dim3 grid((unsigned)((Es / 2 + 31) / 32), (unsigned)((mp.batch + 31) / 32)), block(32, 8);
     pgx::k_expand_bin<<<grid, block, 0, st>>>(cur, Es / 2, 0, Es / 2, ftov_out, Es, 0, mp);
     if ((rc = check_launch(plan, "k_expand_bin"))) return rc;

@@ -399,3 +399,65 @@ def test_small_enum_configuration_major_walk(temperature, batch):
   print(f"vs fp64: configuration-major {err_got:.3g}, list walk {err_ref:.3g}, fp32 oracle {err_oracle:.3g}")
   assert err_got <= max(1e-5, 2.0 * err_oracle), (err_got, err_oracle)
   np.testing.assert_allclose(got_m[~floor], want_m[~floor], atol=2e-5, rtol=2e-6)
+
+
+@pytest.mark.parametrize("temperature", [0.0, 1.0])
+@pytest.mark.parametrize("batch", [17, 40, 100])
+def test_generic_two_pass_binary_difference_storage(temperature, batch):
+  """PATH_GENERIC_BIN: an all-binary graph of pairwise + unary EnumFactors that is neither a grid
+  nor a dense bipartite block (random edges, a hub variable of degree 30) at full sample tiles keeps
+  one float per edge between iterations (k_var_sums_bin / k_enum_pw2_bin / k_enum_unary_bin).
+  Expanding is exact: messages, deltas and decodings are bit-identical to the reference-layout
+  kernels (path disabled), for zero, shared and batched un-normalised initial messages; and equal
+  to the oracle (max-product: bit for bit)."""
+  from pgmax_b200.infer.bp_state import BPArrays
+  rng = np.random.default_rng(4)
+  n = 60
+  variables = vgroup.NDVarArray(num_states=2, shape=(n,))
+  fg = fgraph.FactorGraph(variable_groups=variables)
+  pairs = {(0, j) for j in range(1, 31)}
+  while len(pairs) < 150:
+    i, j = sorted(rng.integers(0, n, size=2))
+    if i != j:
+      pairs.add((int(i), int(j)))
+  pairs = sorted(pairs)
+  fg.add_factors(fgroup.PairwiseFactorGroup(
+      variables_for_factors=[[variables[i], variables[j]] for i, j in pairs],
+      log_potential_matrix=rng.normal(size=(len(pairs), 2, 2))))
+  fg.add_factors(fgroup.EnumFactorGroup(variables_for_factors=[[variables[i]] for i in range(0, n, 3)],
+                                        factor_configs=np.arange(2)[:, None],
+                                        log_potentials=rng.normal(size=(len(range(0, n, 3)), 2))))
+  bp = infer.BP(fg.bp_state, temperature=temperature)
+  plan = bp.context.plan
+  base = bp.init(evidence_updates={variables: rng.gumbel(size=(batch, n, 2))})
+  num_msgs = base.ftov_msgs.shape[-1]
+  graph = bp_oracle.graph_from_context(bp.context)
+  inits = {"zero": base.ftov_msgs,
+           "shared": (rng.normal(size=num_msgs) * 2).astype(np.float32),
+           "batched": (rng.normal(size=(batch, num_msgs)) * 2).astype(np.float32)}
+  for name, msgs in inits.items():
+    arrays = BPArrays(log_potentials=base.log_potentials, ftov_msgs=msgs, evidence=base.evidence)
+    before = plan.launch_count
+    got, got_d = bp.run_with_diffs(arrays, num_iters=6, damping=0.5, temperature=temperature)
+    assert plan.launch_count > before
+    plan.disable_paths(plan.PATH_GENERIC_BIN)
+    ref, ref_d = bp.run_with_diffs(arrays, num_iters=6, damping=0.5, temperature=temperature)
+    plan.disable_paths(0)
+    np.testing.assert_array_equal(got.ftov_msgs, ref.ftov_msgs, err_msg=name)
+    np.testing.assert_array_equal(got_d, ref_d, err_msg=name)
+    want, want_d = bp_oracle.run_bp_batched(graph, arrays.log_potentials, arrays.ftov_msgs, arrays.evidence, 6, 0.5,
+                                            temperature)
+    if temperature == 0.0:
+      np.testing.assert_array_equal(got.ftov_msgs, np.asarray(want).reshape(got.ftov_msgs.shape), err_msg=name)
+    else:
+      np.testing.assert_allclose(got.ftov_msgs, np.asarray(want).reshape(got.ftov_msgs.shape), atol=1e-5, err_msg=name)
+    for _ in range(2):  # capture + replay
+      again, again_d = bp.run_with_diffs(arrays, num_iters=6, damping=0.5, temperature=temperature)
+      np.testing.assert_array_equal(again.ftov_msgs, got.ftov_msgs)
+      np.testing.assert_array_equal(again_d, got_d)
+  # decoding from the variable sums the run leaves behind (pgx_infer_host: PGX_RUN_FINAL_SUMS)
+  res = bp.infer_host(arrays, num_iters=6, damping=0.5, marginals=True)
+  states, marg, ties = bp.context.decode(got, marginals=True)
+  np.testing.assert_array_equal(res["flat_map_states"], states)
+  np.testing.assert_array_equal(res["tie_counts"], ties)
+  np.testing.assert_array_equal(res["marginals"], marg)
