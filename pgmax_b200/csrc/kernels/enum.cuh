@@ -216,6 +216,120 @@ k_enum_small_cm(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_
 }
 
 // ---------------------------------------------------------------------------
+// K2b-dense: pairwise factors whose table holds ALL n0 x n1 configurations in row-major order
+// (PairwiseFactorGroup over multi-state variables, pgmax/fgroup/enum.py:201-353: multi-label MRFs,
+// the 17 x 3-state "heretic" model).  The configuration-major walk of k_enum_small_cm as two nested
+// loops: no configuration-table loads, and the first variable's state i keeps its score term, its
+// maximum and its sum in REGISTERS over the inner loop - only the second variable's columns are
+// read-modify-written in shared memory.  Every edge-state still receives its terms in ascending
+// configuration order (k = i n1 + j): the same operations in the same order as k_enum_small_cm,
+// bit-identical to it (tested).
+// ---------------------------------------------------------------------------
+// kStageLp (potentials shared by the batch, full sample tiles: a warp = 32 samples of ONE factor): the
+// factor's n0 n1 potentials are clipped and staged in shared memory by two coalesced loads per warp
+// instead of one warp-uniform global load per configuration and pass behind the loop's dependences
+// (long-scoreboard stalls were the top stall reason).
+constexpr int kDenseMaxConfigs = 256;  // n0 + n1 <= 32
+// Shared-memory columns per thread: q [ns] (the first variable's slots are overwritten by its damped
+// values as they complete), and the second variable's maxima and sums [n1] each - the first
+// variable's maximum and sum never leave registers: per row i the inner loop runs twice back to back
+// (maximum, then sum), only the second variable needs the two global passes.
+__host__ __device__ constexpr size_t pair_dense_cols(int ns, int n1, bool sum) { return size_t(ns) + (sum ? 2 : 1) * size_t(n1); }
+
+template <bool kSumProduct, bool kStageLp>
+__global__ void __launch_bounds__(kThreads)
+k_enum_pair_dense(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
+                  const float* __restrict__ S, const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  extern __shared__ float es_cols[];
+  UnitLoop L = unit_loop(mp, blk.num_factors);
+  const unsigned live = __ballot_sync(0xffffffffu, L.b_ok);  // (lanes beyond the batch leave: the warp syncs below name the rest)
+  if (!L.b_ok) return;
+  float dmax = 0.f;
+  const int sh = mp.bx_log, ns = blk.ns, n0 = blk.edge_off[1], n1 = ns - n0;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const LaneView lpL = lane_view(lp, mp, L.b);
+  const float T = a.T, c = 1.4426950408889634f / T;
+  float* q = es_cols + threadIdx.x;           // [ns] columns, stride kThreads; slots [0, n0) end up holding damped values
+  float* qb = q + size_t(n0) * kThreads;      // the second variable's part of q
+  float* Mb = q + size_t(ns) * kThreads;      // [n1] maxima, then the damped values
+  float* Zb = Mb + size_t(n1) * kThreads;     // [n1] sums (sum-product only)
+  // per-warp staging area behind the columns
+  float* lps = es_cols + pair_dense_cols(ns, n1, kSumProduct) * kThreads + (threadIdx.x >> 5) * kDenseMaxConfigs;
+  const int lane = threadIdx.x & 31;
+  const int rank = __popc(live & ((1u << lane) - 1u)), nlive = __popc(live);
+  for (int64_t f = L.u; f < L.u_end; f += L.step) {
+    const int64_t mbase = blk.msg_base(f), ebase = blk.edge_base(f), pbase = blk.pot_base(f);
+    if (kStageLp) {
+      __syncwarp(live);  // the previous factor's readers are done
+      for (int t = rank; t < n0 * n1; t += nlive) lps[t] = clip_lp(lpL.q[pbase + t]);
+      __syncwarp(live);
+    }
+    for (int e = 0; e < 2; ++e) {
+      const int64_t vs = edge_vs[ebase + e];
+      for (int s = blk.edge_off[e]; s < blk.edge_off[e + 1]; ++s)
+        q[s * kThreads] = SL[(vs + s - blk.edge_off[e]) << sh] - mo[(mbase + s) << sh];
+    }
+    for (int j = 0; j < n1; ++j) {
+      Mb[j * kThreads] = -INFINITY;
+      if (kSumProduct) Zb[j * kThreads] = 0.f;
+    }
+    auto score = [&](float qi, int i, int j) {
+      return (qi + qb[j * kThreads]) + (kStageLp ? lps[i * n1 + j] : clip_lp(lpL.at(pbase + int64_t(i) * n1 + j)));
+    };
+    // pass 1: the second variable's maxima (max-product: the first variable's too)
+    for (int i = 0; i < n0; ++i) {
+      const float qi = 0.f + q[i * kThreads];
+      float mi = -INFINITY;
+#pragma unroll 4
+      for (int j = 0; j < n1; ++j) {
+        const float sk = score(qi, i, j);
+        mi = fmaxf(mi, sk);
+        Mb[j * kThreads] = fmaxf(Mb[j * kThreads], sk);
+      }
+      if (!kSumProduct) q[i * kThreads] = damp(mo[(mbase + i) << sh], mi - q[i * kThreads], a.d, a.one_minus_d);
+    }
+    // pass 2 (sum-product): per row the first variable's maximum, then both sums
+    if (kSumProduct) {
+      for (int i = 0; i < n0; ++i) {
+        const float qi = 0.f + q[i * kThreads];
+        float mi = -INFINITY;
+#pragma unroll 4
+        for (int j = 0; j < n1; ++j) mi = fmaxf(mi, score(qi, i, j));
+        float zi = 0.f;
+#pragma unroll 4
+        for (int j = 0; j < n1; ++j) {
+          const float sk = score(qi, i, j);
+          zi += ex2_approx((sk - mi) * c);
+          Zb[j * kThreads] += ex2_approx((sk - Mb[j * kThreads]) * c);
+        }
+        const float val = T * logf(zi) + mi;
+        q[i * kThreads] = damp(mo[(mbase + i) << sh], val - q[i * kThreads], a.d, a.one_minus_d);
+      }
+    }
+    for (int j = 0; j < n1; ++j) {
+      const float val = kSumProduct ? T * logf(Zb[j * kThreads]) + Mb[j * kThreads] : Mb[j * kThreads];
+      Mb[j * kThreads] = damp(mo[(mbase + n0 + j) << sh], val - qb[j * kThreads], a.d, a.one_minus_d);
+    }
+    for (int e = 0; e < 2; ++e) {
+      const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
+      const float* D = e == 0 ? q : Mb - size_t(n0) * kThreads;  // damped value of edge-state s: D[s]
+      float mx = -INFINITY;
+      for (int s = s0; s < s1; ++s) mx = fmaxf(mx, D[s * kThreads]);
+      for (int s = s0; s < s1; ++s) {
+        const float out = fmaxf(D[s * kThreads] - mx, kMsgNegInf);
+        const int64_t idx = (mbase + s) << sh;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
+      }
+    }
+  }
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
 // K2b-unary: EnumFactors over ONE variable whose configurations are all its states in order (the
 // bias factors of an RBM, benchmark/rbm_lib.py:141-158).  Every edge-state is in exactly one
 // configuration, so the general update collapses to  f_s = ((0 + q_s) + lp_s) - q_s  for max- AND

@@ -71,7 +71,8 @@ enum AttrGroup { kAttrBigMax = 0, kAttrBipMax = 1, kAttrBipSum = 2, kAttrBigEnum
                  kAttrLatticeBinV1 = 10, kAttrLatticeBinV2 = 11, kAttrLatticeBinV3 = 12, kAttrLatticeBinV4 = 13,
                  kAttrLatticeBinV5 = 14, kAttrLatticeBinV6 = 15, kAttrLatticeBinV7 = 16, kAttrLatticeBinV8 = 17,
                  kAttrLatticeBinV9 = 18, kAttrOrAndMax = 19, kAttrOrAndSum = 20, kAttrBigSum = 21, kAttrEnumSmallMax = 22,
-                 kAttrEnumSmallSum = 23, kAttrEnumCmMax = 24, kAttrEnumCmSum = 25 };
+                 kAttrEnumSmallSum = 23, kAttrEnumCmMax = 24, kAttrEnumCmSum = 25,
+                 kAttrEnumDenseMax = 26, kAttrEnumDenseSum = 27 };
 
 struct EnumBlockPlan {
   pgx::EnumBlockDev dev{};
@@ -86,6 +87,7 @@ struct EnumBlockPlan {
   int num_groups = 0, num_rounds = 0;
   int bigmax = -1;              // index into the plan's BigMaxGroup array, or -1
   int n0 = 0;                   // states of the first variable
+  bool dense2 = false;          // arity 2 and the table is ALL n0 x n1 configurations in row-major order (k_enum_pair_dense)
 };
 
 // A pairwise-binary enum block whose factors form a dense I x J grid (see BipDev).
@@ -487,6 +489,14 @@ int build_enum_block(pgx_plan* plan, const pgx_enum_block* desc_blocks, const st
     if ((rc = upload(fe, &out->d_fac_edge, &plan->device_bytes))) return rc;
     if ((rc = upload(fm, &out->d_fac_msg, &plan->device_bytes))) return rc;
     if ((rc = upload(fp, &out->d_fac_pot, &plan->device_bytes))) return rc;
+  }
+  if (A == 2) {  // the complete table in row-major order?
+    const int n0 = edge_off[1], n1 = ns - edge_off[1];
+    bool dense = int64_t(K) == int64_t(n0) * n1;
+    for (int k = 0; k < K && dense; ++k)
+      dense = cfg_es[size_t(k) * 2] == k / n1 && cfg_es[size_t(k) * 2 + 1] == n0 + k % n1;
+    out->dense2 = dense;
+    out->n0 = n0;
   }
   {  // configs sorted by the first variable's state (arity 2)?
     bool sorted0 = A == 2;
@@ -907,6 +917,28 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       pgx::k_enum_unary<<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old, m_new, a);
       if ((rc = check_launch(plan, "k_enum_unary"))) return rc;
     } else if (eb.variant == kSmall || (eb.variant == kUnary && eb.dev.ns <= pgx::kSmallMaxNS)) {
+      // complete pairwise tables: nested loops, the first variable's running values in registers
+      if (eb.dense2 && eb.dev.ns <= 32 && !(plan->disabled_paths & (PGX_PATH_ENUM_CONFIG_MAJOR | PGX_PATH_ENUM_DENSE_PAIR))) {
+        // potentials shared by the batch + full sample tiles: staged per warp in shared memory
+        const bool stage = lp.kind == 0 && mp.bx_log == 5;
+        const size_t smem = (pgx::pair_dense_cols(eb.dev.ns, eb.dev.ns - eb.n0, kSum) * pgx::kThreads +
+                             (stage ? size_t(pgx::kThreads / 32) * pgx::kDenseMaxConfigs : 0)) * sizeof(float);
+        if (attr_needed(kSum ? kAttrEnumDenseSum : kAttrEnumDenseMax)) {
+          const int most = int((size_t(3) * 32 * pgx::kThreads + size_t(pgx::kThreads / 32) * pgx::kDenseMaxConfigs) * sizeof(float));
+          PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pair_dense<kSum, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+          PGX_CUDA(cudaFuncSetAttribute(pgx::k_enum_pair_dense<kSum, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+        }
+        if (stage)
+          pgx::k_enum_pair_dense<kSum, true><<<grid_for(plan, mp, F), pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs,
+                                                                                                lp, S, m_old, m_new, a);
+        else
+          pgx::k_enum_pair_dense<kSum, false><<<grid_for(plan, mp, F), pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs,
+                                                                                                 lp, S, m_old, m_new, a);
+        if ((rc = check_launch(plan, "k_enum_pair_dense"))) return rc;
+        if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pair_dense";
+        if ((rc = prof_mark(plan, st, int(bi)))) return rc;
+        continue;
+      }
       // configuration-major walk (k_enum_small_cm) while its three columns leave room for two CTAs per SM
       if (eb.dev.ns <= 32 && !(plan->disabled_paths & PGX_PATH_ENUM_CONFIG_MAJOR)) {
         const size_t smem = size_t(kSum ? 3 : 2) * eb.dev.ns * pgx::kThreads * sizeof(float);
@@ -1628,7 +1660,7 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
   // binary-difference storage on the generic two-pass path (k_var_sums_bin / k_enum_pw2_bin / k_enum_unary_bin)
   {
     bool ok = plan->num_edge_states == 2 * plan->num_edges && plan->num_var_states == 2 * plan->num_vars &&
-              plan->num_edges > 0 && plan->bips.empty() && plan->or_f.dev.num_factors == 0 &&
+              plan->num_edges > 0 && plan->or_f.dev.num_factors == 0 &&
               plan->and_f.dev.num_factors == 0 && plan->pool_f.dev.num_factors == 0;
     for (const EnumBlockPlan& eb : plan->enum_blocks)
       ok = ok && (eb.variant == kPw2 || (eb.variant == kUnary && eb.dev.ns == 2));
@@ -2066,7 +2098,9 @@ static int bp_run_enqueue(pgx_plan* plan, void* stream, int64_t batch, const flo
     pull_early = warps0 * 32 <= int64_t(plan->coop_blocks_per_sm[ks0]) * plan->num_sms * pgx::kThreads;
   }
   // Generic two-pass path of an all-binary pairwise graph, full sample tiles: binary-difference storage
-  const bool gbin = plan->gbin_ok && mp.bx_log == 5 && !fused && !lpull && !pull_early &&
+  // (not for plans with dense-grid blocks, even when those run two-pass - exact order: the workspace's
+  // compressed buffers are sized for the single-pass path there)
+  const bool gbin = plan->gbin_ok && plan->bips.empty() && mp.bx_log == 5 && !fused && !lpull && !pull_early &&
                     !(plan->disabled_paths & PGX_PATH_GENERIC_BIN);
   const bool cbin = lbin || gbin;  // messages live in ws.cA / ws.cB, one float per edge
   // Batch tail: a few samples beyond the last full tile run through the tail plan on its own stream.

@@ -375,6 +375,13 @@ def test_small_enum_configuration_major_walk(temperature, batch):
   plan = bp.context.plan
   iters = 7
   got, got_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
+  # the complete 17 x 3 tables take the nested-loop kernel k_enum_pair_dense: the same operations in the
+  # same order as the configuration-major walk (PATH_ENUM_DENSE_PAIR disabled), for every temperature
+  plan.disable_paths(plan.PATH_ENUM_DENSE_PAIR)
+  cm, cm_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
+  plan.disable_paths(0)
+  np.testing.assert_array_equal(got.ftov_msgs, cm.ftov_msgs)
+  np.testing.assert_array_equal(got_d, cm_d)
   plan.disable_paths(plan.PATH_ENUM_CONFIG_MAJOR)
   ref, ref_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
   plan.disable_paths(0)
