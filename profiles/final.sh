@@ -13,7 +13,6 @@ stamp() { echo "[$(( $(date +%s) - t0 )) s] $*"; }
 if [ "${2:-all}" != "captures" ]; then
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -5 | tee $out/${tag}_pytest_gpu.txt
 stamp pytest
-timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; stamp "bench"; head -c 400 $out/${tag}_bench.json; echo
 timeout 100 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2; stamp smoke
 fi
 B="--steps 1 --warmup 1 --no-cpu-baseline --no-extras --no-graph"
@@ -27,7 +26,7 @@ cap deconv 100 k_or_and_fused 11   # odd index: the full-tile launch (the packed
 cap rcn 1 k_enum_big_maxprod_all 5
 cap ising_big 1 k_lattice_bin 3 "--iters 10 --strip-flags 1"
 cap rcn_sum 1 k_enum_big_sumprod_all 5
-cap heretic 256 k_enum_small_cm 5 "--iters 10"
+cap heretic 256 k_enum_pair_dense 5 "--iters 10"
 cap ising50_batch 1024 k_enum_pw2_bin 5 "--iters 10"
 for w in rbm deconv rcn; do
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 40 -c 120 --csv \
@@ -40,4 +39,8 @@ for w in rbm_b1024 deconv_b100 rcn_b1 ising_big_b1 rcn_sum_b1 heretic_b256 ising
   python profiles/source_hot.py $out/${tag}_$w.ncu-rep 30 > $out/${tag}_source_$w.txt 2>&1
 done
 rm -f $out/${tag}_*.ncu-rep
+# the bench line last: its physical_frac fields read the traffic table the captures above just wrote
+if [ "${2:-all}" != "captures" ]; then
+timeout 600 python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; stamp "bench"; head -c 400 $out/${tag}_bench.json; echo
+fi
 ls -la $out | tail -24
