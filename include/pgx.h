@@ -306,6 +306,7 @@ int64_t pgx_plan_compressed_edges(const pgx_plan* plan);
 #define PGX_PATH_ENUM_UNARY 65536u /* one-variable EnumFactors over all states: closed form (k_enum_unary) instead of k_enum_small */
 #define PGX_PATH_ENUM_CONFIG_MAJOR 131072u /* small EnumFactors (<= 32 edge-states): configuration-major walk (k_enum_small_cm) instead of k_enum_small */
 #define PGX_PATH_ENUM_DENSE_PAIR 524288u /* complete n0 x n1 pairwise tables (<= 32 edge-states): nested-loop kernel k_enum_pair_dense instead of k_enum_small_cm */
+#define PGX_PATH_ENUM_PAIR_FEW 1048576u /* complete pairwise tables with a 2 ... 4-state side: that side in registers (k_enum_pair_few) instead of k_enum_pair_dense */
 #define PGX_PATH_GENERIC_BIN 262144u /* all-binary pairwise graphs on the generic two-pass path: binary-difference storage (k_var_sums_bin + k_enum_pw2_bin) */
 #define PGX_PATH_LATTICE_BIN 8192u /* large single-sample lattices on binary-difference storage (k_lattice_bin) */
 #define PGX_PATH_LOGICAL_BIN 256u /* ... with the messages in binary-difference storage (one float per edge) */

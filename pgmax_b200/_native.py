@@ -452,6 +452,7 @@ class Plan:
   PATH_PERM_POTENTIALS, PATH_HALF_BATCH, PATH_STAGED_WIRING = 512, 1024, 2048
   PATH_TAIL_SPLIT, PATH_LATTICE_BIN, PATH_ORAND_FUSED, PATH_VARSUM_COOP = 4096, 8192, 16384, 32768
   PATH_ENUM_UNARY, PATH_ENUM_CONFIG_MAJOR, PATH_GENERIC_BIN, PATH_ENUM_DENSE_PAIR = 65536, 131072, 262144, 524288
+  PATH_ENUM_PAIR_FEW = 1048576
 
   def disable_paths(self, mask: int) -> None:
     """Pin the launch path (PGX_PATH_* bits of include/pgx.h); all paths are bit-identical."""

@@ -330,6 +330,113 @@ k_enum_pair_dense(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edg
 }
 
 // ---------------------------------------------------------------------------
+// K2b-few: complete pairwise tables in which ONE variable has only kFew = 2 ... 4 states (a
+// many-state hidden variable against a binary / ternary pixel: the 17 x 3 "heretic" factors).  The
+// few-state side's terms, maxima and sums are kFew-element REGISTER arrays (the inner loop over it
+// is fully unrolled), the many-state side's are scalars of the outer loop: no shared-memory
+// read-modify-write in the hot loops at all; shared memory holds one column per thread (the
+// many-state side's q, overwritten by its damped values) and the warp's staged potentials.
+// kFewSecond: the few-state variable is the factor's second one (else its first).  Either way both
+// indices ascend, so every edge-state receives its terms in ascending configuration order: the same
+// operations in the same order as k_enum_pair_dense / k_enum_small_cm - bit-identical (tested).
+// Potentials shared by the batch, full sample tiles (a warp = 32 samples of one factor).
+// ---------------------------------------------------------------------------
+template <bool kSumProduct, int kFew, bool kFewSecond>
+__global__ void __launch_bounds__(kThreads)
+k_enum_pair_few(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ edge_vs, View lp,
+                const float* __restrict__ S, const float* __restrict__ m_old, float* __restrict__ m_new, RunArgs a) {
+  extern __shared__ float es_cols[];
+  UnitLoop L = unit_loop(mp, blk.num_factors);
+  const unsigned live = __ballot_sync(0xffffffffu, L.b_ok);
+  if (!L.b_ok) return;
+  float dmax = 0.f;
+  const int ns = blk.ns, nm = ns - kFew;  // states of the many-state variable
+  // edge-state offsets of the two sides inside the factor's message span
+  const int few0 = kFewSecond ? nm : 0, many0 = kFewSecond ? 0 : kFew;
+  const int64_t moff = lane_off(mp, a.Es, L.b);
+  const float* mo = m_old + moff;
+  float* mn = m_new + moff;
+  const float* SL = S + lane_off(mp, a.Vs, L.b);
+  const float T = a.T, c = 1.4426950408889634f / T;
+  float* D = es_cols + threadIdx.x;  // [nm] column, stride kThreads: q of the many-state side, then its damped values
+  float* lps = es_cols + size_t(nm) * kThreads + (threadIdx.x >> 5) * kDenseMaxConfigs;
+  const int lane = threadIdx.x & 31;
+  const int rank = __popc(live & ((1u << lane) - 1u)), nlive = __popc(live);
+  for (int64_t f = L.u; f < L.u_end; f += L.step) {
+    const int64_t mbase = blk.msg_base(f), ebase = blk.edge_base(f), pbase = blk.pot_base(f);
+    __syncwarp(live);  // the previous factor's readers are done
+    for (int t = rank; t < nm * kFew; t += nlive) lps[t] = clip_lp(lp.p[pbase + t]);
+    __syncwarp(live);
+    const int64_t vs_few = edge_vs[ebase + (kFewSecond ? 1 : 0)], vs_many = edge_vs[ebase + (kFewSecond ? 0 : 1)];
+    float qf[kFew], Mf[kFew], Zf[kFew];
+#pragma unroll
+    for (int j = 0; j < kFew; ++j) {
+      qf[j] = SL[(vs_few + j) << 5] - mo[(mbase + few0 + j) << 5];
+      Mf[j] = -INFINITY;
+      Zf[j] = 0.f;
+    }
+    for (int i = 0; i < nm; ++i) D[i * kThreads] = SL[(vs_many + i) << 5] - mo[(mbase + many0 + i) << 5];
+    // s_k = ((0 + q of the first variable's state) + q of the second's) + potential, k = first * n1 + second
+    auto score = [&](float qi, int i, int j) {
+      return kFewSecond ? ((0.f + qi) + qf[j]) + lps[i * kFew + j] : ((0.f + qf[j]) + qi) + lps[j * nm + i];
+    };
+    // pass 1: maxima of the few-state side (max-product: the many-state side's too, finished per row)
+    for (int i = 0; i < nm; ++i) {
+      const float qi = D[i * kThreads];
+      float mi = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kFew; ++j) {
+        const float sk = score(qi, i, j);
+        mi = fmaxf(mi, sk);
+        Mf[j] = fmaxf(Mf[j], sk);
+      }
+      if (!kSumProduct) D[i * kThreads] = damp(mo[(mbase + many0 + i) << 5], mi - qi, a.d, a.one_minus_d);
+    }
+    if (kSumProduct) {
+      for (int i = 0; i < nm; ++i) {
+        const float qi = D[i * kThreads];
+        float sk[kFew], mi = -INFINITY, zi = 0.f;
+#pragma unroll
+        for (int j = 0; j < kFew; ++j) { sk[j] = score(qi, i, j); mi = fmaxf(mi, sk[j]); }
+#pragma unroll
+        for (int j = 0; j < kFew; ++j) {
+          zi += ex2_approx((sk[j] - mi) * c);
+          Zf[j] += ex2_approx((sk[j] - Mf[j]) * c);
+        }
+        D[i * kThreads] = damp(mo[(mbase + many0 + i) << 5], (T * logf(zi) + mi) - qi, a.d, a.one_minus_d);
+      }
+    }
+    {  // the few-state edge: damp, normalise, write
+      float nf[kFew], mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < kFew; ++j) {
+        const float val = kSumProduct ? T * logf(Zf[j]) + Mf[j] : Mf[j];
+        nf[j] = damp(mo[(mbase + few0 + j) << 5], val - qf[j], a.d, a.one_minus_d);
+        mx = fmaxf(mx, nf[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kFew; ++j) {
+        const float out = fmaxf(nf[j] - mx, kMsgNegInf);
+        const int64_t idx = (mbase + few0 + j) << 5;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
+      }
+    }
+    {  // the many-state edge
+      float mx = -INFINITY;
+      for (int i = 0; i < nm; ++i) mx = fmaxf(mx, D[i * kThreads]);
+      for (int i = 0; i < nm; ++i) {
+        const float out = fmaxf(D[i * kThreads] - mx, kMsgNegInf);
+        const int64_t idx = (mbase + many0 + i) << 5;
+        dmax = fmaxf(dmax, fabsf(out - mo[idx]));
+        mn[idx] = out;
+      }
+    }
+  }
+  publish_delta(a.deltas, int64_t(L.b) * a.delta_stride + a.delta_off, dmax);
+}
+
+// ---------------------------------------------------------------------------
 // K2b-unary: EnumFactors over ONE variable whose configurations are all its states in order (the
 // bias factors of an RBM, benchmark/rbm_lib.py:141-158).  Every edge-state is in exactly one
 // configuration, so the general update collapses to  f_s = ((0 + q_s) + lp_s) - q_s  for max- AND
@@ -609,7 +716,7 @@ k_enum_big_maxprod(BatchMap mp, EnumBlockDev blk, const int32_t* __restrict__ ed
 //   * loads run one trip (kBigTrip rounds) ahead of their use in registers;
 //   * work units (factor, sample) of all groups are sorted by configuration count
 //     (descending) and handed out through an atomic counter: the launch ends balanced.
-// Dynamic smem: (2 ns + nwarps * (n1 + 32) + 32) floats of the largest group.
+// Dynamic smem: (2 ns + 32 + nwarps * (n1 + 32) + 32) floats of the largest group.
 // ---------------------------------------------------------------------------
 constexpr int kBigWarps = kThreads / 32;
 struct BigMaxGroup {
@@ -694,7 +801,7 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
     const int64_t f = uf.y;
     const int ns = blk.ns, n0 = blk.edge_off[1], n1 = ns - n0;
     float* q = smem;                       // [ns]
-    float* M = q + ns;                     // [ns] maxima, then damped values
+    float* M = q + ns + 32;                // [ns] maxima, then damped values ([ns, ns + 32) of q: zeros, what idle schedule entries read as their partner's q)
     float* Mw = M + ns;                    // [kBigWarps][n1 + 32] per-warp partner-side maxima
     float* red = Mw + kBigWarps * (n1 + 32);
     const int64_t moff = lane_off(mp, a.Es, b);
@@ -712,6 +819,7 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
       }
     }
     for (int i = threadIdx.x; i < kBigWarps * (n1 + 32); i += blockDim.x) Mw[i] = -INFINITY;
+    if (threadIdx.x < 32) q[ns + threadIdx.x] = 0.f;
     __syncthreads();
 
     {  // ---- configurations: this warp's lane-groups, round by round ---------------------------
@@ -771,7 +879,7 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
           for (int p = 0; p < kPermTrip; ++p) rl[p] = rl_n[p];
           if (r0 + kPermTrip < r_end) request(r0 + kPermTrip);
           // idle entries: potential -inf, partner "state" n1 + j = a dummy slot
-          // (the q read lands in M[], finite or -inf: the sum stays -inf).
+          // (the q read lands in the zero pad behind q: the sum stays -inf).
           // All q reads of the trip first (read-only: they overlap), then the read-max-write chain.
           uint32_t b_s[kPermTrip];
           float sk[kPermTrip];
@@ -882,7 +990,7 @@ k_enum_big_maxprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
 //     pairs are merged once per factor, in warp order (lane-groups are handed to the warps
 //     statically: run-to-run deterministic).
 // exp((x - m) / T) = ex2((x - m) * log2(e) / T): MUFU.EX2, two per configuration.
-// Dynamic smem: (2 ns + 2 nwarps (n1 + 32) + 32) floats of the largest group.
+// Dynamic smem: (2 ns + 32 + 2 nwarps (n1 + 32) + 32) floats of the largest group.
 // Measured on the RCN graph at T = 1, B = 1 (profiles/r02_z_rcn_sum_ab.txt): 0.270 ms per launch
 // (0.44 of the HBM peak on the algorithmic bytes; the instruction mix - two MUFU and five
 // shared-memory accesses per configuration - bounds it, not the trip length: 0.270 - 0.290 ms
@@ -923,7 +1031,7 @@ k_enum_big_sumprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
     const int ns = blk.ns, n0 = blk.edge_off[1], n1 = ns - n0;
     const int wstride = n1 + 32;
     float* q = smem;                        // [ns]
-    float* M = q + ns;                      // [ns] logsumexp values, then damped values
+    float* M = q + ns + 32;                 // [ns] logsumexp values, then damped values ([ns, ns + 32) of q: zeros for idle entries)
     float* Mw = M + ns;                     // [kBigWarps][n1 + 32] per-warp partner-side maxima
     float* Sw = Mw + kBigWarps * wstride;   // [kBigWarps][n1 + 32] ... and sums
     float* red = Sw + kBigWarps * wstride;
@@ -937,10 +1045,11 @@ k_enum_big_sumprod_all(BatchMap mp, const BigMaxGroup* __restrict__ groups, cons
       const int s0 = blk.edge_off[e], s1 = blk.edge_off[e + 1];
       for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
         q[s] = SL[(vs + s - s0) << sh] - mo[(mbase + s) << sh];
-        M[s] = 0.f;  // (idle schedule entries read their "q" from here: anything but NaN / +inf)
+        M[s] = 0.f;
       }
     }
     for (int i = threadIdx.x; i < kBigWarps * wstride; i += blockDim.x) { Mw[i] = kLow; Sw[i] = 0.f; }
+    if (threadIdx.x < 32) q[ns + threadIdx.x] = 0.f;
     __syncthreads();
     {
       const uint32_t qb_s = smem_u32(q) + 4u * n0;

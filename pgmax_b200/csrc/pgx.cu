@@ -917,6 +917,27 @@ int launch_f2v(pgx_plan* plan, cudaStream_t st, const pgx::BatchMap& mp, pgx::Vi
       pgx::k_enum_unary<<<grid_for(plan, mp, F), pgx::kThreads, 0, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old, m_new, a);
       if ((rc = check_launch(plan, "k_enum_unary"))) return rc;
     } else if (eb.variant == kSmall || (eb.variant == kUnary && eb.dev.ns <= pgx::kSmallMaxNS)) {
+      // complete pairwise tables with a 2 ... 4-state side, potentials shared by the batch: that side in registers
+      if (eb.dense2 && eb.dev.ns <= 32 && lp.kind == 0 && mp.bx_log == 5 &&
+          (eb.dev.ns - eb.n0 <= 4 || eb.n0 <= 4) && std::min(eb.n0, eb.dev.ns - eb.n0) >= 2 &&
+          !(plan->disabled_paths & (PGX_PATH_ENUM_CONFIG_MAJOR | PGX_PATH_ENUM_DENSE_PAIR | PGX_PATH_ENUM_PAIR_FEW))) {
+        const bool second = eb.dev.ns - eb.n0 <= 4;  // the few-state variable is the factor's second one
+        const int few = second ? eb.dev.ns - eb.n0 : eb.n0, many = eb.dev.ns - few;
+        const size_t smem = (size_t(many) * pgx::kThreads + size_t(pgx::kThreads / 32) * pgx::kDenseMaxConfigs) * sizeof(float);
+        const dim3 grid = grid_for(plan, mp, F);
+        // (at most 30 columns + the staging area = 38 KB: below the 48 KB that need no attribute)
+#define PGX_PAIR_FEW(FEW, SECOND)                                                                                         \
+  pgx::k_enum_pair_few<kSum, FEW, SECOND><<<grid, pgx::kThreads, smem, st>>>(mp, eb.dev, plan->d_edge_vs, lp, S, m_old,  \
+                                                                             m_new, a)
+        if (few == 2) { if (second) PGX_PAIR_FEW(2, true); else PGX_PAIR_FEW(2, false); }
+        else if (few == 3) { if (second) PGX_PAIR_FEW(3, true); else PGX_PAIR_FEW(3, false); }
+        else { if (second) PGX_PAIR_FEW(4, true); else PGX_PAIR_FEW(4, false); }
+#undef PGX_PAIR_FEW
+        if ((rc = check_launch(plan, "k_enum_pair_few"))) return rc;
+        if (int(bi) == plan->dominant) plan->dominant_name = "k_enum_pair_few";
+        if ((rc = prof_mark(plan, st, int(bi)))) return rc;
+        continue;
+      }
       // complete pairwise tables: nested loops, the first variable's running values in registers
       if (eb.dense2 && eb.dev.ns <= 32 && !(plan->disabled_paths & (PGX_PATH_ENUM_CONFIG_MAJOR | PGX_PATH_ENUM_DENSE_PAIR))) {
         // potentials shared by the batch + full sample tiles: staged per warp in shared memory
@@ -1474,7 +1495,7 @@ int pgx_plan_create(const pgx_graph_desc* desc, pgx_plan** out_plan) {
     const int nwarp = pgx::kThreads / 32;
     for (EnumBlockPlan& eb : plan->enum_blocks) {
       if (eb.bigmax < 0) continue;
-      const size_t smem = (size_t(2) * eb.dev.ns + size_t(nwarp) * (eb.dev.ns - eb.n0 + 32) + 32) * sizeof(float);
+      const size_t smem = (size_t(2) * eb.dev.ns + 32 + size_t(nwarp) * (eb.dev.ns - eb.n0 + 32) + 32) * sizeof(float);
       if (smem > 200 * 1024 || eb.dev.num_factors >= INT32_MAX) { eb.bigmax = -1; continue; }
       eb.bigmax = int(groups.size());
       plan->bigmax_smem = std::max(plan->bigmax_smem, smem);

@@ -337,15 +337,17 @@ def test_rcn_size_factors_sum_product_one_pass(temperature, batch, extreme):
 
 
 @pytest.mark.parametrize("temperature", [0.0, 1.0, 0.4])
-@pytest.mark.parametrize("batch", [None, 5, 70])
-def test_small_enum_configuration_major_walk(temperature, batch):
+@pytest.mark.parametrize("batch,lp_batched", [(None, False), (5, False), (70, False), (5, True), (70, True)])
+def test_small_enum_configuration_major_walk(temperature, batch, lp_batched):
   """k_enum_small_cm (small EnumFactors, <= 32 edge-states: one walk over the configurations per
   pass, per-thread shared-memory columns) against k_enum_small (PATH_ENUM_CONFIG_MAJOR disabled:
   per-edge-state list walks) and the oracle, on 17 x 3-state pairwise factors (the reference's
   "heretic" test model, tests/test_pgmax.py:424-475, cut to 8 x 8 hidden variables), ragged
   three-variable factors with a sparse configuration table (edge-states in one configuration only
-  / in none), and potentials beyond the clip.  Max-product: bit-identical.  Sum-product: ex2
-  instead of expf, same order of additions - at the sum-product tolerance, judged by fp64."""
+  / in none), a four-variable factor (run-time arity instantiation), potentials beyond the clip,
+  shared by the batch (staged per warp by k_enum_pair_dense) or per sample (`lp_batched`).
+  Max-product: bit-identical.  Sum-product: ex2 instead of expf, same order of additions - at the
+  sum-product tolerance, judged by fp64."""
   from pgmax_b200.infer.bp_state import BPArrays
   rng = np.random.default_rng(2)
   pixels = vgroup.NDVarArray(shape=(10, 10), num_states=3)
@@ -357,6 +359,14 @@ def test_small_enum_configuration_major_walk(temperature, batch):
       fg.add_factors(fgroup.PairwiseFactorGroup(
           variables_for_factors=[[hidden[r, c], pixels[r + dr, c + dc]] for r in range(8) for c in range(8)],
           log_potential_matrix=rng.normal(size=(17, 3))))
+  # the same complete tables with the few-state variable FIRST, and 2- / 4-state few sides (k_enum_pair_few)
+  fg.add_factors(fgroup.PairwiseFactorGroup(
+      variables_for_factors=[[pixels[r, c], hidden[(r + 4) % 8, (c + 4) % 8]] for r in range(8) for c in range(8)],
+      log_potential_matrix=rng.normal(size=(3, 17))))
+  fg.add_factors(fgroup.PairwiseFactorGroup(
+      variables_for_factors=[[hidden[r, 0], extra[0]] for r in range(8)], log_potential_matrix=rng.normal(size=(17, 2))))
+  fg.add_factors(fgroup.PairwiseFactorGroup(
+      variables_for_factors=[[extra[1], hidden[0, c]] for c in range(8)], log_potential_matrix=rng.normal(size=(4, 17))))
   # sparse three-variable table over (2, 4, 3) states: state 3 of the middle variable is in no configuration
   configs = np.array([[0, 0, 0], [0, 1, 2], [1, 2, 1], [1, 0, 2], [0, 2, 0], [1, 1, 1]])
   fg.add_factors(fgroup.EnumFactorGroup(
@@ -364,6 +374,10 @@ def test_small_enum_configuration_major_walk(temperature, batch):
       factor_configs=configs, log_potentials=rng.normal(size=(2, 6))))
   fg.add_factors(fgroup.EnumFactorGroup(variables_for_factors=[[extra[0], pixels[0, 0]]],
                                         factor_configs=np.array([[0, 0], [1, 1], [1, 2]])))
+  fg.add_factors(fgroup.EnumFactorGroup(
+      variables_for_factors=[[extra[0], extra[2], extra[3], extra[5]]],
+      factor_configs=np.array([[0, 0, 0, 0], [1, 2, 1, 2], [0, 1, 1, 0], [1, 1, 0, 2], [0, 2, 0, 1]]),
+      log_potentials=rng.normal(size=(1, 5))))
   bp = infer.BP(fg.bp_state, temperature=temperature)
   lead = () if batch is None else (batch,)
   arrays = bp.init(evidence_updates={pixels: rng.gumbel(size=lead + (10, 10, 3)),
@@ -371,6 +385,8 @@ def test_small_enum_configuration_major_walk(temperature, batch):
                                      extra: rng.gumbel(size=lead + (6, 4))})
   lp = np.array(arrays.log_potentials, dtype=np.float32)
   lp[rng.integers(0, lp.size, size=4)] = -3e6
+  if lp_batched:
+    lp = (lp[None, :] + 0.3 * rng.normal(size=(batch, lp.size))).astype(np.float32)
   arrays = BPArrays(log_potentials=lp, ftov_msgs=arrays.ftov_msgs, evidence=arrays.evidence)
   plan = bp.context.plan
   iters = 7
@@ -382,6 +398,13 @@ def test_small_enum_configuration_major_walk(temperature, batch):
   plan.disable_paths(0)
   np.testing.assert_array_equal(got.ftov_msgs, cm.ftov_msgs)
   np.testing.assert_array_equal(got_d, cm_d)
+  # ... and, with a 2 ... 4-state side, shared potentials and full sample tiles, k_enum_pair_few (that side
+  # in registers): again the same operations in the same order as the nested-loop kernel
+  plan.disable_paths(plan.PATH_ENUM_PAIR_FEW)
+  dense, dense_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
+  plan.disable_paths(0)
+  np.testing.assert_array_equal(got.ftov_msgs, dense.ftov_msgs)
+  np.testing.assert_array_equal(got_d, dense_d)
   plan.disable_paths(plan.PATH_ENUM_CONFIG_MAJOR)
   ref, ref_d = bp.run_with_diffs(arrays, num_iters=iters, damping=0.5, temperature=temperature)
   plan.disable_paths(0)
