@@ -279,9 +279,15 @@ int pgx_plan_num_fused_blocks(const pgx_plan* plan);
  * values).  bench.py uses the count for the bytes the kernels actually have to move. */
 int64_t pgx_plan_compressed_edges(const pgx_plan* plan);
 
-/* Specialised launch paths pgx_bp_run may choose from the graph's structure.  Every path
- * computes the same arithmetic in the same order (bit-identical messages); the mask only
- * exists so that tests and profiles can pin a path.  Default: nothing disabled.
+/* Specialised launch paths pgx_bp_run may choose from the graph's structure.  The mask only
+ * exists so that tests and profiles can pin a path.  Default: nothing disabled.  Max-product
+ * (temperature 0): every path performs the same operations in the same order - bit-identical
+ * messages - except the single-pass dense-grid path (tiled partial sums, see
+ * pgx_plan_set_exact_order).  Sum-product: additionally PGX_PATH_ENUM_CONFIG_MAJOR (and the two
+ * paths below it) evaluates exp as ex2 on the hardware unit, and the T > 0 side of
+ * PGX_PATH_MERGED_MAX forms logsumexp in one pass with running maxima, adding the terms in
+ * the order of its round schedule (deterministic, not the ascending configuration order); both
+ * stay within the sum-product tolerance (1e-5) of the serial fp32 evaluation (tests/).
  *   PGX_PATH_LATTICE   index-free stencil kernel for a graph that is one 2-D lattice of
  *                      pairwise binary factors (Ising grids, batch == 1)
  *   PGX_PATH_RESIDENT  all iterations of a small pairwise graph in one cluster /

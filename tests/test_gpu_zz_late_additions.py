@@ -427,8 +427,11 @@ def test_small_enum_configuration_major_walk(temperature, batch, lp_batched):
   err_got, err_ref = np.abs(got_m - exact_m)[~floor].max(), np.abs(ref_m - exact_m)[~floor].max()
   err_oracle = np.abs(want_m - exact_m)[~floor].max()
   print(f"vs fp64: configuration-major {err_got:.3g}, list walk {err_ref:.3g}, fp32 oracle {err_oracle:.3g}")
+  # on this graph (hidden variables of degree 10 - 18, 7 iterations) the serial fp32 oracle itself is
+  # 1e-5 ... 2.4e-5 from the fp64 run, so the device is held to the oracle's own distance from the truth
+  # and, directly, to the sum of the two
   assert err_got <= max(1e-5, 2.0 * err_oracle), (err_got, err_oracle)
-  np.testing.assert_allclose(got_m[~floor], want_m[~floor], atol=2e-5, rtol=2e-6)
+  np.testing.assert_allclose(got_m[~floor], want_m[~floor], atol=5e-5, rtol=2e-6)
 
 
 @pytest.mark.parametrize("temperature", [0.0, 1.0])
