@@ -26,7 +26,7 @@ cap deconv 100 k_or_and_fused 11   # odd index: the full-tile launch (the packed
 cap rcn 1 k_enum_big_maxprod_all 5
 cap ising_big 1 k_lattice_bin 3 "--iters 10 --strip-flags 1"
 cap rcn_sum 1 k_enum_big_sumprod_all 5
-cap heretic 256 k_enum_pair_dense 5 "--iters 10"
+cap heretic 256 k_enum_pair_few 5 "--iters 10"
 cap ising50_batch 1024 k_enum_pw2_bin 5 "--iters 10"
 for w in rbm deconv rcn; do
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 40 -c 120 --csv \
