@@ -71,3 +71,19 @@ def test_no_cpu_fallback(lib):
   # null handles are rejected, not dereferenced
   assert lib.pgx_bp_run(None, None, 1, None, 0, None, 0, None, 0, None, None, 1, 0.5, 0.0) == _native.PGX_ERR_INVALID
   assert b"null plan" in lib.pgx_last_error()
+
+
+def test_flag_constants_match_the_header():
+  """Every PGX_PATH_* / PGX_RUN_* / PGX_STRIP_* bit of include/pgx.h has the same value in the
+  Python mirror (pgmax_b200/_native.py: Plan.PATH_* / Plan.RUN_* / Strip flags), and no two path
+  bits collide."""
+  import re
+  from pgmax_b200 import _native
+  text = open(os.path.join(ROOT, "include", "pgx.h")).read()
+  defines = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+(PGX_(?:PATH|RUN)_[A-Z0-9_]+)\s+(\d+)u", text)}
+  paths = {k: v for k, v in defines.items() if k.startswith("PGX_PATH_")}
+  assert len(paths) >= 20 and len(set(paths.values())) == len(paths)
+  assert all(v & (v - 1) == 0 for v in paths.values())          # single bits
+  for name, value in defines.items():
+    attr = name[len("PGX_"):]
+    assert getattr(_native.Plan, attr) == value, name
